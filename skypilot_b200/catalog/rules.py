@@ -1,0 +1,188 @@
+"""Per-cloud catalog rules that are code, not data.
+
+The reference keeps these inside its per-cloud catalog modules and evaluates
+them with pandas string ops on every call; here each rule runs once per
+distinct instance type at ingest and becomes a flag bit / group id column of
+the structure-of-arrays catalog (include/skyopt.h SKYOPT_F_*).
+
+Reference locations:
+  AWS   default families, 8 vCPU / 4x memory defaults   aws_catalog.py:37-67
+  GCP   default families, n1 host VMs, fixed A100/L4/H100 hosts,
+        accelerator -> host vCPU table                  gcp_catalog.py:41-184
+  Azure family parser, default families, S-series test  azure_catalog.py:41-118,
+                                                        azure.py:708-722
+  Lambda defaults (30 vCPUs)                            lambda_catalog.py:24-25
+"""
+import re
+from typing import Callable, Dict, List, Optional, Tuple
+
+
+class CloudRules:
+    """Static description of one cloud's catalog conventions."""
+
+    def __init__(self,
+                 name: str,
+                 default_family: Optional[Callable[[str], bool]] = None,
+                 host_family: Optional[Callable[[str], bool]] = None,
+                 premium_disk: Optional[Callable[[str], bool]] = None,
+                 group_of: Optional[Callable[[str], int]] = None,
+                 default_cpus: int = 8,
+                 default_mem_ratio: int = 4,
+                 us_regions_first: bool = False,
+                 optimize_by_zone: bool = False,
+                 supports_spot: bool = True,
+                 supports_local_disk: bool = False):
+        self.name = name
+        self.default_family = default_family
+        self.host_family = host_family
+        self.premium_disk = premium_disk
+        self.group_of = group_of
+        self.default_cpus = default_cpus
+        self.default_mem_ratio = default_mem_ratio
+        self.us_regions_first = us_regions_first
+        self.optimize_by_zone = optimize_by_zone
+        self.supports_spot = supports_spot
+        self.supports_local_disk = supports_local_disk
+
+
+# ---- AWS -----------------------------------------------------------------
+AWS_DEFAULT_FAMILIES = ('m6i', 'm6id', 'm7i', 'r6i', 'r6id', 'r7i', 'c6i',
+                        'c6id', 'c7i')
+_AWS_PREFIXES = tuple(f'{fam}.' for fam in AWS_DEFAULT_FAMILIES)
+
+
+def _aws_default(instance_type: str) -> bool:
+    return instance_type.startswith(_AWS_PREFIXES)
+
+
+# ---- GCP -----------------------------------------------------------------
+GCP_DEFAULT_FAMILIES = ('n2-standard', 'n2-highmem', 'n2-highcpu',
+                        'n4-standard', 'n4-highcpu', 'n4-highmem')
+_GCP_PREFIXES = tuple(f'{fam}-' for fam in GCP_DEFAULT_FAMILIES)
+GCP_HOST_VM_FAMILIES = ('n1-standard', 'n1-highmem', 'n1-highcpu')
+
+# accelerator -> count -> the only host VM types it can be attached to
+GCP_FIXED_HOSTS: Dict[str, Dict[int, List[str]]] = {
+    'A100': {
+        1: ['a2-highgpu-1g'], 2: ['a2-highgpu-2g'], 4: ['a2-highgpu-4g'],
+        8: ['a2-highgpu-8g'], 16: ['a2-megagpu-16g']
+    },
+    'A100-80GB': {
+        1: ['a2-ultragpu-1g'], 2: ['a2-ultragpu-2g'], 4: ['a2-ultragpu-4g'],
+        8: ['a2-ultragpu-8g']
+    },
+    'L4': {
+        1: ['g2-standard-4', 'g2-standard-8', 'g2-standard-12',
+            'g2-standard-16', 'g2-standard-32'],
+        2: ['g2-standard-24'], 4: ['g2-standard-48'], 8: ['g2-standard-96']
+    },
+    'H100': {
+        1: ['a3-highgpu-1g'], 2: ['a3-highgpu-2g'], 4: ['a3-highgpu-4g'],
+        8: ['a3-highgpu-8g']
+    },
+    'H100-MEGA': {8: ['a3-megagpu-8g']},
+    'H200': {8: ['a3-ultragpu-8g']},
+    'B200': {8: ['a4-highgpu-8g']},
+}
+# group id (1-based; 0 = none) of every (accelerator, count) host set
+GCP_GROUP_IDS: Dict[Tuple[str, int], int] = {}
+GCP_INSTANCE_GROUP: Dict[str, int] = {}
+GCP_INSTANCE_TO_ACC: Dict[str, Dict[str, int]] = {}
+for _acc, _by_count in GCP_FIXED_HOSTS.items():
+    for _count, _types in _by_count.items():
+        _gid = len(GCP_GROUP_IDS) + 1
+        GCP_GROUP_IDS[(_acc, _count)] = _gid
+        for _t in _types:
+            GCP_INSTANCE_GROUP[_t] = _gid
+            GCP_INSTANCE_TO_ACC[_t] = {_acc: _count}
+assert len(GCP_GROUP_IDS) < 255
+
+# vCPUs of the default n1 host per accelerator count
+GCP_ACC_HOST_CPUS: Dict[str, Dict[int, int]] = {
+    'K80': {1: 4, 2: 8, 4: 16, 8: 32, 16: 64},
+    'V100': {1: 8, 2: 16, 4: 32, 8: 64},
+    'T4': {1: 4, 2: 8, 4: 48},
+    'P100': {1: 8, 2: 16, 4: 32, 8: 64},
+    'DEFAULT': {1: 8, 2: 16, 4: 32, 8: 64, 16: 128},
+}
+GCP_GPU_MEMORY_CPU_RATIO = 4
+
+
+def _gcp_default(instance_type: str) -> bool:
+    return instance_type.startswith(_GCP_PREFIXES)
+
+
+def _gcp_host(instance_type: str) -> bool:
+    return instance_type.startswith(GCP_HOST_VM_FAMILIES)
+
+
+def _gcp_group(instance_type: str) -> int:
+    return GCP_INSTANCE_GROUP.get(instance_type, 0)
+
+
+# ---- Azure ---------------------------------------------------------------
+AZURE_DEFAULT_FAMILIES = ('Ds_v5', 'Es_v5', 'Fs_v2')
+_AZ_DASHED = re.compile(r'([A-Za-z]+)([0-9]+)(-)([0-9]+)(.*)')
+_AZ_PLAIN = re.compile(r'([A-Za-z]+)([0-9]+)(.*)')
+_AZ_SERIES = re.compile(r'(Standard|Basic)_([A-Z]+)([0-9]+)(-[0-9]+)?'
+                        r'([a-z]*)(_[A-Z]+[0-9]+)?(_v[0-9])?(_Promo)?')
+
+
+def azure_instance_family(instance_type: str) -> str:
+    """'Standard_D8s_v5' -> 'Ds_v5'; 'Standard_E4-2ds_v4' -> 'E_ds_v4'."""
+    if instance_type.startswith('Basic_A'):
+        return 'basic_a'
+    if not instance_type.startswith('Standard_'):
+        raise ValueError(f'Unknown Azure instance type: {instance_type}')
+    body = instance_type[len('Standard_'):]
+    if '_Promo' in body:
+        body = body[:-len('_Promo')]
+    if '-' in body:
+        m = _AZ_DASHED.match(body)
+        if m is None:
+            raise ValueError(f'Unknown Azure instance type: {instance_type}')
+        return m.group(1) + '_' + m.group(5)
+    m = _AZ_PLAIN.match(body)
+    if m is None:
+        raise ValueError(f'Unknown Azure instance type: {instance_type}')
+    return m.group(1) + m.group(3)
+
+
+def _azure_default(instance_type: str) -> bool:
+    return azure_instance_family(instance_type) in AZURE_DEFAULT_FAMILIES
+
+
+def azure_is_s_series(instance_type: str) -> bool:
+    m = _AZ_SERIES.match(instance_type)
+    if m is None:
+        raise ValueError(f'Unknown instance type: {instance_type}')
+    return 's' in m.group(5)
+
+
+RULES: Dict[str, CloudRules] = {
+    'aws': CloudRules('aws',
+                      default_family=_aws_default,
+                      us_regions_first=True,
+                      supports_local_disk=True),
+    'gcp': CloudRules('gcp',
+                      default_family=_gcp_default,
+                      host_family=_gcp_host,
+                      group_of=_gcp_group,
+                      optimize_by_zone=True),
+    'azure': CloudRules('azure',
+                        default_family=_azure_default,
+                        premium_disk=azure_is_s_series),
+    'lambda': CloudRules('lambda',
+                         default_cpus=30,
+                         us_regions_first=True,
+                         supports_spot=False),
+}
+
+
+def rules_for(cloud: str) -> CloudRules:
+    """Rules of a cloud; unknown clouds get the plain common.py behaviour."""
+    rules = RULES.get(cloud)
+    if rules is None:
+        rules = CloudRules(cloud)
+        RULES[cloud] = rules
+    return rules

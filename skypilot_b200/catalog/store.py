@@ -1,0 +1,428 @@
+"""Catalog ingest: per-cloud `vms.csv` frames -> structure-of-arrays in HBM.
+
+Replaces the reference's pandas catalog (`read_catalog` / `LazyDataFrame`,
+sky/catalog/common.py:126-266): the CSV columns are dictionary-encoded once,
+per-cloud Python rules become flag bits (rules.py), and the result is uploaded
+to the GPU through `skyopt_catalog_create`. Everything the kernels scan lives
+in ten columns (32 B per row and pass):
+
+  price, spot_price, vcpus, mem : f64   (NaN = missing, as in pandas)
+  acc_key    : u16  id of the (AcceleratorName, AcceleratorCount) pair
+  region_id  : u16  rank of Region among the cloud's region names
+  zone_id    : u16  rank of AvailabilityZone (0xFFFF = missing)
+  flags      : u16  SKYOPT_F_* bits | instance group << 8
+  (+ inst_id i32 and disk_total f64, gathered only for matching rows)
+
+Ranks are taken in Python string order, which is the order pandas sorts the
+object columns in (`sort_values(['Price', 'Region', 'AvailabilityZone'])`,
+common.py:797-802), so comparing ids on the device equals comparing names.
+Row order inside a cloud is the CSV order; "cheapest" ties resolve to the
+lowest row id (the reference's single-key sort is unstable).
+"""
+import ctypes
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+from skypilot_b200 import _native
+from skypilot_b200.catalog import rules as rules_lib
+
+_ROW_ALIGN = 8
+CATALOG_SCHEMA_VERSION = 'v8'
+
+
+def _col(df: pd.DataFrame, name: str, n: int) -> np.ndarray:
+    if name in df.columns:
+        return pd.to_numeric(df[name], errors='coerce').to_numpy(
+            dtype=np.float64, na_value=np.nan)
+    return np.full(n, np.nan)
+
+
+class CloudTable:
+    """Host-side dictionaries and metadata of one cloud."""
+
+    def __init__(self, name: str, index: int):
+        self.name = name
+        self.index = index
+        self.rules = rules_lib.rules_for(name)
+        self.row_begin = 0
+        self.row_end = 0  # exclusive, without padding
+        self.n_rows = 0
+        self.region_names: List[str] = []
+        self.region_lower: Dict[str, int] = {}
+        self.region_exact: Dict[str, int] = {}
+        self.zone_names: List[str] = []
+        self.zone_lower: Dict[str, int] = {}
+        self.zone_exact: Dict[str, int] = {}
+        self.zone_region: List[int] = []
+        self.has_zone_column = False
+        self.inst_begin = 0
+        self.inst_names: List[str] = []
+        self.inst_index: Dict[str, int] = {}  # name -> GLOBAL id
+        self.frame: Optional[pd.DataFrame] = None  # original rows (metadata)
+        self.inst_first_row: Optional[np.ndarray] = None  # local row ids
+
+
+class CatalogStore:
+    """All enabled clouds' catalogs as one SoA table (+ the device handle)."""
+
+    def __init__(self):
+        self.clouds: List[CloudTable] = []
+        self.cloud_index: Dict[str, int] = {}
+        self.acc_keys: List[Tuple[str, float]] = []
+        self.acc_key_index: Dict[Tuple[str, float], int] = {}
+        self.acc_names_lower: List[str] = []
+        self.inst_names: List[str] = []
+        self.inst_cloud: List[int] = []
+        self.columns: Dict[str, np.ndarray] = {}
+        self.n_rows = 0  # padded
+        self.n_real_rows = 0
+        self.max_group_rows = 1
+        self._handle = ctypes.c_void_p(None)
+        self._device: Optional[int] = None
+        self._lock = threading.Lock()
+        self._keepalive: List[np.ndarray] = []
+
+    # ------------------------------------------------------------------ build
+    @classmethod
+    def from_frames(cls,
+                    frames: Dict[str, pd.DataFrame],
+                    order: Optional[Sequence[str]] = None) -> 'CatalogStore':
+        store = cls()
+        names = list(order) if order is not None else list(frames.keys())
+        if len(names) > _native.MAX_CLOUDS:
+            raise ValueError(f'at most {_native.MAX_CLOUDS} clouds')
+        price, spot, vcpus, mem, disk = [], [], [], [], []
+        acc_key, region_id, zone_id, flags, inst_id = [], [], [], [], []
+        cloud_row_offsets = [0]
+        cloud_inst_offsets = [0]
+        cloud_region_offsets = [0]
+        cloud_n_zones = []
+        region_is_us: List[int] = []
+        any_disk = False
+        for ci, name in enumerate(names):
+            df = frames[name].reset_index(drop=True)
+            table = CloudTable(name, ci)
+            table.frame = df
+            n = len(df)
+            table.n_rows = n
+            table.row_begin = cloud_row_offsets[-1]
+            table.row_end = table.row_begin + n
+            rules = table.rules
+            # --- instance types: first-appearance order
+            it = df['InstanceType'] if 'InstanceType' in df.columns else (
+                pd.Series([None] * n, dtype=object))
+            codes, uniques = pd.factorize(it, use_na_sentinel=True)
+            table.inst_names = [str(u) for u in uniques]
+            table.inst_begin = cloud_inst_offsets[-1]
+            table.inst_index = {
+                nm: table.inst_begin + i
+                for i, nm in enumerate(table.inst_names)
+            }
+            gl_inst = np.where(codes >= 0, codes + table.inst_begin,
+                               -1).astype(np.int32)
+            first_row = np.full(len(uniques), -1, dtype=np.int64)
+            if n:
+                order_idx = np.arange(n)
+                valid = codes >= 0
+                # first occurrence per code
+                rev = order_idx[valid][::-1]
+                first_row[codes[valid][::-1]] = rev
+            table.inst_first_row = first_row
+            store.inst_names.extend(table.inst_names)
+            store.inst_cloud.extend([ci] * len(table.inst_names))
+            cloud_inst_offsets.append(table.inst_begin + len(uniques))
+            # --- regions / zones: ranks in string order
+            reg = df['Region'].astype(object)
+            table.region_names = sorted(str(r) for r in reg.dropna().unique())
+            rmap = {nm: i for i, nm in enumerate(table.region_names)}
+            table.region_exact = dict(rmap)
+            for nm, i in rmap.items():
+                low = nm.lower()
+                if low in table.region_lower:
+                    raise ValueError(
+                        f'{name}: regions {nm!r} and '
+                        f'{table.region_names[table.region_lower[low]]!r} '
+                        'differ only in case')
+                table.region_lower[low] = i
+            if len(table.region_names) >= _native.NONE16:
+                raise ValueError(f'{name}: too many regions')
+            if reg.isna().any():
+                raise ValueError(f'{name}: rows without a Region')
+            rid = reg.map(rmap).to_numpy(dtype=np.int64).astype(np.uint16)
+            table.has_zone_column = 'AvailabilityZone' in df.columns
+            zid = np.full(n, _native.NONE16, dtype=np.uint16)
+            if table.has_zone_column:
+                zone = df['AvailabilityZone'].astype(object)
+                table.zone_names = sorted(
+                    str(z) for z in zone.dropna().unique())
+                if len(table.zone_names) >= _native.NONE16:
+                    raise ValueError(f'{name}: too many zones')
+                zmap = {nm: i for i, nm in enumerate(table.zone_names)}
+                table.zone_exact = dict(zmap)
+                table.zone_lower = {nm.lower(): i for nm, i in zmap.items()}
+                has = zone.notna().to_numpy()
+                zid[has] = zone[has].map(zmap).to_numpy(dtype=np.int64)
+                zr = np.full(len(table.zone_names), -1, dtype=np.int64)
+                zr[zid[has]] = rid[has]
+                table.zone_region = [int(v) for v in zr]
+            cloud_region_offsets.append(cloud_region_offsets[-1] +
+                                        len(table.region_names))
+            cloud_n_zones.append(
+                max(len(table.zone_names), 1) if table.has_zone_column else 0)
+            region_is_us.extend(
+                1 if r.startswith('us-') else 0 for r in table.region_names)
+            # --- accelerators: (name, count) dictionary over all clouds
+            ak = np.full(n, _native.NONE16, dtype=np.uint16)
+            if 'AcceleratorName' in df.columns:
+                an = df['AcceleratorName'].astype(object)
+                ac = _col(df, 'AcceleratorCount', n)
+                has = an.notna().to_numpy() & ~np.isnan(ac)
+                if has.any():
+                    pairs = pd.MultiIndex.from_arrays(
+                        [an[has].astype(str).to_numpy(), ac[has]])
+                    pcodes, puniq = pd.factorize(pairs)
+                    ids = np.empty(len(puniq), dtype=np.int64)
+                    for j, (nm, cnt) in enumerate(puniq):
+                        key = (str(nm), float(cnt))
+                        if key not in store.acc_key_index:
+                            store.acc_key_index[key] = len(store.acc_keys)
+                            store.acc_keys.append(key)
+                        ids[j] = store.acc_key_index[key]
+                    ak[has] = ids[pcodes]
+            # --- flags from the per-cloud rules (once per instance type)
+            per_inst = np.zeros(len(uniques), dtype=np.uint16)
+            for j, nm in enumerate(table.inst_names):
+                f = _native.F_HAS_INSTANCE
+                if rules.default_family is None or rules.default_family(nm):
+                    f |= _native.F_DEFAULT_FAMILY
+                if rules.host_family is not None and rules.host_family(nm):
+                    f |= _native.F_HOST_FAMILY
+                if rules.premium_disk is not None:
+                    try:
+                        if rules.premium_disk(nm):
+                            f |= _native.F_PREMIUM_DISK
+                    except ValueError:
+                        pass
+                if rules.group_of is not None:
+                    f |= (rules.group_of(nm) & 0xFF) << 8
+                per_inst[j] = f
+            fl = np.full(n, _native.F_VALID, dtype=np.uint16)
+            has_inst = codes >= 0
+            fl[has_inst] |= per_inst[codes[has_inst]]
+            if rules.default_family is None:
+                # clouds without a default-family rule search the whole frame
+                fl |= _native.F_DEFAULT_FAMILY
+            dt = np.zeros(n, dtype=np.float64)
+            if 'LocalDiskType' in df.columns:
+                any_disk = True
+                ssd = (df['LocalDiskType'] == 'ssd').to_numpy(dtype=bool)
+                fl[ssd] |= _native.F_SSD
+                if 'NVMeSupported' in df.columns:
+                    nv = df['NVMeSupported']
+                    nvme = (nv == True).to_numpy(dtype=bool)  # pylint: disable=singleton-comparison
+                    fl[nvme] |= _native.F_NVME
+                size = np.nan_to_num(_col(df, 'LocalDiskSize', n), nan=0.0)
+                cnt = np.nan_to_num(_col(df, 'LocalDiskCount', n), nan=0.0)
+                dt = size * cnt
+            # --- pad to the row alignment
+            pad = (-n) % _ROW_ALIGN
+
+            def padded(arr, fill):
+                if pad == 0:
+                    return arr
+                return np.concatenate(
+                    [arr, np.full(pad, fill, dtype=arr.dtype)])
+
+            price.append(padded(_col(df, 'Price', n), np.nan))
+            spot.append(padded(_col(df, 'SpotPrice', n), np.nan))
+            vcpus.append(padded(_col(df, 'vCPUs', n), np.nan))
+            mem.append(padded(_col(df, 'MemoryGiB', n), np.nan))
+            disk.append(padded(dt, 0.0))
+            acc_key.append(padded(ak, _native.NONE16))
+            region_id.append(padded(rid, 0))
+            zone_id.append(padded(zid, _native.NONE16))
+            flags.append(padded(fl, 0))
+            inst_id.append(padded(gl_inst, -1))
+            cloud_row_offsets.append(cloud_row_offsets[-1] + n + pad)
+            store.clouds.append(table)
+            store.cloud_index[name] = ci
+            store.n_real_rows += n
+        if len(store.acc_keys) > 32 * _native.ACC_SET_WORDS:
+            raise ValueError('too many distinct (accelerator, count) pairs')
+        cols = store.columns
+        cols['price'] = np.ascontiguousarray(np.concatenate(price))
+        cols['spot_price'] = np.ascontiguousarray(np.concatenate(spot))
+        cols['vcpus'] = np.ascontiguousarray(np.concatenate(vcpus))
+        cols['mem'] = np.ascontiguousarray(np.concatenate(mem))
+        cols['disk_total'] = (np.ascontiguousarray(np.concatenate(disk))
+                              if any_disk else None)
+        cols['acc_key'] = np.ascontiguousarray(np.concatenate(acc_key))
+        cols['region_id'] = np.ascontiguousarray(np.concatenate(region_id))
+        cols['zone_id'] = np.ascontiguousarray(np.concatenate(zone_id))
+        cols['flags'] = np.ascontiguousarray(np.concatenate(flags))
+        cols['inst_id'] = np.ascontiguousarray(np.concatenate(inst_id))
+        store.n_rows = int(cloud_row_offsets[-1])
+        cols['cloud_row_offsets'] = np.asarray(cloud_row_offsets, np.int32)
+        cols['cloud_inst_offsets'] = np.asarray(cloud_inst_offsets, np.int32)
+        cols['cloud_region_offsets'] = np.asarray(cloud_region_offsets,
+                                                  np.int32)
+        cols['cloud_n_zones'] = np.asarray(cloud_n_zones, np.int32)
+        cols['region_is_us'] = np.asarray(region_is_us or [0], np.uint8)
+        # --- CSR: rows grouped by instance type (ascending row order inside)
+        iid = cols['inst_id']
+        n_inst = len(store.inst_names)
+        rows = np.flatnonzero(iid >= 0).astype(np.int32)
+        order_idx = np.argsort(iid[rows], kind='stable')
+        cols['inst_rows'] = np.ascontiguousarray(rows[order_idx])
+        counts = np.bincount(iid[rows], minlength=n_inst)
+        cols['inst_row_offsets'] = np.concatenate(
+            [[0], np.cumsum(counts)]).astype(np.int32)
+        # accelerator-only rows (GCP GPU / TPU rows) grouped by key
+        n_keys = len(store.acc_keys)
+        akc = cols['acc_key']
+        arow = np.flatnonzero((iid < 0) & (akc != _native.NONE16) &
+                              ((cols['flags'] & _native.F_VALID) != 0)).astype(
+                                  np.int32)
+        aorder = np.argsort(akc[arow], kind='stable')
+        cols['acc_rows'] = np.ascontiguousarray(arow[aorder])
+        acounts = np.bincount(akc[arow].astype(np.int64), minlength=n_keys)
+        cols['acc_row_offsets'] = np.concatenate(
+            [[0], np.cumsum(acounts)]).astype(np.int32)
+        iak = np.full(max(n_inst, 1), _native.NONE16, dtype=np.uint16)
+        if n_inst:
+            firsts = cols['inst_rows'][cols['inst_row_offsets'][:-1].clip(
+                max=max(len(cols['inst_rows']) - 1, 0))]
+            nonempty = counts > 0
+            iak[:n_inst][nonempty] = akc[firsts[nonempty]]
+        cols['inst_acc_key'] = iak
+        store.max_group_rows = int(
+            max([1] + list(counts) + list(acounts)))
+        store.acc_names_lower = [k[0].lower() for k in store.acc_keys]
+        return store
+
+    @classmethod
+    def from_directory(cls,
+                       path: str,
+                       clouds: Optional[Sequence[str]] = None
+                      ) -> 'CatalogStore':
+        """Loads `<path>/<cloud>/vms.csv` (the reference's on-disk layout,
+        sky/catalog/common.py:33-35, :65-68)."""
+        frames = {}
+        names = clouds
+        if names is None:
+            names = sorted(
+                d for d in os.listdir(path)
+                if os.path.exists(os.path.join(path, d, 'vms.csv')))
+        for name in names:
+            csv = os.path.join(path, name, 'vms.csv')
+            if not os.path.exists(csv):
+                continue
+            frames[name] = pd.read_csv(csv)
+        if not frames:
+            raise FileNotFoundError(f'no <cloud>/vms.csv below {path}')
+        return cls.from_frames(frames, order=list(frames.keys()))
+
+    # --------------------------------------------------------------- look-ups
+    def cloud(self, name: str) -> CloudTable:
+        return self.clouds[self.cloud_index[name.lower()]]
+
+    def has_cloud(self, name: str) -> bool:
+        return name.lower() in self.cloud_index
+
+    def instance_id(self, cloud: str, instance_type: str) -> int:
+        return self.cloud(cloud).inst_index.get(instance_type, -1)
+
+    def instance_row(self, cloud: str, instance_type: str) -> pd.Series:
+        """First CSV row of an instance type (metadata look-ups)."""
+        table = self.cloud(cloud)
+        gid = table.inst_index.get(instance_type)
+        if gid is None:
+            raise KeyError(instance_type)
+        return table.frame.iloc[int(
+            table.inst_first_row[gid - table.inst_begin])]
+
+    def accelerator_set(self, predicate) -> np.ndarray:
+        """Bitmask (ACC_SET_WORDS u32) of the keys `predicate(name, count)`."""
+        words = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
+        for k, (name, count) in enumerate(self.acc_keys):
+            if predicate(name, count):
+                words[k >> 5] |= np.uint32(1 << (k & 31))
+        return words
+
+    def row_bytes(self) -> int:
+        """Bytes the scan streams per row and pass."""
+        return 3 * 8 + 4 * 2
+
+    # ----------------------------------------------------------------- device
+    def handle(self, device: int = 0) -> ctypes.c_void_p:
+        """Uploads the table on first use (skyopt_catalog_create)."""
+        if self._handle.value is not None:
+            if self._device != device:
+                raise RuntimeError(
+                    f'catalog already resident on device {self._device}')
+            return self._handle
+        with self._lock:
+            if self._handle.value is not None:
+                return self._handle
+            lib = _native.load()
+            c = self.columns
+            desc = _native.CatalogDesc()
+            desc.n_rows = self.n_rows
+            keep = []
+
+            def p(name, dtype):
+                arr = c[name]
+                if arr is None:
+                    return None
+                arr = np.ascontiguousarray(arr, dtype=dtype)
+                keep.append(arr)
+                return arr.ctypes.data
+
+            desc.price = p('price', np.float64)
+            desc.spot_price = p('spot_price', np.float64)
+            desc.vcpus = p('vcpus', np.float64)
+            desc.mem = p('mem', np.float64)
+            desc.disk_total = p('disk_total', np.float64)
+            desc.acc_key = p('acc_key', np.uint16)
+            desc.region_id = p('region_id', np.uint16)
+            desc.zone_id = p('zone_id', np.uint16)
+            desc.flags = p('flags', np.uint16)
+            desc.inst_id = p('inst_id', np.int32)
+            desc.n_clouds = len(self.clouds)
+            desc.n_inst = len(self.inst_names)
+            desc.n_acc_keys = len(self.acc_keys)
+            desc.n_regions = int(c['cloud_region_offsets'][-1])
+            desc.cloud_row_offsets = p('cloud_row_offsets', np.int32)
+            desc.cloud_inst_offsets = p('cloud_inst_offsets', np.int32)
+            desc.cloud_region_offsets = p('cloud_region_offsets', np.int32)
+            desc.cloud_n_zones = p('cloud_n_zones', np.int32)
+            desc.region_is_us = p('region_is_us', np.uint8)
+            desc.inst_row_offsets = p('inst_row_offsets', np.int32)
+            desc.inst_rows = p('inst_rows', np.int32)
+            desc.acc_row_offsets = p('acc_row_offsets', np.int32)
+            desc.acc_rows = p('acc_rows', np.int32)
+            desc.inst_acc_key = p('inst_acc_key', np.uint16)
+            handle = ctypes.c_void_p(None)
+            _native.check(
+                lib.skyopt_catalog_create(ctypes.byref(desc), device,
+                                          ctypes.byref(handle)))
+            del keep
+            self._handle = handle
+            self._device = device
+        return self._handle
+
+    def close(self) -> None:
+        if self._handle.value is not None:
+            _native.load().skyopt_catalog_destroy(self._handle)
+            self._handle = ctypes.c_void_p(None)
+            self._device = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass

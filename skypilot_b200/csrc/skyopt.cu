@@ -1,0 +1,833 @@
+// skyopt.cu -- host side of libskyopt: catalog upload, workspace management
+// and the C-ABI entry points declared in include/skyopt.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo
+//        -fmad=false -shared -Xcompiler -fPIC  (see __graft_entry__.build()).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "skyopt.h"
+#include "skyopt_kernels.cuh"
+
+using namespace skyopt;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CU(expr)                                                            \
+  do {                                                                      \
+    cudaError_t e_ = (expr);                                                \
+    if (e_ != cudaSuccess)                                                  \
+      return fail(SKYOPT_ECUDA, "%s failed: %s (%s:%d)", #expr,             \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);              \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// Private stream + buffers of one in-flight call.
+struct Ctx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  char *dbuf = nullptr; size_t dcap = 0;   // device workspace
+  char *hbuf = nullptr; size_t hcap = 0;   // pinned staging
+  uint32_t *flush = nullptr; size_t flush_words = 0;
+};
+
+// Bump allocator over one buffer; first pass (base == nullptr) only sizes.
+struct Carver {
+  char *base; size_t off = 0;
+  explicit Carver(char *b) : base(b) {}
+  template <typename T> T *take(size_t n) {
+    off = align_up(off);
+    T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+struct SkyoptCatalog {
+  int device = 0;
+  CatDev dev{};
+  std::vector<void *> allocs;
+  int64_t device_bytes = 0;
+  std::vector<int32_t> cloud_row_offsets, cloud_inst_offsets, cloud_n_zones,
+      cloud_region_offsets;
+  std::vector<int32_t> cloud_group_cap;  // max rows of one expand group
+  int sort_n = 2, max_regions = 1, max_zones = 1;
+  int sm_count = 148;
+  std::mutex mu;
+  std::vector<Ctx *> free_ctx;
+};
+
+namespace {
+
+template <typename T>
+int upload(SkyoptCatalog *c, const T *src, size_t n, size_t slack, const T **dst,
+           int fill = 0) {
+  T *p = nullptr;
+  const size_t bytes = (n + slack) * sizeof(T);
+  CU(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+  c->allocs.push_back(p);
+  c->device_bytes += bytes;
+  CU(cudaMemset(p, fill, std::max<size_t>(bytes, 256)));
+  if (n && src) CU(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = p;
+  return 0;
+}
+
+int acquire(SkyoptCatalog *c, Ctx **out) {
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (!c->free_ctx.empty()) {
+      *out = c->free_ctx.back();
+      c->free_ctx.pop_back();
+      return 0;
+    }
+  }
+  Ctx *x = new (std::nothrow) Ctx();
+  if (!x) return fail(SKYOPT_ENOMEM, "out of host memory");
+  CU(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+  for (auto &e : x->ev) CU(cudaEventCreate(&e));
+  *out = x;
+  return 0;
+}
+
+void release(SkyoptCatalog *c, Ctx *x) {
+  std::lock_guard<std::mutex> g(c->mu);
+  c->free_ctx.push_back(x);
+}
+
+int ensure(Ctx *x, size_t dbytes, size_t hbytes) {
+  if (dbytes > x->dcap) {
+    if (x->dbuf) CU(cudaFree(x->dbuf));
+    x->dbuf = nullptr; x->dcap = 0;
+    const size_t cap = align_up(dbytes + dbytes / 4, 1 << 20);
+    CU(cudaMalloc(&x->dbuf, cap));
+    x->dcap = cap;
+  }
+  if (hbytes > x->hcap) {
+    if (x->hbuf) CU(cudaFreeHost(x->hbuf));
+    x->hbuf = nullptr; x->hcap = 0;
+    const size_t cap = align_up(hbytes + hbytes / 4, 1 << 16);
+    CU(cudaMallocHost(&x->hbuf, cap));
+    x->hcap = cap;
+  }
+  return 0;
+}
+
+// Everything one call needs, laid out twice (host staging / device).
+struct Plan {
+  // sizes
+  int nq = 0, nsets = 0, ns = 0, nt = 0, np = 0, ntar = 0, nb = 0, nd = 0;
+  int n_groups = 0, n_blocks = 0, rpt = 4;
+  int64_t n_partials = 0, list_entries = 0, fuzzy_entries = 0;
+  int64_t cand_cap = 0;   // expand candidate buffers
+  int64_t scan_rows = 0, pass_rows = 0;
+  // input region (mirrored host/device)
+  size_t in_bytes = 0;
+  SkyoptQuery *queries; uint32_t *acc_sets; SkyoptSlot *slots; SkyoptTask *tasks;
+  int32_t *parents; double *tariffs; SkyoptBlocked *blocked; SkyoptDag *dags;
+  int32_t *q_order; ScanGroup *groups; int32_t *partial_base, *partial_count;
+  int64_t *list_base, *fuzzy_base, *slot_off, *task_off;
+  // device-only scratch
+  ScanPartial *partials; unsigned long long *list_min, *fuzzy_min;
+  int32_t *cand_region, *cand_zone; double *cand_pa, *cand_pb;
+  int32_t *tc_ref, *tc_slot, *tc_cloud; double *tc_hourly, *tc_value, *dp;
+  int32_t *back; int32_t *err_flag;
+  // output region (device, copied back in one piece)
+  size_t out_off = 0, out_bytes = 0;
+  ScanFinal *finals; uint32_t *any1; int32_t *slot_count, *slot_inst;
+  SkyoptCandidate *chosen; int32_t *chosen_index, *task_n; SkyoptDagResult *dagres;
+  int32_t *err_out;
+  size_t total_bytes = 0;
+};
+
+void carve_inputs(Plan &P, Carver &c) {
+  P.queries = c.take<SkyoptQuery>(P.nq);
+  P.acc_sets = c.take<uint32_t>((size_t)P.nsets * SKYOPT_ACC_SET_WORDS);
+  P.slots = c.take<SkyoptSlot>(P.ns);
+  P.tasks = c.take<SkyoptTask>(P.nt);
+  P.parents = c.take<int32_t>(P.np);
+  P.tariffs = c.take<double>(P.ntar);
+  P.blocked = c.take<SkyoptBlocked>(P.nb);
+  P.dags = c.take<SkyoptDag>(P.nd);
+  P.q_order = c.take<int32_t>(P.nq);
+  P.groups = c.take<ScanGroup>(P.n_groups);
+  P.partial_base = c.take<int32_t>(P.nq);
+  P.partial_count = c.take<int32_t>(P.nq);
+  P.list_base = c.take<int64_t>(P.nq);
+  P.fuzzy_base = c.take<int64_t>(P.nq);
+  P.slot_off = c.take<int64_t>(P.ns);
+  P.task_off = c.take<int64_t>(P.nt + 1);
+}
+
+void carve_rest(Plan &P, Carver &c) {
+  P.partials = c.take<ScanPartial>(P.n_partials);
+  P.list_min = c.take<unsigned long long>(P.list_entries);
+  P.fuzzy_min = c.take<unsigned long long>(P.fuzzy_entries);
+  P.cand_region = c.take<int32_t>(P.cand_cap);
+  P.cand_zone = c.take<int32_t>(P.cand_cap);
+  P.cand_pa = c.take<double>(P.cand_cap);
+  P.cand_pb = c.take<double>(P.cand_cap);
+  P.tc_ref = c.take<int32_t>(P.cand_cap);
+  P.tc_slot = c.take<int32_t>(P.cand_cap);
+  P.tc_cloud = c.take<int32_t>(P.cand_cap);
+  P.tc_hourly = c.take<double>(P.cand_cap);
+  P.tc_value = c.take<double>(P.cand_cap);
+  P.dp = c.take<double>(P.cand_cap);
+  P.back = c.take<int32_t>(P.cand_cap);
+  P.err_flag = c.take<int32_t>(1);
+  c.off = align_up(c.off);
+  P.out_off = c.off;
+  P.finals = c.take<ScanFinal>(P.nq);
+  P.any1 = c.take<uint32_t>(P.nq);
+  P.slot_count = c.take<int32_t>(P.ns);
+  P.slot_inst = c.take<int32_t>(P.ns);
+  P.chosen = c.take<SkyoptCandidate>(P.nt);
+  P.chosen_index = c.take<int32_t>(P.nt);
+  P.task_n = c.take<int32_t>(P.nt);
+  P.dagres = c.take<SkyoptDagResult>(P.nd);
+  P.err_out = c.take<int32_t>(1);
+  c.off = align_up(c.off);
+  P.out_bytes = c.off - P.out_off;
+}
+
+int validate_problem(const SkyoptCatalog *cat, const SkyoptProblem *pb) {
+  const int C = cat->dev.n_clouds;
+  for (int i = 0; i < pb->n_queries; ++i) {
+    const SkyoptQuery &q = pb->queries[i];
+    if (q.cloud < 0 || q.cloud >= C) return fail(SKYOPT_EINVAL, "query %d: bad cloud %d", i, q.cloud);
+    if (q.acc_set >= pb->n_acc_sets || q.fuzzy_set >= pb->n_acc_sets)
+      return fail(SKYOPT_EINVAL, "query %d: accelerator set out of range", i);
+    if ((q.qflags & SKYOPT_Q_ACC) && q.acc_set < 0)
+      return fail(SKYOPT_EINVAL, "query %d: accelerator query without a set", i);
+    if (q.price_col != 0 && q.price_col != 1) return fail(SKYOPT_EINVAL, "query %d: bad price_col", i);
+  }
+  for (int i = 0; i < pb->n_slots; ++i) {
+    const SkyoptSlot &s = pb->slots[i];
+    if (s.cloud < 0 || s.cloud >= C) return fail(SKYOPT_EINVAL, "slot %d: bad cloud", i);
+    if (s.query >= pb->n_queries || s.gate_query >= pb->n_queries)
+      return fail(SKYOPT_EINVAL, "slot %d: query out of range", i);
+    if (s.query < 0 && s.inst_id < -2) return fail(SKYOPT_EINVAL, "slot %d: no instance type", i);
+    if (s.inst_id >= cat->dev.n_inst) return fail(SKYOPT_EINVAL, "slot %d: instance id out of range", i);
+    if (s.acc_set >= pb->n_acc_sets) return fail(SKYOPT_EINVAL, "slot %d: accelerator set out of range", i);
+    if (s.query < 0 && s.inst_id == -1) return fail(SKYOPT_EINVAL, "slot %d: neither query nor instance", i);
+  }
+  for (int i = 0; i < pb->n_tasks; ++i) {
+    const SkyoptTask &t = pb->tasks[i];
+    if (t.slot_begin < 0 || t.slot_end < t.slot_begin || t.slot_end > pb->n_slots)
+      return fail(SKYOPT_EINVAL, "task %d: bad slot range", i);
+    if (t.n_parents < 0 || t.parent_begin < 0 || t.parent_begin + t.n_parents > pb->n_parents)
+      return fail(SKYOPT_EINVAL, "task %d: bad parent range", i);
+    if (t.n_parents > 0 && (t.edge_tariff_begin < 0 ||
+                            t.edge_tariff_begin + t.n_parents * C > pb->n_tariffs))
+      return fail(SKYOPT_EINVAL, "task %d: bad tariff range", i);
+    if (t.src_tariff_begin >= 0 && t.src_tariff_begin + C > pb->n_tariffs)
+      return fail(SKYOPT_EINVAL, "task %d: bad source tariff range", i);
+  }
+  for (int i = 0; i < pb->n_dags; ++i) {
+    const SkyoptDag &d = pb->dags[i];
+    if (d.task_begin < 0 || d.task_end <= d.task_begin || d.task_end > pb->n_tasks)
+      return fail(SKYOPT_EINVAL, "dag %d: bad task range", i);
+    if (d.blocked_begin < 0 || d.blocked_end < d.blocked_begin || d.blocked_end > pb->n_blocked)
+      return fail(SKYOPT_EINVAL, "dag %d: bad blocked range", i);
+    for (int t = d.task_begin; t < d.task_end; ++t) {
+      const SkyoptTask &tk = pb->tasks[t];
+      for (int k = 0; k < tk.n_parents; ++k) {
+        const int lp = pb->parents[tk.parent_begin + k];
+        if (lp < 0 || lp >= t - d.task_begin)
+          return fail(SKYOPT_EINVAL, "dag %d: task order is not topological", i);
+      }
+      if (d.is_chain && tk.n_parents != (t == d.task_begin ? 0 : 1))
+        return fail(SKYOPT_EINVAL, "dag %d: not a chain", i);
+      if (d.is_chain && tk.n_parents == 1 && pb->parents[tk.parent_begin] != t - d.task_begin - 1)
+        return fail(SKYOPT_EINVAL, "dag %d: chain parent must be the previous task", i);
+    }
+  }
+  return 0;
+}
+
+// Sizes, scan grouping and offsets; fills the host staging copy.
+int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
+  const int C = cat->dev.n_clouds;
+  P.nq = pb->n_queries; P.nsets = pb->n_acc_sets; P.ns = pb->n_slots;
+  P.nt = pb->n_tasks; P.np = pb->n_parents; P.ntar = pb->n_tariffs;
+  P.nb = pb->n_blocked; P.nd = pb->n_dags;
+
+  std::vector<std::vector<int>> by_cloud(C);
+  for (int i = 0; i < P.nq; ++i) by_cloud[pb->queries[i].cloud].push_back(i);
+  auto count_blocks = [&](int rpt) {
+    long long blocks = 0;
+    const int tile = kScanThreads * rpt;
+    for (int c = 0; c < C; ++c) {
+      if (by_cloud[c].empty()) continue;
+      const int rows = cat->cloud_row_offsets[c + 1] - cat->cloud_row_offsets[c];
+      const long long tiles = (rows + tile - 1) / tile;
+      const long long chunks = ((long long)by_cloud[c].size() + kQChunk - 1) / kQChunk;
+      blocks += tiles * chunks;
+    }
+    return blocks;
+  };
+  // Large grids use 4 rows/thread (128-bit loads); small catalogs spread
+  // over more, smaller tiles so that all 148 SMs have work.
+  P.rpt = 4;
+  if (count_blocks(4) < 2ll * cat->sm_count) P.rpt = 2;
+  if (P.rpt == 2 && count_blocks(2) < 2ll * cat->sm_count) P.rpt = 1;
+  const int tile = kScanThreads * P.rpt;
+  P.n_groups = 0;
+  for (int c = 0; c < C; ++c)
+    P.n_groups += (int)((by_cloud[c].size() + kQChunk - 1) / kQChunk);
+
+  // candidate capacity: every slot can at most expand to its cloud's largest
+  // instance-type / accelerator group
+  std::vector<int64_t> slot_off(P.ns);
+  int64_t cap = 0;
+  for (int s = 0; s < P.ns; ++s) { slot_off[s] = cap; cap += cat->cloud_group_cap[pb->slots[s].cloud]; }
+  P.cand_cap = cap;
+
+  // partial / table offsets
+  std::vector<int32_t> pbase(P.nq), pcount(P.nq);
+  std::vector<int64_t> lbase(P.nq, 0), fbase(P.nq, 0);
+  int64_t npart = 0, nlist = 0, nfuzzy = 0;
+  P.scan_rows = 0;
+  for (int i = 0; i < P.nq; ++i) {
+    const SkyoptQuery &q = pb->queries[i];
+    const int rows = cat->cloud_row_offsets[q.cloud + 1] - cat->cloud_row_offsets[q.cloud];
+    pcount[i] = (rows + tile - 1) / tile;
+    if (npart + pcount[i] > 0x7FFFFFFFll) return fail(SKYOPT_ELIMIT, "too many scan partials");
+    pbase[i] = (int32_t)npart; npart += pcount[i];
+    P.scan_rows += rows;
+    if (q.qflags & SKYOPT_Q_LIST) { lbase[i] = nlist; nlist += cat->cloud_inst_offsets[q.cloud + 1] - cat->cloud_inst_offsets[q.cloud]; }
+    if (q.qflags & SKYOPT_Q_FUZZY) { fbase[i] = nfuzzy; nfuzzy += cat->dev.n_acc_keys; }
+  }
+  P.n_partials = npart; P.list_entries = nlist; P.fuzzy_entries = nfuzzy;
+
+  Carver sizing(nullptr);
+  carve_inputs(P, sizing);
+  P.in_bytes = align_up(sizing.off);
+  carve_rest(P, sizing);
+  P.total_bytes = align_up(sizing.off);
+  int rc = ensure(x, P.total_bytes, std::max(P.in_bytes, P.out_bytes));
+  if (rc) return rc;
+
+  // host staging copy of the input region
+  Carver h(x->hbuf);
+  carve_inputs(P, h);
+  memcpy(P.queries, pb->queries, sizeof(SkyoptQuery) * P.nq);
+  if (P.nsets) memcpy(P.acc_sets, pb->acc_sets, sizeof(uint32_t) * SKYOPT_ACC_SET_WORDS * P.nsets);
+  if (P.ns) memcpy(P.slots, pb->slots, sizeof(SkyoptSlot) * P.ns);
+  if (P.nt) memcpy(P.tasks, pb->tasks, sizeof(SkyoptTask) * P.nt);
+  if (P.np) memcpy(P.parents, pb->parents, sizeof(int32_t) * P.np);
+  if (P.ntar) memcpy(P.tariffs, pb->tariffs, sizeof(double) * P.ntar);
+  if (P.nb) memcpy(P.blocked, pb->blocked, sizeof(SkyoptBlocked) * P.nb);
+  if (P.nd) memcpy(P.dags, pb->dags, sizeof(SkyoptDag) * P.nd);
+  memcpy(P.partial_base, pbase.data(), sizeof(int32_t) * P.nq);
+  memcpy(P.partial_count, pcount.data(), sizeof(int32_t) * P.nq);
+  memcpy(P.list_base, lbase.data(), sizeof(int64_t) * P.nq);
+  memcpy(P.fuzzy_base, fbase.data(), sizeof(int64_t) * P.nq);
+  if (P.ns) memcpy(P.slot_off, slot_off.data(), sizeof(int64_t) * P.ns);
+  // task candidate capacity = sum of its slots' capacities
+  {
+    int64_t off = 0;
+    for (int t = 0; t < P.nt; ++t) {
+      P.task_off[t] = off;
+      for (int s = pb->tasks[t].slot_begin; s < pb->tasks[t].slot_end; ++s)
+        off += cat->cloud_group_cap[pb->slots[s].cloud];
+    }
+    P.task_off[P.nt] = off;
+    if (off > P.cand_cap) {
+      // slots shared by several tasks would overflow the task arrays
+      return fail(SKYOPT_EINVAL, "a slot belongs to more than one task");
+    }
+  }
+  int g = 0, qpos = 0, block0 = 0;
+  P.pass_rows = 0;
+  for (int c = 0; c < C; ++c) {
+    const auto &qs = by_cloud[c];
+    const int rows = cat->cloud_row_offsets[c + 1] - cat->cloud_row_offsets[c];
+    const int tiles = (rows + tile - 1) / tile;
+    for (size_t b = 0; b < qs.size(); b += kQChunk) {
+      const int n = (int)std::min<size_t>(kQChunk, qs.size() - b);
+      ScanGroup G{};
+      G.row_begin = cat->cloud_row_offsets[c];
+      G.row_end = cat->cloud_row_offsets[c + 1];
+      G.q_begin = qpos; G.q_count = n; G.block0 = block0; G.n_tiles = tiles;
+      for (int k = 0; k < n; ++k) {
+        const SkyoptQuery &q = pb->queries[qs[b + k]];
+        P.q_order[qpos + k] = qs[b + k];
+        G.need |= q.price_col ? 2u : 1u;
+        if (q.qflags & SKYOPT_Q_FUZZY) G.need |= 1u;
+      }
+      P.groups[g++] = G;
+      qpos += n; block0 += tiles;
+      P.pass_rows += rows;
+    }
+  }
+  P.n_blocks = block0;
+
+  // device views
+  Carver d(x->dbuf);
+  carve_inputs(P, d);
+  carve_rest(P, d);
+  return 0;
+}
+
+struct Timeline { float scan_ms = 0, expand_ms = 0, solve_ms = 0; };
+
+// Enqueue K1..K3 on the context's stream. Events ev[1..4] bracket the phases.
+int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
+  cudaStream_t st = x->stream;
+  CU(cudaEventRecord(x->ev[1], st));
+  if (P.nq) {
+    CU(cudaMemsetAsync(P.any1, 0, sizeof(uint32_t) * P.nq, st));
+    if (P.list_entries) CU(cudaMemsetAsync(P.list_min, 0xFF, sizeof(unsigned long long) * P.list_entries, st));
+    if (P.fuzzy_entries) CU(cudaMemsetAsync(P.fuzzy_min, 0xFF, sizeof(unsigned long long) * P.fuzzy_entries, st));
+    if (P.n_blocks) {
+#define LAUNCH_SCAN(R)                                                        \
+  scan_kernel<R><<<P.n_blocks, kScanThreads, 0, st>>>(                        \
+      cat->dev, P.queries, P.q_order, P.groups, P.n_groups, P.acc_sets,       \
+      P.partial_base, P.partials, P.any1, P.list_base, P.list_min,            \
+      P.fuzzy_base, P.fuzzy_min)
+      if (P.rpt == 4) LAUNCH_SCAN(4);
+      else if (P.rpt == 2) LAUNCH_SCAN(2);
+      else LAUNCH_SCAN(1);
+#undef LAUNCH_SCAN
+      CU(cudaGetLastError());
+    }
+    const int fblocks = (P.nq * 32 + 255) / 256;
+    finalize_kernel<<<fblocks, 256, 0, st>>>(cat->dev, P.nq, P.partial_base,
+                                             P.partial_count, P.partials, P.finals);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(x->ev[2], st));
+  if (!solve) return 0;
+  CU(cudaMemsetAsync(P.err_flag, 0, sizeof(int32_t), st));
+  ExpandOut ex{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
+  if (P.ns) {
+    const size_t smem = (size_t)cat->sort_n * 16 + (size_t)cat->max_zones * 8 +
+                        (size_t)cat->max_regions * 4;
+    expand_kernel<<<P.ns, 128, smem, st>>>(cat->dev, P.slots, P.finals, P.any1,
+                                           P.acc_sets, P.slot_off, cat->sort_n,
+                                           cat->max_regions, cat->max_zones, ex,
+                                           P.err_flag);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(x->ev[3], st));
+  if (P.nd) {
+    SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex};
+    SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
+    SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres};
+    solve_kernel<<<P.nd, kSolveThreads, 0, st>>>(cat->dev, in, w, out);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(P.err_out, P.err_flag, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  CU(cudaEventRecord(x->ev[4], st));
+  return 0;
+}
+
+void fill_scan_results(const SkyoptCatalog *cat, const Plan &P, const Plan &H,
+                       SkyoptScanResult *results) {
+  (void)cat; (void)P;
+  for (int i = 0; i < H.nq; ++i) {
+    SkyoptScanResult r{};
+    const ScanFinal &f = H.finals[i];
+    r.any_stage1 = H.any1[i] ? 1 : 0;
+    r.best_row = f.row;
+    r.best_inst = f.inst;
+    r.best_price = f.row >= 0 ? [&] {
+      uint64_t k = f.key;
+      uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+      double d; memcpy(&d, &b, 8); return d; }() : NAN;
+    results[i] = r;
+  }
+}
+
+// Host view of the output region inside the pinned buffer.
+void carve_output_host(const Plan &P, char *hbuf, Plan &H) {
+  H = P;
+  Carver c(hbuf);
+  H.finals = c.take<ScanFinal>(P.nq);
+  H.any1 = c.take<uint32_t>(P.nq);
+  H.slot_count = c.take<int32_t>(P.ns);
+  H.slot_inst = c.take<int32_t>(P.ns);
+  H.chosen = c.take<SkyoptCandidate>(P.nt);
+  H.chosen_index = c.take<int32_t>(P.nt);
+  H.task_n = c.take<int32_t>(P.nt);
+  H.dagres = c.take<SkyoptDagResult>(P.nd);
+  H.err_out = c.take<int32_t>(1);
+}
+
+int copy_solution(SkyoptCatalog *cat, Ctx *x, const Plan &P, const SkyoptProblem *pb,
+                  SkyoptSolution *sol) {
+  Plan H;
+  carve_output_host(P, x->hbuf, H);
+  if (*H.err_out)
+    return fail(SKYOPT_ELIMIT, "an instance-type group exceeds the expand capacity (%d rows)", cat->sort_n);
+  if (sol->scan) fill_scan_results(cat, P, H, sol->scan);
+  if (sol->slot_count && P.ns) memcpy(sol->slot_count, H.slot_count, sizeof(int32_t) * P.ns);
+  if (sol->slot_inst && P.ns) memcpy(sol->slot_inst, H.slot_inst, sizeof(int32_t) * P.ns);
+  if (sol->chosen && P.nt) memcpy(sol->chosen, H.chosen, sizeof(SkyoptCandidate) * P.nt);
+  if (sol->chosen_index && P.nt) memcpy(sol->chosen_index, H.chosen_index, sizeof(int32_t) * P.nt);
+  if (sol->task_n_candidates && P.nt) memcpy(sol->task_n_candidates, H.task_n, sizeof(int32_t) * P.nt);
+  if (sol->dag && P.nd) memcpy(sol->dag, H.dagres, sizeof(SkyoptDagResult) * P.nd);
+  // Tasks of a failed DAG carry no plan.
+  if (sol->chosen_index) {
+    for (int d = 0; d < P.nd; ++d)
+      if (H.dagres[d].status != 0)
+        for (int t = pb->dags[d].task_begin; t < pb->dags[d].task_end; ++t) {
+          sol->chosen_index[t] = -1;
+          if (sol->chosen) { sol->chosen[t] = SkyoptCandidate{}; sol->chosen[t].slot = -1; sol->chosen[t].inst_id = -1; }
+        }
+  }
+  if (sol->cand_cap > 0 && sol->candidates && sol->task_cand_offset) {
+    std::vector<int64_t> off(P.nt + 1, 0);
+    for (int t = 0; t < P.nt; ++t) off[t + 1] = off[t] + H.task_n[t];
+    if (off[P.nt] > sol->cand_cap)
+      return fail(SKYOPT_ELIMIT, "candidate table needs %lld entries, capacity %lld",
+                  (long long)off[P.nt], (long long)sol->cand_cap);
+    memcpy(sol->task_cand_offset, off.data(), sizeof(int64_t) * (P.nt + 1));
+    if (off[P.nt] > 0) {
+      int64_t *d_off = nullptr; SkyoptCandidate *d_tab = nullptr;
+      CU(cudaMalloc(&d_off, sizeof(int64_t) * (P.nt + 1)));
+      CU(cudaMalloc(&d_tab, sizeof(SkyoptCandidate) * off[P.nt]));
+      CU(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * (P.nt + 1), cudaMemcpyHostToDevice, x->stream));
+      ExpandOut ex{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
+      SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex};
+      SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
+      table_kernel<<<P.nt, 128, 0, x->stream>>>(in, w, P.task_n, P.nt, d_off, d_tab);
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(sol->candidates, d_tab, sizeof(SkyoptCandidate) * off[P.nt],
+                            cudaMemcpyDeviceToHost, x->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(x->stream);
+      cudaFree(d_off); cudaFree(d_tab);
+      if (e != cudaSuccess) return fail(SKYOPT_ECUDA, "candidate table: %s", cudaGetErrorString(e));
+    }
+  }
+  return 0;
+}
+
+int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
+  if (!stats) return 0;
+  memset(stats, 0, sizeof(*stats));
+  CU(cudaEventElapsedTime(&stats->scan_ms, x->ev[1], x->ev[2]));
+  if (solve) {
+    CU(cudaEventElapsedTime(&stats->expand_ms, x->ev[2], x->ev[3]));
+    CU(cudaEventElapsedTime(&stats->solve_ms, x->ev[3], x->ev[4]));
+  }
+  CU(cudaEventElapsedTime(&stats->total_ms, x->ev[0], x->ev[5]));
+  stats->scan_launches = P.n_blocks ? 1 : 0;
+  stats->total_launches = (P.n_blocks ? 1 : 0) + (P.nq ? 1 : 0) +
+                          (solve ? ((P.ns ? 1 : 0) + (P.nd ? 1 : 0)) : 0);
+  stats->scan_rows = P.scan_rows;
+  stats->scan_passes_rows = P.pass_rows;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int skyopt_abi_version(void) { return SKYOPT_ABI_VERSION; }
+const char *skyopt_last_error(void) { return g_error.c_str(); }
+
+int skyopt_device_count(int *count) {
+  if (!count) return fail(SKYOPT_EINVAL, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(SKYOPT_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  *count = n;
+  return 0;
+}
+
+int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog **out) {
+  if (!d || !out) return fail(SKYOPT_EINVAL, "NULL argument");
+  *out = nullptr;
+  if (d->n_rows <= 0 || d->n_rows % 8 != 0) return fail(SKYOPT_EINVAL, "n_rows must be a positive multiple of 8");
+  if (d->n_rows > 0x7FFFFFF0ll) return fail(SKYOPT_ELIMIT, "catalog exceeds 2^31 rows");
+  if (d->n_clouds <= 0 || d->n_clouds > SKYOPT_MAX_CLOUDS) return fail(SKYOPT_ELIMIT, "1..%d clouds supported", SKYOPT_MAX_CLOUDS);
+  if (d->n_acc_keys < 0 || d->n_acc_keys > 32 * SKYOPT_ACC_SET_WORDS)
+    return fail(SKYOPT_ELIMIT, "at most %d distinct (accelerator, count) pairs", 32 * SKYOPT_ACC_SET_WORDS);
+  if (!d->price || !d->spot_price || !d->vcpus || !d->mem || !d->acc_key || !d->region_id ||
+      !d->zone_id || !d->flags || !d->inst_id || !d->cloud_row_offsets || !d->cloud_inst_offsets ||
+      !d->cloud_region_offsets || !d->cloud_n_zones || !d->region_is_us || !d->inst_row_offsets ||
+      !d->inst_rows || !d->acc_row_offsets || !d->acc_rows || !d->inst_acc_key)
+    return fail(SKYOPT_EINVAL, "a required column pointer is NULL");
+  if (d->cloud_row_offsets[0] != 0 || d->cloud_row_offsets[d->n_clouds] != d->n_rows)
+    return fail(SKYOPT_EINVAL, "cloud_row_offsets must span [0, n_rows]");
+  for (int c = 0; c < d->n_clouds; ++c)
+    if (d->cloud_row_offsets[c] % 8 != 0 || d->cloud_row_offsets[c + 1] < d->cloud_row_offsets[c])
+      return fail(SKYOPT_EINVAL, "cloud %d row range must be 8-row aligned", c);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(SKYOPT_ENODEV, "no CUDA device available; libskyopt has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SKYOPT_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  SkyoptCatalog *c = new (std::nothrow) SkyoptCatalog();
+  if (!c) return fail(SKYOPT_ENOMEM, "out of host memory");
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+
+  const size_t n = (size_t)d->n_rows;
+  const size_t slack = kScanThreads * 4;  // one tile of over-read
+  int rc = 0;
+  CatDev &v = c->dev;
+  v.n_rows = d->n_rows;
+  v.n_clouds = d->n_clouds; v.n_inst = d->n_inst; v.n_acc_keys = d->n_acc_keys; v.n_regions = d->n_regions;
+  const size_t n_inst_rows = (size_t)d->inst_row_offsets[d->n_inst];
+  const size_t n_acc_rows = (size_t)d->acc_row_offsets[d->n_acc_keys];
+  rc = rc ? rc : upload(c, d->price, n, slack, &v.price);
+  rc = rc ? rc : upload(c, d->spot_price, n, slack, &v.spot);
+  rc = rc ? rc : upload(c, d->vcpus, n, slack, &v.vcpus);
+  rc = rc ? rc : upload(c, d->mem, n, slack, &v.mem);
+  if (d->disk_total) rc = rc ? rc : upload(c, d->disk_total, n, slack, &v.disk_total);
+  rc = rc ? rc : upload(c, d->acc_key, n, slack, &v.acc_key, 0xFF);
+  rc = rc ? rc : upload(c, d->region_id, n, slack, &v.region_id);
+  rc = rc ? rc : upload(c, d->zone_id, n, slack, &v.zone_id, 0xFF);
+  rc = rc ? rc : upload(c, d->flags, n, slack, &v.flags);
+  rc = rc ? rc : upload(c, d->inst_id, n, slack, &v.inst_id, 0xFF);
+  rc = rc ? rc : upload(c, d->cloud_row_offsets, (size_t)d->n_clouds + 1, 0, &v.cloud_row_offsets);
+  rc = rc ? rc : upload(c, d->cloud_inst_offsets, (size_t)d->n_clouds + 1, 0, &v.cloud_inst_offsets);
+  rc = rc ? rc : upload(c, d->cloud_region_offsets, (size_t)d->n_clouds + 1, 0, &v.cloud_region_offsets);
+  rc = rc ? rc : upload(c, d->cloud_n_zones, (size_t)d->n_clouds, 0, &v.cloud_n_zones);
+  rc = rc ? rc : upload(c, d->region_is_us, (size_t)std::max(d->n_regions, 1), 0, &v.region_is_us);
+  rc = rc ? rc : upload(c, d->inst_row_offsets, (size_t)d->n_inst + 1, 0, &v.inst_row_offsets);
+  rc = rc ? rc : upload(c, d->inst_rows, n_inst_rows, 1, &v.inst_rows);
+  rc = rc ? rc : upload(c, d->acc_row_offsets, (size_t)d->n_acc_keys + 1, 0, &v.acc_row_offsets);
+  rc = rc ? rc : upload(c, d->acc_rows, n_acc_rows, 1, &v.acc_rows);
+  rc = rc ? rc : upload(c, d->inst_acc_key, (size_t)std::max(d->n_inst, 1), 0, &v.inst_acc_key, 0xFF);
+  if (rc) { skyopt_catalog_destroy(c); return rc; }
+
+  c->cloud_row_offsets.assign(d->cloud_row_offsets, d->cloud_row_offsets + d->n_clouds + 1);
+  c->cloud_inst_offsets.assign(d->cloud_inst_offsets, d->cloud_inst_offsets + d->n_clouds + 1);
+  c->cloud_region_offsets.assign(d->cloud_region_offsets, d->cloud_region_offsets + d->n_clouds + 1);
+  c->cloud_n_zones.assign(d->cloud_n_zones, d->cloud_n_zones + d->n_clouds);
+  // Expand capacity per cloud: largest instance-type group, or all
+  // accelerator-only rows of one key.
+  c->cloud_group_cap.assign(d->n_clouds, 1);
+  int max_group = 1;
+  for (int cl = 0; cl < d->n_clouds; ++cl) {
+    int cap = 1;
+    for (int i = d->cloud_inst_offsets[cl]; i < d->cloud_inst_offsets[cl + 1]; ++i)
+      cap = std::max(cap, d->inst_row_offsets[i + 1] - d->inst_row_offsets[i]);
+    c->cloud_group_cap[cl] = cap;
+    c->max_regions = std::max(c->max_regions, d->cloud_region_offsets[cl + 1] - d->cloud_region_offsets[cl]);
+    c->max_zones = std::max(c->max_zones, d->cloud_n_zones[cl]);
+  }
+  // accelerator groups may span clouds in the CSR; bound them by the group
+  for (int k = 0; k < d->n_acc_keys; ++k) {
+    const int rows = d->acc_row_offsets[k + 1] - d->acc_row_offsets[k];
+    if (!rows) continue;
+    // an exact accelerator set may union a few keys (case variants): x4 slack
+    for (int cl = 0; cl < d->n_clouds; ++cl) {
+      bool in_cloud = false;
+      for (int i = d->acc_row_offsets[k]; i < d->acc_row_offsets[k + 1] && !in_cloud; ++i)
+        in_cloud = d->acc_rows[i] >= d->cloud_row_offsets[cl] && d->acc_rows[i] < d->cloud_row_offsets[cl + 1];
+      if (in_cloud) c->cloud_group_cap[cl] = std::max(c->cloud_group_cap[cl], rows);
+    }
+  }
+  for (int cl = 0; cl < d->n_clouds; ++cl) max_group = std::max(max_group, c->cloud_group_cap[cl]);
+  if (max_group > SKYOPT_MAX_GROUP_ROWS) {
+    skyopt_catalog_destroy(c);
+    return fail(SKYOPT_ELIMIT, "an instance type has %d rows; the limit is %d", max_group, SKYOPT_MAX_GROUP_ROWS);
+  }
+  c->sort_n = std::max(2, next_pow2(max_group));
+  for (int cl = 0; cl < d->n_clouds; ++cl) c->cloud_group_cap[cl] = c->sort_n;  // sorted output is written sparsely
+  const size_t smem = (size_t)c->sort_n * 16 + (size_t)c->max_zones * 8 + (size_t)c->max_regions * 4;
+  if (smem > 200 * 1024) { skyopt_catalog_destroy(c); return fail(SKYOPT_ELIMIT, "expand needs %zu B of shared memory", smem); }
+  cudaError_t e = cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 8);
+  if (e != cudaSuccess) { skyopt_catalog_destroy(c); return fail(SKYOPT_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  CU(cudaDeviceSynchronize());
+  *out = c;
+  return 0;
+}
+
+int skyopt_catalog_destroy(SkyoptCatalog *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  for (Ctx *x : c->free_ctx) {
+    if (x->stream) cudaStreamDestroy(x->stream);
+    for (auto &e : x->ev) if (e) cudaEventDestroy(e);
+    if (x->dbuf) cudaFree(x->dbuf);
+    if (x->hbuf) cudaFreeHost(x->hbuf);
+    if (x->flush) cudaFree(x->flush);
+    delete x;
+  }
+  for (void *p : c->allocs) cudaFree(p);
+  delete c;
+  return 0;
+}
+
+int skyopt_catalog_bytes(const SkyoptCatalog *c, int64_t *device_bytes, int64_t *row_bytes) {
+  if (!c) return fail(SKYOPT_EINVAL, "NULL catalog");
+  if (device_bytes) *device_bytes = c->device_bytes;
+  // bytes the scan streams per row and pass: one price column, vCPUs,
+  // MemoryGiB (f64) + acc_key, region, zone, flags (u16)
+  if (row_bytes) *row_bytes = 3 * 8 + 4 * 2;
+  return 0;
+}
+
+int skyopt_scan(SkyoptCatalog *cat, const SkyoptQuery *queries, int n_queries,
+                const uint32_t *acc_sets, int n_acc_sets, SkyoptScanResult *results,
+                int32_t *list_ids, double *list_prices, int list_cap,
+                int32_t *fuzzy_keys, double *fuzzy_prices, int fuzzy_cap,
+                SkyoptStats *stats) {
+  if (!cat || !queries || !results || n_queries <= 0) return fail(SKYOPT_EINVAL, "bad arguments");
+  if (list_cap > 2048 || fuzzy_cap > 2048) return fail(SKYOPT_ELIMIT, "list capacity is limited to 2048 entries");
+  SkyoptProblem pb{};
+  pb.queries = queries; pb.n_queries = n_queries; pb.acc_sets = acc_sets; pb.n_acc_sets = n_acc_sets;
+  int rc = validate_problem(cat, &pb);
+  if (rc) return rc;
+  CU(cudaSetDevice(cat->device));
+  Ctx *x = nullptr;
+  if ((rc = acquire(cat, &x))) return rc;
+  Plan P;
+  rc = build_plan(cat, &pb, x, P);
+  const bool want_list = list_ids && list_prices && list_cap > 0;
+  const bool want_fuzzy = fuzzy_keys && fuzzy_prices && fuzzy_cap > 0;
+  int32_t *d_ids = nullptr, *d_cnt = nullptr; double *d_pr = nullptr;
+  auto body = [&]() -> int {
+    if (rc) return rc;
+    cudaStream_t st = x->stream;
+    CU(cudaEventRecord(x->ev[0], st));
+    CU(cudaMemcpyAsync(x->dbuf, x->hbuf, P.in_bytes, cudaMemcpyHostToDevice, st));
+    int r = enqueue_kernels(cat, x, P, false);
+    if (r) return r;
+    CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(x->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    Plan H;
+    carve_output_host(P, x->hbuf, H);
+    fill_scan_results(cat, P, H, results);
+    for (int kind = 0; kind < 2; ++kind) {
+      const bool want = kind == 0 ? want_list : want_fuzzy;
+      if (!want) continue;
+      const int cap = kind == 0 ? list_cap : fuzzy_cap;
+      const int n_entries_max = kind == 0 ? cat->dev.n_inst : cat->dev.n_acc_keys;
+      const int sort_n = std::min(2048, std::max(2, next_pow2(std::max(n_entries_max, cap))));
+      CU(cudaMalloc(&d_ids, sizeof(int32_t) * (size_t)n_queries * cap));
+      CU(cudaMalloc(&d_pr, sizeof(double) * (size_t)n_queries * cap));
+      CU(cudaMalloc(&d_cnt, sizeof(int32_t) * (size_t)n_queries));
+      list_kernel<<<n_queries, 256, (size_t)sort_n * 16, st>>>(
+          cat->dev, P.queries, kind, kind == 0 ? P.list_base : P.fuzzy_base,
+          kind == 0 ? P.list_min : P.fuzzy_min, cap, sort_n, d_ids, d_pr, d_cnt);
+      CU(cudaGetLastError());
+      std::vector<int32_t> cnt(n_queries);
+      CU(cudaMemcpyAsync(kind == 0 ? list_ids : fuzzy_keys, d_ids, sizeof(int32_t) * (size_t)n_queries * cap, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(kind == 0 ? list_prices : fuzzy_prices, d_pr, sizeof(double) * (size_t)n_queries * cap, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int32_t) * (size_t)n_queries, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (int i = 0; i < n_queries; ++i) (kind == 0 ? results[i].n_list : results[i].n_fuzzy) = cnt[i];
+      cudaFree(d_ids); cudaFree(d_pr); cudaFree(d_cnt);
+      d_ids = nullptr; d_pr = nullptr; d_cnt = nullptr;
+    }
+    return fill_stats(x, P, stats, false);
+  };
+  rc = body();
+  if (d_ids) cudaFree(d_ids);
+  if (d_pr) cudaFree(d_pr);
+  if (d_cnt) cudaFree(d_cnt);
+  if (rc) cudaStreamSynchronize(x->stream);
+  release(cat, x);
+  return rc;
+}
+
+int skyopt_optimize(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution *sol,
+                    SkyoptStats *stats) {
+  if (!cat || !pb || !sol) return fail(SKYOPT_EINVAL, "NULL argument");
+  if (pb->n_dags <= 0 || pb->n_tasks <= 0 || pb->n_slots <= 0)
+    return fail(SKYOPT_EINVAL, "empty problem");
+  int rc = validate_problem(cat, pb);
+  if (rc) return rc;
+  CU(cudaSetDevice(cat->device));
+  Ctx *x = nullptr;
+  if ((rc = acquire(cat, &x))) return rc;
+  Plan P;
+  auto body = [&]() -> int {
+    int r = build_plan(cat, pb, x, P);
+    if (r) return r;
+    cudaStream_t st = x->stream;
+    CU(cudaEventRecord(x->ev[0], st));
+    CU(cudaMemcpyAsync(x->dbuf, x->hbuf, P.in_bytes, cudaMemcpyHostToDevice, st));
+    if ((r = enqueue_kernels(cat, x, P, true))) return r;
+    CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(x->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    if ((r = copy_solution(cat, x, P, pb, sol))) return r;
+    return fill_stats(x, P, stats, true);
+  };
+  rc = body();
+  if (rc) cudaStreamSynchronize(x->stream);
+  release(cat, x);
+  return rc;
+}
+
+int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution *sol,
+                          int iters, int flush_l2, float *iter_ms, float *scan_ms,
+                          SkyoptStats *stats) {
+  if (!cat || !pb || !sol || iters <= 0 || !iter_ms) return fail(SKYOPT_EINVAL, "bad arguments");
+  int rc = validate_problem(cat, pb);
+  if (rc) return rc;
+  CU(cudaSetDevice(cat->device));
+  Ctx *x = nullptr;
+  if ((rc = acquire(cat, &x))) return rc;
+  Plan P;
+  auto body = [&]() -> int {
+    int r = build_plan(cat, pb, x, P);
+    if (r) return r;
+    cudaStream_t st = x->stream;
+    const size_t flush_words = (size_t)192 << 20 >> 2;  // 192 MB > 126 MB L2
+    if (flush_l2 && !x->flush) {
+      CU(cudaMalloc(&x->flush, flush_words * 4));
+      x->flush_words = flush_words;
+    }
+    CU(cudaEventRecord(x->ev[0], st));
+    CU(cudaMemcpyAsync(x->dbuf, x->hbuf, P.in_bytes, cudaMemcpyHostToDevice, st));
+    for (int it = 0; it < iters; ++it) {
+      if (flush_l2) {
+        flush_kernel<<<cat->sm_count * 8, 256, 0, st>>>(x->flush, (int64_t)x->flush_words, (uint32_t)it);
+        CU(cudaGetLastError());
+      }
+      if ((r = enqueue_kernels(cat, x, P, true))) return r;
+      CU(cudaStreamSynchronize(st));
+      CU(cudaEventElapsedTime(&iter_ms[it], x->ev[1], x->ev[4]));
+      if (scan_ms) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[1], x->ev[2]));
+    }
+    CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(x->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    if ((r = copy_solution(cat, x, P, pb, sol))) return r;
+    return fill_stats(x, P, stats, true);
+  };
+  rc = body();
+  if (rc) cudaStreamSynchronize(x->stream);
+  release(cat, x);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,945 @@
+// skyopt_kernels.cuh -- sm_100a kernels of the placement-optimizer hot path.
+//
+// K1 scan_kernel      Resources-constraint filter + per-query argmin over the
+//                     SoA catalog (reference sky/catalog/common.py:518-569,
+//                     :641-694). HBM-bound: one pass over 32 B/row streams the
+//                     rows once for up to 32 fused queries whose constraint
+//                     vectors sit in shared memory.
+// K1b finalize_kernel per-query reduction of the per-tile partials.
+// K1c list_kernel     sorted (instance type, min price) / fuzzy tables.
+// K2 expand_kernel    region/zone expansion of the winning instance type,
+//                     ordering and per-candidate hourly price
+//                     (common.py:793-809, :360-400; resources_utils.py:454-502;
+//                     gcp.py:281-331; gcp_catalog.py:424-442).
+// K3 solve_kernel     blocked filter, cost, egress and chain DP / exact DAG
+//                     search (optimizer.py:196-236, :343-357, :429-487,
+//                     :490-637; resources.py:1938-1961).
+//
+// No tensor cores: this path is scan / filter / reduce (BASELINE.json).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "skyopt.h"
+
+namespace skyopt {
+
+constexpr int kScanThreads = 256;
+constexpr int kQChunk = 32;           // queries fused per pass
+constexpr uint64_t kKeyNone = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint64_t kKeyNaN = 0xFFFFFFFFFFFFFFF0ull;  // after every real price
+constexpr uint32_t kRowNone = 0xFFFFFFFFu;
+
+struct CatDev {
+  int64_t n_rows;
+  const double *price, *spot, *vcpus, *mem, *disk_total;
+  const uint16_t *acc_key, *region_id, *zone_id, *flags;
+  const int32_t *inst_id;
+  const int32_t *cloud_row_offsets, *cloud_inst_offsets, *cloud_region_offsets;
+  const int32_t *cloud_n_zones;
+  const uint8_t *region_is_us;
+  const int32_t *inst_row_offsets, *inst_rows, *acc_row_offsets, *acc_rows;
+  const uint16_t *inst_acc_key;
+  int32_t n_clouds, n_inst, n_acc_keys, n_regions;
+};
+
+// One (cloud, query-chunk) unit of the scan grid.
+struct ScanGroup {
+  int32_t row_begin, row_end;
+  int32_t q_begin, q_count;  // into q_order
+  int32_t block0, n_tiles;
+  uint32_t need;             // bit0 on-demand column, bit1 spot column
+  int32_t pad_;
+};
+
+struct ScanPartial {
+  uint64_t key;
+  uint32_t row;
+  uint32_t pad_;
+};
+
+struct ScanFinal {
+  uint64_t key;
+  int32_t row;
+  int32_t inst;
+};
+
+// Total order on prices as unsigned integers (NaN never reaches here).
+__device__ __forceinline__ uint64_t price_key(double p) {
+  uint64_t b = (uint64_t)__double_as_longlong(p);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_price(uint64_t k) {
+  uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__device__ __forceinline__ bool test_bit(const uint32_t *set, uint32_t k) {
+  return (set[k >> 5] >> (k & 31)) & 1u;
+}
+
+template <int RPT>
+struct RowRegs {
+  double od[RPT], sp[RPT], vc[RPT], mm[RPT];
+  uint16_t ak[RPT], rg[RPT], zn[RPT], fl[RPT];
+};
+
+// 128-bit (f64) / 64-bit (u16) vector loads through the read-only path. The
+// catalog arrays are 256 B aligned, cloud ranges are padded to 8 rows and the
+// arrays carry one tile of slack, so every thread's RPT-row group is aligned
+// and in bounds.
+template <int RPT>
+__device__ __forceinline__ void load_f64(const double *__restrict__ col,
+                                         int64_t base, double (&out)[RPT]) {
+  if constexpr (RPT == 4) {
+    const double2 *p = reinterpret_cast<const double2 *>(col + base);
+    double2 a = __ldg(p), b = __ldg(p + 1);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+  } else if constexpr (RPT == 2) {
+    double2 a = __ldg(reinterpret_cast<const double2 *>(col + base));
+    out[0] = a.x; out[1] = a.y;
+  } else {
+    out[0] = __ldg(col + base);
+  }
+}
+template <int RPT>
+__device__ __forceinline__ void load_u16(const uint16_t *__restrict__ col,
+                                         int64_t base, uint16_t (&out)[RPT]) {
+  if constexpr (RPT == 4) {
+    uint2 a = __ldg(reinterpret_cast<const uint2 *>(col + base));
+    out[0] = a.x & 0xFFFF; out[1] = a.x >> 16;
+    out[2] = a.y & 0xFFFF; out[3] = a.y >> 16;
+  } else if constexpr (RPT == 2) {
+    uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(col + base));
+    out[0] = a & 0xFFFF; out[1] = a >> 16;
+  } else {
+    out[0] = __ldg(col + base);
+  }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
+            const int32_t *__restrict__ q_order,
+            const ScanGroup *__restrict__ groups, int n_groups,
+            const uint32_t *__restrict__ acc_sets,
+            const int32_t *__restrict__ partial_base,
+            ScanPartial *__restrict__ partials, uint32_t *__restrict__ any1,
+            const int64_t *__restrict__ list_base,
+            unsigned long long *__restrict__ list_min,
+            const int64_t *__restrict__ fuzzy_base,
+            unsigned long long *__restrict__ fuzzy_min) {
+  constexpr int kWarps = kScanThreads / 32;
+  __shared__ SkyoptQuery sq[kQChunk];
+  __shared__ uint32_t sset[kQChunk][2][SKYOPT_ACC_SET_WORDS];
+  __shared__ int32_t sqid[kQChunk];
+  __shared__ uint64_t wkey[kQChunk][kWarps];
+  __shared__ uint32_t wrow[kQChunk][kWarps];
+  __shared__ uint32_t sany[kQChunk];
+
+  // blockIdx -> (group, tile): groups are sorted by block0.
+  int lo = 0, hi = n_groups - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&groups[mid].block0) <= b) lo = mid; else hi = mid - 1;
+  }
+  const ScanGroup G = groups[lo];
+  const int tile = b - G.block0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = G.q_count;
+
+  // Stage the chunk's constraint vectors (and accelerator-key bitmasks).
+  if (tid < nq) {
+    int qi = __ldg(&q_order[G.q_begin + tid]);
+    sqid[tid] = qi;
+    sq[tid] = queries[qi];
+    sany[tid] = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < nq * 2 * SKYOPT_ACC_SET_WORDS; i += kScanThreads) {
+    int q = i / (2 * SKYOPT_ACC_SET_WORDS);
+    int r = i % (2 * SKYOPT_ACC_SET_WORDS);
+    int which = r / SKYOPT_ACC_SET_WORDS, w = r % SKYOPT_ACC_SET_WORDS;
+    int set = which ? sq[q].fuzzy_set : sq[q].acc_set;
+    sset[q][which][w] =
+        set >= 0 ? __ldg(&acc_sets[(int64_t)set * SKYOPT_ACC_SET_WORDS + w]) : 0u;
+  }
+
+  // Stream this thread's rows into registers: 32 B per row.
+  const int64_t base =
+      (int64_t)G.row_begin + (int64_t)tile * (kScanThreads * RPT) + tid * RPT;
+  RowRegs<RPT> R;
+  if (G.need & 1u) load_f64<RPT>(cat.price, base, R.od);
+  if (G.need & 2u) load_f64<RPT>(cat.spot, base, R.sp);
+  load_f64<RPT>(cat.vcpus, base, R.vc);
+  load_f64<RPT>(cat.mem, base, R.mm);
+  load_u16<RPT>(cat.acc_key, base, R.ak);
+  load_u16<RPT>(cat.region_id, base, R.rg);
+  load_u16<RPT>(cat.zone_id, base, R.zn);
+  load_u16<RPT>(cat.flags, base, R.fl);
+  __syncthreads();
+
+  for (int q = 0; q < nq; ++q) {
+    const SkyoptQuery &Q = sq[q];
+    const bool acc = Q.qflags & SKYOPT_Q_ACC;
+    const bool fuzzy = Q.qflags & SKYOPT_Q_FUZZY;
+    const uint32_t fmask = Q.flags_require | SKYOPT_F_VALID;
+    uint32_t m1 = 0, mf = 0;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const uint32_t f = R.fl[j];
+      bool ok = (base + j < G.row_end) && ((f & fmask) == fmask);
+      ok = ok && (Q.group == 0 || (int)(f >> 8) == Q.group);
+      ok = ok && (Q.region_id < 0 || (int)R.rg[j] == Q.region_id);
+      ok = ok && (Q.zone_id < 0 || (int)R.zn[j] == Q.zone_id);
+      bool ex = ok, fz = false;
+      if (acc) {
+        const uint32_t k = R.ak[j];
+        const bool has = ok && k != SKYOPT_NONE16;
+        ex = has && test_bit(sset[q][0], k);
+        fz = has && fuzzy && test_bit(sset[q][1], k);
+      }
+      m1 |= (uint32_t)ex << j;
+      mf |= (uint32_t)fz << j;
+    }
+    if (Q.disk_op != 0 && (m1 | mf)) {
+      // AWS local-disk size test (common.py:499-504); rare, so the column is
+      // gathered on demand.
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        if (((m1 | mf) >> j) & 1u) {
+          const double total = cat.disk_total ? __ldg(cat.disk_total + base + j) : 0.0;
+          const bool okd = Q.disk_op == SKYOPT_DISK_GE
+                               ? (total >= Q.disk_size)
+                               : (fabs(total - Q.disk_size) < 1.0);
+          if (!okd) { m1 &= ~(1u << j); mf &= ~(1u << j); }
+        }
+      }
+    }
+    uint64_t bkey = kKeyNone;
+    uint32_t brow = kRowNone;
+    if (m1) {
+      sany[q] = 1u;  // benign race: every writer stores 1
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        if (!((m1 >> j) & 1u)) continue;
+        bool ok = (R.fl[j] & Q.flags_require2) == Q.flags_require2;
+        if (Q.cpus_op == SKYOPT_OP_EQ) ok = ok && R.vc[j] == Q.cpus;
+        else if (Q.cpus_op == SKYOPT_OP_GE) ok = ok && R.vc[j] >= Q.cpus;
+        if (Q.mem_op == SKYOPT_OP_EQ) ok = ok && R.mm[j] == Q.mem;
+        else if (Q.mem_op == SKYOPT_OP_GE) ok = ok && R.mm[j] >= Q.mem;
+        else if (Q.mem_op == SKYOPT_OP_RATIO)
+          ok = ok && R.mm[j] >= __dmul_rn(R.vc[j], Q.mem);
+        if (!ok) continue;
+        const double p = Q.price_col ? R.sp[j] : R.od[j];
+        const bool priced = p <= Q.max_price;  // false for NaN
+        uint64_t key = kKeyNone;
+        if (priced) {
+          key = price_key(p);
+          if (key < bkey) { bkey = key; brow = (uint32_t)(base + j); }
+        } else if ((Q.qflags & SKYOPT_Q_KEEP_NAN) && p != p) {
+          key = kKeyNaN;
+        }
+        if ((Q.qflags & SKYOPT_Q_LIST) && key != kKeyNone) {
+          const int inst = __ldg(cat.inst_id + base + j);
+          if (inst >= 0) {
+            const int local = inst - __ldg(&cat.cloud_inst_offsets[Q.cloud]);
+            atomicMin(&list_min[list_base[sqid[q]] + local],
+                      (unsigned long long)key);
+          }
+        }
+      }
+    }
+    if (mf) {
+      // Fuzzy table: min 'Price' per accelerator key (common.py:661-667).
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        if (!((mf >> j) & 1u)) continue;
+        const double p = (G.need & 1u) ? R.od[j] : __ldg(cat.price + base + j);
+        const uint64_t key = (p == p) ? price_key(p) : kKeyNaN;
+        atomicMin(&fuzzy_min[fuzzy_base[sqid[q]] + R.ak[j]],
+                  (unsigned long long)key);
+      }
+    }
+    // Warp argmin of (price key, row) with three REDUX steps; skipped when no
+    // lane has a candidate (the common case for selective queries).
+    if (__any_sync(0xFFFFFFFFu, brow != kRowNone)) {
+      const uint32_t khi = (uint32_t)(bkey >> 32);
+      const uint32_t mhi = __reduce_min_sync(0xFFFFFFFFu, khi);
+      const uint32_t klo = (khi == mhi) ? (uint32_t)bkey : 0xFFFFFFFFu;
+      const uint32_t mlo = __reduce_min_sync(0xFFFFFFFFu, klo);
+      const uint32_t kr = (khi == mhi && klo == mlo) ? brow : kRowNone;
+      const uint32_t mr = __reduce_min_sync(0xFFFFFFFFu, kr);
+      if (lane == 0) {
+        wkey[q][warp] = ((uint64_t)mhi << 32) | mlo;
+        wrow[q][warp] = mr;
+      }
+    } else if (lane == 0) {
+      wkey[q][warp] = kKeyNone;
+      wrow[q][warp] = kRowNone;
+    }
+  }
+  __syncthreads();
+  if (tid < nq) {
+    uint64_t k = kKeyNone;
+    uint32_t r = kRowNone;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const uint64_t kw = wkey[tid][w];
+      const uint32_t rw = wrow[tid][w];
+      if (kw < k || (kw == k && rw < r)) { k = kw; r = rw; }
+    }
+    ScanPartial out;
+    out.key = k; out.row = r; out.pad_ = 0;
+    partials[(int64_t)partial_base[sqid[tid]] + tile] = out;
+    if (sany[tid]) atomicOr(&any1[sqid[tid]], 1u);
+  }
+}
+
+// One warp per query: reduce the per-tile partials.
+__global__ void finalize_kernel(CatDev cat, int n_queries,
+                                const int32_t *__restrict__ partial_base,
+                                const int32_t *__restrict__ partial_count,
+                                const ScanPartial *__restrict__ partials,
+                                ScanFinal *__restrict__ finals) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= n_queries) return;
+  const int64_t pb = partial_base[q];
+  const int n = partial_count[q];
+  uint64_t k = kKeyNone;
+  uint32_t r = kRowNone;
+  for (int i = lane; i < n; i += 32) {
+    const ScanPartial p = partials[pb + i];
+    if (p.key < k || (p.key == k && p.row < r)) { k = p.key; r = p.row; }
+  }
+  for (int off = 16; off; off >>= 1) {
+    const uint64_t ok = __shfl_xor_sync(0xFFFFFFFFu, k, off);
+    const uint32_t orow = __shfl_xor_sync(0xFFFFFFFFu, r, off);
+    if (ok < k || (ok == k && orow < r)) { k = ok; r = orow; }
+  }
+  if (lane == 0) {
+    ScanFinal f;
+    f.key = k;
+    f.row = (r == kRowNone) ? -1 : (int32_t)r;
+    f.inst = (r == kRowNone) ? -1 : cat.inst_id[r];
+    finals[q] = f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Block-wide bitonic sort of (k1, k2) pairs in shared memory, n = power of 2.
+__device__ __forceinline__ void bitonic_sort2(uint64_t *k1, uint64_t *k2, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const uint64_t a1 = k1[lo], a2 = k2[lo], b1 = k1[hi], b2 = k2[hi];
+        const bool gt = (a1 > b1) || (a1 == b1 && a2 > b2);
+        if (gt == up) { k1[lo] = b1; k2[lo] = b2; k1[hi] = a1; k2[hi] = a2; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Sorted tables of skyopt_scan: block per (query, kind). kind 0 = instance
+// types by min price (common.py:692-693), kind 1 = fuzzy accelerator keys by
+// min Price (common.py:665-667).
+__global__ void list_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
+                            int kind, const int64_t *__restrict__ base,
+                            const unsigned long long *__restrict__ table,
+                            int cap, int sort_n, int32_t *__restrict__ out_ids,
+                            double *__restrict__ out_prices,
+                            int32_t *__restrict__ out_count) {
+  extern __shared__ uint64_t smem_u64[];
+  uint64_t *k1 = smem_u64, *k2 = smem_u64 + sort_n;
+  __shared__ int s_n;
+  const int q = blockIdx.x;
+  const SkyoptQuery Q = queries[q];
+  const uint32_t want = kind == 0 ? SKYOPT_Q_LIST : SKYOPT_Q_FUZZY;
+  if (!(Q.qflags & want)) {
+    if (threadIdx.x == 0) out_count[q] = 0;
+    return;
+  }
+  const int n_entries = kind == 0 ? cat.cloud_inst_offsets[Q.cloud + 1] -
+                                        cat.cloud_inst_offsets[Q.cloud]
+                                  : cat.n_acc_keys;
+  const int id0 = kind == 0 ? cat.cloud_inst_offsets[Q.cloud] : 0;
+  if (threadIdx.x == 0) s_n = 0;
+  for (int i = threadIdx.x; i < sort_n; i += blockDim.x) { k1[i] = kKeyNone; k2[i] = kKeyNone; }
+  __syncthreads();
+  const unsigned long long *t = table + base[q];
+  for (int i = threadIdx.x; i < n_entries; i += blockDim.x) {
+    const uint64_t k = t[i];
+    if (k != kKeyNone) {
+      const int pos = atomicAdd(&s_n, 1);
+      if (pos < sort_n) { k1[pos] = k; k2[pos] = (uint64_t)(id0 + i); }
+    }
+  }
+  __syncthreads();
+  const int n = min(s_n, sort_n);
+  bitonic_sort2(k1, k2, sort_n);
+  const int n_out = min(n, cap);
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+    out_ids[(int64_t)q * cap + i] = (int32_t)k2[i];
+    out_prices[(int64_t)q * cap + i] =
+        k1[i] == kKeyNaN ? __longlong_as_double(0x7FF8000000000000ll) : key_price(k1[i]);
+  }
+  if (threadIdx.x == 0) out_count[q] = n_out;
+}
+
+// ---------------------------------------------------------------------------
+// K2: one block per slot.
+struct ExpandOut {
+  int32_t *slot_count;     // [n_slots]
+  int32_t *slot_inst;      // [n_slots]
+  int32_t *cand_region;    // candidate buffers at slot_off[s]
+  int32_t *cand_zone;
+  double *cand_price_a;    // instance price
+  double *cand_price_b;    // GCP accelerator price (0 otherwise)
+};
+
+__global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
+                              const ScanFinal *__restrict__ finals,
+                              const uint32_t *__restrict__ any1,
+                              const uint32_t *__restrict__ acc_sets,
+                              const int64_t *__restrict__ slot_off, int sort_n,
+                              int max_regions, int max_zones, ExpandOut out,
+                              int32_t *__restrict__ err_flag) {
+  extern __shared__ uint64_t smem_u64[];
+  uint64_t *k1 = smem_u64;                 // [sort_n] price key
+  uint64_t *k2 = k1 + sort_n;              // [sort_n] region|zone|local
+  double *bprice = reinterpret_cast<double *>(k2 + sort_n);  // [max_zones]
+  int32_t *first_pos = reinterpret_cast<int32_t *>(bprice + max_zones);  // [max_regions]
+  __shared__ int s_n;
+
+  const int s = blockIdx.x;
+  const SkyoptSlot S = slots[s];
+  const int tid = threadIdx.x;
+  const int cloud = S.cloud;
+  const int reg0 = cat.cloud_region_offsets[cloud];
+  const bool has_zones = cat.cloud_n_zones[cloud] > 0;
+
+  int inst = S.inst_id;
+  bool empty = false;
+  if (S.gate_query >= 0 && any1[S.gate_query] == 0) empty = true;
+  if (S.query >= 0) {
+    const ScanFinal f = finals[S.query];
+    inst = f.inst;
+    if (f.row < 0 || f.inst < 0) empty = true;
+  }
+  if (empty || (inst < 0 && inst != -2)) {
+    if (tid == 0) { out.slot_count[s] = 0; out.slot_inst[s] = -1; }
+    return;
+  }
+  if (tid == 0) s_n = 0;
+  for (int i = tid; i < sort_n; i += blockDim.x) { k1[i] = kKeyNone; k2[i] = kKeyNone; }
+  for (int i = tid; i < max_regions; i += blockDim.x) first_pos[i] = 0x7FFFFFFF;
+  const double kNaN = __longlong_as_double(0x7FF8000000000000ll);
+  for (int i = tid; i < max_zones; i += blockDim.x) bprice[i] = kNaN;
+  __syncthreads();
+
+  const double *pcol = S.price_col ? cat.spot : cat.price;
+  const bool gcp_acc = S.acc_set >= 0;
+
+  // Group A: the rows that define the region/zone order -- the instance
+  // type's rows, or (GCP) the accelerator's rows.
+  auto push_row = [&](int row) {
+    const double p = pcol[row];
+    const int rg = cat.region_id[row];
+    const int zn = cat.zone_id[row];
+    // dropna over [price, Region, AvailabilityZone] (common.py:797-802)
+    if (p != p) return;
+    if (has_zones && zn == SKYOPT_NONE16) return;
+    const int pos = atomicAdd(&s_n, 1);
+    if (pos < sort_n) {
+      k1[pos] = price_key(p);
+      k2[pos] = ((uint64_t)rg << 48) | ((uint64_t)(has_zones ? zn : 0) << 32) |
+                (uint32_t)row;
+    }
+  };
+  if (gcp_acc) {
+    const uint32_t *set = acc_sets + (int64_t)S.acc_set * SKYOPT_ACC_SET_WORDS;
+    for (int k = 0; k < cat.n_acc_keys; ++k) {
+      if (!test_bit(set, k)) continue;  // uniform branch
+      const int b = cat.acc_row_offsets[k], e = cat.acc_row_offsets[k + 1];
+      const int r0 = cat.cloud_row_offsets[cloud], r1 = cat.cloud_row_offsets[cloud + 1];
+      for (int i = b + tid; i < e; i += blockDim.x) {
+        const int row = cat.acc_rows[i];
+        if (row >= r0 && row < r1) push_row(row);
+      }
+    }
+    // Group B: host VM zones with a price (gcp.py:296-322).
+    if (inst >= 0) {
+      const int b = cat.inst_row_offsets[inst], e = cat.inst_row_offsets[inst + 1];
+      for (int i = b + tid; i < e; i += blockDim.x) {
+        const int row = cat.inst_rows[i];
+        const double p = pcol[row];
+        const int zn = cat.zone_id[row];
+        if (p == p && zn != SKYOPT_NONE16 && zn < max_zones) bprice[zn] = p;
+      }
+    }
+  } else {
+    const int b = cat.inst_row_offsets[inst], e = cat.inst_row_offsets[inst + 1];
+    for (int i = b + tid; i < e; i += blockDim.x) push_row(cat.inst_rows[i]);
+  }
+  __syncthreads();
+  if (s_n > sort_n) {
+    if (tid == 0) { atomicExch(err_flag, 1); out.slot_count[s] = 0; out.slot_inst[s] = inst; }
+    return;
+  }
+  const int n = s_n;
+  // sort_values([price, Region, AvailabilityZone]) -- ids are ranks in string
+  // order, the row id keeps equal keys in CSV order.
+  bitonic_sort2(k1, k2, sort_n);
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int rg = (int)(k2[i] >> 48);
+    atomicMin(&first_pos[rg], i);
+  }
+  __syncthreads();
+
+  // Second key: [us regions first,] region first-appearance, sorted position.
+  // Each thread rewrites only its own entries: k1 <- ordering key (or "none"
+  // when the entry is filtered out), k2 <- catalog row.
+  for (int i = tid; i < sort_n; i += blockDim.x) {
+    uint64_t key = kKeyNone, payload = kKeyNone;
+    if (i < n) {
+      const uint64_t v = k2[i];
+      const int rg = (int)(v >> 48);
+      const int zn = (int)((v >> 32) & 0xFFFF);
+      bool keep = true;
+      if (S.region_id >= 0 && rg != S.region_id) keep = false;
+      if (S.zone_id >= 0 && (!has_zones || zn != S.zone_id)) keep = false;
+      const bool split = S.split_by_zone && has_zones;
+      // Region-level candidates: the region's first sorted row carries its
+      // min price. With an explicit zone the (single) matching row is kept.
+      if (!split && S.zone_id < 0 && first_pos[rg] != i) keep = false;
+      if (gcp_acc && inst >= 0) {
+        const double hb = (zn < max_zones) ? bprice[zn] : kNaN;
+        if (hb != hb) keep = false;
+      }
+      if (keep) {
+        const uint64_t us = (S.us_first && !cat.region_is_us[reg0 + rg]) ? 1 : 0;
+        key = (us << 48) | ((uint64_t)first_pos[rg] << 24) | (uint64_t)i;
+        payload = (uint64_t)(uint32_t)(v & 0xFFFFFFFFu);
+      }
+    }
+    k1[i] = key;
+    k2[i] = payload;
+  }
+  bitonic_sort2(k1, k2, sort_n);
+
+  const int64_t off = slot_off[s];
+  int count = 0;
+  for (int i = tid; i < sort_n; i += blockDim.x) {
+    if (k1[i] == kKeyNone) continue;
+    const int row = (int)(k2[i] & 0xFFFFFFFFu);
+    const int rg = cat.region_id[row];
+    const int zn = cat.zone_id[row];
+    const bool split = S.split_by_zone && has_zones;
+    out.cand_region[off + i] = rg;
+    out.cand_zone[off + i] = (split || S.zone_id >= 0) ? (has_zones ? zn : -1) : -1;
+    double pa = pcol[row], pb = 0.0;
+    if (gcp_acc) {
+      // accelerator price at this zone: SpotPrice, falling back to Price when
+      // spot is NaN (gcp_catalog.py:433-442); host VM price from group B.
+      pb = pa;
+      pa = (inst >= 0) ? bprice[zn] : 0.0;
+    }
+    out.cand_price_a[off + i] = pa;
+    out.cand_price_b[off + i] = pb;
+  }
+  // count = number of valid keys (they are sorted to the front)
+  __syncthreads();
+  if (tid == 0) {
+    int lo = 0, hi = sort_n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (k1[mid] != kKeyNone) lo = mid + 1; else hi = mid; }
+    count = lo;
+    out.slot_count[s] = count;
+    out.slot_inst[s] = inst;
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// K3: one block per DAG.
+constexpr int kSolveThreads = 256;
+constexpr int kMaxDagTasks = 16;  // exact search only; chains are unbounded
+
+struct SolveIn {
+  const SkyoptSlot *slots;
+  const SkyoptTask *tasks;
+  const int32_t *parents;
+  const double *tariffs;
+  const SkyoptBlocked *blocked;
+  const SkyoptDag *dags;
+  const int64_t *slot_off;   // [n_slots] into the expand candidate buffers
+  const int64_t *task_off;   // [n_tasks+1] into the task candidate arrays
+  ExpandOut ex;
+};
+
+struct SolveWork {
+  int32_t *tc_ref;    // index into the expand candidate buffers
+  int32_t *tc_slot;
+  int32_t *tc_cloud;
+  double *tc_hourly;
+  double *tc_value;
+  double *dp;
+  int32_t *back;
+};
+
+struct SolveOut {
+  SkyoptCandidate *chosen;     // [n_tasks]
+  int32_t *chosen_index;       // [n_tasks]
+  int32_t *task_n;             // [n_tasks]
+  SkyoptDagResult *dag;        // [n_dags]
+};
+
+__device__ __forceinline__ void lexmin(double &v, int &i, double ov, int oi) {
+  if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+__global__ void __launch_bounds__(kSolveThreads)
+solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
+  constexpr int kWarps = kSolveThreads / 32;
+  __shared__ int s_pos;
+  __shared__ int s_wcount[kWarps];
+  __shared__ int s_fail;
+  __shared__ double s_best_val[SKYOPT_MAX_CLOUDS];
+  __shared__ int s_best_idx[SKYOPT_MAX_CLOUDS];
+  __shared__ double s_tb_val[kMaxDagTasks][SKYOPT_MAX_CLOUDS];
+  __shared__ int s_tb_idx[kMaxDagTasks][SKYOPT_MAX_CLOUDS];
+  __shared__ int s_opt[kMaxDagTasks][SKYOPT_MAX_CLOUDS];  // cloud options
+  __shared__ int s_nopt[kMaxDagTasks];
+  __shared__ double s_red_val[kWarps];
+  __shared__ long long s_red_idx[kWarps];
+
+  const SkyoptDag D = in.dags[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = cat.n_clouds;
+  const int T = D.task_end - D.task_begin;
+  if (tid == 0) s_fail = -1;
+  __syncthreads();
+
+  // ---- Phase A: candidates of every task, in the reference's order
+  // (requested Resources -> enabled clouds -> region/zone order), minus the
+  // blocked ones, with their cost / time value.
+  for (int t = D.task_begin; t < D.task_end; ++t) {
+    const SkyoptTask TK = in.tasks[t];
+    const int64_t toff = in.task_off[t];
+    if (tid == 0) s_pos = 0;
+    __syncthreads();
+    for (int s = TK.slot_begin; s < TK.slot_end; ++s) {
+      const SkyoptSlot S = in.slots[s];
+      const int cnt = in.ex.slot_count[s];
+      const int inst = in.ex.slot_inst[s];
+      const int64_t off = in.slot_off[s];
+      int cand_acc = S.cand_acc_key;
+      if (cand_acc < 0 && inst >= 0) cand_acc = cat.inst_acc_key[inst];
+      for (int base = 0; base < cnt; base += kSolveThreads) {
+        const int i = base + tid;
+        bool keep = i < cnt;
+        int rg = 0, zn = -1;
+        double hourly = 0.0, value = 0.0;
+        if (keep) {
+          rg = in.ex.cand_region[off + i];
+          zn = in.ex.cand_zone[off + i];
+          for (int b = D.blocked_begin; b < D.blocked_end; ++b) {
+            const SkyoptBlocked B = in.blocked[b];
+            const bool m = (B.cloud == -1 || B.cloud == S.cloud) &&
+                           (B.inst_id == -1 || B.inst_id == inst) &&
+                           (B.region_id == -1 || B.region_id == rg) &&
+                           (B.zone_id == -1 || B.zone_id == zn) &&
+                           (B.acc_key == -1 || B.acc_key == cand_acc) &&
+                           (B.use_spot == -1 || B.use_spot == S.use_spot);
+            if (m) { keep = false; break; }
+          }
+          // float(hourly_cost * hours) * max(num_nodes - reserved, 0)
+          hourly = __dadd_rn(in.ex.cand_price_a[off + i], in.ex.cand_price_b[off + i]);
+          value = D.minimize_cost
+                      ? __dmul_rn(__dmul_rn(hourly, S.hours), S.node_mult)
+                      : S.time_value;
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int prefix = s_pos;
+        for (int k = 0; k < warp; ++k) prefix += s_wcount[k];
+        if (keep) {
+          const int64_t o = toff + prefix + __popc(bal & ((1u << lane) - 1u));
+          w.tc_ref[o] = (int32_t)(off + i);
+          w.tc_slot[o] = s;
+          w.tc_cloud[o] = S.cloud;
+          w.tc_hourly[o] = hourly;
+          w.tc_value[o] = value;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int tot = 0;
+          for (int k = 0; k < kWarps; ++k) tot += s_wcount[k];
+          s_pos += tot;
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      out.task_n[t] = s_pos;
+      if (s_pos == 0 && s_fail < 0) s_fail = t - D.task_begin;
+    }
+    __syncthreads();
+  }
+  if (s_fail >= 0) {
+    if (tid == 0) {
+      SkyoptDagResult r; r.status = 1; r.task_fail = s_fail;
+      r.objective = __longlong_as_double(0x7FF8000000000000ll);
+      out.dag[blockIdx.x] = r;
+    }
+    return;
+  }
+
+  const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+
+  if (D.is_chain) {
+    // ---- Phase B: dp[c] = value[c] + min_p (dp[p] + egress(p, c)); strict
+    // '<' => first minimum in candidate order (optimizer.py:456-470). The
+    // egress term depends on the clouds only, so the inner minimum is taken
+    // once per child cloud -- same additions, same comparisons, same winner.
+    for (int t = D.task_begin; t < D.task_end; ++t) {
+      const SkyoptTask TK = in.tasks[t];
+      const int64_t toff = in.task_off[t];
+      const int n = out.task_n[t];
+      if (TK.n_parents == 0) {
+        if (tid < C) {
+          // parent = dummy source: 0 + egress from the inputs' cloud
+          s_best_val[tid] = TK.src_tariff_begin >= 0 ? in.tariffs[TK.src_tariff_begin + tid] : 0.0;
+          s_best_idx[tid] = 0;
+        }
+      } else {
+        const int tp = D.task_begin + in.parents[TK.parent_begin];
+        const int64_t poff = in.task_off[tp];
+        const int np = out.task_n[tp];
+        const double *tar = in.tariffs + TK.edge_tariff_begin;
+        for (int cc = warp; cc < C; cc += kWarps) {
+          double bv = kInf; int bi = 0x7FFFFFFF;
+          for (int p = lane; p < np; p += 32) {
+            const int cp = w.tc_cloud[poff + p];
+            const double eg = (cp != cc) ? tar[cp] : 0.0;
+            lexmin(bv, bi, __dadd_rn(w.dp[poff + p], eg), p);
+          }
+          for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            lexmin(bv, bi, ov, oi);
+          }
+          if (lane == 0) { s_best_val[cc] = bv; s_best_idx[cc] = bi; }
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < n; c += kSolveThreads) {
+        const int cc = w.tc_cloud[toff + c];
+        w.dp[toff + c] = __dadd_rn(w.tc_value[toff + c], s_best_val[cc]);
+        w.back[toff + c] = s_best_idx[cc];
+      }
+      __syncthreads();
+    }
+    // sink: 0 + min_p dp[p] (egress to the dummy sink is 0)
+    {
+      const int t = D.task_end - 1;
+      const int64_t toff = in.task_off[t];
+      const int n = out.task_n[t];
+      double bv = kInf; int bi = 0x7FFFFFFF;
+      for (int p = tid; p < n; p += kSolveThreads) lexmin(bv, bi, w.dp[toff + p], p);
+      for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        lexmin(bv, bi, ov, oi);
+      }
+      if (lane == 0) { s_red_val[warp] = bv; s_red_idx[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int k = 1; k < kWarps; ++k) lexmin(bv, bi, s_red_val[k], (int)s_red_idx[k]);
+        SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = bv;
+        out.dag[blockIdx.x] = r;
+        int idx = bi;
+        for (int tt = D.task_end - 1; tt >= D.task_begin; --tt) {
+          out.chosen_index[tt] = idx;
+          idx = w.back[in.task_off[tt] + idx];
+        }
+      }
+    }
+  } else {
+    // ---- Phase B': exact search replacing the PuLP/CBC ILP
+    // (optimizer.py:490-637). Egress depends on (cloud_u, cloud_v) only, so
+    // within one cloud the cheapest candidate of a task dominates; what is
+    // left is an exhaustive enumeration of cloud assignments.
+    if (T > kMaxDagTasks) {
+      if (tid == 0) {
+        SkyoptDagResult r; r.status = 2; r.task_fail = -1;
+        r.objective = __longlong_as_double(0x7FF8000000000000ll);
+        out.dag[blockIdx.x] = r;
+      }
+      return;
+    }
+    for (int lt = warp; lt < T; lt += kWarps) {
+      const int t = D.task_begin + lt;
+      const int64_t toff = in.task_off[t];
+      const int n = out.task_n[t];
+      for (int cc = 0; cc < C; ++cc) {
+        double bv = kInf; int bi = 0x7FFFFFFF;
+        for (int p = lane; p < n; p += 32)
+          if (w.tc_cloud[toff + p] == cc) lexmin(bv, bi, w.tc_value[toff + p], p);
+        for (int o = 16; o; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+          const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+          lexmin(bv, bi, ov, oi);
+        }
+        if (lane == 0) { s_tb_val[lt][cc] = bv; s_tb_idx[lt][cc] = bi; }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        // options ordered by the candidate index of their representative
+        int no = 0;
+        for (int cc = 0; cc < C; ++cc)
+          if (s_tb_idx[lt][cc] != 0x7FFFFFFF) s_opt[lt][no++] = cc;
+        for (int a = 1; a < no; ++a) {
+          const int v = s_opt[lt][a]; int b2 = a - 1;
+          while (b2 >= 0 && s_tb_idx[lt][s_opt[lt][b2]] > s_tb_idx[lt][v]) { s_opt[lt][b2 + 1] = s_opt[lt][b2]; --b2; }
+          s_opt[lt][b2 + 1] = v;
+        }
+        s_nopt[lt] = no;
+      }
+    }
+    __syncthreads();
+    long long total = 1;
+    bool too_big = false;
+    for (int lt = 0; lt < T; ++lt) {
+      total *= s_nopt[lt];
+      if (total > (1ll << 36)) { too_big = true; break; }
+    }
+    if (too_big) {
+      if (tid == 0) {
+        SkyoptDagResult r; r.status = 2; r.task_fail = -1;
+        r.objective = __longlong_as_double(0x7FF8000000000000ll);
+        out.dag[blockIdx.x] = r;
+      }
+      return;
+    }
+    double bv = kInf; long long bid = 0x7FFFFFFFFFFFFFFFll;
+    for (long long id = tid; id < total; id += kSolveThreads) {
+      int cl[kMaxDagTasks];
+      long long rem = id;
+      for (int lt = T - 1; lt >= 0; --lt) {  // task 0 = most significant digit
+        const int no = s_nopt[lt];
+        cl[lt] = s_opt[lt][(int)(rem % no)];
+        rem /= no;
+      }
+      double obj;
+      if (D.minimize_cost) {
+        obj = 0.0;
+        for (int lt = 0; lt < T; ++lt) obj = __dadd_rn(obj, s_tb_val[lt][cl[lt]]);
+        for (int lt = 0; lt < T; ++lt) {
+          const SkyoptTask TK = in.tasks[D.task_begin + lt];
+          if (TK.n_parents == 0 && TK.src_tariff_begin >= 0)
+            obj = __dadd_rn(obj, in.tariffs[TK.src_tariff_begin + cl[lt]]);
+          for (int k = 0; k < TK.n_parents; ++k) {
+            const int lp = in.parents[TK.parent_begin + k];
+            if (cl[lp] != cl[lt])
+              obj = __dadd_rn(obj, in.tariffs[TK.edge_tariff_begin + k * C + cl[lp]]);
+          }
+        }
+      } else {
+        double fin[kMaxDagTasks];
+        obj = 0.0;
+        for (int lt = 0; lt < T; ++lt) {
+          const SkyoptTask TK = in.tasks[D.task_begin + lt];
+          double start = 0.0;
+          if (TK.n_parents == 0 && TK.src_tariff_begin >= 0)
+            start = fmax(start, in.tariffs[TK.src_tariff_begin + cl[lt]]);
+          for (int k = 0; k < TK.n_parents; ++k) {
+            const int lp = in.parents[TK.parent_begin + k];
+            const double eg = (cl[lp] != cl[lt])
+                                  ? in.tariffs[TK.edge_tariff_begin + k * C + cl[lp]] : 0.0;
+            start = fmax(start, __dadd_rn(fin[lp], eg));
+          }
+          fin[lt] = __dadd_rn(s_tb_val[lt][cl[lt]], start);
+          obj = fmax(obj, fin[lt]);  // sink waits for every leaf
+        }
+      }
+      if (obj < bv || (obj == bv && id < bid)) { bv = obj; bid = id; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+      const long long oi = __shfl_xor_sync(0xFFFFFFFFu, bid, o);
+      if (ov < bv || (ov == bv && oi < bid)) { bv = ov; bid = oi; }
+    }
+    if (lane == 0) { s_red_val[warp] = bv; s_red_idx[warp] = bid; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < kWarps; ++k)
+        if (s_red_val[k] < bv || (s_red_val[k] == bv && s_red_idx[k] < bid)) { bv = s_red_val[k]; bid = s_red_idx[k]; }
+      SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = bv;
+      out.dag[blockIdx.x] = r;
+      long long rem = bid;
+      for (int lt = T - 1; lt >= 0; --lt) {
+        const int no = s_nopt[lt];
+        const int cc = s_opt[lt][(int)(rem % no)];
+        rem /= no;
+        out.chosen_index[D.task_begin + lt] = s_tb_idx[lt][cc];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- the plan as candidate records
+  for (int lt = tid; lt < T; lt += kSolveThreads) {
+    const int t = D.task_begin + lt;
+    const int64_t o = in.task_off[t] + out.chosen_index[t];
+    const int64_t ref = w.tc_ref[o];
+    const int s = w.tc_slot[o];
+    SkyoptCandidate c;
+    c.slot = s;
+    c.inst_id = in.ex.slot_inst[s];
+    c.region_id = in.ex.cand_region[ref];
+    c.zone_id = in.ex.cand_zone[ref];
+    c.hourly = w.tc_hourly[o];
+    c.value = w.tc_value[o];
+    out.chosen[t] = c;
+  }
+}
+
+// Optional full candidate tables (display / _fill_in_launchable_resources).
+__global__ void table_kernel(SolveIn in, SolveWork w, const int32_t *task_n,
+                             int n_tasks, const int64_t *__restrict__ out_off,
+                             SkyoptCandidate *__restrict__ table) {
+  const int t = blockIdx.x;
+  if (t >= n_tasks) return;
+  const int n = task_n[t];
+  const int64_t toff = in.task_off[t];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t o = toff + i;
+    const int64_t ref = w.tc_ref[o];
+    const int s = w.tc_slot[o];
+    SkyoptCandidate c;
+    c.slot = s;
+    c.inst_id = in.ex.slot_inst[s];
+    c.region_id = in.ex.cand_region[ref];
+    c.zone_id = in.ex.cand_zone[ref];
+    c.hourly = w.tc_hourly[o];
+    c.value = w.tc_value[o];
+    table[out_off[t] + i] = c;
+  }
+}
+
+// Evict the catalog from L2 between timed iterations (bench.py).
+__global__ void flush_kernel(uint32_t *buf, int64_t n, uint32_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    buf[i] = v + (uint32_t)i;
+}
+
+}  // namespace skyopt

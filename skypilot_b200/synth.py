@@ -1,0 +1,590 @@
+"""Seeded synthetic instance catalogs in the reference's on-disk schema.
+
+The public multi-cloud catalog is downloaded at first use by the reference
+(sky/catalog/common.py:213-214) and is not obtainable offline, so every parity
+test and bench line runs on catalogs produced here. The column sets follow the
+reference's data fetchers (fetch_aws.py:69-85, fetch_azure.py:106-109,
+fetch_gcp.py:805-816, fetch_lambda_cloud.py:81) and the generator honours the
+invariants the reference asserts on its catalogs:
+
+  * one row per (InstanceType, AvailabilityZone)        (common.py:385)
+  * on-demand Price identical across a region's zones   (common.py:392)
+  * vCPUs / MemoryGiB unique per InstanceType           (common.py:417-423)
+  * zone names unique across regions                    (common.py:355)
+  * Azure / Lambda have no zones                        (azure.py:283-299)
+
+Prices are distinct per (cloud, instance type, region) and spot prices are
+distinct per row so that no decision depends on the reference's unstable
+single-key sort (SURVEY.md "Hard parts"); `tie_suite=True` removes that
+guarantee on purpose.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+AWS_COLUMNS = [
+    'InstanceType', 'AcceleratorName', 'AcceleratorCount', 'vCPUs',
+    'MemoryGiB', 'GpuInfo', 'Price', 'SpotPrice', 'Region', 'AvailabilityZone',
+    'Arch', 'LocalDiskType', 'NVMeSupported', 'LocalDiskSize', 'LocalDiskCount'
+]
+GCP_COLUMNS = [
+    'InstanceType', 'vCPUs', 'MemoryGiB', 'AcceleratorName',
+    'AcceleratorCount', 'GpuInfo', 'Region', 'AvailabilityZone', 'Price',
+    'SpotPrice'
+]
+AZURE_COLUMNS = [
+    'InstanceType', 'AcceleratorName', 'AcceleratorCount', 'vCPUs',
+    'MemoryGiB', 'GpuInfo', 'Price', 'SpotPrice', 'Region', 'Generation'
+]
+LAMBDA_COLUMNS = [
+    'InstanceType', 'AcceleratorName', 'AcceleratorCount', 'vCPUs',
+    'MemoryGiB', 'Price', 'Region', 'GpuInfo', 'SpotPrice'
+]
+
+_AWS_REGIONS = [
+    'us-east-1', 'us-east-2', 'us-west-1', 'us-west-2', 'ca-central-1',
+    'eu-west-1', 'eu-west-2', 'eu-west-3', 'eu-central-1', 'eu-north-1',
+    'eu-south-1', 'ap-south-1', 'ap-northeast-1', 'ap-northeast-2',
+    'ap-northeast-3', 'ap-southeast-1', 'ap-southeast-2', 'ap-east-1',
+    'sa-east-1', 'me-south-1'
+]
+_GCP_REGIONS = [
+    'us-central1', 'us-east1', 'us-east4', 'us-west1', 'us-west2', 'us-west4',
+    'europe-west1', 'europe-west2', 'europe-west4', 'europe-north1',
+    'asia-east1', 'asia-northeast1', 'asia-southeast1', 'asia-south1',
+    'australia-southeast1', 'southamerica-east1'
+]
+_AZURE_REGIONS = [
+    'eastus', 'eastus2', 'westus', 'westus2', 'westus3', 'centralus',
+    'northcentralus', 'southcentralus', 'westcentralus', 'canadacentral',
+    'northeurope', 'westeurope', 'uksouth', 'francecentral', 'japaneast',
+    'southeastasia', 'australiaeast', 'koreacentral'
+]
+_LAMBDA_REGIONS = [
+    'us-east-1', 'us-west-1', 'us-west-2', 'us-south-1', 'us-midwest-1',
+    'europe-central-1', 'asia-northeast-1', 'asia-south-1', 'me-west-1'
+]
+
+_SIZES = [('large', 2), ('xlarge', 4), ('2xlarge', 8), ('4xlarge', 16),
+          ('8xlarge', 32), ('12xlarge', 48), ('16xlarge', 64),
+          ('24xlarge', 96), ('32xlarge', 128)]
+
+# (family, memory GiB per vCPU, $/vCPU-hour, local nvme GB per vCPU or 0)
+_AWS_CPU_FAMILIES = [
+    ('m6i', 4, 0.048, 0), ('m6id', 4, 0.0593, 59), ('m7i', 4, 0.0504, 0),
+    ('r6i', 8, 0.063, 0), ('r6id', 8, 0.0756, 59), ('r7i', 8, 0.0662, 0),
+    ('c6i', 2, 0.0425, 0), ('c6id', 2, 0.0504, 59), ('c7i', 2, 0.0446, 0),
+    ('t3', 4, 0.0416, 0), ('m5', 4, 0.0481, 0), ('c5', 2, 0.0426, 0),
+    ('r5', 8, 0.0631, 0), ('m5d', 4, 0.0565, 37), ('m6a', 4, 0.0432, 0),
+    ('c6a', 2, 0.0383, 0), ('r6a', 8, 0.0567, 0), ('i3', 7.625, 0.078, 237),
+    ('m6g', 4, 0.0385, 0), ('c6g', 2, 0.034, 0)
+]
+# (instance type, accelerator, count, vCPUs, MemoryGiB, $/h, gpu mem MiB,
+#  local disk GB total (0 = none))
+_AWS_GPU_TYPES = [
+    ('p3.2xlarge', 'V100', 1, 8, 61, 3.06, 16384, 0),
+    ('p3.8xlarge', 'V100', 4, 32, 244, 12.24, 16384, 0),
+    ('p3.16xlarge', 'V100', 8, 64, 488, 24.48, 16384, 0),
+    ('p3dn.24xlarge', 'V100-32GB', 8, 96, 768, 31.212, 32768, 1800),
+    ('p4d.24xlarge', 'A100', 8, 96, 1152, 32.7726, 40960, 8000),
+    ('p4de.24xlarge', 'A100-80GB', 8, 96, 1152, 40.9657, 81920, 8000),
+    ('p5.48xlarge', 'H100', 8, 192, 2048, 98.32, 81920, 30400),
+    ('p5e.48xlarge', 'H200', 8, 192, 2048, 108.152, 144384, 30400),
+    ('g4dn.xlarge', 'T4', 1, 4, 16, 0.526, 15360, 125),
+    ('g4dn.2xlarge', 'T4', 1, 8, 32, 0.752, 15360, 225),
+    ('g4dn.4xlarge', 'T4', 1, 16, 64, 1.204, 15360, 225),
+    ('g4dn.8xlarge', 'T4', 1, 32, 128, 2.176, 15360, 900),
+    ('g4dn.16xlarge', 'T4', 1, 64, 256, 4.352, 15360, 900),
+    ('g4dn.12xlarge', 'T4', 4, 48, 192, 3.912, 15360, 900),
+    ('g4dn.metal', 'T4', 8, 96, 384, 7.824, 15360, 1800),
+    ('g5.xlarge', 'A10G', 1, 4, 16, 1.006, 24576, 250),
+    ('g5.2xlarge', 'A10G', 1, 8, 32, 1.212, 24576, 450),
+    ('g5.4xlarge', 'A10G', 1, 16, 64, 1.624, 24576, 600),
+    ('g5.8xlarge', 'A10G', 1, 32, 128, 2.448, 24576, 900),
+    ('g5.16xlarge', 'A10G', 1, 64, 256, 4.096, 24576, 1900),
+    ('g5.12xlarge', 'A10G', 4, 48, 192, 5.672, 24576, 3800),
+    ('g5.24xlarge', 'A10G', 4, 96, 384, 8.144, 24576, 3800),
+    ('g5.48xlarge', 'A10G', 8, 192, 768, 16.288, 24576, 7600),
+    ('g6.xlarge', 'L4', 1, 4, 16, 0.8048, 23034, 250),
+    ('g6.2xlarge', 'L4', 1, 8, 32, 0.9776, 23034, 450),
+    ('g6.4xlarge', 'L4', 1, 16, 64, 1.3232, 23034, 600),
+    ('g6.12xlarge', 'L4', 4, 48, 192, 4.6016, 23034, 3760),
+    ('g6.48xlarge', 'L4', 8, 192, 768, 13.3504, 23034, 7520),
+    ('p2.xlarge', 'K80', 1, 4, 61, 0.9, 12288, 0),
+    ('p2.8xlarge', 'K80', 8, 32, 488, 7.2, 12288, 0),
+    ('p2.16xlarge', 'K80', 16, 64, 732, 14.4, 12288, 0),
+    ('inf1.xlarge', 'Inferentia', 1, 4, 8, 0.228, 8192, 0),
+    ('inf2.xlarge', 'Inferentia2', 1, 4, 16, 0.7582, 32768, 0),
+    ('trn1.2xlarge', 'Trainium', 1, 8, 32, 1.3438, 32768, 475),
+    ('trn1.32xlarge', 'Trainium', 16, 128, 512, 21.5, 32768, 7600),
+]
+_FILLER_ACCS = [('A10G', 24576), ('L4', 23034), ('T4', 15360),
+                ('V100', 16384), ('A100', 40960), ('H100', 81920),
+                ('L40S', 46068), ('RTX6000', 24576), ('A100-80GB', 81920),
+                ('H200', 144384), ('Gaudi', 32768), ('M60', 8192)]
+
+_GCP_VM_FAMILIES = [
+    # (family prefix, sizes, GiB per vCPU, $/vCPU-hour)
+    ('n1-standard', [1, 2, 4, 8, 16, 32, 64, 96], 3.75, 0.0475),
+    ('n1-highmem', [2, 4, 8, 16, 32, 64, 96], 6.5, 0.0592),
+    ('n1-highcpu', [2, 4, 8, 16, 32, 64, 96], 0.9, 0.0354),
+    ('n2-standard', [2, 4, 8, 16, 32, 48, 64, 80, 96, 128], 4, 0.0486),
+    ('n2-highmem', [2, 4, 8, 16, 32, 48, 64, 80, 96, 128], 8, 0.0655),
+    ('n2-highcpu', [2, 4, 8, 16, 32, 48, 64, 80, 96], 1, 0.0359),
+    ('n4-standard', [2, 4, 8, 16, 32, 48, 64, 80], 4, 0.0474),
+    ('n4-highmem', [2, 4, 8, 16, 32, 48, 64, 80], 8, 0.0622),
+    ('n4-highcpu', [2, 4, 8, 16, 32, 48, 64, 80], 2, 0.0408),
+    ('e2-standard', [2, 4, 8, 16, 32], 4, 0.0335),
+    ('c2-standard', [4, 8, 16, 30, 60], 4, 0.0522),
+    ('t2d-standard', [1, 2, 4, 8, 16, 32, 48, 60], 4, 0.0422),
+    ('c3-standard', [4, 8, 22, 44, 88, 176], 4, 0.0523),
+    ('m1-ultramem', [40, 80, 160], 24.025, 0.157),
+]
+# Host VMs that GCP pairs with a fixed accelerator
+# (reference gcp_catalog.py:90-131): (instance type, vCPUs, MemoryGiB, $/h).
+_GCP_ACC_HOST_VMS = [
+    ('a2-highgpu-1g', 12, 85, 0.7357), ('a2-highgpu-2g', 24, 170, 1.4714),
+    ('a2-highgpu-4g', 48, 340, 2.9428), ('a2-highgpu-8g', 96, 680, 5.8856),
+    ('a2-megagpu-16g', 96, 1360, 8.7964), ('a2-ultragpu-1g', 12, 170, 1.1465),
+    ('a2-ultragpu-2g', 24, 340, 2.293), ('a2-ultragpu-4g', 48, 680, 4.586),
+    ('a2-ultragpu-8g', 96, 1360, 9.172), ('g2-standard-4', 4, 16, 0.1498),
+    ('g2-standard-8', 8, 32, 0.2996), ('g2-standard-12', 12, 48, 0.4494),
+    ('g2-standard-16', 16, 64, 0.5992), ('g2-standard-32', 32, 128, 1.1984),
+    ('g2-standard-24', 24, 96, 0.8988), ('g2-standard-48', 48, 192, 1.7976),
+    ('g2-standard-96', 96, 384, 3.5952), ('a3-highgpu-1g', 26, 234, 1.5221),
+    ('a3-highgpu-2g', 52, 468, 3.0442), ('a3-highgpu-4g', 104, 936, 6.0884),
+    ('a3-highgpu-8g', 208, 1872, 12.1768),
+    ('a3-megagpu-8g', 208, 1872, 13.2142),
+    ('a3-ultragpu-8g', 224, 2952, 14.9563),
+    ('a4-highgpu-8g', 224, 3968, 17.3312)
+]
+# (name, counts, $/h per accelerator)
+_GCP_ACCELERATORS = [
+    ('T4', [1, 2, 4], 0.35), ('V100', [1, 2, 4, 8], 2.48),
+    ('P100', [1, 2, 4], 1.46), ('K80', [1, 2, 4, 8], 0.45),
+    ('P4', [1, 2, 4], 0.6), ('A100', [1, 2, 4, 8, 16], 2.9339),
+    ('A100-80GB', [1, 2, 4, 8], 3.9295), ('L4', [1, 2, 4, 8], 0.5604),
+    ('H100', [1, 2, 4, 8], 9.7965), ('H100-MEGA', [8], 10.18),
+    ('H200', [8], 10.8452), ('B200', [8], 13.9)
+]
+_GCP_TPUS = [('tpu-v2-8', 4.5), ('tpu-v3-8', 8.0), ('tpu-v4-8', 12.88),
+             ('tpu-v5litepod-4', 4.8), ('tpu-v2-32', 24.0),
+             ('tpu-v3-32', 32.0)]
+
+# (instance type, acc, count, vCPUs, MemoryGiB, $/h, generation)
+_AZURE_GPU_TYPES = [
+    ('Standard_NC6s_v3', 'V100', 1, 6, 112, 3.06, 'V2'),
+    ('Standard_NC12s_v3', 'V100', 2, 12, 224, 6.12, 'V2'),
+    ('Standard_NC24s_v3', 'V100', 4, 24, 448, 12.24, 'V2'),
+    ('Standard_NC24rs_v3', 'V100', 4, 24, 448, 13.46, 'V2'),
+    ('Standard_ND40rs_v2', 'V100-32GB', 8, 40, 672, 22.032, 'V2'),
+    ('Standard_NC4as_T4_v3', 'T4', 1, 4, 28, 0.5263, 'V2'),
+    ('Standard_NC8as_T4_v3', 'T4', 1, 8, 56, 0.752, 'V2'),
+    ('Standard_NC16as_T4_v3', 'T4', 1, 16, 110, 1.204, 'V2'),
+    ('Standard_NC64as_T4_v3', 'T4', 4, 64, 440, 4.352, 'V2'),
+    ('Standard_ND96asr_v4', 'A100', 8, 96, 900, 27.197, 'V2'),
+    ('Standard_ND96amsr_A100_v4', 'A100-80GB', 8, 96, 1924, 32.77, 'V2'),
+    ('Standard_NC24ads_A100_v4', 'A100-80GB', 1, 24, 220, 3.673, 'V2'),
+    ('Standard_NC48ads_A100_v4', 'A100-80GB', 2, 48, 440, 7.346, 'V2'),
+    ('Standard_NC96ads_A100_v4', 'A100-80GB', 4, 96, 880, 14.692, 'V2'),
+    ('Standard_NV6ads_A10_v5', 'A10', 0.167, 6, 55, 0.454, 'V2'),
+    ('Standard_NV12ads_A10_v5', 'A10', 0.333, 12, 110, 0.908, 'V2'),
+    ('Standard_NV18ads_A10_v5', 'A10', 0.5, 18, 220, 1.6, 'V2'),
+    ('Standard_NV36ads_A10_v5', 'A10', 1, 36, 440, 3.2, 'V2'),
+    ('Standard_NV72ads_A10_v5', 'A10', 2, 72, 880, 6.52, 'V2'),
+    ('Standard_ND96isr_H100_v5', 'H100', 8, 96, 1900, 98.32, 'V2'),
+    ('Standard_NC6', 'K80', 1, 6, 56, 0.9, 'V1'),
+    ('Standard_NC12', 'K80', 2, 12, 112, 1.8, 'V1'),
+    ('Standard_NC24', 'K80', 4, 24, 224, 3.6, 'V1'),
+    ('Standard_NV6', 'M60', 1, 6, 56, 1.14, 'V1'),
+]
+# (name pattern with {n}, sizes, GiB per vCPU, $/vCPU-hour, generation)
+_AZURE_CPU_FAMILIES = [
+    ('Standard_D{n}s_v5', [2, 4, 8, 16, 32, 48, 64, 96], 4, 0.048, 'V2'),
+    ('Standard_E{n}s_v5', [2, 4, 8, 16, 20, 32, 48, 64, 96], 8, 0.063, 'V2'),
+    ('Standard_F{n}s_v2', [2, 4, 8, 16, 32, 48, 64, 72], 2, 0.0423, 'V2'),
+    ('Standard_D{n}_v5', [2, 4, 8, 16, 32, 48, 64, 96], 4, 0.0479, 'V2'),
+    ('Standard_D{n}s_v3', [2, 4, 8, 16, 32, 48, 64], 4, 0.0481, 'V1'),
+    ('Standard_D{n}as_v4', [2, 4, 8, 16, 32, 48, 64, 96], 4, 0.0478, 'V1'),
+    ('Standard_E{n}_v3', [2, 4, 8, 16, 20, 32, 48, 64], 8, 0.0632, 'V1'),
+    ('Standard_B{n}ms', [1, 2, 4, 8, 12, 16, 20], 4, 0.0417, 'V1'),
+    ('Standard_L{n}s_v3', [8, 16, 32, 48, 64, 80], 8, 0.078, 'V2'),
+]
+
+_LAMBDA_TYPES = [
+    ('gpu_1x_a10', 'A10', 1, 30, 200, 0.75),
+    ('gpu_1x_a100', 'A100', 1, 30, 200, 1.29),
+    ('gpu_1x_a100_sxm4', 'A100', 1, 30, 220, 1.2901),
+    ('gpu_2x_a100', 'A100', 2, 60, 400, 2.58),
+    ('gpu_4x_a100', 'A100', 4, 120, 800, 5.16),
+    ('gpu_8x_a100', 'A100', 8, 124, 1800, 10.32),
+    ('gpu_8x_a100_80gb_sxm4', 'A100-80GB', 8, 240, 1800, 14.32),
+    ('gpu_1x_h100_pcie', 'H100', 1, 26, 200, 2.49),
+    ('gpu_1x_h100_sxm5', 'H100', 1, 26, 225, 3.29),
+    ('gpu_8x_h100_sxm5', 'H100', 8, 208, 1800, 23.92),
+    ('gpu_8x_v100', 'V100', 8, 92, 448, 4.4),
+    ('gpu_1x_rtx6000', 'RTX6000', 1, 14, 46, 0.5),
+    ('gpu_1x_a6000', 'A6000', 1, 14, 100, 0.8),
+    ('gpu_2x_a6000', 'A6000', 2, 28, 200, 1.6),
+    ('gpu_4x_a6000', 'A6000', 4, 56, 400, 3.2),
+    ('gpu_1x_gh200', 'GH200', 1, 64, 432, 1.49),
+    ('gpu_8x_b200_sxm6', 'B200', 8, 208, 2900, 39.92),
+    ('cpu_4x_general', None, None, 4, 16, 0.08),
+    ('cpu_32x_general', None, None, 32, 128, 0.64),
+]
+
+
+def _gpu_info(name: str, count, mem_mib: int) -> str:
+    # Shape of the AWS GpuInfo column (a stringified dict; the reference only
+    # literal_evals it in list_accelerators_impl, common.py:721-723).
+    return str({
+        'Gpus': [{
+            'Name': name,
+            'Manufacturer': 'NVIDIA',
+            'Count': count,
+            'MemoryInfo': {
+                'SizeInMiB': mem_mib
+            }
+        }],
+        'TotalGpuMemoryInMiB': int(mem_mib * count)
+    })
+
+
+class _PriceBook:
+    """Hands out prices that are pairwise distinct at a fixed rounding."""
+
+    def __init__(self, decimals: int, distinct: bool):
+        self._decimals = decimals
+        self._step = 10.0**(-decimals)
+        self._distinct = distinct
+        self._seen = set()
+
+    def take(self, value: float) -> float:
+        key = int(round(max(value, self._step) * 10**self._decimals))
+        if self._distinct:
+            while key in self._seen:
+                key += 1
+            self._seen.add(key)
+        return round(key * self._step, self._decimals)
+
+
+def _zones_for(rng, regions: Sequence[str], lo: int, hi: int,
+               style: str) -> Dict[str, List[str]]:
+    out = {}
+    for region in regions:
+        n = int(rng.integers(lo, hi + 1))
+        letters = 'abcdef'[:n]
+        if style == 'aws':
+            out[region] = [f'{region}{c}' for c in letters]
+        else:
+            out[region] = [f'{region}-{c}' for c in letters]
+    return out
+
+
+def _region_multipliers(rng, regions: Sequence[str]) -> Dict[str, float]:
+    mult = {r: float(1.0 + 0.02 * i + rng.uniform(0.0, 0.015))
+            for i, r in enumerate(regions)}
+    return mult
+
+
+def _spot(rng, book: Optional[_PriceBook], price: float,
+          nan_prob: float) -> float:
+    if rng.uniform() < nan_prob:
+        return float('nan')
+    value = price * float(rng.uniform(0.2, 0.5))
+    return book.take(value) if book is not None else value
+
+
+def _filler_types(rng, n_types: int, style: str) -> List[Tuple]:
+    """Extra instance types to reach a requested catalog size.
+
+    Returns (name, acc, count, vcpus, mem, price, gpu_mem) tuples; names never
+    collide with a default family of the cloud (they are not candidates of the
+    CPU branch) but their accelerators take part in the accelerator branch.
+    """
+    out = []
+    fam = 0
+    while len(out) < n_types:
+        fam += 1
+        is_gpu = rng.uniform() < 0.35
+        ratio = float(rng.choice([2, 4, 8]))
+        per_cpu = float(rng.uniform(0.03, 0.09))
+        if is_gpu:
+            acc, gmem = _FILLER_ACCS[int(rng.integers(len(_FILLER_ACCS)))]
+            per_gpu = float(rng.uniform(0.4, 9.0))
+        for si, (size, vcpus) in enumerate(_SIZES):
+            if len(out) >= n_types:
+                break
+            if style == 'aws':
+                name = f'z{fam}{"g" if is_gpu else "a"}.{size}'
+            elif style == 'gcp':
+                name = f'zz{fam}-standard-{vcpus}'
+            else:
+                name = f'Standard_Z{vcpus}zf{fam}_v9'
+            if is_gpu:
+                count = [1, 1, 1, 2, 4, 4, 8, 8, 8][si]
+                out.append((name, acc, count, vcpus, vcpus * ratio,
+                            vcpus * per_cpu + count * per_gpu, gmem))
+            else:
+                out.append((name, None, None, vcpus, vcpus * ratio,
+                            vcpus * per_cpu, 0))
+    return out
+
+
+def make_aws(rng,
+             n_rows: int,
+             decimals: int = 4,
+             distinct: bool = True) -> pd.DataFrame:
+    zones = _zones_for(rng, _AWS_REGIONS, 2, 6, 'aws')
+    mult = _region_multipliers(rng, _AWS_REGIONS)
+    zones_total = sum(len(z) for z in zones.values())
+    types: List[Tuple] = []
+    for fam, ratio, per_cpu, disk_per_cpu in _AWS_CPU_FAMILIES:
+        for size, vcpus in _SIZES:
+            if fam == 't3' and vcpus > 8:
+                continue
+            arch = 'arm64' if fam.endswith('g') else 'x86_64'
+            types.append((f'{fam}.{size}', None, None, vcpus, vcpus * ratio,
+                          vcpus * per_cpu, 0, disk_per_cpu * vcpus, arch))
+    for (name, acc, cnt, vcpus, mem, price, gmem, disk) in _AWS_GPU_TYPES:
+        types.append((name, acc, cnt, vcpus, mem, price, gmem, disk, 'x86_64'))
+    avail = 0.85
+    want = int(max(0, n_rows / (zones_total * avail) - len(types)))
+    for (name, acc, cnt, vcpus, mem, price, gmem) in _filler_types(
+            rng, want, 'aws'):
+        types.append((name, acc, cnt, vcpus, mem, price, gmem, 0, 'x86_64'))
+
+    book = _PriceBook(decimals, distinct)
+    spot_book = _PriceBook(decimals + 2, distinct)
+    rows = []
+    for (name, acc, cnt, vcpus, mem, base, gmem, disk, arch) in types:
+        is_default = name.split('.')[0] in {f[0] for f in _AWS_CPU_FAMILIES[:9]}
+        for region in _AWS_REGIONS:
+            # The default families are offered everywhere so that the CPU
+            # branch always has an answer; the rest come and go per region.
+            if not is_default and rng.uniform() > avail:
+                continue
+            price = book.take(base * mult[region])
+            for zone in zones[region]:
+                if not is_default and rng.uniform() > 0.92:
+                    continue
+                rows.append({
+                    'InstanceType': name,
+                    'AcceleratorName': acc,
+                    'AcceleratorCount': cnt,
+                    'vCPUs': float(vcpus),
+                    'MemoryGiB': float(mem),
+                    'GpuInfo': _gpu_info(acc, cnt, gmem) if acc else None,
+                    'Price': price,
+                    'SpotPrice': _spot(rng, spot_book, price, 0.08),
+                    'Region': region,
+                    'AvailabilityZone': zone,
+                    'Arch': arch,
+                    'LocalDiskType': 'ssd' if disk else None,
+                    'NVMeSupported': True if disk else None,
+                    'LocalDiskSize': float(disk) if disk else None,
+                    'LocalDiskCount': 1.0 if disk else None,
+                })
+    return pd.DataFrame(rows, columns=AWS_COLUMNS)
+
+
+def make_gcp(rng,
+             n_rows: int,
+             decimals: int = 4,
+             distinct: bool = True) -> pd.DataFrame:
+    zones = _zones_for(rng, _GCP_REGIONS, 2, 4, 'gcp')
+    mult = _region_multipliers(rng, _GCP_REGIONS)
+    zones_total = sum(len(z) for z in zones.values())
+    vm_types: List[Tuple] = []
+    for fam, sizes, ratio, per_cpu in _GCP_VM_FAMILIES:
+        for n in sizes:
+            vm_types.append((f'{fam}-{n}', n, n * ratio, n * per_cpu))
+    for name, vcpus, mem, price in _GCP_ACC_HOST_VMS:
+        vm_types.append((name, vcpus, mem, price))
+    n_acc_rows = sum(len(c) for _, c, _ in _GCP_ACCELERATORS) + len(_GCP_TPUS)
+    avail = 0.8
+    want = int(
+        max(0, n_rows / (zones_total * avail) - len(vm_types) -
+            n_acc_rows * 0.6))
+    for (name, _, _, vcpus, mem, price, _) in _filler_types(rng, want, 'gcp'):
+        vm_types.append((name, vcpus, mem, price))
+
+    book = _PriceBook(decimals, distinct)
+    spot_book = _PriceBook(decimals + 2, distinct)
+    rows = []
+    for name, vcpus, mem, base in vm_types:
+        everywhere = name.startswith(('n1-', 'n2-', 'n4-'))
+        for region in _GCP_REGIONS:
+            if not everywhere and rng.uniform() > avail:
+                continue
+            price = book.take(base * mult[region])
+            for zone in zones[region]:
+                if not everywhere and rng.uniform() > 0.9:
+                    continue
+                rows.append({
+                    'InstanceType': name,
+                    'vCPUs': float(vcpus),
+                    'MemoryGiB': float(mem),
+                    'AcceleratorName': None,
+                    'AcceleratorCount': None,
+                    'GpuInfo': None,
+                    'Region': region,
+                    'AvailabilityZone': zone,
+                    'Price': price,
+                    'SpotPrice': _spot(rng, spot_book, price, 0.03),
+                })
+    # Accelerator rows: no InstanceType, priced per (name, count, zone)
+    # (reference fetch_gcp.py:482-486, :599-606).
+    for acc, counts, per_acc in _GCP_ACCELERATORS:
+        for cnt in counts:
+            for region in _GCP_REGIONS:
+                if rng.uniform() > 0.6:
+                    continue
+                price = book.take(per_acc * cnt * mult[region])
+                all_nan_spot = rng.uniform() < 0.1
+                for zone in zones[region]:
+                    if rng.uniform() > 0.8:
+                        continue
+                    rows.append({
+                        'InstanceType': None,
+                        'vCPUs': None,
+                        'MemoryGiB': None,
+                        'AcceleratorName': acc,
+                        'AcceleratorCount': float(cnt),
+                        'GpuInfo': acc,
+                        'Region': region,
+                        'AvailabilityZone': zone,
+                        'Price': price,
+                        'SpotPrice': float('nan') if all_nan_spot else _spot(
+                            rng, spot_book, price, 0.05),
+                    })
+    for acc, per_acc in _GCP_TPUS:
+        for region in _GCP_REGIONS:
+            if rng.uniform() > 0.3:
+                continue
+            price = book.take(per_acc * mult[region])
+            for zone in zones[region][:2]:
+                rows.append({
+                    'InstanceType': None,
+                    'vCPUs': None,
+                    'MemoryGiB': None,
+                    'AcceleratorName': acc,
+                    'AcceleratorCount': 1.0,
+                    'GpuInfo': acc,
+                    'Region': region,
+                    'AvailabilityZone': zone,
+                    'Price': price,
+                    'SpotPrice': _spot(rng, spot_book, price, 0.05),
+                })
+    return pd.DataFrame(rows, columns=GCP_COLUMNS)
+
+
+def make_azure(rng,
+               n_rows: int,
+               decimals: int = 4,
+               distinct: bool = True) -> pd.DataFrame:
+    mult = _region_multipliers(rng, _AZURE_REGIONS)
+    types: List[Tuple] = []
+    for pattern, sizes, ratio, per_cpu, gen in _AZURE_CPU_FAMILIES:
+        for n in sizes:
+            types.append(
+                (pattern.format(n=n), None, None, n, n * ratio, n * per_cpu,
+                 gen))
+    types.extend(_AZURE_GPU_TYPES)
+    avail = 0.85
+    want = int(max(0, n_rows / (len(_AZURE_REGIONS) * avail) - len(types)))
+    for (name, acc, cnt, vcpus, mem, price, _) in _filler_types(
+            rng, want, 'azure'):
+        types.append((name, acc, cnt, vcpus, mem, price, 'V2'))
+    book = _PriceBook(decimals, distinct)
+    spot_book = _PriceBook(decimals + 2, distinct)
+    defaults = ('Standard_D', 'Standard_E', 'Standard_F')
+    rows = []
+    for (name, acc, cnt, vcpus, mem, base, gen) in types:
+        everywhere = name.startswith(defaults) and name.endswith(
+            ('s_v5', 's_v2'))
+        for region in _AZURE_REGIONS:
+            if not everywhere and rng.uniform() > avail:
+                continue
+            price = book.take(base * mult[region])
+            rows.append({
+                'InstanceType': name,
+                'AcceleratorName': acc,
+                'AcceleratorCount': cnt,
+                'vCPUs': float(vcpus),
+                'MemoryGiB': float(mem),
+                'GpuInfo': acc,
+                'Price': price,
+                'SpotPrice': _spot(rng, spot_book, price, 0.1),
+                'Region': region,
+                'Generation': gen,
+            })
+    return pd.DataFrame(rows, columns=AZURE_COLUMNS)
+
+
+def make_lambda(rng,
+                n_rows: int,
+                decimals: int = 4,
+                distinct: bool = True) -> pd.DataFrame:
+    mult = _region_multipliers(rng, _LAMBDA_REGIONS)
+    types = list(_LAMBDA_TYPES)
+    want = int(max(0, n_rows / (len(_LAMBDA_REGIONS) * 0.8) - len(types)))
+    for (name, acc, cnt, vcpus, mem, price, _) in _filler_types(
+            rng, want, 'aws'):
+        types.append((name.replace('.', '_'), acc, cnt, vcpus, mem, price))
+    book = _PriceBook(decimals, distinct)
+    rows = []
+    for (name, acc, cnt, vcpus, mem, base) in types:
+        for region in _LAMBDA_REGIONS:
+            if rng.uniform() > 0.8:
+                continue
+            rows.append({
+                'InstanceType': name,
+                'AcceleratorName': acc,
+                'AcceleratorCount': cnt,
+                'vCPUs': float(vcpus),
+                'MemoryGiB': float(mem),
+                'Price': book.take(base * mult[region]),
+                'Region': region,
+                'GpuInfo': acc,
+                'SpotPrice': float('nan'),
+            })
+    return pd.DataFrame(rows, columns=LAMBDA_COLUMNS)
+
+
+_MAKERS = {
+    'aws': make_aws,
+    'gcp': make_gcp,
+    'azure': make_azure,
+    'lambda': make_lambda
+}
+
+# AWS 60 %, GCP 25 %, Azure 10 %, Lambda 5 %.
+DEFAULT_SHARES = {'aws': 0.60, 'gcp': 0.25, 'azure': 0.10, 'lambda': 0.05}
+
+
+def make_catalogs(seed: int,
+                  n_rows: int = 50_000,
+                  clouds: Sequence[str] = ('aws', 'gcp', 'azure', 'lambda'),
+                  shares: Optional[Dict[str, float]] = None,
+                  decimals: Optional[int] = None,
+                  tie_suite: bool = False) -> Dict[str, pd.DataFrame]:
+    """Returns `{cloud: vms.csv DataFrame}` totalling roughly `n_rows` rows."""
+    shares = dict(shares or DEFAULT_SHARES)
+    total_share = sum(shares[c] for c in clouds)
+    if decimals is None:
+        decimals = 4 if n_rows <= 200_000 else 6
+    out = {}
+    for i, cloud in enumerate(clouds):
+        rng = np.random.default_rng([seed, i])
+        target = int(n_rows * shares[cloud] / total_share)
+        out[cloud] = _MAKERS[cloud](rng,
+                                    target,
+                                    decimals=2 if tie_suite else decimals,
+                                    distinct=not tie_suite)
+    return out
+
+
+def total_rows(catalogs: Dict[str, pd.DataFrame]) -> int:
+    return int(sum(len(df) for df in catalogs.values()))
