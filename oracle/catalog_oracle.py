@@ -1,0 +1,320 @@
+"""CPU oracle, part 1: the catalog queries, restated with pandas.
+
+TEST INFRASTRUCTURE ONLY. Nothing under skypilot_b200/ imports this module;
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may. It exists to check the CUDA path and to give the
+GPU box (which has no /root/reference) a CPU arm with the reference's
+algorithm and data structures.
+
+Each function restates one reference function (file:line given) on the same
+pandas DataFrames the reference reads from `vms.csv`. Parity pinning: this
+restatement is checked against the UNMODIFIED reference through the committed
+fixtures tests/golden/*.json (tests/test_oracle.py) and against the inline
+golden vectors of the reference's tests/unit_tests/test_catalog.py.
+
+One deliberate difference: single-key `sort_values` calls use kind='stable'
+(ties -> first CSV row) where the reference uses pandas' unstable default;
+the reference's result on price ties is build dependent.
+"""
+import re
+from typing import Dict, List, Optional, Tuple, Union
+
+import pandas as pd
+
+# ---- per-cloud constants (aws_catalog.py:37-67, gcp_catalog.py:41-184,
+# azure_catalog.py:41-59, lambda_catalog.py:24-25) --------------------------
+AWS_FAMILIES = ['m6i', 'm6id', 'm7i', 'r6i', 'r6id', 'r7i', 'c6i', 'c6id',
+                'c7i']
+GCP_FAMILIES = ['n2-standard', 'n2-highmem', 'n2-highcpu', 'n4-standard',
+                'n4-highcpu', 'n4-highmem']
+GCP_HOST_FAMILIES = ('n1-standard', 'n1-highmem', 'n1-highcpu')
+AZURE_FAMILIES = ['Ds_v5', 'Es_v5', 'Fs_v2']
+DEFAULT_CPUS = {'aws': 8, 'gcp': 8, 'azure': 8, 'lambda': 30}
+GCP_FIXED = {
+    'A100': {1: ['a2-highgpu-1g'], 2: ['a2-highgpu-2g'],
+             4: ['a2-highgpu-4g'], 8: ['a2-highgpu-8g'],
+             16: ['a2-megagpu-16g']},
+    'A100-80GB': {1: ['a2-ultragpu-1g'], 2: ['a2-ultragpu-2g'],
+                  4: ['a2-ultragpu-4g'], 8: ['a2-ultragpu-8g']},
+    'L4': {1: ['g2-standard-4', 'g2-standard-8', 'g2-standard-12',
+               'g2-standard-16', 'g2-standard-32'],
+           2: ['g2-standard-24'], 4: ['g2-standard-48'],
+           8: ['g2-standard-96']},
+    'H100': {1: ['a3-highgpu-1g'], 2: ['a3-highgpu-2g'],
+             4: ['a3-highgpu-4g'], 8: ['a3-highgpu-8g']},
+    'H100-MEGA': {8: ['a3-megagpu-8g']},
+    'H200': {8: ['a3-ultragpu-8g']},
+    'B200': {8: ['a4-highgpu-8g']},
+}
+GCP_INSTANCE_TO_ACC = {
+    t: {acc: cnt} for acc, by in GCP_FIXED.items() for cnt, ts in by.items()
+    for t in ts
+}
+GCP_HOST_CPUS = {
+    'K80': {1: 4, 2: 8, 4: 16, 8: 32, 16: 64},
+    'V100': {1: 8, 2: 16, 4: 32, 8: 64},
+    'T4': {1: 4, 2: 8, 4: 48},
+    'P100': {1: 8, 2: 16, 4: 32, 8: 64},
+    'DEFAULT': {1: 8, 2: 16, 4: 32, 8: 64, 16: 128},
+}
+
+
+# ---- sky/catalog/common.py -------------------------------------------------
+def filter_region_zone(df, region, zone):
+    """common.py:509-515."""
+    if region is not None:
+        df = df[df['Region'].str.lower() == region.lower()]
+    if zone is not None:
+        df = df[df['AvailabilityZone'].str.lower() == zone.lower()]
+    return df
+
+
+def filter_with_cpus(df, cpus: Optional[str]):
+    """common.py:431-452."""
+    if cpus is None:
+        return df
+    num = float(cpus[:-1] if cpus.endswith('+') else cpus)
+    if cpus.endswith('+'):
+        return df[df['vCPUs'] >= num]
+    return df[df['vCPUs'] == num]
+
+
+def filter_with_mem(df, memory: Optional[str]):
+    """common.py:455-478."""
+    if memory is None:
+        return df
+    body = memory[:-1] if memory.endswith(('+', 'x')) else memory
+    value = float(body)
+    if memory.endswith('+'):
+        return df[df['MemoryGiB'] >= value]
+    if memory.endswith('x'):
+        return df[df['MemoryGiB'] >= df['vCPUs'] * value]
+    return df[df['MemoryGiB'] == value]
+
+
+def filter_with_local_disk(df, local_disk: Optional[str]):
+    """common.py:481-506."""
+    if local_disk is None:
+        return df
+    mode, size = local_disk.lower().split(':')
+    at_least = size.endswith('+')
+    size = float(size[:-1] if at_least else size)
+    df = df[df['LocalDiskType'] == 'ssd']
+    if mode == 'nvme':
+        df = df[df['NVMeSupported'] == True]  # pylint: disable=singleton-comparison
+    total = df['LocalDiskSize'].fillna(0) * df['LocalDiskCount'].fillna(0)
+    if at_least:
+        return df[total >= size]
+    return df[abs(total - size) < 1.0]
+
+
+def instance_type_for_cpus_mem(df, cpus, memory, region=None, zone=None,
+                               use_spot=False,
+                               max_hourly_cost=None) -> Optional[str]:
+    """get_instance_type_for_cpus_mem_impl, common.py:518-569."""
+    df = filter_region_zone(df, region, zone)
+    df = filter_with_cpus(df, cpus)
+    df = filter_with_mem(df, memory)
+    if df.empty:
+        return None
+    price = ('SpotPrice'
+             if use_spot and max_hourly_cost is not None else 'Price')
+    if price not in df.columns or pd.isna(df[price]).all():
+        return None
+    if max_hourly_cost is not None:
+        df = df[df[price] <= max_hourly_cost]
+        if df.empty:
+            return None
+    df = df.sort_values(by=[price], ascending=True, kind='stable')
+    return df['InstanceType'].iloc[0]
+
+
+def instance_type_for_accelerator(
+        df, acc_name, acc_count, cpus=None, memory=None, use_spot=False,
+        region=None, zone=None,
+        max_hourly_cost=None) -> Tuple[Optional[List[str]], List[str]]:
+    """get_instance_type_for_accelerator_impl, common.py:641-694."""
+    result = df[(df['AcceleratorName'].str.fullmatch(acc_name, case=False)) &
+                (abs(df['AcceleratorCount'] - acc_count) <= 0.01)]
+    result = filter_region_zone(result, region, zone)
+    if result.empty:
+        fuzzy = df[(df['AcceleratorName'].str.contains(acc_name, case=False)) &
+                   (df['AcceleratorCount'] >= acc_count)]
+        fuzzy = filter_region_zone(fuzzy, region, zone)
+        fuzzy = fuzzy.sort_values('Price', ascending=True, kind='stable')
+        fuzzy = fuzzy[['AcceleratorName', 'AcceleratorCount']].drop_duplicates()
+        out = []
+        for _, row in fuzzy.iterrows():
+            cnt = float(row['AcceleratorCount'])
+            shown = int(cnt) if cnt.is_integer() else f'{cnt:.2f}'
+            out.append(f'{row["AcceleratorName"]}:{shown}')
+        return None, out
+    result = filter_with_cpus(result, cpus)
+    result = filter_with_mem(result, memory)
+    result = filter_region_zone(result, region, zone)
+    if result.empty:
+        return [], []
+    price = 'SpotPrice' if use_spot else 'Price'
+    if pd.isna(result[price]).all():
+        return [], []
+    if max_hourly_cost is not None:
+        result = result[result[price] <= max_hourly_cost]
+        if result.empty:
+            return [], []
+    result = result.sort_values(price, ascending=True, kind='stable')
+    return list(result['InstanceType'].drop_duplicates()), []
+
+
+def region_zones(df, use_spot) -> List[Tuple[str, Optional[List[str]]]]:
+    """get_region_zones, common.py:793-809 -> [(region, zones or None)]."""
+    price = 'SpotPrice' if use_spot else 'Price'
+    keys = [price, 'Region']
+    has_zone = 'AvailabilityZone' in df.columns
+    if has_zone:
+        keys.append('AvailabilityZone')
+    df = df.dropna(subset=keys).sort_values(keys)
+    regions = list(df['Region'].unique())
+    if not has_zone:
+        return [(r, None) for r in regions]
+    zones = df.groupby('Region')['AvailabilityZone'].apply(list)
+    return [(r, list(zones[r])) for r in regions]
+
+
+def get_instance_rows(df, instance_type, region, zone=None):
+    """_get_instance_type, common.py:269-281."""
+    idx = df['InstanceType'] == instance_type
+    if region is not None:
+        idx &= df['Region'].str.lower() == region.lower()
+    if zone is not None:
+        idx &= df['AvailabilityZone'] == zone
+    return df[idx]
+
+
+def hourly_cost(df, instance_type, use_spot, region, zone) -> float:
+    """get_hourly_cost_impl, common.py:360-400."""
+    df = get_instance_rows(df, instance_type, region, zone)
+    if df.empty:
+        raise ValueError(f'Instance type {instance_type!r} not found.')
+    price = 'SpotPrice' if use_spot else 'Price'
+    if pd.isna(df[price]).all():
+        raise ValueError(f'No {price} found for instance type '
+                         f'{instance_type!r}.')
+    return float(df.loc[df[price].idxmin()][price])
+
+
+# ---- per-cloud wrappers ------------------------------------------------------
+_AZ_DASHED = re.compile(r'([A-Za-z]+)([0-9]+)(-)([0-9]+)(.*)')
+_AZ_PLAIN = re.compile(r'([A-Za-z]+)([0-9]+)(.*)')
+_AZ_SERIES = re.compile(r'(Standard|Basic)_([A-Z]+)([0-9]+)(-[0-9]+)?'
+                        r'([a-z]*)(_[A-Z]+[0-9]+)?(_v[0-9])?(_Promo)?')
+
+
+def azure_family(instance_type: str) -> str:
+    """_get_instance_family, azure_catalog.py:78-98."""
+    if instance_type.startswith('Basic_A'):
+        return 'basic_a'
+    body = instance_type[len('Standard_'):]
+    if '_Promo' in body:
+        body = body[:-len('_Promo')]
+    if '-' in body:
+        m = _AZ_DASHED.match(body)
+        return m.group(1) + '_' + m.group(5)
+    m = _AZ_PLAIN.match(body)
+    return m.group(1) + m.group(3)
+
+
+def azure_disk_tier_ok(instance_type: Optional[str],
+                       disk_tier: Optional[str]) -> bool:
+    """Azure.check_disk_tier, azure.py:724-742 (tiers as strings)."""
+    if disk_tier is None or disk_tier == 'best':
+        return True
+    if disk_tier == 'ultra':
+        return False
+    premium = disk_tier in ('high', 'medium')
+    if premium and instance_type is not None:
+        return 's' in _AZ_SERIES.match(instance_type).group(5)
+    return True
+
+
+def default_instance_type(cloud: str, df, req: Dict) -> Optional[str]:
+    """get_default_instance_type of the four clouds (aws_catalog.py:249-274,
+    gcp_catalog.py:282-311, azure_catalog.py:100-127,
+    lambda_catalog.py:55-75)."""
+    cpus, memory = req.get('cpus'), req.get('memory')
+    if cpus is None and memory is None:
+        cpus = f'{DEFAULT_CPUS[cloud]}+'
+    if memory is None:
+        memory = '4x'
+    if cloud == 'aws':
+        prefix = tuple(f'{f}.' for f in AWS_FAMILIES)
+        df = df[df['InstanceType'].str.startswith(prefix)]
+        df = filter_with_local_disk(df, req.get('local_disk'))
+    elif cloud == 'gcp':
+        prefix = tuple(f'{f}-' for f in GCP_FAMILIES)
+        df = df[df['InstanceType'].notna()]
+        df = df[df['InstanceType'].str.startswith(prefix)]
+    elif cloud == 'azure':
+        df = df[df['InstanceType'].apply(azure_family).isin(AZURE_FAMILIES)]
+        tier = req.get('disk_tier')
+        df = df.loc[df['InstanceType'].apply(
+            lambda t: azure_disk_tier_ok(t, tier))]
+    return instance_type_for_cpus_mem(df, cpus, memory, req.get('region'),
+                                      req.get('zone'),
+                                      bool(req.get('use_spot')),
+                                      req.get('max_hourly_cost'))
+
+
+def gcp_instance_type_for_accelerator(df, acc, count, cpus, memory, use_spot,
+                                      region, zone, max_hourly_cost):
+    """gcp_catalog.get_instance_type_for_accelerator, :334-393."""
+    instance_list, fuzzy = instance_type_for_accelerator(
+        df, acc, count, cpus, memory, use_spot, region, zone, max_hourly_cost)
+    if instance_list is None:
+        return None, fuzzy
+    if acc in GCP_FIXED:
+        vms = df[df['InstanceType'].notna()]
+        types = GCP_FIXED[acc].get(count)
+        if types is None:
+            return None, []
+        vms = vms[vms['InstanceType'].isin(types)]
+        inst = instance_type_for_cpus_mem(vms, cpus, memory)
+        return (None, []) if inst is None else ([inst], [])
+    table = GCP_HOST_CPUS.get(acc, GCP_HOST_CPUS['DEFAULT'])
+    default_cpus = table.get(count)
+    if cpus is None and memory is None:
+        cpus = f'{default_cpus}+'
+    if memory is None:
+        memory = f'{int(cpus.strip("+").strip("x")) * 4}+'
+    vms = df[df['InstanceType'].notna()]
+    vms = vms[vms['InstanceType'].str.startswith(GCP_HOST_FAMILIES)]
+    inst = instance_type_for_cpus_mem(vms, cpus, memory)
+    return (None, []) if inst is None else ([inst], [])
+
+
+def gcp_accelerator_rows(df, acc, count, region, zone=None):
+    """_get_accelerator, gcp_catalog.py:404-417."""
+    idx = (df['AcceleratorName'].str.fullmatch(acc, case=False)) & (
+        df['AcceleratorCount'] == count)
+    if region is not None:
+        idx &= df['Region'] == region
+    if zone is not None:
+        idx &= df['AvailabilityZone'] == zone
+    return df[idx]
+
+
+def gcp_accelerator_hourly_cost(df, acc, count, use_spot, region, zone):
+    """get_accelerator_hourly_cost, gcp_catalog.py:420-442."""
+    rows = gcp_accelerator_rows(df, acc, count, region, zone)
+    min_price = rows['Price'].min()
+    if not use_spot:
+        return min_price
+    idx = rows['SpotPrice'].idxmin()
+    if pd.isnull(idx):
+        return min_price
+    return rows.loc[idx]['SpotPrice']
+
+
+def us_first(regions):
+    """aws_catalog.py:327-336 / lambda_catalog.py:121-129."""
+    return ([r for r in regions if r[0].startswith('us-')] +
+            [r for r in regions if not r[0].startswith('us-')])

@@ -1,0 +1,726 @@
+"""CPU oracle, part 2: the optimizer, restated on top of catalog_oracle.
+
+TEST INFRASTRUCTURE ONLY (see catalog_oracle.py). Restates, in the
+reference's own order of operations and with pandas DataFrames as the data
+structure:
+
+  _fill_in_launchable_resources      sky/optimizer.py:1664-1785
+  Cloud._get_feasible_launchable_resources
+                                     aws.py:881-953, gcp.py:709-823,
+                                     azure.py:485-557, lambda_cloud.py:217-280
+  make_launchables_for_valid_region_zones
+                                     utils/resources_utils.py:454-502
+  regions_with_offering              aws.py:347-367, gcp.py:281-331,
+                                     azure.py:283-299, lambda_cloud.py:72-91
+  Resources.get_cost                 resources.py:1685-1698
+  _estimate_nodes_cost_or_time       optimizer.py:239-426
+  _egress_cost_or_time + tariffs     optimizer.py:75-104, :196-236;
+                                     aws.py:667-688, gcp.py:395-404,
+                                     azure.py:142-165
+  _optimize_by_dp                    optimizer.py:429-487
+  general DAGs                       exact optimum of the objective of
+                                     optimizer.py:490-637 by exhaustive search
+                                     (PuLP/CBC is a third-party solver that is
+                                     not installed; only the objective value
+                                     is comparable, as in the reference's own
+                                     tests/test_optimizer_random_dag.py:110-173)
+  Resources.should_be_blocked_by     resources.py:1938-1961
+
+Requests are plain dicts (keys = Resources kwargs with the cloud as a lower
+case name); a launchable candidate is the dict plus instance_type / region /
+zone. Parity pinning: tests/test_oracle.py replays tests/golden/*.json
+(generated from the unmodified reference) through this module.
+"""
+import itertools
+import math
+import re
+from typing import Any, Dict, List, Optional, Tuple
+
+import pandas as pd
+
+from oracle import catalog_oracle as co
+
+CLOUD_ORDER = ['aws', 'gcp', 'azure', 'lambda']
+
+
+class Unavailable(Exception):
+    """Stands for exceptions.ResourcesUnavailableError."""
+
+
+class Catalog:
+    """{cloud: DataFrame} plus the small caches the reference also keeps."""
+
+    def __init__(self, frames: Dict[str, pd.DataFrame],
+                 enabled: Optional[List[str]] = None):
+        self.frames = frames
+        self.enabled = enabled or [c for c in CLOUD_ORDER if c in frames]
+        names: Dict[str, set] = {}
+        for cloud, df in frames.items():
+            for name in df['AcceleratorName'].dropna().unique():
+                names.setdefault(str(name), set()).add(cloud)
+        self.acc_names = names
+
+
+# ---- request validation (sky/resources.py:442-456) ----------------------------
+def canonical_accelerator(cat: Catalog, name: str,
+                          cloud: Optional[str]) -> str:
+    """accelerator_registry.canonicalize_accelerator_name (:84-132)."""
+    if name.lower().startswith('tpu-'):
+        return name.lower()
+    pattern = re.compile(name, flags=re.IGNORECASE)
+    hits = []
+    for cand, clouds in sorted(cat.acc_names.items()):
+        if pattern.search(cand) is None:
+            continue
+        if name.lower() == cand.lower():
+            return cand
+        if cloud is None or cloud in clouds:
+            hits.append(cand)
+    if not hits:
+        return name
+    if len(hits) == 1:
+        return hits[0]
+    raise ValueError(f'Accelerator name {name!r} is ambiguous.')
+
+
+def normalize_request(cat: Catalog, spec: Dict[str, Any]) -> Dict[str, Any]:
+    """Resources(**spec) + validate(): parse fields, canonicalise, infer."""
+    req = dict(spec)
+    infra = req.pop('infra', None)
+    if infra is not None:
+        parts = infra.strip('/').split('/')
+        req['cloud'] = parts[0]
+        if len(parts) > 1:
+            req['region'] = parts[1]
+        if len(parts) > 2:
+            req['zone'] = parts[2]
+    for key in ('cloud', 'instance_type', 'cpus', 'memory', 'accelerators',
+                'region', 'zone', 'local_disk', 'max_hourly_cost',
+                'disk_tier', 'accelerator_args'):
+        req.setdefault(key, None)
+    req['use_spot'] = bool(req.get('use_spot'))
+    if req['cpus'] is not None:
+        req['cpus'] = str(req['cpus'])
+    if req['memory'] is not None:
+        req['memory'] = str(req['memory'])
+    acc = req['accelerators']
+    if isinstance(acc, str):
+        if ':' in acc:
+            name, cnt = acc.split(':')
+            cnt = float(cnt)
+            acc = {name: int(cnt) if cnt.is_integer() else cnt}
+        else:
+            acc = {acc: 1}
+    if acc is not None:
+        name = list(acc.keys())[0]
+        if 'tpu' in name.lower() and req['cloud'] is None:
+            req['cloud'] = 'gcp'
+        acc = {
+            canonical_accelerator(cat, k, req['cloud']): v
+            for k, v in acc.items()
+        }
+    req['accelerators'] = acc
+    if req['local_disk'] is not None:
+        text = str(req['local_disk']).lower()
+        if ':' not in text:
+            text = (f'{text}:100+' if text in ('nvme', 'ssd') else
+                    f'nvme:{text}')
+        req['local_disk'] = text
+    # region / zone validation with the zone's region filled in
+    if req['region'] is not None or req['zone'] is not None:
+        if req['cloud'] is None:
+            valid = [
+                c for c in cat.enabled
+                if _region_zone_valid(cat, c, req['region'], req['zone'])
+            ]
+            if len(valid) != 1:
+                raise ValueError('Cannot infer cloud from region/zone')
+            req['cloud'] = valid[0]
+        df = cat.frames[req['cloud']]
+        sub = co.filter_region_zone(df, req['region'], None)
+        if sub.empty:
+            raise ValueError(f'Invalid region {req["region"]!r}')
+        if req['region'] is not None:
+            req['region'] = sub['Region'].unique()[0]
+        if req['zone'] is not None:
+            sub = sub[sub['AvailabilityZone'] == req['zone']]
+            if sub.empty:
+                raise ValueError(f'Invalid zone {req["zone"]!r}')
+            req['region'] = sub['Region'].unique()[0]
+    if req['instance_type'] is not None and req['cloud'] is None:
+        valid = [
+            c for c in cat.enabled
+            if req['instance_type'] in cat.frames[c]['InstanceType'].unique()
+        ]
+        if len(valid) != 1:
+            raise ValueError('Invalid or ambiguous instance type')
+        req['cloud'] = valid[0]
+    return req
+
+
+def _region_zone_valid(cat, cloud, region, zone) -> bool:
+    df = cat.frames[cloud]
+    if zone is not None and 'AvailabilityZone' not in df.columns:
+        return False
+    sub = co.filter_region_zone(df, region, None)
+    if sub.empty:
+        return False
+    if zone is not None:
+        return not sub[sub['AvailabilityZone'] == zone].empty
+    return True
+
+
+# ---- feasibility per cloud ------------------------------------------------------
+def _unsupported(cloud: str, req: Dict[str, Any], num_nodes: int) -> bool:
+    """check_features_are_supported for the features a request can need."""
+    if cloud == 'lambda' and (req['use_spot'] or
+                              req['disk_tier'] not in (None, 'best')):
+        return True
+    if req['local_disk'] is not None and cloud != 'aws':
+        return True
+    del num_nodes
+    return False
+
+
+def feasible(cat: Catalog, cloud: str, req: Dict[str, Any],
+             num_nodes: int) -> Tuple[List[Dict[str, Any]], List[str]]:
+    """get_feasible_launchable_resources -> (launchable requests sorted by
+    price, fuzzy candidate strings)."""
+    if _unsupported(cloud, req, num_nodes):
+        return [], []
+    df = cat.frames[cloud]
+    if req['instance_type'] is not None:
+        if cloud == 'azure' and not co.azure_disk_tier_ok(
+                req['instance_type'], req['disk_tier']):
+            return [], []
+        out = dict(req)
+        if cloud == 'aws':
+            if not regions_with_offering(cat, out):
+                return [], []
+        if cloud != 'gcp':
+            out['accelerators'] = None
+            out['_implied_acc'] = _implied_accelerators(df, req['instance_type'])
+        return [out], []
+
+    def make(instance_type, keep_acc=False):
+        r = dict(req)
+        r.update(cloud=cloud, instance_type=instance_type, cpus=None,
+                 memory=None)
+        if not keep_acc:
+            r['accelerators'] = None
+            r['_implied_acc'] = _implied_accelerators(df, instance_type)
+        return r
+
+    acc = req['accelerators']
+    if acc is None:
+        inst = co.default_instance_type(cloud, df, req)
+        if inst is None:
+            return [], []
+        if cloud == 'azure' and not co.azure_disk_tier_ok(inst,
+                                                          req['disk_tier']):
+            return [], []
+        return [make(inst)], []
+    name, count = list(acc.items())[0]
+    if cloud == 'gcp':
+        tpu_vm = name.startswith('tpu') and (
+            (req['accelerator_args'] or {}).get('tpu_vm', True))
+        inst_list, fuzzy = co.gcp_instance_type_for_accelerator(
+            df, name, count, None if tpu_vm else req['cpus'],
+            None if tpu_vm else req['memory'], req['use_spot'], req['region'],
+            req['zone'], req['max_hourly_cost'])
+        if inst_list is None:
+            return [], fuzzy
+        if tpu_vm:
+            n_cpus = 240 if 'v4' in name else 96
+            mem = 400 if 'v4' in name else 334
+            if not _fits(req['cpus'], n_cpus) or not _fits(req['memory'], mem):
+                return [], fuzzy
+            return [make('TPU-VM', keep_acc=True)], fuzzy
+        return [make(inst_list[0], keep_acc=True)], fuzzy
+    if cloud == 'aws':
+        df = co.filter_with_local_disk(df, req['local_disk'])
+    inst_list, fuzzy = co.instance_type_for_accelerator(
+        df, name, count, req['cpus'], req['memory'], req['use_spot'],
+        req['region'], req['zone'], req['max_hourly_cost'])
+    if inst_list is None:
+        return [], fuzzy
+    out = []
+    for inst in inst_list:
+        if cloud == 'azure' and not co.azure_disk_tier_ok(inst,
+                                                          req['disk_tier']):
+            continue
+        out.append(make(inst))
+    return out, fuzzy
+
+
+def _fits(request: Optional[str], available: int) -> bool:
+    if request is None:
+        return True
+    if request.endswith('+'):
+        return float(request[:-1]) <= available
+    return float(request) == available
+
+
+def _implied_accelerators(df, instance_type):
+    """get_accelerators_from_instance_type_impl, common.py:572-590."""
+    rows = df[df['InstanceType'] == instance_type]
+    if rows.empty:
+        return None
+    row = rows.iloc[0]
+    if pd.isnull(row['AcceleratorName']):
+        return None
+    cnt = float(row['AcceleratorCount'])
+    return {row['AcceleratorName']: int(cnt) if int(cnt) == cnt else cnt}
+
+
+def accelerators_of(launchable: Dict[str, Any]):
+    if launchable['accelerators'] is not None:
+        return launchable['accelerators']
+    if launchable['cloud'] == 'gcp':
+        return co.GCP_INSTANCE_TO_ACC.get(launchable['instance_type'])
+    return launchable.get('_implied_acc')
+
+
+def regions_with_offering(cat: Catalog, launchable: Dict[str, Any]):
+    """Cloud.regions_with_offering -> [(region, zones or None)]."""
+    cloud = launchable['cloud']
+    df = cat.frames[cloud]
+    inst, spot = launchable['instance_type'], launchable['use_spot']
+    region, zone = launchable['region'], launchable['zone']
+    if cloud == 'lambda' and spot:
+        return []
+    acc = launchable['accelerators'] if cloud == 'gcp' else None
+    if acc is None:
+        regions = co.region_zones(df[df['InstanceType'] == inst], spot)
+        if cloud in ('aws', 'lambda'):
+            regions = co.us_first(regions)
+    else:
+        name, count = list(acc.items())[0]
+        acc_regions = co.region_zones(
+            co.gcp_accelerator_rows(df, name, count, None), spot)
+        if inst is None or inst == 'TPU-VM':
+            regions = acc_regions
+        else:
+            vm_regions = dict(
+                co.region_zones(df[df['InstanceType'] == inst], spot))
+            regions = []
+            for r1, z1 in acc_regions:
+                if r1 not in vm_regions:
+                    continue
+                zones = [z for z in z1 if z in vm_regions[r1]]
+                if zones:
+                    regions.append((r1, zones))
+    if region is not None:
+        regions = [r for r in regions if r[0] == region]
+    if zone is not None:
+        regions = [(r, [z for z in zs if z == zone]) for r, zs in regions]
+        regions = [r for r in regions if r[1]]
+    return regions
+
+
+def make_launchables(cat: Catalog,
+                     launchable: Dict[str, Any]) -> List[Dict[str, Any]]:
+    """make_launchables_for_valid_region_zones."""
+    out = []
+    by_zone = launchable['cloud'] == 'gcp'
+    for region, zones in regions_with_offering(cat, launchable):
+        if zones is not None and (launchable['use_spot'] or by_zone):
+            for zone in zones:
+                out.append(dict(launchable, region=region, zone=zone))
+        else:
+            out.append(dict(launchable, region=region))
+    return out
+
+
+def get_cost(cat: Catalog, launchable: Dict[str, Any], seconds) -> float:
+    """Resources.get_cost."""
+    hours = seconds / 3600
+    cloud = launchable['cloud']
+    df = cat.frames[cloud]
+    if cloud == 'gcp' and launchable['instance_type'] == 'TPU-VM':
+        hourly = 0
+    else:
+        hourly = co.hourly_cost(df, launchable['instance_type'],
+                                launchable['use_spot'], launchable['region'],
+                                launchable['zone'])
+    if accelerators_of(launchable) is not None and cloud == 'gcp':
+        name, count = list(accelerators_of(launchable).items())[0]
+        if launchable['accelerators'] is not None:
+            hourly += co.gcp_accelerator_hourly_cost(
+                df, name, count, launchable['use_spot'], launchable['region'],
+                launchable['zone'])
+    return float(hourly * hours)
+
+
+def blocked_by(launchable: Dict[str, Any], blocked: Dict[str, Any]) -> bool:
+    """Resources.should_be_blocked_by; `blocked` is a normalised request."""
+    if blocked['cloud'] is not None and launchable['cloud'] != blocked['cloud']:
+        return False
+    if (blocked['instance_type'] is not None and
+            launchable['instance_type'] != blocked['instance_type']):
+        return False
+    if blocked['region'] is not None and (launchable['region'] !=
+                                          blocked['region']):
+        return False
+    if blocked['zone'] is not None and launchable['zone'] != blocked['zone']:
+        return False
+    b_acc = blocked['accelerators']
+    if b_acc is None and blocked['instance_type'] is not None and (
+            blocked['cloud'] is not None):
+        b_acc = blocked.get('_implied_acc')
+    if b_acc is not None and accelerators_of(launchable) != b_acc:
+        return False
+    return launchable['use_spot'] == blocked['use_spot']
+
+
+def fill_in_launchable(cat: Catalog, task: Dict[str, Any],
+                       blocked: List[Dict[str, Any]]):
+    """_fill_in_launchable_resources -> ([(request, [launchables])], fuzzy)."""
+    out = []
+    fuzzy_all = set()
+    for req in task['requests']:
+        launch: List[Dict[str, Any]] = []
+        if req['cloud'] is not None and req['cloud'] not in cat.enabled:
+            out.append((req, []))
+            continue
+        clouds = [req['cloud']] if req['cloud'] is not None else cat.enabled
+        for cloud in clouds:
+            options, fuzzy = feasible(cat, cloud, req, task['num_nodes'])
+            if options:
+                launch.extend(make_launchables(cat, options[0]))
+            else:
+                fuzzy_all.update(fuzzy)
+        launch = [
+            l for l in launch if not any(blocked_by(l, b) for b in blocked)
+        ]
+        out.append((req, launch))
+    return out, sorted(fuzzy_all)
+
+
+# ---- egress ------------------------------------------------------------------------
+def egress_tariff(cloud: str, g: float) -> float:
+    """Cloud.get_egress_cost of AWS / GCP / Azure; 0.0 elsewhere."""
+    if cloud == 'gcp':
+        if g <= 1024:
+            return 0.12 * g
+        if g <= 1024 * 10:
+            return 0.11 * g
+        return 0.08 * g
+    if cloud in ('aws', 'azure'):
+        mid, low = (0.085, 0.09) if cloud == 'aws' else (0.083, 0.0875)
+        if g > 150 * 1024:
+            return 0.05 * g
+        cost = 0.0
+        if g >= 50 * 1024:
+            cost += (g - 50 * 1024) * 0.07
+            g -= 50 * 1024
+        if g >= 10 * 1024:
+            cost += (g - 10 * 1024) * mid
+            g -= 10 * 1024
+        if g > 1:
+            cost += (g - 1) * low
+        cost += 0.0
+        return cost
+    return 0.0
+
+
+def egress(minimize_cost: bool, src: Optional[str], dst: Optional[str],
+           nbytes) -> float:
+    """_egress_cost_or_time with clouds as names (None = dummy)."""
+    if not nbytes:
+        return 0
+    if src is None or dst is None:
+        return 0.0
+    if src == dst:
+        return 0.0
+    if minimize_cost:
+        return egress_tariff(src, nbytes)
+    return nbytes * 8 / 10
+
+
+def _inputs_cloud(url: str) -> str:
+    if url.startswith('s3:'):
+        return 'aws'
+    if url.startswith('gs:'):
+        return 'gcp'
+    raise ValueError(url)
+
+
+def edge_value(minimize_cost, parent, parent_cand, node, cand) -> float:
+    if parent is None:  # dummy source
+        if node.get('inputs') is None:
+            return 0
+        return egress(minimize_cost, _inputs_cloud(node['inputs'][0]),
+                      cand['cloud'], node['inputs'][1])
+    return egress(minimize_cost, parent_cand['cloud'], cand['cloud'],
+                  parent.get('outputs_gb'))
+
+
+# ---- scenario driver -------------------------------------------------------------------
+def _time_estimator(spec):
+    by_acc = spec.get('by_acc', {})
+    default = spec.get('default', 3600)
+    by_cloud = spec.get('by_cloud', {})
+
+    def estimate(req):
+        seconds = default
+        if req['accelerators']:
+            seconds = by_acc.get(list(req['accelerators'].keys())[0], seconds)
+        if req['cloud'] is not None:
+            seconds = by_cloud.get(req['cloud'], seconds)
+        return seconds
+
+    return estimate
+
+
+def estimate_nodes(cat: Catalog, tasks, minimize_cost, blocked):
+    """_estimate_nodes_cost_or_time -> per task [(launchable, value)]."""
+    tables = []
+    for task in tasks:
+        filled, fuzzy = fill_in_launchable(cat, task, blocked)
+        rows = []
+        for req, launch in filled:
+            if task.get('time_est') is None:
+                runtime = 1 * 3600
+            else:
+                runtime = _time_estimator(task['time_est'])(req)
+            for l in launch:
+                if minimize_cost:
+                    value = get_cost(cat, l, runtime) * max(
+                        task['num_nodes'] - 0, 0)
+                else:
+                    value = runtime
+                rows.append((l, value))
+        if not rows:
+            raise Unavailable(
+                f'Catalog does not contain any instances satisfying the '
+                f'request: {task["requests"]}. fuzzy={fuzzy}')
+        tables.append(rows)
+    return tables
+
+
+def optimize_by_dp(tasks, tables, minimize_cost):
+    """_optimize_by_dp on a chain (dummy source / sink implicit)."""
+    dp: List[List[float]] = []
+    back: List[List[int]] = []
+    for i, (task, rows) in enumerate(zip(tasks, tables)):
+        cur, ptr = [], []
+        for cand, value in rows:
+            best = math.inf
+            best_p = -1
+            if i == 0:
+                v = 0 + edge_value(minimize_cost, None, None, task, cand)
+                if v < best:
+                    best, best_p = v, 0
+            else:
+                for p, (pcand, _) in enumerate(tables[i - 1]):
+                    v = dp[i - 1][p] + edge_value(minimize_cost, tasks[i - 1],
+                                                  pcand, task, cand)
+                    if v < best:
+                        best, best_p = v, p
+            cur.append(value + best)
+            ptr.append(best_p)
+        dp.append(cur)
+        back.append(ptr)
+    best, idx = math.inf, -1
+    for p, v in enumerate(dp[-1]):
+        if v + 0 < best:
+            best, idx = v + 0, p
+    plan = [0] * len(tasks)
+    for i in range(len(tasks) - 1, -1, -1):
+        plan[i] = idx
+        idx = back[i][idx]
+    return plan, 0 + best
+
+
+def optimize_exhaustive(tasks, tables, parents, minimize_cost):
+    """Exact optimum of the ILP objective (optimizer.py:605-620) by
+    enumeration over one representative per (task, cloud)."""
+    reps = []
+    for rows in tables:
+        best: Dict[str, int] = {}
+        for i, (cand, value) in enumerate(rows):
+            c = cand['cloud']
+            if c not in best or value < rows[best[c]][1]:
+                best[c] = i
+        reps.append(sorted(best.values()))
+    best_total, best_combo = None, None
+    for combo in itertools.product(*reps):
+        if minimize_cost:
+            total = 0.0
+            for i, rows in enumerate(tables):
+                total += rows[combo[i]][1]
+            for i, task in enumerate(tasks):
+                cand = tables[i][combo[i]][0]
+                if not parents[i]:
+                    total += edge_value(True, None, None, task, cand)
+                for p in parents[i]:
+                    total += edge_value(True, tasks[p], tables[p][combo[p]][0],
+                                        task, cand)
+        else:
+            finish: Dict[int, float] = {}
+            total = 0
+            for i, task in enumerate(tasks):
+                cand = tables[i][combo[i]][0]
+                start = 0
+                if not parents[i]:
+                    start = max(start,
+                                edge_value(False, None, None, task, cand))
+                for p in parents[i]:
+                    start = max(
+                        start, finish[p] + edge_value(
+                            False, tasks[p], tables[p][combo[p]][0], task,
+                            cand))
+                finish[i] = tables[i][combo[i]][1] + start
+                total = max(total, finish[i])
+        if best_total is None or total < best_total:
+            best_total, best_combo = total, combo
+    return list(best_combo), best_total
+
+
+def _record(l: Dict[str, Any]) -> Dict[str, Any]:
+    acc = accelerators_of(l)
+    return {
+        'cloud': l['cloud'], 'instance_type': l['instance_type'],
+        'region': l['region'], 'zone': l['zone'],
+        'accelerators': None if acc is None else
+                        {k: float(v) for k, v in acc.items()},
+        'use_spot': bool(l['use_spot']),
+    }
+
+
+def _is_chain(n: int, edges) -> bool:
+    indeg = [0] * n
+    outdeg = [0] * n
+    for u, v in edges:
+        outdeg[u] += 1
+        indeg[v] += 1
+    return (max(outdeg) <= 1 and outdeg.count(0) == 1 and max(indeg) <= 1 and
+            indeg.count(0) == 1)
+
+
+def _topo(n: int, edges) -> List[int]:
+    indeg = [0] * n
+    for _, v in edges:
+        indeg[v] += 1
+    order, ready = [], [i for i in range(n) if indeg[i] == 0]
+    while ready:
+        u = ready.pop(0)
+        order.append(u)
+        for a, b in edges:
+            if a == u:
+                indeg[b] -= 1
+                if indeg[b] == 0:
+                    ready.append(b)
+    return order
+
+
+_catalog_cache: Dict[str, Catalog] = {}
+
+
+def catalog_for(spec: Dict[str, Any]) -> Catalog:
+    import json  # pylint: disable=import-outside-toplevel
+    from skypilot_b200 import synth  # pylint: disable=import-outside-toplevel
+    key = json.dumps(spec, sort_keys=True)
+    if key not in _catalog_cache:
+        spec = dict(spec)
+        enabled = spec.pop('enabled', None)
+        _catalog_cache[key] = Catalog(synth.make_catalogs(**spec), enabled)
+    return _catalog_cache[key]
+
+
+def run_scenario(catalog_spec: Dict[str, Any],
+                 scenario: Dict[str, Any]) -> Dict[str, Any]:
+    """Same record format as oracle/ref_harness/run_reference.py."""
+    cat = catalog_for(catalog_spec)
+    minimize_cost = scenario.get('minimize', 'cost') == 'cost'
+    record: Dict[str, Any] = {'name': scenario['name']}
+    n = len(scenario['tasks'])
+    edges = [tuple(e) for e in scenario.get('edges', [])]
+    record['is_chain'] = _is_chain(n, edges)
+    try:
+        tasks = []
+        for i, tspec in enumerate(scenario['tasks']):
+            task = dict(tspec)
+            task.setdefault('num_nodes', 1)
+            task['requests'] = [
+                normalize_request(cat, r) for r in tspec['resources']
+            ]
+            tasks.append(task)
+        blocked = []
+        for spec in scenario.get('blocked', []):
+            b = normalize_request(cat, spec)
+            if b['instance_type'] is not None and b['cloud'] is not None:
+                b['_implied_acc'] = _implied_accelerators(
+                    cat.frames[b['cloud']], b['instance_type'])
+            blocked.append(b)
+        for task in tasks:
+            for req in task['requests']:
+                if req['cloud'] is not None and req['cloud'] not in cat.enabled:
+                    if all(r['cloud'] is not None and
+                           r['cloud'] not in cat.enabled
+                           for r in task['requests']):
+                        raise Unavailable(f'{req["cloud"]} is not enabled')
+        order = _topo(n, edges)
+        has_list = any(
+            t.get('resources_kind') == 'list' for t in scenario['tasks'])
+        if has_list:
+            for task in tasks:
+                if task.get('resources_kind') == 'list':
+                    for req in task['requests']:
+                        probe = dict(task, requests=[req])
+                        filled, _ = fill_in_launchable(cat, probe, blocked)
+                        if filled[0][1]:
+                            break
+                    task['requests'] = [req]
+        topo_tasks = [tasks[i] for i in order]
+        local = {g: l for l, g in enumerate(order)}
+        parents = [[local[u] for u, v in edges if v == g] for g in order]
+        tables = estimate_nodes(cat, topo_tasks, minimize_cost, blocked)
+        if record['is_chain']:
+            plan, objective = optimize_by_dp(topo_tasks, tables, minimize_cost)
+        else:
+            plan, objective = optimize_exhaustive(topo_tasks, tables, parents,
+                                                  minimize_cost)
+        by_global = {g: (tables[l], plan[l]) for g, l in local.items()}
+        if not has_list:
+            record['candidates'] = [[[
+                c['cloud'], c['instance_type'], c['region'], c['zone'],
+                float(v)
+            ] for c, v in by_global[g][0]] for g in range(n)]
+        record['plan'] = [
+            _record(by_global[g][0][by_global[g][1]][0]) for g in range(n)
+        ]
+        record['objective'] = float(objective)
+        # totals of the plan (optimizer.py:640-698)
+        chosen = [by_global[g][0][by_global[g][1]] for g in range(n)]
+        total_cost = 0.0
+        finish: Dict[int, float] = {}
+        for g in order:
+            task, (cand, _) = tasks[g], chosen[g]
+            if task.get('time_est') is None:
+                runtime = 1 * 3600
+            else:
+                runtime = _time_estimator(task['time_est'])(dict(
+                    cand, accelerators=accelerators_of(cand)))
+            total_cost += get_cost(cat, cand, runtime) * task['num_nodes']
+            preds = [u for u, v in edges if v == g]
+            start = 0
+            if not preds:
+                total_cost += edge_value(True, None, None, task, cand)
+                start = max(start, edge_value(False, None, None, task, cand))
+            for u in preds:
+                total_cost += edge_value(True, tasks[u], chosen[u][0], task,
+                                         cand)
+                start = max(
+                    start, finish[u] + edge_value(False, tasks[u],
+                                                  chosen[u][0], task, cand))
+            finish[g] = runtime + start
+        record['total_cost'] = float(total_cost)
+        record['total_time'] = float(max(finish.values()))
+    except Unavailable as e:
+        record['error'] = {
+            'type': 'ResourcesUnavailableError',
+            'message': str(e)
+        }
+    return record

@@ -157,6 +157,25 @@ def run_scenario(sky, scenario):
     is_chain = dag.is_chain()
     record['is_chain'] = bool(is_chain)
 
+    has_list = any(
+        t.get('resources_kind') == 'list' for t in scenario['tasks'])
+    if has_list:
+        # Ordered resources are resolved by _optimize_dag's pre-pass
+        # (sky/optimizer.py:1403-1448); only the end-to-end plan is recorded.
+        assert is_chain
+        try:
+            Optimizer.optimize(dag, minimize=target,
+                               blocked_resources=blocked, quiet=True)
+        except exceptions.ResourcesUnavailableError as e:
+            record['error'] = {
+                'type': 'ResourcesUnavailableError',
+                'message': str(e)
+            }
+            return record
+        record['plan'] = [_res_record(t.best_resources) for t in tasks]
+        record['ordered'] = True
+        return record
+
     # Candidate table + (for general DAGs) exhaustive optimum, on a dag with
     # the dummy source/sink attached exactly as Optimizer.optimize does.
     Optimizer._add_dummy_source_sink_nodes(dag)
@@ -183,8 +202,25 @@ def run_scenario(sky, scenario):
             plan, objective = Optimizer._optimize_by_dp(topo, cost_map,
                                                         minimize_cost)
         else:
-            # Exhaustive search (PuLP/CBC is not installed here).
-            names = [list(cost_map[n].keys()) for n in topo]
+            # Exhaustive search (PuLP/CBC is not installed here). Egress
+            # depends on the two clouds only (sky/optimizer.py:75-104), so
+            # inside one cloud the first cheapest candidate of a task
+            # dominates; the product runs over those representatives unless
+            # SKYOPT_FULL_EXHAUSTIVE=1 asks for every combination.
+            full = os.environ.get('SKYOPT_FULL_EXHAUSTIVE') == '1'
+            names = []
+            for n in topo:
+                keys = list(cost_map[n].keys())
+                if not full:
+                    best_of = {}
+                    for r in keys:
+                        c = str(r.cloud)
+                        if c not in best_of or (cost_map[n][r] <
+                                                cost_map[n][best_of[c]]):
+                            best_of[c] = r
+                    keys = [r for r in keys if best_of[str(r.cloud)] is r]
+                names.append(keys)
+            record['exhaustive'] = 'full' if full else 'per-cloud'
             best, best_plan = None, None
             for combo in itertools.product(*names):
                 plan_try = dict(zip(topo, combo))

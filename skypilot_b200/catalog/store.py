@@ -353,6 +353,24 @@ class CatalogStore:
                 words[k >> 5] |= np.uint32(1 << (k & 31))
         return words
 
+    def accelerator_name_clouds(self) -> Dict[str, set]:
+        """{accelerator name: clouds offering it} (the role of the
+        reference's common/accelerators.csv)."""
+        cached = getattr(self, '_acc_name_clouds', None)
+        if cached is not None:
+            return cached
+        out: Dict[str, set] = {}
+        akc = self.columns['acc_key']
+        offsets = self.columns['cloud_row_offsets']
+        for ci, table in enumerate(self.clouds):
+            keys = np.unique(akc[offsets[ci]:offsets[ci + 1]])
+            for k in keys:
+                if k != _native.NONE16:
+                    out.setdefault(self.acc_keys[int(k)][0],
+                                   set()).add(table.name)
+        self._acc_name_clouds = out
+        return out
+
     def row_bytes(self) -> int:
         """Bytes the scan streams per row and pass."""
         return 3 * 8 + 4 * 2

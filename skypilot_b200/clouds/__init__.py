@@ -1,0 +1,19 @@
+"""Clouds known to the placement optimizer (see clouds/cloud.py)."""
+from skypilot_b200.clouds.cloud import Cloud
+from skypilot_b200.clouds.cloud import cloud_in_iterable
+from skypilot_b200.clouds.cloud import CloudCapability
+from skypilot_b200.clouds.cloud import CloudImplementationFeatures
+from skypilot_b200.clouds.cloud import DummyCloud
+from skypilot_b200.clouds.cloud import Region
+from skypilot_b200.clouds.cloud import SlotPlan
+from skypilot_b200.clouds.cloud import Zone
+from skypilot_b200.clouds.aws import AWS
+from skypilot_b200.clouds.azure import Azure
+from skypilot_b200.clouds.gcp import GCP
+from skypilot_b200.clouds.lambda_cloud import Lambda
+
+__all__ = [
+    'AWS', 'Azure', 'Cloud', 'CloudCapability', 'CloudImplementationFeatures',
+    'DummyCloud', 'GCP', 'Lambda', 'Region', 'SlotPlan', 'Zone',
+    'cloud_in_iterable'
+]

@@ -1,0 +1,405 @@
+"""Cloud base class: the feasibility API the optimizer drives.
+
+Mirrors the placement-relevant surface of sky/clouds/cloud.py (Region / Zone
+:77-92, CloudImplementationFeatures :33-62, get_feasible_launchable_resources
+:459-501, check_features_are_supported :712-762, DummyCloud :1030-1033,
+cloud_in_iterable :1037-1039). Provisioning, credentials, images, ... are out
+of scope.
+
+What is new: `plan_feasible()` states a request against this cloud as catalog
+*queries* and an expansion *slot* for the GPU (engine.ProblemBuilder) instead
+of running pandas filters. `get_feasible_launchable_resources()` and the fused
+optimizer share that single description.
+"""
+import collections
+import enum
+from typing import Any, Callable, Dict, Iterable, List, Optional, Set, Tuple
+
+from skypilot_b200 import _native
+from skypilot_b200 import exceptions
+from skypilot_b200.utils import resources_utils
+
+
+class CloudImplementationFeatures(enum.Enum):
+    STOP = 'stop'
+    MULTI_NODE = 'multi-node'
+    CLONE_DISK_FROM_CLUSTER = 'clone_disk_from_cluster'
+    IMAGE_ID = 'image_id'
+    DOCKER_IMAGE = 'docker_image'
+    SPOT_INSTANCE = 'spot_instance'
+    CUSTOM_DISK_TIER = 'custom_disk_tier'
+    CUSTOM_NETWORK_TIER = 'custom_network_tier'
+    OPEN_PORTS = 'open_ports'
+    STORAGE_MOUNTING = 'storage_mounting'
+    HOST_CONTROLLERS = 'host_controllers'
+    HIGH_AVAILABILITY_CONTROLLERS = 'high_availability_controllers'
+    AUTO_TERMINATE = 'auto_terminate'
+    AUTOSTOP = 'autostop'
+    AUTODOWN = 'autodown'
+    CUSTOM_MULTI_NETWORK = 'custom_multi_network'
+    LOCAL_DISK = 'local_disk'
+
+
+class CloudCapability(str, enum.Enum):
+    COMPUTE = 'compute'
+    STORAGE = 'storage'
+
+
+class Region(collections.namedtuple('Region', ['name'])):
+    """A region with an optional ordered zone list."""
+    name: str
+    zones: Optional[List['Zone']] = None
+
+    def set_zones(self, zones: List['Zone']):
+        self.zones = zones
+        for zone in self.zones:
+            zone.region = self
+        return self
+
+
+class Zone(collections.namedtuple('Zone', ['name'])):
+    name: str
+    region: Region
+
+
+class SlotPlan:
+    """How one (request, cloud) pair is answered by the device."""
+
+    def __init__(self):
+        self.slot: Optional[int] = None      # builder slot, None = infeasible
+        self.list_query: Optional[int] = None  # query naming instance types
+        self.fuzzy_query: Optional[int] = None
+        self.gate_query: Optional[int] = None
+        self.hint: Optional[str] = None
+        self.explicit_instance: Optional[str] = None
+        self.no_fuzzy_when_matched = False
+        # instance type name -> launchable Resources (without region / zone)
+        self.make: Optional[Callable[[str], Any]] = None
+
+
+class Cloud:
+    """A cloud whose offerings live in the GPU-resident catalog."""
+
+    _REPR = '<Cloud>'
+    _CATALOG = ''  # key of the cloud in the catalog store
+    _CLOUD_UNSUPPORTED_FEATURES: Dict[CloudImplementationFeatures, str] = {}
+
+    # ---- identity ---------------------------------------------------------
+    def __repr__(self):
+        return self._REPR
+
+    def is_same_cloud(self, other: 'Cloud') -> bool:
+        return isinstance(other, self.__class__)
+
+    @classmethod
+    def display_name(cls) -> str:
+        return cls._REPR
+
+    @classmethod
+    def canonical_name(cls) -> str:
+        return cls.__name__.lower()
+
+    # ---- catalog plumbing ---------------------------------------------------
+    @classmethod
+    def _view(cls):
+        from skypilot_b200 import catalog  # pylint: disable=import-outside-toplevel
+        return catalog.view(cls._CATALOG)
+
+    @classmethod
+    def _rules(cls):
+        from skypilot_b200.catalog import rules  # pylint: disable=import-outside-toplevel
+        return rules.rules_for(cls._CATALOG)
+
+    @classmethod
+    def _catalog_module(cls):
+        from skypilot_b200 import catalog  # pylint: disable=import-outside-toplevel
+        return catalog.module_for(cls._CATALOG)
+
+    # ---- regions / zones ----------------------------------------------------
+    @classmethod
+    def regions_with_offering(cls, instance_type: str,
+                              accelerators: Optional[Dict[str, int]],
+                              use_spot: bool, region: Optional[str],
+                              zone: Optional[str],
+                              resources: Optional[Any] = None) -> List[Region]:
+        del accelerators, resources
+        regions = cls._catalog_module().get_region_zones_for_instance_type(
+            instance_type, use_spot)
+        if region is not None:
+            regions = [r for r in regions if r.name == region]
+        if zone is not None:
+            for r in regions:
+                assert r.zones is not None, r
+                r.set_zones([z for z in r.zones if z.name == zone])
+            regions = [r for r in regions if r.zones]
+        return regions
+
+    @classmethod
+    def optimize_by_zone(cls) -> bool:
+        return False
+
+    def validate_region_zone(
+            self, region: Optional[str],
+            zone: Optional[str]) -> Tuple[Optional[str], Optional[str]]:
+        return self._catalog_module().validate_region_zone(region, zone)
+
+    # ---- prices -------------------------------------------------------------
+    def instance_type_to_hourly_cost(self, instance_type: str, use_spot: bool,
+                                     region: Optional[str] = None,
+                                     zone: Optional[str] = None) -> float:
+        return self._catalog_module().get_hourly_cost(instance_type,
+                                                      use_spot=use_spot,
+                                                      region=region, zone=zone)
+
+    def accelerators_to_hourly_cost(self, accelerators: Dict[str, int],
+                                    use_spot: bool,
+                                    region: Optional[str] = None,
+                                    zone: Optional[str] = None) -> float:
+        del accelerators, use_spot, region, zone
+        return 0
+
+    def get_egress_cost(self, num_gigabytes: float) -> float:
+        del num_gigabytes
+        return 0.0
+
+    # ---- instance metadata --------------------------------------------------
+    def instance_type_exists(self, instance_type: str) -> bool:
+        return self._catalog_module().instance_type_exists(instance_type)
+
+    @classmethod
+    def get_vcpus_mem_from_instance_type(
+            cls, instance_type: str) -> Tuple[Optional[float], Optional[float]]:
+        return cls._catalog_module().get_vcpus_mem_from_instance_type(
+            instance_type)
+
+    @classmethod
+    def get_accelerators_from_instance_type(
+            cls, instance_type: str) -> Optional[Dict[str, Any]]:
+        return cls._catalog_module().get_accelerators_from_instance_type(
+            instance_type)
+
+    @classmethod
+    def get_default_instance_type(cls, cpus=None, memory=None, disk_tier=None,
+                                  local_disk=None, region=None, zone=None,
+                                  use_spot=False,
+                                  max_hourly_cost=None) -> Optional[str]:
+        return cls._catalog_module().get_default_instance_type(
+            cpus=cpus, memory=memory, disk_tier=disk_tier,
+            local_disk=local_disk, region=region, zone=zone,
+            use_spot=use_spot, max_hourly_cost=max_hourly_cost)
+
+    @classmethod
+    def check_disk_tier(cls, instance_type: Optional[str],
+                        disk_tier) -> Tuple[bool, str]:
+        del instance_type, disk_tier
+        return True, ''
+
+    # ---- feature gate -------------------------------------------------------
+    @classmethod
+    def _unsupported_features_for_resources(
+            cls, resources: Any,
+            region: Optional[str] = None
+    ) -> Dict[CloudImplementationFeatures, str]:
+        del resources, region
+        return dict(cls._CLOUD_UNSUPPORTED_FEATURES)
+
+    @classmethod
+    def check_features_are_supported(
+            cls, resources: Any,
+            requested_features: Set[CloudImplementationFeatures],
+            region: Optional[str] = None) -> None:
+        """Raises NotSupportedError naming the unsupported features
+        (sky/clouds/cloud.py:712-762)."""
+        unsupported = cls._unsupported_features_for_resources(
+            resources, region)
+        hit = requested_features.intersection(set(unsupported.keys()))
+        if hit:
+            rows = '\n\t'.join(f'{f.value} | {unsupported[f]}' for f in hit)
+            raise exceptions.NotSupportedError(
+                f'The following features are not supported by {cls._REPR}:'
+                f'\n\tFeature | Reason\n\t{rows}')
+
+    def _check_instance_type_accelerators_combination(self,
+                                                      resources: Any) -> None:
+        del resources
+
+    def _feature_hint(self, resources: Any, num_nodes: int) -> Optional[str]:
+        if resources.is_launchable():
+            self._check_instance_type_accelerators_combination(resources)
+        required = resources.get_required_cloud_features()
+        if num_nodes > 1:
+            required.add(CloudImplementationFeatures.MULTI_NODE)
+        try:
+            self.check_features_are_supported(resources, required)
+        except exceptions.NotSupportedError as e:
+            return str(e)
+        return None
+
+    # ---- feasibility ----------------------------------------------------------
+    def get_feasible_launchable_resources(
+            self, resources: Any,
+            num_nodes: int = 1) -> resources_utils.FeasibleResources:
+        """Offerings of this cloud that satisfy `resources`
+        (sky/clouds/cloud.py:459-501): feature gate, then the catalog filter
+        -- here one `skyopt_scan` call instead of pandas passes."""
+        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        hint = self._feature_hint(resources, num_nodes)
+        if hint is not None:
+            return resources_utils.FeasibleResources([], [], hint)
+        view = self._view()
+        b = engine.ProblemBuilder(view.store)
+        plan = self.plan_feasible(b, resources, want_list=True)
+        if plan.slot is None and plan.list_query is None and (
+                plan.explicit_instance is None):
+            fuzzy: List[str] = []
+            if plan.fuzzy_query is not None:
+                out = engine.scan(b, fuzzy_cap=self._fuzzy_cap(view),
+                                  device=view.device)
+                if not out.results['any_stage1'][plan.fuzzy_query]:
+                    fuzzy = engine.format_fuzzy(
+                        view.store, out.fuzzy_list(plan.fuzzy_query))
+            return resources_utils.FeasibleResources([], fuzzy, plan.hint)
+        if plan.explicit_instance is not None:
+            if plan.slot is None:
+                return resources_utils.FeasibleResources([], [], plan.hint)
+            return resources_utils.FeasibleResources(
+                [plan.make(plan.explicit_instance)], [], None)
+        n_inst = max(len(view.table.inst_names), 1)
+        out = engine.scan(b, list_cap=min(n_inst, 2048),
+                          fuzzy_cap=self._fuzzy_cap(view), device=view.device)
+        return self._feasible_from_scan(view, plan, out)
+
+    @staticmethod
+    def _fuzzy_cap(view) -> int:
+        return min(max(len(view.store.acc_keys), 1), 2048)
+
+    def _feasible_from_scan(self, view, plan: SlotPlan,
+                            out) -> resources_utils.FeasibleResources:
+        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        fuzzy: List[str] = []
+        gate = plan.gate_query if plan.gate_query is not None else (
+            plan.fuzzy_query)
+        if gate is not None and not out.results['any_stage1'][gate]:
+            fuzzy = engine.format_fuzzy(view.store, out.fuzzy_list(gate))
+            return resources_utils.FeasibleResources([], fuzzy, None)
+        q = plan.list_query
+        res = out.results[q]
+        names: List[str] = []
+        if res['best_inst'] >= 0:
+            if out.results['n_list'][q] > 0:
+                names = [
+                    view.store.inst_names[i] for i in out.instance_list(q)
+                ]
+            else:
+                names = [view.store.inst_names[int(res['best_inst'])]]
+        made = [plan.make(n) for n in names]
+        made = [m for m in made if m is not None]
+        return resources_utils.FeasibleResources(made, fuzzy, None)
+
+    def plan_feasible(self, builder, resources: Any,
+                      want_list: bool = False) -> SlotPlan:
+        """States `resources` against this cloud for the device: the template
+        shared by AWS, Azure, Lambda and the other single-table clouds
+        (aws.py:881-953, azure.py:485-557, lambda_cloud.py:217-280)."""
+        rules = self._rules()
+        view = self._view()
+        table = view.table
+        plan = SlotPlan()
+        use_spot = bool(resources.use_spot)
+        if use_spot and not rules.supports_spot:
+            return plan
+        by_zone = bool(table.has_zone_column and
+                       (use_spot or self.optimize_by_zone()))
+        slot_common = dict(
+            cloud=table.index, price_col=1 if use_spot else 0,
+            region_id=_exact_region(table, resources.region),
+            zone_id=_exact_zone(table, resources.zone),
+            split_by_zone=int(by_zone), us_first=int(rules.us_regions_first),
+            use_spot=int(use_spot))
+
+        if resources.instance_type is not None:
+            ok, _ = self.check_disk_tier(resources.instance_type,
+                                         resources.disk_tier)
+            inst = table.inst_index.get(resources.instance_type, -1)
+            plan.explicit_instance = resources.instance_type
+            launchable = resources.copy(accelerators=None)
+            plan.make = lambda name, r=launchable: r
+            if ok and inst >= 0:
+                plan.slot = builder.add_slot(inst_id=inst, **slot_common)
+            return plan
+
+        cloud_obj = self.__class__()
+
+        def make(instance_type: str):
+            ok, _ = self.check_disk_tier(instance_type, resources.disk_tier)
+            if not ok:
+                return None
+            return resources.copy(cloud=cloud_obj, instance_type=instance_type,
+                                  accelerators=None, cpus=None, memory=None)
+
+        plan.make = make
+        premium = self._needs_premium_disk(resources.disk_tier)
+        local_disk = (resources.local_disk
+                      if rules.supports_local_disk else None)
+        accelerators = resources.accelerators
+        if accelerators is None:
+            cpus, memory = resources.cpus, resources.memory
+            if cpus is None and memory is None:
+                cpus = f'{rules.default_cpus}+'
+            if memory is None:
+                memory = f'{rules.default_mem_ratio}x'
+            flags = _native.F_DEFAULT_FAMILY
+            if premium:
+                flags |= _native.F_PREMIUM_DISK
+            spec = builder.cpus_mem_query(
+                self._CATALOG, cpus, memory, resources.region, resources.zone,
+                use_spot, resources.max_hourly_cost, flags_require=flags,
+                local_disk=local_disk)
+            q = builder.add_query(spec)
+            plan.list_query = q
+            plan.slot = builder.add_slot(query=q, **slot_common)
+            return plan
+
+        assert len(accelerators) == 1, resources
+        acc, acc_count = list(accelerators.items())[0]
+        spec = builder.accelerator_query(
+            self._CATALOG, acc, acc_count, resources.cpus, resources.memory,
+            use_spot, resources.region, resources.zone,
+            resources.max_hourly_cost, local_disk=local_disk,
+            flags_require2=_native.F_PREMIUM_DISK if premium else 0,
+            want_list=want_list, want_fuzzy=True)
+        q = builder.add_query(spec)
+        plan.list_query = q
+        plan.fuzzy_query = q
+        plan.slot = builder.add_slot(query=q, **slot_common)
+        return plan
+
+    @classmethod
+    def _needs_premium_disk(cls, disk_tier) -> bool:
+        del disk_tier
+        return False
+
+    # Object-path variant kept for API parity; the fused optimizer never
+    # calls it.
+    def _get_feasible_launchable_resources(
+            self, resources: Any) -> resources_utils.FeasibleResources:
+        return self.get_feasible_launchable_resources(resources)
+
+
+def _exact_region(table, region: Optional[str]) -> int:
+    from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+    return engine.region_exact_id(table, region)
+
+
+def _exact_zone(table, zone: Optional[str]) -> int:
+    from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+    return engine.zone_exact_id(table, zone)
+
+
+class DummyCloud(Cloud):
+    """Zero egress cost from / to; used for the optimizer's source / sink."""
+    _REPR = 'DummyCloud'
+
+
+def cloud_in_iterable(cloud: Cloud, cloud_list: Iterable[Cloud]) -> bool:
+    return any(cloud.is_same_cloud(c) for c in cloud_list)

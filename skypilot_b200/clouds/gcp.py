@@ -1,0 +1,226 @@
+"""Google Cloud Platform (placement-relevant part of sky/clouds/gcp.py).
+
+GCP differs from the single-table clouds: accelerators are separate catalog
+rows (no InstanceType) billed on top of a host VM, candidates are always per
+zone, and the launchable zones are the accelerator's zones that also offer
+the host VM (gcp.py:281-331, :709-823; gcp_catalog.py:334-442).
+"""
+from typing import Any, Dict, Optional
+
+from skypilot_b200 import _native
+from skypilot_b200.catalog import rules
+from skypilot_b200.clouds import cloud
+from skypilot_b200.utils import registry
+
+
+def is_tpu(resources: Optional[Any]) -> bool:
+    if resources is None or resources.accelerators is None:
+        return False
+    acc = list(resources.accelerators.keys())[0]
+    return acc.startswith('tpu')
+
+
+def is_tpu_vm(resources: Optional[Any]) -> bool:
+    """TPU VM unless `accelerator_args: {tpu_vm: False}`
+    (sky/clouds/utils/gcp_utils.py:37-47)."""
+    if not is_tpu(resources):
+        return False
+    args = resources.accelerator_args
+    if args is None:
+        return True
+    return args.get('tpu_vm', True)
+
+
+@registry.CLOUD_REGISTRY.register
+class GCP(cloud.Cloud):
+    _REPR = 'GCP'
+    _CATALOG = 'gcp'
+
+    @classmethod
+    def _unsupported_features_for_resources(cls, resources: Any,
+                                            region: Optional[str] = None):
+        del region
+        unsupported = {}
+        if is_tpu(resources) and not is_tpu_vm(resources):
+            unsupported[cloud.CloudImplementationFeatures.MULTI_NODE] = (
+                'TPU node does not support multi-node. Please set '
+                'num_nodes to 1.')
+        unsupported[cloud.CloudImplementationFeatures.LOCAL_DISK] = (
+            'Local disk is not supported on GCP')
+        return unsupported
+
+    @classmethod
+    def optimize_by_zone(cls) -> bool:
+        return True
+
+    def get_egress_cost(self, num_gigabytes: float) -> float:
+        """Worldwide egress $/GB (gcp.py:395-404)."""
+        if num_gigabytes <= 1024:
+            return 0.12 * num_gigabytes
+        if num_gigabytes <= 1024 * 10:
+            return 0.11 * num_gigabytes
+        return 0.08 * num_gigabytes
+
+    def accelerators_to_hourly_cost(self, accelerators: Dict[str, int],
+                                    use_spot: bool,
+                                    region: Optional[str] = None,
+                                    zone: Optional[str] = None) -> float:
+        assert len(accelerators) == 1, accelerators
+        acc, acc_count = list(accelerators.items())[0]
+        return self._catalog_module().get_accelerator_hourly_cost(
+            acc, acc_count, use_spot=use_spot, region=region, zone=zone)
+
+    @classmethod
+    def get_accelerators_from_instance_type(
+            cls, instance_type: str) -> Optional[Dict[str, Any]]:
+        # GCP attaches accelerators separately; only the fixed A2/G2/A3 hosts
+        # imply one (gcp_catalog.py:313-331).
+        return rules.GCP_INSTANCE_TO_ACC.get(instance_type)
+
+    @classmethod
+    def regions_with_offering(cls, instance_type, accelerators, use_spot,
+                              region, zone, resources=None):
+        del resources
+        module = cls._catalog_module()
+        if accelerators is None:
+            regions = module.get_region_zones_for_instance_type(
+                instance_type, use_spot)
+        else:
+            assert len(accelerators) == 1, accelerators
+            acc, count = list(accelerators.items())[0]
+            regions = module.get_region_zones_for_accelerators(
+                acc, count, use_spot, instance_type=instance_type)
+        if region is not None:
+            regions = [r for r in regions if r.name == region]
+        if zone is not None:
+            for r in regions:
+                assert r.zones is not None, r
+                r.set_zones([z for z in r.zones if z.name == zone])
+            regions = [r for r in regions if r.zones]
+        return regions
+
+    def plan_feasible(self, builder, resources: Any,
+                      want_list: bool = False) -> cloud.SlotPlan:
+        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        view = self._view()
+        table = view.table
+        store = view.store
+        plan = cloud.SlotPlan()
+        use_spot = bool(resources.use_spot)
+        slot_common = dict(
+            cloud=table.index, price_col=1 if use_spot else 0,
+            region_id=engine.region_exact_id(table, resources.region),
+            zone_id=engine.zone_exact_id(table, resources.zone),
+            split_by_zone=1, us_first=0, use_spot=int(use_spot))
+
+        def acc_slot_fields(acc: str, count) -> Dict[str, Any]:
+            _, _, strict = engine.accelerator_sets(store, acc, count)
+            key = store.acc_key_index.get((acc, float(count)), -2)
+            return dict(acc_words=strict, cand_acc_key=key)
+
+        if resources.instance_type is not None:
+            plan.explicit_instance = resources.instance_type
+            plan.make = lambda name, r=resources: r
+            fields = dict(slot_common)
+            if resources._accelerators is not None:  # pylint: disable=protected-access
+                acc, count = list(resources.accelerators.items())[0]
+                fields.update(acc_slot_fields(acc, count))
+            if resources.instance_type == 'TPU-VM':
+                fields['inst_id'] = -2
+            else:
+                inst = table.inst_index.get(resources.instance_type, -1)
+                if inst < 0:
+                    return plan
+                fields['inst_id'] = inst
+            plan.slot = builder.add_slot(**fields)
+            return plan
+
+        gcp = GCP()
+        if resources.accelerators is None:
+            cpus, memory = resources.cpus, resources.memory
+            if cpus is None and memory is None:
+                cpus = f'{self._rules().default_cpus}+'
+            if memory is None:
+                memory = f'{self._rules().default_mem_ratio}x'
+            q = builder.add_query(
+                builder.cpus_mem_query(
+                    'gcp', cpus, memory, resources.region, resources.zone,
+                    use_spot, resources.max_hourly_cost,
+                    flags_require=_native.F_DEFAULT_FAMILY))
+            plan.list_query = q
+            plan.make = lambda name: resources.copy(
+                cloud=gcp, instance_type=name, accelerators=None, cpus=None,
+                memory=None)
+            plan.slot = builder.add_slot(query=q, **slot_common)
+            return plan
+
+        assert len(resources.accelerators) == 1, resources
+        acc, acc_count = list(resources.accelerators.items())[0]
+        tpu_vm = is_tpu_vm(resources)
+        # 1) do accelerator rows exist at all (else: fuzzy candidates)?
+        #    (common.py:657-676 on the full GCP frame)
+        gate = builder.add_query(
+            builder.accelerator_query(
+                'gcp', acc, acc_count, None if tpu_vm else resources.cpus,
+                None if tpu_vm else resources.memory, use_spot,
+                resources.region, resources.zone, resources.max_hourly_cost,
+                want_list=False, want_fuzzy=True))
+        plan.gate_query = gate
+        plan.fuzzy_query = gate
+        acc_dict = {acc: acc_count}
+        plan.make = lambda name: resources.copy(
+            cloud=gcp, instance_type=name, accelerators=acc_dict, cpus=None,
+            memory=None)
+        fields = dict(slot_common)
+        fields.update(acc_slot_fields(acc, acc_count))
+        fields['gate_query'] = gate
+
+        if tpu_vm:
+            # Fixed pseudo host 'TPU-VM' with documented vCPU / memory sizes
+            # (gcp.py:775-806).
+            n_cpus = 240 if 'v4' in acc else 96
+            mem = 400 if 'v4' in acc else 334
+            if not _fits(resources.cpus, n_cpus) or not _fits(
+                    resources.memory, mem):
+                return plan
+            plan.explicit_instance = 'TPU-VM'
+            plan.list_query = None
+            fields['inst_id'] = -2
+            plan.slot = builder.add_slot(**fields)
+            return plan
+
+        # 2) the host VM (gcp_catalog.py:359-393): a fixed A2/G2/A3/A4 type,
+        #    or the cheapest n1 VM with enough vCPUs / memory. Region, zone,
+        #    spot and max_hourly_cost deliberately do not take part.
+        cpus, memory = resources.cpus, resources.memory
+        if acc in rules.GCP_FIXED_HOSTS:
+            group = rules.GCP_GROUP_IDS.get((acc, acc_count))
+            if group is None:
+                return plan
+            spec = builder.cpus_mem_query('gcp', cpus, memory, group=group)
+        else:
+            table_cpus = rules.GCP_ACC_HOST_CPUS.get(
+                acc, rules.GCP_ACC_HOST_CPUS['DEFAULT'])
+            default_cpus = table_cpus.get(acc_count)
+            if cpus is None and memory is None:
+                assert default_cpus is not None, (acc, acc_count)
+                cpus = f'{default_cpus}+'
+            if memory is None:
+                assert cpus is not None, (acc, acc_count)
+                cpu_val = int(cpus.strip('+').strip('x'))
+                memory = f'{cpu_val * rules.GCP_GPU_MEMORY_CPU_RATIO}+'
+            spec = builder.cpus_mem_query(
+                'gcp', cpus, memory, flags_require=_native.F_HOST_FAMILY)
+        host = builder.add_query(spec)
+        plan.list_query = host
+        fields['query'] = host
+        plan.slot = builder.add_slot(**fields)
+        return plan
+
+
+def _fits(request: Optional[str], available: int) -> bool:
+    if request is None:
+        return True
+    if request.endswith('+'):
+        return float(request[:-1]) <= available
+    return float(request) == available

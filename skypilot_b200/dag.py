@@ -1,0 +1,83 @@
+"""`Dag`: tasks plus dependency edges (the optimizer-facing part of
+sky/dag.py: context manager, add / remove, `>>` edges, `is_chain` :159-178)."""
+import threading
+from typing import List, Optional
+
+import networkx as nx
+
+
+class Dag:
+    """A directed acyclic graph of Tasks; `with Dag() as dag:` collects the
+    tasks created inside the block."""
+
+    def __init__(self) -> None:
+        self.tasks: List['object'] = []
+        self.graph = nx.DiGraph()
+        self.name: Optional[str] = None
+
+    def add(self, task) -> None:
+        self.graph.add_node(task)
+        self.tasks.append(task)
+
+    def remove(self, task) -> None:
+        self.tasks.remove(task)
+        self.graph.remove_node(task)
+
+    def add_edge(self, op1, op2) -> None:
+        assert op1 in self.graph.nodes
+        assert op2 in self.graph.nodes
+        self.graph.add_edge(op1, op2)
+
+    def __len__(self) -> int:
+        return len(self.tasks)
+
+    def __enter__(self) -> 'Dag':
+        push_dag(self)
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback) -> None:
+        pop_dag()
+
+    def __repr__(self) -> str:
+        return f'DAG:\n ' + '\n '.join(repr(t) for t in self.tasks)
+
+    def get_graph(self):
+        return self.graph
+
+    def is_chain(self) -> bool:
+        """True iff the tasks form one linear chain: every node has at most
+        one parent / child and exactly one node has none."""
+        nodes = list(self.graph.nodes)
+        if not nodes:
+            return True
+        indeg = [self.graph.in_degree(n) for n in nodes]
+        outdeg = [self.graph.out_degree(n) for n in nodes]
+        return (max(outdeg) <= 1 and outdeg.count(0) == 1 and
+                max(indeg) <= 1 and indeg.count(0) == 1)
+
+
+class _DagContext(threading.local):
+    """Per-thread stack of the DAGs being built."""
+
+    def __init__(self):
+        super().__init__()
+        self.current: Optional[Dag] = None
+        self.stack: List[Dag] = []
+
+    def push(self, dag: Dag) -> None:
+        self.stack.append(dag)
+        self.current = dag
+
+    def pop(self) -> Optional[Dag]:
+        old = self.stack.pop()
+        self.current = self.stack[-1] if self.stack else None
+        return old
+
+
+_context = _DagContext()
+push_dag = _context.push
+pop_dag = _context.pop
+
+
+def get_current_dag() -> Optional[Dag]:
+    return _context.current

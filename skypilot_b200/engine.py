@@ -1,0 +1,505 @@
+"""Host-side assembly of libskyopt problems and the calls into the device.
+
+A `ProblemBuilder` collects catalog queries (constraint vectors), expansion
+slots, tasks and DAGs as numpy structured arrays (layouts of include/skyopt.h)
+and hands them to `skyopt_optimize` / `skyopt_scan` in ONE call; all row-level
+work (filter, argmin, region/zone expansion, cost, blocked filter, DP) happens
+on the GPU. There is no CPU implementation behind these calls.
+"""
+import ctypes
+import math
+import re
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from skypilot_b200 import _native
+from skypilot_b200.catalog.store import CatalogStore
+from skypilot_b200.utils import resources_utils
+
+NO_MATCH_ID = 65534  # a region / zone id no row carries
+_INF = float('inf')
+
+
+def parse_cpus(cpus: Optional[str]) -> Tuple[int, float]:
+    """'8' -> (EQ, 8.0), '8+' -> (GE, 8.0) (sky/catalog/common.py:431-452)."""
+    if cpus is None:
+        return _native.OP_NONE, 0.0
+    text = str(cpus)
+    body = text[:-1] if text.endswith('+') else text
+    try:
+        value = float(body)
+    except ValueError:
+        raise ValueError('The "cpus" field should be either a number or '
+                         f'a string "<number>+". Found: {cpus!r}') from None
+    return (_native.OP_GE if text.endswith('+') else _native.OP_EQ), value
+
+
+def parse_memory(memory: Optional[str]) -> Tuple[int, float]:
+    """'16' EQ, '16+' GE, '4x' RATIO (sky/catalog/common.py:455-478)."""
+    if memory is None:
+        return _native.OP_NONE, 0.0
+    text = str(memory)
+    body = text[:-1] if text.endswith(('+', 'x')) else text
+    try:
+        value = float(body)
+    except ValueError:
+        raise ValueError(
+            'The "memory" field should be either a number or a string '
+            f'"<number>+" or "<number>x". Found: {memory!r}') from None
+    if text.endswith('+'):
+        return _native.OP_GE, value
+    if text.endswith('x'):
+        return _native.OP_RATIO, value
+    return _native.OP_EQ, value
+
+
+def region_filter_id(table, region: Optional[str]) -> int:
+    """Case-insensitive region filter of _filter_region_zone (common.py:509)."""
+    if region is None:
+        return -1
+    return table.region_lower.get(region.lower(), NO_MATCH_ID)
+
+
+def zone_filter_id(table, zone: Optional[str]) -> int:
+    if zone is None:
+        return -1
+    return table.zone_lower.get(zone.lower(), NO_MATCH_ID)
+
+
+def region_exact_id(table, region: Optional[str]) -> int:
+    """Exact-name filter of regions_with_offering (aws.py:360-367)."""
+    if region is None:
+        return -1
+    return table.region_exact.get(region, NO_MATCH_ID)
+
+
+def zone_exact_id(table, zone: Optional[str]) -> int:
+    if zone is None:
+        return -1
+    return table.zone_exact.get(zone, NO_MATCH_ID)
+
+
+def accelerator_sets(store: CatalogStore, acc_name: str,
+                     acc_count) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Dictionary-level accelerator predicates -> key bitmasks.
+
+    exact   name.fullmatch(acc, case=False) & |count - c| <= 0.01
+            (common.py:657-658)
+    fuzzy   name.contains(acc, case=False)  & count >= c   (common.py:661-663)
+    strict  name.fullmatch(acc, case=False) & count == c   (GCP
+            _get_accelerator, gcp_catalog.py:404-417)
+    The string predicates run once per distinct (name, count) pair of the
+    catalog dictionary; rows carry only the pair's id.
+    """
+    pattern = re.compile(acc_name, flags=re.IGNORECASE)
+    count = float(acc_count)
+    exact = store.accelerator_set(lambda n, c: pattern.fullmatch(n) is not None
+                                  and abs(c - count) <= 0.01)
+    fuzzy = store.accelerator_set(
+        lambda n, c: pattern.search(n) is not None and c >= count)
+    strict = store.accelerator_set(lambda n, c: pattern.fullmatch(n) is not None
+                                   and c == count)
+    return exact, fuzzy, strict
+
+
+def format_fuzzy(store: CatalogStore, keys: Sequence[int]) -> List[str]:
+    """'A100:8' / 'A10:0.17' strings (sky/catalog/common.py:668-675)."""
+    out = []
+    for k in keys:
+        name, count = store.acc_keys[int(k)]
+        shown = int(count) if float(count).is_integer() else f'{count:.2f}'
+        out.append(f'{name}:{shown}')
+    return out
+
+
+class ProblemBuilder:
+    """Accumulates one batch for the device."""
+
+    def __init__(self, store: CatalogStore):
+        self.store = store
+        self.queries: List[Dict[str, Any]] = []
+        self._sets: List[bytes] = []
+        self._set_index: Dict[bytes, int] = {}
+        self.slots: List[Dict[str, Any]] = []
+        self.tasks: List[Dict[str, Any]] = []
+        self.parents: List[int] = []
+        self.tariffs: List[float] = []
+        self.blocked: List[Dict[str, int]] = []
+        self.dags: List[Dict[str, int]] = []
+
+    # -- sets / queries -----------------------------------------------------
+    def add_set(self, words: Optional[np.ndarray]) -> int:
+        if words is None:
+            return -1
+        key = np.ascontiguousarray(words, dtype=np.uint32).tobytes()
+        idx = self._set_index.get(key)
+        if idx is None:
+            idx = len(self._sets)
+            self._sets.append(key)
+            self._set_index[key] = idx
+        return idx
+
+    def add_query(self, spec: Dict[str, Any]) -> int:
+        q = dict(spec)
+        q['acc_set'] = self.add_set(q.pop('acc_words', None))
+        q['fuzzy_set'] = self.add_set(q.pop('fuzzy_words', None))
+        self.queries.append(q)
+        return len(self.queries) - 1
+
+    def cpus_mem_query(self,
+                       cloud: str,
+                       cpus: Optional[str],
+                       memory: Optional[str],
+                       region: Optional[str] = None,
+                       zone: Optional[str] = None,
+                       use_spot: bool = False,
+                       max_hourly_cost: Optional[float] = None,
+                       *,
+                       flags_require: int = 0,
+                       group: int = 0,
+                       local_disk: Optional[str] = None) -> Dict[str, Any]:
+        """Constraint vector of get_instance_type_for_cpus_mem_impl
+        (sky/catalog/common.py:518-569)."""
+        table = self.store.cloud(cloud)
+        cop, cval = parse_cpus(cpus)
+        mop, mval = parse_memory(memory)
+        # Spot prices only order the rows when a price cap is set
+        # (common.py:557-561).
+        spot = bool(use_spot and max_hourly_cost is not None)
+        spec = {
+            'cloud': table.index, 'qflags': 0,
+            'flags_require': flags_require | _native.F_HAS_INSTANCE,
+            'group': group, 'price_col': 1 if spot else 0,
+            'cpus_op': cop, 'cpus': cval, 'mem_op': mop, 'mem': mval,
+            'region_id': region_filter_id(table, region),
+            'zone_id': zone_filter_id(table, zone),
+            'max_price': _INF if max_hourly_cost is None else float(
+                max_hourly_cost),
+        }
+        _apply_local_disk(spec, local_disk)
+        return spec
+
+    def accelerator_query(self,
+                          cloud: str,
+                          acc_name: str,
+                          acc_count,
+                          cpus: Optional[str] = None,
+                          memory: Optional[str] = None,
+                          use_spot: bool = False,
+                          region: Optional[str] = None,
+                          zone: Optional[str] = None,
+                          max_hourly_cost: Optional[float] = None,
+                          *,
+                          local_disk: Optional[str] = None,
+                          flags_require2: int = 0,
+                          want_list: bool = False,
+                          want_fuzzy: bool = True) -> Dict[str, Any]:
+        """Constraint vector of get_instance_type_for_accelerator_impl
+        (sky/catalog/common.py:641-694)."""
+        table = self.store.cloud(cloud)
+        exact, fuzzy, _ = accelerator_sets(self.store, acc_name, acc_count)
+        cop, cval = parse_cpus(cpus)
+        mop, mval = parse_memory(memory)
+        qflags = _native.Q_ACC
+        if want_fuzzy:
+            qflags |= _native.Q_FUZZY
+        if want_list:
+            qflags |= _native.Q_LIST
+            if max_hourly_cost is None:
+                qflags |= _native.Q_KEEP_NAN
+        spec = {
+            'cloud': table.index, 'qflags': qflags, 'flags_require': 0,
+            'flags_require2': flags_require2,
+            'acc_words': exact, 'fuzzy_words': fuzzy if want_fuzzy else None,
+            'price_col': 1 if use_spot else 0,
+            'cpus_op': cop, 'cpus': cval, 'mem_op': mop, 'mem': mval,
+            'region_id': region_filter_id(table, region),
+            'zone_id': zone_filter_id(table, zone),
+            'max_price': _INF if max_hourly_cost is None else float(
+                max_hourly_cost),
+        }
+        _apply_local_disk(spec, local_disk)
+        return spec
+
+    # -- slots / tasks / dags ----------------------------------------------
+    def add_slot(self, **fields) -> int:
+        slot = {
+            'query': -1, 'inst_id': -1, 'gate_query': -1, 'acc_set': -1,
+            'price_col': 0, 'region_id': -1, 'zone_id': -1,
+            'split_by_zone': 0, 'us_first': 0, 'cand_acc_key': -1,
+            'use_spot': 0, 'hours': 1.0, 'node_mult': 1.0,
+            'time_value': 3600.0
+        }
+        words = fields.pop('acc_words', None)
+        slot.update(fields)
+        if words is not None:
+            slot['acc_set'] = self.add_set(words)
+        self.slots.append(slot)
+        return len(self.slots) - 1
+
+    def add_task(self,
+                 slot_begin: int,
+                 slot_end: int,
+                 parents: Sequence[int] = (),
+                 edge_tariffs: Sequence[Sequence[float]] = (),
+                 src_tariff: Optional[Sequence[float]] = None) -> int:
+        n_clouds = len(self.store.clouds)
+        task = {
+            'slot_begin': slot_begin, 'slot_end': slot_end,
+            'n_parents': len(parents), 'parent_begin': len(self.parents),
+            'edge_tariff_begin': len(self.tariffs), 'src_tariff_begin': -1
+        }
+        self.parents.extend(int(p) for p in parents)
+        assert len(edge_tariffs) == len(parents)
+        for row in edge_tariffs:
+            assert len(row) == n_clouds
+            self.tariffs.extend(float(v) for v in row)
+        if src_tariff is not None:
+            assert len(src_tariff) == n_clouds
+            task['src_tariff_begin'] = len(self.tariffs)
+            self.tariffs.extend(float(v) for v in src_tariff)
+        self.tasks.append(task)
+        return len(self.tasks) - 1
+
+    def add_blocked(self, **fields) -> int:
+        entry = {
+            'cloud': -1, 'inst_id': -1, 'region_id': -1, 'zone_id': -1,
+            'acc_key': -1, 'use_spot': -1
+        }
+        entry.update(fields)
+        self.blocked.append(entry)
+        return len(self.blocked) - 1
+
+    def add_dag(self, task_begin: int, task_end: int, is_chain: bool,
+                minimize_cost: bool, blocked_begin: int = 0,
+                blocked_end: int = 0) -> int:
+        self.dags.append({
+            'task_begin': task_begin, 'task_end': task_end,
+            'is_chain': int(is_chain), 'minimize_cost': int(minimize_cost),
+            'blocked_begin': blocked_begin, 'blocked_end': blocked_end
+        })
+        return len(self.dags) - 1
+
+    # -- packing ------------------------------------------------------------
+    @staticmethod
+    def _pack(rows: List[Dict[str, Any]], dtype: np.dtype) -> np.ndarray:
+        arr = np.zeros(max(len(rows), 1), dtype=dtype)
+        names = [n for n in dtype.names if n != 'pad_']
+        for name in names:
+            default = -1 if name in ('acc_set', 'fuzzy_set', 'region_id',
+                                     'zone_id') else 0
+            arr[name][:len(rows)] = [r.get(name, default) for r in rows]
+        return arr
+
+    def pack(self) -> 'PackedProblem':
+        return PackedProblem(self)
+
+
+def _apply_local_disk(spec: Dict[str, Any], local_disk: Optional[str]) -> None:
+    """AWS local-disk filter (sky/catalog/common.py:481-506)."""
+    if local_disk is None:
+        return
+    mode, size, at_least = resources_utils.parse_local_disk_str(
+        local_disk.lower())
+    if mode not in ('nvme', 'ssd'):
+        raise ValueError('Local disk should be either nvme or ssd. '
+                         f'Got {local_disk}.')
+    spec['flags_require'] = spec.get('flags_require', 0) | _native.F_SSD
+    if mode == 'nvme':
+        spec['flags_require'] |= _native.F_NVME
+    spec['disk_op'] = _native.DISK_GE if at_least else _native.DISK_NEAR
+    spec['disk_size'] = float(size)
+
+
+class PackedProblem:
+    """numpy arrays + the ctypes view over them."""
+
+    def __init__(self, b: ProblemBuilder):
+        self.store = b.store
+        self.queries = ProblemBuilder._pack(b.queries, _native.QUERY_DTYPE)
+        self.n_queries = len(b.queries)
+        self.n_sets = len(b._sets)  # pylint: disable=protected-access
+        self.acc_sets = np.frombuffer(
+            b''.join(b._sets) or bytes(4 * _native.ACC_SET_WORDS),  # pylint: disable=protected-access
+            dtype=np.uint32).copy()
+        self.slots = ProblemBuilder._pack(b.slots, _native.SLOT_DTYPE)
+        self.n_slots = len(b.slots)
+        self.tasks = ProblemBuilder._pack(b.tasks, _native.TASK_DTYPE)
+        self.n_tasks = len(b.tasks)
+        self.parents = np.asarray(b.parents or [0], dtype=np.int32)
+        self.n_parents = len(b.parents)
+        self.tariffs = np.asarray(b.tariffs or [0.0], dtype=np.float64)
+        self.n_tariffs = len(b.tariffs)
+        self.blocked = ProblemBuilder._pack(b.blocked, _native.BLOCKED_DTYPE)
+        self.n_blocked = len(b.blocked)
+        self.dags = ProblemBuilder._pack(b.dags, _native.DAG_DTYPE)
+        self.n_dags = len(b.dags)
+
+    def c_problem(self) -> _native.Problem:
+        p = _native.Problem()
+        p.queries = self.queries.ctypes.data
+        p.n_queries = self.n_queries
+        p.acc_sets = self.acc_sets.ctypes.data
+        p.n_acc_sets = self.n_sets
+        p.slots = self.slots.ctypes.data
+        p.n_slots = self.n_slots
+        p.tasks = self.tasks.ctypes.data
+        p.n_tasks = self.n_tasks
+        p.parents = self.parents.ctypes.data
+        p.n_parents = self.n_parents
+        p.tariffs = self.tariffs.ctypes.data
+        p.n_tariffs = self.n_tariffs
+        p.blocked = self.blocked.ctypes.data
+        p.n_blocked = self.n_blocked
+        p.dags = self.dags.ctypes.data
+        p.n_dags = self.n_dags
+        return p
+
+    def h2d_bytes(self) -> int:
+        return int(self.queries.nbytes * (self.n_queries > 0) +
+                   self.acc_sets.nbytes * (self.n_sets > 0) +
+                   self.slots.nbytes + self.tasks.nbytes +
+                   self.parents.nbytes + self.tariffs.nbytes +
+                   self.blocked.nbytes * (self.n_blocked > 0) +
+                   self.dags.nbytes)
+
+
+class Solution:
+    """Outputs of skyopt_optimize as numpy arrays."""
+
+    def __init__(self, packed: PackedProblem, want_tables: bool,
+                 table_cap: int = 0):
+        self.packed = packed
+        self.scan = np.zeros(max(packed.n_queries, 1),
+                             dtype=_native.SCAN_RESULT_DTYPE)
+        self.slot_count = np.zeros(max(packed.n_slots, 1), dtype=np.int32)
+        self.slot_inst = np.zeros(max(packed.n_slots, 1), dtype=np.int32)
+        self.chosen = np.zeros(max(packed.n_tasks, 1),
+                               dtype=_native.CANDIDATE_DTYPE)
+        self.chosen_index = np.zeros(max(packed.n_tasks, 1), dtype=np.int32)
+        self.task_n = np.zeros(max(packed.n_tasks, 1), dtype=np.int32)
+        self.dag = np.zeros(max(packed.n_dags, 1),
+                            dtype=_native.DAG_RESULT_DTYPE)
+        self.tables: Optional[np.ndarray] = None
+        self.table_offsets: Optional[np.ndarray] = None
+        if want_tables:
+            cap = table_cap or max(
+                1, packed.n_slots * max(packed.store.max_group_rows, 1))
+            self.tables = np.zeros(cap, dtype=_native.CANDIDATE_DTYPE)
+            self.table_offsets = np.zeros(packed.n_tasks + 1, dtype=np.int64)
+        self.stats = _native.Stats()
+
+    def c_solution(self) -> _native.Solution:
+        s = _native.Solution()
+        s.scan = self.scan.ctypes.data
+        s.slot_count = self.slot_count.ctypes.data
+        s.slot_inst = self.slot_inst.ctypes.data
+        s.chosen = self.chosen.ctypes.data
+        s.chosen_index = self.chosen_index.ctypes.data
+        s.task_n_candidates = self.task_n.ctypes.data
+        s.dag = self.dag.ctypes.data
+        if self.tables is not None:
+            s.candidates = self.tables.ctypes.data
+            s.cand_cap = len(self.tables)
+            s.task_cand_offset = self.table_offsets.ctypes.data
+        else:
+            s.candidates = None
+            s.cand_cap = 0
+            s.task_cand_offset = None
+        return s
+
+    def d2h_bytes(self) -> int:
+        p = self.packed
+        return int(p.n_queries * 20 + p.n_slots * 8 + p.n_tasks *
+                   (_native.CANDIDATE_DTYPE.itemsize + 8) + p.n_dags * 16)
+
+    def task_table(self, task: int) -> np.ndarray:
+        assert self.tables is not None
+        return self.tables[self.table_offsets[task]:self.table_offsets[task +
+                                                                        1]]
+
+
+def solve(builder: ProblemBuilder,
+          device: int = 0,
+          want_tables: bool = False) -> Solution:
+    """One `skyopt_optimize` call for everything the builder holds."""
+    packed = builder.pack()
+    sol = Solution(packed, want_tables)
+    lib = _native.load()
+    handle = builder.store.handle(device)
+    prob = packed.c_problem()
+    csol = sol.c_solution()
+    _native.check(
+        lib.skyopt_optimize(handle, ctypes.byref(prob), ctypes.byref(csol),
+                            ctypes.byref(sol.stats)))
+    return sol
+
+
+def solve_timed(builder: ProblemBuilder, iters: int, flush_l2: bool = True,
+                device: int = 0):
+    """Device-resident timing loop (bench.py): per-iteration kernel times."""
+    packed = builder.pack()
+    sol = Solution(packed, False)
+    lib = _native.load()
+    handle = builder.store.handle(device)
+    prob = packed.c_problem()
+    csol = sol.c_solution()
+    iter_ms = np.zeros(iters, dtype=np.float32)
+    scan_ms = np.zeros(iters, dtype=np.float32)
+    _native.check(
+        lib.skyopt_optimize_timed(handle, ctypes.byref(prob),
+                                  ctypes.byref(csol), iters, int(flush_l2),
+                                  iter_ms.ctypes.data, scan_ms.ctypes.data,
+                                  ctypes.byref(sol.stats)))
+    return sol, iter_ms, scan_ms
+
+
+class ScanOutput:
+
+    def __init__(self, results, list_ids, list_prices, fuzzy_keys,
+                 fuzzy_prices, stats):
+        self.results = results
+        self.list_ids = list_ids
+        self.list_prices = list_prices
+        self.fuzzy_keys = fuzzy_keys
+        self.fuzzy_prices = fuzzy_prices
+        self.stats = stats
+
+    def instance_list(self, q: int) -> List[int]:
+        n = int(self.results['n_list'][q])
+        return [int(v) for v in self.list_ids[q, :n]]
+
+    def fuzzy_list(self, q: int) -> List[int]:
+        n = int(self.results['n_fuzzy'][q])
+        return [int(v) for v in self.fuzzy_keys[q, :n]]
+
+
+def scan(builder: ProblemBuilder,
+         list_cap: int = 0,
+         fuzzy_cap: int = 0,
+         device: int = 0) -> ScanOutput:
+    """`skyopt_scan`: filter + argmin (+ sorted tables) for the queries."""
+    packed = builder.pack()
+    n = packed.n_queries
+    assert n > 0
+    lib = _native.load()
+    handle = builder.store.handle(device)
+    results = np.zeros(n, dtype=_native.SCAN_RESULT_DTYPE)
+    list_ids = list_prices = fuzzy_keys = fuzzy_prices = None
+    if list_cap:
+        list_ids = np.full((n, list_cap), -1, dtype=np.int32)
+        list_prices = np.full((n, list_cap), math.nan, dtype=np.float64)
+    if fuzzy_cap:
+        fuzzy_keys = np.full((n, fuzzy_cap), -1, dtype=np.int32)
+        fuzzy_prices = np.full((n, fuzzy_cap), math.nan, dtype=np.float64)
+    stats = _native.Stats()
+    _native.check(
+        lib.skyopt_scan(handle, packed.queries.ctypes.data, n,
+                        packed.acc_sets.ctypes.data, packed.n_sets,
+                        results.ctypes.data, _native.ptr(list_ids),
+                        _native.ptr(list_prices), list_cap,
+                        _native.ptr(fuzzy_keys), _native.ptr(fuzzy_prices),
+                        fuzzy_cap, ctypes.byref(stats)))
+    return ScanOutput(results, list_ids, list_prices, fuzzy_keys,
+                      fuzzy_prices, stats)

@@ -1,0 +1,663 @@
+"""The placement optimizer behind `Optimizer.optimize(dag)`.
+
+Public surface and semantics follow sky/optimizer.py (Optimizer.optimize
+:106-142, _optimize_dag :1381-1512, _estimate_nodes_cost_or_time :239-426,
+_fill_in_launchable_resources :1664-1785, chain DP :429-487, general DAGs
+:490-637, totals :640-698, egress :75-104 / :196-236). The inner loops do not
+run here: `_solve()` states the whole DAG -- every (task, requested
+Resources, cloud) feasibility filter, the region/zone expansion, per-candidate
+cost, the blocked filter and the DP / exact search -- as ONE device problem
+(engine.ProblemBuilder -> skyopt_optimize) and reads back the plan. Host code
+keeps what is Python by nature: per-cloud rules, time-estimator callbacks,
+egress tariffs (a few scalars per edge) and building the `Resources` objects
+of the answer.
+"""
+import collections
+import enum
+import logging
+from typing import Any, Dict, Iterable, List, Optional, Tuple
+
+import networkx as nx
+
+from skypilot_b200 import catalog
+from skypilot_b200 import check as sky_check
+from skypilot_b200 import clouds
+from skypilot_b200 import dag as dag_lib
+from skypilot_b200 import engine
+from skypilot_b200 import exceptions
+from skypilot_b200 import resources as resources_lib
+from skypilot_b200 import task as task_lib
+from skypilot_b200.utils import resources_utils
+
+logger = logging.getLogger(__name__)
+
+_DUMMY_SOURCE_NAME = 'skypilot-dummy-source'
+_DUMMY_SINK_NAME = 'skypilot-dummy-sink'
+
+_TaskToCostMap = Dict[task_lib.Task, Dict[resources_lib.Resources, float]]
+_PerCloudCandidates = Dict[clouds.Cloud, List[resources_lib.Resources]]
+_TaskToPerCloudCandidates = Dict[task_lib.Task, _PerCloudCandidates]
+
+
+class OptimizeTarget(enum.Enum):
+    COST = 0
+    TIME = 1
+
+
+class DummyResources(resources_lib.Resources):
+    """Resources of the dummy source / sink: zero cost, zero egress."""
+    _REPR = 'DummyResources'
+
+    def __repr__(self) -> str:
+        return DummyResources._REPR
+
+    def get_cost(self, seconds):
+        return 0
+
+
+def _is_dummy(task: task_lib.Task) -> bool:
+    return task.name in (_DUMMY_SOURCE_NAME, _DUMMY_SINK_NAME)
+
+
+class _SlotInfo:
+    """Host memo of one device slot: who asked, on which cloud, and how to
+    turn the answer back into a Resources."""
+    __slots__ = ('task', 'resources', 'cloud', 'plan', 'table')
+
+    def __init__(self, task, resources, cloud, plan, table):
+        self.task = task
+        self.resources = resources
+        self.cloud = cloud
+        self.plan = plan
+        self.table = table
+
+
+class _Problem:
+    """A DAG stated for the device plus what is needed to read the answer."""
+
+    def __init__(self, builder, tasks, slot_info, hints, minimize_cost,
+                 is_chain):
+        self.builder = builder
+        self.tasks: List[task_lib.Task] = tasks
+        self.slot_info: List[_SlotInfo] = slot_info
+        self.hints = hints
+        self.minimize_cost = minimize_cost
+        self.is_chain = is_chain
+        self.solution: Optional[engine.Solution] = None
+
+    def launchable(self, cand) -> resources_lib.Resources:
+        """The launchable Resources of one device candidate record."""
+        info = self.slot_info[int(cand['slot'])]
+        inst = int(cand['inst_id'])
+        name = 'TPU-VM' if inst == -2 else (
+            self.builder.store.inst_names[inst])
+        base = info.plan.make(name)
+        region = info.table.region_names[int(cand['region_id'])]
+        zid = int(cand['zone_id'])
+        if zid >= 0:
+            return base.copy(region=region, zone=info.table.zone_names[zid])
+        return base.copy(region=region)
+
+
+class Optimizer:
+    """Assigns the best launchable Resources to every task of a DAG."""
+
+    # ------------------------------------------------------------------ egress
+    @staticmethod
+    def _egress_cost(src_cloud: clouds.Cloud, dst_cloud: clouds.Cloud,
+                     gigabytes: float) -> float:
+        if isinstance(src_cloud, clouds.DummyCloud) or isinstance(
+                dst_cloud, clouds.DummyCloud):
+            return 0.0
+        if not src_cloud.is_same_cloud(dst_cloud):
+            return src_cloud.get_egress_cost(num_gigabytes=gigabytes)
+        return 0.0
+
+    @staticmethod
+    def _egress_time(src_cloud: clouds.Cloud, dst_cloud: clouds.Cloud,
+                     gigabytes: float) -> float:
+        if isinstance(src_cloud, clouds.DummyCloud) or isinstance(
+                dst_cloud, clouds.DummyCloud):
+            return 0.0
+        if not src_cloud.is_same_cloud(dst_cloud):
+            bandwidth_gbps = 10  # sky/optimizer.py:97-101
+            return gigabytes * 8 / bandwidth_gbps
+        return 0.0
+
+    @staticmethod
+    def _get_egress_info(parent, parent_resources, node, resources):
+        if isinstance(parent_resources.cloud, clouds.DummyCloud):
+            if node.get_inputs() is None:
+                return None, None, 0
+            src_cloud = node.get_inputs_cloud()
+            nbytes = node.get_estimated_inputs_size_gigabytes()
+        else:
+            src_cloud = parent_resources.cloud
+            nbytes = parent.get_estimated_outputs_size_gigabytes()
+        return src_cloud, resources.cloud, nbytes
+
+    @staticmethod
+    def _egress_cost_or_time(minimize_cost: bool, parent, parent_resources,
+                             node, resources):
+        src_cloud, dst_cloud, nbytes = Optimizer._get_egress_info(
+            parent, parent_resources, node, resources)
+        if not nbytes:
+            return 0
+        assert src_cloud is not None and dst_cloud is not None
+        fn = Optimizer._egress_cost if minimize_cost else (
+            Optimizer._egress_time)
+        return fn(src_cloud, dst_cloud, nbytes)
+
+    # -------------------------------------------------------------- public API
+    @staticmethod
+    def optimize(dag: 'dag_lib.Dag',
+                 minimize: OptimizeTarget = OptimizeTarget.COST,
+                 blocked_resources: Optional[Iterable[
+                     resources_lib.Resources]] = None,
+                 quiet: bool = False) -> 'dag_lib.Dag':
+        """Finds the best execution plan and stores it in
+        `task.best_resources` of every task (sky/optimizer.py:106-142).
+
+        Raises:
+            exceptions.ResourcesUnavailableError: a task has no candidate.
+            exceptions.NoCloudAccessError: no cloud is enabled.
+        """
+        _check_specified_clouds(dag)
+        Optimizer._add_dummy_source_sink_nodes(dag)
+        try:
+            Optimizer._optimize_dag(
+                dag=dag,
+                minimize_cost=minimize == OptimizeTarget.COST,
+                blocked_resources=blocked_resources,
+                quiet=quiet)
+        finally:
+            Optimizer._remove_dummy_source_sink_nodes(dag)
+        return dag
+
+    @staticmethod
+    def _add_dummy_source_sink_nodes(dag: 'dag_lib.Dag') -> None:
+        """Source -> every root, every leaf -> Sink (sky/optimizer.py:145)."""
+        graph = dag.get_graph()
+        roots = [n for n, d in graph.in_degree() if d == 0]
+        leaves = [n for n, d in graph.out_degree() if d == 0]
+
+        def make_dummy(name):
+            dummy = task_lib.Task(name)
+            dummy.set_resources({DummyResources(cloud=clouds.DummyCloud())})
+            dummy.set_time_estimator(lambda _: 0)
+            return dummy
+
+        with dag:
+            source = make_dummy(_DUMMY_SOURCE_NAME)
+            for node in roots:
+                source >> node  # pylint: disable=pointless-statement
+            sink = make_dummy(_DUMMY_SINK_NAME)
+            for node in leaves:
+                node >> sink  # pylint: disable=pointless-statement
+
+    @staticmethod
+    def _remove_dummy_source_sink_nodes(dag: 'dag_lib.Dag') -> None:
+        source = [t for t in dag.tasks if t.name == _DUMMY_SOURCE_NAME]
+        sink = [t for t in dag.tasks if t.name == _DUMMY_SINK_NAME]
+        if not source and not sink:
+            return
+        assert len(source) == len(sink) == 1, dag.tasks
+        dag.remove(source[0])
+        dag.remove(sink[0])
+
+    # ---------------------------------------------------- problem construction
+    @staticmethod
+    def _runtime(task, n_resources: int, orig_resources) -> float:
+        """Estimated runtime in seconds (sky/optimizer.py:320-339)."""
+        if task.time_estimator_func is None:
+            return 1 * 3600
+        if n_resources == 1 and task.time_estimator_func is None:
+            return 1 * 3600
+        return task.estimate_runtime(orig_resources)
+
+    @staticmethod
+    def _state_problem(dag_graph,
+                       topo_real: List[task_lib.Task],
+                       minimize_cost: bool,
+                       blocked_resources,
+                       is_chain: bool,
+                       builder: Optional[engine.ProblemBuilder] = None
+                      ) -> _Problem:
+        """States all real tasks of one DAG for the device."""
+        enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+            raise_if_no_cloud_access=True)
+        store = catalog.get_store()
+        b = builder if builder is not None else engine.ProblemBuilder(store)
+        n_clouds = len(store.clouds)
+        cloud_objs = [_cloud_object(t.name) for t in store.clouds]
+        slot_info: List[_SlotInfo] = [None] * len(b.slots)  # type: ignore
+        hints: Dict[Any, Dict[Any, str]] = collections.defaultdict(dict)
+        local_index = {t: i for i, t in enumerate(topo_real)}
+        task_begin = len(b.tasks)
+        for task in topo_real:
+            slot_begin = len(b.slots)
+            n_res = len(list(task.resources))
+            for res in task.resources:
+                res.validate()
+                if res.cloud is not None and not clouds.cloud_in_iterable(
+                        res.cloud, enabled):
+                    continue
+                clouds_list = [res.cloud] if res.cloud is not None else enabled
+                runtime = Optimizer._runtime(task, n_res, res)
+                for cloud in clouds_list:
+                    if not store.has_cloud(cloud.canonical_name()):
+                        continue
+                    hint = cloud._feature_hint(res, task.num_nodes)  # pylint: disable=protected-access
+                    if hint is not None:
+                        hints[res][cloud] = hint
+                        continue
+                    before = len(b.slots)
+                    plan = cloud.plan_feasible(b, res)
+                    if plan.hint is not None:
+                        hints[res][cloud] = plan.hint
+                    if plan.slot is None:
+                        continue
+                    assert len(b.slots) == before + 1
+                    slot = b.slots[plan.slot]
+                    slot['hours'] = runtime / 3600
+                    slot['node_mult'] = float(max(task.num_nodes, 0))
+                    slot['time_value'] = float(runtime)
+                    slot_info.append(
+                        _SlotInfo(task, res, cloud, plan,
+                                  store.cloud(cloud.canonical_name())))
+            slot_end = len(b.slots)
+            parents = [
+                p for p in dag_graph.predecessors(task) if not _is_dummy(p)
+            ]
+            edge_rows = []
+            for p in parents:
+                nbytes = p.get_estimated_outputs_size_gigabytes()
+                if not nbytes:
+                    edge_rows.append([0.0] * n_clouds)
+                elif minimize_cost:
+                    edge_rows.append([
+                        float(c.get_egress_cost(num_gigabytes=nbytes))
+                        for c in cloud_objs
+                    ])
+                else:
+                    edge_rows.append([nbytes * 8 / 10] * n_clouds)
+            src_row = None
+            if not parents and task.get_inputs() is not None:
+                nbytes = task.get_estimated_inputs_size_gigabytes()
+                if nbytes:
+                    src = task.get_inputs_cloud()
+                    fn = (Optimizer._egress_cost
+                          if minimize_cost else Optimizer._egress_time)
+                    src_row = [float(fn(src, c, nbytes)) for c in cloud_objs]
+            b.add_task(slot_begin, slot_end,
+                       [local_index[p] for p in parents], edge_rows, src_row)
+        blocked_begin = len(b.blocked)
+        for blocked in blocked_resources or []:
+            _add_blocked(b, store, blocked)
+        b.add_dag(task_begin, len(b.tasks), is_chain, minimize_cost,
+                  blocked_begin, len(b.blocked))
+        return _Problem(b, list(topo_real), slot_info, hints, minimize_cost,
+                        is_chain)
+
+    @staticmethod
+    def _solve(problem: _Problem, want_tables: bool = False) -> engine.Solution:
+        problem.solution = engine.solve(problem.builder,
+                                        device=catalog.get_device(),
+                                        want_tables=want_tables)
+        return problem.solution
+
+    # ------------------------------------------------------------ _optimize_dag
+    @staticmethod
+    def _optimize_dag(
+        dag: 'dag_lib.Dag',
+        minimize_cost: bool = True,
+        blocked_resources: Optional[Iterable[resources_lib.Resources]] = None,
+        quiet: bool = False,
+    ) -> Dict[task_lib.Task, resources_lib.Resources]:
+        """Finds the optimal task -> Resources mapping for the whole DAG,
+        egress included (sky/optimizer.py:1381-1512). `dag` carries the dummy
+        source / sink like in the reference."""
+        blocked = list(blocked_resources or [])
+        ordered_choice = Optimizer._resolve_ordered_resources(dag, blocked)
+        graph = dag.get_graph()
+        topo_order = list(nx.topological_sort(graph))
+        topo_real = [t for t in topo_order if not _is_dummy(t)]
+        saved = {}
+        for task, choice in ordered_choice.items():
+            saved[task] = task.resources
+            task.resources = {choice}
+        try:
+            problem = Optimizer._state_problem(graph, topo_real, minimize_cost,
+                                               blocked, dag.is_chain())
+            sol = Optimizer._solve(problem, want_tables=not quiet)
+        finally:
+            for task, original in saved.items():
+                task.resources = original
+        res = sol.dag[0]
+        if res['status'] == 1:
+            failed = topo_real[int(res['task_fail'])]
+            Optimizer._raise_unavailable(failed, blocked)
+        if res['status'] != 0:
+            raise exceptions.ResourcesUnavailableError(
+                'The DAG is too large for the exact general-DAG search '
+                '(more than 16 tasks or 2^36 cloud assignments).')
+        best_plan: Dict[task_lib.Task, resources_lib.Resources] = {}
+        for i, task in enumerate(topo_real):
+            launchable = problem.launchable(sol.chosen[i])
+            task.best_resources = launchable
+            best_plan[task] = launchable
+        for t in topo_order:
+            if _is_dummy(t):
+                t.best_resources = list(t.resources)[0]
+                best_plan[t] = t.best_resources
+        if not quiet:
+            objective = float(res['objective'])
+            if minimize_cost:
+                total_cost = objective
+                total_time = Optimizer._compute_total_time(
+                    graph, topo_order, best_plan)
+            else:
+                total_time = objective
+                total_cost = Optimizer._compute_total_cost(
+                    graph, topo_order, best_plan)
+            Optimizer.print_optimized_plan(problem, sol, total_time,
+                                           total_cost)
+        return best_plan
+
+    @staticmethod
+    def _resolve_ordered_resources(dag, blocked) -> Dict[Any, Any]:
+        """Ordered (list) resources: the first alternative with any launchable
+        candidate wins; no joint optimisation (sky/optimizer.py:1403-1448).
+        All alternatives of all such tasks are probed in one device call."""
+        probes = []
+        for task in dag.tasks:
+            if isinstance(task.resources, list) and not _is_dummy(task):
+                probes.append(task)
+        if not probes:
+            return {}
+        store = catalog.get_store()
+        b = engine.ProblemBuilder(store)
+        graph = nx.DiGraph()
+        index = []
+        for task in probes:
+            for alt in task.resources:
+                probe = task_lib.Task.__new__(task_lib.Task)
+                probe.__dict__.update(task.__dict__)
+                probe.resources = {alt}
+                graph.add_node(probe)
+                Optimizer._state_problem(graph, [probe], True, blocked, True,
+                                         builder=b)
+                index.append((task, alt))
+        sol = engine.solve(b, device=catalog.get_device())
+        choice: Dict[Any, Any] = {}
+        for i, (task, alt) in enumerate(index):
+            if task not in choice and sol.task_n[i] > 0:
+                choice[task] = alt
+        for task in probes:
+            # nothing launchable: keep the last alternative so that the error
+            # message names a concrete request
+            choice.setdefault(task, task.resources[-1])
+        return choice
+
+    # --------------------------------------------- object-level reference API
+    @staticmethod
+    def _estimate_nodes_cost_or_time(
+        topo_order: List[task_lib.Task],
+        minimize_cost: bool = True,
+        blocked_resources: Optional[Iterable[resources_lib.Resources]] = None,
+        quiet: bool = False
+    ) -> Tuple[_TaskToCostMap, _TaskToPerCloudCandidates]:
+        """node -> {launchable Resources -> cost or time}, in the reference's
+        candidate order (sky/optimizer.py:239-426). The table is computed on
+        the device; this wrapper only materialises the Resources objects."""
+        del quiet
+        node_to_cost_map: _TaskToCostMap = collections.defaultdict(dict)
+        node_to_candidate_map: _TaskToPerCloudCandidates = {}
+        real = [t for t in topo_order if not _is_dummy(t)]
+        graph = nx.DiGraph()
+        graph.add_nodes_from(real)
+        problem = Optimizer._state_problem(graph, real, minimize_cost,
+                                           list(blocked_resources or []), True)
+        # every task is costed independently here: one single-task DAG each
+        b = problem.builder
+        b.dags = []
+        n_blocked = len(b.blocked)
+        for i in range(len(real)):
+            b.tasks[i]['n_parents'] = 0
+            b.add_dag(i, i + 1, True, minimize_cost, 0, n_blocked)
+        sol = Optimizer._solve(problem, want_tables=True)
+        for i, task in enumerate(real):
+            if sol.task_n[i] == 0:
+                Optimizer._raise_unavailable(task,
+                                             list(blocked_resources or []))
+            per_cloud: _PerCloudCandidates = collections.defaultdict(list)
+            for cand in sol.task_table(i):
+                launchable = problem.launchable(cand)
+                value = float(cand['value'])
+                node_to_cost_map[task][launchable] = value
+                info = problem.slot_info[int(cand['slot'])]
+                if not per_cloud[info.cloud]:
+                    per_cloud[info.cloud].append(
+                        info.plan.make(launchable.instance_type))
+            node_to_candidate_map[task] = per_cloud
+        for t in topo_order:
+            if _is_dummy(t):
+                node_to_cost_map[t][list(t.resources)[0]] = 0
+        return node_to_cost_map, node_to_candidate_map
+
+    @staticmethod
+    def _raise_unavailable(task, blocked) -> None:
+        """Builds the reference's error text (sky/optimizer.py:368-425)."""
+        _, _, fuzzy, resource_hints = _fill_in_launchable_resources(
+            task, blocked, quiet=True)
+        fuzzy_str = ''
+        if fuzzy:
+            fuzzy_str = f'\nTry one of these offered accelerators: {fuzzy}'
+        reprs = ', '.join(f'{task.num_nodes}x ' + r.repr_with_region_zone
+                          for r in task.resources)
+        indent = ' ' * len('Hint: ')
+        hints_concat = '\n'.join(f'Resource: {r!r}\n' + '\n'.join(h)
+                                 for r, h in resource_hints.items() if h)
+        hints_fmt = '\n'.join(
+            f'{indent}{line}' for line in hints_concat.split('\n')
+        ) if hints_concat else ''
+        hints_str = (f'Hint: Check Per Resource Hint\n{hints_fmt}'
+                     if hints_fmt else '')
+        raise exceptions.ResourcesUnavailableError(
+            'Catalog does not contain any instances satisfying the request: '
+            f'{reprs}.\nTo fix: relax or change the resource requirements.'
+            f'{fuzzy_str}\n\nHint: sky gpus list to list available '
+            f'accelerators.\n{indent}sky check to check the enabled clouds.\n'
+            f'{hints_str}')
+
+    @staticmethod
+    def _compute_total_time(graph, topo_order, plan) -> float:
+        """Critical-path time of a plan (sky/optimizer.py:640-671)."""
+        finish: Dict[Any, float] = {}
+
+        def finish_time(node):
+            if node in finish:
+                return finish[node]
+            resources = plan[node]
+            if node.time_estimator_func is None:
+                execution = 1 * 3600
+            else:
+                execution = node.estimate_runtime(resources)
+            preds = [0]
+            for pred in graph.predecessors(node):
+                egress = Optimizer._egress_cost_or_time(False, pred,
+                                                        plan[pred], node,
+                                                        resources)
+                preds.append(finish_time(pred) + egress)
+            finish[node] = execution + max(preds)
+            return finish[node]
+
+        return finish_time(topo_order[-1])
+
+    @staticmethod
+    def _compute_total_cost(graph, topo_order, plan) -> float:
+        """Execution + egress cost of a plan (sky/optimizer.py:674-698)."""
+        total = 0.
+        for node in topo_order:
+            resources = plan[node]
+            if node.time_estimator_func is None:
+                execution = 1 * 3600
+            else:
+                execution = node.estimate_runtime(resources)
+            total += resources.get_cost(execution) * node.num_nodes
+            for pred in graph.predecessors(node):
+                total += Optimizer._egress_cost_or_time(
+                    True, pred, plan[pred], node, resources)
+        return total
+
+    @staticmethod
+    def print_optimized_plan(problem: _Problem, sol: engine.Solution,
+                             total_time: float, total_cost: float) -> None:
+        """Logs the chosen plan and the per-task alternatives (compact form
+        of sky/optimizer.py:738-1033)."""
+        lines = []
+        if len(problem.tasks) > 1:
+            lines.append(f'Estimated total runtime: {total_time / 3600:.1f} '
+                         f'hours; estimated total cost: ${total_cost:.1f}')
+        for i, task in enumerate(problem.tasks):
+            best = task.best_resources
+            lines.append(
+                f'{task}: {task.num_nodes}x {best.repr_with_region_zone} '
+                f'${float(sol.chosen[i]["hourly"]):.4f}/hr '
+                f'({int(sol.task_n[i])} candidates)')
+        logger.info('Optimizer plan:\n  ' + '\n  '.join(lines))
+
+
+def _cloud_object(name: str) -> clouds.Cloud:
+    from skypilot_b200.utils import registry  # pylint: disable=import-outside-toplevel
+    if name in registry.CLOUD_REGISTRY:
+        return registry.CLOUD_REGISTRY.from_str(name)
+    return clouds.DummyCloud()
+
+
+def _add_blocked(b: engine.ProblemBuilder, store, blocked) -> None:
+    """One `should_be_blocked_by` wildcard (sky/resources.py:1938-1961) as
+    device entries; names are resolved against each cloud's dictionaries."""
+    targets = []
+    if blocked.cloud is not None:
+        name = blocked.cloud.canonical_name()
+        if not store.has_cloud(name):
+            return
+        targets = [store.cloud(name)]
+    else:
+        targets = list(store.clouds)
+    acc_key = -1
+    accs = blocked.accelerators
+    if accs is not None:
+        if len(accs) != 1:
+            return
+        name, count = list(accs.items())[0]
+        acc_key = store.acc_key_index.get((name, float(count)), -2)
+    needs_cloud = (blocked.instance_type is not None or
+                   blocked.region is not None or blocked.zone is not None)
+    if not needs_cloud and blocked.cloud is None:
+        b.add_blocked(acc_key=acc_key, use_spot=int(blocked.use_spot))
+        return
+    for table in targets:
+        entry = dict(cloud=table.index, acc_key=acc_key,
+                     use_spot=int(blocked.use_spot))
+        if blocked.instance_type is not None:
+            entry['inst_id'] = table.inst_index.get(
+                blocked.instance_type,
+                -2 if blocked.instance_type != 'TPU-VM' else -2)
+        if blocked.region is not None:
+            entry['region_id'] = table.region_exact.get(blocked.region, -2)
+        if blocked.zone is not None:
+            entry['zone_id'] = table.zone_exact.get(blocked.zone, -2)
+        b.add_blocked(**entry)
+
+
+def _filter_out_blocked_launchable_resources(launchable_resources,
+                                             blocked_resources):
+    available = []
+    for resources in launchable_resources:
+        for blocked in blocked_resources:
+            if resources.should_be_blocked_by(blocked):
+                break
+        else:
+            available.append(resources)
+    return available
+
+
+def _check_specified_clouds(dag: 'dag_lib.Dag') -> None:
+    """A task pinned to a cloud that is not enabled cannot be placed
+    (sky/optimizer.py:1541-1607)."""
+    enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+        raise_if_no_cloud_access=True)
+    for task in dag.tasks:
+        specified, disabled = set(), set()
+        for resources in task.resources:
+            cloud_str = str(resources.cloud)
+            if (resources.cloud is not None and
+                    not clouds.cloud_in_iterable(resources.cloud, enabled)):
+                disabled.add(cloud_str)
+            specified.add(cloud_str)
+        if disabled:
+            is_or_are = 'is' if len(disabled) == 1 else 'are'
+            task_name = f' {task.name!r}' if task.name is not None else ''
+            msg = (f'Task{task_name} requires {", ".join(sorted(disabled))} '
+                   f'which {is_or_are} not enabled. To enable access, change '
+                   'the task cloud requirement or run: sky check '
+                   f'{" ".join(c.lower() for c in sorted(disabled))}')
+            if specified == disabled:
+                raise exceptions.ResourcesUnavailableError(msg)
+            logger.warning(msg)
+
+
+def _fill_in_launchable_resources(
+    task: task_lib.Task,
+    blocked_resources: Optional[Iterable[resources_lib.Resources]],
+    quiet: bool = False
+) -> Tuple[Dict[resources_lib.Resources, List[resources_lib.Resources]],
+           _PerCloudCandidates, List[str], Dict[resources_lib.Resources,
+                                                List[str]]]:
+    """requested Resources -> launchable Resources, per-cloud feasible lists,
+    fuzzy candidates and hints (sky/optimizer.py:1664-1785). Object-level
+    path: one `skyopt_scan` per cloud plus one expansion call per cheapest
+    instance type."""
+    enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+        raise_if_no_cloud_access=True)
+    launchable: Dict[resources_lib.Resources,
+                     List[resources_lib.Resources]] = (
+                         collections.defaultdict(list))
+    all_fuzzy = set()
+    cloud_candidates: _PerCloudCandidates = collections.defaultdict(list)
+    resource_hints: Dict[resources_lib.Resources,
+                         List[str]] = collections.defaultdict(list)
+    blocked = list(blocked_resources or [])
+    for resources in task.resources:
+        resources.validate()
+        if (resources.cloud is not None and
+                not clouds.cloud_in_iterable(resources.cloud, enabled)):
+            launchable[resources] = []
+            continue
+        clouds_list = ([resources.cloud]
+                       if resources.cloud is not None else enabled)
+        for cloud in clouds_list:
+            feasible = cloud.get_feasible_launchable_resources(
+                resources, task.num_nodes)
+            if feasible.hint is not None:
+                resource_hints[resources].append(feasible.hint)
+            if feasible.resources_list:
+                cheapest = feasible.resources_list[0]
+                launchable[resources].extend(
+                    resources_utils.make_launchables_for_valid_region_zones(
+                        cheapest))
+                cloud_candidates[cloud].extend(feasible.resources_list)
+            else:
+                all_fuzzy.update(feasible.fuzzy_candidate_list)
+        if not launchable[resources] and not (
+                quiet or resources.no_missing_accel_warnings):
+            logger.info(f'No resource satisfying '
+                        f'{resources.repr_with_region_zone} on '
+                        f'{clouds_list}.')
+            if all_fuzzy:
+                logger.info(f'Did you mean: {sorted(all_fuzzy)}')
+        launchable[resources] = _filter_out_blocked_launchable_resources(
+            launchable[resources], blocked)
+    return launchable, cloud_candidates, sorted(all_fuzzy), resource_hints

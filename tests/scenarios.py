@@ -1,0 +1,291 @@
+"""Parity scenarios: declarative DAGs that every implementation must answer
+identically -- the unmodified reference (oracle/ref_harness, build container
+only -> tests/golden/*.json), the portable pandas oracle (oracle/) and the
+CUDA path (skypilot_b200).
+
+Scenario schema (JSON-able):
+  name        unique id
+  minimize    'cost' (default) | 'time'
+  tasks       list of
+      name, num_nodes (1),
+      resources       list of Resources kwargs (cloud given by name)
+      resources_kind  'single' (default) | 'set' | 'list'
+      outputs_gb      estimated output size feeding the egress term
+      inputs          [url, gigabytes]
+      time_est        {'default': s, 'by_acc': {name: s}, 'by_cloud': {..}}
+  edges       list of [parent index, child index]
+  blocked     list of Resources kwargs (wildcards)
+
+Catalog specs are arguments of skypilot_b200.synth.make_catalogs.
+"""
+import copy
+
+CATALOGS = {
+    # cfg2/cfg3 of SURVEY.md section 8d: multi-cloud, ~50k rows
+    'multi50k': {'seed': 1, 'n_rows': 50000,
+                 'clouds': ['aws', 'gcp', 'azure', 'lambda']},
+    # cfg1: AWS only
+    'aws50k': {'seed': 0, 'n_rows': 50000, 'clouds': ['aws']},
+    # small catalogs for many cheap cases
+    'multi6k': {'seed': 7, 'n_rows': 6000,
+                'clouds': ['aws', 'gcp', 'azure', 'lambda']},
+    'three4k': {'seed': 11, 'n_rows': 4000,
+                'clouds': ['aws', 'gcp', 'azure']},
+}
+
+
+def _single(name, **res):
+    extra = {}
+    for key in ('num_nodes', 'outputs_gb', 'inputs', 'time_est'):
+        if key in res:
+            extra[key] = res.pop(key)
+    task = {'resources': [res]}
+    task.update(extra)
+    return {'name': name, 'tasks': [task]}
+
+
+def _chain(name, specs, **kw):
+    tasks = []
+    for i, spec in enumerate(specs):
+        spec = dict(spec)
+        task = {'name': f't{i}'}
+        for key in ('num_nodes', 'outputs_gb', 'inputs', 'time_est',
+                    'resources_kind'):
+            if key in spec:
+                task[key] = spec.pop(key)
+        task['resources'] = spec.pop('resources', None) or [spec]
+        tasks.append(task)
+    sc = {'name': name, 'tasks': tasks,
+          'edges': [[i, i + 1] for i in range(len(tasks) - 1)]}
+    sc.update(kw)
+    return sc
+
+
+CFG2_TASKS = [
+    {'accelerators': 'V100', 'outputs_gb': 10},
+    {'accelerators': 'T4', 'outputs_gb': 10},
+    {'accelerators': 'A100:8', 'outputs_gb': 10},
+    {'accelerators': 'H100:8', 'outputs_gb': 10},
+    {'accelerators': 'L4', 'outputs_gb': 10},
+    {'cpus': '8+', 'outputs_gb': 10},
+    {'cpus': '32+', 'memory': '128+', 'outputs_gb': 10},
+    {'memory': '4x', 'outputs_gb': 10},
+]
+
+
+def basic_scenarios():
+    """Work on every multi-cloud catalog."""
+    s = []
+    for acc in ['V100', 'T4', 'A100:8', 'H100:8', 'L4', 'A10G:4', 'K80',
+                'A100-80GB:8', 'A100', 'V100:4', 'T4:4', 'L4:8', 'H200:8',
+                'A10', 'A10:0.5', 'tpu-v3-8', 'v100', 'a100-80gb:8', 'B200:8',
+                'P100:2', 'A100:16']:
+        s.append(_single(f'acc_{acc.replace(":", "x")}', accelerators=acc))
+    s += [
+        _single('cpu_default'),
+        _single('cpu_8p', cpus='8+'),
+        _single('cpu_4', cpus='4'),
+        _single('cpu_32p_mem128p', cpus='32+', memory='128+'),
+        _single('mem_64p', memory='64+'),
+        _single('mem_16', memory='16'),
+        _single('mem_4x', memory='4x'),
+        _single('mem_8x_cpu16p', cpus='16+', memory='8x'),
+        _single('cpu_2_mem_8p', cpus=2, memory='8+'),
+        _single('cpu_96p', cpus='96+'),
+        _single('v100_cpus16p', accelerators='V100', cpus='16+'),
+        _single('t4_mem64p', accelerators='T4', memory='64+'),
+        _single('a100_8_cpus_96', accelerators='A100:8', cpus='96'),
+        _single('spot_v100', accelerators='V100', use_spot=True),
+        _single('spot_t4x4', accelerators='T4:4', use_spot=True),
+        _single('spot_a100x8', accelerators='A100:8', use_spot=True),
+        _single('spot_cpu', cpus='8+', use_spot=True),
+        _single('spot_cpu_cap', cpus='8+', use_spot=True,
+                max_hourly_cost=0.2),
+        _single('cap_v100', accelerators='V100', max_hourly_cost=2.0),
+        _single('cap_cpu', cpus='16+', max_hourly_cost=0.7),
+        _single('cap_tiny', accelerators='H100:8', max_hourly_cost=0.5),
+        _single('nodes4_v100', accelerators='V100', num_nodes=4),
+        _single('aws_only_t4', cloud='aws', accelerators='T4'),
+        _single('gcp_only_t4', cloud='gcp', accelerators='T4'),
+        _single('gcp_only_a100', cloud='gcp', accelerators='A100:4'),
+        _single('gcp_only_l4', cloud='gcp', accelerators='L4'),
+        _single('gcp_only_cpu', cloud='gcp', cpus='16+'),
+        _single('gcp_spot_v100', cloud='gcp', accelerators='V100:2',
+                use_spot=True),
+        _single('gcp_t4_cpus8', cloud='gcp', accelerators='T4', cpus='8+'),
+        _single('gcp_tpu_spot', accelerators='tpu-v2-8', use_spot=True),
+        _single('azure_only_v100', cloud='azure', accelerators='V100'),
+        _single('azure_only_cpu', cloud='azure', cpus='4+'),
+        _single('azure_spot_t4', cloud='azure', accelerators='T4',
+                use_spot=True),
+        _single('azure_a10_frac', cloud='azure', accelerators='A10:0.167'),
+        _single('lambda_only_a100', cloud='lambda', accelerators='A100'),
+        _single('lambda_only_cpu', cloud='lambda'),
+        _single('lambda_spot', cloud='lambda', accelerators='A100',
+                use_spot=True),
+        _single('aws_region', infra='aws/us-west-2', accelerators='V100'),
+        _single('aws_region_cpu', infra='aws/eu-west-1', cpus='8+'),
+        _single('gcp_region', infra='gcp/us-central1', accelerators='T4'),
+        _single('azure_region', infra='azure/westus2', cpus='8+'),
+        _single('aws_inst', cloud='aws', instance_type='p3.2xlarge'),
+        _single('aws_inst_spot', cloud='aws', instance_type='g4dn.xlarge',
+                use_spot=True),
+        _single('aws_inst_region', infra='aws/us-east-2',
+                instance_type='m6i.2xlarge'),
+        _single('gcp_inst', cloud='gcp', instance_type='n2-standard-8'),
+        _single('gcp_inst_acc', cloud='gcp', instance_type='n1-standard-8',
+                accelerators='T4'),
+        _single('azure_inst', cloud='azure',
+                instance_type='Standard_NC6s_v3'),
+        _single('lambda_inst', cloud='lambda', instance_type='gpu_1x_a100'),
+        _single('inst_no_cloud', instance_type='p3.8xlarge'),
+        _single('aws_local_disk', cloud='aws', cpus='8+',
+                local_disk='nvme:400+'),
+        _single('aws_local_disk_acc', cloud='aws', accelerators='A100:8',
+                local_disk='ssd:1000+'),
+        _single('aws_local_disk_exact', cloud='aws', accelerators='T4',
+                local_disk='nvme:125'),
+        _single('azure_disk_high', cloud='azure', cpus='8+',
+                disk_tier='high'),
+        _single('azure_disk_low_acc', cloud='azure', accelerators='K80',
+                disk_tier='low'),
+        _single('none_v100x3', accelerators='V100:3'),
+        _single('none_cpus', cpus='4000+'),
+        _single('none_acc_name', accelerators='NoSuchGPU'),
+        _single('none_fuzzy_a100x3', accelerators='A100:3'),
+    ]
+    s += [
+        _chain('chain2_egress_small', [
+            {'accelerators': 'T4', 'outputs_gb': 0.5}, {'cpus': '8+'}]),
+        _chain('chain2_egress_big', [
+            {'accelerators': 'T4', 'outputs_gb': 500}, {'cpus': '8+'}]),
+        _chain('chain2_no_outputs', [
+            {'accelerators': 'V100'}, {'accelerators': 'A100:8'}]),
+        _chain('chain3_mixed', [
+            {'accelerators': 'V100', 'outputs_gb': 100},
+            {'accelerators': 'A100:8', 'outputs_gb': 2000, 'num_nodes': 2},
+            {'cpus': '4+'}]),
+        _chain('chain2_inputs_s3', [
+            {'accelerators': 'T4', 'inputs': ['s3://bucket/data', 800],
+             'outputs_gb': 1}, {'cpus': '2+'}]),
+        _chain('chain2_inputs_gs', [
+            {'accelerators': 'V100', 'inputs': ['gs://bucket/data', 3000],
+             'outputs_gb': 200}, {'accelerators': 'T4'}]),
+        _chain('cfg2_chain8', CFG2_TASKS),
+        _chain('chain8_spot', [dict(t, use_spot=True) for t in CFG2_TASKS]),
+        _chain('chain2_time', [
+            {'accelerators': 'V100', 'outputs_gb': 50,
+             'time_est': {'default': 7200, 'by_acc': {'V100': 3000}}},
+            {'cpus': '8+', 'time_est': {'default': 600}}], minimize='time'),
+        _chain('chain2_time_est_cost', [
+            {'accelerators': 'A100:8', 'outputs_gb': 20,
+             'time_est': {'default': 1800}},
+            {'accelerators': 'T4', 'time_est': {'default': 5400}}]),
+        _chain('chain_blocked_region', [
+            {'accelerators': 'V100', 'outputs_gb': 10}, {'cpus': '8+'}],
+               blocked=[{'cloud': 'aws', 'region': 'us-east-1'},
+                        {'cloud': 'aws', 'region': 'us-east-2'}]),
+        _chain('chain_blocked_cloud', [
+            {'accelerators': 'T4', 'outputs_gb': 10}, {'cpus': '8+'}],
+               blocked=[{'cloud': 'aws'}, {'cloud': 'azure'}]),
+        _chain('chain_blocked_inst', [{'accelerators': 'T4'}],
+               blocked=[{'cloud': 'aws', 'instance_type': 'g4dn.xlarge'},
+                        {'cloud': 'azure',
+                         'instance_type': 'Standard_NC4as_T4_v3',
+                         'region': 'eastus'}]),
+        _chain('chain_blocked_all', [{'cloud': 'lambda',
+                                      'accelerators': 'A100'}],
+               blocked=[{'cloud': 'lambda'}]),
+        _chain('ordered_list', [
+            {'resources': [{'accelerators': 'V100:3'},
+                           {'accelerators': 'H100:8'},
+                           {'accelerators': 'T4'}],
+             'resources_kind': 'list', 'outputs_gb': 5}, {'cpus': '8+'}]),
+        _chain('any_of_set', [
+            {'resources': [{'accelerators': 'A100:8'},
+                           {'accelerators': 'H100:8'},
+                           {'accelerators': 'V100:8'}],
+             'resources_kind': 'set', 'outputs_gb': 5}, {'cpus': '8+'}]),
+    ]
+    diamond = {
+        'name': 'cfg3_diamond',
+        'tasks': [
+            {'name': 'a', 'resources': [{'accelerators': 'V100'}],
+             'outputs_gb': 100},
+            {'name': 'b', 'resources': [{'accelerators': 'T4'}],
+             'outputs_gb': 5},
+            {'name': 'c', 'resources': [{'cpus': '32+', 'memory': '128+'}],
+             'outputs_gb': 5},
+            {'name': 'd', 'resources': [{'accelerators': 'A100:8'}]},
+        ],
+        'edges': [[0, 1], [0, 2], [1, 3], [2, 3]],
+    }
+    s.append(diamond)
+    big = copy.deepcopy(diamond)
+    big['name'] = 'diamond_big_egress'
+    big['tasks'][0]['outputs_gb'] = 5000
+    big['tasks'][1]['outputs_gb'] = 4000
+    big['tasks'][2]['outputs_gb'] = 3000
+    s.append(big)
+    tdiam = copy.deepcopy(diamond)
+    tdiam['name'] = 'diamond_time'
+    tdiam['minimize'] = 'time'
+    for i, secs in enumerate([3600, 1800, 7200, 900]):
+        tdiam['tasks'][i]['time_est'] = {'default': secs}
+    s.append(tdiam)
+    s.append({
+        'name': 'fork_two_sinks',
+        'tasks': [
+            {'name': 'a', 'resources': [{'accelerators': 'T4'}],
+             'outputs_gb': 1500},
+            {'name': 'b', 'resources': [{'cpus': '8+'}]},
+            {'name': 'c', 'resources': [{'accelerators': 'V100'}]},
+        ],
+        'edges': [[0, 1], [0, 2]],
+    })
+    s.append({
+        'name': 'two_independent',
+        'tasks': [
+            {'name': 'a', 'resources': [{'accelerators': 'T4'}]},
+            {'name': 'b', 'resources': [{'cpus': '8+'}]},
+        ],
+        'edges': [],
+    })
+    return s
+
+
+def aws_scenarios():
+    """cfg1 and friends on the AWS-only catalog."""
+    return [
+        _single('cfg1_v100', accelerators='V100'),
+        _single('aws_t4', accelerators='T4'),
+        _single('aws_cpu', cpus='8+'),
+        _single('aws_spot_v100', accelerators='V100', use_spot=True),
+        _single('aws_zone', infra='aws/us-east-1/us-east-1a',
+                accelerators='V100'),
+        _single('aws_zone_spot', infra='aws/us-east-1/us-east-1b',
+                cpus='4+', use_spot=True),
+        _chain('aws_chain8', CFG2_TASKS),
+        _single('aws_none', accelerators='P100'),
+    ]
+
+
+def no_lambda_scenarios():
+    """The basic suite without requests pinned to a cloud the catalog lacks
+    (the reference would try to download that cloud's catalog)."""
+    out = []
+    for sc in basic_scenarios():
+        pinned = [
+            r.get('cloud') for t in sc['tasks'] for r in t['resources']
+        ] + [b.get('cloud') for b in sc.get('blocked', [])]
+        if 'lambda' not in pinned:
+            out.append(sc)
+    return out
+
+
+SUITES = {
+    'multi50k': basic_scenarios,
+    'multi6k': basic_scenarios,
+    'three4k': no_lambda_scenarios,
+    'aws50k': aws_scenarios,
+}

@@ -1,0 +1,62 @@
+"""CUDA path vs the unmodified reference (committed golden fixtures).
+
+For every scenario of tests/scenarios.py the fused device path must return
+the reference's plan (cloud, instance type, region, zone: identical), the
+ordered candidate tables of every task (identical order and identity, values
+within 1e-6 relative) and the objective / total cost / total time.
+"""
+import json
+import os
+
+import pytest
+
+from tests import scenario_runner as runner
+from tests import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases():
+    out = []
+    for catalog in scenarios.SUITES:
+        path = os.path.join(runner.GOLDEN_DIR, f'{catalog}.json')
+        if not os.path.exists(path):
+            continue
+        for sc in scenarios.SUITES[catalog]():
+            out.append(pytest.param(catalog, sc, id=f'{catalog}:{sc["name"]}'))
+    return out
+
+
+_golden_cache = {}
+
+
+def _golden(catalog):
+    if catalog not in _golden_cache:
+        payload = runner.load_golden(catalog)
+        _golden_cache[catalog] = (payload['catalog'], {
+            r['name']: r for r in payload['records']
+        })
+    return _golden_cache[catalog]
+
+
+@pytest.mark.parametrize('catalog,scenario', _cases())
+def test_scenario_matches_reference(catalog, scenario):
+    spec, records = _golden(catalog)
+    assert spec == scenarios.CATALOGS[catalog], (
+        'fixture was generated for a different catalog spec; rerun '
+        'oracle/ref_harness/gen_golden.py')
+    golden = records[scenario['name']]
+    runner.activate_catalog(spec)
+    got = runner.run_scenario(scenario)
+    unordered = any(
+        t.get('resources_kind') == 'set' for t in scenario['tasks'])
+    diffs = runner.compare(golden, got, unordered_candidates=unordered)
+    if diffs:
+        out = os.path.join(os.path.dirname(runner.GOLDEN_DIR), '..',
+                           'gpurun_out')
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, 'parity_failures.jsonl'), 'a',
+                  encoding='utf-8') as f:
+            f.write(json.dumps({'catalog': catalog, 'name': scenario['name'],
+                                'diffs': diffs, 'got': got}) + '\n')
+    assert not diffs, '\n'.join(diffs)
