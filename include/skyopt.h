@@ -277,6 +277,8 @@ typedef struct SkyoptStats {
   int32_t total_launches;
   int64_t scan_rows;       /* sum over queries of rows scanned */
   int64_t scan_passes_rows; /* rows streamed from HBM (queries fused per pass) */
+  float scan_kernel_ms;     /* the scan kernel launch alone (events around it) */
+  int32_t scan_blocks;      /* its grid size */
 } SkyoptStats;
 
 typedef struct SkyoptCatalog SkyoptCatalog; /* opaque */
@@ -317,11 +319,13 @@ int skyopt_optimize(SkyoptCatalog *cat, const SkyoptProblem *problem,
  * Device-resident timing loop for bench.py: uploads `problem` once, then runs
  * the kernels `iters` times, flushing L2 (writing a buffer > 126 MB) before
  * every iteration when flush_l2 != 0; per-iteration device times (CUDA
- * events around the kernels only) are written to iter_ms[iters].
+ * events around the kernels only) are written to iter_ms[iters] and the
+ * duration of the scan kernel launch alone to scan_kernel_ms[iters].
  */
 int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *problem,
                           SkyoptSolution *solution, int iters, int flush_l2,
-                          float *iter_ms, float *scan_ms, SkyoptStats *stats);
+                          float *iter_ms, float *scan_kernel_ms,
+                          SkyoptStats *stats);
 
 #ifdef __cplusplus
 }

@@ -152,6 +152,7 @@ class Stats(ctypes.Structure):
         ('solve_ms', ctypes.c_float), ('total_ms', ctypes.c_float),
         ('scan_launches', ctypes.c_int32), ('total_launches', ctypes.c_int32),
         ('scan_rows', ctypes.c_int64), ('scan_passes_rows', ctypes.c_int64),
+        ('scan_kernel_ms', ctypes.c_float), ('scan_blocks', ctypes.c_int32),
     ]
 
     def as_dict(self):

@@ -367,7 +367,7 @@ class Cloud:
             use_spot, resources.region, resources.zone,
             resources.max_hourly_cost, local_disk=local_disk,
             flags_require2=_native.F_PREMIUM_DISK if premium else 0,
-            want_list=want_list, want_fuzzy=True)
+            want_list=want_list, want_fuzzy=want_list)
         q = builder.add_query(spec)
         plan.list_query = q
         plan.fuzzy_query = q

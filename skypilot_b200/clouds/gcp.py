@@ -164,7 +164,7 @@ class GCP(cloud.Cloud):
                 'gcp', acc, acc_count, None if tpu_vm else resources.cpus,
                 None if tpu_vm else resources.memory, use_spot,
                 resources.region, resources.zone, resources.max_hourly_cost,
-                want_list=False, want_fuzzy=True))
+                want_list=False, want_fuzzy=want_list))
         plan.gate_query = gate
         plan.fuzzy_query = gate
         acc_dict = {acc: acc_count}
@@ -203,10 +203,14 @@ class GCP(cloud.Cloud):
                 acc, rules.GCP_ACC_HOST_CPUS['DEFAULT'])
             default_cpus = table_cpus.get(acc_count)
             if cpus is None and memory is None:
-                assert default_cpus is not None, (acc, acc_count)
+                if default_cpus is None:
+                    # No host-VM rule for this count: the reference only gets
+                    # here when accelerator rows exist (and then asserts,
+                    # gcp_catalog.py:376-378); keep the gate for the fuzzy
+                    # list and offer nothing.
+                    return plan
                 cpus = f'{default_cpus}+'
             if memory is None:
-                assert cpus is not None, (acc, acc_count)
                 cpu_val = int(cpus.strip('+').strip('x'))
                 memory = f'{cpu_val * rules.GCP_GPU_MEMORY_CPU_RATIO}+'
             spec = builder.cpus_mem_query(

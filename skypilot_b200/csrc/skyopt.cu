@@ -48,7 +48,7 @@ inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 // Private stream + buffers of one in-flight call.
 struct Ctx {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {};
+  cudaEvent_t ev[8] = {};
   char *dbuf = nullptr; size_t dcap = 0;   // device workspace
   char *hbuf = nullptr; size_t hcap = 0;   // pinned staging
   uint32_t *flush = nullptr; size_t flush_words = 0;
@@ -151,7 +151,7 @@ struct Plan {
   SkyoptQuery *queries; uint32_t *acc_sets; SkyoptSlot *slots; SkyoptTask *tasks;
   int32_t *parents; double *tariffs; SkyoptBlocked *blocked; SkyoptDag *dags;
   int32_t *q_order; ScanGroup *groups; int32_t *partial_base, *partial_count;
-  int64_t *list_base, *fuzzy_base, *slot_off, *task_off;
+  int64_t *list_base, *fuzzy_base, *slot_off, *task_off; int32_t *task_dag;
   // device-only scratch
   ScanPartial *partials; unsigned long long *list_min, *fuzzy_min;
   int32_t *cand_region, *cand_zone; double *cand_pa, *cand_pb;
@@ -182,6 +182,7 @@ void carve_inputs(Plan &P, Carver &c) {
   P.fuzzy_base = c.take<int64_t>(P.nq);
   P.slot_off = c.take<int64_t>(P.ns);
   P.task_off = c.take<int64_t>(P.nt + 1);
+  P.task_dag = c.take<int32_t>(P.nt);
 }
 
 void carve_rest(Plan &P, Carver &c) {
@@ -363,6 +364,9 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
       return fail(SKYOPT_EINVAL, "a slot belongs to more than one task");
     }
   }
+  for (int t = 0; t < P.nt; ++t) P.task_dag[t] = 0;
+  for (int d = 0; d < P.nd; ++d)
+    for (int t = pb->dags[d].task_begin; t < pb->dags[d].task_end; ++t) P.task_dag[t] = d;
   int g = 0, qpos = 0, block0 = 0;
   P.pass_rows = 0;
   for (int c = 0; c < C; ++c) {
@@ -402,10 +406,10 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
   cudaStream_t st = x->stream;
   CU(cudaEventRecord(x->ev[1], st));
   if (P.nq) {
-    CU(cudaMemsetAsync(P.any1, 0, sizeof(uint32_t) * P.nq, st));
     if (P.list_entries) CU(cudaMemsetAsync(P.list_min, 0xFF, sizeof(unsigned long long) * P.list_entries, st));
     if (P.fuzzy_entries) CU(cudaMemsetAsync(P.fuzzy_min, 0xFF, sizeof(unsigned long long) * P.fuzzy_entries, st));
     if (P.n_blocks) {
+      CU(cudaEventRecord(x->ev[6], st));
 #define LAUNCH_SCAN(R)                                                        \
   scan_kernel<R><<<P.n_blocks, kScanThreads, 0, st>>>(                        \
       cat->dev, P.queries, P.q_order, P.groups, P.n_groups, P.acc_sets,       \
@@ -416,15 +420,17 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
       else LAUNCH_SCAN(1);
 #undef LAUNCH_SCAN
       CU(cudaGetLastError());
+      CU(cudaEventRecord(x->ev[7], st));
     }
     const int fblocks = (P.nq * 32 + 255) / 256;
     finalize_kernel<<<fblocks, 256, 0, st>>>(cat->dev, P.nq, P.partial_base,
-                                             P.partial_count, P.partials, P.finals);
+                                             P.partial_count, P.partials, P.finals,
+                                             P.any1, P.err_out);
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(x->ev[2], st));
   if (!solve) return 0;
-  CU(cudaMemsetAsync(P.err_flag, 0, sizeof(int32_t), st));
+  if (!P.nq) CU(cudaMemsetAsync(P.err_out, 0, sizeof(int32_t), st));
   ExpandOut ex{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
   if (P.ns) {
     const size_t smem = (size_t)cat->sort_n * 16 + (size_t)cat->max_zones * 8 +
@@ -432,7 +438,7 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
     expand_kernel<<<P.ns, 128, smem, st>>>(cat->dev, P.slots, P.finals, P.any1,
                                            P.acc_sets, P.slot_off, cat->sort_n,
                                            cat->max_regions, cat->max_zones, ex,
-                                           P.err_flag);
+                                           P.err_out);
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(x->ev[3], st));
@@ -440,10 +446,11 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
     SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex};
     SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
     SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres};
+    gather_kernel<<<P.nt, kGatherThreads, 0, st>>>(cat->dev, in, w, P.task_dag, P.task_n);
+    CU(cudaGetLastError());
     solve_kernel<<<P.nd, kSolveThreads, 0, st>>>(cat->dev, in, w, out);
     CU(cudaGetLastError());
   }
-  CU(cudaMemcpyAsync(P.err_out, P.err_flag, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   CU(cudaEventRecord(x->ev[4], st));
   return 0;
 }
@@ -541,9 +548,11 @@ int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
   CU(cudaEventElapsedTime(&stats->total_ms, x->ev[0], x->ev[5]));
   stats->scan_launches = P.n_blocks ? 1 : 0;
   stats->total_launches = (P.n_blocks ? 1 : 0) + (P.nq ? 1 : 0) +
-                          (solve ? ((P.ns ? 1 : 0) + (P.nd ? 1 : 0)) : 0);
+                          (solve ? ((P.ns ? 1 : 0) + (P.nd ? 2 : 0)) : 0);
   stats->scan_rows = P.scan_rows;
   stats->scan_passes_rows = P.pass_rows;
+  stats->scan_blocks = P.n_blocks;
+  if (P.n_blocks) CU(cudaEventElapsedTime(&stats->scan_kernel_ms, x->ev[6], x->ev[7]));
   return 0;
 }
 
@@ -816,7 +825,7 @@ int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSol
       if ((r = enqueue_kernels(cat, x, P, true))) return r;
       CU(cudaStreamSynchronize(st));
       CU(cudaEventElapsedTime(&iter_ms[it], x->ev[1], x->ev[4]));
-      if (scan_ms) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[1], x->ev[2]));
+      if (scan_ms && P.n_blocks) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[6], x->ev[7]));
     }
     CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(x->ev[5], st));

@@ -79,11 +79,42 @@ __device__ __forceinline__ bool test_bit(const uint32_t *set, uint32_t k) {
   return (set[k >> 5] >> (k & 31)) & 1u;
 }
 
-template <int RPT>
-struct RowRegs {
-  double od[RPT], sp[RPT], vc[RPT], mm[RPT];
-  uint16_t ak[RPT], rg[RPT], zn[RPT], fl[RPT];
+// Constraint vector of one query as the scan loop wants it: everything that
+// is an equality test on small integers (flags, group, region, zone, row
+// validity) is folded into one 64-bit (mask, value) pair against the row key
+//   key = flags | region << 16 | zone << 32,
+// and the vCPU / memory operators become closed intervals.
+struct QueryS {
+  uint32_t mask_lo, mask_hi, val_lo, val_hi;
+  uint32_t qflags;       // SKYOPT_Q_*
+  uint32_t flags2;       // flags_require2
+  int32_t price_col, cpus_op, mem_op, disk_op;
+  int32_t cloud;
+  uint32_t req_flags;    // flag bits every matching row carries
+  uint32_t sig_lo, sig_hi;  // 64-bit signature of the accelerator keys wanted
+  double cpu_lo, cpu_hi, mem_lo, mem_hi, cap, disk_size;
 };
+
+__device__ __forceinline__ QueryS make_query_s(const SkyoptQuery &q) {
+  const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+  QueryS s;
+  uint64_t mask = (uint64_t)((q.flags_require | SKYOPT_F_VALID) & 0xFFu);
+  uint64_t val = mask;
+  if (q.group != 0) { mask |= 0xFF00ull; val |= ((uint64_t)(q.group & 0xFF)) << 8; }
+  if (q.region_id >= 0) { mask |= 0xFFFFull << 16; val |= ((uint64_t)(q.region_id & 0xFFFF)) << 16; }
+  if (q.zone_id >= 0) { mask |= 0xFFFFull << 32; val |= ((uint64_t)(q.zone_id & 0xFFFF)) << 32; }
+  s.mask_lo = (uint32_t)mask; s.mask_hi = (uint32_t)(mask >> 32);
+  s.val_lo = (uint32_t)val; s.val_hi = (uint32_t)(val >> 32);
+  s.qflags = q.qflags; s.flags2 = q.flags_require2;
+  s.price_col = q.price_col; s.cpus_op = q.cpus_op; s.mem_op = q.mem_op;
+  s.disk_op = q.disk_op; s.cloud = q.cloud;
+  s.req_flags = (q.flags_require | SKYOPT_F_VALID) & 0xFFu;
+  s.sig_lo = 0xFFFFFFFFu; s.sig_hi = 0xFFFFFFFFu;  // refined while staging the sets
+  s.cpu_lo = q.cpus; s.cpu_hi = (q.cpus_op == SKYOPT_OP_GE) ? kInf : q.cpus;
+  s.mem_lo = q.mem;  s.mem_hi = (q.mem_op == SKYOPT_OP_GE) ? kInf : q.mem;
+  s.cap = q.max_price; s.disk_size = q.disk_size;
+  return s;
+}
 
 // 128-bit (f64) / 64-bit (u16) vector loads through the read-only path. The
 // catalog arrays are 256 B aligned, cloud ranges are padded to 8 rows and the
@@ -105,7 +136,7 @@ __device__ __forceinline__ void load_f64(const double *__restrict__ col,
 }
 template <int RPT>
 __device__ __forceinline__ void load_u16(const uint16_t *__restrict__ col,
-                                         int64_t base, uint16_t (&out)[RPT]) {
+                                         int64_t base, uint32_t (&out)[RPT]) {
   if constexpr (RPT == 4) {
     uint2 a = __ldg(reinterpret_cast<const uint2 *>(col + base));
     out[0] = a.x & 0xFFFF; out[1] = a.x >> 16;
@@ -118,8 +149,10 @@ __device__ __forceinline__ void load_u16(const uint16_t *__restrict__ col,
   }
 }
 
+constexpr int kSetStride = SKYOPT_ACC_SET_WORDS + 1;  // + a zero word for "no key"
+
 template <int RPT>
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 3)
 scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
             const int32_t *__restrict__ q_order,
             const ScanGroup *__restrict__ groups, int n_groups,
@@ -131,12 +164,13 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
             const int64_t *__restrict__ fuzzy_base,
             unsigned long long *__restrict__ fuzzy_min) {
   constexpr int kWarps = kScanThreads / 32;
-  __shared__ SkyoptQuery sq[kQChunk];
-  __shared__ uint32_t sset[kQChunk][2][SKYOPT_ACC_SET_WORDS];
+  __shared__ QueryS sq[kQChunk];
+  __shared__ uint32_t sset[kQChunk][2][kSetStride];
   __shared__ int32_t sqid[kQChunk];
   __shared__ uint64_t wkey[kQChunk][kWarps];
   __shared__ uint32_t wrow[kQChunk][kWarps];
   __shared__ uint32_t sany[kQChunk];
+  __shared__ uint32_t ssig[kQChunk][2];
 
   // blockIdx -> (group, tile): groups are sorted by block0.
   int lo = 0, hi = n_groups - 1;
@@ -150,59 +184,113 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nq = G.q_count;
 
-  // Stage the chunk's constraint vectors (and accelerator-key bitmasks).
+  // Stream this thread's rows into registers first (32 B per row); the
+  // constraint vectors are staged while the loads are in flight.
+  const int64_t base =
+      (int64_t)G.row_begin + (int64_t)tile * (kScanThreads * RPT) + tid * RPT;
+  double od[RPT], sp[RPT], vc[RPT], mm[RPT];
+  uint32_t ak[RPT], rg[RPT], zn[RPT], fl[RPT];
+  if (G.need & 1u) load_f64<RPT>(cat.price, base, od);
+  if (G.need & 2u) load_f64<RPT>(cat.spot, base, sp);
+  load_f64<RPT>(cat.vcpus, base, vc);
+  load_f64<RPT>(cat.mem, base, mm);
+  load_u16<RPT>(cat.acc_key, base, ak);
+  load_u16<RPT>(cat.region_id, base, rg);
+  load_u16<RPT>(cat.zone_id, base, zn);
+  load_u16<RPT>(cat.flags, base, fl);
+
+  // Stage the chunk's constraint vectors, then the accelerator-key bitmasks
+  // they reference (set indices come from shared memory, so the global loads
+  // of one thread are independent and overlap).
+  __shared__ int32_t sset_idx[kQChunk][2];
   if (tid < nq) {
-    int qi = __ldg(&q_order[G.q_begin + tid]);
+    const int qi = __ldg(&q_order[G.q_begin + tid]);
+    const SkyoptQuery q = queries[qi];
     sqid[tid] = qi;
-    sq[tid] = queries[qi];
+    sq[tid] = make_query_s(q);
+    sset_idx[tid][0] = (q.qflags & SKYOPT_Q_ACC) ? q.acc_set : -1;
+    sset_idx[tid][1] = (q.qflags & SKYOPT_Q_FUZZY) ? q.fuzzy_set : -1;
     sany[tid] = 0;
   }
   __syncthreads();
-  for (int i = tid; i < nq * 2 * SKYOPT_ACC_SET_WORDS; i += kScanThreads) {
-    int q = i / (2 * SKYOPT_ACC_SET_WORDS);
-    int r = i % (2 * SKYOPT_ACC_SET_WORDS);
-    int which = r / SKYOPT_ACC_SET_WORDS, w = r % SKYOPT_ACC_SET_WORDS;
-    int set = which ? sq[q].fuzzy_set : sq[q].acc_set;
-    sset[q][which][w] =
-        set >= 0 ? __ldg(&acc_sets[(int64_t)set * SKYOPT_ACC_SET_WORDS + w]) : 0u;
+  for (int i = tid; i < nq * 2 * kSetStride; i += kScanThreads) {
+    const int q = i / (2 * kSetStride);
+    const int r = i % (2 * kSetStride);
+    const int which = r / kSetStride, w = r % kSetStride;
+    const int set = sset_idx[q][which];
+    sset[q][which][w] = (set >= 0 && w < SKYOPT_ACC_SET_WORDS)
+        ? __ldg(&acc_sets[(int64_t)set * SKYOPT_ACC_SET_WORDS + w]) : 0u;
   }
-
-  // Stream this thread's rows into registers: 32 B per row.
-  const int64_t base =
-      (int64_t)G.row_begin + (int64_t)tile * (kScanThreads * RPT) + tid * RPT;
-  RowRegs<RPT> R;
-  if (G.need & 1u) load_f64<RPT>(cat.price, base, R.od);
-  if (G.need & 2u) load_f64<RPT>(cat.spot, base, R.sp);
-  load_f64<RPT>(cat.vcpus, base, R.vc);
-  load_f64<RPT>(cat.mem, base, R.mm);
-  load_u16<RPT>(cat.acc_key, base, R.ak);
-  load_u16<RPT>(cat.region_id, base, R.rg);
-  load_u16<RPT>(cat.zone_id, base, R.zn);
-  load_u16<RPT>(cat.flags, base, R.fl);
+  for (int i = tid; i < nq * kWarps; i += kScanThreads) {
+    wkey[i / kWarps][i % kWarps] = kKeyNone;
+    wrow[i / kWarps][i % kWarps] = kRowNone;
+  }
+  // Per-row integer key and accelerator-bit address, computed once.
+  uint32_t klo[RPT], khi[RPT], aw[RPT], ab[RPT];
+  // Warp-level summaries: which flag bits / accelerator keys (id mod 64)
+  // occur in this warp's 32*RPT rows. A query whose requirements are not in
+  // the summary skips the warp with a handful of instructions.
+  uint32_t fl_or = 0, sg_lo = 0, sg_hi = 0;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const bool in_range = base + j < G.row_end;
+    const uint32_t f = in_range ? fl[j] : 0u;
+    klo[j] = f | (rg[j] << 16);
+    khi[j] = zn[j];
+    const bool has = ak[j] != SKYOPT_NONE16 && (f & SKYOPT_F_VALID);
+    aw[j] = (ak[j] == SKYOPT_NONE16) ? (uint32_t)SKYOPT_ACC_SET_WORDS : (ak[j] >> 5);
+    ab[j] = ak[j] & 31u;
+    fl_or |= f;
+    if (has) { if (ak[j] & 32u) sg_hi |= 1u << ab[j]; else sg_lo |= 1u << ab[j]; }
+  }
+  fl_or = __reduce_or_sync(0xFFFFFFFFu, fl_or & 0xFFu);
+  sg_lo = __reduce_or_sync(0xFFFFFFFFu, sg_lo);
+  sg_hi = __reduce_or_sync(0xFFFFFFFFu, sg_hi);
+  __syncthreads();
+  if (tid < nq) {
+    // signature of the keys an accelerator query can match (exact | fuzzy)
+    uint32_t lo32 = 0, hi32 = 0;
+    if (sq[tid].qflags & SKYOPT_Q_ACC) {
+      for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
+        const uint32_t bits = sset[tid][0][w] | sset[tid][1][w];
+        if (w & 1) hi32 |= bits; else lo32 |= bits;
+      }
+    } else {
+      lo32 = hi32 = 0xFFFFFFFFu;
+    }
+    ssig[tid][0] = lo32; ssig[tid][1] = hi32;
+  }
   __syncthreads();
 
   for (int q = 0; q < nq; ++q) {
-    const SkyoptQuery &Q = sq[q];
-    const bool acc = Q.qflags & SKYOPT_Q_ACC;
-    const bool fuzzy = Q.qflags & SKYOPT_Q_FUZZY;
-    const uint32_t fmask = Q.flags_require | SKYOPT_F_VALID;
+    const QueryS &Q = sq[q];
+    const uint32_t qf = Q.qflags;
+    {
+      // warp-uniform early out
+      const uint32_t rq = Q.req_flags;
+      const bool acc_possible = !(qf & SKYOPT_Q_ACC) ||
+                                (((ssig[q][0] & sg_lo) | (ssig[q][1] & sg_hi)) != 0u);
+      if ((fl_or & rq) != rq || !acc_possible) continue;
+    }
     uint32_t m1 = 0, mf = 0;
+    {
+      const uint32_t mlo = Q.mask_lo, mhi = Q.mask_hi, vlo = Q.val_lo, vhi = Q.val_hi;
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const uint32_t f = R.fl[j];
-      bool ok = (base + j < G.row_end) && ((f & fmask) == fmask);
-      ok = ok && (Q.group == 0 || (int)(f >> 8) == Q.group);
-      ok = ok && (Q.region_id < 0 || (int)R.rg[j] == Q.region_id);
-      ok = ok && (Q.zone_id < 0 || (int)R.zn[j] == Q.zone_id);
-      bool ex = ok, fz = false;
-      if (acc) {
-        const uint32_t k = R.ak[j];
-        const bool has = ok && k != SKYOPT_NONE16;
-        ex = has && test_bit(sset[q][0], k);
-        fz = has && fuzzy && test_bit(sset[q][1], k);
+      for (int j = 0; j < RPT; ++j) {
+        const uint32_t t = ((klo[j] ^ vlo) & mlo) | ((khi[j] ^ vhi) & mhi);
+        m1 |= (uint32_t)(t == 0u) << j;
       }
-      m1 |= (uint32_t)ex << j;
-      mf |= (uint32_t)fz << j;
+    }
+    if (qf & SKYOPT_Q_ACC) {
+      uint32_t me = 0;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) me |= ((sset[q][0][aw[j]] >> ab[j]) & 1u) << j;
+      if (qf & SKYOPT_Q_FUZZY) {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) mf |= ((sset[q][1][aw[j]] >> ab[j]) & 1u) << j;
+        mf &= m1;
+      }
+      m1 &= me;
     }
     if (Q.disk_op != 0 && (m1 | mf)) {
       // AWS local-disk size test (common.py:499-504); rare, so the column is
@@ -225,24 +313,23 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         if (!((m1 >> j) & 1u)) continue;
-        bool ok = (R.fl[j] & Q.flags_require2) == Q.flags_require2;
-        if (Q.cpus_op == SKYOPT_OP_EQ) ok = ok && R.vc[j] == Q.cpus;
-        else if (Q.cpus_op == SKYOPT_OP_GE) ok = ok && R.vc[j] >= Q.cpus;
-        if (Q.mem_op == SKYOPT_OP_EQ) ok = ok && R.mm[j] == Q.mem;
-        else if (Q.mem_op == SKYOPT_OP_GE) ok = ok && R.mm[j] >= Q.mem;
-        else if (Q.mem_op == SKYOPT_OP_RATIO)
-          ok = ok && R.mm[j] >= __dmul_rn(R.vc[j], Q.mem);
+        bool ok = (fl[j] & Q.flags2) == Q.flags2;
+        if (Q.cpus_op) ok = ok && (vc[j] >= Q.cpu_lo) && (vc[j] <= Q.cpu_hi);
+        if (Q.mem_op == SKYOPT_OP_RATIO)
+          ok = ok && mm[j] >= __dmul_rn(vc[j], Q.mem_lo);
+        else if (Q.mem_op)
+          ok = ok && (mm[j] >= Q.mem_lo) && (mm[j] <= Q.mem_hi);
         if (!ok) continue;
-        const double p = Q.price_col ? R.sp[j] : R.od[j];
-        const bool priced = p <= Q.max_price;  // false for NaN
+        const double p = Q.price_col ? sp[j] : od[j];
+        const bool priced = p <= Q.cap;  // false for NaN
         uint64_t key = kKeyNone;
         if (priced) {
           key = price_key(p);
           if (key < bkey) { bkey = key; brow = (uint32_t)(base + j); }
-        } else if ((Q.qflags & SKYOPT_Q_KEEP_NAN) && p != p) {
+        } else if ((qf & SKYOPT_Q_KEEP_NAN) && p != p) {
           key = kKeyNaN;
         }
-        if ((Q.qflags & SKYOPT_Q_LIST) && key != kKeyNone) {
+        if ((qf & SKYOPT_Q_LIST) && key != kKeyNone) {
           const int inst = __ldg(cat.inst_id + base + j);
           if (inst >= 0) {
             const int local = inst - __ldg(&cat.cloud_inst_offsets[Q.cloud]);
@@ -257,28 +344,25 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         if (!((mf >> j) & 1u)) continue;
-        const double p = (G.need & 1u) ? R.od[j] : __ldg(cat.price + base + j);
+        const double p = (G.need & 1u) ? od[j] : __ldg(cat.price + base + j);
         const uint64_t key = (p == p) ? price_key(p) : kKeyNaN;
-        atomicMin(&fuzzy_min[fuzzy_base[sqid[q]] + R.ak[j]],
+        atomicMin(&fuzzy_min[fuzzy_base[sqid[q]] + ak[j]],
                   (unsigned long long)key);
       }
     }
     // Warp argmin of (price key, row) with three REDUX steps; skipped when no
     // lane has a candidate (the common case for selective queries).
     if (__any_sync(0xFFFFFFFFu, brow != kRowNone)) {
-      const uint32_t khi = (uint32_t)(bkey >> 32);
-      const uint32_t mhi = __reduce_min_sync(0xFFFFFFFFu, khi);
-      const uint32_t klo = (khi == mhi) ? (uint32_t)bkey : 0xFFFFFFFFu;
-      const uint32_t mlo = __reduce_min_sync(0xFFFFFFFFu, klo);
-      const uint32_t kr = (khi == mhi && klo == mlo) ? brow : kRowNone;
+      const uint32_t khi32 = (uint32_t)(bkey >> 32);
+      const uint32_t mhi32 = __reduce_min_sync(0xFFFFFFFFu, khi32);
+      const uint32_t klo32 = (khi32 == mhi32) ? (uint32_t)bkey : 0xFFFFFFFFu;
+      const uint32_t mlo32 = __reduce_min_sync(0xFFFFFFFFu, klo32);
+      const uint32_t kr = (khi32 == mhi32 && klo32 == mlo32) ? brow : kRowNone;
       const uint32_t mr = __reduce_min_sync(0xFFFFFFFFu, kr);
       if (lane == 0) {
-        wkey[q][warp] = ((uint64_t)mhi << 32) | mlo;
+        wkey[q][warp] = ((uint64_t)mhi32 << 32) | mlo32;
         wrow[q][warp] = mr;
       }
-    } else if (lane == 0) {
-      wkey[q][warp] = kKeyNone;
-      wrow[q][warp] = kRowNone;
     }
   }
   __syncthreads();
@@ -292,9 +376,8 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
       if (kw < k || (kw == k && rw < r)) { k = kw; r = rw; }
     }
     ScanPartial out;
-    out.key = k; out.row = r; out.pad_ = 0;
+    out.key = k; out.row = r; out.pad_ = sany[tid];
     partials[(int64_t)partial_base[sqid[tid]] + tile] = out;
-    if (sany[tid]) atomicOr(&any1[sqid[tid]], 1u);
   }
 }
 
@@ -303,18 +386,24 @@ __global__ void finalize_kernel(CatDev cat, int n_queries,
                                 const int32_t *__restrict__ partial_base,
                                 const int32_t *__restrict__ partial_count,
                                 const ScanPartial *__restrict__ partials,
-                                ScanFinal *__restrict__ finals) {
+                                ScanFinal *__restrict__ finals,
+                                uint32_t *__restrict__ any1,
+                                int32_t *__restrict__ err_flag) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *err_flag = 0;
   if (q >= n_queries) return;
   const int64_t pb = partial_base[q];
   const int n = partial_count[q];
   uint64_t k = kKeyNone;
   uint32_t r = kRowNone;
+  uint32_t any = 0;
   for (int i = lane; i < n; i += 32) {
     const ScanPartial p = partials[pb + i];
+    any |= p.pad_;
     if (p.key < k || (p.key == k && p.row < r)) { k = p.key; r = p.row; }
   }
+  any = __reduce_or_sync(0xFFFFFFFFu, any);
   for (int off = 16; off; off >>= 1) {
     const uint64_t ok = __shfl_xor_sync(0xFFFFFFFFu, k, off);
     const uint32_t orow = __shfl_xor_sync(0xFFFFFFFFu, r, off);
@@ -326,6 +415,7 @@ __global__ void finalize_kernel(CatDev cat, int n_queries,
     f.row = (r == kRowNone) ? -1 : (int32_t)r;
     f.inst = (r == kRowNone) ? -1 : cat.inst_id[r];
     finals[q] = f;
+    any1[q] = any;
   }
 }
 
@@ -605,6 +695,105 @@ __device__ __forceinline__ void lexmin(double &v, int &i, double ov, int oi) {
   if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
+// K3a: one block per task -- its candidates in the reference's order
+// (requested Resources -> enabled clouds -> region/zone order), minus the
+// blocked ones, with their cost / time value.
+constexpr int kGatherThreads = 128;
+constexpr int kMaxTaskSlots = 64;
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_kernel(CatDev cat, SolveIn in, SolveWork w, const int32_t *__restrict__ task_dag,
+              int32_t *__restrict__ task_n) {
+  constexpr int kWarps = kGatherThreads / 32;
+  __shared__ int s_cnt[kMaxTaskSlots + 1];   // exclusive prefix of slot counts
+  __shared__ int s_inst[kMaxTaskSlots];
+  __shared__ int s_acc[kMaxTaskSlots];
+  __shared__ int s_wcount[kWarps];
+  __shared__ int s_pos;
+  const int t = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SkyoptTask TK = in.tasks[t];
+  const SkyoptDag D = in.dags[task_dag[t]];
+  const int64_t toff = in.task_off[t];
+  const int n_slots = TK.slot_end - TK.slot_begin;
+  int kept_total = 0;
+  for (int s0 = 0; s0 < n_slots; s0 += kMaxTaskSlots) {
+    const int ns = min(kMaxTaskSlots, n_slots - s0);
+    if (tid < ns) {
+      const int s = TK.slot_begin + s0 + tid;
+      const int inst = in.ex.slot_inst[s];
+      int acc = in.slots[s].cand_acc_key;
+      if (acc < 0 && inst >= 0) acc = cat.inst_acc_key[inst];
+      s_inst[tid] = inst;
+      s_acc[tid] = acc;
+      s_cnt[tid + 1] = in.ex.slot_count[s];
+    }
+    if (tid == 0) { s_cnt[0] = 0; s_pos = kept_total; }
+    __syncthreads();
+    if (tid == 0) for (int i = 0; i < ns; ++i) s_cnt[i + 1] += s_cnt[i];
+    __syncthreads();
+    const int total = s_cnt[ns];
+    for (int base = 0; base < total; base += kGatherThreads) {
+      const int g = base + tid;
+      bool keep = g < total;
+      int ls = 0, i = 0, s = 0, rg = 0, zn = -1;
+      double hourly = 0.0, value = 0.0;
+      int64_t ref = 0;
+      if (keep) {
+        while (s_cnt[ls + 1] <= g) ++ls;
+        i = g - s_cnt[ls];
+        s = TK.slot_begin + s0 + ls;
+        const SkyoptSlot S = in.slots[s];
+        ref = in.slot_off[s] + i;
+        rg = in.ex.cand_region[ref];
+        zn = in.ex.cand_zone[ref];
+        const int inst = s_inst[ls], cand_acc = s_acc[ls];
+        for (int b = D.blocked_begin; b < D.blocked_end; ++b) {
+          const SkyoptBlocked B = in.blocked[b];
+          const bool m = (B.cloud == -1 || B.cloud == S.cloud) &&
+                         (B.inst_id == -1 || B.inst_id == inst) &&
+                         (B.region_id == -1 || B.region_id == rg) &&
+                         (B.zone_id == -1 || B.zone_id == zn) &&
+                         (B.acc_key == -1 || B.acc_key == cand_acc) &&
+                         (B.use_spot == -1 || B.use_spot == S.use_spot);
+          if (m) { keep = false; break; }
+        }
+        // float(hourly_cost * hours) * max(num_nodes - reserved, 0)
+        hourly = __dadd_rn(in.ex.cand_price_a[ref], in.ex.cand_price_b[ref]);
+        value = D.minimize_cost
+                    ? __dmul_rn(__dmul_rn(hourly, S.hours), S.node_mult)
+                    : S.time_value;
+        if (keep) {
+          // stash the cloud in the low bits of nothing: written below
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+      if (lane == 0) s_wcount[warp] = __popc(bal);
+      __syncthreads();
+      int prefix = s_pos;
+      for (int k = 0; k < warp; ++k) prefix += s_wcount[k];
+      if (keep) {
+        const int64_t o = toff + prefix + __popc(bal & ((1u << lane) - 1u));
+        w.tc_ref[o] = (int32_t)ref;
+        w.tc_slot[o] = s;
+        w.tc_cloud[o] = in.slots[s].cloud;
+        w.tc_hourly[o] = hourly;
+        w.tc_value[o] = value;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int k = 0; k < kWarps; ++k) tot += s_wcount[k];
+        s_pos += tot;
+      }
+      __syncthreads();
+    }
+    kept_total = s_pos;
+    __syncthreads();
+  }
+  if (tid == 0) task_n[t] = kept_total;
+}
+
 __global__ void __launch_bounds__(kSolveThreads)
 solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   constexpr int kWarps = kSolveThreads / 32;
@@ -627,73 +816,12 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   if (tid == 0) s_fail = -1;
   __syncthreads();
 
-  // ---- Phase A: candidates of every task, in the reference's order
-  // (requested Resources -> enabled clouds -> region/zone order), minus the
-  // blocked ones, with their cost / time value.
-  for (int t = D.task_begin; t < D.task_end; ++t) {
-    const SkyoptTask TK = in.tasks[t];
-    const int64_t toff = in.task_off[t];
-    if (tid == 0) s_pos = 0;
-    __syncthreads();
-    for (int s = TK.slot_begin; s < TK.slot_end; ++s) {
-      const SkyoptSlot S = in.slots[s];
-      const int cnt = in.ex.slot_count[s];
-      const int inst = in.ex.slot_inst[s];
-      const int64_t off = in.slot_off[s];
-      int cand_acc = S.cand_acc_key;
-      if (cand_acc < 0 && inst >= 0) cand_acc = cat.inst_acc_key[inst];
-      for (int base = 0; base < cnt; base += kSolveThreads) {
-        const int i = base + tid;
-        bool keep = i < cnt;
-        int rg = 0, zn = -1;
-        double hourly = 0.0, value = 0.0;
-        if (keep) {
-          rg = in.ex.cand_region[off + i];
-          zn = in.ex.cand_zone[off + i];
-          for (int b = D.blocked_begin; b < D.blocked_end; ++b) {
-            const SkyoptBlocked B = in.blocked[b];
-            const bool m = (B.cloud == -1 || B.cloud == S.cloud) &&
-                           (B.inst_id == -1 || B.inst_id == inst) &&
-                           (B.region_id == -1 || B.region_id == rg) &&
-                           (B.zone_id == -1 || B.zone_id == zn) &&
-                           (B.acc_key == -1 || B.acc_key == cand_acc) &&
-                           (B.use_spot == -1 || B.use_spot == S.use_spot);
-            if (m) { keep = false; break; }
-          }
-          // float(hourly_cost * hours) * max(num_nodes - reserved, 0)
-          hourly = __dadd_rn(in.ex.cand_price_a[off + i], in.ex.cand_price_b[off + i]);
-          value = D.minimize_cost
-                      ? __dmul_rn(__dmul_rn(hourly, S.hours), S.node_mult)
-                      : S.time_value;
-        }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-        if (lane == 0) s_wcount[warp] = __popc(bal);
-        __syncthreads();
-        int prefix = s_pos;
-        for (int k = 0; k < warp; ++k) prefix += s_wcount[k];
-        if (keep) {
-          const int64_t o = toff + prefix + __popc(bal & ((1u << lane) - 1u));
-          w.tc_ref[o] = (int32_t)(off + i);
-          w.tc_slot[o] = s;
-          w.tc_cloud[o] = S.cloud;
-          w.tc_hourly[o] = hourly;
-          w.tc_value[o] = value;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          int tot = 0;
-          for (int k = 0; k < kWarps; ++k) tot += s_wcount[k];
-          s_pos += tot;
-        }
-        __syncthreads();
-      }
-    }
-    if (tid == 0) {
-      out.task_n[t] = s_pos;
-      if (s_pos == 0 && s_fail < 0) s_fail = t - D.task_begin;
-    }
-    __syncthreads();
+  // ---- Phase A ran in gather_kernel: candidate tables are ready.
+  if (tid == 0) {
+    for (int t = D.task_begin; t < D.task_end; ++t)
+      if (out.task_n[t] == 0) { s_fail = t - D.task_begin; break; }
   }
+  __syncthreads();
   if (s_fail >= 0) {
     if (tid == 0) {
       SkyoptDagResult r; r.status = 1; r.task_fail = s_fail;

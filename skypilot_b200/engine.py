@@ -428,6 +428,15 @@ def solve(builder: ProblemBuilder,
     sol = Solution(packed, want_tables)
     lib = _native.load()
     handle = builder.store.handle(device)
+    if packed.n_slots == 0:
+        # Host rules (feature gates, unknown names) left nothing to ask the
+        # device: every task is without candidates.
+        sol.dag['status'][:] = 1
+        for d in range(packed.n_dags):
+            sol.dag['task_fail'][d] = 0
+        sol.dag['objective'][:] = math.nan
+        sol.chosen_index[:] = -1
+        return sol
     prob = packed.c_problem()
     csol = sol.c_solution()
     _native.check(

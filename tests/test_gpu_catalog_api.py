@@ -1,0 +1,203 @@
+"""GPU tests of the catalog function table (the drop-in boundary at the
+catalog layer): the reference's own inline known-answer vectors and the
+per-cloud functions, checked against the pandas oracle."""
+import numpy as np
+import pytest
+
+import skypilot_b200 as sky
+from oracle import catalog_oracle as co
+from skypilot_b200.catalog import common
+from tests import reference_vectors as rv
+from tests import scenario_runner as runner
+from tests import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('cpus,memory,region,zone,expected', rv.AZ_CASES)
+def test_cpus_mem_with_az(cpus, memory, region, zone, expected):
+    df = rv.az_frame()
+    assert common.get_instance_type_for_cpus_mem_impl(
+        df, cpus=cpus, memory_gb_or_ratio=memory, region=region,
+        zone=zone) == expected
+
+
+@pytest.mark.parametrize('cpus,memory,region,expected', rv.NO_AZ_CASES)
+def test_cpus_mem_no_az(cpus, memory, region, expected):
+    df = rv.no_az_frame()
+    assert common.get_instance_type_for_cpus_mem_impl(
+        df, cpus=cpus, memory_gb_or_ratio=memory, region=region) == expected
+
+
+def test_hourly_cost_is_python_float():
+    df = rv.price_frame()
+    for spot, want in ((False, 1.5), (True, 0.5)):
+        cost = common.get_hourly_cost_impl(df, 'test-instance', use_spot=spot,
+                                           region=None, zone=None)
+        assert type(cost) is float and cost == want  # pylint: disable=unidiomatic-typecheck
+
+
+@pytest.mark.parametrize('local_disk,expected', rv.LOCAL_DISK_CASES)
+def test_local_disk_selection(local_disk, expected):
+    view = common.filter_with_local_disk(rv.local_disk_frame(), local_disk)
+    assert common.get_instance_type_for_cpus_mem_impl(
+        view, cpus='1+', memory_gb_or_ratio=None, region=None) == expected
+
+
+@pytest.fixture(scope='module')
+def frames():
+    store = runner.activate_catalog(scenarios.CATALOGS['multi6k'])
+    return {t.name: t.frame for t in store.clouds}
+
+
+ACC_CASES = [
+    ('aws', 'V100', 1, {}), ('aws', 'T4', 1, {'cpus': '8+'}),
+    ('aws', 'A100', 8, {'use_spot': True}), ('aws', 'A100', 3, {}),
+    ('aws', 'T4', 1, {'region': 'us-west-2'}),
+    ('aws', 'V100', 4, {'max_hourly_cost': 1.0}),
+    ('azure', 'A10', 0.5, {}), ('azure', 'V100', 2, {'memory': '200+'}),
+    ('lambda', 'A100', 1, {}), ('lambda', 'H100', 3, {}),
+    ('aws', 'NoSuch', 1, {}), ('azure', 'K80', 1, {'use_spot': True}),
+]
+
+
+@pytest.mark.parametrize('cloud,acc,count,kw', ACC_CASES)
+def test_instance_type_for_accelerator_lists(frames, cloud, acc, count, kw):
+    """(sorted instance types, fuzzy candidates) == the pandas oracle's."""
+    want = co.instance_type_for_accelerator(frames[cloud], acc, count, **kw)
+    got = sky.catalog.get_instance_type_for_accelerator(acc, count,
+                                                        clouds=cloud, **kw)
+    assert got[0] == want[0]
+    assert got[1] == want[1]
+
+
+@pytest.mark.parametrize('cloud,instance_type,spot', [
+    ('aws', 'p3.2xlarge', False), ('aws', 'g4dn.xlarge', True),
+    ('gcp', 'n2-standard-8', False), ('gcp', 'n1-highmem-8', True),
+    ('azure', 'Standard_NC6s_v3', True), ('lambda', 'gpu_1x_a100', False),
+])
+def test_region_zones_and_hourly_cost(frames, cloud, instance_type, spot):
+    df = frames[cloud]
+    want = co.region_zones(df[df['InstanceType'] == instance_type], spot)
+    if cloud in ('aws', 'lambda'):
+        want = co.us_first(want)
+    got = sky.catalog.get_region_zones_for_instance_type(instance_type, spot,
+                                                         clouds=cloud)
+    assert [(r.name, None if r.zones is None else [z.name for z in r.zones])
+            for r in got] == want
+    for region, zones in want[:3]:
+        assert sky.catalog.get_hourly_cost(
+            instance_type, spot, region, None, clouds=cloud) == (
+                co.hourly_cost(df, instance_type, spot, region, None))
+        if zones:
+            assert sky.catalog.get_hourly_cost(
+                instance_type, spot, region, zones[0], clouds=cloud) == (
+                    co.hourly_cost(df, instance_type, spot, region, zones[0]))
+    assert sky.catalog.get_hourly_cost(
+        instance_type, spot, None, None,
+        clouds=cloud) == co.hourly_cost(df, instance_type, spot, None, None)
+
+
+@pytest.mark.parametrize('acc,count,spot', [('T4', 1, False), ('V100', 2, True),
+                                            ('A100', 8, False),
+                                            ('tpu-v3-8', 1, True)])
+def test_gcp_accelerator_functions(frames, acc, count, spot):
+    df = frames['gcp']
+    want = co.region_zones(co.gcp_accelerator_rows(df, acc, count, None), spot)
+    got = sky.catalog.get_region_zones_for_accelerators(acc, count, spot,
+                                                        clouds='gcp')
+    assert [(r.name, [z.name for z in r.zones]) for r in got] == want
+    for region, zones in want[:2]:
+        w = co.gcp_accelerator_hourly_cost(df, acc, count, spot, region,
+                                           zones[0])
+        g = sky.catalog.get_accelerator_hourly_cost(acc, count, spot, region,
+                                                    zones[0], clouds='gcp')
+        assert g == pytest.approx(float(w), rel=1e-12)
+    inst, fuzzy = sky.catalog.get_instance_type_for_accelerator(
+        acc, count, clouds='gcp') if not acc.startswith('tpu') else ([None],
+                                                                     [])
+    if not acc.startswith('tpu'):
+        w_inst, w_fuzzy = co.gcp_instance_type_for_accelerator(
+            df, acc, count, None, None, False, None, None, None)
+        assert inst == w_inst and fuzzy == w_fuzzy
+
+
+def test_feasible_resources_object_path(frames):
+    """Cloud.get_feasible_launchable_resources / _fill_in_launchable_resources
+    (the non-fused API) agree with the fused optimizer's candidate tables."""
+    del frames
+    from skypilot_b200 import optimizer as opt_lib
+    task = sky.Task('t')
+    task.set_resources(sky.Resources(accelerators='T4'))
+    launchable, per_cloud, fuzzy, hints = (
+        opt_lib._fill_in_launchable_resources(task, None, quiet=True))  # pylint: disable=protected-access
+    objs = list(launchable.values())[0]
+    with sky.Dag() as dag:
+        dag.add(task)
+    opt_lib.Optimizer._add_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+    try:
+        import networkx as nx
+        topo = list(nx.topological_sort(dag.get_graph()))
+        cost_map, _ = opt_lib.Optimizer._estimate_nodes_cost_or_time(topo)  # pylint: disable=protected-access
+    finally:
+        opt_lib.Optimizer._remove_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+    fused = list(cost_map[task].keys())
+    key = lambda r: (str(r.cloud), r.instance_type, r.region, r.zone)  # noqa: E731
+    assert [key(r) for r in objs] == [key(r) for r in fused]
+    for r, v in cost_map[task].items():
+        assert r.get_cost(3600) == pytest.approx(v, rel=1e-12)
+    assert not fuzzy and not hints
+    assert all(len(v) >= 1 for v in per_cloud.values())
+    bad = sky.Task('bad')
+    bad.set_resources(sky.Resources(accelerators='A100:3'))
+    _, _, fuzzy, _ = opt_lib._fill_in_launchable_resources(bad, None,  # pylint: disable=protected-access
+                                                            quiet=True)
+    assert 'A100:8' in fuzzy or 'A100:4' in fuzzy
+
+
+def test_batch_of_independent_dags_matches_single_calls():
+    """cfg5 shape: many single-task DAGs in ONE device call == one by one."""
+    import networkx as nx
+    from skypilot_b200 import engine
+    from skypilot_b200 import optimizer as opt_lib
+    store = runner.activate_catalog(scenarios.CATALOGS['multi6k'])
+    rng = np.random.default_rng(4)
+    accs = [None, 'V100', 'T4', 'A100:8', 'L4', 'H100:8', 'A10G', 'K80']
+    specs = []
+    for _ in range(64):
+        spec = {}
+        acc = accs[int(rng.integers(len(accs)))]
+        if acc:
+            spec['accelerators'] = acc
+        cpus = [None, '2+', '8+', '32+'][int(rng.integers(4))]
+        if cpus:
+            spec['cpus'] = cpus
+        if rng.uniform() < 0.3:
+            spec['use_spot'] = True
+        specs.append(spec)
+    b = engine.ProblemBuilder(store)
+    problems, singles = [], []
+    for spec in specs:
+        with sky.Dag() as dag:
+            t = sky.Task('t')
+            t.set_resources(sky.Resources(**spec))
+        graph = dag.get_graph()
+        problems.append(
+            opt_lib.Optimizer._state_problem(graph, [t], True, [], True,  # pylint: disable=protected-access
+                                             builder=b))
+        try:
+            sky.optimize(dag, quiet=True)
+            r = t.best_resources
+            singles.append((str(r.cloud), r.instance_type, r.region, r.zone))
+        except sky.exceptions.ResourcesUnavailableError:
+            singles.append(None)
+    sol = engine.solve(b)
+    assert len(sol.dag) == len(specs)
+    for i, prob in enumerate(problems):
+        if sol.dag[i]['status'] != 0:
+            assert singles[i] is None
+            continue
+        r = prob.launchable(sol.chosen[i])
+        assert (str(r.cloud), r.instance_type, r.region,
+                r.zone) == singles[i]
+    del nx

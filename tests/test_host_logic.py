@@ -1,0 +1,268 @@
+"""CPU tests of the host side: catalog ingest, constraint-vector
+construction, Resources / Dag semantics, egress tariffs and the C ABI
+(symbols and struct layouts only -- no kernel runs without a GPU)."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import skypilot_b200 as sky
+from skypilot_b200 import _native
+from skypilot_b200 import engine
+from skypilot_b200 import synth
+from skypilot_b200.catalog import rules
+from skypilot_b200.catalog.store import CatalogStore
+from skypilot_b200.utils import registry
+from tests import reference_vectors as rv
+from tests import scenario_runner as runner
+from tests import scenarios
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def store():
+    return runner.activate_catalog(scenarios.CATALOGS['multi6k'])
+
+
+# ---- C ABI -----------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    """Every function include/skyopt.h declares is exported by libskyopt.so."""
+    with open(os.path.join(_REPO, 'include', 'skyopt.h'),
+              encoding='utf-8') as f:
+        header = f.read()
+    declared = set(re.findall(r'\b(skyopt_[a-z_]+)\s*\(', header))
+    assert declared == set(_native.EXPORTS)
+    lib = _native.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.skyopt_abi_version() == _native.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    """numpy dtypes mirror the C structs (sizes / key offsets)."""
+    assert _native.QUERY_DTYPE.itemsize == 88
+    assert _native.QUERY_DTYPE.fields['cpus'][1] == 56
+    assert _native.QUERY_DTYPE.fields['max_price'][1] == 80
+    assert _native.SLOT_DTYPE.itemsize == 72
+    assert _native.SLOT_DTYPE.fields['hours'][1] == 48
+    assert _native.CANDIDATE_DTYPE.fields['hourly'][1] == 16
+    assert _native.DAG_RESULT_DTYPE.fields['objective'][1] == 8
+    assert ctypes.sizeof(_native.Stats) == 48
+
+
+def test_no_device_fails_loudly():
+    """Without a GPU the product path raises; it never falls back to CPU."""
+    if _native.device_count() > 0:
+        pytest.skip('a GPU is present')
+    frames = synth.make_catalogs(5, 600, clouds=['aws'])
+    st = CatalogStore.from_frames(frames)
+    with pytest.raises(_native.SkyoptError):
+        st.handle(0)
+
+
+# ---- ingest ----------------------------------------------------------------
+def test_ingest_layout(store):
+    c = store.columns
+    offs = c['cloud_row_offsets']
+    assert offs[0] == 0 and offs[-1] == store.n_rows
+    assert all(o % 8 == 0 for o in offs)
+    assert store.n_real_rows == sum(t.n_rows for t in store.clouds)
+    for name in ('price', 'spot_price', 'vcpus', 'mem'):
+        assert c[name].dtype == np.float64 and len(c[name]) == store.n_rows
+    for name in ('acc_key', 'region_id', 'zone_id', 'flags'):
+        assert c[name].dtype == np.uint16 and len(c[name]) == store.n_rows
+    # padding rows are invalid
+    for t, b, e in zip(store.clouds, offs[:-1], offs[1:]):
+        assert np.all(c['flags'][b:b + t.n_rows] & _native.F_VALID)
+        assert not np.any(c['flags'][b + t.n_rows:e] & _native.F_VALID)
+
+
+def test_ingest_columns_round_trip(store):
+    """Decoding the SoA columns gives back the CSV frame of every cloud."""
+    c = store.columns
+    for t in store.clouds:
+        b, e = t.row_begin, t.row_end
+        df = t.frame
+        assert np.array_equal(
+            np.nan_to_num(c['price'][b:e], nan=-1.0),
+            np.nan_to_num(df['Price'].to_numpy(dtype=float), nan=-1.0))
+        regions = [t.region_names[i] for i in c['region_id'][b:e]]
+        assert regions == list(df['Region'])
+        inst = [
+            None if i < 0 else store.inst_names[i] for i in c['inst_id'][b:e]
+        ]
+        want = [None if x != x or x is None else x
+                for x in df['InstanceType'].astype(object)]
+        assert inst == want
+        if t.has_zone_column:
+            zones = [
+                None if z == _native.NONE16 else t.zone_names[z]
+                for z in c['zone_id'][b:e]
+            ]
+            wantz = [None if x != x or x is None else x
+                     for x in df['AvailabilityZone'].astype(object)]
+            assert zones == wantz
+
+
+def test_region_ids_are_ranks_in_string_order(store):
+    for t in store.clouds:
+        assert t.region_names == sorted(t.region_names)
+        assert t.zone_names == sorted(t.zone_names)
+
+
+def test_csr_groups_rows_by_instance_type(store):
+    c = store.columns
+    off, rows, iid = c['inst_row_offsets'], c['inst_rows'], c['inst_id']
+    for inst in range(0, len(store.inst_names), 37):
+        seg = rows[off[inst]:off[inst + 1]]
+        assert len(seg) > 0
+        assert np.all(iid[seg] == inst)
+        assert np.all(np.diff(seg) > 0)
+    assert off[-1] == int(np.sum(iid >= 0))
+
+
+def test_flag_rules(store):
+    aws = store.cloud('aws')
+    c = store.columns
+    for name, want in (('m6i.2xlarge', True), ('c7i.large', True),
+                       ('m5.large', False), ('p3.2xlarge', False)):
+        row = aws.row_begin + int(aws.inst_first_row[aws.inst_index[name] -
+                                                     aws.inst_begin])
+        assert bool(c['flags'][row] & _native.F_DEFAULT_FAMILY) is want
+    assert rules.azure_instance_family('Standard_D8s_v5') == 'Ds_v5'
+    assert rules.azure_instance_family('Standard_NC4as_T4_v3') == 'NCas_T4_v3'
+    assert rules.azure_instance_family('Standard_E4-2ds_v4') == 'E_ds_v4'
+    assert rules.azure_is_s_series('Standard_D8s_v5')
+    assert not rules.azure_is_s_series('Standard_D8_v5')
+    gcp = store.cloud('gcp')
+    row = gcp.row_begin + int(
+        gcp.inst_first_row[gcp.inst_index['a2-highgpu-8g'] - gcp.inst_begin])
+    assert (c['flags'][row] >> 8) == rules.GCP_GROUP_IDS[('A100', 8)]
+
+
+# ---- constraint vectors ------------------------------------------------------
+def test_cpus_memory_parsing():
+    assert engine.parse_cpus('8+') == (_native.OP_GE, 8.0)
+    assert engine.parse_cpus('4') == (_native.OP_EQ, 4.0)
+    assert engine.parse_cpus(None) == (_native.OP_NONE, 0.0)
+    assert engine.parse_memory('16+') == (_native.OP_GE, 16.0)
+    assert engine.parse_memory('4x') == (_native.OP_RATIO, 4.0)
+    assert engine.parse_memory('32') == (_native.OP_EQ, 32.0)
+    with pytest.raises(ValueError):
+        engine.parse_cpus('many')
+
+
+def test_accelerator_sets_follow_pandas_semantics(store):
+    exact, fuzzy, strict = engine.accelerator_sets(store, 'a100', 8)
+    names = lambda words: sorted(  # noqa: E731
+        store.acc_keys[k] for k in range(len(store.acc_keys))
+        if (words[k >> 5] >> (k & 31)) & 1)
+    assert names(exact) == [('A100', 8.0)]
+    assert names(strict) == [('A100', 8.0)]
+    got = names(fuzzy)
+    assert ('A100-80GB', 8.0) in got and ('A100', 16.0) in got
+    assert all('a100' in n.lower() and c >= 8 for n, c in got)
+    exact, _, strict = engine.accelerator_sets(store, 'A10', 0.17)
+    assert names(exact) == [('A10', 0.167)]  # |count - c| <= 0.01
+    assert names(strict) == []               # count == c
+
+
+def test_problem_for_a_chain(store):
+    del store
+    sc = next(s for s in scenarios.basic_scenarios()
+              if s['name'] == 'chain2_egress_big')
+    dag, tasks = runner.build_dag(sc)
+    import networkx as nx
+    from skypilot_b200.optimizer import Optimizer
+    graph = dag.get_graph()
+    topo = list(nx.topological_sort(graph))
+    problem = Optimizer._state_problem(graph, topo, True, [], True)  # pylint: disable=protected-access
+    p = problem.builder.pack()
+    # T4 on 4 clouds (GCP needs a gate + a host query) and cpus=8+ on 4
+    assert (p.n_tasks, p.n_slots, p.n_queries, p.n_dags) == (2, 8, 9, 1)
+    assert list(p.tasks['n_parents'][:2]) == [0, 1]
+    aws_i = problem.builder.store.cloud_index['aws']
+    assert p.tariffs[aws_i] == pytest.approx(
+        sky.AWS().get_egress_cost(500))
+    q_cpu = p.queries[p.slots['query'][4]]
+    assert q_cpu['cpus_op'] == _native.OP_GE and q_cpu['cpus'] == 8.0
+    assert q_cpu['mem_op'] == _native.OP_RATIO and q_cpu['mem'] == 4.0
+    assert q_cpu['flags_require'] & _native.F_DEFAULT_FAMILY
+    assert math.isinf(q_cpu['max_price'])
+    del tasks
+
+
+# ---- Resources / Dag -----------------------------------------------------------
+def _res(kwargs):
+    kwargs = dict(kwargs)
+    kwargs['cloud'] = registry.CLOUD_REGISTRY.from_str(kwargs['cloud'])
+    return sky.Resources(**kwargs)
+
+
+@pytest.mark.parametrize('cand,blocked,expected', rv.BLOCKED_CASES)
+def test_should_be_blocked_by(cand, blocked, expected):
+    assert _res(cand).should_be_blocked_by(_res(blocked)) is expected
+
+
+@pytest.mark.parametrize('edges,n,expected', rv.CHAIN_CASES)
+def test_dag_is_chain(edges, n, expected):
+    with sky.Dag() as dag:
+        tasks = [sky.Task(f't{i}') for i in range(n)]
+        for u, v in edges:
+            tasks[u] >> tasks[v]  # pylint: disable=pointless-statement
+    assert dag.is_chain() is expected
+
+
+def test_resources_parsing_and_copy():
+    r = sky.Resources(accelerators='V100:4', cpus='8+', memory=32,
+                      use_spot=True)
+    assert r.accelerators == {'V100': 4}
+    assert r.cpus == '8+' and r.memory == '32'
+    c = r.copy(cloud=sky.AWS(), instance_type='p3.8xlarge', region='us-east-1')
+    assert c.is_launchable() and c.use_spot and c.region == 'us-east-1'
+    assert not r.is_launchable()
+    assert sky.Resources(accelerators='A10:0.5').accelerators == {'A10': 0.5}
+    assert sky.Resources(infra='aws/us-east-1/us-east-1a').zone == 'us-east-1a'
+    with pytest.raises(ValueError):
+        sky.Resources(cpus='-1')
+    with pytest.raises(ValueError):
+        sky.Resources(accelerators='V100:x')
+
+
+def test_validate_canonicalises_and_infers(store):
+    del store
+    r = sky.Resources(accelerators='a100-80gb:8')
+    r.validate()
+    assert r.accelerators == {'A100-80GB': 8}
+    r = sky.Resources(instance_type='p3.8xlarge')
+    r.validate()
+    assert isinstance(r.cloud, sky.AWS)
+    r = sky.Resources(cloud=sky.AWS(), zone='us-east-1a')
+    r.validate()
+    assert r.region == 'us-east-1'
+    with pytest.raises(ValueError):
+        sky.Resources(cloud=sky.AWS(), region='mars-1').validate()
+
+
+def test_egress_tariffs_match_the_oracle():
+    from oracle import optimizer_oracle as oo
+    for cloud, name in ((sky.AWS(), 'aws'), (sky.GCP(), 'gcp'),
+                        (sky.Azure(), 'azure'), (sky.Lambda(), 'lambda')):
+        for g in (0.5, 1, 80, 1024, 5000, 10240, 20000, 51200, 60000, 153600,
+                  200000):
+            assert cloud.get_egress_cost(g) == oo.egress_tariff(name, g)
+
+
+def test_dummy_nodes_round_trip():
+    from skypilot_b200.optimizer import Optimizer
+    with sky.Dag() as dag:
+        a, b = sky.Task('a'), sky.Task('b')
+        a >> b  # pylint: disable=pointless-statement
+    Optimizer._add_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+    assert len(dag.tasks) == 4 and dag.is_chain()
+    Optimizer._remove_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+    assert dag.tasks == [a, b]
