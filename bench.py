@@ -192,8 +192,9 @@ def main():
     parser.add_argument('--impl', default='ours',
                         choices=['ours', 'reference'])
     parser.add_argument('--cpu-baseline-steps', type=int, default=5)
-    parser.add_argument('--no-stress', action='store_true',
-                        help='skip the extra cfg4 HBM-stress measurement')
+    parser.add_argument('--scan-mode', default='auto',
+                        choices=['auto', 'tile', 'stream', 'stream3'],
+                        help='scan kernel variant (tuning / tests)')
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -245,6 +246,8 @@ def main():
     n_rows = synth.total_rows(frames)
     store = sky.catalog.load_frames(frames, device=local_rank)
     store.handle(local_rank)
+    if args.scan_mode != 'auto':
+        store.set_scan_mode(args.scan_mode, local_rank)
     n_tasks = workload['tasks']
     n_candidates = n_rows * n_tasks
 

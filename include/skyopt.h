@@ -293,6 +293,11 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *desc, int device,
 int skyopt_catalog_destroy(SkyoptCatalog *cat);
 int skyopt_catalog_bytes(const SkyoptCatalog *cat, int64_t *device_bytes,
                          int64_t *row_bytes);
+/* Scan kernel selection: 0 = auto (by catalog size), 1 = one tile per block
+ * (rows straight to registers), 2 = streaming kernel (TMA double buffering
+ * through shared memory). Results are identical; used by tests and tuning.
+ * The environment variable SKYOPT_SCAN_MODE=tile|stream sets the default. */
+int skyopt_catalog_set_scan_mode(SkyoptCatalog *cat, int mode);
 
 /*
  * Filter + argmin only: get_instance_type_for_accelerator_impl /

@@ -163,6 +163,7 @@ EXPORTS = (
     'skyopt_abi_version', 'skyopt_last_error', 'skyopt_device_count',
     'skyopt_catalog_create', 'skyopt_catalog_destroy', 'skyopt_catalog_bytes',
     'skyopt_scan', 'skyopt_optimize', 'skyopt_optimize_timed',
+    'skyopt_catalog_set_scan_mode',
 )
 
 _lib = None
@@ -200,6 +201,9 @@ def load() -> ctypes.CDLL:
             ctypes.c_void_p,
             ctypes.POINTER(ctypes.c_int64),
             ctypes.POINTER(ctypes.c_int64)
+        ]
+        lib.skyopt_catalog_set_scan_mode.argtypes = [
+            ctypes.c_void_p, ctypes.c_int
         ]
         lib.skyopt_scan.argtypes = [
             ctypes.c_void_p, _p, ctypes.c_int, _p, ctypes.c_int, _p, _p, _p,

@@ -433,6 +433,12 @@ class CatalogStore:
             self._device = device
         return self._handle
 
+    def set_scan_mode(self, mode: str, device: int = 0) -> None:
+        """'auto' | 'tile' | 'stream' (skyopt_catalog_set_scan_mode)."""
+        code = {'auto': 0, 'tile': 1, 'stream': 2, 'stream3': 3}[mode]
+        _native.check(_native.load().skyopt_catalog_set_scan_mode(
+            self.handle(device), code))
+
     def close(self) -> None:
         if self._handle.value is not None:
             _native.load().skyopt_catalog_destroy(self._handle)

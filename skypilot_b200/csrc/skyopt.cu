@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -78,6 +79,7 @@ struct SkyoptCatalog {
   std::vector<int32_t> cloud_group_cap;  // max rows of one expand group
   int sort_n = 2, max_regions = 1, max_zones = 1;
   int sm_count = 148;
+  int scan_mode = 0;  // 0 auto, 1 one tile per block, 2 streaming (TMA) kernel
   std::mutex mu;
   std::vector<Ctx *> free_ctx;
 };
@@ -142,7 +144,7 @@ int ensure(Ctx *x, size_t dbytes, size_t hbytes) {
 struct Plan {
   // sizes
   int nq = 0, nsets = 0, ns = 0, nt = 0, np = 0, ntar = 0, nb = 0, nd = 0;
-  int n_groups = 0, n_blocks = 0, rpt = 4;
+  int n_groups = 0, n_blocks = 0, rpt = 4, tpb = 1; bool stream = false;
   int64_t n_partials = 0, list_entries = 0, fuzzy_entries = 0;
   int64_t cand_cap = 0;   // expand candidate buffers
   int64_t scan_rows = 0, pass_rows = 0;
@@ -280,7 +282,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
 
   std::vector<std::vector<int>> by_cloud(C);
   for (int i = 0; i < P.nq; ++i) by_cloud[pb->queries[i].cloud].push_back(i);
-  auto count_blocks = [&](int rpt) {
+  auto count_tiles = [&](int rpt) {
     long long blocks = 0;
     const int tile = kScanThreads * rpt;
     for (int c = 0; c < C; ++c) {
@@ -292,11 +294,22 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     }
     return blocks;
   };
-  // Large grids use 4 rows/thread (128-bit loads); small catalogs spread
-  // over more, smaller tiles so that all 148 SMs have work.
-  P.rpt = 4;
-  if (count_blocks(4) < 2ll * cat->sm_count) P.rpt = 2;
-  if (P.rpt == 2 && count_blocks(2) < 2ll * cat->sm_count) P.rpt = 1;
+  // Large scans stream several 1024-row tiles per block through shared
+  // memory (TMA double buffering, constraint vectors staged once); sized so
+  // that the grid is about one wave of 2 blocks per SM. Small scans use one
+  // tile per block, with smaller tiles when there is too little work to
+  // cover all SMs.
+  P.rpt = 4; P.tpb = 1; P.stream = false;
+  const long long tiles4 = count_tiles(4);
+  const long long wave = 2ll * cat->sm_count;
+  if (cat->scan_mode >= 2 || (cat->scan_mode == 0 && tiles4 >= 2 * wave)) {
+    P.stream = true;
+    P.tpb = (int)std::max<long long>(1, (tiles4 + wave - 1) / wave);
+    if (cat->scan_mode == 3) P.tpb = 3;  // tests: force the multi-tile loop
+  } else {
+    if (tiles4 < wave) P.rpt = 2;
+    if (P.rpt == 2 && count_tiles(2) < wave) P.rpt = 1;
+  }
   const int tile = kScanThreads * P.rpt;
   P.n_groups = 0;
   for (int c = 0; c < C; ++c)
@@ -317,7 +330,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   for (int i = 0; i < P.nq; ++i) {
     const SkyoptQuery &q = pb->queries[i];
     const int rows = cat->cloud_row_offsets[q.cloud + 1] - cat->cloud_row_offsets[q.cloud];
-    pcount[i] = (rows + tile - 1) / tile;
+    pcount[i] = ((rows + tile - 1) / tile + P.tpb - 1) / P.tpb;
     if (npart + pcount[i] > 0x7FFFFFFFll) return fail(SKYOPT_ELIMIT, "too many scan partials");
     pbase[i] = (int32_t)npart; npart += pcount[i];
     P.scan_rows += rows;
@@ -372,13 +385,15 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   for (int c = 0; c < C; ++c) {
     const auto &qs = by_cloud[c];
     const int rows = cat->cloud_row_offsets[c + 1] - cat->cloud_row_offsets[c];
-    const int tiles = (rows + tile - 1) / tile;
+    const int total_tiles = (rows + tile - 1) / tile;
+    const int tiles = (total_tiles + P.tpb - 1) / P.tpb;  // blocks of the group
     for (size_t b = 0; b < qs.size(); b += kQChunk) {
       const int n = (int)std::min<size_t>(kQChunk, qs.size() - b);
       ScanGroup G{};
       G.row_begin = cat->cloud_row_offsets[c];
       G.row_end = cat->cloud_row_offsets[c + 1];
       G.q_begin = qpos; G.q_count = n; G.block0 = block0; G.n_tiles = tiles;
+      G.tiles_per_block = P.tpb; G.total_tiles = total_tiles;
       for (int k = 0; k < n; ++k) {
         const SkyoptQuery &q = pb->queries[qs[b + k]];
         P.q_order[qpos + k] = qs[b + k];
@@ -409,16 +424,15 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
     if (P.list_entries) CU(cudaMemsetAsync(P.list_min, 0xFF, sizeof(unsigned long long) * P.list_entries, st));
     if (P.fuzzy_entries) CU(cudaMemsetAsync(P.fuzzy_min, 0xFF, sizeof(unsigned long long) * P.fuzzy_entries, st));
     if (P.n_blocks) {
+      ScanArgs sa{cat->dev, P.queries, P.q_order, P.groups, P.n_groups, P.acc_sets,
+                  P.partial_base, P.partials, P.list_base, P.list_min,
+                  P.fuzzy_base, P.fuzzy_min};
       CU(cudaEventRecord(x->ev[6], st));
-#define LAUNCH_SCAN(R)                                                        \
-  scan_kernel<R><<<P.n_blocks, kScanThreads, 0, st>>>(                        \
-      cat->dev, P.queries, P.q_order, P.groups, P.n_groups, P.acc_sets,       \
-      P.partial_base, P.partials, P.any1, P.list_base, P.list_min,            \
-      P.fuzzy_base, P.fuzzy_min)
-      if (P.rpt == 4) LAUNCH_SCAN(4);
-      else if (P.rpt == 2) LAUNCH_SCAN(2);
-      else LAUNCH_SCAN(1);
-#undef LAUNCH_SCAN
+      if (P.stream)
+        scan_stream_kernel<<<P.n_blocks, kScanThreads, kStreamStages * sizeof(StreamStage), st>>>(sa);
+      else if (P.rpt == 4) scan_kernel<4><<<P.n_blocks, kScanThreads, 0, st>>>(sa);
+      else if (P.rpt == 2) scan_kernel<2><<<P.n_blocks, kScanThreads, 0, st>>>(sa);
+      else scan_kernel<1><<<P.n_blocks, kScanThreads, 0, st>>>(sa);
       CU(cudaGetLastError());
       CU(cudaEventRecord(x->ev[7], st));
     }
@@ -602,7 +616,7 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog 
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
 
   const size_t n = (size_t)d->n_rows;
-  const size_t slack = kScanThreads * 4;  // one tile of over-read
+  const size_t slack = kStreamTile;  // one tile of over-read
   int rc = 0;
   CatDev &v = c->dev;
   v.n_rows = d->n_rows;
@@ -668,9 +682,26 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog 
   for (int cl = 0; cl < d->n_clouds; ++cl) c->cloud_group_cap[cl] = c->sort_n;  // sorted output is written sparsely
   const size_t smem = (size_t)c->sort_n * 16 + (size_t)c->max_zones * 8 + (size_t)c->max_regions * 4;
   if (smem > 200 * 1024) { skyopt_catalog_destroy(c); return fail(SKYOPT_ELIMIT, "expand needs %zu B of shared memory", smem); }
-  cudaError_t e = cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 8);
+  // The attribute is per function, not per catalog: only ever raise it.
+  static std::mutex attr_mu;
+  static size_t attr_expand = 48 * 1024;
+  cudaError_t e = cudaSuccess;
+  {
+    std::lock_guard<std::mutex> g(attr_mu);
+    if (smem > attr_expand) {
+      e = cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) attr_expand = smem;
+    }
+  }
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(scan_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kStreamStages * sizeof(StreamStage)));
   if (e != cudaSuccess) { skyopt_catalog_destroy(c); return fail(SKYOPT_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  if (const char *mode = getenv("SKYOPT_SCAN_MODE")) {
+    if (!strcmp(mode, "tile")) c->scan_mode = 1;
+    else if (!strcmp(mode, "stream")) c->scan_mode = 2;
+    else if (!strcmp(mode, "stream3")) c->scan_mode = 3;
+  }
   CU(cudaDeviceSynchronize());
   *out = c;
   return 0;
@@ -689,6 +720,12 @@ int skyopt_catalog_destroy(SkyoptCatalog *c) {
   }
   for (void *p : c->allocs) cudaFree(p);
   delete c;
+  return 0;
+}
+
+int skyopt_catalog_set_scan_mode(SkyoptCatalog *c, int mode) {
+  if (!c || mode < 0 || mode > 3) return fail(SKYOPT_EINVAL, "scan mode must be 0 (auto), 1 (tile), 2 (stream) or 3 (stream, 3 tiles per block)");
+  c->scan_mode = mode;
   return 0;
 }
 

@@ -48,8 +48,10 @@ struct CatDev {
 struct ScanGroup {
   int32_t row_begin, row_end;
   int32_t q_begin, q_count;  // into q_order
-  int32_t block0, n_tiles;
+  int32_t block0, n_tiles;   // first block, number of blocks (partials)
   uint32_t need;             // bit0 on-demand column, bit1 spot column
+  int32_t tiles_per_block;   // stream kernel: consecutive tiles per block
+  int32_t total_tiles;       // stream kernel: tiles of the row range
   int32_t pad_;
 };
 
@@ -150,81 +152,106 @@ __device__ __forceinline__ void load_u16(const uint16_t *__restrict__ col,
 }
 
 constexpr int kSetStride = SKYOPT_ACC_SET_WORDS + 1;  // + a zero word for "no key"
+constexpr int kScanWarps = kScanThreads / 32;
 
-template <int RPT>
-__global__ void __launch_bounds__(kScanThreads, 3)
-scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
-            const int32_t *__restrict__ q_order,
-            const ScanGroup *__restrict__ groups, int n_groups,
-            const uint32_t *__restrict__ acc_sets,
-            const int32_t *__restrict__ partial_base,
-            ScanPartial *__restrict__ partials, uint32_t *__restrict__ any1,
-            const int64_t *__restrict__ list_base,
-            unsigned long long *__restrict__ list_min,
-            const int64_t *__restrict__ fuzzy_base,
-            unsigned long long *__restrict__ fuzzy_min) {
-  constexpr int kWarps = kScanThreads / 32;
-  __shared__ QueryS sq[kQChunk];
-  __shared__ uint32_t sset[kQChunk][2][kSetStride];
-  __shared__ int32_t sqid[kQChunk];
-  __shared__ uint64_t wkey[kQChunk][kWarps];
-  __shared__ uint32_t wrow[kQChunk][kWarps];
-  __shared__ uint32_t sany[kQChunk];
-  __shared__ uint32_t ssig[kQChunk][2];
+// Shared-memory state of one scan block: the staged constraint vectors of up
+// to kQChunk queries and the per-warp running minima.
+struct ScanShared {
+  QueryS sq[kQChunk];
+  uint32_t sset[kQChunk][2][kSetStride];
+  int32_t sqid[kQChunk];
+  int32_t sset_idx[kQChunk][2];
+  uint64_t wkey[kQChunk][kScanWarps];
+  uint32_t wrow[kQChunk][kScanWarps];
+  uint32_t sany[kQChunk];
+  uint32_t ssig[kQChunk][2];
+  uint32_t sreq[kQChunk];
+};
 
-  // blockIdx -> (group, tile): groups are sorted by block0.
-  int lo = 0, hi = n_groups - 1;
-  const int b = blockIdx.x;
+struct ScanArgs {
+  CatDev cat;
+  const SkyoptQuery *queries;
+  const int32_t *q_order;
+  const ScanGroup *groups;
+  int n_groups;
+  const uint32_t *acc_sets;
+  const int32_t *partial_base;
+  ScanPartial *partials;
+  const int64_t *list_base;
+  unsigned long long *list_min;
+  const int64_t *fuzzy_base;
+  unsigned long long *fuzzy_min;
+};
+
+__device__ __forceinline__ ScanGroup find_group(const ScanArgs &a, int b) {
+  // blockIdx -> group: groups are sorted by block0.
+  int lo = 0, hi = a.n_groups - 1;
   while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (__ldg(&groups[mid].block0) <= b) lo = mid; else hi = mid - 1;
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&a.groups[mid].block0) <= b) lo = mid; else hi = mid - 1;
   }
-  const ScanGroup G = groups[lo];
-  const int tile = b - G.block0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  return a.groups[lo];
+}
+
+// Stage the chunk's constraint vectors, then the accelerator-key bitmasks
+// they reference (set indices come from shared memory, so the global loads
+// of one thread are independent and overlap). Ends with a barrier.
+__device__ __forceinline__ void stage_queries(const ScanArgs &a, const ScanGroup &G,
+                                              ScanShared &S) {
+  const int tid = threadIdx.x;
   const int nq = G.q_count;
-
-  // Stream this thread's rows into registers first (32 B per row); the
-  // constraint vectors are staged while the loads are in flight.
-  const int64_t base =
-      (int64_t)G.row_begin + (int64_t)tile * (kScanThreads * RPT) + tid * RPT;
-  double od[RPT], sp[RPT], vc[RPT], mm[RPT];
-  uint32_t ak[RPT], rg[RPT], zn[RPT], fl[RPT];
-  if (G.need & 1u) load_f64<RPT>(cat.price, base, od);
-  if (G.need & 2u) load_f64<RPT>(cat.spot, base, sp);
-  load_f64<RPT>(cat.vcpus, base, vc);
-  load_f64<RPT>(cat.mem, base, mm);
-  load_u16<RPT>(cat.acc_key, base, ak);
-  load_u16<RPT>(cat.region_id, base, rg);
-  load_u16<RPT>(cat.zone_id, base, zn);
-  load_u16<RPT>(cat.flags, base, fl);
-
-  // Stage the chunk's constraint vectors, then the accelerator-key bitmasks
-  // they reference (set indices come from shared memory, so the global loads
-  // of one thread are independent and overlap).
-  __shared__ int32_t sset_idx[kQChunk][2];
   if (tid < nq) {
-    const int qi = __ldg(&q_order[G.q_begin + tid]);
-    const SkyoptQuery q = queries[qi];
-    sqid[tid] = qi;
-    sq[tid] = make_query_s(q);
-    sset_idx[tid][0] = (q.qflags & SKYOPT_Q_ACC) ? q.acc_set : -1;
-    sset_idx[tid][1] = (q.qflags & SKYOPT_Q_FUZZY) ? q.fuzzy_set : -1;
-    sany[tid] = 0;
+    const int qi = __ldg(&a.q_order[G.q_begin + tid]);
+    const SkyoptQuery q = a.queries[qi];
+    S.sqid[tid] = qi;
+    S.sq[tid] = make_query_s(q);
+    S.sset_idx[tid][0] = (q.qflags & SKYOPT_Q_ACC) ? q.acc_set : -1;
+    S.sset_idx[tid][1] = (q.qflags & SKYOPT_Q_FUZZY) ? q.fuzzy_set : -1;
+    S.sany[tid] = 0;
+  }
+  for (int i = tid; i < nq * kScanWarps; i += kScanThreads) {
+    S.wkey[i / kScanWarps][i % kScanWarps] = kKeyNone;
+    S.wrow[i / kScanWarps][i % kScanWarps] = kRowNone;
   }
   __syncthreads();
   for (int i = tid; i < nq * 2 * kSetStride; i += kScanThreads) {
     const int q = i / (2 * kSetStride);
     const int r = i % (2 * kSetStride);
     const int which = r / kSetStride, w = r % kSetStride;
-    const int set = sset_idx[q][which];
-    sset[q][which][w] = (set >= 0 && w < SKYOPT_ACC_SET_WORDS)
-        ? __ldg(&acc_sets[(int64_t)set * SKYOPT_ACC_SET_WORDS + w]) : 0u;
+    const int set = S.sset_idx[q][which];
+    S.sset[q][which][w] = (set >= 0 && w < SKYOPT_ACC_SET_WORDS)
+        ? __ldg(&a.acc_sets[(int64_t)set * SKYOPT_ACC_SET_WORDS + w]) : 0u;
   }
-  for (int i = tid; i < nq * kWarps; i += kScanThreads) {
-    wkey[i / kWarps][i % kWarps] = kKeyNone;
-    wrow[i / kWarps][i % kWarps] = kRowNone;
+  __syncthreads();
+  if (tid < nq) {
+    // 64-bit signature (key id mod 64) of the keys an accelerator query can
+    // match (exact | fuzzy): the warp-level early out tests against it.
+    uint32_t lo32 = 0, hi32 = 0;
+    if (S.sq[tid].qflags & SKYOPT_Q_ACC) {
+      for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
+        const uint32_t bits = S.sset[tid][0][w] | S.sset[tid][1][w];
+        if (w & 1) hi32 |= bits; else lo32 |= bits;
+      }
+    } else {
+      lo32 = hi32 = 0xFFFFFFFFu;
+    }
+    S.ssig[tid][0] = lo32; S.ssig[tid][1] = hi32;
+    S.sreq[tid] = S.sq[tid].req_flags;
   }
+  __syncthreads();
+}
+
+// Score this thread's RPT rows (already in registers) against every staged
+// query; per-warp running minima accumulate in S.wkey / S.wrow.
+template <int RPT>
+__device__ __forceinline__ void score_rows(
+    const ScanArgs &a, const ScanGroup &G, ScanShared &S, int64_t base,
+    const double (&od)[RPT], const double (&sp)[RPT], const double (&vc)[RPT],
+    const double (&mm)[RPT], const uint32_t (&ak)[RPT], const uint32_t (&rg)[RPT],
+    const uint32_t (&zn)[RPT], const uint32_t (&fl)[RPT]) {
+  const CatDev &cat = a.cat;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nq = G.q_count;
   // Per-row integer key and accelerator-bit address, computed once.
   uint32_t klo[RPT], khi[RPT], aw[RPT], ab[RPT];
   // Warp-level summaries: which flag bits / accelerator keys (id mod 64)
@@ -246,32 +273,27 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
   fl_or = __reduce_or_sync(0xFFFFFFFFu, fl_or & 0xFFu);
   sg_lo = __reduce_or_sync(0xFFFFFFFFu, sg_lo);
   sg_hi = __reduce_or_sync(0xFFFFFFFFu, sg_hi);
-  __syncthreads();
-  if (tid < nq) {
-    // signature of the keys an accelerator query can match (exact | fuzzy)
-    uint32_t lo32 = 0, hi32 = 0;
-    if (sq[tid].qflags & SKYOPT_Q_ACC) {
-      for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
-        const uint32_t bits = sset[tid][0][w] | sset[tid][1][w];
-        if (w & 1) hi32 |= bits; else lo32 |= bits;
-      }
-    } else {
-      lo32 = hi32 = 0xFFFFFFFFu;
-    }
-    ssig[tid][0] = lo32; ssig[tid][1] = hi32;
-  }
-  __syncthreads();
 
-  for (int q = 0; q < nq; ++q) {
-    const QueryS &Q = sq[q];
-    const uint32_t qf = Q.qflags;
-    {
-      // warp-uniform early out
-      const uint32_t rq = Q.req_flags;
-      const bool acc_possible = !(qf & SKYOPT_Q_ACC) ||
-                                (((ssig[q][0] & sg_lo) | (ssig[q][1] & sg_hi)) != 0u);
-      if ((fl_or & rq) != rq || !acc_possible) continue;
+  // Warp-level early out, evaluated for all (<= 32) queries at once: lane q
+  // tests query q's requirements against the warp summaries; the ballot is
+  // the set of queries that can match anything in these rows.
+  uint32_t active;
+  {
+    bool pass = false;
+    if (lane < nq) {
+      const uint32_t rq = S.sreq[lane];
+      const bool is_acc = S.sq[lane].qflags & SKYOPT_Q_ACC;
+      pass = ((fl_or & rq) == rq) &&
+             (!is_acc ||
+              (((S.ssig[lane][0] & sg_lo) | (S.ssig[lane][1] & sg_hi)) != 0u));
     }
+    active = __ballot_sync(0xFFFFFFFFu, pass);
+  }
+  while (active) {
+    const int q = __ffs(active) - 1;
+    active &= active - 1;
+    const QueryS &Q = S.sq[q];
+    const uint32_t qf = Q.qflags;
     uint32_t m1 = 0, mf = 0;
     {
       const uint32_t mlo = Q.mask_lo, mhi = Q.mask_hi, vlo = Q.val_lo, vhi = Q.val_hi;
@@ -284,10 +306,10 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
     if (qf & SKYOPT_Q_ACC) {
       uint32_t me = 0;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) me |= ((sset[q][0][aw[j]] >> ab[j]) & 1u) << j;
+      for (int j = 0; j < RPT; ++j) me |= ((S.sset[q][0][aw[j]] >> ab[j]) & 1u) << j;
       if (qf & SKYOPT_Q_FUZZY) {
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) mf |= ((sset[q][1][aw[j]] >> ab[j]) & 1u) << j;
+        for (int j = 0; j < RPT; ++j) mf |= ((S.sset[q][1][aw[j]] >> ab[j]) & 1u) << j;
         mf &= m1;
       }
       m1 &= me;
@@ -309,7 +331,7 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
     uint64_t bkey = kKeyNone;
     uint32_t brow = kRowNone;
     if (m1) {
-      sany[q] = 1u;  // benign race: every writer stores 1
+      S.sany[q] = 1u;  // benign race: every writer stores 1
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         if (!((m1 >> j) & 1u)) continue;
@@ -333,7 +355,7 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
           const int inst = __ldg(cat.inst_id + base + j);
           if (inst >= 0) {
             const int local = inst - __ldg(&cat.cloud_inst_offsets[Q.cloud]);
-            atomicMin(&list_min[list_base[sqid[q]] + local],
+            atomicMin(&a.list_min[a.list_base[S.sqid[q]] + local],
                       (unsigned long long)key);
           }
         }
@@ -346,12 +368,13 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
         if (!((mf >> j) & 1u)) continue;
         const double p = (G.need & 1u) ? od[j] : __ldg(cat.price + base + j);
         const uint64_t key = (p == p) ? price_key(p) : kKeyNaN;
-        atomicMin(&fuzzy_min[fuzzy_base[sqid[q]] + ak[j]],
+        atomicMin(&a.fuzzy_min[a.fuzzy_base[S.sqid[q]] + ak[j]],
                   (unsigned long long)key);
       }
     }
     // Warp argmin of (price key, row) with three REDUX steps; skipped when no
-    // lane has a candidate (the common case for selective queries).
+    // lane has a candidate (the common case for selective queries). Lane 0
+    // folds the result into the warp's running minimum.
     if (__any_sync(0xFFFFFFFFu, brow != kRowNone)) {
       const uint32_t khi32 = (uint32_t)(bkey >> 32);
       const uint32_t mhi32 = __reduce_min_sync(0xFFFFFFFFu, khi32);
@@ -360,25 +383,177 @@ scan_kernel(CatDev cat, const SkyoptQuery *__restrict__ queries,
       const uint32_t kr = (khi32 == mhi32 && klo32 == mlo32) ? brow : kRowNone;
       const uint32_t mr = __reduce_min_sync(0xFFFFFFFFu, kr);
       if (lane == 0) {
-        wkey[q][warp] = ((uint64_t)mhi32 << 32) | mlo32;
-        wrow[q][warp] = mr;
+        const uint64_t k = ((uint64_t)mhi32 << 32) | mlo32;
+        const uint64_t ok_ = S.wkey[q][warp];
+        if (k < ok_ || (k == ok_ && mr < S.wrow[q][warp])) {
+          S.wkey[q][warp] = k;
+          S.wrow[q][warp] = mr;
+        }
       }
     }
   }
+}
+
+// Block reduction of the per-warp minima -> one partial per (query, block).
+__device__ __forceinline__ void finish_block(const ScanArgs &a, const ScanGroup &G,
+                                             ScanShared &S, int block_in_group) {
   __syncthreads();
-  if (tid < nq) {
+  const int tid = threadIdx.x;
+  if (tid < G.q_count) {
     uint64_t k = kKeyNone;
     uint32_t r = kRowNone;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const uint64_t kw = wkey[tid][w];
-      const uint32_t rw = wrow[tid][w];
+    for (int w = 0; w < kScanWarps; ++w) {
+      const uint64_t kw = S.wkey[tid][w];
+      const uint32_t rw = S.wrow[tid][w];
       if (kw < k || (kw == k && rw < r)) { k = kw; r = rw; }
     }
     ScanPartial out;
-    out.key = k; out.row = r; out.pad_ = sany[tid];
-    partials[(int64_t)partial_base[sqid[tid]] + tile] = out;
+    out.key = k; out.row = r; out.pad_ = S.sany[tid];
+    a.partials[(int64_t)a.partial_base[S.sqid[tid]] + block_in_group] = out;
   }
+}
+
+// K1, small catalogs: one tile of 256*RPT rows per block, rows go straight
+// from global memory to registers.
+template <int RPT>
+__global__ void __launch_bounds__(kScanThreads, 3) scan_kernel(ScanArgs a) {
+  __shared__ ScanShared S;
+  const ScanGroup G = find_group(a, blockIdx.x);
+  const int tile = blockIdx.x - G.block0;
+  const int tid = threadIdx.x;
+  // Stream this thread's rows into registers first (32 B per row); the
+  // constraint vectors are staged while the loads are in flight.
+  const int64_t base =
+      (int64_t)G.row_begin + (int64_t)tile * (kScanThreads * RPT) + tid * RPT;
+  double od[RPT], sp[RPT], vc[RPT], mm[RPT];
+  uint32_t ak[RPT], rg[RPT], zn[RPT], fl[RPT];
+  if (G.need & 1u) load_f64<RPT>(a.cat.price, base, od);
+  if (G.need & 2u) load_f64<RPT>(a.cat.spot, base, sp);
+  load_f64<RPT>(a.cat.vcpus, base, vc);
+  load_f64<RPT>(a.cat.mem, base, mm);
+  load_u16<RPT>(a.cat.acc_key, base, ak);
+  load_u16<RPT>(a.cat.region_id, base, rg);
+  load_u16<RPT>(a.cat.zone_id, base, zn);
+  load_u16<RPT>(a.cat.flags, base, fl);
+  stage_queries(a, G, S);
+  score_rows<RPT>(a, G, S, base, od, sp, vc, mm, ak, rg, zn, fl);
+  finish_block(a, G, S, tile);
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier plumbing for the streaming kernel ------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kStreamRPT = 4;
+constexpr int kStreamTile = kScanThreads * kStreamRPT;   // 1024 rows
+constexpr int kStreamStages = 2;
+// one stage: price, spot, vcpus, mem (f64) + acc_key, region, zone, flags (u16)
+constexpr int kStageBytes = kStreamTile * (4 * 8 + 4 * 2);
+
+struct StreamStage {
+  double od[kStreamTile], sp[kStreamTile], vc[kStreamTile], mm[kStreamTile];
+  uint16_t ak[kStreamTile], rg[kStreamTile], zn[kStreamTile], fl[kStreamTile];
+};
+static_assert(sizeof(StreamStage) == kStageBytes, "stage layout");
+
+// K1, large catalogs: each block owns `tiles_per_block` consecutive tiles of
+// one (cloud, query chunk) group. Thread 0 keeps two tiles in flight with
+// cp.async.bulk (TMA) into shared memory, completion is signalled through
+// mbarriers; all threads copy their rows out to registers, hand the stage
+// back and score the rows while the next tiles stream in. The constraint
+// vectors are staged once per block.
+__global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(ScanArgs a) {
+  extern __shared__ __align__(128) unsigned char stream_smem[];
+  StreamStage *stages = reinterpret_cast<StreamStage *>(stream_smem);
+  __shared__ ScanShared S;
+  __shared__ __align__(8) uint64_t full[kStreamStages];
+  const ScanGroup G = find_group(a, blockIdx.x);
+  const int blk = blockIdx.x - G.block0;
+  const int tid = threadIdx.x;
+  const int t0 = blk * G.tiles_per_block;
+  const int ntiles = min(G.tiles_per_block, G.total_tiles - t0);
+  const CatDev &cat = a.cat;
+
+  auto issue = [&](int i) {
+    // tile t0 + i -> stage i % kStreamStages (thread 0 only)
+    StreamStage &st = stages[i % kStreamStages];
+    uint64_t *bar = &full[i % kStreamStages];
+    const int64_t row = (int64_t)G.row_begin + (int64_t)(t0 + i) * kStreamTile;
+    uint32_t bytes = kStreamTile * (2 * 8 + 4 * 2);
+    if (G.need & 1u) bytes += kStreamTile * 8;
+    if (G.need & 2u) bytes += kStreamTile * 8;
+    mbar_expect_tx(bar, bytes);
+    if (G.need & 1u) bulk_g2s(st.od, cat.price + row, kStreamTile * 8, bar);
+    if (G.need & 2u) bulk_g2s(st.sp, cat.spot + row, kStreamTile * 8, bar);
+    bulk_g2s(st.vc, cat.vcpus + row, kStreamTile * 8, bar);
+    bulk_g2s(st.mm, cat.mem + row, kStreamTile * 8, bar);
+    bulk_g2s(st.ak, cat.acc_key + row, kStreamTile * 2, bar);
+    bulk_g2s(st.rg, cat.region_id + row, kStreamTile * 2, bar);
+    bulk_g2s(st.zn, cat.zone_id + row, kStreamTile * 2, bar);
+    bulk_g2s(st.fl, cat.flags + row, kStreamTile * 2, bar);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < kStreamStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 0; i < min(kStreamStages, ntiles); ++i) issue(i);
+  stage_queries(a, G, S);
+
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % kStreamStages;
+    mbar_wait(&full[s], (uint32_t)((i / kStreamStages) & 1));
+    const StreamStage &st = stages[s];
+    double od[kStreamRPT], sp[kStreamRPT], vc[kStreamRPT], mm[kStreamRPT];
+    uint32_t ak[kStreamRPT], rg[kStreamRPT], zn[kStreamRPT], fl[kStreamRPT];
+    const int r0 = tid * kStreamRPT;
+    auto ld4 = [&](const double *col, double (&out)[kStreamRPT]) {
+      const double2 x = *reinterpret_cast<const double2 *>(col + r0);
+      const double2 y = *reinterpret_cast<const double2 *>(col + r0 + 2);
+      out[0] = x.x; out[1] = x.y; out[2] = y.x; out[3] = y.y;
+    };
+    auto ld4u = [&](const uint16_t *col, uint32_t (&out)[kStreamRPT]) {
+      const uint2 x = *reinterpret_cast<const uint2 *>(col + r0);
+      out[0] = x.x & 0xFFFF; out[1] = x.x >> 16; out[2] = x.y & 0xFFFF; out[3] = x.y >> 16;
+    };
+    if (G.need & 1u) ld4(st.od, od);
+    if (G.need & 2u) ld4(st.sp, sp);
+    ld4(st.vc, vc); ld4(st.mm, mm);
+    ld4u(st.ak, ak); ld4u(st.rg, rg); ld4u(st.zn, zn); ld4u(st.fl, fl);
+    __syncthreads();  // every thread has its rows: the stage can be refilled
+    if (tid == 0 && i + kStreamStages < ntiles) issue(i + kStreamStages);
+    const int64_t base = (int64_t)G.row_begin + (int64_t)(t0 + i) * kStreamTile + r0;
+    score_rows<kStreamRPT>(a, G, S, base, od, sp, vc, mm, ak, rg, zn, fl);
+  }
+  finish_block(a, G, S, blk);
 }
 
 // One warp per query: reduce the per-tile partials.

@@ -92,6 +92,10 @@ def accelerator_sets(store: CatalogStore, acc_name: str,
     The string predicates run once per distinct (name, count) pair of the
     catalog dictionary; rows carry only the pair's id.
     """
+    cache = store.__dict__.setdefault('_acc_set_cache', {})
+    hit = cache.get((acc_name, float(acc_count)))
+    if hit is not None:
+        return hit
     pattern = re.compile(acc_name, flags=re.IGNORECASE)
     count = float(acc_count)
     exact = store.accelerator_set(lambda n, c: pattern.fullmatch(n) is not None
@@ -100,6 +104,9 @@ def accelerator_sets(store: CatalogStore, acc_name: str,
         lambda n, c: pattern.search(n) is not None and c >= count)
     strict = store.accelerator_set(lambda n, c: pattern.fullmatch(n) is not None
                                    and c == count)
+    # The dictionary is immutable once the store is built, so the three
+    # bitmasks are a pure function of (name, count).
+    cache[(acc_name, float(acc_count))] = (exact, fuzzy, strict)
     return exact, fuzzy, strict
 
 

@@ -60,3 +60,25 @@ def test_scenario_matches_reference(catalog, scenario):
             f.write(json.dumps({'catalog': catalog, 'name': scenario['name'],
                                 'diffs': diffs, 'got': got}) + '\n')
     assert not diffs, '\n'.join(diffs)
+
+
+@pytest.mark.parametrize('mode', ['tile', 'stream', 'stream3'])
+@pytest.mark.parametrize('catalog', ['multi50k', 'aws50k'])
+def test_scan_kernel_variants_agree_with_reference(catalog, mode):
+    """Both scan kernels (one tile per block / TMA streaming with one and
+    with three tiles per block) must give the reference's answers."""
+    spec, records = _golden(catalog)
+    store = runner.activate_catalog(spec)
+    store.set_scan_mode(mode)
+    try:
+        failures = []
+        for sc in scenarios.SUITES[catalog]():
+            got = runner.run_scenario(sc)
+            unordered = any(
+                t.get('resources_kind') == 'set' for t in sc['tasks'])
+            diffs = runner.compare(records[sc['name']], got, unordered)
+            if diffs:
+                failures.append((sc['name'], diffs[:3]))
+        assert not failures, failures
+    finally:
+        store.set_scan_mode('auto')
