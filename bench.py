@@ -192,6 +192,8 @@ def main():
     parser.add_argument('--impl', default='ours',
                         choices=['ours', 'reference'])
     parser.add_argument('--cpu-baseline-steps', type=int, default=5)
+    parser.add_argument('--no-stress', action='store_true',
+                        help='skip the extra cfg4 (1M rows x 32 tasks) run')
     parser.add_argument('--scan-mode', default='auto',
                         choices=['auto', 'tile', 'stream', 'stream3'],
                         help='scan kernel variant (tuning / tests)')
@@ -242,111 +244,126 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    frames = synth.make_catalogs(**workload['catalog'])
-    n_rows = synth.total_rows(frames)
-    store = sky.catalog.load_frames(frames, device=local_rank)
-    store.handle(local_rank)
-    if args.scan_mode != 'auto':
-        store.set_scan_mode(args.scan_mode, local_rank)
-    n_tasks = workload['tasks']
-    n_candidates = n_rows * n_tasks
+    def measure(workload_name):
+        workload = WORKLOADS[workload_name]
+        scenario = chain_scenario(workload['tasks'])
+        frames = synth.make_catalogs(**workload['catalog'])
+        n_rows = synth.total_rows(frames)
+        store = sky.catalog.load_frames(frames, device=local_rank)
+        store.handle(local_rank)
+        if args.scan_mode != 'auto':
+            store.set_scan_mode(args.scan_mode, local_rank)
+        n_tasks = workload['tasks']
+        n_candidates = n_rows * n_tasks
 
-    dag, tasks = runner.build_dag(scenario)
-    Optimizer = opt_lib.Optimizer
+        dag, tasks = runner.build_dag(scenario)
+        Optimizer = opt_lib.Optimizer
 
-    # ---- device-resident arm: the problem is uploaded once, kernels re-run
-    Optimizer._add_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
-    try:
-        graph = dag.get_graph()
-        topo = [t for t in nx.topological_sort(graph)
-                if not opt_lib._is_dummy(t)]  # pylint: disable=protected-access
-        problem = Optimizer._state_problem(graph, topo, True, [], True)  # pylint: disable=protected-access
-    finally:
-        Optimizer._remove_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
-    engine.solve_timed(problem.builder, args.warmup, True, local_rank)
-    barrier()
-    with ClockSampler(local_rank) as clocks:
-        t0 = time.perf_counter()
-        sol, iter_ms, scan_ms = engine.solve_timed(problem.builder, args.steps,
-                                                   True, local_rank)
-        wall_resident = time.perf_counter() - t0
-        device_ms = float(np.sum(iter_ms))
-        device_ms = max_over_ranks(device_ms)
+        # ---- device-resident arm: the problem is uploaded once, kernels re-run
+        Optimizer._add_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+        try:
+            graph = dag.get_graph()
+            topo = [t for t in nx.topological_sort(graph)
+                    if not opt_lib._is_dummy(t)]  # pylint: disable=protected-access
+            problem = Optimizer._state_problem(graph, topo, True, [], True)  # pylint: disable=protected-access
+        finally:
+            Optimizer._remove_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+        engine.solve_timed(problem.builder, args.warmup, True, local_rank)
         barrier()
+        with ClockSampler(local_rank) as clocks:
+            t0 = time.perf_counter()
+            sol, iter_ms, scan_ms = engine.solve_timed(problem.builder, args.steps,
+                                                       True, local_rank)
+            wall_resident = time.perf_counter() - t0
+            device_ms = float(np.sum(iter_ms))
+            device_ms = max_over_ranks(device_ms)
+            barrier()
 
-        # ---- end to end through the public API, host buffers in and out
-        for _ in range(args.warmup):
-            Optimizer.optimize(dag, quiet=True)
-        barrier()
-        e2e_times = []
-        t_e2e0 = time.perf_counter()
-        for _ in range(args.steps):
-            t1 = time.perf_counter()
-            Optimizer.optimize(dag, quiet=True)
-            e2e_times.append(time.perf_counter() - t1)
-        e2e_total = time.perf_counter() - t_e2e0
-        e2e_total = max_over_ranks(e2e_total)
-        barrier()
-    assert sol.dag[0]['status'] == 0
-    plan = [runner.res_record(t.best_resources) for t in tasks]
+            # ---- end to end through the public API, host buffers in and out
+            for _ in range(args.warmup):
+                Optimizer.optimize(dag, quiet=True)
+            barrier()
+            e2e_times = []
+            t_e2e0 = time.perf_counter()
+            for _ in range(args.steps):
+                t1 = time.perf_counter()
+                Optimizer.optimize(dag, quiet=True)
+                e2e_times.append(time.perf_counter() - t1)
+            e2e_total = time.perf_counter() - t_e2e0
+            e2e_total = max_over_ranks(e2e_total)
+            barrier()
+        assert sol.dag[0]['status'] == 0
+        plan = [runner.res_record(t.best_resources) for t in tasks]
 
-    ms_per_step = device_ms / args.steps
-    value = world * n_candidates / (ms_per_step / 1e3)
-    e2e_value = world * n_candidates * args.steps / e2e_total
-    packed = problem.builder.pack()
-    stats = sol.stats
-    scan_kernel_ms = float(np.mean(scan_ms))
-    row_bytes = store.row_bytes()
-    scan_bytes = int(stats.scan_passes_rows) * row_bytes
-    peak, peak_src = measured_peaks()
-    achieved = scan_bytes / (scan_kernel_ms / 1e3) / 1e9 if scan_kernel_ms else 0
+        ms_per_step = device_ms / args.steps
+        value = world * n_candidates / (ms_per_step / 1e3)
+        e2e_value = world * n_candidates * args.steps / e2e_total
+        packed = problem.builder.pack()
+        stats = sol.stats
+        scan_kernel_ms = float(np.mean(scan_ms))
+        row_bytes = store.row_bytes()
+        scan_bytes = int(stats.scan_passes_rows) * row_bytes
+        peak, peak_src = measured_peaks()
+        achieved = scan_bytes / (scan_kernel_ms / 1e3) / 1e9 if scan_kernel_ms else 0
 
-    line = {
-        'metric': 'candidate (task,instance) placements scored/sec',
-        'value': value, 'unit': 'candidates/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic',
-        'config': {
-            'workload': f'{args.workload}: {workload["desc"]}',
-            'catalog': workload['catalog'], 'catalog_rows': n_rows,
-            'tasks': n_tasks, 'candidates_per_step': n_candidates,
-            'l2': 'flushed before every step (192 MB write)',
-            'parallelism': ('one DAG stream per GPU, catalog replicated, '
-                            'no collective'),
-        },
-        'optimize_p50_ms': 1e3 * statistics.median(e2e_times),
-        'optimize_p90_ms': 1e3 * sorted(e2e_times)[int(0.9 *
-                                                       len(e2e_times))],
-        'e2e': {
-            'value': e2e_value, 'unit': 'candidates/s',
-            'h2d_bytes_per_step': packed.h2d_bytes(),
-            'd2h_bytes_per_step': sol.d2h_bytes(),
-            'ms_per_step': 1e3 * e2e_total / args.steps,
-        },
-        'gpu_launches': int(stats.total_launches) * args.steps,
-        'phases_ms': {
-            'scan_kernel': scan_kernel_ms,
-            'scan_total': float(stats.scan_ms),
-            'expand': float(stats.expand_ms),
-            'solve': float(stats.solve_ms),
-        },
-        'roofline': {
-            'kernel': 'scan_kernel', 'bound': 'hbm', 'achieved': achieved,
-            'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
-            'frac': achieved / peak if peak else None,
-            'algorithmic_bytes_per_launch': scan_bytes,
-            'bytes_per_row': row_bytes,
-            'rows_streamed_per_launch': int(stats.scan_passes_rows),
-            'queries_fused_per_pass': 32,
-            'traffic': None,
-        },
-        'clocks': clocks.summary(),
-        'wall_check_ms_per_step': 1e3 * wall_resident / args.steps,
-        'plan': [p['instance_type'] for p in plan],
-    }
+        line = {
+            'metric': 'candidate (task,instance) placements scored/sec',
+            'value': value, 'unit': 'candidates/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {
+                'workload': f'{args.workload}: {workload["desc"]}',
+                'catalog': workload['catalog'], 'catalog_rows': n_rows,
+                'tasks': n_tasks, 'candidates_per_step': n_candidates,
+                'l2': 'flushed before every step (192 MB write)',
+                'parallelism': ('one DAG stream per GPU, catalog replicated, '
+                                'no collective'),
+            },
+            'optimize_p50_ms': 1e3 * statistics.median(e2e_times),
+            'optimize_p90_ms': 1e3 * sorted(e2e_times)[int(0.9 *
+                                                           len(e2e_times))],
+            'e2e': {
+                'value': e2e_value, 'unit': 'candidates/s',
+                'h2d_bytes_per_step': packed.h2d_bytes(),
+                'd2h_bytes_per_step': sol.d2h_bytes(),
+                'ms_per_step': 1e3 * e2e_total / args.steps,
+            },
+            'gpu_launches': int(stats.total_launches) * args.steps,
+            'phases_ms': {
+                'scan_kernel': scan_kernel_ms,
+                'scan_total': float(stats.scan_ms),
+                'expand': float(stats.expand_ms),
+                'solve': float(stats.solve_ms),
+            },
+            'roofline': {
+                'kernel': 'scan_kernel', 'bound': 'hbm', 'achieved': achieved,
+                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
+                'frac': achieved / peak if peak else None,
+                'algorithmic_bytes_per_launch': scan_bytes,
+                'bytes_per_row': row_bytes,
+                'rows_streamed_per_launch': int(stats.scan_passes_rows),
+                'queries_fused_per_pass': 32,
+                'traffic': None,
+            },
+            'clocks': clocks.summary(),
+            'wall_check_ms_per_step': 1e3 * wall_resident / args.steps,
+            'plan': [p['instance_type'] for p in plan],
+        }
 
+        return line, scenario, n_candidates
+
+    line, scenario, n_candidates = measure(args.workload)
+    workload = WORKLOADS[args.workload]
+    if args.workload != 'cfg4' and not args.no_stress:
+        # HBM-stress configuration next to the latency configuration
+        stress, _, _ = measure('cfg4')
+        line['hbm_stress'] = {
+            k: stress[k] for k in ('value', 'unit', 'ms_per_step', 'e2e',
+                                   'roofline', 'phases_ms', 'config',
+                                   'optimize_p50_ms')
+        }
     if rank == 0 and world == 1:
         # ---- CPU baseline: the pandas oracle on a bounded sample
         ref_args = argparse.Namespace(**vars(args))

@@ -144,7 +144,7 @@ int ensure(Ctx *x, size_t dbytes, size_t hbytes) {
 struct Plan {
   // sizes
   int nq = 0, nsets = 0, ns = 0, nt = 0, np = 0, ntar = 0, nb = 0, nd = 0;
-  int n_groups = 0, n_blocks = 0, rpt = 4, tpb = 1; bool stream = false;
+  int n_groups = 0, n_blocks = 0, rpt = 4, tpb = 1; bool stream = false; bool want_finalize = true;
   int64_t n_partials = 0, list_entries = 0, fuzzy_entries = 0;
   int64_t cand_cap = 0;   // expand candidate buffers
   int64_t scan_rows = 0, pass_rows = 0;
@@ -152,10 +152,10 @@ struct Plan {
   size_t in_bytes = 0;
   SkyoptQuery *queries; uint32_t *acc_sets; SkyoptSlot *slots; SkyoptTask *tasks;
   int32_t *parents; double *tariffs; SkyoptBlocked *blocked; SkyoptDag *dags;
-  int32_t *q_order; ScanGroup *groups; int32_t *partial_base, *partial_count;
+  ScanQuery *squeries; ScanGroup *groups; const ScanGroup *host_groups = nullptr; int32_t *partial_base, *partial_count;
   int64_t *list_base, *fuzzy_base, *slot_off, *task_off; int32_t *task_dag;
   // device-only scratch
-  ScanPartial *partials; unsigned long long *list_min, *fuzzy_min;
+  ScanPartial *partials; unsigned long long *list_min, *fuzzy_min, *gbest;
   int32_t *cand_region, *cand_zone; double *cand_pa, *cand_pb;
   int32_t *tc_ref, *tc_slot, *tc_cloud; double *tc_hourly, *tc_value, *dp;
   int32_t *back; int32_t *err_flag;
@@ -176,7 +176,7 @@ void carve_inputs(Plan &P, Carver &c) {
   P.tariffs = c.take<double>(P.ntar);
   P.blocked = c.take<SkyoptBlocked>(P.nb);
   P.dags = c.take<SkyoptDag>(P.nd);
-  P.q_order = c.take<int32_t>(P.nq);
+  P.squeries = c.take<ScanQuery>(P.nq);
   P.groups = c.take<ScanGroup>(P.n_groups);
   P.partial_base = c.take<int32_t>(P.nq);
   P.partial_count = c.take<int32_t>(P.nq);
@@ -191,6 +191,7 @@ void carve_rest(Plan &P, Carver &c) {
   P.partials = c.take<ScanPartial>(P.n_partials);
   P.list_min = c.take<unsigned long long>(P.list_entries);
   P.fuzzy_min = c.take<unsigned long long>(P.fuzzy_entries);
+  P.gbest = c.take<unsigned long long>(P.nq);
   P.cand_region = c.take<int32_t>(P.cand_cap);
   P.cand_zone = c.take<int32_t>(P.cand_cap);
   P.cand_pa = c.take<double>(P.cand_cap);
@@ -306,6 +307,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     P.stream = true;
     P.tpb = (int)std::max<long long>(1, (tiles4 + wave - 1) / wave);
     if (cat->scan_mode == 3) P.tpb = 3;  // tests: force the multi-tile loop
+    if (const char *t = getenv("SKYOPT_TPB")) P.tpb = std::max(1, atoi(t));
   } else {
     if (tiles4 < wave) P.rpt = 2;
     if (P.rpt == 2 && count_tiles(2) < wave) P.rpt = 1;
@@ -395,10 +397,32 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
       G.q_begin = qpos; G.q_count = n; G.block0 = block0; G.n_tiles = tiles;
       G.tiles_per_block = P.tpb; G.total_tiles = total_tiles;
       for (int k = 0; k < n; ++k) {
-        const SkyoptQuery &q = pb->queries[qs[b + k]];
-        P.q_order[qpos + k] = qs[b + k];
+        const int qi = qs[b + k];
+        const SkyoptQuery &q = pb->queries[qi];
         G.need |= q.price_col ? 2u : 1u;
         if (q.qflags & SKYOPT_Q_FUZZY) G.need |= 1u;
+        // the staged record: constraint vector, offsets and key bitmasks
+        ScanQuery &R = P.squeries[qpos + k];
+        memset(&R, 0, sizeof(R));
+        R.s = make_query_s(q);
+        R.qid = qi;
+        R.partial_base = pbase[qi];
+        R.list_base = lbase[qi];
+        R.fuzzy_base = fbase[qi];
+        uint32_t lo32 = 0, hi32 = 0;
+        const int set_idx[2] = {(q.qflags & SKYOPT_Q_ACC) ? q.acc_set : -1,
+                                (q.qflags & SKYOPT_Q_FUZZY) ? q.fuzzy_set : -1};
+        for (int which = 0; which < 2; ++which) {
+          if (set_idx[which] < 0) continue;
+          const uint32_t *src = pb->acc_sets + (size_t)set_idx[which] * SKYOPT_ACC_SET_WORDS;
+          for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
+            R.set[which][w] = src[w];
+            if (w & 1) hi32 |= src[w]; else lo32 |= src[w];
+          }
+        }
+        // 64-bit signature (key id mod 64) of the keys the query can match
+        R.s.sig_lo = (q.qflags & SKYOPT_Q_ACC) ? lo32 : 0xFFFFFFFFu;
+        R.s.sig_hi = (q.qflags & SKYOPT_Q_ACC) ? hi32 : 0xFFFFFFFFu;
       }
       P.groups[g++] = G;
       qpos += n; block0 += tiles;
@@ -407,26 +431,42 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   }
   P.n_blocks = block0;
 
+  const ScanGroup *host_groups = P.groups;
   // device views
   Carver d(x->dbuf);
   carve_inputs(P, d);
   carve_rest(P, d);
+  P.host_groups = host_groups;  // pinned staging copy stays valid for the call
   return 0;
 }
 
 struct Timeline { float scan_ms = 0, expand_ms = 0, solve_ms = 0; };
 
 // Enqueue K1..K3 on the context's stream. Events ev[1..4] bracket the phases.
-int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
+int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
+                    bool want_scan_results = true) {
   cudaStream_t st = x->stream;
   CU(cudaEventRecord(x->ev[1], st));
   if (P.nq) {
+    CU(cudaMemsetAsync(P.gbest, 0xFF, sizeof(unsigned long long) * P.nq, st));
     if (P.list_entries) CU(cudaMemsetAsync(P.list_min, 0xFF, sizeof(unsigned long long) * P.list_entries, st));
     if (P.fuzzy_entries) CU(cudaMemsetAsync(P.fuzzy_min, 0xFF, sizeof(unsigned long long) * P.fuzzy_entries, st));
     if (P.n_blocks) {
-      ScanArgs sa{cat->dev, P.queries, P.q_order, P.groups, P.n_groups, P.acc_sets,
-                  P.partial_base, P.partials, P.list_base, P.list_min,
-                  P.fuzzy_base, P.fuzzy_min};
+      ScanArgs sa{};
+      sa.cat = cat->dev; sa.squeries = P.squeries; sa.groups = P.groups;
+      sa.n_groups = P.n_groups; sa.partials = P.partials;
+      sa.list_min = P.list_min; sa.fuzzy_min = P.fuzzy_min; sa.gbest = P.gbest;
+      sa.zero_flag = P.err_out;
+      for (int i = 0; i < std::min(P.n_groups, kInlineGroups); ++i) sa.inline_groups[i] = P.host_groups[i];
+      sa.n_blocks = P.n_blocks;
+      sa.debug = 0;
+      if (const char *dbg = getenv("SKYOPT_DEBUG")) sa.debug = (uint32_t)atoi(dbg);
+      sa.perm_mul = 1;
+      for (uint32_t cand : {7919u, 104729u, 1299709u, 15485863u}) {
+        uint64_t x = cand, y = (uint64_t)P.n_blocks;  // gcd
+        while (y) { const uint64_t t = x % y; x = y; y = t; }
+        if (x == 1) { sa.perm_mul = cand; break; }
+      }
       CU(cudaEventRecord(x->ev[6], st));
       if (P.stream)
         scan_stream_kernel<<<P.n_blocks, kScanThreads, kStreamStages * sizeof(StreamStage), st>>>(sa);
@@ -436,20 +476,23 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve) {
       CU(cudaGetLastError());
       CU(cudaEventRecord(x->ev[7], st));
     }
-    const int fblocks = (P.nq * 32 + 255) / 256;
-    finalize_kernel<<<fblocks, 256, 0, st>>>(cat->dev, P.nq, P.partial_base,
-                                             P.partial_count, P.partials, P.finals,
-                                             P.any1, P.err_out);
-    CU(cudaGetLastError());
+    if (want_scan_results || !solve) {
+      const int fblocks = (P.nq * 32 + 255) / 256;
+      finalize_kernel<<<fblocks, 256, 0, st>>>(cat->dev, P.nq, P.partial_base,
+                                               P.partial_count, P.partials, P.finals,
+                                               P.any1, P.err_out);
+      CU(cudaGetLastError());
+    }
   }
   CU(cudaEventRecord(x->ev[2], st));
   if (!solve) return 0;
-  if (!P.nq) CU(cudaMemsetAsync(P.err_out, 0, sizeof(int32_t), st));
+  if (!P.n_blocks) CU(cudaMemsetAsync(P.err_out, 0, sizeof(int32_t), st));
   ExpandOut ex{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
   if (P.ns) {
     const size_t smem = (size_t)cat->sort_n * 16 + (size_t)cat->max_zones * 8 +
                         (size_t)cat->max_regions * 4;
-    expand_kernel<<<P.ns, 128, smem, st>>>(cat->dev, P.slots, P.finals, P.any1,
+    expand_kernel<<<P.ns, 128, smem, st>>>(cat->dev, P.slots, P.partial_base,
+                                           P.partial_count, P.partials,
                                            P.acc_sets, P.slot_off, cat->sort_n,
                                            cat->max_regions, cat->max_zones, ex,
                                            P.err_out);
@@ -561,7 +604,7 @@ int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
   }
   CU(cudaEventElapsedTime(&stats->total_ms, x->ev[0], x->ev[5]));
   stats->scan_launches = P.n_blocks ? 1 : 0;
-  stats->total_launches = (P.n_blocks ? 1 : 0) + (P.nq ? 1 : 0) +
+  stats->total_launches = (P.n_blocks ? 1 : 0) + ((P.nq && (P.want_finalize || !solve)) ? 1 : 0) +
                           (solve ? ((P.ns ? 1 : 0) + (P.nd ? 2 : 0)) : 0);
   stats->scan_rows = P.scan_rows;
   stats->scan_passes_rows = P.pass_rows;
@@ -820,7 +863,8 @@ int skyopt_optimize(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution 
     cudaStream_t st = x->stream;
     CU(cudaEventRecord(x->ev[0], st));
     CU(cudaMemcpyAsync(x->dbuf, x->hbuf, P.in_bytes, cudaMemcpyHostToDevice, st));
-    if ((r = enqueue_kernels(cat, x, P, true))) return r;
+    P.want_finalize = sol->scan != nullptr;
+    if ((r = enqueue_kernels(cat, x, P, true, sol->scan != nullptr))) return r;
     CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(x->ev[5], st));
     CU(cudaStreamSynchronize(st));
@@ -854,12 +898,13 @@ int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSol
     }
     CU(cudaEventRecord(x->ev[0], st));
     CU(cudaMemcpyAsync(x->dbuf, x->hbuf, P.in_bytes, cudaMemcpyHostToDevice, st));
+    P.want_finalize = sol->scan != nullptr;
     for (int it = 0; it < iters; ++it) {
       if (flush_l2) {
         flush_kernel<<<cat->sm_count * 8, 256, 0, st>>>(x->flush, (int64_t)x->flush_words, (uint32_t)it);
         CU(cudaGetLastError());
       }
-      if ((r = enqueue_kernels(cat, x, P, true))) return r;
+      if ((r = enqueue_kernels(cat, x, P, true, sol->scan != nullptr))) return r;
       CU(cudaStreamSynchronize(st));
       CU(cudaEventElapsedTime(&iter_ms[it], x->ev[1], x->ev[4]));
       if (scan_ms && P.n_blocks) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[6], x->ev[7]));

@@ -97,8 +97,8 @@ struct QueryS {
   double cpu_lo, cpu_hi, mem_lo, mem_hi, cap, disk_size;
 };
 
-__device__ __forceinline__ QueryS make_query_s(const SkyoptQuery &q) {
-  const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+__host__ __device__ inline QueryS make_query_s(const SkyoptQuery &q) {
+  const double kInf = 1.0 / 0.0;
   QueryS s;
   uint64_t mask = (uint64_t)((q.flags_require | SKYOPT_F_VALID) & 0xFFu);
   uint64_t val = mask;
@@ -154,37 +154,65 @@ __device__ __forceinline__ void load_u16(const uint16_t *__restrict__ col,
 constexpr int kSetStride = SKYOPT_ACC_SET_WORDS + 1;  // + a zero word for "no key"
 constexpr int kScanWarps = kScanThreads / 32;
 
-// Shared-memory state of one scan block: the staged constraint vectors of up
-// to kQChunk queries and the per-warp running minima.
+// One query in scan order, exactly as a block stages it: the host lays these
+// records out per (cloud, chunk) group, so staging is ONE coalesced copy with
+// no dependent look-ups (set indices, partial offsets and signatures are
+// resolved on the host).
+struct ScanQuery {
+  QueryS s;
+  int32_t qid;           // index in the caller's query array
+  int32_t partial_base;  // first partial of this query
+  int64_t list_base;     // into list_min (SKYOPT_Q_LIST)
+  int64_t fuzzy_base;    // into fuzzy_min (SKYOPT_Q_FUZZY)
+  uint32_t set[2][kSetStride];  // exact / fuzzy accelerator-key bitmasks
+};
+static_assert(sizeof(ScanQuery) % 8 == 0, "ScanQuery must be 8-byte granular");
+
+// Shared-memory state of one scan block: the staged queries and the per-warp
+// running minima.
 struct ScanShared {
-  QueryS sq[kQChunk];
-  uint32_t sset[kQChunk][2][kSetStride];
-  int32_t sqid[kQChunk];
-  int32_t sset_idx[kQChunk][2];
+  ScanQuery q[kQChunk];
   uint64_t wkey[kQChunk][kScanWarps];
   uint32_t wrow[kQChunk][kScanWarps];
+  uint64_t gb[kQChunk];   // best price key any block has found so far
   uint32_t sany[kQChunk];
-  uint32_t ssig[kQChunk][2];
-  uint32_t sreq[kQChunk];
 };
+
+constexpr int kInlineGroups = 8;
 
 struct ScanArgs {
   CatDev cat;
-  const SkyoptQuery *queries;
-  const int32_t *q_order;
+  const ScanQuery *squeries;   // scan order
   const ScanGroup *groups;
   int n_groups;
-  const uint32_t *acc_sets;
-  const int32_t *partial_base;
   ScanPartial *partials;
-  const int64_t *list_base;
   unsigned long long *list_min;
-  const int64_t *fuzzy_base;
   unsigned long long *fuzzy_min;
+  unsigned long long *gbest;   // [n_queries] in scan order: running best key
+  int32_t *zero_flag;          // cleared by the first block (expand's error flag)
+  int n_blocks;                // grid size
+  uint32_t perm_mul;           // odd, coprime with n_blocks
+  uint32_t debug;              // SKYOPT_DEBUG bits (profiling experiments only)
+  ScanGroup inline_groups[kInlineGroups];  // copy of groups[] when it fits
 };
 
+// Launch order -> work unit. Expensive tiles (rows that many queries match)
+// sit next to each other in the catalog; a multiplicative permutation spreads
+// them over the whole launch instead of leaving them to the last wave.
+__device__ __forceinline__ int permuted_block(const ScanArgs &a) {
+  return (int)(((uint64_t)blockIdx.x * a.perm_mul) % (uint32_t)a.n_blocks);
+}
+
 __device__ __forceinline__ ScanGroup find_group(const ScanArgs &a, int b) {
-  // blockIdx -> group: groups are sorted by block0.
+  // blockIdx -> group: groups are sorted by block0. Small tables travel in
+  // the kernel parameters (constant bank, no memory round trip).
+  if (a.n_groups <= kInlineGroups) {
+    ScanGroup g = a.inline_groups[0];
+#pragma unroll
+    for (int i = 1; i < kInlineGroups; ++i)
+      if (i < a.n_groups && a.inline_groups[i].block0 <= b) g = a.inline_groups[i];
+    return g;
+  }
   int lo = 0, hi = a.n_groups - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -193,50 +221,23 @@ __device__ __forceinline__ ScanGroup find_group(const ScanArgs &a, int b) {
   return a.groups[lo];
 }
 
-// Stage the chunk's constraint vectors, then the accelerator-key bitmasks
-// they reference (set indices come from shared memory, so the global loads
-// of one thread are independent and overlap). Ends with a barrier.
+// Stage the chunk's queries: one coalesced copy. Ends with a barrier.
 __device__ __forceinline__ void stage_queries(const ScanArgs &a, const ScanGroup &G,
                                               ScanShared &S) {
   const int tid = threadIdx.x;
   const int nq = G.q_count;
-  if (tid < nq) {
-    const int qi = __ldg(&a.q_order[G.q_begin + tid]);
-    const SkyoptQuery q = a.queries[qi];
-    S.sqid[tid] = qi;
-    S.sq[tid] = make_query_s(q);
-    S.sset_idx[tid][0] = (q.qflags & SKYOPT_Q_ACC) ? q.acc_set : -1;
-    S.sset_idx[tid][1] = (q.qflags & SKYOPT_Q_FUZZY) ? q.fuzzy_set : -1;
-    S.sany[tid] = 0;
-  }
+  const uint2 *src = reinterpret_cast<const uint2 *>(a.squeries + G.q_begin);
+  uint2 *dst = reinterpret_cast<uint2 *>(S.q);
+  const int n8 = nq * (int)(sizeof(ScanQuery) / 8);
+  for (int i = tid; i < n8; i += kScanThreads) dst[i] = __ldg(src + i);
   for (int i = tid; i < nq * kScanWarps; i += kScanThreads) {
     S.wkey[i / kScanWarps][i % kScanWarps] = kKeyNone;
     S.wrow[i / kScanWarps][i % kScanWarps] = kRowNone;
   }
-  __syncthreads();
-  for (int i = tid; i < nq * 2 * kSetStride; i += kScanThreads) {
-    const int q = i / (2 * kSetStride);
-    const int r = i % (2 * kSetStride);
-    const int which = r / kSetStride, w = r % kSetStride;
-    const int set = S.sset_idx[q][which];
-    S.sset[q][which][w] = (set >= 0 && w < SKYOPT_ACC_SET_WORDS)
-        ? __ldg(&a.acc_sets[(int64_t)set * SKYOPT_ACC_SET_WORDS + w]) : 0u;
-  }
-  __syncthreads();
   if (tid < nq) {
-    // 64-bit signature (key id mod 64) of the keys an accelerator query can
-    // match (exact | fuzzy): the warp-level early out tests against it.
-    uint32_t lo32 = 0, hi32 = 0;
-    if (S.sq[tid].qflags & SKYOPT_Q_ACC) {
-      for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
-        const uint32_t bits = S.sset[tid][0][w] | S.sset[tid][1][w];
-        if (w & 1) hi32 |= bits; else lo32 |= bits;
-      }
-    } else {
-      lo32 = hi32 = 0xFFFFFFFFu;
-    }
-    S.ssig[tid][0] = lo32; S.ssig[tid][1] = hi32;
-    S.sreq[tid] = S.sq[tid].req_flags;
+    S.sany[tid] = 0;
+    // Running best of the whole grid (pruning bound); stale values are fine.
+    S.gb[tid] = *reinterpret_cast<volatile unsigned long long *>(a.gbest + G.q_begin + tid);
   }
   __syncthreads();
 }
@@ -273,6 +274,24 @@ __device__ __forceinline__ void score_rows(
   fl_or = __reduce_or_sync(0xFFFFFFFFu, fl_or & 0xFFu);
   sg_lo = __reduce_or_sync(0xFFFFFFFFu, sg_lo);
   sg_hi = __reduce_or_sync(0xFFFFFFFFu, sg_hi);
+  // Cheapest price of the warp's rows, per price column: a query whose
+  // running best (over the whole grid) is already below it cannot improve
+  // here -- branch-and-bound on the argmin.
+  uint64_t wmin[2] = {kKeyNone, kKeyNone};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if (!(G.need & (1u << c))) continue;
+    uint64_t k = kKeyNone;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const double p = c ? sp[j] : od[j];
+      if ((klo[j] & SKYOPT_F_VALID) && p == p) k = min(k, price_key(p));
+    }
+    const uint32_t h = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)(k >> 32));
+    const uint32_t l = __reduce_min_sync(
+        0xFFFFFFFFu, ((uint32_t)(k >> 32) == h) ? (uint32_t)k : 0xFFFFFFFFu);
+    wmin[c] = ((uint64_t)h << 32) | l;
+  }
 
   // Warp-level early out, evaluated for all (<= 32) queries at once: lane q
   // tests query q's requirements against the warp summaries; the ballot is
@@ -281,18 +300,22 @@ __device__ __forceinline__ void score_rows(
   {
     bool pass = false;
     if (lane < nq) {
-      const uint32_t rq = S.sreq[lane];
-      const bool is_acc = S.sq[lane].qflags & SKYOPT_Q_ACC;
+      const QueryS &L = S.q[lane].s;
+      const uint32_t rq = L.req_flags;
       pass = ((fl_or & rq) == rq) &&
-             (!is_acc ||
-              (((S.ssig[lane][0] & sg_lo) | (S.ssig[lane][1] & sg_hi)) != 0u));
+             (!(L.qflags & SKYOPT_Q_ACC) ||
+              (((L.sig_lo & sg_lo) | (L.sig_hi & sg_hi)) != 0u));
+      // bound: only tables (LIST / FUZZY) and the first-stage "any" bit of
+      // accelerator queries without a full match need rows that cannot win
+      const bool prunable = !(L.qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY));
+      if (prunable && (L.price_col ? wmin[1] : wmin[0]) > S.gb[lane]) pass = false;
     }
     active = __ballot_sync(0xFFFFFFFFu, pass);
   }
   while (active) {
     const int q = __ffs(active) - 1;
     active &= active - 1;
-    const QueryS &Q = S.sq[q];
+    const QueryS &Q = S.q[q].s;
     const uint32_t qf = Q.qflags;
     uint32_t m1 = 0, mf = 0;
     {
@@ -306,10 +329,10 @@ __device__ __forceinline__ void score_rows(
     if (qf & SKYOPT_Q_ACC) {
       uint32_t me = 0;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) me |= ((S.sset[q][0][aw[j]] >> ab[j]) & 1u) << j;
+      for (int j = 0; j < RPT; ++j) me |= ((S.q[q].set[0][aw[j]] >> ab[j]) & 1u) << j;
       if (qf & SKYOPT_Q_FUZZY) {
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) mf |= ((S.sset[q][1][aw[j]] >> ab[j]) & 1u) << j;
+        for (int j = 0; j < RPT; ++j) mf |= ((S.q[q].set[1][aw[j]] >> ab[j]) & 1u) << j;
         mf &= m1;
       }
       m1 &= me;
@@ -335,6 +358,11 @@ __device__ __forceinline__ void score_rows(
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         if (!((m1 >> j) & 1u)) continue;
+        if (!(qf & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY))) {
+          // strictly worse than a full match found elsewhere: cannot win
+          const double pp = Q.price_col ? sp[j] : od[j];
+          if (pp == pp && price_key(pp) > S.gb[q]) continue;
+        }
         bool ok = (fl[j] & Q.flags2) == Q.flags2;
         if (Q.cpus_op) ok = ok && (vc[j] >= Q.cpu_lo) && (vc[j] <= Q.cpu_hi);
         if (Q.mem_op == SKYOPT_OP_RATIO)
@@ -355,7 +383,7 @@ __device__ __forceinline__ void score_rows(
           const int inst = __ldg(cat.inst_id + base + j);
           if (inst >= 0) {
             const int local = inst - __ldg(&cat.cloud_inst_offsets[Q.cloud]);
-            atomicMin(&a.list_min[a.list_base[S.sqid[q]] + local],
+            atomicMin(&a.list_min[S.q[q].list_base + local],
                       (unsigned long long)key);
           }
         }
@@ -368,7 +396,7 @@ __device__ __forceinline__ void score_rows(
         if (!((mf >> j) & 1u)) continue;
         const double p = (G.need & 1u) ? od[j] : __ldg(cat.price + base + j);
         const uint64_t key = (p == p) ? price_key(p) : kKeyNaN;
-        atomicMin(&a.fuzzy_min[a.fuzzy_base[S.sqid[q]] + ak[j]],
+        atomicMin(&a.fuzzy_min[S.q[q].fuzzy_base + ak[j]],
                   (unsigned long long)key);
       }
     }
@@ -388,6 +416,12 @@ __device__ __forceinline__ void score_rows(
         if (k < ok_ || (k == ok_ && mr < S.wrow[q][warp])) {
           S.wkey[q][warp] = k;
           S.wrow[q][warp] = mr;
+        }
+        if (k < S.gb[q]) {
+          // publish the bound (any achieved key is a valid bound, so the
+          // unsynchronised shared copy is harmless)
+          S.gb[q] = k;
+          atomicMin(a.gbest + G.q_begin + q, (unsigned long long)k);
         }
       }
     }
@@ -410,18 +444,20 @@ __device__ __forceinline__ void finish_block(const ScanArgs &a, const ScanGroup 
     }
     ScanPartial out;
     out.key = k; out.row = r; out.pad_ = S.sany[tid];
-    a.partials[(int64_t)a.partial_base[S.sqid[tid]] + block_in_group] = out;
+    a.partials[(int64_t)S.q[tid].partial_base + block_in_group] = out;
   }
 }
 
 // K1, small catalogs: one tile of 256*RPT rows per block, rows go straight
 // from global memory to registers.
 template <int RPT>
-__global__ void __launch_bounds__(kScanThreads, 3) scan_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(kScanThreads, 768 / kScanThreads) scan_kernel(ScanArgs a) {
   __shared__ ScanShared S;
-  const ScanGroup G = find_group(a, blockIdx.x);
-  const int tile = blockIdx.x - G.block0;
+  const int vb = permuted_block(a);
+  const ScanGroup G = find_group(a, vb);
+  const int tile = vb - G.block0;
   const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0 && a.zero_flag) *a.zero_flag = 0;
   // Stream this thread's rows into registers first (32 B per row); the
   // constraint vectors are staged while the loads are in flight.
   const int64_t base =
@@ -437,7 +473,8 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_kernel(ScanArgs a) {
   load_u16<RPT>(a.cat.zone_id, base, zn);
   load_u16<RPT>(a.cat.flags, base, fl);
   stage_queries(a, G, S);
-  score_rows<RPT>(a, G, S, base, od, sp, vc, mm, ak, rg, zn, fl);
+  if (!(a.debug & 1u)) score_rows<RPT>(a, G, S, base, od, sp, vc, mm, ak, rg, zn, fl);
+  else if (vc[0] == -1.25 && fl[0] == 77u && ak[0] + rg[0] + zn[0] == 5u && mm[0] == od[0]) S.sany[0] = 1;
   finish_block(a, G, S, tile);
 }
 
@@ -488,23 +525,27 @@ static_assert(sizeof(StreamStage) == kStageBytes, "stage layout");
 // mbarriers; all threads copy their rows out to registers, hand the stage
 // back and score the rows while the next tiles stream in. The constraint
 // vectors are staged once per block.
-__global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(kScanThreads, 512 / kScanThreads) scan_stream_kernel(ScanArgs a) {
   extern __shared__ __align__(128) unsigned char stream_smem[];
   StreamStage *stages = reinterpret_cast<StreamStage *>(stream_smem);
   __shared__ ScanShared S;
   __shared__ __align__(8) uint64_t full[kStreamStages];
-  const ScanGroup G = find_group(a, blockIdx.x);
-  const int blk = blockIdx.x - G.block0;
+  const int vb = permuted_block(a);
+  const ScanGroup G = find_group(a, vb);
+  const int blk = vb - G.block0;
   const int tid = threadIdx.x;
-  const int t0 = blk * G.tiles_per_block;
-  const int ntiles = min(G.tiles_per_block, G.total_tiles - t0);
+  if (blockIdx.x == 0 && tid == 0 && a.zero_flag) *a.zero_flag = 0;
+  // Block `blk` of the group owns tiles blk, blk + n_blocks, blk + 2*n_blocks,
+  // ...: every block gets the same mix of cheap and expensive catalog regions.
+  const int stride = G.n_tiles;
+  const int ntiles = (G.total_tiles - blk + stride - 1) / stride;
   const CatDev &cat = a.cat;
 
   auto issue = [&](int i) {
     // tile t0 + i -> stage i % kStreamStages (thread 0 only)
     StreamStage &st = stages[i % kStreamStages];
     uint64_t *bar = &full[i % kStreamStages];
-    const int64_t row = (int64_t)G.row_begin + (int64_t)(t0 + i) * kStreamTile;
+    const int64_t row = (int64_t)G.row_begin + (int64_t)(blk + i * stride) * kStreamTile;
     uint32_t bytes = kStreamTile * (2 * 8 + 4 * 2);
     if (G.need & 1u) bytes += kStreamTile * 8;
     if (G.need & 2u) bytes += kStreamTile * 8;
@@ -550,8 +591,12 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(ScanArgs a
     ld4u(st.ak, ak); ld4u(st.rg, rg); ld4u(st.zn, zn); ld4u(st.fl, fl);
     __syncthreads();  // every thread has its rows: the stage can be refilled
     if (tid == 0 && i + kStreamStages < ntiles) issue(i + kStreamStages);
-    const int64_t base = (int64_t)G.row_begin + (int64_t)(t0 + i) * kStreamTile + r0;
-    score_rows<kStreamRPT>(a, G, S, base, od, sp, vc, mm, ak, rg, zn, fl);
+    const int64_t base =
+        (int64_t)G.row_begin + (int64_t)(blk + i * stride) * kStreamTile + r0;
+    if (!(a.debug & 1u))
+      score_rows<kStreamRPT>(a, G, S, base, od, sp, vc, mm, ak, rg, zn, fl);
+    else if (vc[0] == -1.25 && fl[0] == 77u && ak[0] + rg[0] + zn[0] == 5u && mm[0] == od[0])
+      S.sany[0] = 1;
   }
   finish_block(a, G, S, blk);
 }
@@ -670,9 +715,41 @@ struct ExpandOut {
   double *cand_price_b;    // GCP accelerator price (0 otherwise)
 };
 
+// Block-wide reduction of one query's per-block scan partials: the cheapest
+// fully-matching row (lowest row id on a price tie) and the any-match bit.
+// Every thread gets the result. `red` is scratch for blockDim/32 entries.
+struct PartialBest { uint64_t key; uint32_t row; uint32_t any; };
+__device__ __forceinline__ PartialBest reduce_partials(
+    const ScanPartial *__restrict__ partials, int64_t pb, int n, PartialBest *red) {
+  uint64_t k = kKeyNone; uint32_t r = kRowNone, any = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const ScanPartial p = partials[pb + i];
+    any |= p.pad_;
+    if (p.key < k || (p.key == k && p.row < r)) { k = p.key; r = p.row; }
+  }
+  for (int off = 16; off; off >>= 1) {
+    const uint64_t ok = __shfl_xor_sync(0xFFFFFFFFu, k, off);
+    const uint32_t orow = __shfl_xor_sync(0xFFFFFFFFu, r, off);
+    if (ok < k || (ok == k && orow < r)) { k = ok; r = orow; }
+  }
+  any = __reduce_or_sync(0xFFFFFFFFu, any);
+  const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();  // `red` may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) { red[warp].key = k; red[warp].row = r; red[warp].any = any; }
+  __syncthreads();
+  PartialBest b = red[0];
+  for (int w = 1; w < nw; ++w) {
+    const PartialBest o = red[w];
+    b.any |= o.any;
+    if (o.key < b.key || (o.key == b.key && o.row < b.row)) { b.key = o.key; b.row = o.row; }
+  }
+  return b;
+}
+
 __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
-                              const ScanFinal *__restrict__ finals,
-                              const uint32_t *__restrict__ any1,
+                              const int32_t *__restrict__ partial_base,
+                              const int32_t *__restrict__ partial_count,
+                              const ScanPartial *__restrict__ partials,
                               const uint32_t *__restrict__ acc_sets,
                               const int64_t *__restrict__ slot_off, int sort_n,
                               int max_regions, int max_zones, ExpandOut out,
@@ -691,13 +768,24 @@ __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
   const int reg0 = cat.cloud_region_offsets[cloud];
   const bool has_zones = cat.cloud_n_zones[cloud] > 0;
 
+  // The scan leaves one partial per (query, block); this slot's block folds
+  // the partials of the queries it depends on itself (no separate pass).
+  __shared__ PartialBest s_red[8];
   int inst = S.inst_id;
   bool empty = false;
-  if (S.gate_query >= 0 && any1[S.gate_query] == 0) empty = true;
+  if (S.gate_query >= 0) {
+    const PartialBest g = reduce_partials(partials, partial_base[S.gate_query],
+                                          partial_count[S.gate_query], s_red);
+    if (g.any == 0) empty = true;
+  }
   if (S.query >= 0) {
-    const ScanFinal f = finals[S.query];
-    inst = f.inst;
-    if (f.row < 0 || f.inst < 0) empty = true;
+    const PartialBest f = reduce_partials(partials, partial_base[S.query],
+                                          partial_count[S.query], s_red);
+    if (f.row == kRowNone) empty = true;
+    else {
+      inst = cat.inst_id[f.row];
+      if (inst < 0) empty = true;
+    }
   }
   if (empty || (inst < 0 && inst != -2)) {
     if (tid == 0) { out.slot_count[s] = 0; out.slot_inst[s] = -1; }
@@ -836,6 +924,8 @@ __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
 // K3: one block per DAG.
 constexpr int kSolveThreads = 256;
 constexpr int kMaxDagTasks = 16;  // exact search only; chains are unbounded
+constexpr int kFastTasks = 32;    // chain DP kept in shared memory
+constexpr int kDpCap = 1024;      // ... when every task has <= kDpCap candidates
 
 struct SolveIn {
   const SkyoptSlot *slots;
@@ -1008,6 +1098,121 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
 
   const double kInf = __longlong_as_double(0x7FF0000000000000ll);
 
+  // ---- Phase B, fast path: short chains whose candidate tables fit in
+  // shared memory. Same recurrence and operation order as the general path
+  // below; the DP state, the per-edge tariffs and the back-pointers (kept per
+  // (task, child cloud): the best parent only depends on the child's cloud)
+  // never leave the SM, so a task costs two barriers instead of several
+  // dependent global round trips.
+  {
+    __shared__ int s_tn[kFastTasks], s_src[kFastTasks], s_np[kFastTasks];
+    __shared__ long long s_toff[kFastTasks];
+    __shared__ double s_tar[kFastTasks][SKYOPT_MAX_CLOUDS];
+    __shared__ double s_dpb[2][kDpCap];
+    __shared__ unsigned char s_clb[2][kDpCap];
+    __shared__ int s_bk_idx[kFastTasks][SKYOPT_MAX_CLOUDS];
+    __shared__ unsigned char s_bk_cl[kFastTasks][SKYOPT_MAX_CLOUDS];
+    __shared__ int s_fast;
+    if (tid == 0) s_fast = (D.is_chain && T <= kFastTasks) ? 1 : 0;
+    __syncthreads();
+    if (s_fast) {
+      if (tid < T) {
+        const int t = D.task_begin + tid;
+        const SkyoptTask TK = in.tasks[t];
+        s_tn[tid] = out.task_n[t];
+        s_toff[tid] = in.task_off[t];
+        s_np[tid] = TK.n_parents;
+        s_src[tid] = TK.n_parents ? TK.edge_tariff_begin : TK.src_tariff_begin;
+        if (out.task_n[t] > kDpCap) s_fast = 0;
+      }
+      __syncthreads();
+    }
+    if (s_fast) {
+      for (int i = tid; i < T * C; i += kSolveThreads) {
+        const int lt = i / C, cc = i % C;
+        s_tar[lt][cc] = s_src[lt] >= 0 ? in.tariffs[s_src[lt] + cc] : 0.0;
+      }
+      __syncthreads();
+      int cur = 0;
+      for (int lt = 0; lt < T; ++lt) {
+        const int n = s_tn[lt];
+        const long long toff = s_toff[lt];
+        constexpr int kPer = kDpCap / kSolveThreads;
+        double v[kPer]; int c4[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const int c = tid + k * kSolveThreads;
+          if (c < n) { v[k] = w.tc_value[toff + c]; c4[k] = w.tc_cloud[toff + c]; }
+        }
+        if (s_np[lt] == 0) {
+          if (tid < C) {
+            // parent = dummy source: 0 + egress from the inputs' cloud
+            s_best_val[tid] = s_tar[lt][tid];
+            s_best_idx[tid] = 0;
+            s_bk_idx[lt][tid] = 0; s_bk_cl[lt][tid] = 0;
+          }
+        } else {
+          const int np = s_tn[lt - 1];
+          const double *dpp = s_dpb[cur ^ 1];
+          const unsigned char *clp = s_clb[cur ^ 1];
+          for (int cc = warp; cc < C; cc += kWarps) {
+            double bv = kInf; int bi = 0x7FFFFFFF;
+            for (int p = lane; p < np; p += 32) {
+              const int cp = clp[p];
+              const double eg = (cp != cc) ? s_tar[lt][cp] : 0.0;
+              lexmin(bv, bi, __dadd_rn(dpp[p], eg), p);
+            }
+            for (int o = 16; o; o >>= 1) {
+              const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+              const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+              lexmin(bv, bi, ov, oi);
+            }
+            if (lane == 0) {
+              s_best_val[cc] = bv; s_best_idx[cc] = bi;
+              s_bk_idx[lt][cc] = bi;
+              s_bk_cl[lt][cc] = (bi != 0x7FFFFFFF) ? clp[bi] : 0;
+            }
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const int c = tid + k * kSolveThreads;
+          if (c < n) {
+            s_dpb[cur][c] = __dadd_rn(v[k], s_best_val[c4[k]]);
+            s_clb[cur][c] = (unsigned char)c4[k];
+          }
+        }
+        __syncthreads();
+        cur ^= 1;
+      }
+      // sink: 0 + min_p dp[p] (egress to the dummy sink is 0)
+      const int last = cur ^ 1;
+      const int n = s_tn[T - 1];
+      double bv = kInf; int bi = 0x7FFFFFFF;
+      for (int p = tid; p < n; p += kSolveThreads) lexmin(bv, bi, s_dpb[last][p], p);
+      for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        lexmin(bv, bi, ov, oi);
+      }
+      if (lane == 0) { s_red_val[warp] = bv; s_red_idx[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int k = 1; k < kWarps; ++k) lexmin(bv, bi, s_red_val[k], (int)s_red_idx[k]);
+        SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = bv;
+        out.dag[blockIdx.x] = r;
+        int idx = bi;
+        int cl = s_clb[last][bi];
+        for (int lt = T - 1; lt >= 0; --lt) {
+          out.chosen_index[D.task_begin + lt] = idx;
+          idx = s_bk_idx[lt][cl];
+          cl = s_bk_cl[lt][cl];
+        }
+      }
+    }
+    if (s_fast) goto plan_records;
+  }
   if (D.is_chain) {
     // ---- Phase B: dp[c] = value[c] + min_p (dp[p] + egress(p, c)); strict
     // '<' => first minimum in candidate order (optimizer.py:456-470). The
@@ -1197,6 +1402,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
       }
     }
   }
+plan_records:
   __syncthreads();
   // ---- the plan as candidate records
   for (int lt = tid; lt < T; lt += kSolveThreads) {

@@ -376,10 +376,12 @@ class Solution:
     """Outputs of skyopt_optimize as numpy arrays."""
 
     def __init__(self, packed: PackedProblem, want_tables: bool,
-                 table_cap: int = 0):
+                 table_cap: int = 0, want_scan: bool = False):
         self.packed = packed
-        self.scan = np.zeros(max(packed.n_queries, 1),
-                             dtype=_native.SCAN_RESULT_DTYPE)
+        # per-query scan results cost an extra kernel; only on request
+        self.scan = (np.zeros(max(packed.n_queries, 1),
+                              dtype=_native.SCAN_RESULT_DTYPE)
+                     if want_scan else None)
         self.slot_count = np.zeros(max(packed.n_slots, 1), dtype=np.int32)
         self.slot_inst = np.zeros(max(packed.n_slots, 1), dtype=np.int32)
         self.chosen = np.zeros(max(packed.n_tasks, 1),
@@ -399,7 +401,7 @@ class Solution:
 
     def c_solution(self) -> _native.Solution:
         s = _native.Solution()
-        s.scan = self.scan.ctypes.data
+        s.scan = None if self.scan is None else self.scan.ctypes.data
         s.slot_count = self.slot_count.ctypes.data
         s.slot_inst = self.slot_inst.ctypes.data
         s.chosen = self.chosen.ctypes.data
