@@ -295,15 +295,17 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     }
     return blocks;
   };
-  // Large scans stream several 1024-row tiles per block through shared
-  // memory (TMA double buffering, constraint vectors staged once); sized so
-  // that the grid is about one wave of 2 blocks per SM. Small scans use one
-  // tile per block, with smaller tiles when there is too little work to
-  // cover all SMs.
+  // One tile of 256*RPT rows per block (rows go straight to registers), with
+  // smaller tiles when there is too little work to cover all SMs. The TMA
+  // streaming kernel (several 1024-row tiles per block through shared memory)
+  // is selectable (SKYOPT_SCAN_MODE=stream / skyopt_catalog_set_scan_mode):
+  // on B200 it is slower for this workload -- scoring, not the row stream,
+  // is the critical path and fewer, longer-lived blocks overlap it worse
+  // (profiles/round1_scan_experiments.md) -- so "auto" never picks it.
   P.rpt = 4; P.tpb = 1; P.stream = false;
   const long long tiles4 = count_tiles(4);
   const long long wave = 2ll * cat->sm_count;
-  if (cat->scan_mode >= 2 || (cat->scan_mode == 0 && tiles4 >= 2 * wave)) {
+  if (cat->scan_mode >= 2) {
     P.stream = true;
     P.tpb = (int)std::max<long long>(1, (tiles4 + wave - 1) / wave);
     if (cat->scan_mode == 3) P.tpb = 3;  // tests: force the multi-tile loop
