@@ -73,8 +73,10 @@ class SlotPlan:
         self.hint: Optional[str] = None
         self.explicit_instance: Optional[str] = None
         self.no_fuzzy_when_matched = False
-        # instance type name -> launchable Resources (without region / zone)
-        self.make: Optional[Callable[[str], Any]] = None
+        # (instance type name, requested Resources) -> launchable Resources
+        # (without region / zone); takes the request as an argument so that a
+        # cached plan can serve any Resources object with the same fields
+        self.make: Optional[Callable[[str, Any], Any]] = None
 
 
 class Cloud:
@@ -263,18 +265,18 @@ class Cloud:
             if plan.slot is None:
                 return resources_utils.FeasibleResources([], [], plan.hint)
             return resources_utils.FeasibleResources(
-                [plan.make(plan.explicit_instance)], [], None)
+                [plan.make(plan.explicit_instance, resources)], [], None)
         n_inst = max(len(view.table.inst_names), 1)
         out = engine.scan(b, list_cap=min(n_inst, 2048),
                           fuzzy_cap=self._fuzzy_cap(view), device=view.device)
-        return self._feasible_from_scan(view, plan, out)
+        return self._feasible_from_scan(view, plan, out, resources)
 
     @staticmethod
     def _fuzzy_cap(view) -> int:
         return min(max(len(view.store.acc_keys), 1), 2048)
 
-    def _feasible_from_scan(self, view, plan: SlotPlan,
-                            out) -> resources_utils.FeasibleResources:
+    def _feasible_from_scan(self, view, plan: SlotPlan, out,
+                            resources) -> resources_utils.FeasibleResources:
         from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
         fuzzy: List[str] = []
         gate = plan.gate_query if plan.gate_query is not None else (
@@ -292,9 +294,59 @@ class Cloud:
                 ]
             else:
                 names = [view.store.inst_names[int(res['best_inst'])]]
-        made = [plan.make(n) for n in names]
+        made = [plan.make(n, resources) for n in names]
         made = [m for m in made if m is not None]
         return resources_utils.FeasibleResources(made, fuzzy, None)
+
+    @staticmethod
+    def _request_key(resources: Any) -> tuple:
+        """Every field of a request that plan_feasible / _feature_hint read.
+        Resources are immutable by convention (sky/resources.py:132-134), so
+        two requests with the same key get the same constraint vectors."""
+        r = resources
+        accs = r._accelerators  # pylint: disable=protected-access
+        args = r.accelerator_args
+        return (r.instance_type, r._cpus, r._memory,  # pylint: disable=protected-access
+                None if accs is None else tuple(accs.items()),
+                None if args is None else args.get('tpu_vm', True),
+                r.use_spot, r.region, r.zone, r.disk_tier, r.network_tier,
+                r.local_disk, r.max_hourly_cost,
+                None if r.image_id is None else tuple(sorted(
+                    (str(k), v) for k, v in r.image_id.items())),
+                None if r.ports is None else tuple(r.ports))
+
+    def plan_cached(self, builder, resources: Any,
+                    num_nodes: int = 1) -> SlotPlan:
+        """`_feature_hint` + `plan_feasible`, memoised per (cloud, request
+        fields) on the catalog store and replayed into `builder`: the fused
+        optimizer states the same request shapes over and over (failover
+        re-optimisation, batches of DAGs), and the Python rule code is the
+        dominant host cost once the row work is on the GPU."""
+        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        store = builder.store
+        cache = store.__dict__.setdefault('_plan_cache', {})
+        key = (self.__class__, num_nodes > 1, self._request_key(resources))
+        tmpl = cache.get(key)
+        if tmpl is None:
+            plan = SlotPlan()
+            recorder = engine.ProblemBuilder(store)
+            plan.hint = self._feature_hint(resources, num_nodes)
+            if plan.hint is None:
+                plan = self.plan_feasible(recorder, resources)
+            tmpl = (plan, recorder)
+            cache[key] = tmpl
+        plan, recorder = tmpl
+        if plan.slot is None:
+            return plan
+        qmap = [builder.replay_query(recorder, i)
+                for i in range(len(recorder.queries))]
+        out = SlotPlan()
+        out.__dict__.update(plan.__dict__)
+        out.slot = builder.replay_slot(recorder, plan.slot, qmap)
+        for name in ('list_query', 'fuzzy_query', 'gate_query'):
+            v = getattr(plan, name)
+            setattr(out, name, None if v is None else qmap[v])
+        return out
 
     def plan_feasible(self, builder, resources: Any,
                       want_list: bool = False) -> SlotPlan:
@@ -322,20 +374,19 @@ class Cloud:
                                          resources.disk_tier)
             inst = table.inst_index.get(resources.instance_type, -1)
             plan.explicit_instance = resources.instance_type
-            launchable = resources.copy(accelerators=None)
-            plan.make = lambda name, r=launchable: r
+            plan.make = lambda name, res: res.copy(accelerators=None)
             if ok and inst >= 0:
                 plan.slot = builder.add_slot(inst_id=inst, **slot_common)
             return plan
 
         cloud_obj = self.__class__()
 
-        def make(instance_type: str):
-            ok, _ = self.check_disk_tier(instance_type, resources.disk_tier)
+        def make(instance_type: str, res):
+            ok, _ = self.check_disk_tier(instance_type, res.disk_tier)
             if not ok:
                 return None
-            return resources.copy(cloud=cloud_obj, instance_type=instance_type,
-                                  accelerators=None, cpus=None, memory=None)
+            return res.copy(cloud=cloud_obj, instance_type=instance_type,
+                            accelerators=None, cpus=None, memory=None)
 
         plan.make = make
         premium = self._needs_premium_disk(resources.disk_tier)

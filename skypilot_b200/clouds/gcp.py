@@ -120,7 +120,7 @@ class GCP(cloud.Cloud):
 
         if resources.instance_type is not None:
             plan.explicit_instance = resources.instance_type
-            plan.make = lambda name, r=resources: r
+            plan.make = lambda name, res: res
             fields = dict(slot_common)
             if resources._accelerators is not None:  # pylint: disable=protected-access
                 acc, count = list(resources.accelerators.items())[0]
@@ -148,7 +148,7 @@ class GCP(cloud.Cloud):
                     use_spot, resources.max_hourly_cost,
                     flags_require=_native.F_DEFAULT_FAMILY))
             plan.list_query = q
-            plan.make = lambda name: resources.copy(
+            plan.make = lambda name, res: res.copy(
                 cloud=gcp, instance_type=name, accelerators=None, cpus=None,
                 memory=None)
             plan.slot = builder.add_slot(query=q, **slot_common)
@@ -168,7 +168,7 @@ class GCP(cloud.Cloud):
         plan.gate_query = gate
         plan.fuzzy_query = gate
         acc_dict = {acc: acc_count}
-        plan.make = lambda name: resources.copy(
+        plan.make = lambda name, res: res.copy(
             cloud=gcp, instance_type=name, accelerators=acc_dict, cpus=None,
             memory=None)
         fields = dict(slot_common)

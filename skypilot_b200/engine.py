@@ -147,6 +147,34 @@ class ProblemBuilder:
             self._set_index[key] = idx
         return idx
 
+    def _add_set_bytes(self, key: bytes) -> int:
+        idx = self._set_index.get(key)
+        if idx is None:
+            idx = len(self._sets)
+            self._sets.append(key)
+            self._set_index[key] = idx
+        return idx
+
+    def replay_query(self, recorder: 'ProblemBuilder', i: int) -> int:
+        """Copies query `i` of a recorded plan (Cloud.plan_cached)."""
+        q = dict(recorder.queries[i])
+        for name in ('acc_set', 'fuzzy_set'):
+            if q[name] >= 0:
+                q[name] = self._add_set_bytes(recorder._sets[q[name]])  # pylint: disable=protected-access
+        self.queries.append(q)
+        return len(self.queries) - 1
+
+    def replay_slot(self, recorder: 'ProblemBuilder', i: int,
+                    qmap: List[int]) -> int:
+        slot = dict(recorder.slots[i])
+        for name in ('query', 'gate_query'):
+            if slot[name] >= 0:
+                slot[name] = qmap[slot[name]]
+        if slot['acc_set'] >= 0:
+            slot['acc_set'] = self._add_set_bytes(recorder._sets[slot['acc_set']])  # pylint: disable=protected-access
+        self.slots.append(slot)
+        return len(self.slots) - 1
+
     def add_query(self, spec: Dict[str, Any]) -> int:
         q = dict(spec)
         q['acc_set'] = self.add_set(q.pop('acc_words', None))

@@ -91,7 +91,7 @@ class _Problem:
         inst = int(cand['inst_id'])
         name = 'TPU-VM' if inst == -2 else (
             self.builder.store.inst_names[inst])
-        base = info.plan.make(name)
+        base = info.plan.make(name, info.resources)
         region = info.table.region_names[int(cand['region_id'])]
         zid = int(cand['zone_id'])
         if zid >= 0:
@@ -238,7 +238,10 @@ class Optimizer:
             slot_begin = len(b.slots)
             n_res = len(list(task.resources))
             for res in task.resources:
-                res.validate()
+                if res.__dict__.get('_validated_store') is not store:
+                    # validate() is idempotent and only depends on the catalog
+                    res.validate()
+                    res.__dict__['_validated_store'] = store
                 if res.cloud is not None and not clouds.cloud_in_iterable(
                         res.cloud, enabled):
                     continue
@@ -247,17 +250,11 @@ class Optimizer:
                 for cloud in clouds_list:
                     if not store.has_cloud(cloud.canonical_name()):
                         continue
-                    hint = cloud._feature_hint(res, task.num_nodes)  # pylint: disable=protected-access
-                    if hint is not None:
-                        hints[res][cloud] = hint
-                        continue
-                    before = len(b.slots)
-                    plan = cloud.plan_feasible(b, res)
+                    plan = cloud.plan_cached(b, res, task.num_nodes)
                     if plan.hint is not None:
                         hints[res][cloud] = plan.hint
                     if plan.slot is None:
                         continue
-                    assert len(b.slots) == before + 1
                     slot = b.slots[plan.slot]
                     slot['hours'] = runtime / 3600
                     slot['node_mult'] = float(max(task.num_nodes, 0))
@@ -438,7 +435,8 @@ class Optimizer:
                 info = problem.slot_info[int(cand['slot'])]
                 if not per_cloud[info.cloud]:
                     per_cloud[info.cloud].append(
-                        info.plan.make(launchable.instance_type))
+                        info.plan.make(launchable.instance_type,
+                                       info.resources))
             node_to_candidate_map[task] = per_cloud
         for t in topo_order:
             if _is_dummy(t):

@@ -585,9 +585,49 @@ class Resources:
             features.add(f.LOCAL_DISK)
         return features
 
+    _PLAIN_FIELDS = {
+        'cloud': '_cloud', 'instance_type': '_instance_type',
+        'region': '_region', 'zone': '_zone', 'labels': '_labels',
+        'max_hourly_cost': '_max_hourly_cost', 'job_recovery': '_job_recovery',
+    }
+
     def copy(self, **override) -> 'Resources':
         """A new Resources with some fields replaced
-        (sky/resources.py:2076-2143)."""
+        (sky/resources.py:2076-2143). Fields that need no re-parsing are
+        cloned directly; the rest go through the same setters as __init__."""
+        new = Resources.__new__(Resources)
+        new.__dict__.update(self.__dict__)
+        new.__dict__.pop('_validated_store', None)
+        if self._accelerators is not None:
+            new._accelerators = dict(self._accelerators)
+        for key, value in override.items():
+            attr = Resources._PLAIN_FIELDS.get(key)
+            if attr is not None:
+                setattr(new, attr, value)
+            elif key == 'cpus':
+                new._set_cpus(value)
+            elif key == 'memory':
+                new._set_memory(value)
+            elif key == 'accelerators':
+                new._set_accelerators(value, override.get(
+                    'accelerator_args', self._accelerator_args))
+            elif key == 'accelerator_args':
+                if 'accelerators' not in override:
+                    new._accelerator_args = value
+            elif key == 'use_spot':
+                new._use_spot_specified = value is not None
+                new._use_spot = value if value is not None else False
+            elif key == 'no_missing_accel_warnings':
+                new._no_missing_accel_warnings = value
+            elif key in ('disk_size', 'image_id', 'disk_tier', 'network_tier',
+                         'local_disk', 'ports', 'infra'):
+                # rare: rebuild through the constructor
+                return self._copy_via_init(**override)
+            else:
+                raise AssertionError(f'unknown Resources field {key!r}')
+        return new
+
+    def _copy_via_init(self, **override) -> 'Resources':
         use_spot = self._use_spot if self._use_spot_specified else None
         resources = Resources(
             cloud=override.pop('cloud', self._cloud),
