@@ -51,9 +51,23 @@ extern "C" {
 #define SKYOPT_MAX_GROUP_ROWS 4096 /* rows of one instance type / acc key */
 
 /*
+ * Summary of 128 consecutive rows ("zone map" entry), computed at ingest:
+ * the scan tests a query against it before touching the rows.
+ */
+typedef struct SkyoptZone {
+  uint32_t flags_or;   /* OR of the low flag byte over the valid rows */
+  uint32_t sig_lo;     /* bit (acc_key % 64) for every valid row's key ... */
+  uint32_t sig_hi;     /* ... bits 32..63 */
+  uint32_t pad_;
+  uint64_t min_key[2]; /* cheapest 'Price' / 'SpotPrice' of the valid rows as
+                          an order-preserving integer key (see
+                          skyopt_price_key); all ones = none */
+} SkyoptZone;
+
+/*
  * The catalog as structure-of-arrays columns (host pointers; copied to HBM by
  * skyopt_catalog_create). Rows of all clouds are concatenated cloud by cloud
- * in original CSV order; each cloud's range is padded to a multiple of 8 rows
+ * in original CSV order; each cloud's range is padded to a multiple of 128 rows
  * with flags == 0 rows. Replaces the pandas DataFrames of
  * sky/catalog/common.py:126-266 (LazyDataFrame / read_catalog).
  */
@@ -76,7 +90,7 @@ typedef struct SkyoptCatalogDesc {
   int32_t n_inst;            /* instance types over all clouds */
   int32_t n_acc_keys;        /* <= 32 * SKYOPT_ACC_SET_WORDS */
   int32_t n_regions;         /* total over clouds */
-  const int32_t *cloud_row_offsets;  /* [n_clouds+1], multiples of 8 */
+  const int32_t *cloud_row_offsets;  /* [n_clouds+1], multiples of 128 */
   const int32_t *cloud_inst_offsets; /* [n_clouds+1] instance ids per cloud */
   const int32_t *cloud_region_offsets; /* [n_clouds+1] into region tables */
   const int32_t *cloud_n_zones;      /* [n_clouds]; 0 = cloud has no
@@ -91,6 +105,7 @@ typedef struct SkyoptCatalogDesc {
                                         grouped by acc_key (GCP) */
   const uint16_t *inst_acc_key;      /* [n_inst] acc_key of the type's first
                                         row (common.py:572-590) */
+  const SkyoptZone *zone_map;        /* [n_rows / 128] static row summaries */
 } SkyoptCatalogDesc;
 
 /* comparison operators of a query */
@@ -284,6 +299,8 @@ typedef struct SkyoptStats {
 typedef struct SkyoptCatalog SkyoptCatalog; /* opaque */
 
 int skyopt_abi_version(void);
+/* Order-preserving map double -> uint64 used for prices (NaN excluded). */
+uint64_t skyopt_price_key(double price);
 const char *skyopt_last_error(void);
 int skyopt_device_count(int *count);
 

@@ -22,11 +22,12 @@ Azure = clouds.Azure
 Lambda = clouds.Lambda
 
 optimize = Optimizer.optimize
+optimize_batch = Optimizer.optimize_batch
 
 __version__ = '0.1.0'
 
 __all__ = [
     'AWS', 'Azure', 'Dag', 'DummyResources', 'GCP', 'Lambda', 'Optimizer',
     'OptimizeTarget', 'Resources', 'Task', 'catalog', 'check', 'clouds',
-    'exceptions', 'optimize'
+    'exceptions', 'optimize', 'optimize_batch'
 ]

@@ -89,6 +89,12 @@ CANDIDATE_DTYPE = np.dtype([
     ('zone_id', '<i4'), ('hourly', '<f8'), ('value', '<f8'),
 ], align=True)
 
+ZONE_DTYPE = np.dtype([
+    ('flags_or', '<u4'), ('sig_lo', '<u4'), ('sig_hi', '<u4'), ('pad_', '<u4'),
+    ('min_key', '<u8', (2,)),
+], align=True)
+ZONE_ROWS = 128
+
 DAG_RESULT_DTYPE = np.dtype([
     ('status', '<i4'), ('task_fail', '<i4'), ('objective', '<f8'),
 ], align=True)
@@ -121,6 +127,7 @@ class CatalogDesc(ctypes.Structure):
         ('cloud_region_offsets', _p), ('cloud_n_zones', _p),
         ('region_is_us', _p), ('inst_row_offsets', _p), ('inst_rows', _p),
         ('acc_row_offsets', _p), ('acc_rows', _p), ('inst_acc_key', _p),
+        ('zone_map', _p),
     ]
 
 
@@ -163,7 +170,7 @@ EXPORTS = (
     'skyopt_abi_version', 'skyopt_last_error', 'skyopt_device_count',
     'skyopt_catalog_create', 'skyopt_catalog_destroy', 'skyopt_catalog_bytes',
     'skyopt_scan', 'skyopt_optimize', 'skyopt_optimize_timed',
-    'skyopt_catalog_set_scan_mode',
+    'skyopt_catalog_set_scan_mode', 'skyopt_price_key',
 )
 
 _lib = None
@@ -190,6 +197,8 @@ def load() -> ctypes.CDLL:
                 'optimizer hot path has no CPU fallback.')
         lib = ctypes.CDLL(path)
         lib.skyopt_abi_version.restype = ctypes.c_int
+        lib.skyopt_price_key.restype = ctypes.c_uint64
+        lib.skyopt_price_key.argtypes = [ctypes.c_double]
         lib.skyopt_last_error.restype = ctypes.c_char_p
         lib.skyopt_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
         lib.skyopt_catalog_create.argtypes = [

@@ -30,7 +30,7 @@ import pandas as pd
 from skypilot_b200 import _native
 from skypilot_b200.catalog import rules as rules_lib
 
-_ROW_ALIGN = 8
+_ROW_ALIGN = _native.ZONE_ROWS  # clouds start on a zone-map boundary
 CATALOG_SCHEMA_VERSION = 'v8'
 
 
@@ -39,6 +39,43 @@ def _col(df: pd.DataFrame, name: str, n: int) -> np.ndarray:
         return pd.to_numeric(df[name], errors='coerce').to_numpy(
             dtype=np.float64, na_value=np.nan)
     return np.full(n, np.nan)
+
+
+def price_keys(values: np.ndarray) -> np.ndarray:
+    """Order-preserving double -> uint64 map (skyopt_price_key in C): flip
+    the sign bit of non-negative values, all bits of negative ones."""
+    bits = np.ascontiguousarray(values, dtype=np.float64).view(np.uint64)
+    neg = (bits >> np.uint64(63)).astype(bool)
+    return np.where(neg, ~bits, bits | np.uint64(1 << 63))
+
+
+def _zone_map(cols: Dict[str, np.ndarray]) -> np.ndarray:
+    """Static summary of every 128-row chunk: flag bits and accelerator keys
+    (mod 64) that occur, cheapest Price / SpotPrice. The scan kernel tests a
+    query against the summary before it touches the chunk's rows."""
+    zr = _native.ZONE_ROWS
+    n = len(cols['flags'])
+    assert n % zr == 0
+    nz = n // zr
+    flags = cols['flags'].reshape(nz, zr)
+    valid = (flags & _native.F_VALID) != 0
+    zone = np.zeros(nz, dtype=_native.ZONE_DTYPE)
+    zone['flags_or'] = np.bitwise_or.reduce(
+        np.where(valid, flags & 0xFF, 0).astype(np.uint32), axis=1)
+    ak = cols['acc_key'].reshape(nz, zr).astype(np.uint64)
+    has = valid & (ak != _native.NONE16)
+    sig = np.bitwise_or.reduce(
+        np.where(has, np.uint64(1) << (ak & np.uint64(63)), np.uint64(0)),
+        axis=1)
+    zone['sig_lo'] = (sig & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    zone['sig_hi'] = (sig >> np.uint64(32)).astype(np.uint32)
+    none = np.uint64(0xFFFFFFFFFFFFFFFF)
+    for c, name in enumerate(('price', 'spot_price')):
+        p = cols[name].reshape(nz, zr)
+        ok = valid & ~np.isnan(p)
+        keys = np.where(ok, price_keys(np.nan_to_num(p, nan=0.0)), none)
+        zone['min_key'][:, c] = keys.min(axis=1)
+    return zone
 
 
 class CloudTable:
@@ -81,8 +118,7 @@ class CatalogStore:
         self.n_rows = 0  # padded
         self.n_real_rows = 0
         self.max_group_rows = 1
-        self._handle = ctypes.c_void_p(None)
-        self._device: Optional[int] = None
+        self._handles: Dict[int, ctypes.c_void_p] = {}
         self._lock = threading.Lock()
         self._keepalive: List[np.ndarray] = []
 
@@ -299,6 +335,7 @@ class CatalogStore:
             nonempty = counts > 0
             iak[:n_inst][nonempty] = akc[firsts[nonempty]]
         cols['inst_acc_key'] = iak
+        cols['zone_map'] = _zone_map(cols)
         store.max_group_rows = int(
             max([1] + list(counts) + list(acounts)))
         store.acc_names_lower = [k[0].lower() for k in store.acc_keys]
@@ -377,15 +414,16 @@ class CatalogStore:
 
     # ----------------------------------------------------------------- device
     def handle(self, device: int = 0) -> ctypes.c_void_p:
-        """Uploads the table on first use (skyopt_catalog_create)."""
-        if self._handle.value is not None:
-            if self._device != device:
-                raise RuntimeError(
-                    f'catalog already resident on device {self._device}')
-            return self._handle
+        """Device copy of the table (skyopt_catalog_create), made on first
+        use; one replica per GPU (the catalog is small: replicate, don't
+        shard -- SURVEY.md section 8e)."""
+        hit = self._handles.get(device)
+        if hit is not None:
+            return hit
         with self._lock:
-            if self._handle.value is not None:
-                return self._handle
+            hit = self._handles.get(device)
+            if hit is not None:
+                return hit
             lib = _native.load()
             c = self.columns
             desc = _native.CatalogDesc()
@@ -424,14 +462,16 @@ class CatalogStore:
             desc.acc_row_offsets = p('acc_row_offsets', np.int32)
             desc.acc_rows = p('acc_rows', np.int32)
             desc.inst_acc_key = p('inst_acc_key', np.uint16)
+            zm = np.ascontiguousarray(c['zone_map'])
+            keep.append(zm)
+            desc.zone_map = zm.ctypes.data
             handle = ctypes.c_void_p(None)
             _native.check(
                 lib.skyopt_catalog_create(ctypes.byref(desc), device,
                                           ctypes.byref(handle)))
             del keep
-            self._handle = handle
-            self._device = device
-        return self._handle
+            self._handles[device] = handle
+        return handle
 
     def set_scan_mode(self, mode: str, device: int = 0) -> None:
         """'auto' | 'tile' | 'stream' (skyopt_catalog_set_scan_mode)."""
@@ -440,10 +480,9 @@ class CatalogStore:
             self.handle(device), code))
 
     def close(self) -> None:
-        if self._handle.value is not None:
-            _native.load().skyopt_catalog_destroy(self._handle)
-            self._handle = ctypes.c_void_p(None)
-            self._device = None
+        for handle in list(self._handles.values()):
+            _native.load().skyopt_catalog_destroy(handle)
+        self._handles.clear()
 
     def __del__(self):
         try:

@@ -314,6 +314,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     if (tiles4 < wave) P.rpt = 2;
     if (P.rpt == 2 && count_tiles(2) < wave) P.rpt = 1;
   }
+  if (const char *r = getenv("SKYOPT_RPT")) { const int v = atoi(r); if (v == 1 || v == 2 || v == 4) P.rpt = v; }
   const int tile = kScanThreads * P.rpt;
   P.n_groups = 0;
   for (int c = 0; c < C; ++c)
@@ -463,6 +464,11 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
       sa.n_blocks = P.n_blocks;
       sa.debug = 0;
       if (const char *dbg = getenv("SKYOPT_DEBUG")) sa.debug = (uint32_t)atoi(dbg);
+      static unsigned long long *tl = nullptr; static int tl_blocks = 0;
+      if (sa.debug & 2u) {
+        if (tl_blocks < P.n_blocks) { if (tl) cudaFree(tl); CU(cudaMalloc(&tl, (size_t)P.n_blocks * 64)); tl_blocks = P.n_blocks; }
+        sa.timeline = tl;
+      }
       sa.perm_mul = 1;
       for (uint32_t cand : {7919u, 104729u, 1299709u, 15485863u}) {
         uint64_t x = cand, y = (uint64_t)P.n_blocks;  // gcd
@@ -477,6 +483,15 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
       else scan_kernel<1><<<P.n_blocks, kScanThreads, 0, st>>>(sa);
       CU(cudaGetLastError());
       CU(cudaEventRecord(x->ev[7], st));
+      if (sa.debug & 2u) {
+        // profiling experiment: dump the per-block timeline of this launch
+        std::vector<unsigned long long> h((size_t)P.n_blocks * 8);
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpy(h.data(), sa.timeline, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (const char *path = getenv("SKYOPT_TIMELINE")) {
+          if (FILE *f = fopen(path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        }
+      }
     }
     if (want_scan_results || !solve) {
       const int fblocks = (P.nq * 32 + 255) / 256;
@@ -620,6 +635,11 @@ int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
 extern "C" {
 
 int skyopt_abi_version(void) { return SKYOPT_ABI_VERSION; }
+
+uint64_t skyopt_price_key(double price) {
+  uint64_t b; memcpy(&b, &price, 8);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
 const char *skyopt_last_error(void) { return g_error.c_str(); }
 
 int skyopt_device_count(int *count) {
@@ -634,7 +654,7 @@ int skyopt_device_count(int *count) {
 int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog **out) {
   if (!d || !out) return fail(SKYOPT_EINVAL, "NULL argument");
   *out = nullptr;
-  if (d->n_rows <= 0 || d->n_rows % 8 != 0) return fail(SKYOPT_EINVAL, "n_rows must be a positive multiple of 8");
+  if (d->n_rows <= 0 || d->n_rows % kZoneRows != 0) return fail(SKYOPT_EINVAL, "n_rows must be a positive multiple of 128");
   if (d->n_rows > 0x7FFFFFF0ll) return fail(SKYOPT_ELIMIT, "catalog exceeds 2^31 rows");
   if (d->n_clouds <= 0 || d->n_clouds > SKYOPT_MAX_CLOUDS) return fail(SKYOPT_ELIMIT, "1..%d clouds supported", SKYOPT_MAX_CLOUDS);
   if (d->n_acc_keys < 0 || d->n_acc_keys > 32 * SKYOPT_ACC_SET_WORDS)
@@ -642,13 +662,13 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog 
   if (!d->price || !d->spot_price || !d->vcpus || !d->mem || !d->acc_key || !d->region_id ||
       !d->zone_id || !d->flags || !d->inst_id || !d->cloud_row_offsets || !d->cloud_inst_offsets ||
       !d->cloud_region_offsets || !d->cloud_n_zones || !d->region_is_us || !d->inst_row_offsets ||
-      !d->inst_rows || !d->acc_row_offsets || !d->acc_rows || !d->inst_acc_key)
+      !d->inst_rows || !d->acc_row_offsets || !d->acc_rows || !d->inst_acc_key || !d->zone_map)
     return fail(SKYOPT_EINVAL, "a required column pointer is NULL");
   if (d->cloud_row_offsets[0] != 0 || d->cloud_row_offsets[d->n_clouds] != d->n_rows)
     return fail(SKYOPT_EINVAL, "cloud_row_offsets must span [0, n_rows]");
   for (int c = 0; c < d->n_clouds; ++c)
-    if (d->cloud_row_offsets[c] % 8 != 0 || d->cloud_row_offsets[c + 1] < d->cloud_row_offsets[c])
-      return fail(SKYOPT_EINVAL, "cloud %d row range must be 8-row aligned", c);
+    if (d->cloud_row_offsets[c] % kZoneRows != 0 || d->cloud_row_offsets[c + 1] < d->cloud_row_offsets[c])
+      return fail(SKYOPT_EINVAL, "cloud %d row range must be 128-row aligned", c);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(SKYOPT_ENODEV, "no CUDA device available; libskyopt has no CPU fallback");
@@ -688,6 +708,9 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog 
   rc = rc ? rc : upload(c, d->acc_row_offsets, (size_t)d->n_acc_keys + 1, 0, &v.acc_row_offsets);
   rc = rc ? rc : upload(c, d->acc_rows, n_acc_rows, 1, &v.acc_rows);
   rc = rc ? rc : upload(c, d->inst_acc_key, (size_t)std::max(d->n_inst, 1), 0, &v.inst_acc_key, 0xFF);
+  static_assert(sizeof(SkyoptZone) == sizeof(RowSummary), "zone map ABI");
+  rc = rc ? rc : upload(c, reinterpret_cast<const RowSummary *>(d->zone_map), n / kZoneRows,
+                        kStreamTile / kZoneRows + 1, &v.zone_map);
   if (rc) { skyopt_catalog_destroy(c); return rc; }
 
   c->cloud_row_offsets.assign(d->cloud_row_offsets, d->cloud_row_offsets + d->n_clouds + 1);

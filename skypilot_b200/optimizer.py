@@ -205,6 +205,100 @@ class Optimizer:
         dag.remove(source[0])
         dag.remove(sink[0])
 
+    @staticmethod
+    def optimize_batch(dags: List['dag_lib.Dag'],
+                       minimize: OptimizeTarget = OptimizeTarget.COST,
+                       blocked_resources: Optional[Iterable[
+                           resources_lib.Resources]] = None,
+                       devices: Optional[List[int]] = None,
+                       return_exceptions: bool = False) -> List[Any]:
+        """Optimizes independent DAGs together (BASELINE.json config 5).
+
+        DAG *i* goes to GPU `devices[i % len(devices)]`; every GPU holds a
+        replica of the catalog and solves its shard as ONE device problem
+        (one H2D, five launches, one D2H), the shards run concurrently from
+        one host thread per GPU. No collective is involved: the DAGs are
+        independent (north_star: "no NCCL needed").
+
+        Returns the DAGs (each task's `best_resources` set). A DAG without a
+        feasible plan raises ResourcesUnavailableError, or -- with
+        `return_exceptions` -- yields the exception object in its slot.
+        """
+        import threading  # pylint: disable=import-outside-toplevel
+        minimize_cost = minimize == OptimizeTarget.COST
+        blocked = list(blocked_resources or [])
+        store = catalog.get_store()
+        devices = list(devices) if devices else [catalog.get_device()]
+        shards: List[List[int]] = [[] for _ in devices]
+        for i in range(len(dags)):
+            shards[i % len(devices)].append(i)
+        problems: Dict[int, _Problem] = {}
+        builders = [engine.ProblemBuilder(store) for _ in devices]
+        first_task: Dict[int, int] = {}
+        for shard, b in zip(shards, builders):
+            for i in shard:
+                dag = dags[i]
+                _check_specified_clouds(dag)
+                choice = Optimizer._resolve_ordered_resources(dag, blocked)
+                saved = {t: t.resources for t in choice}
+                for t, c in choice.items():
+                    t.resources = {c}
+                Optimizer._add_dummy_source_sink_nodes(dag)
+                try:
+                    graph = dag.get_graph()
+                    topo = [t for t in nx.topological_sort(graph)
+                            if not _is_dummy(t)]
+                    first_task[i] = len(b.tasks)
+                    problems[i] = Optimizer._state_problem(
+                        graph, topo, minimize_cost, blocked, dag.is_chain(),
+                        builder=b)
+                finally:
+                    Optimizer._remove_dummy_source_sink_nodes(dag)
+                    for t, original in saved.items():
+                        t.resources = original
+        solutions: List[Optional[engine.Solution]] = [None] * len(devices)
+        errors: List[Optional[BaseException]] = [None] * len(devices)
+
+        def run(k: int) -> None:
+            try:
+                if builders[k].dags:
+                    solutions[k] = engine.solve(builders[k], device=devices[k])
+            except BaseException as e:  # pylint: disable=broad-except
+                errors[k] = e
+
+        threads = [threading.Thread(target=run, args=(k,))
+                   for k in range(len(devices))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        out: List[Any] = [None] * len(dags)
+        for k, shard in enumerate(shards):
+            sol = solutions[k]
+            for d, i in enumerate(shard):
+                problem = problems[i]
+                res = sol.dag[d]
+                try:
+                    if res['status'] == 1:
+                        Optimizer._raise_unavailable(
+                            problem.tasks[int(res['task_fail'])], blocked)
+                    if res['status'] != 0:
+                        raise exceptions.ResourcesUnavailableError(
+                            'The DAG is too large for the exact general-DAG '
+                            'search.')
+                    for j, task in enumerate(problem.tasks):
+                        task.best_resources = problem.launchable(
+                            sol.chosen[first_task[i] + j])
+                    out[i] = dags[i]
+                except exceptions.ResourcesUnavailableError as e:
+                    if not return_exceptions:
+                        raise
+                    out[i] = e
+        return out
+
     # ---------------------------------------------------- problem construction
     @staticmethod
     def _runtime(task, n_resources: int, orig_resources) -> float:

@@ -201,3 +201,59 @@ def test_batch_of_independent_dags_matches_single_calls():
         assert (str(r.cloud), r.instance_type, r.region,
                 r.zone) == singles[i]
     del nx
+
+
+def _random_single_task_dags(n, seed):
+    rng = np.random.default_rng(seed)
+    accs = [None, 'V100', 'T4', 'A100:8', 'L4', 'H100:8', 'A10G', 'K80',
+            'A100:3', 'T4:4']
+    dags, tasks = [], []
+    for _ in range(n):
+        spec = {}
+        acc = accs[int(rng.integers(len(accs)))]
+        if acc:
+            spec['accelerators'] = acc
+        cpus = [None, '2+', '8+', '32+'][int(rng.integers(4))]
+        if cpus:
+            spec['cpus'] = cpus
+        mem = [None, '16+', '4x'][int(rng.integers(3))]
+        if mem and not acc:
+            spec['memory'] = mem
+        if rng.uniform() < 0.3:
+            spec['use_spot'] = True
+        with sky.Dag() as dag:
+            t = sky.Task('t')
+            t.set_resources(sky.Resources(**spec))
+        dags.append(dag)
+        tasks.append(t)
+    return dags, tasks
+
+
+def test_optimize_batch_matches_one_by_one():
+    """BASELINE config 5 shape: a batch of independent single-task DAGs,
+    sharded over every visible GPU, equals optimizing them one at a time."""
+    from skypilot_b200 import _native
+    runner.activate_catalog(scenarios.CATALOGS['multi6k'])
+    dags, tasks = _random_single_task_dags(200, seed=4)
+    want = []
+    for dag, t in zip(dags, tasks):
+        try:
+            sky.optimize(dag, quiet=True)
+            r = t.best_resources
+            want.append((str(r.cloud), r.instance_type, r.region, r.zone))
+        except sky.exceptions.ResourcesUnavailableError:
+            want.append(None)
+        t.best_resources = None
+    devices = list(range(_native.device_count()))
+    out = sky.optimize_batch(dags, devices=devices, return_exceptions=True)
+    got = []
+    for o, t in zip(out, tasks):
+        if isinstance(o, Exception):
+            got.append(None)
+        else:
+            r = t.best_resources
+            got.append((str(r.cloud), r.instance_type, r.region, r.zone))
+    assert got == want
+    assert any(w is None for w in want) and any(w is not None for w in want)
+    with pytest.raises(sky.exceptions.ResourcesUnavailableError):
+        sky.optimize_batch(dags, devices=devices)

@@ -144,6 +144,37 @@ def test_flag_rules(store):
     assert (c['flags'][row] >> 8) == rules.GCP_GROUP_IDS[('A100', 8)]
 
 
+def test_zone_map_summarises_every_chunk(store):
+    from skypilot_b200.catalog import store as store_lib
+    c = store.columns
+    zm = c['zone_map']
+    zr = _native.ZONE_ROWS
+    assert len(zm) == store.n_rows // zr
+    lib = _native.load()
+    for v in (0.0, 0.0001, 0.526, 3.06, 98.32, 1e6, -1.5):
+        assert int(store_lib.price_keys(np.array([v]))[0]) == (
+            lib.skyopt_price_key(v))
+    keys_sorted = store_lib.price_keys(np.array([-2.0, -1.0, 0.0, 0.5, 7.0]))
+    assert list(keys_sorted) == sorted(keys_sorted)
+    none = np.uint64(0xFFFFFFFFFFFFFFFF)
+    for z in range(0, len(zm), 7):
+        rows = slice(z * zr, (z + 1) * zr)
+        fl = c['flags'][rows]
+        valid = (fl & _native.F_VALID) != 0
+        assert zm['flags_or'][z] == int(
+            np.bitwise_or.reduce(np.where(valid, fl & 0xFF, 0)))
+        sig = 0
+        for k, ok in zip(c['acc_key'][rows], valid):
+            if ok and k != _native.NONE16:
+                sig |= 1 << (int(k) % 64)
+        assert (int(zm['sig_hi'][z]) << 32 | int(zm['sig_lo'][z])) == sig
+        for col, name in enumerate(('price', 'spot_price')):
+            p = c[name][rows]
+            ok = valid & ~np.isnan(p)
+            want = (store_lib.price_keys(p[ok]).min() if ok.any() else none)
+            assert zm['min_key'][z, col] == want
+
+
 # ---- constraint vectors ------------------------------------------------------
 def test_cpus_memory_parsing():
     assert engine.parse_cpus('8+') == (_native.OP_GE, 8.0)

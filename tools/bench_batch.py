@@ -1,0 +1,71 @@
+"""BASELINE config 5: a batch of independent single-task DAGs through
+Optimizer.optimize_batch, sharded over the visible GPUs (one host process,
+one thread per GPU, catalog replicated, no collective).
+
+    python tools/bench_batch.py [n_dags] [n_gpus]
+"""
+import json
+import sys
+import time
+
+sys.path.insert(0, '.')
+import numpy as np  # noqa: E402
+import skypilot_b200 as sky  # noqa: E402
+from skypilot_b200 import _native, synth  # noqa: E402
+
+
+def make_dags(n, seed=4):
+    rng = np.random.default_rng(seed)
+    accs = [None, 'V100', 'T4', 'A100:8', 'L4', 'H100:8', 'A10G', 'K80',
+            'A100', 'T4:4', 'V100:4', 'L4:8']
+    regions = [None] * 10 + ['us-east-1', 'us-west-2']
+    dags = []
+    for _ in range(n):
+        spec = {}
+        acc = accs[int(rng.integers(len(accs)))]
+        if acc:
+            spec['accelerators'] = acc
+        cpus = [None, '2+', '8+', '32+'][int(rng.integers(4))]
+        if cpus:
+            spec['cpus'] = cpus
+        mem = [None, '16+', '4x'][int(rng.integers(3))]
+        if mem and not acc:
+            spec['memory'] = mem
+        if rng.uniform() < 0.5:
+            spec['use_spot'] = True
+        region = regions[int(rng.integers(len(regions)))]
+        if region:
+            spec['infra'] = f'aws/{region}'
+        with sky.Dag() as dag:
+            sky.Task('t').set_resources(sky.Resources(**spec))
+        dags.append(dag)
+    return dags
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+    ngpu = int(sys.argv[2]) if len(sys.argv) > 2 else _native.device_count()
+    frames = synth.make_catalogs(1, 50000)
+    store = sky.catalog.load_frames(frames)
+    rows = synth.total_rows(frames)
+    devices = list(range(ngpu))
+    for d in devices:
+        store.handle(d)
+    dags = make_dags(n)
+    sky.optimize_batch(dags[:200], devices=devices, return_exceptions=True)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = sky.optimize_batch(dags, devices=devices, return_exceptions=True)
+        times.append(time.perf_counter() - t0)
+    ok = sum(not isinstance(o, Exception) for o in out)
+    best = min(times)
+    print(json.dumps({
+        'workload': f'cfg5: {n} single-task DAGs, {rows}-row catalog',
+        'n_gpus': ngpu, 'seconds': best, 'dags_per_s': n / best,
+        'candidates_per_s': n * rows / best, 'feasible': ok
+    }))
+
+
+if __name__ == '__main__':
+    main()
