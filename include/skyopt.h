@@ -338,6 +338,23 @@ int skyopt_optimize(SkyoptCatalog *cat, const SkyoptProblem *problem,
                     SkyoptSolution *solution, SkyoptStats *stats);
 
 /*
+ * DP / exact search alone, on candidate tables the caller already has:
+ * Optimizer._optimize_by_dp (optimizer.py:429-487) and _optimize_by_ilp
+ * (:490-637) as stand-alone operators. Task t's candidates are
+ * values[task_offsets[t] .. task_offsets[t+1]) (cost or time entering the
+ * objective, in the reference's dictionary order) with their cloud index in
+ * `clouds`; tasks / parents / tariffs / dags as in SkyoptProblem (slot fields
+ * of the tasks are ignored). Writes the chosen candidate index per task.
+ */
+int skyopt_solve_tables(SkyoptCatalog *cat, const double *values,
+                        const int32_t *clouds, const int64_t *task_offsets,
+                        const SkyoptTask *tasks, int n_tasks,
+                        const int32_t *parents, int n_parents,
+                        const double *tariffs, int n_tariffs,
+                        const SkyoptDag *dags, int n_dags,
+                        int32_t *chosen_index, SkyoptDagResult *results);
+
+/*
  * Device-resident timing loop for bench.py: uploads `problem` once, then runs
  * the kernels `iters` times, flushing L2 (writing a buffer > 126 MB) before
  * every iteration when flush_l2 != 0; per-iteration device times (CUDA

@@ -517,7 +517,7 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
   }
   CU(cudaEventRecord(x->ev[3], st));
   if (P.nd) {
-    SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex};
+    SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex, 0};
     SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
     SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres};
     gather_kernel<<<P.nt, kGatherThreads, 0, st>>>(cat->dev, in, w, P.task_dag, P.task_n);
@@ -596,7 +596,7 @@ int copy_solution(SkyoptCatalog *cat, Ctx *x, const Plan &P, const SkyoptProblem
       CU(cudaMalloc(&d_tab, sizeof(SkyoptCandidate) * off[P.nt]));
       CU(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * (P.nt + 1), cudaMemcpyHostToDevice, x->stream));
       ExpandOut ex{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
-      SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex};
+      SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex, 0};
       SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
       table_kernel<<<P.nt, 128, 0, x->stream>>>(in, w, P.task_n, P.nt, d_off, d_tab);
       cudaError_t e = cudaGetLastError();
@@ -895,6 +895,82 @@ int skyopt_optimize(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution 
     CU(cudaStreamSynchronize(st));
     if ((r = copy_solution(cat, x, P, pb, sol))) return r;
     return fill_stats(x, P, stats, true);
+  };
+  rc = body();
+  if (rc) cudaStreamSynchronize(x->stream);
+  release(cat, x);
+  return rc;
+}
+
+int skyopt_solve_tables(SkyoptCatalog *cat, const double *values, const int32_t *clouds,
+                        const int64_t *task_offsets, const SkyoptTask *tasks, int n_tasks,
+                        const int32_t *parents, int n_parents, const double *tariffs,
+                        int n_tariffs, const SkyoptDag *dags, int n_dags,
+                        int32_t *chosen_index, SkyoptDagResult *results) {
+  if (!cat || !values || !clouds || !task_offsets || !tasks || !dags || !chosen_index || !results ||
+      n_tasks <= 0 || n_dags <= 0)
+    return fail(SKYOPT_EINVAL, "bad arguments");
+  const int C = cat->dev.n_clouds;
+  SkyoptProblem pb{};
+  pb.tasks = tasks; pb.n_tasks = n_tasks; pb.parents = parents; pb.n_parents = n_parents;
+  pb.tariffs = tariffs; pb.n_tariffs = n_tariffs; pb.dags = dags; pb.n_dags = n_dags;
+  // reuse the structural checks (slot ranges are irrelevant here)
+  std::vector<SkyoptTask> tk(tasks, tasks + n_tasks);
+  for (auto &t : tk) { t.slot_begin = 0; t.slot_end = 0; }
+  pb.tasks = tk.data();
+  int rc = validate_problem(cat, &pb);
+  if (rc) return rc;
+  const int64_t total = task_offsets[n_tasks];
+  if (task_offsets[0] != 0 || total < 0) return fail(SKYOPT_EINVAL, "bad task_offsets");
+  for (int t = 0; t < n_tasks; ++t)
+    if (task_offsets[t + 1] < task_offsets[t]) return fail(SKYOPT_EINVAL, "bad task_offsets");
+  for (int64_t i = 0; i < total; ++i)
+    if (clouds[i] < 0 || clouds[i] >= C) return fail(SKYOPT_EINVAL, "candidate %lld: bad cloud", (long long)i);
+  CU(cudaSetDevice(cat->device));
+  Ctx *x = nullptr;
+  if ((rc = acquire(cat, &x))) return rc;
+  auto body = [&]() -> int {
+    Carver sizing(nullptr);
+    auto carve = [&](Carver &c, double *&d_val, int32_t *&d_cl, int64_t *&d_off, SkyoptTask *&d_tasks,
+                     int32_t *&d_par, double *&d_tar, SkyoptDag *&d_dags, int32_t *&d_tn,
+                     double *&d_dp, int32_t *&d_back, int32_t *&d_idx, SkyoptDagResult *&d_res) {
+      d_val = c.take<double>(total); d_cl = c.take<int32_t>(total);
+      d_off = c.take<int64_t>(n_tasks + 1); d_tasks = c.take<SkyoptTask>(n_tasks);
+      d_par = c.take<int32_t>(n_parents); d_tar = c.take<double>(n_tariffs);
+      d_dags = c.take<SkyoptDag>(n_dags); d_tn = c.take<int32_t>(n_tasks);
+      d_dp = c.take<double>(total); d_back = c.take<int32_t>(total);
+      d_idx = c.take<int32_t>(n_tasks); d_res = c.take<SkyoptDagResult>(n_dags);
+    };
+    double *v, *tar, *dp; int32_t *cl, *par, *tn, *back, *idx; int64_t *off;
+    SkyoptTask *dt; SkyoptDag *dd; SkyoptDagResult *res;
+    carve(sizing, v, cl, off, dt, par, tar, dd, tn, dp, back, idx, res);
+    int r = ensure(x, align_up(sizing.off), 256);
+    if (r) return r;
+    Carver d(x->dbuf);
+    carve(d, v, cl, off, dt, par, tar, dd, tn, dp, back, idx, res);
+    cudaStream_t st = x->stream;
+    std::vector<int32_t> counts(n_tasks);
+    for (int t = 0; t < n_tasks; ++t) counts[t] = (int32_t)(task_offsets[t + 1] - task_offsets[t]);
+    CU(cudaMemcpyAsync(v, values, sizeof(double) * total, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cl, clouds, sizeof(int32_t) * total, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(off, task_offsets, sizeof(int64_t) * (n_tasks + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dt, tk.data(), sizeof(SkyoptTask) * n_tasks, cudaMemcpyHostToDevice, st));
+    if (n_parents) CU(cudaMemcpyAsync(par, parents, sizeof(int32_t) * n_parents, cudaMemcpyHostToDevice, st));
+    if (n_tariffs) CU(cudaMemcpyAsync(tar, tariffs, sizeof(double) * n_tariffs, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dd, dags, sizeof(SkyoptDag) * n_dags, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(tn, counts.data(), sizeof(int32_t) * n_tasks, cudaMemcpyHostToDevice, st));
+    SolveIn in{nullptr, dt, par, tar, nullptr, dd, nullptr, off, ExpandOut{}, 1};
+    SolveWork w{nullptr, nullptr, cl, nullptr, v, dp, back};
+    SolveOut out{nullptr, idx, tn, res};
+    solve_kernel<<<n_dags, kSolveThreads, 0, st>>>(cat->dev, in, w, out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(chosen_index, idx, sizeof(int32_t) * n_tasks, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(results, res, sizeof(SkyoptDagResult) * n_dags, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int d2 = 0; d2 < n_dags; ++d2)
+      if (results[d2].status != 0)
+        for (int t = dags[d2].task_begin; t < dags[d2].task_end; ++t) chosen_index[t] = -1;
+    return 0;
   };
   rc = body();
   if (rc) cudaStreamSynchronize(x->stream);

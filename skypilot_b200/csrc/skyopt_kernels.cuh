@@ -1008,6 +1008,7 @@ struct SolveIn {
   const int64_t *slot_off;   // [n_slots] into the expand candidate buffers
   const int64_t *task_off;   // [n_tasks+1] into the task candidate arrays
   ExpandOut ex;
+  int tables_only;           // candidates were given by the caller: no slots
 };
 
 struct SolveWork {
@@ -1475,6 +1476,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   }
 plan_records:
   __syncthreads();
+  if (in.tables_only) return;
   // ---- the plan as candidate records
   for (int lt = tid; lt < T; lt += kSolveThreads) {
     const int t = D.task_begin + lt;

@@ -549,3 +549,60 @@ def scan(builder: ProblemBuilder,
                         fuzzy_cap, ctypes.byref(stats)))
     return ScanOutput(results, list_ids, list_prices, fuzzy_keys,
                       fuzzy_prices, stats)
+
+
+def solve_tables(store: CatalogStore, values: Sequence[Sequence[float]],
+                 clouds: Sequence[Sequence[int]],
+                 parents: Sequence[Sequence[int]],
+                 edge_tariffs: Sequence[Sequence[Sequence[float]]],
+                 src_tariffs: Sequence[Optional[Sequence[float]]],
+                 is_chain: bool, minimize_cost: bool,
+                 device: int = 0) -> Tuple[List[int], float, int]:
+    """`skyopt_solve_tables`: chain DP / exact DAG search on candidate tables
+    the caller supplies (one DAG). Returns (chosen index per task, objective,
+    status)."""
+    n_tasks = len(values)
+    n_clouds = len(store.clouds)
+    offsets = np.zeros(n_tasks + 1, dtype=np.int64)
+    for t, v in enumerate(values):
+        offsets[t + 1] = offsets[t] + len(v)
+    flat_v = np.ascontiguousarray(
+        np.concatenate([np.asarray(v, dtype=np.float64) for v in values])
+        if offsets[-1] else np.zeros(1))
+    flat_c = np.ascontiguousarray(
+        np.concatenate([np.asarray(c, dtype=np.int32) for c in clouds])
+        if offsets[-1] else np.zeros(1, dtype=np.int32))
+    tasks = np.zeros(n_tasks, dtype=_native.TASK_DTYPE)
+    par: List[int] = []
+    tar: List[float] = []
+    for t in range(n_tasks):
+        tasks['n_parents'][t] = len(parents[t])
+        tasks['parent_begin'][t] = len(par)
+        tasks['edge_tariff_begin'][t] = len(tar)
+        tasks['src_tariff_begin'][t] = -1
+        par.extend(int(p) for p in parents[t])
+        for row in edge_tariffs[t]:
+            assert len(row) == n_clouds
+            tar.extend(float(x) for x in row)
+        if src_tariffs[t] is not None:
+            tasks['src_tariff_begin'][t] = len(tar)
+            tar.extend(float(x) for x in src_tariffs[t])
+    par_a = np.asarray(par or [0], dtype=np.int32)
+    tar_a = np.asarray(tar or [0.0], dtype=np.float64)
+    dags = np.zeros(1, dtype=_native.DAG_DTYPE)
+    dags['task_end'] = n_tasks
+    dags['is_chain'] = int(is_chain)
+    dags['minimize_cost'] = int(minimize_cost)
+    chosen = np.zeros(n_tasks, dtype=np.int32)
+    results = np.zeros(1, dtype=_native.DAG_RESULT_DTYPE)
+    lib = _native.load()
+    _native.check(
+        lib.skyopt_solve_tables(store.handle(device), flat_v.ctypes.data,
+                                flat_c.ctypes.data, offsets.ctypes.data,
+                                tasks.ctypes.data, n_tasks,
+                                par_a.ctypes.data, len(par),
+                                tar_a.ctypes.data, len(tar),
+                                dags.ctypes.data, 1, chosen.ctypes.data,
+                                results.ctypes.data))
+    return ([int(i) for i in chosen], float(results['objective'][0]),
+            int(results['status'][0]))

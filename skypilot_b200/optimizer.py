@@ -490,6 +490,90 @@ class Optimizer:
             choice.setdefault(task, task.resources[-1])
         return choice
 
+    # ------------------------------------------------ stand-alone DP / DAG search
+    @staticmethod
+    def _solve_cost_map(graph, topo_order, node_to_cost_map, minimize_cost,
+                        is_chain):
+        """Shared body of _optimize_by_dp / _optimize_by_ilp: the candidate
+        tables of the reference's `node_to_cost_map` go to the device as they
+        are (values in dictionary order + the candidate's cloud), the egress
+        tariffs as per-edge scalars; the DP / exact search runs in
+        solve_kernel (skyopt_solve_tables)."""
+        store = catalog.get_store()
+        cloud_objs = [_cloud_object(t.name) for t in store.clouds]
+        n_clouds = len(cloud_objs)
+        real = [t for t in topo_order if not _is_dummy(t)]
+        index = {t: i for i, t in enumerate(real)}
+        values, cl, parents, edge_rows, src_rows, keys = [], [], [], [], [], []
+        for task in real:
+            table = node_to_cost_map[task]
+            keys.append(list(table.keys()))
+            values.append([float(v) for v in table.values()])
+            row = []
+            for r in table.keys():
+                name = r.cloud.canonical_name()
+                if not store.has_cloud(name):
+                    raise ValueError(f'{r.cloud} is not in the loaded catalog')
+                row.append(store.cloud_index[name])
+            cl.append(row)
+            preds = [p for p in graph.predecessors(task) if not _is_dummy(p)]
+            parents.append([index[p] for p in preds])
+            rows = []
+            for p in preds:
+                nbytes = p.get_estimated_outputs_size_gigabytes()
+                if not nbytes:
+                    rows.append([0.0] * n_clouds)
+                elif minimize_cost:
+                    rows.append([float(c.get_egress_cost(num_gigabytes=nbytes))
+                                 for c in cloud_objs])
+                else:
+                    rows.append([nbytes * 8 / 10] * n_clouds)
+            edge_rows.append(rows)
+            src = None
+            if not preds and task.get_inputs() is not None:
+                nbytes = task.get_estimated_inputs_size_gigabytes()
+                if nbytes:
+                    src_cloud = task.get_inputs_cloud()
+                    fn = (Optimizer._egress_cost
+                          if minimize_cost else Optimizer._egress_time)
+                    src = [float(fn(src_cloud, c, nbytes)) for c in cloud_objs]
+            src_rows.append(src)
+        chosen, objective, status = engine.solve_tables(
+            store, values, cl, parents, edge_rows, src_rows, is_chain,
+            minimize_cost, device=catalog.get_device())
+        if status != 0:
+            raise exceptions.ResourcesUnavailableError(
+                'No launchable resource found, or the DAG is too large for '
+                'the exact general-DAG search (16 tasks / 2^36 assignments).')
+        best_plan = {}
+        for task, idx, ks in zip(real, chosen, keys):
+            task.best_resources = ks[idx]
+            best_plan[task] = ks[idx]
+        for t in topo_order:
+            if _is_dummy(t):
+                t.best_resources = list(t.resources)[0]
+                best_plan[t] = t.best_resources
+        return best_plan, objective
+
+    @staticmethod
+    def _optimize_by_dp(topo_order, node_to_cost_map, minimize_cost=True):
+        """Chain DP on a given cost map (sky/optimizer.py:429-487)."""
+        graph = nx.DiGraph()
+        graph.add_nodes_from(topo_order)
+        for a, b in zip(topo_order[:-1], topo_order[1:]):
+            graph.add_edge(a, b)
+        return Optimizer._solve_cost_map(graph, topo_order, node_to_cost_map,
+                                         minimize_cost, True)
+
+    @staticmethod
+    def _optimize_by_ilp(graph, topo_order, node_to_cost_map,
+                         minimize_cost=True):
+        """General DAGs (sky/optimizer.py:490-637): the reference builds a
+        0/1 ILP and calls CBC; here the exact optimum of the same objective
+        comes from an exhaustive search on the device."""
+        return Optimizer._solve_cost_map(graph, topo_order, node_to_cost_map,
+                                         minimize_cost, False)
+
     # --------------------------------------------- object-level reference API
     @staticmethod
     def _estimate_nodes_cost_or_time(
