@@ -172,8 +172,12 @@ def bench_reference(args, workload, scenario, n_candidates):
         'config': {'workload': f'{args.workload}: {workload["desc"]}',
                    'catalog': spec},
         'cpu_baseline': {
-            'value': value, 'unit': 'candidates/s', 'cores': 1,
-            'kind': 'port',
+            'value': value, 'unit': 'candidates/s',
+            'cores': 1, 'kind': 'port',
+            'threads': ('single-threaded pandas, like the reference except for '
+                        'its ThreadPool fan-out across clouds, which is slower '
+                        'under the GIL (measured 1.73 s vs 1.54 s per cfg2 step; '
+                        'SKYOPT_ORACLE_THREADS=1 enables it)'),
             'sample': (f'{sample_tasks} of {len(scenario["tasks"])} tasks per '
                        f'step, {args.steps} steps, full catalog')
         },

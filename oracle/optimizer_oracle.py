@@ -373,6 +373,32 @@ def blocked_by(launchable: Dict[str, Any], blocked: Dict[str, Any]) -> bool:
     return launchable['use_spot'] == blocked['use_spot']
 
 
+def parallel_threads() -> int:
+    """get_parallel_threads (utils/subprocess_utils.py:100-109)."""
+    import os  # pylint: disable=import-outside-toplevel
+    return max(4, (os.cpu_count() or 1) - 1)
+
+
+_pool = None
+
+
+def _run_in_parallel(fn, args):
+    """run_in_parallel (utils/subprocess_utils.py:112-141): ordered map over
+    a thread pool; a single argument runs inline."""
+    global _pool
+    import os  # pylint: disable=import-outside-toplevel
+    args = list(args)
+    # Measured here (8 vCPU, cfg2): the thread pool is ~12 % SLOWER than the
+    # plain loop (pandas holds the GIL), so the baseline uses the loop unless
+    # SKYOPT_ORACLE_THREADS=1 asks for the reference's exact structure.
+    if len(args) <= 1 or os.environ.get('SKYOPT_ORACLE_THREADS') != '1':
+        return [fn(a) for a in args]
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor  # pylint: disable=import-outside-toplevel
+        _pool = ThreadPoolExecutor(max_workers=parallel_threads())
+    return list(_pool.map(fn, args))
+
+
 def fill_in_launchable(cat: Catalog, task: Dict[str, Any],
                        blocked: List[Dict[str, Any]]):
     """_fill_in_launchable_resources -> ([(request, [launchables])], fuzzy)."""
@@ -384,8 +410,12 @@ def fill_in_launchable(cat: Catalog, task: Dict[str, Any],
             out.append((req, []))
             continue
         clouds = [req['cloud']] if req['cloud'] is not None else cat.enabled
-        for cloud in clouds:
-            options, fuzzy = feasible(cat, cloud, req, task['num_nodes'])
+        # the reference fans the clouds out over a thread pool
+        # (sky/optimizer.py:1712-1715, utils/subprocess_utils.py:100-141)
+        results = _run_in_parallel(
+            lambda cloud, r=req, n=task['num_nodes']: feasible(cat, cloud, r, n),
+            clouds)
+        for cloud, (options, fuzzy) in zip(clouds, results):
             if options:
                 launch.extend(make_launchables(cat, options[0]))
             else:
