@@ -8,8 +8,12 @@ vector is scored against every catalog row (filter + argmin), the winners are
 expanded to region/zone candidates and costed, and the chain DP picks the
 plan. Workloads (BASELINE.json `configs`):
 
-  cfg2  8-task chain DAG, synthetic multi-cloud catalog (~50k rows)   [default]
-  cfg4  32-task chain DAG, synthetic 1M-row catalog (HBM stress)
+  cfg4  32-task chain DAG, synthetic 1M-row catalog -- the configuration the
+        throughput / HBM-roofline target is quoted on (BASELINE.md section 4,
+        item 4; BASELINE.json configs[3])                             [default]
+  cfg2  8-task chain DAG, synthetic multi-cloud catalog (~50k rows) -- the
+        optimize() p50 latency configuration (configs[1]); measured in the
+        same run and reported under "latency_cfg2"
 
 `value`  = candidates / s with everything resident in HBM (CUDA events around
            the kernels; L2 is flushed by writing 192 MB before every step);
@@ -76,6 +80,18 @@ def measured_peaks():
             peaks = json.load(f)
         return float(peaks['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def measured_traffic(workload_name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch, from
+    the committed ncu capture (profiles/round1_traffic.json); None if the
+    capture does not cover this workload."""
+    path = os.path.join(_REPO, 'profiles', 'round1_traffic.json')
+    try:
+        with open(path, encoding='utf-8') as f:
+            return json.load(f)[workload_name]['traffic']
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -192,12 +208,12 @@ def main():
     parser.add_argument('--gpus', type=int, default=1)
     parser.add_argument('--steps', type=int, default=30)
     parser.add_argument('--warmup', type=int, default=5)
-    parser.add_argument('--workload', default='cfg2', choices=list(WORKLOADS))
+    parser.add_argument('--workload', default='cfg4', choices=list(WORKLOADS))
     parser.add_argument('--impl', default='ours',
                         choices=['ours', 'reference'])
     parser.add_argument('--cpu-baseline-steps', type=int, default=5)
-    parser.add_argument('--no-stress', action='store_true',
-                        help='skip the extra cfg4 (1M rows x 32 tasks) run')
+    parser.add_argument('--no-latency', action='store_true',
+                        help='skip the extra cfg2 (optimize() p50) run')
     parser.add_argument('--scan-mode', default='auto',
                         choices=['auto', 'tile', 'stream', 'stream3'],
                         help='scan kernel variant (tuning / tests)')
@@ -360,13 +376,14 @@ def main():
 
     line, scenario, n_candidates = measure(args.workload)
     workload = WORKLOADS[args.workload]
-    if args.workload != 'cfg4' and not args.no_stress:
-        # HBM-stress configuration next to the latency configuration
-        stress, _, _ = measure('cfg4')
-        line['hbm_stress'] = {
-            k: stress[k] for k in ('value', 'unit', 'ms_per_step', 'e2e',
-                                   'roofline', 'phases_ms', 'config',
-                                   'optimize_p50_ms')
+    if args.workload != 'cfg2' and not args.no_latency:
+        # the latency configuration (BASELINE.json configs[1]) next to the
+        # throughput / roofline configuration
+        lat, _, _ = measure('cfg2')
+        line['latency_cfg2'] = {
+            k: lat[k] for k in ('value', 'unit', 'ms_per_step', 'e2e',
+                                'roofline', 'phases_ms', 'config',
+                                'optimize_p50_ms', 'optimize_p90_ms')
         }
     if rank == 0 and world == 1:
         # ---- CPU baseline: the pandas oracle on a bounded sample

@@ -325,7 +325,11 @@ class Cloud:
         from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
         store = builder.store
         cache = store.__dict__.setdefault('_plan_cache', {})
-        key = (self.__class__, num_nodes > 1, self._request_key(resources))
+        rkey = resources.__dict__.get('_request_key')
+        if rkey is None:
+            rkey = self._request_key(resources)
+            resources.__dict__['_request_key'] = rkey
+        key = (self.__class__, num_nodes > 1, rkey)
         tmpl = cache.get(key)
         if tmpl is None:
             plan = SlotPlan()
@@ -338,14 +342,15 @@ class Cloud:
         plan, recorder = tmpl
         if plan.slot is None:
             return plan
-        qmap = [builder.replay_query(recorder, i)
-                for i in range(len(recorder.queries))]
+        qbase = builder.n_queries
+        for i in range(recorder.n_queries):
+            builder.replay_query(recorder, i)
         out = SlotPlan()
         out.__dict__.update(plan.__dict__)
-        out.slot = builder.replay_slot(recorder, plan.slot, qmap)
+        out.slot = builder.replay_slot(recorder, plan.slot, qbase)
         for name in ('list_query', 'fuzzy_query', 'gate_query'):
             v = getattr(plan, name)
-            setattr(out, name, None if v is None else qmap[v])
+            setattr(out, name, None if v is None else qbase + v)
         return out
 
     def plan_feasible(self, builder, resources: Any,

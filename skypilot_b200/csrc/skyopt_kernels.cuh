@@ -729,6 +729,29 @@ __device__ __forceinline__ void bitonic_sort2(uint64_t *k1, uint64_t *k2, int n)
   __syncthreads();
 }
 
+// Sort the first `n` (k1, k2) pairs (keys unique; entries >= n hold the
+// "none" key). Small inputs -- the usual case: one instance type's rows -- are
+// ranked by counting (each element counts the smaller ones: n broadcast reads,
+// no barriers in the loop); larger ones fall back to the bitonic network.
+constexpr int kCountSortMax = 256;
+__device__ __forceinline__ void sort_pairs(uint64_t *k1, uint64_t *k2, uint64_t *t1,
+                                           uint64_t *t2, int n, int sort_n) {
+  if (n > kCountSortMax) { bitonic_sort2(k1, k2, sort_n); return; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t a1 = k1[i], a2 = k2[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const uint64_t b1 = k1[j], b2 = k2[j];
+      rank += (b1 < a1) || (b1 == a1 && b2 < a2);
+    }
+    t1[rank] = a1; t2[rank] = a2;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { k1[i] = t1[i]; k2[i] = t2[i]; }
+  __syncthreads();
+}
+
 // Sorted tables of skyopt_scan: block per (query, kind). kind 0 = instance
 // types by min price (common.py:692-693), kind 1 = fuzzy accelerator keys by
 // min Price (common.py:665-667).
@@ -831,6 +854,7 @@ __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
   double *bprice = reinterpret_cast<double *>(k2 + sort_n);  // [max_zones]
   int32_t *first_pos = reinterpret_cast<int32_t *>(bprice + max_zones);  // [max_regions]
   __shared__ int s_n;
+  __shared__ uint64_t s_t1[kCountSortMax], s_t2[kCountSortMax];  // counting-sort scratch
 
   const int s = blockIdx.x;
   const SkyoptSlot S = slots[s];
@@ -921,7 +945,7 @@ __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
   const int n = s_n;
   // sort_values([price, Region, AvailabilityZone]) -- ids are ranks in string
   // order, the row id keeps equal keys in CSV order.
-  bitonic_sort2(k1, k2, sort_n);
+  sort_pairs(k1, k2, s_t1, s_t2, n, sort_n);
   for (int i = tid; i < n; i += blockDim.x) {
     const int rg = (int)(k2[i] >> 48);
     atomicMin(&first_pos[rg], i);
@@ -955,9 +979,11 @@ __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
       }
     }
     k1[i] = key;
-    k2[i] = payload;
+    // filtered-out entries keep distinct (none, i) pairs: the counting sort
+    // needs unique keys
+    k2[i] = (key == kKeyNone && i < n) ? (uint64_t)i : payload;
   }
-  bitonic_sort2(k1, k2, sort_n);
+  sort_pairs(k1, k2, s_t1, s_t2, n, sort_n);
 
   const int64_t off = slot_off[s];
   int count = 0;
@@ -1153,11 +1179,16 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   if (tid == 0) s_fail = -1;
   __syncthreads();
 
-  // ---- Phase A ran in gather_kernel: candidate tables are ready.
-  if (tid == 0) {
-    for (int t = D.task_begin; t < D.task_end; ++t)
-      if (out.task_n[t] == 0) { s_fail = t - D.task_begin; break; }
-  }
+  // ---- Phase A ran in gather_kernel: candidate tables are ready. First
+  // task without a candidate (all tasks are checked at once: a serial scan
+  // would be one dependent memory round trip per task).
+  __shared__ int s_first_empty;
+  if (tid == 0) s_first_empty = 0x7FFFFFFF;
+  __syncthreads();
+  for (int lt = tid; lt < T; lt += kSolveThreads)
+    if (out.task_n[D.task_begin + lt] == 0) atomicMin(&s_first_empty, lt);
+  __syncthreads();
+  if (tid == 0 && s_first_empty != 0x7FFFFFFF) s_fail = s_first_empty;
   __syncthreads();
   if (s_fail >= 0) {
     if (tid == 0) {
@@ -1206,16 +1237,26 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
       }
       __syncthreads();
       int cur = 0;
-      for (int lt = 0; lt < T; ++lt) {
+      constexpr int kPer = kDpCap / kSolveThreads;
+      // The next task's values / clouds are fetched while the current task
+      // is reduced (software pipelining over the dependent chain of tasks).
+      double vn[kPer]; int cn[kPer];
+      auto fetch = [&](int lt) {
         const int n = s_tn[lt];
         const long long toff = s_toff[lt];
-        constexpr int kPer = kDpCap / kSolveThreads;
-        double v[kPer]; int c4[kPer];
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
           const int c = tid + k * kSolveThreads;
-          if (c < n) { v[k] = w.tc_value[toff + c]; c4[k] = w.tc_cloud[toff + c]; }
+          if (c < n) { vn[k] = w.tc_value[toff + c]; cn[k] = w.tc_cloud[toff + c]; }
         }
+      };
+      fetch(0);
+      for (int lt = 0; lt < T; ++lt) {
+        const int n = s_tn[lt];
+        double v[kPer]; int c4[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) { v[k] = vn[k]; c4[k] = cn[k]; }
+        if (lt + 1 < T) fetch(lt + 1);
         if (s_np[lt] == 0) {
           if (tid < C) {
             // parent = dummy source: 0 + egress from the inputs' cloud

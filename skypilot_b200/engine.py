@@ -120,67 +120,100 @@ def format_fuzzy(store: CatalogStore, keys: Sequence[int]) -> List[str]:
     return out
 
 
+def set_id(store: CatalogStore, key: bytes) -> int:
+    """Store-wide id of an accelerator-key bitmask (registered on first use;
+    the table is tiny: a few dozen 128-byte sets per catalog)."""
+    reg = store.__dict__.setdefault('_set_registry', {})
+    idx = reg.get(key)
+    if idx is None:
+        idx = len(reg)
+        reg[key] = idx
+        store.__dict__.pop('_set_table', None)
+    return idx
+
+
+def set_table(store: CatalogStore) -> np.ndarray:
+    table = store.__dict__.get('_set_table')
+    if table is None:
+        reg = store.__dict__.get('_set_registry', {})
+        table = np.frombuffer(b''.join(reg.keys()), dtype=np.uint32).copy() if (
+            reg) else np.zeros(0, dtype=np.uint32)
+        store.__dict__['_set_table'] = table
+    return table
+
+
 class ProblemBuilder:
-    """Accumulates one batch for the device."""
+    """Accumulates one batch for the device.
+
+    Queries and slots are kept as packed records (bytes of the C structs), so
+    that replaying a cached plan (Cloud.plan_cached) is a list append and
+    `pack()` is one `b''.join` per table instead of a Python loop per field.
+    Accelerator-key sets are registered once per catalog store and referenced
+    by a store-wide id.
+    """
 
     def __init__(self, store: CatalogStore):
         self.store = store
-        self.queries: List[Dict[str, Any]] = []
-        self._sets: List[bytes] = []
-        self._set_index: Dict[bytes, int] = {}
-        self.slots: List[Dict[str, Any]] = []
+        self.query_recs: List[bytes] = []
+        self.slot_recs: List[bytes] = []
+        self.slot_qbase: List[int] = []
+        self.slot_cost: List[Optional[Tuple[float, float, float]]] = []
         self.tasks: List[Dict[str, Any]] = []
         self.parents: List[int] = []
         self.tariffs: List[float] = []
         self.blocked: List[Dict[str, int]] = []
         self.dags: List[Dict[str, int]] = []
 
+    @property
+    def n_queries(self) -> int:
+        return len(self.query_recs)
+
+    @property
+    def n_slots(self) -> int:
+        return len(self.slot_recs)
+
     # -- sets / queries -----------------------------------------------------
     def add_set(self, words: Optional[np.ndarray]) -> int:
         if words is None:
             return -1
-        key = np.ascontiguousarray(words, dtype=np.uint32).tobytes()
-        idx = self._set_index.get(key)
-        if idx is None:
-            idx = len(self._sets)
-            self._sets.append(key)
-            self._set_index[key] = idx
-        return idx
+        return set_id(self.store,
+                      np.ascontiguousarray(words, dtype=np.uint32).tobytes())
 
-    def _add_set_bytes(self, key: bytes) -> int:
-        idx = self._set_index.get(key)
-        if idx is None:
-            idx = len(self._sets)
-            self._sets.append(key)
-            self._set_index[key] = idx
-        return idx
+    @staticmethod
+    def _record(fields: Dict[str, Any], dtype: np.dtype) -> bytes:
+        rec = np.zeros(1, dtype=dtype)
+        for name in dtype.names:
+            if name == 'pad_':
+                continue
+            default = -1 if name in ('acc_set', 'fuzzy_set', 'region_id',
+                                     'zone_id') else 0
+            rec[name][0] = fields.get(name, default)
+        return rec.tobytes()
 
     def replay_query(self, recorder: 'ProblemBuilder', i: int) -> int:
         """Copies query `i` of a recorded plan (Cloud.plan_cached)."""
-        q = dict(recorder.queries[i])
-        for name in ('acc_set', 'fuzzy_set'):
-            if q[name] >= 0:
-                q[name] = self._add_set_bytes(recorder._sets[q[name]])  # pylint: disable=protected-access
-        self.queries.append(q)
-        return len(self.queries) - 1
+        self.query_recs.append(recorder.query_recs[i])
+        return len(self.query_recs) - 1
 
     def replay_slot(self, recorder: 'ProblemBuilder', i: int,
-                    qmap: List[int]) -> int:
-        slot = dict(recorder.slots[i])
-        for name in ('query', 'gate_query'):
-            if slot[name] >= 0:
-                slot[name] = qmap[slot[name]]
-        if slot['acc_set'] >= 0:
-            slot['acc_set'] = self._add_set_bytes(recorder._sets[slot['acc_set']])  # pylint: disable=protected-access
-        self.slots.append(slot)
-        return len(self.slots) - 1
+                    qbase: int) -> int:
+        """Copies slot `i` of a recorded plan whose queries were replayed
+        starting at index `qbase`."""
+        self.slot_recs.append(recorder.slot_recs[i])
+        self.slot_qbase.append(qbase)
+        self.slot_cost.append(None)
+        return len(self.slot_recs) - 1
+
+    def set_slot_cost(self, slot: int, hours: float, node_mult: float,
+                      time_value: float) -> None:
+        self.slot_cost[slot] = (hours, node_mult, time_value)
 
     def add_query(self, spec: Dict[str, Any]) -> int:
         q = dict(spec)
         q['acc_set'] = self.add_set(q.pop('acc_words', None))
         q['fuzzy_set'] = self.add_set(q.pop('fuzzy_words', None))
-        self.queries.append(q)
-        return len(self.queries) - 1
+        self.query_recs.append(self._record(q, _native.QUERY_DTYPE))
+        return len(self.query_recs) - 1
 
     def cpus_mem_query(self,
                        cloud: str,
@@ -270,8 +303,10 @@ class ProblemBuilder:
         slot.update(fields)
         if words is not None:
             slot['acc_set'] = self.add_set(words)
-        self.slots.append(slot)
-        return len(self.slots) - 1
+        self.slot_recs.append(self._record(slot, _native.SLOT_DTYPE))
+        self.slot_qbase.append(0)
+        self.slot_cost.append(None)
+        return len(self.slot_recs) - 1
 
     def add_task(self,
                  slot_begin: int,
@@ -352,14 +387,34 @@ class PackedProblem:
 
     def __init__(self, b: ProblemBuilder):
         self.store = b.store
-        self.queries = ProblemBuilder._pack(b.queries, _native.QUERY_DTYPE)
-        self.n_queries = len(b.queries)
-        self.n_sets = len(b._sets)  # pylint: disable=protected-access
-        self.acc_sets = np.frombuffer(
-            b''.join(b._sets) or bytes(4 * _native.ACC_SET_WORDS),  # pylint: disable=protected-access
-            dtype=np.uint32).copy()
-        self.slots = ProblemBuilder._pack(b.slots, _native.SLOT_DTYPE)
-        self.n_slots = len(b.slots)
+        self.n_queries = b.n_queries
+        self.queries = (np.frombuffer(b''.join(b.query_recs),
+                                      dtype=_native.QUERY_DTYPE)
+                        if b.query_recs else np.zeros(
+                            1, dtype=_native.QUERY_DTYPE))
+        sets = set_table(b.store)
+        self.n_sets = len(sets) // _native.ACC_SET_WORDS
+        self.acc_sets = sets if len(sets) else np.zeros(
+            _native.ACC_SET_WORDS, dtype=np.uint32)
+        self.n_slots = b.n_slots
+        if b.slot_recs:
+            slots = np.frombuffer(b''.join(b.slot_recs),
+                                  dtype=_native.SLOT_DTYPE).copy()
+            qbase = np.asarray(b.slot_qbase, dtype=np.int32)
+            if qbase.any():
+                for name in ('query', 'gate_query'):
+                    col = slots[name]
+                    slots[name] = np.where(col >= 0, col + qbase, col)
+            costed = [i for i, c in enumerate(b.slot_cost) if c is not None]
+            if costed:
+                cost = np.asarray([b.slot_cost[i] for i in costed],
+                                  dtype=np.float64)
+                slots['hours'][costed] = cost[:, 0]
+                slots['node_mult'][costed] = cost[:, 1]
+                slots['time_value'][costed] = cost[:, 2]
+            self.slots = slots
+        else:
+            self.slots = np.zeros(1, dtype=_native.SLOT_DTYPE)
         self.tasks = ProblemBuilder._pack(b.tasks, _native.TASK_DTYPE)
         self.n_tasks = len(b.tasks)
         self.parents = np.asarray(b.parents or [0], dtype=np.int32)

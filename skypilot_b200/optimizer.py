@@ -235,25 +235,29 @@ class Optimizer:
         problems: Dict[int, _Problem] = {}
         builders = [engine.ProblemBuilder(store) for _ in devices]
         first_task: Dict[int, int] = {}
+        enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+            raise_if_no_cloud_access=True)
         for shard, b in zip(shards, builders):
             for i in shard:
                 dag = dags[i]
-                _check_specified_clouds(dag)
+                _check_specified_clouds(dag, enabled)
                 choice = Optimizer._resolve_ordered_resources(dag, blocked)
                 saved = {t: t.resources for t in choice}
                 for t, c in choice.items():
                     t.resources = {c}
-                Optimizer._add_dummy_source_sink_nodes(dag)
                 try:
+                    # The dummy source / sink of the single-DAG path only
+                    # matter to the reference's Python DP; the device problem
+                    # is stated on the real tasks (a DAG is a chain with the
+                    # dummies attached iff it is one without them).
                     graph = dag.get_graph()
-                    topo = [t for t in nx.topological_sort(graph)
-                            if not _is_dummy(t)]
+                    topo = (list(dag.tasks) if len(dag.tasks) == 1 else list(
+                        nx.topological_sort(graph)))
                     first_task[i] = len(b.tasks)
                     problems[i] = Optimizer._state_problem(
                         graph, topo, minimize_cost, blocked, dag.is_chain(),
-                        builder=b)
+                        builder=b, enabled=enabled)
                 finally:
-                    Optimizer._remove_dummy_source_sink_nodes(dag)
                     for t, original in saved.items():
                         t.resources = original
         solutions: List[Optional[engine.Solution]] = [None] * len(devices)
@@ -315,21 +319,23 @@ class Optimizer:
                        minimize_cost: bool,
                        blocked_resources,
                        is_chain: bool,
-                       builder: Optional[engine.ProblemBuilder] = None
+                       builder: Optional[engine.ProblemBuilder] = None,
+                       enabled: Optional[List[clouds.Cloud]] = None
                       ) -> _Problem:
         """States all real tasks of one DAG for the device."""
-        enabled = sky_check.get_cached_enabled_clouds_or_refresh(
-            raise_if_no_cloud_access=True)
+        if enabled is None:
+            enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+                raise_if_no_cloud_access=True)
         store = catalog.get_store()
         b = builder if builder is not None else engine.ProblemBuilder(store)
         n_clouds = len(store.clouds)
         cloud_objs = [_cloud_object(t.name) for t in store.clouds]
-        slot_info: List[_SlotInfo] = [None] * len(b.slots)  # type: ignore
+        slot_info: List[_SlotInfo] = [None] * b.n_slots  # type: ignore
         hints: Dict[Any, Dict[Any, str]] = collections.defaultdict(dict)
         local_index = {t: i for i, t in enumerate(topo_real)}
         task_begin = len(b.tasks)
         for task in topo_real:
-            slot_begin = len(b.slots)
+            slot_begin = b.n_slots
             n_res = len(list(task.resources))
             for res in task.resources:
                 if res.__dict__.get('_validated_store') is not store:
@@ -349,14 +355,13 @@ class Optimizer:
                         hints[res][cloud] = plan.hint
                     if plan.slot is None:
                         continue
-                    slot = b.slots[plan.slot]
-                    slot['hours'] = runtime / 3600
-                    slot['node_mult'] = float(max(task.num_nodes, 0))
-                    slot['time_value'] = float(runtime)
+                    b.set_slot_cost(plan.slot, runtime / 3600,
+                                    float(max(task.num_nodes, 0)),
+                                    float(runtime))
                     slot_info.append(
                         _SlotInfo(task, res, cloud, plan,
                                   store.cloud(cloud.canonical_name())))
-            slot_end = len(b.slots)
+            slot_end = b.n_slots
             parents = [
                 p for p in dag_graph.predecessors(task) if not _is_dummy(p)
             ]
@@ -760,11 +765,12 @@ def _filter_out_blocked_launchable_resources(launchable_resources,
     return available
 
 
-def _check_specified_clouds(dag: 'dag_lib.Dag') -> None:
+def _check_specified_clouds(dag: 'dag_lib.Dag', enabled=None) -> None:
     """A task pinned to a cloud that is not enabled cannot be placed
     (sky/optimizer.py:1541-1607)."""
-    enabled = sky_check.get_cached_enabled_clouds_or_refresh(
-        raise_if_no_cloud_access=True)
+    if enabled is None:
+        enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+            raise_if_no_cloud_access=True)
     for task in dag.tasks:
         specified, disabled = set(), set()
         for resources in task.resources:
