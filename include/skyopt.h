@@ -58,7 +58,8 @@ typedef struct SkyoptZone {
   uint32_t flags_or;   /* OR of the low flag byte over the valid rows */
   uint32_t sig_lo;     /* bit (acc_key % 64) for every valid row's key ... */
   uint32_t sig_hi;     /* ... bits 32..63 */
-  uint32_t pad_;
+  uint32_t groups;     /* bit (group % 32) for every valid row whose flags
+                          high byte (GCP fixed-host group) is non-zero */
   uint64_t min_key[2]; /* cheapest 'Price' / 'SpotPrice' of the valid rows as
                           an order-preserving integer key (see
                           skyopt_price_key); all ones = none */

@@ -1,0 +1,249 @@
+"""TEST INFRASTRUCTURE — CPU restatement of `sky.catalog.list_accelerators`.
+
+Only tests/ may import this module (see oracle/catalog_oracle.py's header).
+
+Follows, in plain Python over the catalog frames:
+  * sky/catalog/common.py:697-790  `list_accelerators_impl`
+  * sky/catalog/gcp_catalog.py:445-571  GCP: host VM per accelerator row,
+    combined price, TPU regrouping
+  * sky/catalog/__init__.py:56-85  merge of the per-cloud dictionaries
+  * sky/catalog/{aws,azure,lambda}_catalog.py `list_accelerators` wrappers
+
+Pinned against tests/golden/accel_*.json (outputs of the unmodified
+reference, oracle/ref_harness/gen_golden.py --listings) by
+tests/test_oracle_listing.py.
+
+One deliberate difference: when GCP's pre-filter leaves no rows the reference
+raises `TypeError` under pandas 3.0 (an empty `Series.apply` result has `str`
+dtype and cannot be divided, common.py:722-725); with the pandas versions the
+reference pins it returns no GCP entries. The restatement returns no entries.
+"""
+import ast
+import math
+import re
+from typing import Dict, List, Optional, Sequence
+
+from oracle import catalog_oracle as co
+
+CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
+                 'lambda': 'Lambda'}
+
+
+def _isnan(x) -> bool:
+    return x is None or (isinstance(x, float) and math.isnan(x))
+
+
+def _norm(x):
+    """Hashable stand-in where NaN equals NaN (pandas' duplicate test)."""
+    return None if _isnan(x) else x
+
+
+def _nan_last(x):
+    return (1, 0.0) if _isnan(x) else (0, x)
+
+
+def _device_memory(gpu_infos: Sequence) -> Optional[List[float]]:
+    """GiB of the first GPU from the AWS-style GpuInfo dict, for all rows or
+    for none (common.py:716-729)."""
+    out = []
+    try:
+        for text in gpu_infos:
+            info = ast.literal_eval(text)
+            out.append(info['Gpus'][0]['MemoryInfo']['SizeInMiB'] / 1024.0)
+    except (ValueError, SyntaxError):
+        return None
+    return out
+
+
+def _contains(pattern: str, text, case_sensitive: bool) -> bool:
+    if _isnan(text):
+        return False
+    return re.search(pattern, text,
+                     0 if case_sensitive else re.IGNORECASE) is not None
+
+
+def _records(df) -> List[dict]:
+    return df.to_dict('records')
+
+
+def listing_impl(cloud: str, rows: List[dict], gpus_only: bool,
+                 name_filter: Optional[str], region_filter: Optional[str],
+                 quantity_filter: Optional[int], case_sensitive: bool,
+                 all_regions: bool) -> Dict[str, List[tuple]]:
+    """`rows`: catalog rows as dicts (CSV order). Returns
+    {accelerator: [(cloud, instance_type, name, count, cpus, device_memory,
+    memory, price, spot_price, region), ...]}."""
+    if gpus_only:
+        rows = [r for r in rows if not _isnan(r.get('GpuInfo'))]
+    if not rows:
+        return {}
+    dev = _device_memory([r.get('GpuInfo') for r in rows])
+    # projection + drop rows without accelerator + exact-duplicate removal
+    seen = set()
+    kept = []
+    for i, r in enumerate(rows):
+        if _isnan(r.get('AcceleratorName')):
+            continue
+        rec = (r.get('InstanceType'), r['AcceleratorName'],
+               r['AcceleratorCount'], r.get('vCPUs'),
+               None if dev is None else dev[i], r.get('MemoryGiB'),
+               r.get('Price'), r.get('SpotPrice'), r.get('Region'))
+        key = tuple(_norm(v) for v in rec)
+        if key in seen:
+            continue
+        seen.add(key)
+        kept.append(rec)
+    if name_filter is not None:
+        kept = [k for k in kept if _contains(name_filter, k[1], case_sensitive)]
+    if region_filter is not None:
+        kept = [k for k in kept
+                if _contains(region_filter, k[8], case_sensitive)]
+    if quantity_filter is not None:
+        kept = [k for k in kept if float(k[2]) == quantity_filter]
+    groups: Dict[str, List[tuple]] = {}
+    for k in kept:
+        groups.setdefault(k[1], []).append(k)
+    out = {}
+    for name in sorted(groups):
+        members = groups[name]
+        # cheapest (Price, SpotPrice[, Region]) first, NaN last, stable
+        if all_regions:
+            members = sorted(members, key=lambda k: (_nan_last(k[6]),
+                                                     _nan_last(k[7]), k[8]))
+        else:
+            members = sorted(members,
+                             key=lambda k: (_nan_last(k[6]), _nan_last(k[7])))
+        first = {}
+        for k in members:
+            ident = (_norm(k[0]), k[1], float(k[2]), _norm(k[3]), _norm(k[5]))
+            if all_regions:
+                ident += (k[8],)
+            first.setdefault(ident, k)
+        infos = [(cloud, k[0], k[1], float(k[2]), k[3], k[4], k[5], k[6],
+                  k[7], k[8]) for k in first.values()]
+        # the reference's final ordering, NaN semantics of tuple comparison
+        # included (common.py:783-787)
+        infos.sort(key=lambda t: (t[3], t[1], 0 if _isnan(t[4]) else t[4],
+                                  t[7], t[8], t[9]))
+        out[name] = infos
+    return out
+
+
+def _gcp_host(vm_rows_by_zone, acc_name: str, count: int, region: str,
+              zone: str) -> Optional[dict]:
+    """Cheapest host VM of the zone for an accelerator row
+    (gcp_catalog.py:460-487); ties -> first CSV row."""
+    cands = vm_rows_by_zone.get((region.lower(), zone.lower()), [])
+    if acc_name in co.GCP_FIXED:
+        allowed = set(co.GCP_FIXED[acc_name][count])
+        cands = [r for r in cands if r['InstanceType'] in allowed]
+    else:
+        table = co.GCP_HOST_CPUS.get(acc_name, co.GCP_HOST_CPUS['DEFAULT'])
+        cpus = table[count]
+        memory = cpus * 4
+        cands = [r for r in cands
+                 if r['InstanceType'].startswith(co.GCP_HOST_FAMILIES) and
+                 r['vCPUs'] >= cpus and r['MemoryGiB'] >= memory]
+    cands = [r for r in cands if not _isnan(r['Price'])]
+    if not cands:
+        return None
+    best = cands[0]
+    for r in cands[1:]:
+        if r['Price'] < best['Price']:
+            best = r
+    return best
+
+
+def gcp_listing(df, gpus_only, name_filter, region_filter, quantity_filter,
+                case_sensitive, all_regions, require_price):
+    rows = _records(df)
+    tpu_rows: List[dict] = []
+    if require_price:
+        acc = [r for r in rows if not _isnan(r['AcceleratorName'])]
+        if gpus_only:
+            acc = [r for r in acc if not _isnan(r['GpuInfo'])]
+        if name_filter is not None:
+            acc = [r for r in acc if _contains(name_filter,
+                                               r['AcceleratorName'],
+                                               case_sensitive)]
+        if region_filter is not None:
+            acc = [r for r in acc
+                   if _contains(region_filter, r['Region'], case_sensitive)]
+        acc = [dict(r, AcceleratorCount=int(r['AcceleratorCount']))
+               for r in acc]
+        if quantity_filter is not None:
+            acc = [r for r in acc if r['AcceleratorCount'] == quantity_filter]
+        tpu_rows = [r for r in acc if r['AcceleratorName'].startswith('tpu-')]
+        gpu_rows = [r for r in acc
+                    if not r['AcceleratorName'].startswith('tpu-')]
+        vm_by_zone: Dict[tuple, List[dict]] = {}
+        for r in rows:
+            if _isnan(r['InstanceType']) or _isnan(r['AvailabilityZone']):
+                continue
+            vm_by_zone.setdefault(
+                (r['Region'].lower(), r['AvailabilityZone'].lower()),
+                []).append(r)
+        merged = []
+        for r in gpu_rows:
+            assert _isnan(r['InstanceType']), r
+            host = _gcp_host(vm_by_zone, r['AcceleratorName'],
+                             r['AcceleratorCount'], r['Region'],
+                             r['AvailabilityZone'])
+            if host is None or _isnan(r['Price']):
+                continue
+            # inner join on (InstanceType, Region, AvailabilityZone): every
+            # VM row of that type in the zone (exactly one by the catalog's
+            # invariant, common.py:385)
+            for h in vm_by_zone[(r['Region'].lower(),
+                                 r['AvailabilityZone'].lower())]:
+                if (h['InstanceType'] != host['InstanceType'] or
+                        h['Region'] != r['Region'] or
+                        h['AvailabilityZone'] != r['AvailabilityZone']):
+                    continue
+                merged.append(dict(
+                    r, InstanceType=h['InstanceType'], vCPUs=h['vCPUs'],
+                    MemoryGiB=h['MemoryGiB'], Price=r['Price'] + h['Price'],
+                    SpotPrice=(float('nan') if _isnan(r['SpotPrice']) or
+                               _isnan(h['SpotPrice']) else
+                               r['SpotPrice'] + h['SpotPrice'])))
+        rows = merged + tpu_rows
+    results = listing_impl('GCP', rows, gpus_only, name_filter, region_filter,
+                           quantity_filter, case_sensitive, all_regions)
+    if tpu_rows:
+        # one entry per TPU generation (gcp_catalog.py:553-570)
+        for name in list(results.keys()):
+            if name.startswith('tpu-'):
+                version = name.split('-')[1]
+                infos = results.pop(name)
+                results.setdefault(f'tpu-{version}', []).extend(infos)
+        for name in list(results.keys()):
+            if name.startswith('tpu-'):
+                results[name] = sorted(results[name],
+                                       key=lambda t: (t[7], t[8], t[9]))
+    return results
+
+
+def list_accelerators(frames: Dict[str, 'object'], gpus_only: bool = True,
+                      name_filter: Optional[str] = None,
+                      region_filter: Optional[str] = None,
+                      quantity_filter: Optional[int] = None, clouds=None,
+                      case_sensitive: bool = True, all_regions: bool = False,
+                      require_price: bool = True) -> Dict[str, List[tuple]]:
+    if clouds is None:
+        clouds = list(frames.keys())
+    if isinstance(clouds, str):
+        clouds = [clouds]
+    merged: Dict[str, List[tuple]] = {}
+    for cloud in clouds:
+        df = frames[cloud.lower()]
+        if cloud.lower() == 'gcp':
+            part = gcp_listing(df, gpus_only, name_filter, region_filter,
+                               quantity_filter, case_sensitive, all_regions,
+                               require_price)
+        else:
+            part = listing_impl(CLOUD_DISPLAY[cloud.lower()], _records(df),
+                                gpus_only, name_filter, region_filter,
+                                quantity_filter, case_sensitive, all_regions)
+        for name, infos in part.items():
+            merged.setdefault(name, []).extend(infos)
+    return merged

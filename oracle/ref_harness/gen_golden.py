@@ -21,17 +21,25 @@ from tests import scenarios  # noqa: E402  pylint: disable=wrong-import-position
 
 
 def main():
-    wanted = sys.argv[1:] or list(scenarios.SUITES.keys())
+    """`gen_golden.py [catalog ...]` regenerates the optimizer fixtures,
+    `gen_golden.py --listings [catalog ...]` the accelerator listings
+    (tests/golden/accel_<catalog>.json)."""
+    argv = sys.argv[1:]
+    listings = '--listings' in argv
+    argv = [a for a in argv if a != '--listings']
+    suites = scenarios.LISTING_SUITES if listings else scenarios.SUITES
+    prefix = 'accel_' if listings else ''
+    wanted = argv or list(suites.keys())
     out_dir = os.path.join(_REPO, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
     for name in wanted:
         spec = dict(scenarios.CATALOGS[name])
-        suite = scenarios.SUITES[name]()
+        suite = suites[name]()
         with tempfile.NamedTemporaryFile('w', suffix='.json',
                                          delete=False) as f:
             json.dump(suite, f)
             sc_path = f.name
-        out_path = os.path.join(out_dir, f'{name}.json')
+        out_path = os.path.join(out_dir, f'{prefix}{name}.json')
         tmp_out = out_path + '.tmp'
         cmd = [
             sys.executable,

@@ -141,7 +141,37 @@ def _finite(x):
     return x if math.isfinite(x) else repr(x)
 
 
+def _plain(x):
+    """JSON-able scalar: NaN / None -> None, numpy scalars -> Python."""
+    if x is None:
+        return None
+    if isinstance(x, str):
+        return x
+    x = float(x)
+    return None if math.isnan(x) else x
+
+
+def run_listing(sky, scenario):
+    """`sky.catalog.list_accelerators(**kwargs)` (sky/catalog/__init__.py:
+    56-85) -> {name: [InstanceTypeInfo fields ...]} in the reference's order."""
+    from sky import catalog
+    bootstrap.clear_request_cache()
+    result = catalog.list_accelerators(**scenario.get('kwargs', {}))
+    out = {}
+    for name, infos in result.items():
+        out[name] = [[
+            i.cloud, _plain(i.instance_type), i.accelerator_name,
+            _plain(i.accelerator_count), _plain(i.cpu_count),
+            _plain(i.device_memory), _plain(i.memory), _plain(i.price),
+            _plain(i.spot_price), i.region
+        ] for i in infos]
+    return {'name': scenario['name'], 'listing': out,
+            'order': list(result.keys())}
+
+
 def run_scenario(sky, scenario):
+    if scenario.get('kind') == 'list_accelerators':
+        return run_listing(sky, scenario)
     from sky import exceptions
     from sky import optimizer as opt_lib
     from sky.utils import common as sky_common

@@ -90,7 +90,7 @@ CANDIDATE_DTYPE = np.dtype([
 ], align=True)
 
 ZONE_DTYPE = np.dtype([
-    ('flags_or', '<u4'), ('sig_lo', '<u4'), ('sig_hi', '<u4'), ('pad_', '<u4'),
+    ('flags_or', '<u4'), ('sig_lo', '<u4'), ('sig_hi', '<u4'), ('groups', '<u4'),
     ('min_key', '<u8', (2,)),
 ], align=True)
 ZONE_ROWS = 128

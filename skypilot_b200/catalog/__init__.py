@@ -52,6 +52,16 @@ def get_store(required: bool = True) -> Optional[CatalogStore]:
     return _store
 
 
+def clear_request_level_cache() -> None:
+    """Drops the host-side memos kept on the active store (stated request
+    plans, accelerator-name sets) — the counterpart of the reference's
+    `annotations.clear_request_level_cache()` (tests/conftest.py:51-52).
+    Device-resident catalog columns are untouched."""
+    if _store is not None:
+        _store.__dict__.pop('_plan_cache', None)
+        _store.__dict__.pop('_acc_set_cache', None)
+
+
 def get_device() -> int:
     return _device
 

@@ -51,7 +51,7 @@ def price_keys(values: np.ndarray) -> np.ndarray:
 
 def _zone_map(cols: Dict[str, np.ndarray]) -> np.ndarray:
     """Static summary of every 128-row chunk: flag bits and accelerator keys
-    (mod 64) that occur, cheapest Price / SpotPrice. The scan kernel tests a
+    (mod 64) that occur, fixed-host groups (mod 32), cheapest Price / SpotPrice. The scan kernel tests a
     query against the summary before it touches the chunk's rows."""
     zr = _native.ZONE_ROWS
     n = len(cols['flags'])
@@ -69,6 +69,10 @@ def _zone_map(cols: Dict[str, np.ndarray]) -> np.ndarray:
         axis=1)
     zone['sig_lo'] = (sig & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     zone['sig_hi'] = (sig >> np.uint64(32)).astype(np.uint32)
+    grp = (flags >> 8).astype(np.uint32)
+    zone['groups'] = np.bitwise_or.reduce(
+        np.where(valid & (grp != 0), np.uint32(1) << (grp & np.uint32(31)),
+                 np.uint32(0)), axis=1)
     none = np.uint64(0xFFFFFFFFFFFFFFFF)
     for c, name in enumerate(('price', 'spot_price')):
         p = cols[name].reshape(nz, zr)

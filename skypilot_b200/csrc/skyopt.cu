@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "skyopt.h"
@@ -72,6 +73,24 @@ struct Carver {
 struct SkyoptCatalog {
   int device = 0;
   CatDev dev{};
+  // flag_density[c][m]: fraction of cloud c's 128-row chunks whose summary
+  // carries every flag bit of m -- how often a query requiring m survives the
+  // zone-map test (used to size the scan's query groups).
+  std::vector<std::array<float, 256>> flag_density;
+  // Static tile classes. For every tile size (256 << r rows, r = 0..2) the
+  // tiles of a cloud are split into those where default-family rows are
+  // common ("dense": requests without accelerators match most of their rows)
+  // and the rest; each class has its own flag_density, so the dense part of a
+  // catalog can be scanned with few queries per block and the sparse part
+  // with all of them fused.
+  struct TileClass {
+    int n_tiles = 0;
+    int list0 = -1;  // offset into the device tile list; -1 = the run of
+    int tile0 = 0;   //   n_tiles consecutive tiles starting at tile0
+    std::array<float, 256> density{};
+  };
+  std::vector<std::array<TileClass, 2>> tile_class[3];  // [r][cloud][0 sparse, 1 dense]
+  const int32_t *d_tile_list = nullptr;
   std::vector<void *> allocs;
   int64_t device_bytes = 0;
   std::vector<int32_t> cloud_row_offsets, cloud_inst_offsets, cloud_n_zones,
@@ -144,7 +163,7 @@ int ensure(Ctx *x, size_t dbytes, size_t hbytes) {
 struct Plan {
   // sizes
   int nq = 0, nsets = 0, ns = 0, nt = 0, np = 0, ntar = 0, nb = 0, nd = 0;
-  int n_groups = 0, n_blocks = 0, rpt = 4, tpb = 1; bool stream = false; bool want_finalize = true;
+  int n_groups = 0, n_blocks = 0, rpt = 4, tpb = 1, nsq = 0; bool stream = false; bool want_finalize = true;
   int64_t n_partials = 0, list_entries = 0, fuzzy_entries = 0;
   int64_t cand_cap = 0;   // expand candidate buffers
   int64_t scan_rows = 0, pass_rows = 0;
@@ -152,7 +171,7 @@ struct Plan {
   size_t in_bytes = 0;
   SkyoptQuery *queries; uint32_t *acc_sets; SkyoptSlot *slots; SkyoptTask *tasks;
   int32_t *parents; double *tariffs; SkyoptBlocked *blocked; SkyoptDag *dags;
-  ScanQuery *squeries; ScanGroup *groups; const ScanGroup *host_groups = nullptr; int32_t *partial_base, *partial_count;
+  ScanQuery *squeries; QueryTest *qtests; ScanGroup *groups; const ScanGroup *host_groups = nullptr; int32_t *partial_base, *partial_count;
   int64_t *list_base, *fuzzy_base, *slot_off, *task_off; int32_t *task_dag;
   // device-only scratch
   ScanPartial *partials; unsigned long long *list_min, *fuzzy_min, *gbest;
@@ -176,7 +195,8 @@ void carve_inputs(Plan &P, Carver &c) {
   P.tariffs = c.take<double>(P.ntar);
   P.blocked = c.take<SkyoptBlocked>(P.nb);
   P.dags = c.take<SkyoptDag>(P.nd);
-  P.squeries = c.take<ScanQuery>(P.nq);
+  P.squeries = c.take<ScanQuery>(P.nsq);
+  P.qtests = c.take<QueryTest>(P.nsq);
   P.groups = c.take<ScanGroup>(P.n_groups);
   P.partial_base = c.take<int32_t>(P.nq);
   P.partial_count = c.take<int32_t>(P.nq);
@@ -191,7 +211,7 @@ void carve_rest(Plan &P, Carver &c) {
   P.partials = c.take<ScanPartial>(P.n_partials);
   P.list_min = c.take<unsigned long long>(P.list_entries);
   P.fuzzy_min = c.take<unsigned long long>(P.fuzzy_entries);
-  P.gbest = c.take<unsigned long long>(P.nq);
+  P.gbest = c.take<unsigned long long>(P.nsq);
   P.cand_region = c.take<int32_t>(P.cand_cap);
   P.cand_zone = c.take<int32_t>(P.cand_cap);
   P.cand_pa = c.take<double>(P.cand_cap);
@@ -283,15 +303,57 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
 
   std::vector<std::vector<int>> by_cloud(C);
   for (int i = 0; i < P.nq; ++i) by_cloud[pb->queries[i].cloud].push_back(i);
-  auto count_tiles = [&](int rpt) {
+  // Scan units: a (cloud, tile class) pair with its own query groups. Up to 32
+  // queries share one pass over a unit's rows. A row chunk that many queries
+  // match at once is scored query by query by one warp, so groups are cut
+  // early when the expected number of queries surviving the zone-map test per
+  // chunk (the class's flag density; accelerator and fixed-host queries are
+  // selective by key) reaches kDenseCut: the dense tiles of the catalog are
+  // then spread over more blocks instead of forming the tail of the launch,
+  // while the sparse tiles keep all queries fused.
+  static const float kDenseCut = [] {
+    const char *e = getenv("SKYOPT_DENSE_CUT");
+    return e ? (float)atof(e) : 3.0f;
+  }();
+  // n_tiles: tiles of the unit; n_blocks: blocks of each of its groups; tpb:
+  // tiles per block (strided over the unit's tile list)
+  struct Unit { int cloud, klass, n_tiles, n_blocks, tpb, list0, tile0; std::vector<int> cuts; };
+  auto make_units = [&](int rpt, int tpb, bool by_class, std::vector<Unit> &units) {
     long long blocks = 0;
+    units.clear();
     const int tile = kScanThreads * rpt;
+    const int r = rpt == 4 ? 2 : (rpt == 2 ? 1 : 0);
     for (int c = 0; c < C; ++c) {
-      if (by_cloud[c].empty()) continue;
+      const auto &qs = by_cloud[c];
+      if (qs.empty()) continue;
       const int rows = cat->cloud_row_offsets[c + 1] - cat->cloud_row_offsets[c];
-      const long long tiles = (rows + tile - 1) / tile;
-      const long long chunks = ((long long)by_cloud[c].size() + kQChunk - 1) / kQChunk;
-      blocks += tiles * chunks;
+      for (int k = 0; k < (by_class ? 2 : 1); ++k) {
+        Unit u; u.cloud = c; u.klass = k; u.tpb = tpb;
+        const float *density;
+        if (by_class) {
+          const SkyoptCatalog::TileClass &tc = cat->tile_class[r][c][k];
+          if (tc.n_tiles == 0) continue;
+          u.n_tiles = tc.n_tiles; u.list0 = tc.list0; u.tile0 = tc.tile0; density = tc.density.data();
+        } else {
+          u.n_tiles = (rows + tile - 1) / tile; u.list0 = -1; u.tile0 = 0;
+          density = cat->flag_density[c].data();
+        }
+        u.n_blocks = (u.n_tiles + tpb - 1) / tpb;
+        u.cuts.push_back(0);
+        float dens = 0.f; int n = 0;
+        for (size_t i = 0; i < qs.size(); ++i) {
+          const SkyoptQuery &q = pb->queries[qs[i]];
+          float dq = density[(q.flags_require | SKYOPT_F_VALID) & 0xFFu];
+          if ((q.qflags & SKYOPT_Q_ACC) || q.group != 0) dq *= 0.05f;
+          if (n > 0 && (n == kQChunk || dens + dq > kDenseCut)) {
+            u.cuts.push_back((int)i); dens = 0.f; n = 0;
+          }
+          dens += dq; ++n;
+        }
+        u.cuts.push_back((int)qs.size());
+        blocks += (long long)u.n_blocks * (long long)(u.cuts.size() - 1);
+        units.push_back(std::move(u));
+      }
     }
     return blocks;
   };
@@ -303,22 +365,38 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   // is the critical path and fewer, longer-lived blocks overlap it worse
   // (profiles/round1_scan_experiments.md) -- so "auto" never picks it.
   P.rpt = 4; P.tpb = 1; P.stream = false;
-  const long long tiles4 = count_tiles(4);
+  std::vector<Unit> units;
   const long long wave = 2ll * cat->sm_count;
   if (cat->scan_mode >= 2) {
     P.stream = true;
+    const long long tiles4 = make_units(4, 1, false, units);
     P.tpb = (int)std::max<long long>(1, (tiles4 + wave - 1) / wave);
     if (cat->scan_mode == 3) P.tpb = 3;  // tests: force the multi-tile loop
     if (const char *t = getenv("SKYOPT_TPB")) P.tpb = std::max(1, atoi(t));
+    make_units(4, P.tpb, false, units);
   } else {
-    if (tiles4 < wave) P.rpt = 2;
-    if (P.rpt == 2 && count_tiles(2) < wave) P.rpt = 1;
+    if (const char *r = getenv("SKYOPT_RPT")) {
+      const int v = atoi(r);
+      if (v == 1 || v == 2 || v == 4) P.rpt = v;
+      make_units(P.rpt, 1, true, units);
+    } else if (make_units(4, 1, true, units) < wave) {
+      P.rpt = 2;
+      if (make_units(2, 1, true, units) < wave) { P.rpt = 1; make_units(1, 1, true, units); }
+    }
+    // dense units first (their blocks live longest) when asked; with the
+    // permuted launch order it makes no measurable difference
+    static const bool dense_first = [] { const char *e = getenv("SKYOPT_DENSE_FIRST"); return e && atoi(e) != 0; }();
+    if (dense_first)
+      std::stable_sort(units.begin(), units.end(), [](const Unit &a, const Unit &b) { return a.klass > b.klass; });
   }
-  if (const char *r = getenv("SKYOPT_RPT")) { const int v = atoi(r); if (v == 1 || v == 2 || v == 4) P.rpt = v; }
   const int tile = kScanThreads * P.rpt;
-  P.n_groups = 0;
-  for (int c = 0; c < C; ++c)
-    P.n_groups += (int)((by_cloud[c].size() + kQChunk - 1) / kQChunk);
+  P.n_groups = 0; P.nsq = 0;
+  std::vector<int> cloud_tiles(C, 0);  // partial slots of one query of the cloud
+  for (const Unit &u : units) {
+    P.n_groups += (int)u.cuts.size() - 1;
+    P.nsq += (int)by_cloud[u.cloud].size();
+    cloud_tiles[u.cloud] += u.n_blocks;
+  }
 
   // candidate capacity: every slot can at most expand to its cloud's largest
   // instance-type / accelerator group
@@ -335,7 +413,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   for (int i = 0; i < P.nq; ++i) {
     const SkyoptQuery &q = pb->queries[i];
     const int rows = cat->cloud_row_offsets[q.cloud + 1] - cat->cloud_row_offsets[q.cloud];
-    pcount[i] = ((rows + tile - 1) / tile + P.tpb - 1) / P.tpb;
+    pcount[i] = cloud_tiles[q.cloud];
     if (npart + pcount[i] > 0x7FFFFFFFll) return fail(SKYOPT_ELIMIT, "too many scan partials");
     pbase[i] = (int32_t)npart; npart += pcount[i];
     P.scan_rows += rows;
@@ -387,18 +465,28 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     for (int t = pb->dags[d].task_begin; t < pb->dags[d].task_end; ++t) P.task_dag[t] = d;
   int g = 0, qpos = 0, block0 = 0;
   P.pass_rows = 0;
+  std::vector<int> unit_pbase(C, 0);  // partial slots used by earlier units of the cloud
   for (int c = 0; c < C; ++c) {
+    // algorithmic passes: the minimum (32 fused queries per pass over the
+    // cloud's rows), whatever grouping is chosen
+    const int rows = cat->cloud_row_offsets[c + 1] - cat->cloud_row_offsets[c];
+    P.pass_rows += (int64_t)rows * (int64_t)((by_cloud[c].size() + kQChunk - 1) / kQChunk);
+  }
+  for (const Unit &u : units) {
+    const int c = u.cloud;
     const auto &qs = by_cloud[c];
     const int rows = cat->cloud_row_offsets[c + 1] - cat->cloud_row_offsets[c];
     const int total_tiles = (rows + tile - 1) / tile;
-    const int tiles = (total_tiles + P.tpb - 1) / P.tpb;  // blocks of the group
-    for (size_t b = 0; b < qs.size(); b += kQChunk) {
-      const int n = (int)std::min<size_t>(kQChunk, qs.size() - b);
+    const int tiles = u.n_blocks;  // blocks of each group of the unit
+    for (size_t ci = 0; ci + 1 < u.cuts.size(); ++ci) {
+      const size_t b = (size_t)u.cuts[ci];
+      const int n = u.cuts[ci + 1] - u.cuts[ci];
       ScanGroup G{};
       G.row_begin = cat->cloud_row_offsets[c];
       G.row_end = cat->cloud_row_offsets[c + 1];
       G.q_begin = qpos; G.q_count = n; G.block0 = block0; G.n_tiles = tiles;
-      G.tiles_per_block = P.tpb; G.total_tiles = total_tiles;
+      G.tiles_per_block = u.tpb; G.total_tiles = P.stream ? total_tiles : u.n_tiles;
+      G.list0 = u.list0; G.tile0 = u.tile0;
       for (int k = 0; k < n; ++k) {
         const int qi = qs[b + k];
         const SkyoptQuery &q = pb->queries[qi];
@@ -409,7 +497,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
         memset(&R, 0, sizeof(R));
         R.s = make_query_s(q);
         R.qid = qi;
-        R.partial_base = pbase[qi];
+        R.partial_base = pbase[qi] + unit_pbase[c];
         R.list_base = lbase[qi];
         R.fuzzy_base = fbase[qi];
         uint32_t lo32 = 0, hi32 = 0;
@@ -426,11 +514,16 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
         // 64-bit signature (key id mod 64) of the keys the query can match
         R.s.sig_lo = (q.qflags & SKYOPT_Q_ACC) ? lo32 : 0xFFFFFFFFu;
         R.s.sig_hi = (q.qflags & SKYOPT_Q_ACC) ? hi32 : 0xFFFFFFFFu;
+        QueryTest &T = P.qtests[qpos + k];
+        T.req_flags = R.s.req_flags; T.grp_bit = R.s.grp_bit;
+        T.sig_lo = R.s.sig_lo; T.sig_hi = R.s.sig_hi;
+        T.qflags = R.s.qflags; T.price_col = (uint32_t)(R.s.price_col ? 1 : 0);
+        T.partial_base = R.partial_base; T.pad_ = 0;
       }
       P.groups[g++] = G;
       qpos += n; block0 += tiles;
-      P.pass_rows += rows;
     }
+    unit_pbase[c] += tiles;
   }
   P.n_blocks = block0;
 
@@ -451,26 +544,30 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
   cudaStream_t st = x->stream;
   CU(cudaEventRecord(x->ev[1], st));
   if (P.nq) {
-    CU(cudaMemsetAsync(P.gbest, 0xFF, sizeof(unsigned long long) * P.nq, st));
+    CU(cudaMemsetAsync(P.gbest, 0xFF, sizeof(unsigned long long) * P.nsq, st));
     if (P.list_entries) CU(cudaMemsetAsync(P.list_min, 0xFF, sizeof(unsigned long long) * P.list_entries, st));
     if (P.fuzzy_entries) CU(cudaMemsetAsync(P.fuzzy_min, 0xFF, sizeof(unsigned long long) * P.fuzzy_entries, st));
     if (P.n_blocks) {
       ScanArgs sa{};
-      sa.cat = cat->dev; sa.squeries = P.squeries; sa.groups = P.groups;
+      sa.cat = cat->dev; sa.squeries = P.squeries; sa.qtests = P.qtests; sa.groups = P.groups;
       sa.n_groups = P.n_groups; sa.partials = P.partials;
       sa.list_min = P.list_min; sa.fuzzy_min = P.fuzzy_min; sa.gbest = P.gbest;
-      sa.zero_flag = P.err_out;
-      for (int i = 0; i < std::min(P.n_groups, kInlineGroups); ++i) sa.inline_groups[i] = P.host_groups[i];
+      sa.zero_flag = P.err_out; sa.tile_list = cat->d_tile_list;
+      for (int i = 0; i < std::min(P.n_groups, kInlineGroups); ++i) { sa.inline_groups[i] = P.host_groups[i]; sa.inline_block0[i] = P.host_groups[i].block0; }
       sa.n_blocks = P.n_blocks;
       sa.debug = 0;
       if (const char *dbg = getenv("SKYOPT_DEBUG")) sa.debug = (uint32_t)atoi(dbg);
       static unsigned long long *tl = nullptr; static int tl_blocks = 0;
       if (sa.debug & 2u) {
-        if (tl_blocks < P.n_blocks) { if (tl) cudaFree(tl); CU(cudaMalloc(&tl, (size_t)P.n_blocks * 64)); tl_blocks = P.n_blocks; }
+        if (tl_blocks < P.n_blocks) { if (tl) cudaFree(tl); CU(cudaMalloc(&tl, (size_t)P.n_blocks * 64 + 1024)); tl_blocks = P.n_blocks; }
         sa.timeline = tl;
+        CU(cudaMemsetAsync(tl + (size_t)P.n_blocks * 8, 0, 1024, st));
+        if (const char *e = getenv("SKYOPT_TRACE_VB")) sa.trace_vb = (uint32_t)atoi(e);
+        if (const char *e = getenv("SKYOPT_TRACE_WARP")) sa.trace_warp = (uint32_t)atoi(e);
       }
       sa.perm_mul = 1;
-      for (uint32_t cand : {7919u, 104729u, 1299709u, 15485863u}) {
+      static const bool permute = [] { const char *e = getenv("SKYOPT_PERM"); return !e || atoi(e) != 0; }();
+      if (permute) for (uint32_t cand : {7919u, 104729u, 1299709u, 15485863u}) {
         uint64_t x = cand, y = (uint64_t)P.n_blocks;  // gcd
         while (y) { const uint64_t t = x % y; x = y; y = t; }
         if (x == 1) { sa.perm_mul = cand; break; }
@@ -485,7 +582,7 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
       CU(cudaEventRecord(x->ev[7], st));
       if (sa.debug & 2u) {
         // profiling experiment: dump the per-block timeline of this launch
-        std::vector<unsigned long long> h((size_t)P.n_blocks * 8);
+        std::vector<unsigned long long> h((size_t)P.n_blocks * 8 + 128);
         CU(cudaStreamSynchronize(st));
         CU(cudaMemcpy(h.data(), sa.timeline, h.size() * 8, cudaMemcpyDeviceToHost));
         if (const char *path = getenv("SKYOPT_TIMELINE")) {
@@ -713,6 +810,60 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog 
                         kStreamTile / kZoneRows + 1, &v.zone_map);
   if (rc) { skyopt_catalog_destroy(c); return rc; }
 
+  c->flag_density.assign(d->n_clouds, std::array<float, 256>{});
+  for (int cl = 0; cl < d->n_clouds; ++cl) {
+    const int64_t z0 = d->cloud_row_offsets[cl] / kZoneRows, z1 = d->cloud_row_offsets[cl + 1] / kZoneRows;
+    std::array<int64_t, 256> exact{};  // chunks per exact flag byte
+    for (int64_t z = z0; z < z1; ++z) exact[d->zone_map[z].flags_or & 0xFFu]++;
+    for (int m = 0; m < 256; ++m) {
+      int64_t n = 0;
+      for (int f = 0; f < 256; ++f) if ((f & m) == m) n += exact[f];
+      c->flag_density[cl][m] = z1 > z0 ? (float)((double)n / (double)(z1 - z0)) : 0.f;
+    }
+  }
+  {
+    std::vector<int32_t> tile_list;
+    for (int r = 0; r < 3; ++r) {
+      const int cpt = 2 << r;  // 128-row chunks per tile
+      c->tile_class[r].assign(d->n_clouds, {});
+      for (int cl = 0; cl < d->n_clouds; ++cl) {
+        const int64_t z0 = d->cloud_row_offsets[cl] / kZoneRows, z1 = d->cloud_row_offsets[cl + 1] / kZoneRows;
+        const int n_tiles = (int)((z1 - z0 + cpt - 1) / cpt);
+        std::vector<int32_t> members[2];
+        std::array<int64_t, 256> exact[2] = {};
+        int64_t chunks[2] = {0, 0};
+        for (int t = 0; t < n_tiles; ++t) {
+          int with_default = 0, n = 0;
+          for (int64_t z = z0 + (int64_t)t * cpt; z < std::min<int64_t>(z1, z0 + (int64_t)(t + 1) * cpt); ++z, ++n)
+            with_default += (d->zone_map[z].flags_or & SKYOPT_F_DEFAULT_FAMILY) ? 1 : 0;
+          const int k = (with_default * 4 >= n) ? 1 : 0;
+          members[k].push_back(t);
+          for (int64_t z = z0 + (int64_t)t * cpt; z < std::min<int64_t>(z1, z0 + (int64_t)(t + 1) * cpt); ++z)
+            exact[k][d->zone_map[z].flags_or & 0xFFu]++;
+          chunks[k] += n;
+        }
+        for (int k = 0; k < 2; ++k) {
+          SkyoptCatalog::TileClass &tc = c->tile_class[r][cl][k];
+          tc.n_tiles = (int)members[k].size();
+          if (tc.n_tiles > 0) {
+            tc.tile0 = members[k].front();
+            if (members[k].back() - members[k].front() + 1 != tc.n_tiles) {
+              tc.list0 = (int)tile_list.size();
+              tile_list.insert(tile_list.end(), members[k].begin(), members[k].end());
+            }
+          }
+          for (int m = 0; m < 256; ++m) {
+            int64_t n = 0;
+            for (int f = 0; f < 256; ++f) if ((f & m) == m) n += exact[k][f];
+            tc.density[m] = chunks[k] ? (float)((double)n / (double)chunks[k]) : 0.f;
+          }
+        }
+      }
+    }
+    if (tile_list.empty()) tile_list.push_back(0);
+    rc = upload(c, tile_list.data(), tile_list.size(), 0, &c->d_tile_list);
+    if (rc) { skyopt_catalog_destroy(c); return rc; }
+  }
   c->cloud_row_offsets.assign(d->cloud_row_offsets, d->cloud_row_offsets + d->n_clouds + 1);
   c->cloud_inst_offsets.assign(d->cloud_inst_offsets, d->cloud_inst_offsets + d->n_clouds + 1);
   c->cloud_region_offsets.assign(d->cloud_region_offsets, d->cloud_region_offsets + d->n_clouds + 1);
@@ -994,7 +1145,8 @@ int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSol
     cudaStream_t st = x->stream;
     const size_t flush_words = (size_t)192 << 20 >> 2;  // 192 MB > 126 MB L2
     if (flush_l2 && !x->flush) {
-      CU(cudaMalloc(&x->flush, flush_words * 4));
+      CU(cudaMalloc(&x->flush, flush_words * 8));  // second half: read pass
+      CU(cudaMemset(x->flush + flush_words, 0, flush_words * 4));
       x->flush_words = flush_words;
     }
     CU(cudaEventRecord(x->ev[0], st));
@@ -1004,6 +1156,11 @@ int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSol
       if (flush_l2) {
         flush_kernel<<<cat->sm_count * 8, 256, 0, st>>>(x->flush, (int64_t)x->flush_words, (uint32_t)it);
         CU(cudaGetLastError());
+        static const bool read_pass = [] { const char *e = getenv("SKYOPT_FLUSH"); return e && !strcmp(e, "read"); }();
+        if (read_pass) {
+          flush_read_kernel<<<cat->sm_count * 8, 256, 0, st>>>(x->flush + x->flush_words, (int64_t)x->flush_words, x->flush);
+          CU(cudaGetLastError());
+        }
       }
       if ((r = enqueue_kernels(cat, x, P, true, sol->scan != nullptr))) return r;
       CU(cudaStreamSynchronize(st));

@@ -26,6 +26,10 @@
 namespace skyopt {
 
 constexpr int kScanThreads = 256;
+#ifndef SKYOPT_SCAN_BLOCKS_PER_SM
+#define SKYOPT_SCAN_BLOCKS_PER_SM 3
+#endif
+constexpr int kScanBlocksPerSM = SKYOPT_SCAN_BLOCKS_PER_SM;
 constexpr int kQChunk = 32;           // queries fused per pass
 constexpr uint64_t kKeyNone = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kKeyNaN = 0xFFFFFFFFFFFFFFF0ull;  // after every real price
@@ -53,6 +57,8 @@ struct ScanGroup {
   uint32_t need;             // bit0 on-demand column, bit1 spot column
   int32_t tiles_per_block;   // stream kernel: consecutive tiles per block
   int32_t total_tiles;       // stream kernel: tiles of the row range
+  int32_t list0;             // first entry of the group's tile list; -1 = the run
+  int32_t tile0;             //   of consecutive tiles starting at tile0
   int32_t pad_;
 };
 
@@ -69,8 +75,12 @@ struct ScanFinal {
 };
 
 // Total order on prices as unsigned integers (NaN never reaches here).
-__device__ __forceinline__ uint64_t price_key(double p) {
+__host__ __device__ __forceinline__ uint64_t price_key(double p) {
+#ifdef __CUDA_ARCH__
   uint64_t b = (uint64_t)__double_as_longlong(p);
+#else
+  uint64_t b; memcpy(&b, &p, 8);
+#endif
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 __device__ __forceinline__ double key_price(uint64_t k) {
@@ -95,6 +105,8 @@ struct QueryS {
   int32_t cloud;
   uint32_t req_flags;    // flag bits every matching row carries
   uint32_t sig_lo, sig_hi;  // 64-bit signature of the accelerator keys wanted
+  uint32_t grp_bit;      // bit (group % 32) of a fixed-host group query, else 0
+  uint32_t pad_;
   double cpu_lo, cpu_hi, mem_lo, mem_hi, cap, disk_size;
 };
 
@@ -113,8 +125,10 @@ __host__ __device__ inline QueryS make_query_s(const SkyoptQuery &q) {
   s.disk_op = q.disk_op; s.cloud = q.cloud;
   s.req_flags = (q.flags_require | SKYOPT_F_VALID) & 0xFFu;
   s.sig_lo = 0xFFFFFFFFu; s.sig_hi = 0xFFFFFFFFu;  // refined while staging the sets
+  s.grp_bit = (q.group != 0) ? (1u << (q.group & 31)) : 0u;
+  s.pad_ = 0;
   s.cpu_lo = q.cpus; s.cpu_hi = (q.cpus_op == SKYOPT_OP_GE) ? kInf : q.cpus;
-  s.mem_lo = q.mem;  s.mem_hi = (q.mem_op == SKYOPT_OP_GE) ? kInf : q.mem;
+  s.mem_lo = q.mem;  s.mem_hi = (q.mem_op == SKYOPT_OP_EQ) ? q.mem : kInf;
   s.cap = q.max_price; s.disk_size = q.disk_size;
   return s;
 }
@@ -167,7 +181,19 @@ struct ScanQuery {
   int64_t fuzzy_base;    // into fuzzy_min (SKYOPT_Q_FUZZY)
   uint32_t set[2][kSetStride];  // exact / fuzzy accelerator-key bitmasks
 };
-static_assert(sizeof(ScanQuery) % 8 == 0, "ScanQuery must be 8-byte granular");
+static_assert(sizeof(ScanQuery) % 16 == 0, "ScanQuery is staged with 16-byte loads");
+
+// What the zone-map test needs of a query (same order as the ScanQuery
+// records): a block reads these straight from global memory, one per lane,
+// and stages the full records only of the queries that survive for at least
+// one of its warps.
+struct QueryTest {
+  uint32_t req_flags, grp_bit, sig_lo, sig_hi;
+  uint32_t qflags, price_col;
+  int32_t partial_base;
+  uint32_t pad_;
+};
+static_assert(sizeof(QueryTest) == 32, "QueryTest is read as two 16-byte words");
 
 // Shared-memory state of one scan block: the staged queries and the per-warp
 // running minima.
@@ -177,24 +203,29 @@ struct ScanShared {
   uint32_t wrow[kQChunk][kScanWarps];
   uint64_t gb[kQChunk];   // best price key any block has found so far
   uint32_t sany[kQChunk];
+  uint32_t wact[kScanWarps];  // per-warp masks of surviving queries
 };
 
-constexpr int kInlineGroups = 8;
+constexpr int kInlineGroups = 32;
 
 struct ScanArgs {
   CatDev cat;
   const ScanQuery *squeries;   // scan order
+  const QueryTest *qtests;     // scan order, parallel to squeries
   const ScanGroup *groups;
   int n_groups;
   ScanPartial *partials;
   unsigned long long *list_min;
   unsigned long long *fuzzy_min;
   unsigned long long *gbest;   // [n_queries] in scan order: running best key
+  const int32_t *tile_list;    // static tile classes (see SkyoptCatalog::TileClass)
   int32_t *zero_flag;          // cleared by the first block (expand's error flag)
   int n_blocks;                // grid size
   uint32_t perm_mul;           // odd, coprime with n_blocks
   uint32_t debug;              // bit 1: record the per-block timeline (profiling)
+  uint32_t trace_vb, trace_warp;  // debug & 4: per-iteration trace of one warp
   unsigned long long *timeline;  // debug & 2: per block {start, staged, scored, end} ns + smid
+  int32_t inline_block0[kInlineGroups];    // first block of each group
   ScanGroup inline_groups[kInlineGroups];  // copy of groups[] when it fits
 };
 
@@ -223,13 +254,16 @@ __device__ __forceinline__ int permuted_block(const ScanArgs &a) {
 
 __device__ __forceinline__ ScanGroup find_group(const ScanArgs &a, int b) {
   // blockIdx -> group: groups are sorted by block0. Small tables travel in
-  // the kernel parameters (constant bank, no memory round trip).
+  // the kernel parameters (constant bank, no memory round trip): five
+  // branch-free halving steps over the first-block table, then one record.
   if (a.n_groups <= kInlineGroups) {
-    ScanGroup g = a.inline_groups[0];
+    int idx = 0;
 #pragma unroll
-    for (int i = 1; i < kInlineGroups; ++i)
-      if (i < a.n_groups && a.inline_groups[i].block0 <= b) g = a.inline_groups[i];
-    return g;
+    for (int step = kInlineGroups / 2; step >= 1; step >>= 1) {
+      const int probe = idx + step;
+      if (probe < a.n_groups && a.inline_block0[probe] <= b) idx = probe;
+    }
+    return a.inline_groups[idx];
   }
   int lo = 0, hi = a.n_groups - 1;
   while (lo < hi) {
@@ -244,10 +278,24 @@ __device__ __forceinline__ void stage_queries(const ScanArgs &a, const ScanGroup
                                               ScanShared &S) {
   const int tid = threadIdx.x;
   const int nq = G.q_count;
-  const uint2 *src = reinterpret_cast<const uint2 *>(a.squeries + G.q_begin);
-  uint2 *dst = reinterpret_cast<uint2 *>(S.q);
-  const int n8 = nq * (int)(sizeof(ScanQuery) / 8);
-  for (int i = tid; i < n8; i += kScanThreads) dst[i] = __ldg(src + i);
+  // All of a thread's 16-byte loads are issued before the first store, so a
+  // full chunk costs one L2 round trip instead of one per loop iteration.
+  const uint4 *src = reinterpret_cast<const uint4 *>(a.squeries + G.q_begin);
+  uint4 *dst = reinterpret_cast<uint4 *>(S.q);
+  const int n16 = nq * (int)(sizeof(ScanQuery) / 16);
+  constexpr int kStageLoads =
+      (kQChunk * (int)(sizeof(ScanQuery) / 16) + kScanThreads - 1) / kScanThreads;
+  uint4 v[kStageLoads];
+#pragma unroll
+  for (int k = 0; k < kStageLoads; ++k) {
+    const int i = tid + k * kScanThreads;
+    if (i < n16) v[k] = __ldg(src + i);
+  }
+#pragma unroll
+  for (int k = 0; k < kStageLoads; ++k) {
+    const int i = tid + k * kScanThreads;
+    if (i < n16) dst[i] = v[k];
+  }
   for (int i = tid; i < nq * kScanWarps; i += kScanThreads) {
     S.wkey[i / kScanWarps][i % kScanWarps] = kKeyNone;
     S.wrow[i / kScanWarps][i % kScanWarps] = kRowNone;
@@ -265,7 +313,8 @@ __device__ __forceinline__ void stage_queries(const ScanArgs &a, const ScanGroup
 // catalog, so it is computed once at ingest for every 128-row chunk (the
 // "zone map"); the streaming kernel derives it from the rows it holds.
 struct RowSummary {
-  uint32_t fl_or, sg_lo, sg_hi, pad_;
+  uint32_t fl_or, sg_lo, sg_hi;
+  uint32_t grp;       // bit (group % 32) of every fixed-host group present
   uint64_t wmin[2];   // price keys (kKeyNone = no priced valid row)
 };
 static_assert(sizeof(RowSummary) == 32, "zone map entry layout");
@@ -282,7 +331,7 @@ __device__ __forceinline__ uint32_t active_queries(const ScanShared &S, int nq,
   if (lane < nq) {
     const QueryS &L = S.q[lane].s;
     const uint32_t rq = L.req_flags;
-    pass = ((z.fl_or & rq) == rq) &&
+    pass = ((z.fl_or & rq) == rq) && ((z.grp & L.grp_bit) == L.grp_bit) &&
            (!(L.qflags & SKYOPT_Q_ACC) ||
             (((L.sig_lo & z.sg_lo) | (L.sig_hi & z.sg_hi)) != 0u));
     const bool prunable = !(L.qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY));
@@ -297,12 +346,13 @@ __device__ __forceinline__ RowSummary summarize_rows(
     const ScanGroup &G, int64_t base, const double (&od)[RPT], const double (&sp)[RPT],
     const uint32_t (&ak)[RPT], const uint32_t (&fl)[RPT]) {
   RowSummary z;
-  uint32_t fl_or = 0, sg_lo = 0, sg_hi = 0;
+  uint32_t fl_or = 0, sg_lo = 0, sg_hi = 0, grp = 0;
   uint64_t k[2] = {kKeyNone, kKeyNone};
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const uint32_t f = (base + j < G.row_end) ? fl[j] : 0u;
     fl_or |= f;
+    if ((f & SKYOPT_F_VALID) && (f >> 8)) grp |= 1u << ((f >> 8) & 31u);
     if (ak[j] != SKYOPT_NONE16 && (f & SKYOPT_F_VALID)) {
       if (ak[j] & 32u) sg_hi |= 1u << (ak[j] & 31u); else sg_lo |= 1u << (ak[j] & 31u);
     }
@@ -314,7 +364,7 @@ __device__ __forceinline__ RowSummary summarize_rows(
   z.fl_or = __reduce_or_sync(0xFFFFFFFFu, fl_or & 0xFFu);
   z.sg_lo = __reduce_or_sync(0xFFFFFFFFu, sg_lo);
   z.sg_hi = __reduce_or_sync(0xFFFFFFFFu, sg_hi);
-  z.pad_ = 0;
+  z.grp = __reduce_or_sync(0xFFFFFFFFu, grp);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const uint32_t h = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)(k[c] >> 32));
@@ -327,29 +377,43 @@ __device__ __forceinline__ RowSummary summarize_rows(
 
 // Score this thread's RPT rows (already in registers) against the `active`
 // staged queries; per-warp running minima accumulate in S.wkey / S.wrow.
+// (Variants that turn the fp64 columns into order-preserving integer keys --
+// B200 issues only one fp64 warp-instruction per cycle per SM,
+// tools/fp64_probe.cu -- were measured 1-3 us slower on cfg4: the inner loop
+// is bound by its dependent-issue latency at two to six resident warps per
+// scheduler, not by the fp64 pipe, and 64-bit integer compares are two
+// instructions each.)
 template <int RPT>
 __device__ __forceinline__ void score_rows(
     const ScanArgs &a, const ScanGroup &G, ScanShared &S, int64_t base, uint32_t active,
     const double (&od)[RPT], const double (&sp)[RPT], const double (&vc)[RPT],
     const double (&mm)[RPT], const uint32_t (&ak)[RPT], const uint32_t (&rg)[RPT],
-    const uint32_t (&zn)[RPT], const uint32_t (&fl)[RPT]) {
+    const uint32_t (&zn)[RPT], const uint32_t (&fl)[RPT],
+    unsigned long long *trace = nullptr) {
   const CatDev &cat = a.cat;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // Per-row integer key and accelerator-bit address, computed once.
-  uint32_t klo[RPT], khi[RPT], aw[RPT], ab[RPT];
+  int trace_n = 0;
+  // Per-row integer key, computed once and kept in two registers per row:
+  //   klo = flags | region << 16,  khi = zone | accelerator key << 16
+  // ("no accelerator" becomes key 32 * SKYOPT_ACC_SET_WORDS, whose bitmask
+  // word is the zero word after every set).
+  uint32_t klo[RPT], khi[RPT];
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const uint32_t f = (base + j < G.row_end) ? fl[j] : 0u;
+    const uint32_t key = (ak[j] == SKYOPT_NONE16) ? (uint32_t)(32 * SKYOPT_ACC_SET_WORDS) : ak[j];
     klo[j] = f | (rg[j] << 16);
-    khi[j] = zn[j];
-    aw[j] = (ak[j] == SKYOPT_NONE16) ? (uint32_t)SKYOPT_ACC_SET_WORDS : (ak[j] >> 5);
-    ab[j] = ak[j] & 31u;
+    khi[j] = zn[j] | (key << 16);
   }
   while (active) {
     const int q = __ffs(active) - 1;
     active &= active - 1;
     const QueryS &Q = S.q[q].s;
     const uint32_t qf = Q.qflags;
+    if (trace && lane == 0 && trace_n < 30) {  // profiling (SKYOPT_DEBUG & 4)
+      trace[4 * trace_n] = (unsigned long long)S.q[q].qid;
+      trace[4 * trace_n + 1] = (unsigned long long)clock64();
+    }
     uint32_t m1 = 0, mf = 0;
     {
       const uint32_t mlo = Q.mask_lo, mhi = Q.mask_hi, vlo = Q.val_lo, vhi = Q.val_hi;
@@ -362,10 +426,12 @@ __device__ __forceinline__ void score_rows(
     if (qf & SKYOPT_Q_ACC) {
       uint32_t me = 0;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) me |= ((S.q[q].set[0][aw[j]] >> ab[j]) & 1u) << j;
+      for (int j = 0; j < RPT; ++j)
+        me |= ((S.q[q].set[0][khi[j] >> 21] >> ((khi[j] >> 16) & 31u)) & 1u) << j;
       if (qf & SKYOPT_Q_FUZZY) {
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) mf |= ((S.q[q].set[1][aw[j]] >> ab[j]) & 1u) << j;
+        for (int j = 0; j < RPT; ++j)
+          mf |= ((S.q[q].set[1][khi[j] >> 21] >> ((khi[j] >> 16) & 31u)) & 1u) << j;
         mf &= m1;
       }
       m1 &= me;
@@ -386,25 +452,28 @@ __device__ __forceinline__ void score_rows(
     }
     uint64_t bkey = kKeyNone;
     uint32_t brow = kRowNone;
+    if (trace && lane == 0 && trace_n < 30) trace[4 * trace_n + 2] = (unsigned long long)clock64();
     if (m1) {
       S.sany[q] = 1u;  // benign race: every writer stores 1
-      // Second stage, branch-free over the thread's RPT rows: the fp64
-      // compares of different rows are independent, so they pipeline instead
-      // of running as RPT divergent sections.
+      // Second stage, branch-free over the thread's RPT rows (the operators
+      // are per query, so they select thresholds instead of code paths): the
+      // rows' fp64 compares are independent and pipeline.
       const uint32_t f2 = Q.flags2;
-      const int cop = Q.cpus_op, mop = Q.mem_op, pcol = Q.price_col;
+      const int mop = Q.mem_op, pcol = Q.price_col;
+      const bool nocpu = Q.cpus_op == 0, nomem = mop == 0, ratio = mop == SKYOPT_OP_RATIO;
       const double clo = Q.cpu_lo, chi = Q.cpu_hi, mlo = Q.mem_lo, mhi = Q.mem_hi;
       const double cap = Q.cap;
       uint32_t okm = 0;
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
-        bool ok = ((m1 >> j) & 1u) && ((fl[j] & f2) == f2);
-        if (cop) ok = ok & (vc[j] >= clo) & (vc[j] <= chi);
-        if (mop == SKYOPT_OP_RATIO) ok = ok & (mm[j] >= __dmul_rn(vc[j], mlo));
-        else if (mop) ok = ok & (mm[j] >= mlo) & (mm[j] <= mhi);
-        okm |= (uint32_t)ok << j;
+        // 'rx': MemoryGiB >= vCPUs * r (common.py:476), else the interval
+        const double lo = ratio ? __dmul_rn(vc[j], mlo) : mlo;
+        const bool okc = nocpu | ((vc[j] >= clo) & (vc[j] <= chi));
+        const bool okr = nomem | ((mm[j] >= lo) & (mm[j] <= mhi));
+        const bool okj = ((m1 >> j) & 1u) & ((klo[j] & f2) == f2) & okc & okr;
+        okm |= (uint32_t)okj << j;
         const double p = pcol ? sp[j] : od[j];
-        const uint64_t key = (ok & (p <= cap)) ? price_key(p) : kKeyNone;  // NaN: false
+        const uint64_t key = (okj & (p <= cap)) ? price_key(p) : kKeyNone;  // NaN: false
         if (key < bkey) { bkey = key; brow = (uint32_t)(base + j); }
       }
       if ((qf & SKYOPT_Q_LIST) && okm) {
@@ -434,10 +503,11 @@ __device__ __forceinline__ void score_rows(
         if (!((mf >> j) & 1u)) continue;
         const double p = (G.need & 1u) ? od[j] : __ldg(cat.price + base + j);
         const uint64_t key = (p == p) ? price_key(p) : kKeyNaN;
-        atomicMin(&a.fuzzy_min[S.q[q].fuzzy_base + ak[j]],
+        atomicMin(&a.fuzzy_min[S.q[q].fuzzy_base + (khi[j] >> 16)],
                   (unsigned long long)key);
       }
     }
+    if (trace && lane == 0 && trace_n < 30) { trace[4 * trace_n + 3] = (unsigned long long)clock64(); ++trace_n; }
     // Warp argmin of (price key, row) with three REDUX steps; skipped when no
     // lane has a candidate (the common case for selective queries). Lane 0
     // folds the result into the warp's running minimum.
@@ -501,37 +571,100 @@ __device__ __forceinline__ void finish_block(const ScanArgs &a, const ScanGroup 
 constexpr int kZoneRows = 128;  // rows per zone-map entry
 
 template <int RPT>
-__global__ void __launch_bounds__(kScanThreads, 768 / kScanThreads) scan_kernel(ScanArgs a) {
-  __shared__ ScanShared S;
+__global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_kernel(ScanArgs a) {
+  __shared__ __align__(16) ScanShared S;
   const int vb = permuted_block(a);
   const ScanGroup G = find_group(a, vb);
-  const int tile = vb - G.block0;
-  const int tid = threadIdx.x;
+  const int slot = vb - G.block0;  // partial slot of this block within its group
+  // the group's tiles: a run of consecutive tiles, or an explicit list
+  const int tile = (G.list0 < 0) ? G.tile0 + slot : __ldg(a.tile_list + G.list0 + slot);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = G.q_count;
   if (blockIdx.x == 0 && tid == 0 && a.zero_flag) *a.zero_flag = 0;
   mark(a, 0);
   const int64_t base =
       (int64_t)G.row_begin + (int64_t)tile * (kScanThreads * RPT) + tid * RPT;
-  // The warp's zone-map entry travels while the constraint vectors are
-  // staged (cloud ranges are 128-row aligned, so an entry never mixes clouds;
-  // with RPT < 4 several warps share one entry, which is merely less tight).
-  const int64_t warp_row = base - (int64_t)(tid & 31) * RPT;
-  RowSummary z;
-  {
+  const int64_t warp_row = base - (int64_t)lane * RPT;
+
+  // ---- phase A: zone-map test, lane q <-> query q, operands straight from
+  // global memory (the warp's 32-byte summary of its rows, the query's
+  // 32-byte test record, the grid-wide running best). Cloud ranges are
+  // 128-row aligned, so a summary never mixes clouds; with RPT < 4 several
+  // warps share one, which is merely less tight. (Letting one warp test all
+  // eight chunks of the tile saves a quarter of the kernel's instructions and
+  // was measured slower: the block is latency-bound, not issue-bound.)
+  bool pass = false;
+  QueryTest qt;
+  unsigned long long gb = kKeyNone;
+  if (lane < nq) {
+    const uint4 *tp = reinterpret_cast<const uint4 *>(a.qtests + G.q_begin + lane);
+    const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+    qt.req_flags = t0.x; qt.grp_bit = t0.y; qt.sig_lo = t0.z; qt.sig_hi = t0.w;
+    qt.qflags = t1.x; qt.price_col = t1.y; qt.partial_base = (int32_t)t1.z;
+    // stale values of the running best are fine: any achieved key is a bound
+    gb = *reinterpret_cast<volatile unsigned long long *>(a.gbest + G.q_begin + lane);
+  }
+  if (warp_row < G.row_end) {
     const uint4 *zp = reinterpret_cast<const uint4 *>(a.cat.zone_map + warp_row / kZoneRows);
     const uint4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
-    z.fl_or = z0.x; z.sg_lo = z0.y; z.sg_hi = z0.z; z.pad_ = 0;
-    z.wmin[0] = ((uint64_t)z1.y << 32) | z1.x;
-    z.wmin[1] = ((uint64_t)z1.w << 32) | z1.z;
+    if (lane < nq) {
+      pass = ((z0.x & qt.req_flags) == qt.req_flags) && ((z0.w & qt.grp_bit) == qt.grp_bit) &&
+             (!(qt.qflags & SKYOPT_Q_ACC) || (((qt.sig_lo & z0.y) | (qt.sig_hi & z0.z)) != 0u));
+      // branch-and-bound on the argmin: nothing in these rows is cheaper than
+      // what the grid already has (table queries need every matching row)
+      const uint64_t wmin = qt.price_col ? (((uint64_t)z1.w << 32) | z1.z)
+                                         : (((uint64_t)z1.y << 32) | z1.x);
+      if (!(qt.qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY)) && wmin > gb) pass = false;
+    }
   }
-  stage_queries(a, G, S);
+  const uint32_t active = __ballot_sync(0xFFFFFFFFu, pass);
+  if (lane == 0) S.wact[warp] = active;
+  __syncthreads();
+  uint32_t wanted = 0;  // queries some warp of the block has to score
+#pragma unroll
+  for (int w = 0; w < kScanWarps; ++w) wanted |= S.wact[w];
+  if (wanted == 0) {
+    // The summaries prove that no row of this tile can match or improve any
+    // query: one empty partial per query and the block is done, without ever
+    // staging the constraint vectors.
+    if (tid < nq) {
+      ScanPartial out;
+      out.key = kKeyNone; out.row = kRowNone; out.pad_ = 0;
+      a.partials[(int64_t)qt.partial_base + slot] = out;
+    }
+    mark(a, 3);
+    return;
+  }
+
+  // ---- phase B: stage the surviving queries' records (16-byte loads, one
+  // record per warp at a time), initialise the per-warp minima.
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.squeries + G.q_begin);
+    uint4 *dst = reinterpret_cast<uint4 *>(S.q);
+    constexpr int kWords = (int)(sizeof(ScanQuery) / 16);
+    static_assert(kWords <= 32, "one lane per 16-byte word of a record");
+    uint32_t todo = wanted;
+    for (int k = 0; todo; ++k) {
+      const int q = __ffs(todo) - 1;
+      todo &= todo - 1;
+      if ((k & (kScanWarps - 1)) == warp && lane < kWords)
+        dst[q * kWords + lane] = __ldg(src + q * kWords + lane);
+    }
+    for (int i = tid; i < nq * kScanWarps; i += kScanThreads) {
+      S.wkey[i / kScanWarps][i % kScanWarps] = kKeyNone;
+      S.wrow[i / kScanWarps][i % kScanWarps] = kRowNone;
+    }
+    if (tid < nq) { S.sany[tid] = 0; S.gb[tid] = gb; }
+  }
+  __syncthreads();
   mark(a, 1);
-  const uint32_t active =
-      (warp_row < G.row_end) ? active_queries(S, G.q_count, z) : 0u;
+  // ---- phase C: only warps with something to score stream their rows
+  // (32 B per row); the others are proven non-matching / non-improving by the
+  // summary. (Measured and rejected: several tiles per block -- the per-tile
+  // latencies serialise inside the block, while independent blocks overlap
+  // them; dealing the surviving (chunk, query) pairs evenly to the block's
+  // warps -- no gain, more registers.)
   if (active) {
-    // Only warps with something to score stream their rows (32 B per row);
-    // the others are proven non-matching / non-improving by the summary.
-    // (Issuing the loads before the staging barrier was measured slower: the
-    // staging copy then queues behind 32 KB of row traffic per block.)
     double od[RPT], sp[RPT], vc[RPT], mm[RPT];
     uint32_t ak[RPT], rg[RPT], zn[RPT], fl[RPT];
     if (G.need & 1u) load_f64<RPT>(a.cat.price, base, od);
@@ -542,10 +675,32 @@ __global__ void __launch_bounds__(kScanThreads, 768 / kScanThreads) scan_kernel(
     load_u16<RPT>(a.cat.region_id, base, rg);
     load_u16<RPT>(a.cat.zone_id, base, zn);
     load_u16<RPT>(a.cat.flags, base, fl);
-    score_rows<RPT>(a, G, S, base, active, od, sp, vc, mm, ak, rg, zn, fl);
+    unsigned long long *trace = nullptr;
+    if ((a.debug & 4u) && vb == (int)a.trace_vb && warp == (int)a.trace_warp)
+      trace = a.timeline + (size_t)a.n_blocks * 8;
+    score_rows<RPT>(a, G, S, base, active, od, sp, vc, mm, ak, rg, zn, fl, trace);
+    if (trace && lane == 0) { trace[126] = (unsigned long long)clock64(); trace[127] = __popc(active); }
   }
   mark(a, 2);
-  finish_block(a, G, S, tile);
+  // Block reduction of the per-warp minima -> one partial per (query, block).
+  __syncthreads();
+  if (tid < nq) {
+    uint64_t k = kKeyNone;
+    uint32_t r = kRowNone;
+    uint32_t any = 0;
+    if ((wanted >> tid) & 1u) {
+#pragma unroll
+      for (int w = 0; w < kScanWarps; ++w) {
+        const uint64_t kw = S.wkey[tid][w];
+        const uint32_t rw = S.wrow[tid][w];
+        if (kw < k || (kw == k && rw < r)) { k = kw; r = rw; }
+      }
+      any = S.sany[tid];
+    }
+    ScanPartial out;
+    out.key = k; out.row = r; out.pad_ = any;
+    a.partials[(int64_t)qt.partial_base + slot] = out;
+  }
   mark(a, 3);
 }
 
@@ -599,7 +754,7 @@ static_assert(sizeof(StreamStage) == kStageBytes, "stage layout");
 __global__ void __launch_bounds__(kScanThreads, 512 / kScanThreads) scan_stream_kernel(ScanArgs a) {
   extern __shared__ __align__(128) unsigned char stream_smem[];
   StreamStage *stages = reinterpret_cast<StreamStage *>(stream_smem);
-  __shared__ ScanShared S;
+  __shared__ __align__(16) ScanShared S;
   __shared__ __align__(8) uint64_t full[kStreamStages];
   const int vb = permuted_block(a);
   const ScanGroup G = find_group(a, vb);
@@ -1563,6 +1718,17 @@ __global__ void flush_kernel(uint32_t *buf, int64_t n, uint32_t v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     buf[i] = v + (uint32_t)i;
+}
+
+// Second half of the optional write-then-read flush: after this pass the L2
+// holds clean lines only, so evictions inside the timed region are not
+// write-backs of the flush's own data.
+__global__ void flush_read_kernel(const uint32_t *buf, int64_t n, uint32_t *sink) {
+  uint32_t acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    acc ^= __ldcg(buf + i);
+  if (acc == 0x9E3779B9u) *sink = acc;  // keeps the loads alive
 }
 
 }  // namespace skyopt

@@ -289,3 +289,64 @@ SUITES = {
     'three4k': no_lambda_scenarios,
     'aws50k': aws_scenarios,
 }
+
+
+# ---------------------------------------------------------------------------
+# Accelerator listings (`sky.catalog.list_accelerators`, SURVEY.md section 8f
+# rank 2). A case is {'name', 'kind': 'list_accelerators', 'kwargs'}; the
+# harness records {accelerator: [[cloud, instance_type, accelerator_name,
+# accelerator_count, cpu_count, device_memory, memory, price, spot_price,
+# region], ...]} in the reference's order.
+def listing_cases(clouds=('aws', 'gcp', 'azure', 'lambda')):
+    clouds = list(clouds)
+
+    def _listing(name, **kwargs):
+        # `clouds=None` would walk every registered cloud (and try to
+        # download their catalogs); the cases name the catalog's clouds.
+        kwargs.setdefault('clouds', clouds)
+        return {'name': name, 'kind': 'list_accelerators', 'kwargs': kwargs}
+
+    s = [
+        _listing('all_default'),
+        _listing('all_with_cpus', gpus_only=False),
+        _listing('no_price', require_price=False),
+        _listing('q1', quantity_filter=1),
+        _listing('q8', quantity_filter=8),
+        _listing('q3', quantity_filter=3),
+        _listing('name_v100', name_filter='V100'),
+        _listing('name_a100_regex', name_filter='^A100'),
+        _listing('name_a10_prefix', name_filter='A10'),
+        _listing('name_lower_insensitive', name_filter='a10',
+                 case_sensitive=False),
+        _listing('name_lower_sensitive', name_filter='a10'),
+        _listing('name_alt', name_filter='T4|L4|K80'),
+        _listing('name_tpu', name_filter='tpu'),
+        _listing('name_tpu_v3_regions', name_filter='tpu-v3',
+                 all_regions=True),
+        _listing('name_none', name_filter='NoSuchGpu'),
+        _listing('region_us', region_filter='us-'),
+        _listing('region_europe', region_filter='europe|eu-'),
+        _listing('region_upper_insensitive', region_filter='US-WEST',
+                 case_sensitive=False),
+        _listing('v100_all_regions', name_filter='V100', all_regions=True),
+        _listing('h100_q8_all_regions', name_filter='H100', quantity_filter=8,
+                 all_regions=True),
+        _listing('t4_us_q1', name_filter='T4', region_filter='us',
+                 quantity_filter=1),
+    ]
+    for c in clouds:
+        s.append(_listing(f'{c}_only', clouds=c))
+        s.append(_listing(f'{c}_a100_regions', clouds=c, name_filter='A100',
+                          all_regions=True))
+        s.append(_listing(f'{c}_no_price_q2', clouds=c, require_price=False,
+                          quantity_filter=2))
+    if len(clouds) > 1:
+        s.append(_listing('two_clouds', clouds=clouds[:2],
+                          name_filter='V100|T4'))
+    return s
+
+
+LISTING_SUITES = {
+    'multi6k': listing_cases,
+    'three4k': lambda: listing_cases(('aws', 'gcp', 'azure')),
+}
