@@ -1174,7 +1174,7 @@ __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
 
 // ---------------------------------------------------------------------------
 // K3: one block per DAG.
-constexpr int kSolveThreads = 256;
+constexpr int kSolveThreads = 1024;  // 32 warps: one per task of a short chain
 constexpr int kMaxDagTasks = 16;  // exact search only; chains are unbounded
 constexpr int kFastTasks = 32;    // chain DP kept in shared memory
 constexpr int kDpCap = 1024;      // ... when every task has <= kDpCap candidates
@@ -1356,20 +1356,28 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
 
   const double kInf = __longlong_as_double(0x7FF0000000000000ll);
 
-  // ---- Phase B, fast path: short chains whose candidate tables fit in
-  // shared memory. Same recurrence and operation order as the general path
-  // below; the DP state, the per-edge tariffs and the back-pointers (kept per
-  // (task, child cloud): the best parent only depends on the child's cloud)
-  // never leave the SM, so a task costs two barriers instead of several
-  // dependent global round trips.
+  // ---- Phase B, fast path for chains of up to kFastTasks tasks. The
+  // recurrence  dp[c] = value[c] + min_p (dp[p] + egress(p, c))  is the
+  // reference's (optimizer.py:456-470), but it is not evaluated task after
+  // task: egress depends on the two clouds only and x -> fl(x + e) is
+  // monotone, so with  mv[t][g] = min value of task t's candidates in cloud g
+  // (all tasks at once) the per-cloud minima of dp obey a recurrence over
+  // C-vectors,
+  //   B[t][h] = min_g fl(D[t-1][g] + e_t(g, h)),  D[t][g] = fl(mv[t][g] + B[t][g]),
+  // which one warp walks in shared memory; the winners (first minimum in
+  // candidate order, as the strict '<' of the reference picks) are then found
+  // for all (task, child cloud) pairs in parallel from the same sums the
+  // reference forms. Three barriers instead of two per task.
   {
     __shared__ int s_tn[kFastTasks], s_src[kFastTasks], s_np[kFastTasks];
     __shared__ long long s_toff[kFastTasks];
     __shared__ double s_tar[kFastTasks][SKYOPT_MAX_CLOUDS];
-    __shared__ double s_dpb[2][kDpCap];
-    __shared__ unsigned char s_clb[2][kDpCap];
-    __shared__ int s_bk_idx[kFastTasks][SKYOPT_MAX_CLOUDS];
-    __shared__ unsigned char s_bk_cl[kFastTasks][SKYOPT_MAX_CLOUDS];
+    __shared__ unsigned long long s_mv[kFastTasks][SKYOPT_MAX_CLOUDS];  // price_key(min value)
+    __shared__ double s_B[kFastTasks][SKYOPT_MAX_CLOUDS];
+    __shared__ double s_D[kFastTasks][SKYOPT_MAX_CLOUDS];
+    __shared__ int s_bk_idx[kFastTasks + 1][SKYOPT_MAX_CLOUDS];
+    __shared__ unsigned char s_bk_cl[kFastTasks + 1][SKYOPT_MAX_CLOUDS];
+    __shared__ double s_obj;
     __shared__ int s_fast;
     if (tid == 0) s_fast = (D.is_chain && T <= kFastTasks) ? 1 : 0;
     __syncthreads();
@@ -1381,101 +1389,89 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
         s_toff[tid] = in.task_off[t];
         s_np[tid] = TK.n_parents;
         s_src[tid] = TK.n_parents ? TK.edge_tariff_begin : TK.src_tariff_begin;
-        if (out.task_n[t] > kDpCap) s_fast = 0;
       }
+      for (int i = tid; i < T * C; i += kSolveThreads) s_mv[i / C][i % C] = kKeyNone;
       __syncthreads();
-    }
-    if (s_fast) {
       for (int i = tid; i < T * C; i += kSolveThreads) {
         const int lt = i / C, cc = i % C;
         s_tar[lt][cc] = s_src[lt] >= 0 ? in.tariffs[s_src[lt] + cc] : 0.0;
       }
-      __syncthreads();
-      int cur = 0;
-      constexpr int kPer = kDpCap / kSolveThreads;
-      // The next task's values / clouds are fetched while the current task
-      // is reduced (software pipelining over the dependent chain of tasks).
-      double vn[kPer]; int cn[kPer];
-      auto fetch = [&](int lt) {
+      // per-(task, cloud) minimum value, every task at once (a warp per task)
+      for (int lt = warp; lt < T; lt += kWarps) {
         const int n = s_tn[lt];
         const long long toff = s_toff[lt];
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          const int c = tid + k * kSolveThreads;
-          if (c < n) { vn[k] = w.tc_value[toff + c]; cn[k] = w.tc_cloud[toff + c]; }
-        }
-      };
-      fetch(0);
-      for (int lt = 0; lt < T; ++lt) {
-        const int n = s_tn[lt];
-        double v[kPer]; int c4[kPer];
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) { v[k] = vn[k]; c4[k] = cn[k]; }
-        if (lt + 1 < T) fetch(lt + 1);
-        if (s_np[lt] == 0) {
-          if (tid < C) {
-            // parent = dummy source: 0 + egress from the inputs' cloud
-            s_best_val[tid] = s_tar[lt][tid];
-            s_best_idx[tid] = 0;
-            s_bk_idx[lt][tid] = 0; s_bk_cl[lt][tid] = 0;
-          }
-        } else {
-          const int np = s_tn[lt - 1];
-          const double *dpp = s_dpb[cur ^ 1];
-          const unsigned char *clp = s_clb[cur ^ 1];
-          for (int cc = warp; cc < C; cc += kWarps) {
-            double bv = kInf; int bi = 0x7FFFFFFF;
-            for (int p = lane; p < np; p += 32) {
-              const int cp = clp[p];
-              const double eg = (cp != cc) ? s_tar[lt][cp] : 0.0;
-              lexmin(bv, bi, __dadd_rn(dpp[p], eg), p);
-            }
-            for (int o = 16; o; o >>= 1) {
-              const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
-              const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
-              lexmin(bv, bi, ov, oi);
-            }
-            if (lane == 0) {
-              s_best_val[cc] = bv; s_best_idx[cc] = bi;
-              s_bk_idx[lt][cc] = bi;
-              s_bk_cl[lt][cc] = (bi != 0x7FFFFFFF) ? clp[bi] : 0;
-            }
-          }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          const int c = tid + k * kSolveThreads;
-          if (c < n) {
-            s_dpb[cur][c] = __dadd_rn(v[k], s_best_val[c4[k]]);
-            s_clb[cur][c] = (unsigned char)c4[k];
-          }
-        }
-        __syncthreads();
-        cur ^= 1;
+        for (int c = lane; c < n; c += 32)
+          atomicMin(&s_mv[lt][w.tc_cloud[toff + c]], (unsigned long long)price_key(w.tc_value[toff + c]));
       }
-      // sink: 0 + min_p dp[p] (egress to the dummy sink is 0)
-      const int last = cur ^ 1;
-      const int n = s_tn[T - 1];
-      double bv = kInf; int bi = 0x7FFFFFFF;
-      for (int p = tid; p < n; p += kSolveThreads) lexmin(bv, bi, s_dpb[last][p], p);
-      for (int o = 16; o; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
-        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
-        lexmin(bv, bi, ov, oi);
+      __syncthreads();
+      if (warp == 0) {
+        // the C-vector recurrence: lane h owns cloud h
+        for (int lt = 0; lt < T; ++lt) {
+          if (lane < C) {
+            double b;
+            if (s_np[lt] == 0) {
+              b = s_tar[lt][lane];  // dummy source: 0 + egress from the inputs' cloud
+            } else {
+              b = kInf;
+              for (int g = 0; g < C; ++g) {
+                const double e = (g != lane) ? s_tar[lt][g] : 0.0;
+                const double v = __dadd_rn(s_D[lt - 1][g], e);
+                if (v < b) b = v;
+              }
+            }
+            s_B[lt][lane] = b;
+            const unsigned long long mk = s_mv[lt][lane];
+            s_D[lt][lane] = (mk == kKeyNone) ? kInf : __dadd_rn(key_price(mk), b);
+          }
+          __syncwarp();
+        }
       }
-      if (lane == 0) { s_red_val[warp] = bv; s_red_idx[warp] = bi; }
+      __syncthreads();
+      // winners: pair (lt, h) = first minimum over task lt's candidates p of
+      // fl(dp[p] + e_{lt+1}(cloud(p), h)); the pair (T-1, 0) is the dummy sink
+      // (egress 0).
+      const int n_pairs = (T - 1) * C + 1;
+      for (int pr = warp; pr < n_pairs; pr += kWarps) {
+        const bool sink = pr == n_pairs - 1;
+        const int lt = sink ? T - 1 : pr / C;    // parent task
+        const int h = sink ? 0 : pr % C;         // child cloud
+        double bv = kInf; int bi = 0x7FFFFFFF;
+        // a child cloud without candidates never asks for its parent
+        if (sink || s_mv[lt + 1][h] != kKeyNone) {
+          const int n = s_tn[lt];
+          const long long toff = s_toff[lt];
+          for (int p = lane; p < n; p += 32) {
+            const int cp = w.tc_cloud[toff + p];
+            const double dpp = __dadd_rn(w.tc_value[toff + p], s_B[lt][cp]);
+            const double e = (!sink && cp != h) ? s_tar[lt + 1][cp] : 0.0;
+            lexmin(bv, bi, sink ? dpp : __dadd_rn(dpp, e), p);
+          }
+          for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            lexmin(bv, bi, ov, oi);
+          }
+        }
+        if (lane == 0) {
+          const int slot_t = sink ? T : lt + 1;  // indexed by the child task
+          s_bk_idx[slot_t][h] = bi;
+          s_bk_cl[slot_t][h] = (bi != 0x7FFFFFFF) ? (unsigned char)w.tc_cloud[s_toff[lt] + bi] : 0;
+          if (sink) s_obj = bv;
+        }
+      }
       __syncthreads();
       if (tid == 0) {
-        for (int k = 1; k < kWarps; ++k) lexmin(bv, bi, s_red_val[k], (int)s_red_idx[k]);
-        SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = bv;
+        SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = s_obj;
         out.dag[blockIdx.x] = r;
-        int idx = bi;
-        int cl = s_clb[last][bi];
+        int idx = s_bk_idx[T][0];
+        int cl = s_bk_cl[T][0];
         for (int lt = T - 1; lt >= 0; --lt) {
           out.chosen_index[D.task_begin + lt] = idx;
-          idx = s_bk_idx[lt][cl];
-          cl = s_bk_cl[lt][cl];
+          if (lt > 0) {
+            const int ni = s_bk_idx[lt][cl];
+            cl = s_bk_cl[lt][cl];
+            idx = ni;
+          }
         }
       }
     }
