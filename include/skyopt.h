@@ -331,6 +331,22 @@ int skyopt_scan(SkyoptCatalog *cat, const SkyoptQuery *queries, int n_queries,
                 double *fuzzy_prices, int fuzzy_cap, SkyoptStats *stats);
 
 /*
+ * Cheapest offering per group for accelerator listings: the reduction inside
+ * list_accelerators_impl (sky/catalog/common.py:756-768,
+ * sort_values(['Price', 'SpotPrice'[, 'Region']]).drop_duplicates(keep=
+ * 'first')). group_ids are global instance-type ids (by_acc_key == 0) or
+ * accelerator-key ids (by_acc_key != 0: GCP's accelerator-only rows,
+ * gcp_catalog.py:445-571) of `cloud`. region_mask (may be NULL = every region)
+ * has one bit per region of the cloud (local region id). out_rows receives,
+ * per group, the catalog row of the winner -- or, with per_region, one row
+ * per region of the cloud ([n_groups][n_regions_of_cloud]); -1 = no row.
+ */
+int skyopt_list_offerings(SkyoptCatalog *cat, int cloud, int by_acc_key,
+                          const int32_t *group_ids, int n_groups,
+                          const uint32_t *region_mask, int per_region,
+                          int32_t *out_rows);
+
+/*
  * The fused hot path: Optimizer._optimize_dag (optimizer.py:1381-1512) for a
  * batch of independent DAGs -- scan, expansion, cost, blocked filter and
  * chain DP / exact DAG search stay on the device; one H2D and one D2H copy.

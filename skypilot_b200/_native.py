@@ -171,7 +171,7 @@ EXPORTS = (
     'skyopt_catalog_create', 'skyopt_catalog_destroy', 'skyopt_catalog_bytes',
     'skyopt_scan', 'skyopt_optimize', 'skyopt_optimize_timed',
     'skyopt_catalog_set_scan_mode', 'skyopt_price_key',
-    'skyopt_solve_tables',
+    'skyopt_solve_tables', 'skyopt_list_offerings',
 )
 
 _lib = None
@@ -218,6 +218,10 @@ def load() -> ctypes.CDLL:
         lib.skyopt_solve_tables.argtypes = [
             ctypes.c_void_p, _p, _p, _p, _p, ctypes.c_int, _p, ctypes.c_int, _p,
             ctypes.c_int, _p, ctypes.c_int, _p, _p
+        ]
+        lib.skyopt_list_offerings.argtypes = [
+            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _p, ctypes.c_int, _p,
+            ctypes.c_int, _p
         ]
         lib.skyopt_scan.argtypes = [
             ctypes.c_void_p, _p, ctypes.c_int, _p, ctypes.c_int, _p, _p, _p,

@@ -103,6 +103,56 @@ def _map_clouds_catalog(clouds: Union[None, str, List[str]], method: str,
     return results[0] if single else results
 
 
+def list_accelerators(gpus_only: bool = True, name_filter: Optional[str] = None,
+                      region_filter: Optional[str] = None,
+                      quantity_filter: Optional[int] = None, clouds=None,
+                      case_sensitive: bool = True, all_regions: bool = False,
+                      require_price: bool = True):
+    """Accelerators offered by the loaded clouds -> {name: [InstanceTypeInfo]}
+    (sky/catalog/__init__.py:56-85). The per-row reduction runs on the device
+    (`skyopt_list_offerings`, catalog/listing.py)."""
+    results = _map_clouds_catalog(clouds, 'list_accelerators', gpus_only,
+                                  name_filter, region_filter, quantity_filter,
+                                  case_sensitive, all_regions, require_price)
+    if not isinstance(results, list):
+        results = [results]
+    merged: Dict[str, list] = {}
+    for result in results:
+        for gpu, items in result.items():
+            merged.setdefault(gpu, []).extend(items)
+    return merged
+
+
+def list_accelerator_counts(gpus_only: bool = True,
+                            name_filter: Optional[str] = None,
+                            region_filter: Optional[str] = None,
+                            quantity_filter: Optional[int] = None,
+                            clouds=None) -> Dict[str, List[float]]:
+    """{accelerator: sorted available counts}
+    (sky/catalog/__init__.py:88-119)."""
+    results = _map_clouds_catalog(clouds, 'list_accelerators', gpus_only,
+                                  name_filter, region_filter, quantity_filter,
+                                  all_regions=False, require_price=False)
+    if not isinstance(results, list):
+        results = [results]
+    counts: Dict[str, set] = {}
+    for result in results:
+        for gpu, items in result.items():
+            for item in items:
+                counts.setdefault(gpu, set()).add(item.accelerator_count)
+    return {gpu: sorted(c) for gpu, c in counts.items()}
+
+
+def get_arch_from_instance_type(instance_type: str, clouds=None):
+    return _map_clouds_catalog(clouds, 'get_arch_from_instance_type',
+                               instance_type)
+
+
+def get_local_disk_from_instance_type(instance_type: str, clouds=None):
+    return _map_clouds_catalog(clouds, 'get_local_disk_from_instance_type',
+                               instance_type)
+
+
 def instance_type_exists(instance_type: str, clouds=None) -> bool:
     return _map_clouds_catalog(clouds, 'instance_type_exists', instance_type)
 

@@ -126,3 +126,20 @@ class CloudCatalog:
         return common.get_region_zones_for_instance_type_impl(
             self._view(), instance_type, use_spot,
             us_first=self.rules.us_regions_first)
+
+    def list_accelerators(self, gpus_only: bool,
+                          name_filter: Optional[str] = None,
+                          region_filter: Optional[str] = None,
+                          quantity_filter: Optional[int] = None,
+                          case_sensitive: bool = True,
+                          all_regions: bool = False,
+                          require_price: bool = True):
+        """Instance types offering accelerators, grouped by accelerator name
+        (`list_accelerators` of sky/catalog/aws_catalog.py:339-352 and the
+        other single-table clouds; common.py:697-790)."""
+        del require_price  # unused, as in the reference
+        from skypilot_b200.catalog import listing  # pylint: disable=import-outside-toplevel
+        return listing.generic_listing(self.cloud, self._view(), gpus_only,
+                                       name_filter, region_filter,
+                                       quantity_filter, case_sensitive,
+                                       all_regions)

@@ -14,3 +14,4 @@ get_arch_from_instance_type = _impl.get_arch_from_instance_type
 get_local_disk_from_instance_type = _impl.get_local_disk_from_instance_type
 get_instance_type_for_accelerator = _impl.get_instance_type_for_accelerator
 get_region_zones_for_instance_type = _impl.get_region_zones_for_instance_type
+list_accelerators = _impl.list_accelerators

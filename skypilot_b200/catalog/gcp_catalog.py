@@ -146,3 +146,17 @@ def get_accelerator_hourly_cost(accelerator: str, count: int,
         return float('nan')
     # `hourly` = host (0 here) + accelerator price
     return float(np.min(cands['hourly']))
+
+
+def list_accelerators(gpus_only: bool, name_filter: Optional[str] = None,
+                      region_filter: Optional[str] = None,
+                      quantity_filter: Optional[int] = None,
+                      case_sensitive: bool = True, all_regions: bool = False,
+                      require_price: bool = True):
+    """GPUs / TPUs offered by GCP with the price of accelerator + cheapest
+    host VM of the zone (gcp_catalog.py:445-571)."""
+    from skypilot_b200.catalog import listing  # pylint: disable=import-outside-toplevel
+    return listing.gcp_listing(_impl._view(), gpus_only, name_filter,  # pylint: disable=protected-access
+                               region_filter, quantity_filter, case_sensitive,
+                               all_regions, require_price)
+

@@ -1,0 +1,388 @@
+"""Accelerator listings: `sky.catalog.list_accelerators` on the device catalog.
+
+Mirrors sky/catalog/common.py:697-790 (`list_accelerators_impl`), the GCP
+variant sky/catalog/gcp_catalog.py:445-571 and the merge in
+sky/catalog/__init__.py:56-85. The row work -- for every instance type (or
+GCP accelerator key) the cheapest (Price, SpotPrice) row, per region when
+`all_regions` -- is `skyopt_list_offerings`; GCP's "cheapest host VM of the
+accelerator's zone" join is one `skyopt_scan` batch. What stays on the host is
+per *type*, not per row: the regex filters over the dictionary of names, the
+final ordering of a few hundred entries, and building the tuples.
+"""
+import ast
+import math
+import re
+from typing import Any, Dict, List, NamedTuple, Optional, Tuple
+
+import numpy as np
+
+from skypilot_b200 import _native
+from skypilot_b200 import engine
+from skypilot_b200.catalog import rules
+
+_NAN = float('nan')
+
+
+class InstanceTypeInfo(NamedTuple):
+    """sky/catalog/common.py:38-62."""
+    cloud: str
+    instance_type: Optional[str]
+    accelerator_name: str
+    accelerator_count: float
+    cpu_count: Optional[float]
+    device_memory: Optional[float]
+    memory: Optional[float]
+    price: float
+    spot_price: float
+    region: str
+
+
+CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
+                 'lambda': 'Lambda'}
+
+
+def _isnan(x) -> bool:
+    return x is None or (isinstance(x, float) and math.isnan(x))
+
+
+def _nan_last(x) -> Tuple[int, float]:
+    return (1, 0.0) if _isnan(x) else (0, float(x))
+
+
+def _search(pattern: str, text: Any, case_sensitive: bool) -> bool:
+    """pandas `str.contains(pattern, case=..., regex=True)` on one value."""
+    if _isnan(text):
+        return False
+    return re.search(pattern, str(text),
+                     0 if case_sensitive else re.IGNORECASE) is not None
+
+
+class _TypeMeta:
+    """Per-instance-type columns of a cloud (first CSV row of the type)."""
+
+    def __init__(self, table):
+        frame = table.frame
+        rows = table.inst_first_row
+        ok = rows >= 0
+        idx = np.where(ok, rows, 0)
+
+        def col(name, default=None):
+            if name in frame.columns:
+                values = frame[name].to_numpy(dtype=object)[idx]
+            else:
+                values = np.full(len(idx), default, dtype=object)
+            return values
+
+        self.acc_name = col('AcceleratorName')
+        self.acc_count = col('AcceleratorCount')
+        self.vcpus = col('vCPUs')
+        self.mem = col('MemoryGiB')
+        self.gpu_info = col('GpuInfo')
+
+
+def _type_meta(table) -> _TypeMeta:
+    meta = table.__dict__.get('_type_meta')
+    if meta is None:
+        meta = _TypeMeta(table)
+        table.__dict__['_type_meta'] = meta
+    return meta
+
+
+def _device_memory_table(table, gpus_only: bool) -> Optional[Dict[str, float]]:
+    """GiB of the first GPU per distinct GpuInfo text, or None when any
+    considered row does not hold the AWS-style dict (then the reference sets
+    the column to None for every row, common.py:716-729)."""
+    cache = table.__dict__.setdefault('_device_memory', {})
+    if gpus_only in cache:
+        return cache[gpus_only]
+    frame = table.frame
+    result: Optional[Dict[str, float]] = {}
+    if 'GpuInfo' not in frame.columns:
+        result = None
+    else:
+        info = frame['GpuInfo']
+        if not gpus_only and info.isna().any():
+            result = None  # literal_eval(nan) -> ValueError
+        else:
+            try:
+                for text in info.dropna().unique():
+                    parsed = ast.literal_eval(text)
+                    result[text] = (
+                        parsed['Gpus'][0]['MemoryInfo']['SizeInMiB'] / 1024.0)
+            except (ValueError, SyntaxError):
+                result = None
+    cache[gpus_only] = result
+    return result
+
+
+def _region_mask(table, region_filter: Optional[str],
+                 case_sensitive: bool) -> Optional[np.ndarray]:
+    if region_filter is None:
+        return None
+    n = max(len(table.region_names), 1)
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    for i, name in enumerate(table.region_names):
+        if _search(region_filter, name, case_sensitive):
+            words[i >> 5] |= np.uint32(1 << (i & 31))
+    return words
+
+
+def _offer_rows(store, table, device: int, by_acc_key: bool,
+                group_ids: List[int], mask: Optional[np.ndarray],
+                per_region: bool) -> np.ndarray:
+    """Winner rows [n_groups, n_regions or 1] (global row ids, -1 = none)."""
+    n_regions = max(len(table.region_names), 1)
+    slots = n_regions if per_region else 1
+    out = np.full((len(group_ids), slots), -1, dtype=np.int32)
+    if not group_ids:
+        return out
+    ids = np.ascontiguousarray(group_ids, dtype=np.int32)
+    lib = _native.load()
+    handle = store.handle(device)
+    _native.check(
+        lib.skyopt_list_offerings(handle, table.index, int(by_acc_key),
+                                  ids.ctypes.data, len(ids),
+                                  _native.ptr(mask), int(per_region),
+                                  out.ctypes.data))
+    return out
+
+
+def _finalize(cloud: str, entries: List[tuple],
+              all_regions: bool) -> Dict[str, List[InstanceTypeInfo]]:
+    """`entries`: (order, instance_type, name, count, cpus, device_memory,
+    memory, price, spot, region) in any order. Applies the tail of
+    list_accelerators_impl (common.py:756-790): per accelerator, rows sorted
+    by (Price, SpotPrice[, Region]) with NaN last (stable in CSV order), first
+    row per (type, name, count, cpus, memory[, region]) kept, then the
+    reference's Python sort."""
+    groups: Dict[str, List[tuple]] = {}
+    for e in sorted(entries, key=lambda e: e[0]):
+        groups.setdefault(e[2], []).append(e)
+    out: Dict[str, List[InstanceTypeInfo]] = {}
+    for name in sorted(groups):
+        members = groups[name]
+        if all_regions:
+            members = sorted(members, key=lambda e: (_nan_last(e[7]),
+                                                     _nan_last(e[8]), e[9]))
+        else:
+            members = sorted(members,
+                             key=lambda e: (_nan_last(e[7]), _nan_last(e[8])))
+        first: Dict[tuple, tuple] = {}
+        for e in members:
+            ident = (None if _isnan(e[1]) else e[1], e[2], float(e[3]),
+                     None if _isnan(e[4]) else e[4],
+                     None if _isnan(e[6]) else e[6])
+            if all_regions:
+                ident += (e[9],)
+            first.setdefault(ident, e)
+        infos = [
+            InstanceTypeInfo(cloud, e[1], e[2], float(e[3]), e[4], e[5], e[6],
+                             e[7], e[8], e[9]) for e in first.values()
+        ]
+        infos.sort(key=lambda i: (i.accelerator_count, i.instance_type,
+                                  i.cpu_count if not _isnan(i.cpu_count) else 0,
+                                  i.price, i.spot_price, i.region))
+        out[name] = infos
+    return out
+
+
+def _instance_entries(store, table, device: int, gpus_only: bool,
+                      name_filter: Optional[str], region_filter: Optional[str],
+                      quantity_filter: Optional[int], case_sensitive: bool,
+                      all_regions: bool) -> List[tuple]:
+    """Entries of the instance types that carry accelerators."""
+    meta = _type_meta(table)
+    mask = _region_mask(table, region_filter, case_sensitive)
+    dev = _device_memory_table(table, gpus_only)
+    selected = []
+    for j in range(len(table.inst_names)):
+        name = meta.acc_name[j]
+        if _isnan(name):
+            continue
+        if gpus_only and _isnan(meta.gpu_info[j]):
+            continue
+        if name_filter is not None and not _search(name_filter, name,
+                                                   case_sensitive):
+            continue
+        if quantity_filter is not None and float(
+                meta.acc_count[j]) != quantity_filter:
+            continue
+        selected.append(j)
+    cols = store.columns
+    rows = _offer_rows(store, table, device, False,
+                       [table.inst_begin + j for j in selected], mask,
+                       all_regions)
+    price, spot, region = cols['price'], cols['spot_price'], cols['region_id']
+    entries = []
+    for k, j in enumerate(selected):
+        memory = None
+        if dev is not None and not _isnan(meta.gpu_info[j]):
+            memory = dev[meta.gpu_info[j]]
+        for row in rows[k]:
+            if row < 0:
+                continue
+            entries.append(
+                (int(row), table.inst_names[j], str(meta.acc_name[j]),
+                 float(meta.acc_count[j]), meta.vcpus[j], memory, meta.mem[j],
+                 float(price[row]), float(spot[row]),
+                 table.region_names[int(region[row])]))
+    return entries
+
+
+def generic_listing(cloud: str, view, gpus_only: bool,
+                    name_filter: Optional[str], region_filter: Optional[str],
+                    quantity_filter: Optional[int], case_sensitive: bool = True,
+                    all_regions: bool = False
+                   ) -> Dict[str, List[InstanceTypeInfo]]:
+    """`list_accelerators_impl` for a cloud whose accelerators come with the
+    instance type (AWS, Azure, Lambda, ...)."""
+    entries = _instance_entries(view.store, view.table, view.device, gpus_only,
+                                name_filter, region_filter, quantity_filter,
+                                case_sensitive, all_regions)
+    return _finalize(CLOUD_DISPLAY.get(cloud, cloud), entries, all_regions)
+
+
+# --------------------------------------------------------------------- GCP
+def _acc_key_entries(store, table, device: int, keys: List[int],
+                     mask: Optional[np.ndarray], all_regions: bool,
+                     order_base: int) -> List[tuple]:
+    """Entries of accelerator-only rows (InstanceType NaN): TPUs, and every
+    accelerator when no price is required."""
+    cols = store.columns
+    rows = _offer_rows(store, table, device, True, keys, mask, all_regions)
+    price, spot, region = cols['price'], cols['spot_price'], cols['region_id']
+    entries = []
+    for k, key in enumerate(keys):
+        name, count = store.acc_keys[key]
+        for row in rows[k]:
+            if row < 0:
+                continue
+            entries.append((order_base + int(row), _NAN, name, float(count),
+                            _NAN, None, _NAN, float(price[row]),
+                            float(spot[row]),
+                            table.region_names[int(region[row])]))
+    return entries
+
+
+def _gcp_acc_keys(store, table) -> List[int]:
+    """Accelerator keys that have accelerator-only rows in this cloud."""
+    cached = table.__dict__.get('_acc_only_keys')
+    if cached is None:
+        cols = store.columns
+        offs = cols['acc_row_offsets']
+        acc_rows = cols['acc_rows']
+        cached = []
+        for k in range(len(store.acc_keys)):
+            b, e = int(offs[k]), int(offs[k + 1])
+            if e > b and np.any((acc_rows[b:e] >= table.row_begin) &
+                                (acc_rows[b:e] < table.row_end)):
+                cached.append(k)
+        table.__dict__['_acc_only_keys'] = cached
+    return cached
+
+
+def _gcp_host_spec(builder, name: str, count: int, region: str,
+                   zone: str) -> Dict[str, Any]:
+    """The host-VM filter of one accelerator row (gcp_catalog.py:460-487)."""
+    if name in rules.GCP_FIXED_HOSTS:
+        group = rules.GCP_GROUP_IDS[(name, count)]  # KeyError like the reference
+        return builder.cpus_mem_query('gcp', None, None, region, zone,
+                                      group=group)
+    table = rules.GCP_ACC_HOST_CPUS.get(name, rules.GCP_ACC_HOST_CPUS['DEFAULT'])
+    cpus = table[count]
+    memory = cpus * rules.GCP_GPU_MEMORY_CPU_RATIO
+    return builder.cpus_mem_query('gcp', f'{cpus}+', f'{memory}+', region,
+                                  zone, flags_require=_native.F_HOST_FAMILY)
+
+
+def gcp_listing(view, gpus_only: bool, name_filter: Optional[str],
+                region_filter: Optional[str], quantity_filter: Optional[int],
+                case_sensitive: bool = True, all_regions: bool = False,
+                require_price: bool = True
+               ) -> Dict[str, List[InstanceTypeInfo]]:
+    store, table, device = view.store, view.table, view.device
+    cols = store.columns
+    mask = _region_mask(table, region_filter, case_sensitive)
+    keys = []
+    for k in _gcp_acc_keys(store, table):
+        name, count = store.acc_keys[k]
+        # accelerator rows of the GCP catalog carry GpuInfo (= the name)
+        if name_filter is not None and not _search(name_filter, name,
+                                                   case_sensitive):
+            continue
+        if quantity_filter is not None and (
+                int(count) if require_price else float(count)) != quantity_filter:
+            continue
+        keys.append(k)
+    tpu_keys = [k for k in keys if store.acc_keys[k][0].startswith('tpu-')]
+    gpu_keys = [k for k in keys if not store.acc_keys[k][0].startswith('tpu-')]
+    big = int(store.n_rows)
+    entries: List[tuple] = []
+    if not require_price:
+        # whole frame: accelerator-only rows keep their own price, instance
+        # types that carry accelerators are listed like on other clouds
+        entries += _instance_entries(store, table, device, gpus_only,
+                                     name_filter, region_filter,
+                                     quantity_filter, case_sensitive,
+                                     all_regions)
+        entries += _acc_key_entries(store, table, device, keys, mask,
+                                    all_regions, 0)
+    else:
+        # one host-VM look-up per accelerator row, as a single scan batch
+        offs, acc_rows = cols['acc_row_offsets'], cols['acc_rows']
+        price, spot = cols['price'], cols['spot_price']
+        region_id, zone_id = cols['region_id'], cols['zone_id']
+        builder = engine.ProblemBuilder(store)
+        query_of: Dict[tuple, int] = {}
+        wanted = []  # (acc row, query, key)
+        for k in gpu_keys:
+            name, count = store.acc_keys[k]
+            for row in acc_rows[int(offs[k]):int(offs[k + 1])]:
+                row = int(row)
+                if row < table.row_begin or row >= table.row_end:
+                    continue
+                rg = int(region_id[row])
+                if mask is not None and not (int(mask[rg >> 5]) >> (rg & 31)) & 1:
+                    continue
+                zn = int(zone_id[row])
+                if zn == _native.NONE16 or math.isnan(price[row]):
+                    continue
+                region, zone = table.region_names[rg], table.zone_names[zn]
+                spec = _gcp_host_spec(builder, name, int(count), region, zone)
+                ident = (spec['flags_require'], spec['group'], spec['cpus_op'],
+                         spec['cpus'], spec['mem_op'], spec['mem'], rg, zn)
+                q = query_of.get(ident)
+                if q is None:
+                    q = builder.add_query(spec)
+                    query_of[ident] = q
+                wanted.append((row, q, k))
+        if wanted:
+            result = engine.scan(builder, device=device).results
+            vcpus, mem, inst = cols['vcpus'], cols['mem'], cols['inst_id']
+            for row, q, k in wanted:
+                host = int(result['best_row'][q])
+                if host < 0:
+                    continue  # no host VM in that zone
+                name, count = store.acc_keys[k]
+                entries.append(
+                    (row, store.inst_names[int(inst[host])], name,
+                     float(int(count)), float(vcpus[host]), None,
+                     float(mem[host]), float(price[row] + price[host]),
+                     float(spot[row] + spot[host]),
+                     table.region_names[int(region_id[row])]))
+        entries += _acc_key_entries(store, table, device, tpu_keys, mask,
+                                    all_regions, big)
+    results = _finalize('GCP', entries, all_regions)
+    if require_price and tpu_keys:
+        # one entry per TPU generation (gcp_catalog.py:553-570)
+        for name in list(results.keys()):
+            if name.startswith('tpu-'):
+                version = name.split('-')[1]
+                infos = results.pop(name)
+                results.setdefault(f'tpu-{version}', []).extend(infos)
+        for name in list(results.keys()):
+            if name.startswith('tpu-'):
+                results[name] = sorted(
+                    results[name],
+                    key=lambda i: (i.price, i.spot_price, i.region))
+    return results

@@ -957,6 +957,50 @@ int skyopt_catalog_bytes(const SkyoptCatalog *c, int64_t *device_bytes, int64_t 
   return 0;
 }
 
+int skyopt_list_offerings(SkyoptCatalog *cat, int cloud, int by_acc_key,
+                          const int32_t *group_ids, int n_groups,
+                          const uint32_t *region_mask, int per_region,
+                          int32_t *out_rows) {
+  if (!cat || !group_ids || !out_rows || n_groups <= 0) return fail(SKYOPT_EINVAL, "bad arguments");
+  if (cloud < 0 || cloud >= cat->dev.n_clouds) return fail(SKYOPT_EINVAL, "cloud %d out of range", cloud);
+  const int n_max = by_acc_key ? cat->dev.n_acc_keys : cat->dev.n_inst;
+  for (int i = 0; i < n_groups; ++i)
+    if (group_ids[i] < 0 || group_ids[i] >= n_max) return fail(SKYOPT_EINVAL, "group %d: id %d out of range", i, group_ids[i]);
+  const int n_regions = cat->cloud_region_offsets[cloud + 1] - cat->cloud_region_offsets[cloud];
+  const int slots = per_region ? std::max(n_regions, 1) : 1;
+  const size_t smem = (size_t)slots * 20 + 8;
+  if (smem > 48 * 1024) return fail(SKYOPT_ELIMIT, "cloud has too many regions (%d)", n_regions);
+  CU(cudaSetDevice(cat->device));
+  Ctx *x = nullptr;
+  int rc = acquire(cat, &x);
+  if (rc) return rc;
+  int32_t *d_ids = nullptr, *d_out = nullptr; uint32_t *d_mask = nullptr;
+  const int mask_words = (std::max(n_regions, 1) + 31) / 32;
+  auto body = [&]() -> int {
+    cudaStream_t st = x->stream;
+    CU(cudaMalloc(&d_ids, sizeof(int32_t) * (size_t)n_groups));
+    CU(cudaMalloc(&d_out, sizeof(int32_t) * (size_t)n_groups * slots));
+    CU(cudaMemcpyAsync(d_ids, group_ids, sizeof(int32_t) * (size_t)n_groups, cudaMemcpyHostToDevice, st));
+    if (region_mask) {
+      CU(cudaMalloc(&d_mask, sizeof(uint32_t) * (size_t)mask_words));
+      CU(cudaMemcpyAsync(d_mask, region_mask, sizeof(uint32_t) * (size_t)mask_words, cudaMemcpyHostToDevice, st));
+    }
+    offer_kernel<<<n_groups, 128, smem, st>>>(cat->dev, cloud, by_acc_key ? 1 : 0, d_ids, d_mask,
+                                              per_region ? 1 : 0, std::max(n_regions, 1), d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_rows, d_out, sizeof(int32_t) * (size_t)n_groups * slots, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+  };
+  rc = body();
+  if (rc) cudaStreamSynchronize(x->stream);
+  if (d_ids) cudaFree(d_ids);
+  if (d_out) cudaFree(d_out);
+  if (d_mask) cudaFree(d_mask);
+  release(cat, x);
+  return rc;
+}
+
 int skyopt_scan(SkyoptCatalog *cat, const SkyoptQuery *queries, int n_queries,
                 const uint32_t *acc_sets, int n_acc_sets, SkyoptScanResult *results,
                 int32_t *list_ids, double *list_prices, int list_cap,

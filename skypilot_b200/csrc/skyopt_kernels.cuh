@@ -1710,6 +1710,69 @@ __global__ void table_kernel(SolveIn in, SolveWork w, const int32_t *task_n,
 }
 
 // Evict the catalog from L2 between timed iterations (bench.py).
+// Cheapest offering of each group (an instance type's rows, or -- GCP -- the
+// accelerator-only rows of one (name, count) key): the row with the
+// lexicographically smallest (Price, SpotPrice), missing values last, first
+// CSV row on ties -- what list_accelerators_impl keeps after
+// sort_values(['Price', 'SpotPrice'[, 'Region']]).drop_duplicates(keep='first')
+// (common.py:756-768) -- over the regions the caller's filter allows; with
+// `per_region` one winner per region. One block per group; three passes over
+// the group's rows with shared-memory atomics (price, then spot price among
+// the cheapest, then row).
+__global__ void __launch_bounds__(128)
+offer_kernel(CatDev cat, int cloud, int by_acc_key, const int32_t *__restrict__ group_ids,
+             const uint32_t *__restrict__ region_mask, int per_region, int n_regions,
+             int32_t *__restrict__ out_rows) {
+  extern __shared__ unsigned long long offer_smem[];
+  const int slots = per_region ? n_regions : 1;
+  unsigned long long *best_p = offer_smem;          // [slots]
+  unsigned long long *best_s = best_p + slots;      // [slots]
+  unsigned int *best_row = reinterpret_cast<unsigned int *>(best_s + slots);  // [slots]
+  const int g = group_ids[blockIdx.x];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < slots; i += blockDim.x) { best_p[i] = kKeyNone; best_s[i] = kKeyNone; best_row[i] = kRowNone; }
+  __syncthreads();
+  const int32_t *rows = by_acc_key ? cat.acc_rows : cat.inst_rows;
+  const int32_t *offs = by_acc_key ? cat.acc_row_offsets : cat.inst_row_offsets;
+  const int b = offs[g], e = offs[g + 1];
+  const int r0 = cat.cloud_row_offsets[cloud], r1 = cat.cloud_row_offsets[cloud + 1];
+  auto allowed = [&](int row, int &slot) {
+    if (row < r0 || row >= r1) return false;
+    const int rg = cat.region_id[row];
+    if (region_mask && !((region_mask[rg >> 5] >> (rg & 31)) & 1u)) return false;
+    slot = per_region ? rg : 0;
+    return true;
+  };
+  auto keys = [&](int row, unsigned long long &pk, unsigned long long &sk) {
+    const double p = cat.price[row], sp = cat.spot[row];
+    pk = (p == p) ? price_key(p) : kKeyNaN;
+    sk = (sp == sp) ? price_key(sp) : kKeyNaN;
+  };
+  for (int i = b + tid; i < e; i += blockDim.x) {
+    const int row = rows[i]; int slot;
+    if (!allowed(row, slot)) continue;
+    unsigned long long pk, sk; keys(row, pk, sk);
+    atomicMin(&best_p[slot], pk);
+  }
+  __syncthreads();
+  for (int i = b + tid; i < e; i += blockDim.x) {
+    const int row = rows[i]; int slot;
+    if (!allowed(row, slot)) continue;
+    unsigned long long pk, sk; keys(row, pk, sk);
+    if (pk == best_p[slot]) atomicMin(&best_s[slot], sk);
+  }
+  __syncthreads();
+  for (int i = b + tid; i < e; i += blockDim.x) {
+    const int row = rows[i]; int slot;
+    if (!allowed(row, slot)) continue;
+    unsigned long long pk, sk; keys(row, pk, sk);
+    if (pk == best_p[slot] && sk == best_s[slot]) atomicMin(&best_row[slot], (unsigned int)row);
+  }
+  __syncthreads();
+  for (int i = tid; i < slots; i += blockDim.x)
+    out_rows[(int64_t)blockIdx.x * slots + i] = (best_row[i] == kRowNone) ? -1 : (int32_t)best_row[i];
+}
+
 __global__ void flush_kernel(uint32_t *buf, int64_t n, uint32_t v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
