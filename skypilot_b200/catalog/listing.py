@@ -95,22 +95,19 @@ def _device_memory_table(table, gpus_only: bool) -> Optional[Dict[str, float]]:
     cache = table.__dict__.setdefault('_device_memory', {})
     if gpus_only in cache:
         return cache[gpus_only]
-    frame = table.frame
     result: Optional[Dict[str, float]] = {}
-    if 'GpuInfo' not in frame.columns:
+    if table.gpu_info_unique is None:
         result = None
+    elif not gpus_only and table.gpu_info_any_nan:
+        result = None  # literal_eval(nan) -> ValueError
     else:
-        info = frame['GpuInfo']
-        if not gpus_only and info.isna().any():
-            result = None  # literal_eval(nan) -> ValueError
-        else:
-            try:
-                for text in info.dropna().unique():
-                    parsed = ast.literal_eval(text)
-                    result[text] = (
-                        parsed['Gpus'][0]['MemoryInfo']['SizeInMiB'] / 1024.0)
-            except (ValueError, SyntaxError):
-                result = None
+        try:
+            for text in table.gpu_info_unique:
+                parsed = ast.literal_eval(text)
+                result[text] = (
+                    parsed['Gpus'][0]['MemoryInfo']['SizeInMiB'] / 1024.0)
+        except (ValueError, SyntaxError):
+            result = None
     cache[gpus_only] = result
     return result
 

@@ -20,6 +20,8 @@ Row order inside a cloud is the CSV order; "cheapest" ties resolve to the
 lowest row id (the reference's single-key sort is unstable).
 """
 import ctypes
+import hashlib
+import json
 import os
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -47,6 +49,9 @@ def price_keys(values: np.ndarray) -> np.ndarray:
     bits = np.ascontiguousarray(values, dtype=np.float64).view(np.uint64)
     neg = (bits >> np.uint64(63)).astype(bool)
     return np.where(neg, ~bits, bits | np.uint64(1 << 63))
+
+
+CACHE_VERSION = 1  # layout of the columnar cache written by CatalogStore.save
 
 
 def _zone_map(cols: Dict[str, np.ndarray]) -> np.ndarray:
@@ -105,6 +110,10 @@ class CloudTable:
         self.inst_index: Dict[str, int] = {}  # name -> GLOBAL id
         self.frame: Optional[pd.DataFrame] = None  # original rows (metadata)
         self.inst_first_row: Optional[np.ndarray] = None  # local row ids
+        # summary of the 'GpuInfo' column (accelerator listings): None = no
+        # such column
+        self.gpu_info_any_nan = False
+        self.gpu_info_unique: Optional[List[str]] = []
 
 
 class CatalogStore:
@@ -148,6 +157,12 @@ class CatalogStore:
             table = CloudTable(name, ci)
             table.frame = df
             n = len(df)
+            if 'GpuInfo' in df.columns:
+                info = df['GpuInfo']
+                table.gpu_info_any_nan = bool(info.isna().any())
+                table.gpu_info_unique = [str(t) for t in info.dropna().unique()]
+            else:
+                table.gpu_info_unique = None
             table.n_rows = n
             table.row_begin = cloud_row_offsets[-1]
             table.row_end = table.row_begin + n
@@ -348,24 +363,137 @@ class CatalogStore:
     @classmethod
     def from_directory(cls,
                        path: str,
-                       clouds: Optional[Sequence[str]] = None
-                      ) -> 'CatalogStore':
+                       clouds: Optional[Sequence[str]] = None,
+                       use_cache: bool = True) -> 'CatalogStore':
         """Loads `<path>/<cloud>/vms.csv` (the reference's on-disk layout,
-        sky/catalog/common.py:33-35, :65-68)."""
-        frames = {}
+        sky/catalog/common.py:33-35, :65-68).
+
+        The parsed catalog is kept next to the CSVs as a columnar binary cache
+        (`<path>/.skyopt_cache/<key>/`, see `save`): the reference re-parses
+        the CSVs in every process (`pd.read_csv` behind LazyDataFrame,
+        common.py:126-164, ~1.5 s for the public catalog); a warm start here
+        maps the same columns that are uploaded to the GPU. The key covers the
+        files' names, sizes and modification times, so an edited or refreshed
+        CSV is parsed again."""
+        path = os.path.expanduser(path)
         names = clouds
         if names is None:
             names = sorted(
                 d for d in os.listdir(path)
                 if os.path.exists(os.path.join(path, d, 'vms.csv')))
-        for name in names:
-            csv = os.path.join(path, name, 'vms.csv')
-            if not os.path.exists(csv):
-                continue
-            frames[name] = pd.read_csv(csv)
-        if not frames:
+        files = [(name, os.path.join(path, name, 'vms.csv')) for name in names]
+        files = [(name, csv) for name, csv in files if os.path.exists(csv)]
+        if not files:
             raise FileNotFoundError(f'no <cloud>/vms.csv below {path}')
-        return cls.from_frames(frames, order=list(frames.keys()))
+        cache_dir = None
+        if use_cache:
+            sig = []
+            for name, csv in files:
+                st = os.stat(csv)
+                sig.append([name, st.st_size, st.st_mtime_ns])
+            key = hashlib.sha256(
+                json.dumps([CACHE_VERSION, sig]).encode()).hexdigest()[:24]
+            cache_dir = os.path.join(path, '.skyopt_cache', key)
+            if os.path.exists(os.path.join(cache_dir, 'meta.json')):
+                try:
+                    return cls.load(cache_dir)
+                except (OSError, ValueError, KeyError):
+                    pass  # unreadable cache: parse the CSVs again
+        frames = {name: pd.read_csv(csv) for name, csv in files}
+        store = cls.from_frames(frames, order=list(frames.keys()))
+        if cache_dir is not None:
+            try:
+                store.save(cache_dir)
+            except OSError:
+                pass  # read-only catalog directory: stay uncached
+        return store
+
+    # ------------------------------------------------------ columnar cache
+    def save(self, directory: str) -> None:
+        """Writes the catalog as a columnar binary cache: `columns.npz` (the
+        SoA columns exactly as they are uploaded, zone map included),
+        `meta.json` (dictionaries: region / zone / instance-type names,
+        accelerator keys) and `types_<cloud>.parquet` (one CSV row per
+        instance type, for metadata look-ups)."""
+        os.makedirs(directory, exist_ok=True)
+        arrays = {k: v for k, v in self.columns.items() if v is not None}
+        tmp = os.path.join(directory, 'columns.tmp.npz')
+        np.savez(tmp, **arrays)
+        os.replace(tmp, os.path.join(directory, 'columns.npz'))
+        meta = {
+            'version': CACHE_VERSION, 'n_rows': self.n_rows,
+            'n_real_rows': self.n_real_rows,
+            'max_group_rows': self.max_group_rows,
+            'acc_keys': [[n, c] for n, c in self.acc_keys],
+            'inst_cloud': self.inst_cloud, 'clouds': []
+        }
+        for t in self.clouds:
+            rows = t.inst_first_row
+            types = t.frame.iloc[np.where(rows >= 0, rows, 0)].reset_index(
+                drop=True)
+            types.to_parquet(os.path.join(directory, f'types_{t.name}.parquet'))
+            meta['clouds'].append({
+                'name': t.name, 'row_begin': t.row_begin, 'row_end': t.row_end,
+                'n_rows': t.n_rows, 'region_names': t.region_names,
+                'zone_names': t.zone_names, 'zone_region': t.zone_region,
+                'has_zone_column': t.has_zone_column,
+                'inst_begin': t.inst_begin, 'inst_names': t.inst_names,
+                'inst_has_row': [bool(r >= 0) for r in rows],
+                'gpu_info_any_nan': t.gpu_info_any_nan,
+                'gpu_info_unique': t.gpu_info_unique,
+            })
+        tmp = os.path.join(directory, 'meta.tmp.json')
+        with open(tmp, 'w', encoding='utf-8') as f:
+            json.dump(meta, f)
+        os.replace(tmp, os.path.join(directory, 'meta.json'))  # commit point
+
+    @classmethod
+    def load(cls, directory: str) -> 'CatalogStore':
+        """Inverse of `save`: no CSV parsing, no per-row work."""
+        with open(os.path.join(directory, 'meta.json'), encoding='utf-8') as f:
+            meta = json.load(f)
+        if meta.get('version') != CACHE_VERSION:
+            raise ValueError('catalog cache version mismatch')
+        store = cls()
+        with np.load(os.path.join(directory, 'columns.npz')) as data:
+            for k in data.files:
+                store.columns[k] = np.ascontiguousarray(data[k])
+        store.columns.setdefault('disk_total', None)
+        store.n_rows = int(meta['n_rows'])
+        store.n_real_rows = int(meta['n_real_rows'])
+        store.max_group_rows = int(meta['max_group_rows'])
+        store.acc_keys = [(str(n), float(c)) for n, c in meta['acc_keys']]
+        store.acc_key_index = {k: i for i, k in enumerate(store.acc_keys)}
+        store.acc_names_lower = [k[0].lower() for k in store.acc_keys]
+        store.inst_cloud = [int(c) for c in meta['inst_cloud']]
+        for ci, m in enumerate(meta['clouds']):
+            t = CloudTable(m['name'], ci)
+            t.row_begin, t.row_end = int(m['row_begin']), int(m['row_end'])
+            t.n_rows = int(m['n_rows'])
+            t.region_names = list(m['region_names'])
+            t.region_exact = {nm: i for i, nm in enumerate(t.region_names)}
+            t.region_lower = {nm.lower(): i
+                              for i, nm in enumerate(t.region_names)}
+            t.zone_names = list(m['zone_names'])
+            t.zone_exact = {nm: i for i, nm in enumerate(t.zone_names)}
+            t.zone_lower = {nm.lower(): i for i, nm in enumerate(t.zone_names)}
+            t.zone_region = [int(v) for v in m['zone_region']]
+            t.has_zone_column = bool(m['has_zone_column'])
+            t.inst_begin = int(m['inst_begin'])
+            t.inst_names = list(m['inst_names'])
+            t.inst_index = {nm: t.inst_begin + i
+                            for i, nm in enumerate(t.inst_names)}
+            t.frame = pd.read_parquet(
+                os.path.join(directory, f'types_{t.name}.parquet'))
+            has_row = np.asarray(m['inst_has_row'], dtype=bool)
+            t.inst_first_row = np.where(has_row, np.arange(len(has_row)),
+                                        -1).astype(np.int64)
+            t.gpu_info_any_nan = bool(m['gpu_info_any_nan'])
+            t.gpu_info_unique = m['gpu_info_unique']
+            store.inst_names.extend(t.inst_names)
+            store.clouds.append(t)
+            store.cloud_index[t.name] = ci
+        return store
 
     # --------------------------------------------------------------- look-ups
     def cloud(self, name: str) -> CloudTable:

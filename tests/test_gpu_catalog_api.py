@@ -257,3 +257,28 @@ def test_optimize_batch_matches_one_by_one():
     assert any(w is None for w in want) and any(w is not None for w in want)
     with pytest.raises(sky.exceptions.ResourcesUnavailableError):
         sky.optimize_batch(dags, devices=devices)
+
+
+def test_optimize_on_a_cache_loaded_catalog(tmp_path):
+    """A store read back from the columnar cache plans like the parsed one."""
+    from skypilot_b200 import synth
+    from skypilot_b200.catalog.store import CatalogStore
+    spec = dict(scenarios.CATALOGS['multi6k'])
+    spec.pop('enabled', None)
+    frames = synth.make_catalogs(**spec)
+    for cloud, df in frames.items():
+        (tmp_path / cloud).mkdir()
+        df.to_csv(tmp_path / cloud / 'vms.csv', index=False)
+    names = list(frames.keys())
+    plans = []
+    for _ in range(2):  # first: parse + write the cache, second: cache hit
+        store = CatalogStore.from_directory(str(tmp_path), clouds=names)
+        sky.catalog.set_store(store)
+        dag, tasks = runner.build_dag(scenarios.basic_scenarios()[0])
+        sky.Optimizer.optimize(dag, quiet=True)
+        plans.append([runner.res_record(t.best_resources) for t in tasks])
+        listing = sky.catalog.list_accelerators(clouds=names,
+                                                name_filter='V100')
+        plans.append({k: [tuple(i) for i in v] for k, v in listing.items()})
+    assert plans[0] == plans[2]
+    assert repr(plans[1]) == repr(plans[3])

@@ -297,3 +297,70 @@ def test_dummy_nodes_round_trip():
     assert len(dag.tasks) == 4 and dag.is_chain()
     Optimizer._remove_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
     assert dag.tasks == [a, b]
+
+
+# ---------------------------------------------------------------------------
+# columnar catalog cache (CatalogStore.save / load / from_directory)
+def _write_catalog_dir(tmp_path, frames):
+    for cloud, df in frames.items():
+        (tmp_path / cloud).mkdir()
+        df.to_csv(tmp_path / cloud / 'vms.csv', index=False)
+
+
+def _assert_same_store(a, b):
+    assert set(a.columns) == set(b.columns)
+    for k, v in a.columns.items():
+        w = b.columns[k]
+        if v is None:
+            assert w is None
+            continue
+        assert v.dtype == w.dtype and v.shape == w.shape, k
+        assert v.tobytes() == w.tobytes(), k  # NaN payloads included
+    assert a.acc_keys == b.acc_keys and a.inst_names == b.inst_names
+    assert a.n_rows == b.n_rows and a.max_group_rows == b.max_group_rows
+    for ta, tb in zip(a.clouds, b.clouds):
+        assert ta.name == tb.name
+        assert ta.region_names == tb.region_names
+        assert ta.zone_names == tb.zone_names
+        assert ta.zone_region == tb.zone_region
+        assert ta.inst_index == tb.inst_index
+        assert ta.gpu_info_unique == tb.gpu_info_unique
+        assert ta.gpu_info_any_nan == tb.gpu_info_any_nan
+
+
+def test_catalog_cache_round_trip(tmp_path):
+    from skypilot_b200 import synth
+    from skypilot_b200.catalog.store import CatalogStore
+    frames = synth.make_catalogs(seed=5, n_rows=3000,
+                                 clouds=['aws', 'gcp', 'azure', 'lambda'])
+    _write_catalog_dir(tmp_path, frames)
+    parsed = CatalogStore.from_directory(str(tmp_path), use_cache=False)
+    first = CatalogStore.from_directory(str(tmp_path))    # writes the cache
+    cached = CatalogStore.from_directory(str(tmp_path))   # reads it
+    caches = os.listdir(tmp_path / '.skyopt_cache')
+    assert len(caches) == 1
+    _assert_same_store(parsed, first)
+    _assert_same_store(parsed, cached)
+    # metadata look-ups work on the per-type frame of a cached store
+    row_a = parsed.instance_row('aws', 'p3.2xlarge')
+    row_b = cached.instance_row('aws', 'p3.2xlarge')
+    for col in ('InstanceType', 'AcceleratorName', 'AcceleratorCount', 'vCPUs',
+                'MemoryGiB', 'Arch'):
+        assert row_a[col] == row_b[col]
+
+
+def test_catalog_cache_is_invalidated_by_an_edited_csv(tmp_path):
+    from skypilot_b200 import synth
+    from skypilot_b200.catalog.store import CatalogStore
+    frames = synth.make_catalogs(seed=6, n_rows=2000, clouds=['aws'])
+    _write_catalog_dir(tmp_path, frames)
+    CatalogStore.from_directory(str(tmp_path))
+    df = frames['aws'].copy()
+    df.loc[0, 'Price'] = 123.456
+    df.to_csv(tmp_path / 'aws' / 'vms.csv', index=False)
+    st = os.stat(tmp_path / 'aws' / 'vms.csv')
+    os.utime(tmp_path / 'aws' / 'vms.csv', ns=(st.st_atime_ns,
+                                                st.st_mtime_ns + 10**9))
+    again = CatalogStore.from_directory(str(tmp_path))
+    assert again.columns['price'][0] == 123.456
+    assert len(os.listdir(tmp_path / '.skyopt_cache')) == 2
