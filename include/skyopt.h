@@ -372,6 +372,27 @@ int skyopt_solve_tables(SkyoptCatalog *cat, const double *values,
                         int32_t *chosen_index, SkyoptDagResult *results);
 
 /*
+ * Failover re-optimisation (the provisioner's retry loop,
+ * sky/backends/cloud_vm_ray_backend.py:332-339, :1817-1825: every failed launch
+ * adds a wildcard to blocked_resources and calls Optimizer.optimize again).
+ * A session runs skyopt_optimize once and keeps the expanded candidate sets
+ * of its DAGs resident on the device; skyopt_session_resolve then only
+ * uploads a new blocked list (applied to every DAG of the session), re-runs
+ * the blocked filter + cost kernel and the solver, and reads the plan back --
+ * no catalog scan, no region/zone expansion. The session owns a private
+ * stream and workspace until it is closed; `problem`'s own blocked entries
+ * are the list of the first solve.
+ */
+typedef struct SkyoptSession SkyoptSession;
+int skyopt_session_open(SkyoptCatalog *cat, const SkyoptProblem *problem,
+                        SkyoptSolution *solution, SkyoptStats *stats,
+                        SkyoptSession **out);
+int skyopt_session_resolve(SkyoptSession *session, const SkyoptBlocked *blocked,
+                           int n_blocked, SkyoptSolution *solution,
+                           SkyoptStats *stats);
+void skyopt_session_close(SkyoptSession *session);
+
+/*
  * Device-resident timing loop for bench.py: uploads `problem` once, then runs
  * the kernels `iters` times, flushing L2 (writing a buffer > 126 MB) before
  * every iteration when flush_l2 != 0; per-iteration device times (CUDA

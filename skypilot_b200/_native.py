@@ -172,6 +172,7 @@ EXPORTS = (
     'skyopt_scan', 'skyopt_optimize', 'skyopt_optimize_timed',
     'skyopt_catalog_set_scan_mode', 'skyopt_price_key',
     'skyopt_solve_tables', 'skyopt_list_offerings',
+    'skyopt_session_open', 'skyopt_session_resolve', 'skyopt_session_close',
 )
 
 _lib = None
@@ -219,6 +220,20 @@ def load() -> ctypes.CDLL:
             ctypes.c_void_p, _p, _p, _p, _p, ctypes.c_int, _p, ctypes.c_int, _p,
             ctypes.c_int, _p, ctypes.c_int, _p, _p
         ]
+        lib.skyopt_session_open.argtypes = [
+            ctypes.c_void_p,
+            ctypes.POINTER(Problem),
+            ctypes.POINTER(Solution),
+            ctypes.POINTER(Stats),
+            ctypes.POINTER(ctypes.c_void_p)
+        ]
+        lib.skyopt_session_resolve.argtypes = [
+            ctypes.c_void_p, _p, ctypes.c_int,
+            ctypes.POINTER(Solution),
+            ctypes.POINTER(Stats)
+        ]
+        lib.skyopt_session_close.argtypes = [ctypes.c_void_p]
+        lib.skyopt_session_close.restype = None
         lib.skyopt_list_offerings.argtypes = [
             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _p, ctypes.c_int, _p,
             ctypes.c_int, _p

@@ -1097,6 +1097,121 @@ int skyopt_optimize(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution 
   return rc;
 }
 
+struct SkyoptSession {
+  SkyoptCatalog *cat = nullptr;
+  Ctx *x = nullptr;
+  Plan P;
+  std::vector<SkyoptDag> dags;       // host copy: task ranges, flags
+  SkyoptBlocked *d_blocked = nullptr;
+  SkyoptDag *d_dags = nullptr;
+  int blocked_cap = 0;
+};
+
+int skyopt_session_open(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution *sol,
+                        SkyoptStats *stats, SkyoptSession **out) {
+  if (!cat || !pb || !sol || !out) return fail(SKYOPT_EINVAL, "NULL argument");
+  *out = nullptr;
+  if (pb->n_dags <= 0 || pb->n_tasks <= 0 || pb->n_slots <= 0)
+    return fail(SKYOPT_EINVAL, "empty problem");
+  int rc = validate_problem(cat, pb);
+  if (rc) return rc;
+  CU(cudaSetDevice(cat->device));
+  SkyoptSession *s = new (std::nothrow) SkyoptSession();
+  if (!s) return fail(SKYOPT_ENOMEM, "out of host memory");
+  s->cat = cat;
+  if ((rc = acquire(cat, &s->x))) { delete s; return rc; }
+  Ctx *x = s->x;
+  auto body = [&]() -> int {
+    int r = build_plan(cat, pb, x, s->P);
+    if (r) return r;
+    cudaStream_t st = x->stream;
+    CU(cudaEventRecord(x->ev[0], st));
+    CU(cudaMemcpyAsync(x->dbuf, x->hbuf, s->P.in_bytes, cudaMemcpyHostToDevice, st));
+    s->P.want_finalize = sol->scan != nullptr;
+    if ((r = enqueue_kernels(cat, x, s->P, true, sol->scan != nullptr))) return r;
+    CU(cudaMemcpyAsync(x->hbuf, x->dbuf + s->P.out_off, s->P.out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(x->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    if ((r = copy_solution(cat, x, s->P, pb, sol))) return r;
+    return fill_stats(x, s->P, stats, true);
+  };
+  rc = body();
+  if (rc) {
+    cudaStreamSynchronize(x->stream);
+    release(cat, x);
+    delete s;
+    return rc;
+  }
+  s->dags.assign(pb->dags, pb->dags + pb->n_dags);
+  *out = s;
+  return 0;
+}
+
+int skyopt_session_resolve(SkyoptSession *s, const SkyoptBlocked *blocked, int n_blocked,
+                           SkyoptSolution *sol, SkyoptStats *stats) {
+  if (!s || !sol || n_blocked < 0 || (n_blocked > 0 && !blocked)) return fail(SKYOPT_EINVAL, "bad arguments");
+  SkyoptCatalog *cat = s->cat;
+  Ctx *x = s->x;
+  Plan &P = s->P;
+  CU(cudaSetDevice(cat->device));
+  cudaStream_t st = x->stream;
+  if (n_blocked > s->blocked_cap || !s->d_dags) {
+    const int cap = std::max(64, 2 * n_blocked);
+    SkyoptBlocked *nb = nullptr;
+    CU(cudaMalloc(&nb, sizeof(SkyoptBlocked) * (size_t)cap));
+    if (s->d_blocked) { CU(cudaStreamSynchronize(st)); cudaFree(s->d_blocked); }
+    s->d_blocked = nb; s->blocked_cap = cap;
+    if (!s->d_dags) CU(cudaMalloc(&s->d_dags, sizeof(SkyoptDag) * s->dags.size()));
+  }
+  for (SkyoptDag &d : s->dags) { d.blocked_begin = 0; d.blocked_end = n_blocked; }
+  // The copies below read pageable host memory: they are staged before the
+  // call returns, and the stream is synchronised further down.
+  if (n_blocked) CU(cudaMemcpyAsync(s->d_blocked, blocked, sizeof(SkyoptBlocked) * (size_t)n_blocked, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(s->d_dags, s->dags.data(), sizeof(SkyoptDag) * s->dags.size(), cudaMemcpyHostToDevice, st));
+  P.blocked = s->d_blocked; P.dags = s->d_dags;
+  CU(cudaEventRecord(x->ev[0], st));
+  CU(cudaEventRecord(x->ev[1], st));
+  CU(cudaEventRecord(x->ev[6], st)); CU(cudaEventRecord(x->ev[7], st));
+  CU(cudaEventRecord(x->ev[2], st));
+  CU(cudaEventRecord(x->ev[3], st));
+  {
+    ExpandOut ex{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
+    SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex, 0};
+    SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
+    SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres};
+    gather_kernel<<<P.nt, kGatherThreads, 0, st>>>(cat->dev, in, w, P.task_dag, P.task_n);
+    CU(cudaGetLastError());
+    solve_kernel<<<P.nd, kSolveThreads, 0, st>>>(cat->dev, in, w, out);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(x->ev[4], st));
+  CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(x->ev[5], st));
+  CU(cudaStreamSynchronize(st));
+  SkyoptProblem pb{};
+  pb.dags = s->dags.data(); pb.n_dags = (int)s->dags.size();
+  int rc = copy_solution(cat, x, P, &pb, sol);
+  if (rc) return rc;
+  rc = fill_stats(x, P, stats, true);
+  if (stats && !rc) {
+    // nothing was scanned or expanded this time
+    stats->scan_launches = 0; stats->total_launches = 2;
+    stats->scan_rows = 0; stats->scan_passes_rows = 0; stats->scan_blocks = 0;
+    stats->scan_kernel_ms = 0.f;
+  }
+  return rc;
+}
+
+void skyopt_session_close(SkyoptSession *s) {
+  if (!s) return;
+  cudaSetDevice(s->cat->device);
+  cudaStreamSynchronize(s->x->stream);
+  if (s->d_blocked) cudaFree(s->d_blocked);
+  if (s->d_dags) cudaFree(s->d_dags);
+  release(s->cat, s->x);
+  delete s;
+}
+
 int skyopt_solve_tables(SkyoptCatalog *cat, const double *values, const int32_t *clouds,
                         const int64_t *task_offsets, const SkyoptTask *tasks, int n_tasks,
                         const int32_t *parents, int n_parents, const double *tariffs,

@@ -537,6 +537,55 @@ def solve(builder: ProblemBuilder,
     return sol
 
 
+class Session:
+    """`skyopt_session_*`: one full solve, then re-solves under a new blocked
+    list with the candidate sets kept on the device (failover loop)."""
+
+    def __init__(self, builder: ProblemBuilder, device: int = 0,
+                 want_tables: bool = False):
+        self.builder = builder
+        self.want_tables = want_tables
+        self._lib = _native.load()
+        self._handle = ctypes.c_void_p()
+        self.packed = builder.pack()
+        if self.packed.n_slots == 0:
+            raise ValueError('a session needs at least one slot')
+        self.solution = Solution(self.packed, want_tables)
+        prob = self.packed.c_problem()
+        csol = self.solution.c_solution()
+        _native.check(
+            self._lib.skyopt_session_open(builder.store.handle(device),
+                                          ctypes.byref(prob),
+                                          ctypes.byref(csol),
+                                          ctypes.byref(self.solution.stats),
+                                          ctypes.byref(self._handle)))
+
+    def resolve(self, blocked: List[Dict[str, int]]) -> Solution:
+        """Re-masks and re-solves; `blocked` are `add_blocked`-style dicts."""
+        if not self._handle:
+            raise RuntimeError('session is closed')
+        rows = ProblemBuilder._pack(blocked, _native.BLOCKED_DTYPE)  # pylint: disable=protected-access
+        sol = Solution(self.packed, self.want_tables)
+        csol = sol.c_solution()
+        _native.check(
+            self._lib.skyopt_session_resolve(
+                self._handle, rows.ctypes.data if len(blocked) else None,
+                len(blocked), ctypes.byref(csol), ctypes.byref(sol.stats)))
+        self.solution = sol
+        return sol
+
+    def close(self) -> None:
+        if self._handle:
+            self._lib.skyopt_session_close(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
 def solve_timed(builder: ProblemBuilder, iters: int, flush_l2: bool = True,
                 device: int = 0):
     """Device-resident timing loop (bench.py): per-iteration kernel times."""

@@ -429,6 +429,15 @@ class Optimizer:
         finally:
             for task, original in saved.items():
                 task.resources = original
+        return Optimizer._apply_solution(problem, sol, graph, topo_order,
+                                         topo_real, minimize_cost, blocked,
+                                         quiet)
+
+    @staticmethod
+    def _apply_solution(problem, sol, graph, topo_order, topo_real,
+                        minimize_cost, blocked, quiet):
+        """Device result -> `best_resources` of every task (or the reference's
+        ResourcesUnavailableError)."""
         res = sol.dag[0]
         if res['status'] == 1:
             failed = topo_real[int(res['task_fail'])]
@@ -459,6 +468,13 @@ class Optimizer:
             Optimizer.print_optimized_plan(problem, sol, total_time,
                                            total_cost)
         return best_plan
+
+    @staticmethod
+    def session(dag: 'dag_lib.Dag',
+                minimize: OptimizeTarget = OptimizeTarget.COST,
+                quiet: bool = True) -> 'OptimizerSession':
+        """Failover re-optimisation of one DAG: see OptimizerSession."""
+        return OptimizerSession(dag, minimize, quiet)
 
     @staticmethod
     def _resolve_ordered_resources(dag, blocked) -> Dict[Any, Any]:
@@ -707,6 +723,86 @@ class Optimizer:
                 f'${float(sol.chosen[i]["hourly"]):.4f}/hr '
                 f'({int(sol.task_n[i])} candidates)')
         logger.info('Optimizer plan:\n  ' + '\n  '.join(lines))
+
+
+class OptimizerSession:
+    """`Optimizer.optimize(dag, blocked_resources=...)` for the provisioner's
+    failover loop (sky/backends/cloud_vm_ray_backend.py:332-339, :1817-1825),
+    where the same DAG is optimised again and again under a growing blocked
+    list. The first `optimize()` is a full device solve; the expanded
+    candidate sets stay on the device, and every later call only uploads the
+    blocked wildcards and re-runs the blocked filter and the solver
+    (`skyopt_session_resolve`). Results are those of `Optimizer.optimize`.
+
+        with Optimizer.session(dag) as s:
+            s.optimize()
+            while launch_failed:
+                blocked.append(failed_resources)
+                s.optimize(blocked)
+
+    Tasks with ordered (list) resources resolve their choice against the
+    blocked list on the host first (optimizer.py:1403-1448), so they fall back
+    to a full `Optimizer.optimize` per call.
+    """
+
+    def __init__(self, dag, minimize=OptimizeTarget.COST, quiet: bool = True):
+        self.dag = dag
+        self.minimize_cost = minimize == OptimizeTarget.COST
+        self.minimize = minimize
+        self.quiet = quiet
+        self._session: Optional[engine.Session] = None
+        self._problem = None
+        self._fallback = any(isinstance(t.resources, list) for t in dag.tasks)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self) -> None:
+        if self._session is not None:
+            self._session.close()
+            self._session = None
+
+    def optimize(self, blocked_resources=None):
+        blocked = list(blocked_resources or [])
+        if self._fallback:
+            return Optimizer.optimize(self.dag, self.minimize, blocked,
+                                      self.quiet)
+        dag = self.dag
+        _check_specified_clouds(dag)
+        Optimizer._add_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+        try:
+            graph = dag.get_graph()
+            topo_order = list(nx.topological_sort(graph))
+            topo_real = [t for t in topo_order if not _is_dummy(t)]
+            store = catalog.get_store()
+            if self._session is None:
+                problem = Optimizer._state_problem(  # pylint: disable=protected-access
+                    graph, topo_real, self.minimize_cost, blocked,
+                    dag.is_chain())
+                self._problem = problem
+                if problem.builder.n_slots == 0:
+                    sol = Optimizer._solve(problem)  # pylint: disable=protected-access
+                else:
+                    self._session = engine.Session(
+                        problem.builder, device=catalog.get_device(),
+                        want_tables=not self.quiet)
+                    sol = self._session.solution
+                    problem.solution = sol
+            else:
+                scratch = engine.ProblemBuilder(store)
+                for r in blocked:
+                    _add_blocked(scratch, store, r)
+                sol = self._session.resolve(scratch.blocked)
+                self._problem.solution = sol
+            Optimizer._apply_solution(  # pylint: disable=protected-access
+                self._problem, sol, graph, topo_order, topo_real,
+                self.minimize_cost, blocked, self.quiet)
+        finally:
+            Optimizer._remove_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
+        return dag
 
 
 def _cloud_object(name: str) -> clouds.Cloud:

@@ -282,3 +282,53 @@ def test_optimize_on_a_cache_loaded_catalog(tmp_path):
         plans.append({k: [tuple(i) for i in v] for k, v in listing.items()})
     assert plans[0] == plans[2]
     assert repr(plans[1]) == repr(plans[3])
+
+
+def _failover_blocked(sky_mod, plan_record):
+    """The wildcard a failed launch of `plan_record` adds: zone, else region
+    (sky/backends/cloud_vm_ray_backend.py:332-339)."""
+    from skypilot_b200.utils import registry
+    kw = dict(cloud=registry.CLOUD_REGISTRY.from_str(plan_record['cloud']),
+              instance_type=plan_record['instance_type'],
+              region=plan_record['region'])
+    if plan_record['zone'] is not None:
+        kw['zone'] = plan_record['zone']
+    r = sky_mod.Resources(**kw)
+    r._use_spot_specified = False  # pylint: disable=protected-access
+    return r
+
+
+@pytest.mark.parametrize('name', ['acc_V100', 'acc_A100x8', 'cpu_default', 'cfg2_chain8',
+                                  'chain8_spot', 'cfg3_diamond'])
+def test_session_follows_full_reoptimisation(name):
+    """OptimizerSession (candidate sets resident, re-mask + re-solve) gives
+    the plans of a full Optimizer.optimize for a growing blocked list."""
+    runner.activate_catalog(scenarios.CATALOGS['multi6k'])
+    by_name = {s['name']: s for s in scenarios.basic_scenarios()}
+    if name not in by_name:
+        pytest.skip(f'no scenario {name}')
+    sc = by_name[name]
+    dag_a, tasks_a = runner.build_dag(sc)
+    dag_b, tasks_b = runner.build_dag(sc)
+    blocked = []
+    with sky.Optimizer.session(dag_a) as session:
+        for step in range(6):
+            err_a = err_b = None
+            try:
+                session.optimize(blocked)
+            except sky.exceptions.ResourcesUnavailableError as e:
+                err_a = str(e)
+            try:
+                sky.Optimizer.optimize(dag_b, blocked_resources=blocked,
+                                       quiet=True)
+            except sky.exceptions.ResourcesUnavailableError as e:
+                err_b = str(e)
+            assert (err_a is None) == (err_b is None), (step, err_a, err_b)
+            if err_a is not None:
+                assert err_a == err_b
+                break
+            plan_a = [runner.res_record(t.best_resources) for t in tasks_a]
+            plan_b = [runner.res_record(t.best_resources) for t in tasks_b]
+            assert plan_a == plan_b, step
+            # the launch of the first task's placement "fails"
+            blocked.append(_failover_blocked(sky, plan_a[0]))
