@@ -23,12 +23,15 @@ from tests import scenarios  # noqa: E402  pylint: disable=wrong-import-position
 def main():
     """`gen_golden.py [catalog ...]` regenerates the optimizer fixtures,
     `gen_golden.py --listings [catalog ...]` the accelerator listings
-    (tests/golden/accel_<catalog>.json)."""
+    (tests/golden/accel_<catalog>.json), `--job-groups` the JobGroup plans
+    (tests/golden/jobgroup_<catalog>.json)."""
     argv = sys.argv[1:]
     listings = '--listings' in argv
-    argv = [a for a in argv if a != '--listings']
-    suites = scenarios.LISTING_SUITES if listings else scenarios.SUITES
-    prefix = 'accel_' if listings else ''
+    groups = '--job-groups' in argv
+    argv = [a for a in argv if a not in ('--listings', '--job-groups')]
+    suites = (scenarios.LISTING_SUITES if listings else
+              scenarios.JOB_GROUP_SUITES if groups else scenarios.SUITES)
+    prefix = 'accel_' if listings else 'jobgroup_' if groups else ''
     wanted = argv or list(suites.keys())
     out_dir = os.path.join(_REPO, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)

@@ -169,9 +169,60 @@ def run_listing(sky, scenario):
             'order': list(result.keys())}
 
 
+def run_job_group(sky, scenario):
+    """`Optimizer.optimize_job_group` (sky/optimizer.py:1039-1200) on a
+    parallel-execution DAG. Besides the plan, records the common infras the
+    reference found: with several of them and more than one job its choice is
+    the first element of a Python set (see skypilot_b200/optimizer.py)."""
+    from sky import dag as dag_lib
+    from sky import exceptions
+    from sky import optimizer as opt_lib
+    from sky.utils import common as sky_common
+    bootstrap.clear_request_cache()
+    minimize_cost = scenario.get('minimize', 'cost') == 'cost'
+    target = (sky_common.OptimizeTarget.COST
+              if minimize_cost else sky_common.OptimizeTarget.TIME)
+    dag, tasks = build_dag(sky, scenario)
+    dag.name = scenario['name']
+    dag.set_execution(dag_lib.DagExecution.PARALLEL)
+    record = {'name': scenario['name']}
+    # the common infras, computed the reference's way
+    try:
+        launchables = {}
+        for t in tasks:
+            per_req, _, _, _ = opt_lib._fill_in_launchable_resources(
+                t, blocked_resources=None, quiet=True)
+            by_cloud = {}
+            for lst in per_req.values():
+                for res in lst:
+                    by_cloud.setdefault(res.cloud, []).append(res)
+            launchables[t] = by_cloud
+        if all(launchables[t] for t in tasks):
+            common = opt_lib.Optimizer._find_common_infras(launchables)
+            record['common_infras'] = sorted(
+                [str(c).lower(), r] for c, r in common)
+    except exceptions.ResourcesUnavailableError:
+        pass
+    bootstrap.clear_request_cache()
+    try:
+        opt_lib.Optimizer.optimize_job_group(dag, target, None, quiet=True)
+    except exceptions.ResourcesUnavailableError as e:
+        record['error'] = {'type': 'ResourcesUnavailableError',
+                           'message': str(e)}
+        return record
+    record['plan'] = [_res_record(t.best_resources) for t in tasks]
+    record['overrides'] = [[
+        [None if r.cloud is None else str(r.cloud).lower(), r.region]
+        for r in list(t.resources)
+    ] for t in tasks]
+    return record
+
+
 def run_scenario(sky, scenario):
     if scenario.get('kind') == 'list_accelerators':
         return run_listing(sky, scenario)
+    if scenario.get('kind') == 'job_group':
+        return run_job_group(sky, scenario)
     from sky import exceptions
     from sky import optimizer as opt_lib
     from sky.utils import common as sky_common

@@ -1,9 +1,16 @@
 """`Dag`: tasks plus dependency edges (the optimizer-facing part of
 sky/dag.py: context manager, add / remove, `>>` edges, `is_chain` :159-178)."""
+import enum
 import threading
 from typing import List, Optional
 
 import networkx as nx
+
+
+class DagExecution(enum.Enum):
+    """How the tasks of a multi-task DAG run (sky/dag.py:12-19)."""
+    SERIAL = 'serial'      # pipeline
+    PARALLEL = 'parallel'  # job group: all tasks start together
 
 
 class Dag:
@@ -14,6 +21,14 @@ class Dag:
         self.tasks: List['object'] = []
         self.graph = nx.DiGraph()
         self.name: Optional[str] = None
+        self.execution: Optional[DagExecution] = None
+
+    def is_job_group(self) -> bool:
+        """Parallel execution mode makes a DAG a JobGroup (sky/dag.py:91-97)."""
+        return self.execution == DagExecution.PARALLEL
+
+    def set_execution(self, execution: DagExecution) -> None:
+        self.execution = execution
 
     def add(self, task) -> None:
         self.graph.add_node(task)

@@ -15,6 +15,7 @@ of the answer.
 import collections
 import enum
 import logging
+import math
 from typing import Any, Dict, Iterable, List, Optional, Tuple
 
 import networkx as nx
@@ -302,6 +303,134 @@ class Optimizer:
                         raise
                     out[i] = e
         return out
+
+    # -------------------------------------------------------------- job groups
+    @staticmethod
+    def optimize_job_group(dag: 'dag_lib.Dag',
+                           minimize: OptimizeTarget = OptimizeTarget.COST,
+                           blocked_resources: Optional[Iterable[
+                               resources_lib.Resources]] = None,
+                           quiet: bool = False) -> 'dag_lib.Dag':
+        """Places all jobs of a JobGroup on one (cloud, region)
+        (sky/optimizer.py:1039-1200, :1265-1378).
+
+        The candidate tables of every job come from ONE device call (the jobs
+        are stated as independent single-task DAGs); the intersection of
+        their (cloud, region) sets and the per-infra sums run on those tables.
+        Without a common infra each job keeps its own optimum, like
+        `_optimize_independent`.
+
+        Where the reference is not deterministic this implementation is: its
+        `_select_best_infra` looks the infra's Cloud *object* up in the other
+        jobs' candidate dicts, and since every launchable carries a fresh
+        `AWS()` / `GCP()` instance (aws.py:905) the look-up fails for all jobs
+        but the first, every infra is discarded and `common_infras[0]` -- the
+        first element of a Python set of strings -- is returned. Here the
+        infra with the lowest total cost (or time) wins, ties by (cloud,
+        region) order. With exactly one common infra, with one job, and
+        without a common infra both agree.
+        """
+        if not dag.is_job_group():
+            return Optimizer.optimize(dag, minimize, blocked_resources, quiet)
+        minimize_cost = minimize == OptimizeTarget.COST
+        blocked = list(blocked_resources or [])
+        tasks = list(dag.tasks)
+        _check_specified_clouds(dag)
+        enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+            raise_if_no_cloud_access=True)
+        store = catalog.get_store()
+        b = engine.ProblemBuilder(store)
+        problems = []
+        ordered = Optimizer._resolve_ordered_resources(dag, blocked)
+        saved = {t: t.resources for t in ordered}
+        for t, c in ordered.items():
+            t.resources = {c}
+        try:
+            for task in tasks:
+                graph = nx.DiGraph()
+                graph.add_node(task)
+                problems.append(
+                    Optimizer._state_problem(graph, [task], minimize_cost,
+                                             blocked, True, builder=b,
+                                             enabled=enabled))
+        finally:
+            for t, original in saved.items():
+                t.resources = original
+        sol = engine.solve(b, device=catalog.get_device(), want_tables=True)
+        # per job: ordered candidates as (cloud index, region id, value, record)
+        tables = []
+        for i, task in enumerate(tasks):
+            rows = sol.task_table(i) if sol.tables is not None else []
+            if len(rows) == 0:
+                raise exceptions.ResourcesUnavailableError(
+                    f'No resources available for job "{task.name}" '
+                    f'in JobGroup "{dag.name}"')
+            cands = []
+            for cand in rows:
+                info = problems[i].slot_info[int(cand['slot'])]
+                score = float(cand['value'])
+                if task.time_estimator_func is not None:
+                    # unlike the DAG path, the job-group score estimates the
+                    # runtime on the launchable (sky/optimizer.py:1348-1361)
+                    runtime = task.estimate_runtime(
+                        problems[i].launchable(cand))
+                    if runtime is None:
+                        runtime = 3600
+                    score = (float(float(cand['hourly']) * (runtime / 3600)) *
+                             task.num_nodes if minimize_cost else runtime)
+                cands.append((info.table.index, int(cand['region_id']), score,
+                              cand))
+            tables.append(cands)
+        common = Optimizer._find_common_infras(tables)
+        if not common:
+            if not quiet:
+                logger.warning('No common infrastructure found for all jobs. '
+                               'Falling back to independent optimization.')
+            for i, task in enumerate(tasks):
+                task.best_resources = problems[i].launchable(sol.chosen[i])
+            return dag
+        best = Optimizer._select_best_infra(common, tables, store)
+        cloud_idx, region_id = best
+        for i, task in enumerate(tasks):
+            for c, r, _, cand in tables[i]:
+                if c == cloud_idx and r == region_id:
+                    resources = problems[i].launchable(cand)
+                    task.best_resources = resources
+                    # keeps the constraint through re-serialisation
+                    # (sky/optimizer.py:1182-1193)
+                    task.set_resources_override({
+                        'cloud': resources.cloud, 'region': resources.region
+                    })
+                    break
+        if not quiet:
+            table = store.clouds[cloud_idx]
+            logger.info('Selected infrastructure: %s/%s', table.name,
+                        table.region_names[region_id])
+        return dag
+
+    @staticmethod
+    def _find_common_infras(tables) -> List[Tuple[int, int]]:
+        """(cloud, region) pairs every job has a candidate in
+        (sky/optimizer.py:1265-1313), in (cloud, region) order."""
+        common = None
+        for cands in tables:
+            infras = {(c, r) for c, r, _, _ in cands}
+            common = infras if common is None else common & infras
+        return sorted(common or [])
+
+    @staticmethod
+    def _select_best_infra(common, tables, store) -> Tuple[int, int]:
+        """Lowest sum over the jobs of their cheapest (or fastest) candidate
+        on the infra (sky/optimizer.py:1315-1378)."""
+        best, best_score = None, math.inf
+        for infra in common:
+            total = 0.0
+            for cands in tables:
+                total += min(v for c, r, v, _ in cands if (c, r) == infra)
+            if total < best_score:
+                best, best_score = infra, total
+        del store
+        return best if best is not None else common[0]
 
     # ---------------------------------------------------- problem construction
     @staticmethod

@@ -89,6 +89,13 @@ class Task:
         self.resources = resources
         return self
 
+    def set_resources_override(self, override_params) -> 'Task':
+        """Applies the overrides to every alternative
+        (sky/task.py:1330-1338)."""
+        new = [res.copy(**override_params) for res in list(self.resources)]
+        self.set_resources(type(self.resources)(new))
+        return self
+
     def set_time_estimator(self, func) -> 'Task':
         self.time_estimator_func = func
         return self

@@ -350,3 +350,69 @@ LISTING_SUITES = {
     'multi6k': listing_cases,
     'three4k': lambda: listing_cases(('aws', 'gcp', 'azure')),
 }
+
+
+# ---------------------------------------------------------------------------
+# JobGroups (`Optimizer.optimize_job_group`).
+# {'name', 'kind': 'job_group', 'tasks': [...], 'minimize'}; the harness
+# records the plan, the (cloud, region) overrides left on the tasks and the
+# common infras the reference found.
+def _job_group(name, specs, **kw):
+    tasks = []
+    for i, spec in enumerate(specs):
+        spec = dict(spec)
+        extra = {k: spec.pop(k) for k in ('num_nodes', 'time_est')
+                 if k in spec}
+        tasks.append(dict(name=f'job{i}', resources=[spec], **extra))
+    return dict(name=name, kind='job_group', tasks=tasks, **kw)
+
+
+def job_group_cases():
+    return [
+        _job_group('jg_single_v100', [dict(accelerators='V100')]),
+        _job_group('jg_single_cpu_spot', [dict(cpus='8+', use_spot=True)]),
+        _job_group('jg_single_time', [
+            dict(accelerators='A100:8',
+                 time_est={'default': 7200, 'by_cloud': {'gcp': 3600}})
+        ], minimize='time'),
+        _job_group('jg_single_cost_estimator', [
+            dict(accelerators='A100:8',
+                 time_est={'default': 7200, 'by_cloud': {'gcp': 1800}})
+        ]),
+        _job_group('jg_two_region_pinned', [
+            dict(accelerators='V100', cloud='aws', region='us-east-1'),
+            dict(cpus='8+', cloud='aws', region='us-east-1')
+        ]),
+        _job_group('jg_two_gcp_region', [
+            dict(accelerators='T4', cloud='gcp', region='us-central1'),
+            dict(cpus='16+', memory='64+', cloud='gcp', region='us-central1',
+                 num_nodes=2)
+        ]),
+        _job_group('jg_three_spot_region', [
+            dict(accelerators='T4', cloud='aws', region='us-west-2',
+                 use_spot=True),
+            dict(cpus='4+', cloud='aws', region='us-west-2', use_spot=True),
+            dict(memory='32+', cloud='aws', region='us-west-2')
+        ]),
+        _job_group('jg_no_common', [
+            dict(accelerators='V100', cloud='aws'),
+            dict(cpus='8+', cloud='gcp')
+        ]),
+        _job_group('jg_no_common_regions', [
+            dict(cpus='8+', cloud='aws', region='us-east-1'),
+            dict(cpus='8+', cloud='aws', region='us-west-2')
+        ]),
+        _job_group('jg_two_free', [
+            dict(accelerators='V100'), dict(cpus='8+')
+        ]),
+        _job_group('jg_three_one_cloud', [
+            dict(accelerators='A100:8', cloud='gcp'),
+            dict(accelerators='T4', cloud='gcp'), dict(cpus='32+', cloud='gcp')
+        ]),
+        _job_group('jg_unavailable', [
+            dict(accelerators='V100'), dict(accelerators='A100:3')
+        ]),
+    ]
+
+
+JOB_GROUP_SUITES = {'multi6k': job_group_cases}
