@@ -120,7 +120,7 @@ class ClockSampler:
                     self.samples.append([v.strip() for v in out.split(',')])
             except Exception:  # pylint: disable=broad-except
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         self._thread.start()
@@ -398,7 +398,8 @@ def main():
         line['latency_cfg2'] = {
             k: lat[k] for k in ('value', 'unit', 'ms_per_step', 'e2e',
                                 'roofline', 'phases_ms', 'config',
-                                'optimize_p50_ms', 'optimize_p90_ms')
+                                'optimize_p50_ms', 'optimize_p90_ms',
+                                'optimize_cold_p50_ms')
         }
     if rank == 0 and world == 1:
         # ---- CPU baseline: the pandas oracle on a bounded sample
