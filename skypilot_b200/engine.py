@@ -8,6 +8,7 @@ on the GPU. There is no CPU implementation behind these calls.
 """
 import ctypes
 import math
+import struct
 import re
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -142,6 +143,39 @@ def set_table(store: CatalogStore) -> np.ndarray:
     return table
 
 
+_MINUS_ONE_DEFAULT = frozenset(('acc_set', 'fuzzy_set', 'region_id',
+                                'zone_id'))
+_PACKERS: Dict[Any, Tuple[struct.Struct, Tuple[str, ...]]] = {}
+_FORMATS = {'i4': 'i', 'u4': 'I', 'f8': 'd', 'i8': 'q', 'u8': 'Q', 'u2': 'H',
+            'i2': 'h'}
+
+
+def _packer(dtype: np.dtype) -> Tuple[struct.Struct, Tuple[str, ...]]:
+    """struct.Struct equivalent of an aligned numpy record dtype."""
+    key = id(dtype)
+    hit = _PACKERS.get(key)
+    if hit is not None:
+        return hit
+    fmt, names, offset = '<', [], 0
+    for name in dtype.names:
+        field_dtype, field_offset = dtype.fields[name][:2]
+        if field_offset > offset:
+            fmt += f'{field_offset - offset}x'
+        code = _FORMATS[field_dtype.str.lstrip('<=|')]
+        if name == 'pad_':
+            fmt += f'{field_dtype.itemsize}x'
+        else:
+            fmt += code
+            names.append(name)
+        offset = field_offset + field_dtype.itemsize
+    if dtype.itemsize > offset:
+        fmt += f'{dtype.itemsize - offset}x'
+    packer = struct.Struct(fmt)
+    assert packer.size == dtype.itemsize, (packer.size, dtype.itemsize)
+    _PACKERS[key] = (packer, tuple(names))
+    return _PACKERS[key]
+
+
 class ProblemBuilder:
     """Accumulates one batch for the device.
 
@@ -181,14 +215,13 @@ class ProblemBuilder:
 
     @staticmethod
     def _record(fields: Dict[str, Any], dtype: np.dtype) -> bytes:
-        rec = np.zeros(1, dtype=dtype)
-        for name in dtype.names:
-            if name == 'pad_':
-                continue
-            default = -1 if name in ('acc_set', 'fuzzy_set', 'region_id',
-                                     'zone_id') else 0
-            rec[name][0] = fields.get(name, default)
-        return rec.tobytes()
+        """One C struct as bytes (struct.pack with the dtype's exact layout:
+        an order of magnitude cheaper than a one-element numpy record)."""
+        packer, names = _packer(dtype)
+        get = fields.get
+        return packer.pack(*[
+            get(n, -1 if n in _MINUS_ONE_DEFAULT else 0) for n in names
+        ])
 
     def replay_query(self, recorder: 'ProblemBuilder', i: int) -> int:
         """Copies query `i` of a recorded plan (Cloud.plan_cached)."""
