@@ -1,5 +1,6 @@
 """Time the scan kernel alone on a bench workload (profiling experiments:
 SKYOPT_DEBUG / SKYOPT_SCAN_MODE environment variables apply)."""
+import os
 import sys
 import numpy as np
 sys.path.insert(0, '.')
@@ -21,8 +22,9 @@ topo = [t for t in nx.topological_sort(graph) if not opt_lib._is_dummy(t)]
 problem = O._state_problem(graph, topo, True, [], True)
 for mode in sys.argv[2:] or ['auto']:
     store.set_scan_mode(mode)
-    engine.solve_timed(problem.builder, 5, True)
-    sol, iter_ms, scan_ms = engine.solve_timed(problem.builder, 30, True)
+    flush = os.environ.get('SKYOPT_NOFLUSH') != '1'  # warm-cache experiment
+    engine.solve_timed(problem.builder, 5, flush)
+    sol, iter_ms, scan_ms = engine.solve_timed(problem.builder, 30, flush)
     print(name, mode, 'scan_kernel_us', round(1e3 * float(np.mean(scan_ms)), 2),
           'min', round(1e3 * float(np.min(scan_ms)), 2),
           'step_us', round(1e3 * float(np.mean(iter_ms)), 2),
