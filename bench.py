@@ -257,12 +257,8 @@ def main():
             dist.barrier()
 
     def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch  # pylint: disable=import-outside-toplevel
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        from skypilot_b200 import sharding  # pylint: disable=import-outside-toplevel
+        return sharding.max_over_ranks(x, dist, device='cuda')
 
     def measure(workload_name):
         workload = WORKLOADS[workload_name]

@@ -1,9 +1,15 @@
 """BASELINE config 5: a batch of independent single-task DAGs through
-Optimizer.optimize_batch, sharded over the visible GPUs (one host process,
-one thread per GPU, catalog replicated, no collective).
+Optimizer.optimize_batch, sharded over the GPUs (catalog replicated, no
+collective).
 
-    python tools/bench_batch.py [n_dags] [n_gpus]
+    python tools/bench_batch.py [n_dags] [n_gpus]        # one process, a thread per GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 tools/bench_batch.py [n_dags]   # a rank per GPU
+
+Under torchrun DAG i goes to rank i % N (skypilot_b200/sharding.py); the time
+is the slowest rank's, the plans are collected on rank 0.
 """
+import os
 import json
 import sys
 import time
@@ -42,8 +48,48 @@ def make_dags(n, seed=4):
     return dags
 
 
+def main_ranks(n: int, world: int) -> None:
+    import torch
+    import torch.distributed as dist
+    from skypilot_b200 import sharding
+    rank, local = int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    frames = synth.make_catalogs(1, 50000)
+    store = sky.catalog.load_frames(frames, device=local)
+    store.handle(local)
+    rows = synth.total_rows(frames)
+    dags = make_dags(n)
+    sharding.optimize_shard(dags[:200], rank, world, local,
+                            return_exceptions=True)
+    best = None
+    for _ in range(3):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = sharding.optimize_shard(dags, rank, world, local,
+                                      return_exceptions=True)
+        torch.cuda.synchronize()
+        dt = sharding.max_over_ranks(time.perf_counter() - t0, dist, 'cuda')
+        best = dt if best is None else min(best, dt)
+    feasible = sharding.gather_on_root(
+        [not isinstance(o, Exception) for o in out], n, dist)
+    if rank == 0:
+        print(json.dumps({
+            'workload': f'cfg5: {n} single-task DAGs, {rows}-row catalog',
+            'n_gpus': world, 'mode': 'one rank per GPU', 'seconds': best,
+            'dags_per_s': n / best, 'candidates_per_s': n * rows / best,
+            'feasible': int(sum(feasible))
+        }))
+    dist.destroy_process_group()
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:
+        main_ranks(n, world)
+        return
     ngpu = int(sys.argv[2]) if len(sys.argv) > 2 else _native.device_count()
     frames = synth.make_catalogs(1, 50000)
     store = sky.catalog.load_frames(frames)

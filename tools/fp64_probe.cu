@@ -1,3 +1,4 @@
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o tools/fp64_probe tools/fp64_probe.cu
 // Micro-benchmark: issue cost of the instruction kinds the scan's inner loop
 // uses (fp64 compare / multiply, 64-bit integer compare, REDUX), 8 warps / SM.
 #include <cstdio>
