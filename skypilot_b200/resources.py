@@ -29,8 +29,18 @@ def canonicalize_accelerator_name(accelerator: str,
     store = catalog.get_store(required=False)
     if store is None:
         return accelerator
-    pattern = re.compile(accelerator, flags=re.IGNORECASE)
     cloud_name = None if cloud is None else cloud.canonical_name()
+    memo = store.__dict__.setdefault('_canonical_acc_names', {})
+    hit = memo.get((accelerator, cloud_name))
+    if hit is not None:
+        return hit
+    memo[(accelerator, cloud_name)] = name = _canonical_name(
+        store, accelerator, cloud_name)
+    return name
+
+
+def _canonical_name(store, accelerator: str, cloud_name: Optional[str]) -> str:
+    pattern = re.compile(accelerator, flags=re.IGNORECASE)
     by_name = store.accelerator_name_clouds()
     names = []
     for name, where in sorted(by_name.items()):

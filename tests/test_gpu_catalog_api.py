@@ -332,3 +332,38 @@ def test_session_follows_full_reoptimisation(name):
             assert plan_a == plan_b, step
             # the launch of the first task's placement "fails"
             blocked.append(_failover_blocked(sky, plan_a[0]))
+
+
+def test_concurrent_optimize_calls_share_one_catalog():
+    """The C ABI is reentrant: calls from several host threads (the
+    reference fans out over a ThreadPool, sky/optimizer.py:1712-1715) borrow
+    private streams / workspaces from the same catalog handle."""
+    import threading
+    runner.activate_catalog(scenarios.CATALOGS['multi6k'])
+    cases = [s for s in scenarios.basic_scenarios()
+             if s['name'] in ('acc_V100', 'cpu_default', 'cfg2_chain8',
+                              'chain8_spot', 'acc_T4', 'mem_4x')]
+    want = []
+    for sc in cases:
+        dag, tasks = runner.build_dag(sc)
+        sky.Optimizer.optimize(dag, quiet=True)
+        want.append([runner.res_record(t.best_resources) for t in tasks])
+    errors = []
+
+    def work(k):
+        try:
+            for it in range(15):
+                i = (k + it) % len(cases)
+                dag, tasks = runner.build_dag(cases[i])
+                sky.Optimizer.optimize(dag, quiet=True)
+                got = [runner.res_record(t.best_resources) for t in tasks]
+                assert got == want[i], (k, it)
+        except BaseException as e:  # pylint: disable=broad-except
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
