@@ -56,7 +56,9 @@ def clear_request_level_cache() -> None:
     """Drops the host-side memos kept on the active store (stated request
     plans, accelerator-name sets) — the counterpart of the reference's
     `annotations.clear_request_level_cache()` (tests/conftest.py:51-52).
-    Device-resident catalog columns are untouched."""
+    Device-resident catalog columns are untouched. (Resources objects pin
+    their plan templates too; callers that want a cold start pop
+    `_plan_templates` / `_request_key` from them, as bench.py does.)"""
     if _store is not None:
         _store.__dict__.pop('_plan_cache', None)
         _store.__dict__.pop('_acc_set_cache', None)

@@ -316,42 +316,48 @@ class Cloud:
                 None if r.ports is None else tuple(r.ports))
 
     def plan_cached(self, builder, resources: Any,
-                    num_nodes: int = 1) -> SlotPlan:
+                    num_nodes: int = 1) -> Tuple[SlotPlan, Optional[int]]:
         """`_feature_hint` + `plan_feasible`, memoised per (cloud, request
         fields) on the catalog store and replayed into `builder`: the fused
         optimizer states the same request shapes over and over (failover
         re-optimisation, batches of DAGs), and the Python rule code is the
-        dominant host cost once the row work is on the GPU."""
-        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        dominant host cost once the row work is on the GPU.
+
+        Returns the (shared, read-only) plan template and the index of the
+        slot it added to `builder` (None: nothing to ask the device)."""
         store = builder.store
-        cache = store.__dict__.setdefault('_plan_cache', {})
-        rkey = resources.__dict__.get('_request_key')
-        if rkey is None:
-            rkey = self._request_key(resources)
-            resources.__dict__['_request_key'] = rkey
-        key = (self.__class__, num_nodes > 1, rkey)
-        tmpl = cache.get(key)
+        multi = num_nodes > 1
+        # templates are also pinned on the Resources object, which skips
+        # hashing the long request key when the same object is stated again
+        local = resources.__dict__.get('_plan_templates')
+        if local is None or local[0] is not store:
+            local = (store, {})
+            resources.__dict__['_plan_templates'] = local
+        tmpl = local[1].get((self.__class__, multi))
         if tmpl is None:
-            plan = SlotPlan()
-            recorder = engine.ProblemBuilder(store)
-            plan.hint = self._feature_hint(resources, num_nodes)
-            if plan.hint is None:
-                plan = self.plan_feasible(recorder, resources)
-            tmpl = (plan, recorder)
-            cache[key] = tmpl
+            from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+            cache = store.__dict__.setdefault('_plan_cache', {})
+            rkey = resources.__dict__.get('_request_key')
+            if rkey is None:
+                rkey = self._request_key(resources)
+                resources.__dict__['_request_key'] = rkey
+            key = (self.__class__, multi, rkey)
+            tmpl = cache.get(key)
+            if tmpl is None:
+                plan = SlotPlan()
+                recorder = engine.ProblemBuilder(store)
+                plan.hint = self._feature_hint(resources, num_nodes)
+                if plan.hint is None:
+                    plan = self.plan_feasible(recorder, resources)
+                tmpl = (plan, recorder)
+                cache[key] = tmpl
+            local[1][(self.__class__, multi)] = tmpl
         plan, recorder = tmpl
         if plan.slot is None:
-            return plan
-        qbase = builder.n_queries
-        for i in range(recorder.n_queries):
-            builder.replay_query(recorder, i)
-        out = SlotPlan()
-        out.__dict__.update(plan.__dict__)
-        out.slot = builder.replay_slot(recorder, plan.slot, qbase)
-        for name in ('list_query', 'fuzzy_query', 'gate_query'):
-            v = getattr(plan, name)
-            setattr(out, name, None if v is None else qbase + v)
-        return out
+            return plan, None
+        qbase = len(builder.query_recs)
+        builder.query_recs.extend(recorder.query_recs)
+        return plan, builder.replay_slot(recorder, plan.slot, qbase)
 
     def plan_feasible(self, builder, resources: Any,
                       want_list: bool = False) -> SlotPlan:

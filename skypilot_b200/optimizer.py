@@ -95,9 +95,17 @@ class _Problem:
         base = info.plan.make(name, info.resources)
         region = info.table.region_names[int(cand['region_id'])]
         zid = int(cand['zone_id'])
-        if zid >= 0:
-            return base.copy(region=region, zone=info.table.zone_names[zid])
-        return base.copy(region=region)
+        zone = info.table.zone_names[zid] if zid >= 0 else None
+        if base is info.resources:
+            # the request itself (explicit instance type): never mutated
+            if zone is not None:
+                return base.copy(region=region, zone=zone)
+            return base.copy(region=region)
+        # `make` returned a fresh copy: place it without a second clone
+        base._region = region  # pylint: disable=protected-access
+        if zone is not None:
+            base._zone = zone  # pylint: disable=protected-access
+        return base
 
 
 class Optimizer:
@@ -458,7 +466,12 @@ class Optimizer:
         store = catalog.get_store()
         b = builder if builder is not None else engine.ProblemBuilder(store)
         n_clouds = len(store.clouds)
-        cloud_objs = [_cloud_object(t.name) for t in store.clouds]
+        cloud_objs = store.__dict__.get('_cloud_objs')
+        if cloud_objs is None:
+            cloud_objs = [_cloud_object(t.name) for t in store.clouds]
+            store.__dict__['_cloud_objs'] = cloud_objs
+        # enabled clouds that the catalog holds, with their tables
+        tables = store.__dict__.setdefault('_tables_by_class', {})
         slot_info: List[_SlotInfo] = [None] * b.n_slots  # type: ignore
         hints: Dict[Any, Dict[Any, str]] = collections.defaultdict(dict)
         local_index = {t: i for i, t in enumerate(topo_real)}
@@ -476,20 +489,24 @@ class Optimizer:
                     continue
                 clouds_list = [res.cloud] if res.cloud is not None else enabled
                 runtime = Optimizer._runtime(task, n_res, res)
+                hours = runtime / 3600
+                nodes = float(max(task.num_nodes, 0))
                 for cloud in clouds_list:
-                    if not store.has_cloud(cloud.canonical_name()):
+                    table = tables.get(cloud.__class__, 0)
+                    if table == 0:
+                        name = cloud.canonical_name()
+                        table = store.cloud(name) if store.has_cloud(
+                            name) else None
+                        tables[cloud.__class__] = table
+                    if table is None:
                         continue
-                    plan = cloud.plan_cached(b, res, task.num_nodes)
+                    plan, slot = cloud.plan_cached(b, res, task.num_nodes)
                     if plan.hint is not None:
                         hints[res][cloud] = plan.hint
-                    if plan.slot is None:
+                    if slot is None:
                         continue
-                    b.set_slot_cost(plan.slot, runtime / 3600,
-                                    float(max(task.num_nodes, 0)),
-                                    float(runtime))
-                    slot_info.append(
-                        _SlotInfo(task, res, cloud, plan,
-                                  store.cloud(cloud.canonical_name())))
+                    b.set_slot_cost(slot, hours, nodes, float(runtime))
+                    slot_info.append(_SlotInfo(task, res, cloud, plan, table))
             slot_end = b.n_slots
             parents = [
                 p for p in dag_graph.predecessors(task) if not _is_dummy(p)

@@ -609,6 +609,7 @@ class Resources:
         new.__dict__.update(self.__dict__)
         new.__dict__.pop('_validated_store', None)
         new.__dict__.pop('_request_key', None)
+        new.__dict__.pop('_plan_templates', None)
         if self._accelerators is not None:
             new._accelerators = dict(self._accelerators)
         for key, value in override.items():
