@@ -476,51 +476,100 @@ class Optimizer:
         hints: Dict[Any, Dict[Any, str]] = collections.defaultdict(dict)
         local_index = {t: i for i, t in enumerate(topo_real)}
         task_begin = len(b.tasks)
+        generation = store.__dict__.get('_memo_generation', 0)
+        enabled_key = tuple(type(c) for c in enabled)
         for task in topo_real:
             slot_begin = b.n_slots
-            n_res = len(list(task.resources))
-            for res in task.resources:
-                if res.__dict__.get('_validated_store') is not store:
-                    # validate() is idempotent and only depends on the catalog
-                    res.validate()
-                    res.__dict__['_validated_store'] = store
-                if res.cloud is not None and not clouds.cloud_in_iterable(
-                        res.cloud, enabled):
-                    continue
-                clouds_list = [res.cloud] if res.cloud is not None else enabled
-                runtime = Optimizer._runtime(task, n_res, res)
-                hours = runtime / 3600
-                nodes = float(max(task.num_nodes, 0))
-                for cloud in clouds_list:
-                    table = tables.get(cloud.__class__, 0)
-                    if table == 0:
-                        name = cloud.canonical_name()
-                        table = store.cloud(name) if store.has_cloud(
-                            name) else None
-                        tables[cloud.__class__] = table
-                    if table is None:
+            res_list = list(task.resources)
+            n_res = len(res_list)
+            nodes = float(max(task.num_nodes, 0))
+            # A task stated before (same catalog, clouds, request objects,
+            # node count) is replayed from its recorded slice of the problem:
+            # its query / slot records are bytes that do not depend on the DAG
+            # around it. Only the runtime (a user callback) is asked again.
+            stated = task.__dict__.get('_stated')
+            ids = tuple(map(id, res_list))
+            if (stated is not None and stated[0] is store and
+                    stated[1] == generation and stated[2] == enabled_key and
+                    stated[3] is task.resources and stated[4] == ids and
+                    stated[5] == (task.num_nodes > 1)):
+                (q_recs, slot_recs, qbase_rel, slot_res, infos,
+                 task_hints) = stated[6]
+                q0 = len(b.query_recs)
+                b.query_recs.extend(q_recs)
+                b.slot_recs.extend(slot_recs)
+                b.slot_qbase.extend([q0 + r for r in qbase_rel])
+                costs = []
+                for res in res_list:
+                    runtime = Optimizer._runtime(task, n_res, res)
+                    costs.append((runtime / 3600, nodes, float(runtime)))
+                b.slot_cost.extend([costs[k] for k in slot_res])
+                slot_info.extend(infos)
+                for res, by_cloud in task_hints.items():
+                    hints[res].update(by_cloud)
+            else:
+                q_mark, info_mark = len(b.query_recs), len(slot_info)
+                slot_res: List[int] = []
+                task_hints: Dict[Any, Dict[Any, str]] = {}
+                for k, res in enumerate(res_list):
+                    if res.__dict__.get('_validated_store') is not store:
+                        # validate() is idempotent and only depends on the
+                        # catalog
+                        res.validate()
+                        res.__dict__['_validated_store'] = store
+                    if res.cloud is not None and not clouds.cloud_in_iterable(
+                            res.cloud, enabled):
                         continue
-                    plan, slot = cloud.plan_cached(b, res, task.num_nodes)
-                    if plan.hint is not None:
-                        hints[res][cloud] = plan.hint
-                    if slot is None:
-                        continue
-                    b.set_slot_cost(slot, hours, nodes, float(runtime))
-                    slot_info.append(_SlotInfo(task, res, cloud, plan, table))
+                    clouds_list = ([res.cloud]
+                                   if res.cloud is not None else enabled)
+                    runtime = Optimizer._runtime(task, n_res, res)
+                    hours = runtime / 3600
+                    for cloud in clouds_list:
+                        table = tables.get(cloud.__class__, 0)
+                        if table == 0:
+                            name = cloud.canonical_name()
+                            table = store.cloud(name) if store.has_cloud(
+                                name) else None
+                            tables[cloud.__class__] = table
+                        if table is None:
+                            continue
+                        plan, slot = cloud.plan_cached(b, res, task.num_nodes)
+                        if plan.hint is not None:
+                            hints[res][cloud] = plan.hint
+                            task_hints.setdefault(res, {})[cloud] = plan.hint
+                        if slot is None:
+                            continue
+                        b.set_slot_cost(slot, hours, nodes, float(runtime))
+                        slot_info.append(
+                            _SlotInfo(task, res, cloud, plan, table))
+                        slot_res.append(k)
+                task.__dict__['_stated'] = (
+                    store, generation, enabled_key, task.resources, ids,
+                    task.num_nodes > 1,
+                    (b.query_recs[q_mark:], b.slot_recs[slot_begin:],
+                     [qb - q_mark for qb in b.slot_qbase[slot_begin:]],
+                     slot_res, slot_info[info_mark:], task_hints))
             slot_end = b.n_slots
             parents = [
                 p for p in dag_graph.predecessors(task) if not _is_dummy(p)
             ]
             edge_rows = []
+            tariff_rows = store.__dict__.setdefault('_tariff_rows', {})
             for p in parents:
                 nbytes = p.get_estimated_outputs_size_gigabytes()
                 if not nbytes:
                     edge_rows.append([0.0] * n_clouds)
                 elif minimize_cost:
-                    edge_rows.append([
-                        float(c.get_egress_cost(num_gigabytes=nbytes))
-                        for c in cloud_objs
-                    ])
+                    # the clouds' piecewise tariffs are pure functions of the
+                    # size: one row per distinct size
+                    row = tariff_rows.get(nbytes)
+                    if row is None:
+                        row = [
+                            float(c.get_egress_cost(num_gigabytes=nbytes))
+                            for c in cloud_objs
+                        ]
+                        tariff_rows[nbytes] = row
+                    edge_rows.append(row)
                 else:
                     edge_rows.append([nbytes * 8 / 10] * n_clouds)
             src_row = None
