@@ -364,3 +364,65 @@ def test_catalog_cache_is_invalidated_by_an_edited_csv(tmp_path):
     again = CatalogStore.from_directory(str(tmp_path))
     assert again.columns['price'][0] == 123.456
     assert len(os.listdir(tmp_path / '.skyopt_cache')) == 2
+
+
+# ---------------------------------------------------------------------------
+# host-side statement memos (plan templates, per-task replay) never change
+# what is sent to the device
+def _packed_bytes(dag):
+    import networkx as nx
+    from skypilot_b200 import optimizer as opt_lib
+    graph = dag.get_graph()
+    topo = list(nx.topological_sort(graph))
+    problem = opt_lib.Optimizer._state_problem(graph, topo, True, [],  # pylint: disable=protected-access
+                                               dag.is_chain())
+    p = problem.builder.pack()
+    return (p.queries[:p.n_queries].tobytes(), p.slots[:p.n_slots].tobytes(),
+            p.tasks[:p.n_tasks].tobytes(), p.n_slots,
+            [i.cloud.canonical_name() for i in problem.slot_info])
+
+
+def _chain(specs, num_nodes=1):
+    import skypilot_b200 as sky
+    with sky.Dag() as dag:
+        prev = None
+        for i, spec in enumerate(specs):
+            t = sky.Task(f't{i}', num_nodes=num_nodes).set_resources(
+                sky.Resources(**spec))
+            t.set_outputs('s3://bucket/x', estimated_size_gigabytes=10 * (i + 1))
+            if prev is not None:
+                prev >> t  # pylint: disable=pointless-statement
+            prev = t
+    return dag
+
+
+def test_statement_memos_are_transparent(store):
+    import skypilot_b200 as sky
+    specs = [dict(accelerators='V100'), dict(cpus='8+'),
+             dict(accelerators='T4', use_spot=True), dict(memory='32+')]
+    dag = _chain(specs)
+    first = _packed_bytes(dag)
+    assert _packed_bytes(dag) == first            # replayed from the memos
+    assert _packed_bytes(_chain(specs)) == first  # fresh objects, same request
+    # a changed request is stated afresh
+    dag.tasks[1].set_resources(sky.Resources(cpus='16+', memory='64+'))
+    specs2 = list(specs)
+    specs2[1] = dict(cpus='16+', memory='64+')
+    assert _packed_bytes(dag) == _packed_bytes(_chain(specs2))
+    # so is a changed node count
+    for t in dag.tasks:
+        t.num_nodes = 3
+    assert _packed_bytes(dag) == _packed_bytes(_chain(specs2, num_nodes=3))
+    # and a changed set of enabled clouds
+    try:
+        sky.check.set_enabled_clouds(['aws', 'gcp'])
+        limited = _packed_bytes(dag)
+        assert limited == _packed_bytes(_chain(specs2, num_nodes=3))
+        assert set(limited[4]) <= {'aws', 'gcp'}
+    finally:
+        sky.check.set_enabled_clouds(None)
+    full = _packed_bytes(dag)
+    assert full == _packed_bytes(_chain(specs2, num_nodes=3))
+    # dropping the memos changes nothing either
+    sky.catalog.clear_request_level_cache()
+    assert _packed_bytes(dag) == full
