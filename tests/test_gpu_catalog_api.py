@@ -367,3 +367,48 @@ def test_concurrent_optimize_calls_share_one_catalog():
     for t in threads:
         t.join()
     assert not errors, errors[0]
+
+
+@pytest.mark.parametrize('seed', range(5))
+def test_session_random_blocked_lists(seed):
+    """Random wildcards of varying specificity, derived from the current
+    plan, accumulate; the session and a full re-optimisation stay in step."""
+    from skypilot_b200.utils import registry
+    rng = np.random.default_rng(50 + seed)
+    runner.activate_catalog(scenarios.CATALOGS['multi6k'])
+    by_name = {s['name']: s for s in scenarios.basic_scenarios()}
+    sc = by_name[['cfg2_chain8', 'chain3_mixed', 'chain8_spot',
+                  'chain2_egress_big', 'cfg2_chain8'][seed]]
+    dag_a, tasks_a = runner.build_dag(sc)
+    dag_b, tasks_b = runner.build_dag(sc)
+    blocked = []
+    with sky.Optimizer.session(dag_a) as session:
+        for step in range(8):
+            err_a = err_b = None
+            try:
+                session.optimize(blocked)
+            except sky.exceptions.ResourcesUnavailableError as e:
+                err_a = str(e)
+            try:
+                sky.Optimizer.optimize(dag_b, blocked_resources=blocked,
+                                       quiet=True)
+            except sky.exceptions.ResourcesUnavailableError as e:
+                err_b = str(e)
+            assert err_a == err_b, step
+            if err_a is not None:
+                break
+            plan_a = [runner.res_record(t.best_resources) for t in tasks_a]
+            plan_b = [runner.res_record(t.best_resources) for t in tasks_b]
+            assert plan_a == plan_b, step
+            rec = plan_a[int(rng.integers(len(plan_a)))]
+            kind = int(rng.integers(4))
+            kw = dict(cloud=registry.CLOUD_REGISTRY.from_str(rec['cloud']))
+            if kind >= 1:
+                kw['region'] = rec['region']
+            if kind >= 2:
+                kw['instance_type'] = rec['instance_type']
+            if kind >= 3 and rec['zone'] is not None:
+                kw['zone'] = rec['zone']
+            r = sky.Resources(**kw)
+            r._use_spot_specified = False  # pylint: disable=protected-access
+            blocked.append(r)
