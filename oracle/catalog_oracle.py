@@ -30,6 +30,13 @@ GCP_FAMILIES = ['n2-standard', 'n2-highmem', 'n2-highcpu', 'n4-standard',
 GCP_HOST_FAMILIES = ('n1-standard', 'n1-highmem', 'n1-highcpu')
 AZURE_FAMILIES = ['Ds_v5', 'Es_v5', 'Fs_v2']
 DEFAULT_CPUS = {'aws': 8, 'gcp': 8, 'azure': 8, 'lambda': 30}
+# the small GPU clouds: (default vCPUs, default memory ratio) of their
+# get_default_instance_type; None = no default (runpod_catalog.py:46-60,
+# paperspace_catalog.py:51-64, do_catalog.py:51-64,
+# fluidstack_catalog.py:18-19, :53-72, cudo_catalog.py:17-18, :52-74)
+GPU_CLOUD_DEFAULTS = {'runpod': (None, None), 'paperspace': (None, None),
+                      'do': (None, None), 'fluidstack': (6, 4),
+                      'cudo': (8, 2)}
 GCP_FIXED = {
     'A100': {1: ['a2-highgpu-1g'], 2: ['a2-highgpu-2g'],
              4: ['a2-highgpu-4g'], 8: ['a2-highgpu-8g'],
@@ -241,6 +248,16 @@ def default_instance_type(cloud: str, df, req: Dict) -> Optional[str]:
     gcp_catalog.py:282-311, azure_catalog.py:100-127,
     lambda_catalog.py:55-75)."""
     cpus, memory = req.get('cpus'), req.get('memory')
+    if cloud in GPU_CLOUD_DEFAULTS:
+        d_cpus, d_ratio = GPU_CLOUD_DEFAULTS[cloud]
+        if cpus is None and memory is None and d_cpus is not None:
+            cpus = f'{d_cpus}+'
+        if memory is None and d_ratio is not None:
+            memory = f'{d_ratio}x'
+        return instance_type_for_cpus_mem(df, cpus, memory, req.get('region'),
+                                          req.get('zone'),
+                                          req.get('use_spot', False),
+                                          req.get('max_hourly_cost'))
     if cpus is None and memory is None:
         cpus = f'{DEFAULT_CPUS[cloud]}+'
     if memory is None:

@@ -26,7 +26,9 @@ from typing import Dict, List, Optional, Sequence
 from oracle import catalog_oracle as co
 
 CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
-                 'lambda': 'Lambda'}
+                 'lambda': 'Lambda', 'runpod': 'RunPod',
+                 'paperspace': 'Paperspace', 'do': 'DO',
+                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo'}
 
 
 def _isnan(x) -> bool:

@@ -40,7 +40,14 @@ import pandas as pd
 
 from oracle import catalog_oracle as co
 
-CLOUD_ORDER = ['aws', 'gcp', 'azure', 'lambda']
+CLOUD_ORDER = ['aws', 'gcp', 'azure', 'lambda', 'runpod', 'paperspace', 'do',
+               'fluidstack', 'cudo']
+# single-table GPU clouds without spot instances and zones
+# ({paperspace,do,fluidstack,cudo}.py: SPOT_INSTANCE in
+# _CLOUD_UNSUPPORTED_FEATURES, `if use_spot: return []` in
+# regions_with_offering); RunPod has both but no multi-node (runpod.py:28-48)
+NO_SPOT_CLOUDS = ('lambda', 'paperspace', 'do', 'fluidstack', 'cudo')
+GPU_CLOUDS = ('runpod', 'paperspace', 'do', 'fluidstack', 'cudo')
 
 
 class Unavailable(Exception):
@@ -147,6 +154,12 @@ def normalize_request(cat: Catalog, spec: Dict[str, Any]) -> Dict[str, Any]:
             if sub.empty:
                 raise ValueError(f'Invalid zone {req["zone"]!r}')
             req['region'] = sub['Region'].unique()[0]
+    if (req['instance_type'] is not None and req['cloud'] is not None and
+            req['instance_type'] != 'TPU-VM' and req['instance_type'] not in
+            cat.frames[req['cloud']]['InstanceType'].unique()):
+        # Resources._try_validate_instance_type, sky/resources.py:1340-1353
+        raise ValueError(f'Invalid instance type {req["instance_type"]!r} '
+                         f'for cloud {req["cloud"]}.')
     if req['instance_type'] is not None and req['cloud'] is None:
         valid = [
             c for c in cat.enabled
@@ -173,12 +186,15 @@ def _region_zone_valid(cat, cloud, region, zone) -> bool:
 # ---- feasibility per cloud ------------------------------------------------------
 def _unsupported(cloud: str, req: Dict[str, Any], num_nodes: int) -> bool:
     """check_features_are_supported for the features a request can need."""
-    if cloud == 'lambda' and (req['use_spot'] or
-                              req['disk_tier'] not in (None, 'best')):
+    if cloud in NO_SPOT_CLOUDS and req['use_spot']:
+        return True
+    if (cloud == 'lambda' or cloud in GPU_CLOUDS) and (
+            req['disk_tier'] not in (None, 'best')):
         return True
     if req['local_disk'] is not None and cloud != 'aws':
         return True
-    del num_nodes
+    if cloud == 'runpod' and num_nodes > 1:
+        return True
     return False
 
 
@@ -240,8 +256,9 @@ def feasible(cat: Catalog, cloud: str, req: Dict[str, Any],
     if cloud == 'aws':
         df = co.filter_with_local_disk(df, req['local_disk'])
     inst_list, fuzzy = co.instance_type_for_accelerator(
-        df, name, count, req['cpus'], req['memory'], req['use_spot'],
-        req['region'], req['zone'], req['max_hourly_cost'])
+        df, name, count, req['cpus'],
+        None if cloud == 'runpod' else req['memory'],  # runpod.py:284-296
+        req['use_spot'], req['region'], req['zone'], req['max_hourly_cost'])
     if inst_list is None:
         return [], fuzzy
     out = []
@@ -287,13 +304,13 @@ def regions_with_offering(cat: Catalog, launchable: Dict[str, Any]):
     df = cat.frames[cloud]
     inst, spot = launchable['instance_type'], launchable['use_spot']
     region, zone = launchable['region'], launchable['zone']
-    if cloud == 'lambda' and spot:
+    if cloud in NO_SPOT_CLOUDS and spot:
         return []
     acc = launchable['accelerators'] if cloud == 'gcp' else None
     if acc is None:
         regions = co.region_zones(df[df['InstanceType'] == inst], spot)
-        if cloud in ('aws', 'lambda'):
-            regions = co.us_first(regions)
+        if cloud in ('aws', 'lambda', 'fluidstack'):
+            regions = co.us_first(regions)  # fluidstack_catalog.py:118-131
     else:
         name, count = list(acc.items())[0]
         acc_regions = co.region_zones(

@@ -96,9 +96,10 @@ class CloudCatalog:
                                   ) -> Optional[str]:
         """Cheapest instance of the default families (e.g.
         sky/catalog/aws_catalog.py:249-274)."""
-        if cpus is None and memory is None:
+        if (cpus is None and memory is None and
+                self.rules.default_cpus is not None):
             cpus = f'{self.rules.default_cpus}+'
-        if memory is None:
+        if memory is None and self.rules.default_mem_ratio is not None:
             memory = f'{self.rules.default_mem_ratio}x'
         view = self._default_view(disk_tier, local_disk)
         return common.get_instance_type_for_cpus_mem_impl(

@@ -38,7 +38,9 @@ class InstanceTypeInfo(NamedTuple):
 
 
 CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
-                 'lambda': 'Lambda'}
+                 'lambda': 'Lambda', 'runpod': 'RunPod',
+                 'paperspace': 'Paperspace', 'do': 'DO',
+                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo'}
 
 
 def _isnan(x) -> bool:

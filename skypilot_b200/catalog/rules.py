@@ -26,12 +26,13 @@ class CloudRules:
                  host_family: Optional[Callable[[str], bool]] = None,
                  premium_disk: Optional[Callable[[str], bool]] = None,
                  group_of: Optional[Callable[[str], int]] = None,
-                 default_cpus: int = 8,
-                 default_mem_ratio: int = 4,
+                 default_cpus: Optional[int] = 8,
+                 default_mem_ratio: Optional[int] = 4,
                  us_regions_first: bool = False,
                  optimize_by_zone: bool = False,
                  supports_spot: bool = True,
-                 supports_local_disk: bool = False):
+                 supports_local_disk: bool = False,
+                 acc_query_memory: bool = True):
         self.name = name
         self.default_family = default_family
         self.host_family = host_family
@@ -43,6 +44,8 @@ class CloudRules:
         self.optimize_by_zone = optimize_by_zone
         self.supports_spot = supports_spot
         self.supports_local_disk = supports_local_disk
+        # does the accelerator look-up receive the request's memory?
+        self.acc_query_memory = acc_query_memory
 
 
 # ---- AWS -----------------------------------------------------------------
@@ -176,6 +179,23 @@ RULES: Dict[str, CloudRules] = {
                          default_cpus=30,
                          us_regions_first=True,
                          supports_spot=False),
+    # The small GPU clouds (one table, accelerators part of the instance
+    # type). Defaults of get_default_instance_type: none on RunPod /
+    # Paperspace / DO (runpod_catalog.py:46-60, paperspace_catalog.py:51-64,
+    # do_catalog.py:51-64), 6 vCPUs x4 on Fluidstack
+    # (fluidstack_catalog.py:18-19), 8 vCPUs x2 on Cudo (cudo_catalog.py:
+    # 17-18). RunPod does not hand the memory request to the accelerator
+    # look-up (runpod.py:284-296) and is the only one with spot and zones.
+    'runpod': CloudRules('runpod', default_cpus=None, default_mem_ratio=None,
+                         acc_query_memory=False),
+    'paperspace': CloudRules('paperspace', default_cpus=None,
+                             default_mem_ratio=None, supports_spot=False),
+    'do': CloudRules('do', default_cpus=None, default_mem_ratio=None,
+                     supports_spot=False),
+    'fluidstack': CloudRules('fluidstack', default_cpus=6, default_mem_ratio=4,
+                             us_regions_first=True, supports_spot=False),
+    'cudo': CloudRules('cudo', default_cpus=8, default_mem_ratio=2,
+                       supports_spot=False),
 }
 
 

@@ -11,9 +11,14 @@ from skypilot_b200.clouds.aws import AWS
 from skypilot_b200.clouds.azure import Azure
 from skypilot_b200.clouds.gcp import GCP
 from skypilot_b200.clouds.lambda_cloud import Lambda
+from skypilot_b200.clouds.gpu_clouds import Cudo
+from skypilot_b200.clouds.gpu_clouds import DO
+from skypilot_b200.clouds.gpu_clouds import Fluidstack
+from skypilot_b200.clouds.gpu_clouds import Paperspace
+from skypilot_b200.clouds.gpu_clouds import RunPod
 
 __all__ = [
     'AWS', 'Azure', 'Cloud', 'CloudCapability', 'CloudImplementationFeatures',
-    'DummyCloud', 'GCP', 'Lambda', 'Region', 'SlotPlan', 'Zone',
-    'cloud_in_iterable'
+    'Cudo', 'DO', 'DummyCloud', 'Fluidstack', 'GCP', 'Lambda', 'Paperspace',
+    'Region', 'RunPod', 'SlotPlan', 'Zone', 'cloud_in_iterable'
 ]

@@ -406,9 +406,10 @@ class Cloud:
         accelerators = resources.accelerators
         if accelerators is None:
             cpus, memory = resources.cpus, resources.memory
-            if cpus is None and memory is None:
+            if (cpus is None and memory is None and
+                    rules.default_cpus is not None):
                 cpus = f'{rules.default_cpus}+'
-            if memory is None:
+            if memory is None and rules.default_mem_ratio is not None:
                 memory = f'{rules.default_mem_ratio}x'
             flags = _native.F_DEFAULT_FAMILY
             if premium:
@@ -425,7 +426,8 @@ class Cloud:
         assert len(accelerators) == 1, resources
         acc, acc_count = list(accelerators.items())[0]
         spec = builder.accelerator_query(
-            self._CATALOG, acc, acc_count, resources.cpus, resources.memory,
+            self._CATALOG, acc, acc_count, resources.cpus,
+            resources.memory if rules.acc_query_memory else None,
             use_spot, resources.region, resources.zone,
             resources.max_hourly_cost, local_disk=local_disk,
             flags_require2=_native.F_PREMIUM_DISK if premium else 0,

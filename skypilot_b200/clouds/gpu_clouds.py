@@ -1,0 +1,170 @@
+"""The small single-table GPU clouds: RunPod, Paperspace, DigitalOcean,
+Fluidstack, Cudo (placement-relevant part of sky/clouds/{runpod,paperspace,
+do,fluidstack,cudo}.py).
+
+They all follow the Lambda template (`Cloud.plan_feasible`); what differs is
+data: the features they do not support (the optimizer only acts on the ones a
+request can ask for -- spot, multi-node, disk / network tier, image, local
+disk -- and quotes the reasons in its hints), whether the catalog has zones
+and spot prices (RunPod only), and the defaults of `get_default_instance_type`
+(catalog/rules.py).
+"""
+from typing import Any, Dict, Optional
+
+from skypilot_b200.clouds import cloud
+from skypilot_b200.utils import registry
+
+_F = cloud.CloudImplementationFeatures
+
+
+class _GpuCloud(cloud.Cloud):
+    """No zones, no spot: `regions_with_offering` is empty for spot requests
+    and asserts that no zone is asked for (e.g. paperspace.py:87-107)."""
+    _UNSUPPORTED: Dict[Any, str] = {}
+    _ZONE_MESSAGE = ''
+
+    @classmethod
+    def _unsupported_features_for_resources(cls, resources: Any,
+                                            region: Optional[str] = None):
+        del resources, region
+        return dict(cls._UNSUPPORTED)
+
+    @classmethod
+    def regions_with_offering(cls, instance_type, accelerators, use_spot,
+                              region, zone, resources=None):
+        assert zone is None, cls._ZONE_MESSAGE
+        if use_spot:
+            return []
+        return super().regions_with_offering(instance_type, accelerators,
+                                             use_spot, region, zone, resources)
+
+
+@registry.CLOUD_REGISTRY.register
+class RunPod(cloud.Cloud):
+    """RunPod: zones and spot prices in the catalog, single node only
+    (runpod.py:28-48, :80-107)."""
+    _REPR = 'RunPod'
+    _CATALOG = 'runpod'
+
+    @classmethod
+    def _unsupported_features_for_resources(cls, resources: Any,
+                                            region: Optional[str] = None):
+        del resources, region
+        return {
+            _F.STOP: 'Stopping not supported.',
+            _F.MULTI_NODE:
+                ('Multi-node not supported yet, as the interconnection among '
+                 'nodes are non-trivial on RunPod.'),
+            _F.CUSTOM_DISK_TIER:
+                'Customizing disk tier is not supported yet on RunPod.',
+            _F.CUSTOM_NETWORK_TIER:
+                'Custom network tier is not supported yet on RunPod.',
+            _F.STORAGE_MOUNTING:
+                ('Mounting object stores is not supported on RunPod. To read '
+                 'data from object stores on RunPod, use `mode: COPY` to copy '
+                 'the data to local disk.'),
+            _F.HIGH_AVAILABILITY_CONTROLLERS:
+                'High availability controllers are not supported on RunPod.',
+            _F.CUSTOM_MULTI_NETWORK:
+                ('Customized multiple network interfaces are not supported on '
+                 'RunPod.'),
+            _F.LOCAL_DISK: 'Local disk is not supported on RunPod',
+        }
+
+
+@registry.CLOUD_REGISTRY.register
+class Paperspace(_GpuCloud):
+    _REPR = 'Paperspace'
+    _CATALOG = 'paperspace'
+    _ZONE_MESSAGE = 'Paperspace does not support zones.'
+    _UNSUPPORTED = {
+        _F.CLONE_DISK_FROM_CLUSTER:
+            'Migrating disk is not supported in Paperspace.',
+        _F.SPOT_INSTANCE: 'Spot instances are not supported in Paperspace.',
+        _F.IMAGE_ID: 'Specifying image ID is not supported for Paperspace.',
+        _F.CUSTOM_DISK_TIER:
+            'Custom disk tiers is not supported in Paperspace.',
+        _F.CUSTOM_NETWORK_TIER:
+            'Custom network tier is currently not supported in Paperspace.',
+        _F.HIGH_AVAILABILITY_CONTROLLERS:
+            'High availability controllers are not supported in Paperspace.',
+        _F.CUSTOM_MULTI_NETWORK:
+            ('Customized multiple network interfaces are not supported in '
+             'Paperspace.'),
+        _F.LOCAL_DISK: 'Local disk is not supported on Paperspace',
+    }
+
+
+@registry.CLOUD_REGISTRY.register
+class DO(_GpuCloud):
+    """DigitalOcean."""
+    _REPR = 'DO'
+    _CATALOG = 'do'
+    _ZONE_MESSAGE = 'DO does not support zones.'
+    _UNSUPPORTED = {
+        _F.CLONE_DISK_FROM_CLUSTER: 'Migrating disk is not supported in DO.',
+        _F.SPOT_INSTANCE: 'Spot instances are not supported in DO.',
+        _F.CUSTOM_DISK_TIER: 'Custom disk tiers is not supported in DO.',
+        _F.CUSTOM_NETWORK_TIER:
+            'Custom network tier is currently not supported in DO.',
+        _F.HIGH_AVAILABILITY_CONTROLLERS:
+            'High availability controllers are not supported in DO.',
+        _F.CUSTOM_MULTI_NETWORK:
+            ('Customized multiple network interfaces are not supported in '
+             'DO.'),
+        _F.LOCAL_DISK: 'Local disk is not supported on DO',
+    }
+
+
+@registry.CLOUD_REGISTRY.register
+class Fluidstack(_GpuCloud):
+    _REPR = 'Fluidstack'
+    _CATALOG = 'fluidstack'
+    _ZONE_MESSAGE = 'FluidStack does not support zones.'
+    _UNSUPPORTED = {
+        _F.STOP: 'Stopping clusters in FluidStack is not supported in SkyPilot',
+        _F.CLONE_DISK_FROM_CLUSTER:
+            'Migrating disk is not supported in Fluidstack.',
+        _F.SPOT_INSTANCE: 'Spot instances are not supported in Fluidstack.',
+        _F.IMAGE_ID: 'Specifying image ID is not supported for Fluidstack.',
+        _F.CUSTOM_DISK_TIER:
+            'Custom disk tiers is not supported in Fluidstack.',
+        _F.CUSTOM_NETWORK_TIER:
+            'Custom network tier is currently not supported in Fluidstack.',
+        _F.HOST_CONTROLLERS: 'Host controllers are not supported in Fluidstack.',
+        _F.HIGH_AVAILABILITY_CONTROLLERS:
+            'High availability controllers are not supported in Fluidstack.',
+        _F.CUSTOM_MULTI_NETWORK:
+            ('Customized multiple network interfaces are not supported in '
+             'Fluidstack.'),
+        _F.LOCAL_DISK: 'Local disk is not supported on Fluidstack',
+    }
+
+
+@registry.CLOUD_REGISTRY.register
+class Cudo(_GpuCloud):
+    _REPR = 'Cudo'
+    _CATALOG = 'cudo'
+    _ZONE_MESSAGE = 'Cudo does not support zones.'
+    _UNSUPPORTED = {
+        _F.STOP: 'Stopping not supported.',
+        _F.SPOT_INSTANCE:
+            'Spot is not supported, as Cudo API does not implement spot.',
+        _F.CUSTOM_DISK_TIER:
+            'Custom disk tier is currently not supported on Cudo Compute',
+        _F.CUSTOM_NETWORK_TIER:
+            'Custom network tier is currently not supported on Cudo Compute',
+        _F.IMAGE_ID: 'Image ID is currently not supported on Cudo. ',
+        _F.DOCKER_IMAGE:
+            ('Docker image is currently not supported on Cudo. You can try '
+             'running docker command inside the `run` section in task.yaml.'),
+        _F.HOST_CONTROLLERS:
+            ('Cudo Compute cannot host a controller as it does not '
+             'autostopping, which will leave the controller to run '
+             'indefinitely.'),
+        _F.HIGH_AVAILABILITY_CONTROLLERS:
+            'High availability controllers are not supported on Cudo.',
+        _F.CUSTOM_MULTI_NETWORK:
+            'Customized multiple network interfaces are not supported on Cudo.',
+        _F.LOCAL_DISK: 'Local disk is not supported on Cudo',
+    }

@@ -553,15 +553,108 @@ def make_lambda(rng,
     return pd.DataFrame(rows, columns=LAMBDA_COLUMNS)
 
 
+# ---------------------------------------------------------------------------
+# The small GPU clouds share one CSV shape (fetch_runpod.py, fetch_cudo.py,
+# fetch_fluidstack.py ...): one row per (instance type, region[, zone]),
+# accelerators part of the instance type. What differs per cloud: naming,
+# regions, whether there is an AvailabilityZone column / a spot price.
+_SIMPLE_CLOUDS = {
+    # name: (instance prefix, regions, zones per region, spot prices)
+    'runpod': ('', ['US', 'CA', 'NL', 'SE', 'RO', 'IS', 'CZ'], (1, 3), True),
+    'paperspace': ('', ['East Coast (NY2)', 'West Coast (CA1)',
+                        'Europe (AMS1)'], None, False),
+    'do': ('gpu-', ['nyc1', 'nyc2', 'sfo3', 'tor1', 'ams3', 'lon1', 'fra1',
+                    'blr1', 'sgp1', 'syd1'], None, False),
+    'fluidstack': ('', ['us-east-1', 'us-west-2', 'eu-north-1', 'eu-west-2',
+                        'ca-east-1', 'ap-south-1'], None, False),
+    'cudo': ('', ['gb-bournemouth', 'no-luster-1', 'se-smedjebacken-1',
+                  'se-stockholm-1', 'us-newyork-1', 'us-santaclara-1',
+                  'us-carlsbad-1'], None, False),
+}
+_SIMPLE_TYPES = [
+    # (suffix, accelerator, count, vcpus, memory, price)
+    ('1x_A100-80GB', 'A100-80GB', 1, 16, 128, 1.89),
+    ('2x_A100-80GB', 'A100-80GB', 2, 32, 256, 3.78),
+    ('4x_A100-80GB', 'A100-80GB', 4, 64, 512, 7.56),
+    ('8x_A100-80GB', 'A100-80GB', 8, 128, 1024, 15.12),
+    ('1x_A100', 'A100', 1, 12, 90, 1.39), ('8x_A100', 'A100', 8, 96, 720, 11.1),
+    ('1x_H100', 'H100', 1, 24, 180, 2.69), ('2x_H100', 'H100', 2, 48, 360, 5.4),
+    ('8x_H100', 'H100', 8, 192, 1440, 21.5),
+    ('1x_V100', 'V100', 1, 8, 52, 0.69), ('4x_V100', 'V100', 4, 32, 208, 2.8),
+    ('1x_T4', 'T4', 1, 4, 16, 0.29), ('4x_T4', 'T4', 4, 16, 64, 1.2),
+    ('1x_L4', 'L4', 1, 8, 32, 0.44), ('8x_L4', 'L4', 8, 64, 256, 3.6),
+    ('1x_A10', 'A10', 1, 8, 32, 0.6), ('1x_RTX4090', 'RTX4090', 1, 16, 62, 0.74),
+    ('2x_RTX4090', 'RTX4090', 2, 32, 124, 1.5),
+    ('1x_A6000', 'A6000', 1, 8, 48, 0.79), ('1x_K80', 'K80', 1, 4, 30, 0.21),
+    ('cpu_2', None, None, 2, 4, 0.031), ('cpu_4', None, None, 4, 16, 0.072),
+    ('cpu_8', None, None, 8, 32, 0.151), ('cpu_8_himem', None, None, 8, 64, 0.212),
+    ('cpu_16', None, None, 16, 64, 0.302), ('cpu_32', None, None, 32, 128, 0.611),
+    ('cpu_64', None, None, 64, 512, 1.42),
+]
+SIMPLE_COLUMNS = [
+    'InstanceType', 'AcceleratorName', 'AcceleratorCount', 'vCPUs',
+    'MemoryGiB', 'Price', 'Region', 'GpuInfo', 'SpotPrice'
+]
+
+
+def make_simple(cloud: str):
+    """Generator of a small single-table GPU cloud's `vms.csv`."""
+    prefix, regions, zones, has_spot = _SIMPLE_CLOUDS[cloud]
+
+    def make(rng, n_rows: int, decimals: int = 4,
+             distinct: bool = True) -> pd.DataFrame:
+        mult = _region_multipliers(rng, regions)
+        types = [(prefix + n, a, c, v, m, p)
+                 for (n, a, c, v, m, p) in _SIMPLE_TYPES]
+        per_type = len(regions) * 0.8 * (2 if zones else 1)
+        want = int(max(0, n_rows / per_type - len(types)))
+        for (name, acc, cnt, vcpus, mem, price, _) in _filler_types(
+                rng, want, 'aws'):
+            types.append((prefix + name.replace('.', '_'), acc, cnt, vcpus,
+                          mem, price))
+        book = _PriceBook(decimals, distinct)
+        spot_book = _PriceBook(decimals + 2, distinct) if has_spot else None
+        zone_names = (_zones_for(rng, regions, zones[0], zones[1], 'dash')
+                      if zones else None)
+        rows = []
+        for (name, acc, cnt, vcpus, mem, base) in types:
+            for region in regions:
+                if rng.uniform() > 0.8:
+                    continue
+                price = book.take(base * mult[region])
+                for zone in (zone_names[region] if zones else [None]):
+                    if zones and rng.uniform() > 0.85:
+                        continue
+                    row = {
+                        'InstanceType': name, 'AcceleratorName': acc,
+                        'AcceleratorCount': cnt, 'vCPUs': float(vcpus),
+                        'MemoryGiB': float(mem), 'Price': price,
+                        'Region': region, 'GpuInfo': acc,
+                        'SpotPrice': (_spot(rng, spot_book, price, 0.15)
+                                      if has_spot else float('nan')),
+                    }
+                    if zones:
+                        row['AvailabilityZone'] = zone
+                    rows.append(row)
+        cols = SIMPLE_COLUMNS + (['AvailabilityZone'] if zones else [])
+        return pd.DataFrame(rows, columns=cols)
+
+    return make
+
+
 _MAKERS = {
     'aws': make_aws,
     'gcp': make_gcp,
     'azure': make_azure,
     'lambda': make_lambda
 }
+for _name in _SIMPLE_CLOUDS:
+    _MAKERS[_name] = make_simple(_name)
 
 # SURVEY.md section 8d: AWS 60 %, GCP 25 %, Azure 10 %, Lambda 5 %.
-DEFAULT_SHARES = {'aws': 0.60, 'gcp': 0.25, 'azure': 0.10, 'lambda': 0.05}
+DEFAULT_SHARES = {'aws': 0.60, 'gcp': 0.25, 'azure': 0.10, 'lambda': 0.05,
+                  'runpod': 0.05, 'paperspace': 0.03, 'do': 0.04,
+                  'fluidstack': 0.04, 'cudo': 0.04}
 
 
 def make_catalogs(seed: int,

@@ -31,6 +31,10 @@ CATALOGS = {
                 'clouds': ['aws', 'gcp', 'azure', 'lambda']},
     'three4k': {'seed': 11, 'n_rows': 4000,
                 'clouds': ['aws', 'gcp', 'azure']},
+    # the small single-table GPU clouds next to AWS
+    'gpuclouds': {'seed': 13, 'n_rows': 4000,
+                  'clouds': ['aws', 'runpod', 'paperspace', 'do',
+                             'fluidstack', 'cudo']},
 }
 
 
@@ -283,11 +287,72 @@ def no_lambda_scenarios():
     return out
 
 
+def gpu_cloud_scenarios():
+    """Requests that exercise the small GPU clouds' templates: defaults (or
+    their absence), spot (RunPod only), zones (RunPod only), multi-node,
+    memory passed to the accelerator look-up or not, us-first regions."""
+    s = []
+    for acc in ['V100', 'T4', 'A100:8', 'H100:8', 'L4', 'RTX4090',
+                'A100-80GB:4', 'A6000', 'K80', 'H100:3', 'rtx4090:2']:
+        s.append(_single(f'acc_{acc.replace(":", "x")}', accelerators=acc))
+    for cloud in ['runpod', 'paperspace', 'do', 'fluidstack', 'cudo']:
+        s.append(_single(f'{cloud}_default', cloud=cloud))
+        s.append(_single(f'{cloud}_cpus8p', cloud=cloud, cpus='8+'))
+        s.append(_single(f'{cloud}_mem64p', cloud=cloud, memory='64+'))
+        s.append(_single(f'{cloud}_cpus4_mem16', cloud=cloud, cpus='4',
+                         memory='16'))
+        s.append(_single(f'{cloud}_a100_80', cloud=cloud,
+                         accelerators='A100-80GB'))
+        s.append(_single(f'{cloud}_h100_mem', cloud=cloud, accelerators='H100',
+                         memory='200+'))
+        s.append(_single(f'{cloud}_t4_cpus', cloud=cloud, accelerators='T4:4',
+                         cpus='16+'))
+        s.append(_single(f'{cloud}_spot', cloud=cloud, accelerators='L4',
+                         use_spot=True))
+        s.append(_single(f'{cloud}_multinode', cloud=cloud,
+                         accelerators='V100', num_nodes=2))
+        s.append(_single(f'{cloud}_cap', cloud=cloud, accelerators='A100',
+                         max_hourly_cost=1.0))
+        s.append(_single(f'{cloud}_fuzzy', cloud=cloud, accelerators='A100:3'))
+    s += [
+        _single('spot_any', accelerators='RTX4090', use_spot=True),
+        _single('spot_cpu', cpus='8+', use_spot=True),
+        _single('runpod_region', cloud='runpod', region='NL',
+                accelerators='A100-80GB'),
+        _single('runpod_zone', cloud='runpod', region='US', zone='US-a',
+                accelerators='T4'),
+        _single('runpod_spot_zone', cloud='runpod', accelerators='H100',
+                use_spot=True, region='CA'),
+        _single('fluidstack_region', cloud='fluidstack', region='eu-north-1',
+                cpus='4+'),
+        _single('do_instance', cloud='do', instance_type='gpu-1x_H100'),
+        _single('cudo_instance_region', cloud='cudo',
+                instance_type='8x_A100', region='us-newyork-1'),
+        _single('multinode_any', accelerators='A100:8', num_nodes=4),
+        _chain('chain_mixed', [
+            dict(accelerators='H100:8', outputs_gb=20),
+            dict(cpus='8+', outputs_gb=20),
+            dict(accelerators='RTX4090', use_spot=True, outputs_gb=20),
+            dict(memory='64+')
+        ]),
+        _chain('chain_pinned', [
+            dict(cloud='runpod', accelerators='A100-80GB', use_spot=True,
+                 outputs_gb=100),
+            dict(cloud='aws', cpus='16+', outputs_gb=100),
+            dict(cloud='cudo', accelerators='T4')
+        ]),
+        dict(_single('blocked_cheapest', accelerators='T4'),
+             blocked=[dict(cloud='do'), dict(cloud='paperspace')]),
+    ]
+    return s
+
+
 SUITES = {
     'multi50k': basic_scenarios,
     'multi6k': basic_scenarios,
     'three4k': no_lambda_scenarios,
     'aws50k': aws_scenarios,
+    'gpuclouds': gpu_cloud_scenarios,
 }
 
 
@@ -349,6 +414,8 @@ def listing_cases(clouds=('aws', 'gcp', 'azure', 'lambda')):
 LISTING_SUITES = {
     'multi6k': listing_cases,
     'three4k': lambda: listing_cases(('aws', 'gcp', 'azure')),
+    'gpuclouds': lambda: listing_cases(
+        ('aws', 'runpod', 'paperspace', 'do', 'fluidstack', 'cudo')),
 }
 
 
