@@ -258,6 +258,17 @@ def default_instance_type(cloud: str, df, req: Dict) -> Optional[str]:
                                           req.get('zone'),
                                           req.get('use_spot', False),
                                           req.get('max_hourly_cost'))
+    if cloud == 'ibm':
+        # ibm_catalog.py:17-19, :98-122: family bx2, 8 vCPUs, 32 GB
+        if cpus is None and memory is None:
+            cpus = '8+'
+        if memory is None:
+            memory = '32+'
+        df = df[df['InstanceType'].str.startswith('bx2-')]
+        return instance_type_for_cpus_mem(df, cpus, memory, req.get('region'),
+                                          req.get('zone'),
+                                          req.get('use_spot', False),
+                                          req.get('max_hourly_cost'))
     if cpus is None and memory is None:
         cpus = f'{DEFAULT_CPUS[cloud]}+'
     if memory is None:

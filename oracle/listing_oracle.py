@@ -28,7 +28,7 @@ from oracle import catalog_oracle as co
 CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
                  'lambda': 'Lambda', 'runpod': 'RunPod',
                  'paperspace': 'Paperspace', 'do': 'DO',
-                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo'}
+                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo', 'ibm': 'IBM'}
 
 
 def _isnan(x) -> bool:

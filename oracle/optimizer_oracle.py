@@ -41,7 +41,7 @@ import pandas as pd
 from oracle import catalog_oracle as co
 
 CLOUD_ORDER = ['aws', 'gcp', 'azure', 'lambda', 'runpod', 'paperspace', 'do',
-               'fluidstack', 'cudo']
+               'fluidstack', 'cudo', 'ibm']
 # single-table GPU clouds without spot instances and zones
 # ({paperspace,do,fluidstack,cudo}.py: SPOT_INSTANCE in
 # _CLOUD_UNSUPPORTED_FEATURES, `if use_spot: return []` in
@@ -188,7 +188,7 @@ def _unsupported(cloud: str, req: Dict[str, Any], num_nodes: int) -> bool:
     """check_features_are_supported for the features a request can need."""
     if cloud in NO_SPOT_CLOUDS and req['use_spot']:
         return True
-    if (cloud == 'lambda' or cloud in GPU_CLOUDS) and (
+    if (cloud in ('lambda', 'ibm') or cloud in GPU_CLOUDS) and (
             req['disk_tier'] not in (None, 'best')):
         return True
     if req['local_disk'] is not None and cloud != 'aws':
@@ -258,7 +258,9 @@ def feasible(cat: Catalog, cloud: str, req: Dict[str, Any],
     inst_list, fuzzy = co.instance_type_for_accelerator(
         df, name, count, req['cpus'],
         None if cloud == 'runpod' else req['memory'],  # runpod.py:284-296
-        req['use_spot'], req['region'], req['zone'], req['max_hourly_cost'])
+        # IBM does not hand the spot flag to the look-up (ibm.py:283-295)
+        False if cloud == 'ibm' else req['use_spot'], req['region'],
+        req['zone'], req['max_hourly_cost'])
     if inst_list is None:
         return [], fuzzy
     out = []
@@ -304,8 +306,8 @@ def regions_with_offering(cat: Catalog, launchable: Dict[str, Any]):
     df = cat.frames[cloud]
     inst, spot = launchable['instance_type'], launchable['use_spot']
     region, zone = launchable['region'], launchable['zone']
-    if cloud in NO_SPOT_CLOUDS and spot:
-        return []
+    if (cloud in NO_SPOT_CLOUDS or cloud == 'ibm') and spot:
+        return []  # ibm.py:88-92: no spot offering in any region
     acc = launchable['accelerators'] if cloud == 'gcp' else None
     if acc is None:
         regions = co.region_zones(df[df['InstanceType'] == inst], spot)
@@ -467,6 +469,13 @@ def egress_tariff(cloud: str, g: float) -> float:
         if g > 1:
             cost += (g - 1) * low
         cost += 0.0
+        return cost
+    if cloud == 'ibm':
+        # ibm.py:162-181, as written there (the tiers are not clamped)
+        cost = 0.0
+        for threshold, price in ((150, 0.05), (50, 0.07), (0, 0.09)):
+            cost += (g - threshold) * price
+            g -= g - threshold
         return cost
     return 0.0
 
@@ -671,7 +680,9 @@ def catalog_for(spec: Dict[str, Any]) -> Catalog:
     key = json.dumps(spec, sort_keys=True)
     if key not in _catalog_cache:
         spec = dict(spec)
-        enabled = spec.pop('enabled', None)
+        # enabled clouds in the harness' order: the catalog spec's
+        # (oracle/ref_harness/run_reference.py main())
+        enabled = spec.pop('enabled', None) or list(spec.get('clouds') or []) or None
         _catalog_cache[key] = Catalog(synth.make_catalogs(**spec), enabled)
     return _catalog_cache[key]
 

@@ -99,7 +99,9 @@ class CloudCatalog:
         if (cpus is None and memory is None and
                 self.rules.default_cpus is not None):
             cpus = f'{self.rules.default_cpus}+'
-        if memory is None and self.rules.default_mem_ratio is not None:
+        if memory is None and self.rules.default_memory is not None:
+            memory = self.rules.default_memory
+        elif memory is None and self.rules.default_mem_ratio is not None:
             memory = f'{self.rules.default_mem_ratio}x'
         view = self._default_view(disk_tier, local_disk)
         return common.get_instance_type_for_cpus_mem_impl(

@@ -40,7 +40,7 @@ class InstanceTypeInfo(NamedTuple):
 CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
                  'lambda': 'Lambda', 'runpod': 'RunPod',
                  'paperspace': 'Paperspace', 'do': 'DO',
-                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo'}
+                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo', 'ibm': 'IBM'}
 
 
 def _isnan(x) -> bool:

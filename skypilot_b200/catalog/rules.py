@@ -32,7 +32,9 @@ class CloudRules:
                  optimize_by_zone: bool = False,
                  supports_spot: bool = True,
                  supports_local_disk: bool = False,
-                 acc_query_memory: bool = True):
+                 acc_query_memory: bool = True,
+                 default_memory: Optional[str] = None,
+                 spot_without_regions: bool = False):
         self.name = name
         self.default_family = default_family
         self.host_family = host_family
@@ -46,6 +48,12 @@ class CloudRules:
         self.supports_local_disk = supports_local_disk
         # does the accelerator look-up receive the request's memory?
         self.acc_query_memory = acc_query_memory
+        # default memory request when it is not a vCPU ratio (IBM: '32+')
+        self.default_memory = default_memory
+        # spot requests are not rejected as a feature but find no region
+        # (IBM: regions_with_offering returns [] for spot, ibm.py:88-92), and
+        # the accelerator look-up ignores the spot flag (ibm.py:283-295)
+        self.spot_without_regions = spot_without_regions
 
 
 # ---- AWS -----------------------------------------------------------------
@@ -196,6 +204,11 @@ RULES: Dict[str, CloudRules] = {
                              us_regions_first=True, supports_spot=False),
     'cudo': CloudRules('cudo', default_cpus=8, default_mem_ratio=2,
                        supports_spot=False),
+    # IBM: default family bx2, 8 vCPUs, 32 GB (ibm_catalog.py:17-19, :98-122)
+    'ibm': CloudRules('ibm',
+                      default_family=lambda name: name.startswith('bx2-'),
+                      default_cpus=8, default_mem_ratio=None,
+                      default_memory='32+', spot_without_regions=True),
 }
 
 

@@ -371,6 +371,8 @@ class Cloud:
         use_spot = bool(resources.use_spot)
         if use_spot and not rules.supports_spot:
             return plan
+        # IBM: the queries are stated, but a spot request gets no slot
+        no_slot = use_spot and rules.spot_without_regions
         by_zone = bool(table.has_zone_column and
                        (use_spot or self.optimize_by_zone()))
         slot_common = dict(
@@ -386,7 +388,7 @@ class Cloud:
             inst = table.inst_index.get(resources.instance_type, -1)
             plan.explicit_instance = resources.instance_type
             plan.make = lambda name, res: res.copy(accelerators=None)
-            if ok and inst >= 0:
+            if ok and inst >= 0 and not no_slot:
                 plan.slot = builder.add_slot(inst_id=inst, **slot_common)
             return plan
 
@@ -409,7 +411,9 @@ class Cloud:
             if (cpus is None and memory is None and
                     rules.default_cpus is not None):
                 cpus = f'{rules.default_cpus}+'
-            if memory is None and rules.default_mem_ratio is not None:
+            if memory is None and rules.default_memory is not None:
+                memory = rules.default_memory
+            elif memory is None and rules.default_mem_ratio is not None:
                 memory = f'{rules.default_mem_ratio}x'
             flags = _native.F_DEFAULT_FAMILY
             if premium:
@@ -420,7 +424,8 @@ class Cloud:
                 local_disk=local_disk)
             q = builder.add_query(spec)
             plan.list_query = q
-            plan.slot = builder.add_slot(query=q, **slot_common)
+            if not no_slot:
+                plan.slot = builder.add_slot(query=q, **slot_common)
             return plan
 
         assert len(accelerators) == 1, resources
@@ -428,14 +433,16 @@ class Cloud:
         spec = builder.accelerator_query(
             self._CATALOG, acc, acc_count, resources.cpus,
             resources.memory if rules.acc_query_memory else None,
-            use_spot, resources.region, resources.zone,
+            use_spot and not rules.spot_without_regions, resources.region,
+            resources.zone,
             resources.max_hourly_cost, local_disk=local_disk,
             flags_require2=_native.F_PREMIUM_DISK if premium else 0,
             want_list=want_list, want_fuzzy=want_list)
         q = builder.add_query(spec)
         plan.list_query = q
         plan.fuzzy_query = q
-        plan.slot = builder.add_slot(query=q, **slot_common)
+        if not no_slot:
+            plan.slot = builder.add_slot(query=q, **slot_common)
         return plan
 
     @classmethod

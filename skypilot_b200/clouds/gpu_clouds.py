@@ -1,6 +1,6 @@
-"""The small single-table GPU clouds: RunPod, Paperspace, DigitalOcean,
-Fluidstack, Cudo (placement-relevant part of sky/clouds/{runpod,paperspace,
-do,fluidstack,cudo}.py).
+"""The single-table clouds beyond Lambda: RunPod, Paperspace, DigitalOcean,
+Fluidstack, Cudo, IBM (placement-relevant part of sky/clouds/{runpod,
+paperspace,do,fluidstack,cudo,ibm}.py).
 
 They all follow the Lambda template (`Cloud.plan_feasible`); what differs is
 data: the features they do not support (the optimizer only acts on the ones a
@@ -168,3 +168,56 @@ class Cudo(_GpuCloud):
             'Customized multiple network interfaces are not supported on Cudo.',
         _F.LOCAL_DISK: 'Local disk is not supported on Cudo',
     }
+
+
+@registry.CLOUD_REGISTRY.register
+class IBM(cloud.Cloud):
+    """IBM VPC: zones, a default family (bx2), no spot offering -- a spot
+    request passes the feature gate but `regions_with_offering` is empty
+    (ibm.py:80-104) -- and an egress tariff (ibm.py:162-181)."""
+    _REPR = 'IBM'
+    _CATALOG = 'ibm'
+
+    @classmethod
+    def _unsupported_features_for_resources(cls, resources: Any,
+                                            region: Optional[str] = None):
+        del region
+        features = {
+            _F.CLONE_DISK_FROM_CLUSTER:
+                'Migrating disk is currently not supported on IBM.',
+            _F.DOCKER_IMAGE:
+                ('Docker image is currently not supported on IBM. You can try '
+                 'running docker command inside the `run` section in '
+                 'task.yaml.'),
+            _F.CUSTOM_DISK_TIER:
+                'Custom disk tier is currently not supported on IBM.',
+            _F.OPEN_PORTS: 'Opening ports is currently not supported on IBM.',
+            _F.HIGH_AVAILABILITY_CONTROLLERS:
+                'High availability controllers are not supported on IBM.',
+            _F.CUSTOM_MULTI_NETWORK:
+                ('Customized multiple network interfaces are not supported on '
+                 'IBM.'),
+            _F.LOCAL_DISK: 'Local disk is not supported on IBM',
+        }
+        if resources.use_spot:
+            features[_F.STOP] = ('Stopping spot instances is currently not '
+                                 'supported on IBM.')
+        return features
+
+    @classmethod
+    def regions_with_offering(cls, instance_type, accelerators, use_spot,
+                              region, zone, resources=None):
+        if use_spot:
+            return []
+        return super().regions_with_offering(instance_type, accelerators,
+                                             use_spot, region, zone, resources)
+
+    def get_egress_cost(self, num_gigabytes: float) -> float:
+        """The Dallas object-storage tariff as the reference evaluates it
+        (ibm.py:162-181): every tier above its threshold is billed at the
+        tier's price and the remainder is handed down."""
+        cost = 0.0
+        for threshold, price_per_gb in ((150, 0.05), (50, 0.07), (0, 0.09)):
+            cost += (num_gigabytes - threshold) * price_per_gb
+            num_gigabytes -= num_gigabytes - threshold
+        return cost

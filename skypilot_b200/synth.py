@@ -642,7 +642,61 @@ def make_simple(cloud: str):
     return make
 
 
+_IBM_REGIONS = ['us-south', 'us-east', 'eu-de', 'eu-gb', 'jp-tok', 'au-syd',
+                'ca-tor', 'br-sao']
+IBM_COLUMNS = [
+    'InstanceType', 'AcceleratorName', 'AcceleratorCount', 'vCPUs',
+    'MemoryGiB', 'GpuInfo', 'Price', 'SpotPrice', 'Region', 'AvailabilityZone'
+]
+
+
+def make_ibm(rng, n_rows: int, decimals: int = 4,
+             distinct: bool = True) -> pd.DataFrame:
+    """IBM VPC profiles (fetch_ibm.py:95-130): `<family>-<vcpus>x<mem>`, the
+    balanced `bx2` family is the default one; no spot prices."""
+    mult = _region_multipliers(rng, _IBM_REGIONS)
+    zones = _zones_for(rng, _IBM_REGIONS, 2, 3, 'dash')
+    types = []
+    for fam, ratio, base in (('bx2', 4, 0.048), ('cx2', 2, 0.041),
+                             ('mx2', 8, 0.063), ('bx3d', 5, 0.055)):
+        for v in (2, 4, 8, 16, 32, 48, 64, 96, 128):
+            types.append((f'{fam}-{v}x{v * ratio}', None, None, v, v * ratio,
+                          base * v))
+    for name, acc, cnt, v, m, price in (
+            ('gx2-8x64x1v100', 'V100', 1, 8, 64, 2.44),
+            ('gx2-16x128x2v100', 'V100', 2, 16, 128, 4.87),
+            ('gx2-32x256x2v100', 'V100', 2, 32, 256, 5.6),
+            ('gx3-16x80x1l4', 'L4', 1, 16, 80, 1.3),
+            ('gx3-32x160x2l4', 'L4', 2, 32, 160, 2.6),
+            ('gx3-64x320x4l4', 'L4', 4, 64, 320, 5.2),
+            ('gx3-24x120x1l40s', 'L40S', 1, 24, 120, 2.7),
+            ('gx3d-160x1792x8h100', 'H100', 8, 160, 1792, 85.0)):
+        types.append((name, acc, cnt, v, m, price))
+    per_type = len(_IBM_REGIONS) * 0.85 * 2.5
+    want = int(max(0, n_rows / per_type - len(types)))
+    for (name, acc, cnt, vcpus, mem, price, _) in _filler_types(
+            rng, want, 'aws'):
+        types.append((name.replace('.', '-'), acc, cnt, vcpus, mem, price))
+    book = _PriceBook(decimals, distinct)
+    rows = []
+    for (name, acc, cnt, vcpus, mem, base) in types:
+        for region in _IBM_REGIONS:
+            if rng.uniform() > 0.85:
+                continue
+            price = book.take(base * mult[region])
+            for zone in zones[region]:
+                rows.append({
+                    'InstanceType': name, 'AcceleratorName': acc,
+                    'AcceleratorCount': cnt, 'vCPUs': float(vcpus),
+                    'MemoryGiB': float(mem), 'GpuInfo': acc, 'Price': price,
+                    'SpotPrice': float('nan'), 'Region': region,
+                    'AvailabilityZone': zone,
+                })
+    return pd.DataFrame(rows, columns=IBM_COLUMNS)
+
+
 _MAKERS = {
+    'ibm': make_ibm,
     'aws': make_aws,
     'gcp': make_gcp,
     'azure': make_azure,
@@ -654,7 +708,7 @@ for _name in _SIMPLE_CLOUDS:
 # AWS 60 %, GCP 25 %, Azure 10 %, Lambda 5 %.
 DEFAULT_SHARES = {'aws': 0.60, 'gcp': 0.25, 'azure': 0.10, 'lambda': 0.05,
                   'runpod': 0.05, 'paperspace': 0.03, 'do': 0.04,
-                  'fluidstack': 0.04, 'cudo': 0.04}
+                  'fluidstack': 0.04, 'cudo': 0.04, 'ibm': 0.08}
 
 
 def make_catalogs(seed: int,

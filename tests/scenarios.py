@@ -32,6 +32,8 @@ CATALOGS = {
     'three4k': {'seed': 11, 'n_rows': 4000,
                 'clouds': ['aws', 'gcp', 'azure']},
     # the small single-table GPU clouds next to AWS
+    # IBM (default family, zones, egress tariff) next to AWS and Cudo
+    'ibm5k': {'seed': 17, 'n_rows': 5000, 'clouds': ['aws', 'ibm', 'cudo']},
     'gpuclouds': {'seed': 13, 'n_rows': 4000,
                   'clouds': ['aws', 'runpod', 'paperspace', 'do',
                              'fluidstack', 'cudo']},
@@ -347,12 +349,67 @@ def gpu_cloud_scenarios():
     return s
 
 
+def ibm_scenarios():
+    s = [
+        _single('ibm_default', cloud='ibm'),
+        _single('ibm_cpus16p', cloud='ibm', cpus='16+'),
+        _single('ibm_mem100p', cloud='ibm', memory='100+'),
+        _single('ibm_cpus4_mem16', cloud='ibm', cpus='4', memory='16'),
+        _single('ibm_v100', cloud='ibm', accelerators='V100'),
+        _single('ibm_v100x2_cpus', cloud='ibm', accelerators='V100:2',
+                cpus='32+'),
+        _single('ibm_l4_region', cloud='ibm', accelerators='L4',
+                region='eu-de'),
+        _single('ibm_l4_zone', cloud='ibm', accelerators='L4:2',
+                region='us-south', zone='us-south-b'),
+        _single('ibm_h100', cloud='ibm', accelerators='H100:8'),
+        _single('ibm_spot', cloud='ibm', accelerators='V100', use_spot=True),
+        _single('ibm_spot_cpu', cloud='ibm', cpus='8+', use_spot=True),
+        _single('ibm_fuzzy', cloud='ibm', accelerators='L4:3'),
+        _single('ibm_cap', cloud='ibm', accelerators='L40S',
+                max_hourly_cost=1.0),
+        _single('ibm_instance', cloud='ibm', instance_type='mx2-8x64'),
+        _single('ibm_instance_zone', cloud='ibm',
+                instance_type='gx2-8x64x1v100', region='us-east'),
+        _single('ibm_multinode', cloud='ibm', accelerators='V100',
+                num_nodes=3),
+        _single('any_v100', accelerators='V100'),
+        _single('any_cpu', cpus='8+'),
+        _single('any_l4_spot', accelerators='L4', use_spot=True),
+        _chain('chain_from_ibm_small', [
+            dict(cloud='ibm', accelerators='V100', outputs_gb=30),
+            dict(cpus='8+', outputs_gb=30), dict(accelerators='L4')
+        ]),
+        _chain('chain_from_ibm_big', [
+            dict(cloud='ibm', cpus='16+', outputs_gb=500),
+            dict(cpus='8+', outputs_gb=500), dict(accelerators='T4')
+        ]),
+        _chain('chain_to_ibm', [
+            dict(cloud='aws', accelerators='T4', outputs_gb=120),
+            dict(cloud='ibm', cpus='4+', outputs_gb=5),
+            dict(cloud='cudo', accelerators='T4')
+        ]),
+        _chain('chain_free_mid_egress', [
+            dict(accelerators='V100', outputs_gb=100),
+            dict(memory='64+', outputs_gb=100), dict(accelerators='H100:8')
+        ]),
+        _chain('chain_time', [
+            dict(cloud='ibm', accelerators='L4', outputs_gb=80),
+            dict(cpus='8+')
+        ], minimize='time'),
+        dict(_single('ibm_blocked_region', cloud='ibm', accelerators='V100'),
+             blocked=[dict(cloud='ibm', region='us-south')]),
+    ]
+    return s
+
+
 SUITES = {
     'multi50k': basic_scenarios,
     'multi6k': basic_scenarios,
     'three4k': no_lambda_scenarios,
     'aws50k': aws_scenarios,
     'gpuclouds': gpu_cloud_scenarios,
+    'ibm5k': ibm_scenarios,
 }
 
 
