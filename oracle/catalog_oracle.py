@@ -36,7 +36,8 @@ DEFAULT_CPUS = {'aws': 8, 'gcp': 8, 'azure': 8, 'lambda': 30}
 # fluidstack_catalog.py:18-19, :53-72, cudo_catalog.py:17-18, :52-74)
 GPU_CLOUD_DEFAULTS = {'runpod': (None, None), 'paperspace': (None, None),
                       'do': (None, None), 'fluidstack': (6, 4),
-                      'cudo': (8, 2)}
+                      'cudo': (8, 2), 'hyperbolic': (None, None),
+                      'primeintellect': (None, None)}
 GCP_FIXED = {
     'A100': {1: ['a2-highgpu-1g'], 2: ['a2-highgpu-2g'],
              4: ['a2-highgpu-4g'], 8: ['a2-highgpu-8g'],
@@ -254,8 +255,11 @@ def default_instance_type(cloud: str, df, req: Dict) -> Optional[str]:
             cpus = f'{d_cpus}+'
         if memory is None and d_ratio is not None:
             memory = f'{d_ratio}x'
-        return instance_type_for_cpus_mem(df, cpus, memory, req.get('region'),
-                                          req.get('zone'),
+        # primeintellect.py:205-212 does not pass region / zone on
+        in_region = cloud != 'primeintellect'
+        return instance_type_for_cpus_mem(df, cpus, memory,
+                                          req.get('region') if in_region else None,
+                                          req.get('zone') if in_region else None,
                                           req.get('use_spot', False),
                                           req.get('max_hourly_cost'))
     if cloud == 'ibm':

@@ -28,7 +28,9 @@ from oracle import catalog_oracle as co
 CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
                  'lambda': 'Lambda', 'runpod': 'RunPod',
                  'paperspace': 'Paperspace', 'do': 'DO',
-                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo', 'ibm': 'IBM'}
+                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo', 'ibm': 'IBM',
+                 'hyperbolic': 'Hyperbolic',
+                 'primeintellect': 'PrimeIntellect'}
 
 
 def _isnan(x) -> bool:

@@ -41,13 +41,16 @@ import pandas as pd
 from oracle import catalog_oracle as co
 
 CLOUD_ORDER = ['aws', 'gcp', 'azure', 'lambda', 'runpod', 'paperspace', 'do',
-               'fluidstack', 'cudo', 'ibm']
+               'fluidstack', 'cudo', 'ibm', 'hyperbolic', 'primeintellect']
 # single-table GPU clouds without spot instances and zones
 # ({paperspace,do,fluidstack,cudo}.py: SPOT_INSTANCE in
 # _CLOUD_UNSUPPORTED_FEATURES, `if use_spot: return []` in
 # regions_with_offering); RunPod has both but no multi-node (runpod.py:28-48)
-NO_SPOT_CLOUDS = ('lambda', 'paperspace', 'do', 'fluidstack', 'cudo')
-GPU_CLOUDS = ('runpod', 'paperspace', 'do', 'fluidstack', 'cudo')
+NO_SPOT_CLOUDS = ('lambda', 'paperspace', 'do', 'fluidstack', 'cudo',
+                  'hyperbolic')
+GPU_CLOUDS = ('runpod', 'paperspace', 'do', 'fluidstack', 'cudo', 'hyperbolic',
+              'primeintellect')
+SINGLE_NODE_CLOUDS = ('runpod', 'hyperbolic', 'primeintellect')
 
 
 class Unavailable(Exception):
@@ -193,7 +196,7 @@ def _unsupported(cloud: str, req: Dict[str, Any], num_nodes: int) -> bool:
         return True
     if req['local_disk'] is not None and cloud != 'aws':
         return True
-    if cloud == 'runpod' and num_nodes > 1:
+    if cloud in SINGLE_NODE_CLOUDS and num_nodes > 1:
         return True
     return False
 
@@ -257,7 +260,8 @@ def feasible(cat: Catalog, cloud: str, req: Dict[str, Any],
         df = co.filter_with_local_disk(df, req['local_disk'])
     inst_list, fuzzy = co.instance_type_for_accelerator(
         df, name, count, req['cpus'],
-        None if cloud == 'runpod' else req['memory'],  # runpod.py:284-296
+        # runpod.py:284-296, primeintellect.py:219-229: no memory argument
+        None if cloud in ('runpod', 'primeintellect') else req['memory'],
         # IBM does not hand the spot flag to the look-up (ibm.py:283-295)
         False if cloud == 'ibm' else req['use_spot'], req['region'],
         req['zone'], req['max_hourly_cost'])

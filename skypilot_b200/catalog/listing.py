@@ -40,7 +40,9 @@ class InstanceTypeInfo(NamedTuple):
 CLOUD_DISPLAY = {'aws': 'AWS', 'gcp': 'GCP', 'azure': 'Azure',
                  'lambda': 'Lambda', 'runpod': 'RunPod',
                  'paperspace': 'Paperspace', 'do': 'DO',
-                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo', 'ibm': 'IBM'}
+                 'fluidstack': 'Fluidstack', 'cudo': 'Cudo', 'ibm': 'IBM',
+                 'hyperbolic': 'Hyperbolic',
+                 'primeintellect': 'PrimeIntellect'}
 
 
 def _isnan(x) -> bool:

@@ -34,7 +34,8 @@ class CloudRules:
                  supports_local_disk: bool = False,
                  acc_query_memory: bool = True,
                  default_memory: Optional[str] = None,
-                 spot_without_regions: bool = False):
+                 spot_without_regions: bool = False,
+                 default_query_region: bool = True):
         self.name = name
         self.default_family = default_family
         self.host_family = host_family
@@ -54,6 +55,9 @@ class CloudRules:
         # (IBM: regions_with_offering returns [] for spot, ibm.py:88-92), and
         # the accelerator look-up ignores the spot flag (ibm.py:283-295)
         self.spot_without_regions = spot_without_regions
+        # is the default instance type chosen within the requested region /
+        # zone? (PrimeIntellect does not pass them, primeintellect.py:205-212)
+        self.default_query_region = default_query_region
 
 
 # ---- AWS -----------------------------------------------------------------
@@ -204,6 +208,16 @@ RULES: Dict[str, CloudRules] = {
                              us_regions_first=True, supports_spot=False),
     'cudo': CloudRules('cudo', default_cpus=8, default_mem_ratio=2,
                        supports_spot=False),
+    # Hyperbolic: one pseudo region, no defaults (hyperbolic_catalog.py:68-81);
+    # PrimeIntellect: no defaults, memory not handed to the accelerator
+    # look-up, default instance chosen regardless of region
+    # (primeintellect.py:196-232)
+    'hyperbolic': CloudRules('hyperbolic', default_cpus=None,
+                             default_mem_ratio=None, supports_spot=False),
+    'primeintellect': CloudRules('primeintellect', default_cpus=None,
+                                 default_mem_ratio=None,
+                                 acc_query_memory=False,
+                                 default_query_region=False),
     # IBM: default family bx2, 8 vCPUs, 32 GB (ibm_catalog.py:17-19, :98-122)
     'ibm': CloudRules('ibm',
                       default_family=lambda name: name.startswith('bx2-'),

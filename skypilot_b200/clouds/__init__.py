@@ -14,12 +14,15 @@ from skypilot_b200.clouds.lambda_cloud import Lambda
 from skypilot_b200.clouds.gpu_clouds import Cudo
 from skypilot_b200.clouds.gpu_clouds import DO
 from skypilot_b200.clouds.gpu_clouds import Fluidstack
+from skypilot_b200.clouds.gpu_clouds import Hyperbolic
 from skypilot_b200.clouds.gpu_clouds import IBM
+from skypilot_b200.clouds.gpu_clouds import PrimeIntellect
 from skypilot_b200.clouds.gpu_clouds import Paperspace
 from skypilot_b200.clouds.gpu_clouds import RunPod
 
 __all__ = [
     'AWS', 'Azure', 'Cloud', 'CloudCapability', 'CloudImplementationFeatures',
-    'Cudo', 'DO', 'DummyCloud', 'Fluidstack', 'GCP', 'IBM', 'Lambda', 'Paperspace',
+    'Cudo', 'DO', 'DummyCloud', 'Fluidstack', 'GCP', 'Hyperbolic', 'IBM',
+    'Lambda', 'Paperspace', 'PrimeIntellect',
     'Region', 'RunPod', 'SlotPlan', 'Zone', 'cloud_in_iterable'
 ]

@@ -418,8 +418,10 @@ class Cloud:
             flags = _native.F_DEFAULT_FAMILY
             if premium:
                 flags |= _native.F_PREMIUM_DISK
+            q_region = resources.region if rules.default_query_region else None
+            q_zone = resources.zone if rules.default_query_region else None
             spec = builder.cpus_mem_query(
-                self._CATALOG, cpus, memory, resources.region, resources.zone,
+                self._CATALOG, cpus, memory, q_region, q_zone,
                 use_spot, resources.max_hourly_cost, flags_require=flags,
                 local_disk=local_disk)
             q = builder.add_query(spec)

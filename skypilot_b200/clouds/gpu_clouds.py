@@ -1,6 +1,7 @@
 """The single-table clouds beyond Lambda: RunPod, Paperspace, DigitalOcean,
-Fluidstack, Cudo, IBM (placement-relevant part of sky/clouds/{runpod,
-paperspace,do,fluidstack,cudo,ibm}.py).
+Fluidstack, Cudo, Hyperbolic, PrimeIntellect, IBM (placement-relevant part of
+sky/clouds/{runpod,paperspace,do,fluidstack,cudo,hyperbolic,primeintellect,
+ibm}.py).
 
 They all follow the Lambda template (`Cloud.plan_feasible`); what differs is
 data: the features they do not support (the optimizer only acts on the ones a
@@ -168,6 +169,73 @@ class Cudo(_GpuCloud):
             'Customized multiple network interfaces are not supported on Cudo.',
         _F.LOCAL_DISK: 'Local disk is not supported on Cudo',
     }
+
+
+@registry.CLOUD_REGISTRY.register
+class Hyperbolic(cloud.Cloud):
+    """Hyperbolic: one pseudo region ('default'), single node, no spot
+    (hyperbolic.py:28-62, :86-103)."""
+    _REPR = 'Hyperbolic'
+    _CATALOG = 'hyperbolic'
+
+    @classmethod
+    def _unsupported_features_for_resources(cls, resources: Any,
+                                            region: Optional[str] = None):
+        del resources, region
+        return {
+            _F.STOP: 'Stopping not supported.',
+            _F.MULTI_NODE: 'Multi-node not supported.',
+            _F.CUSTOM_DISK_TIER: 'Custom disk tiers not supported.',
+            _F.STORAGE_MOUNTING: 'Storage mounting not supported.',
+            _F.HIGH_AVAILABILITY_CONTROLLERS:
+                'High availability controllers not supported.',
+            _F.SPOT_INSTANCE: 'Spot instances not supported.',
+            _F.CLONE_DISK_FROM_CLUSTER: 'Disk cloning not supported.',
+            _F.DOCKER_IMAGE: 'Docker images not supported.',
+            _F.OPEN_PORTS: 'Opening ports not supported.',
+            _F.IMAGE_ID: 'Custom image IDs not supported.',
+            _F.CUSTOM_NETWORK_TIER: 'Custom network tiers not supported.',
+            _F.HOST_CONTROLLERS: 'Host controllers not supported.',
+            _F.AUTO_TERMINATE: 'Auto-termination not supported.',
+            _F.AUTOSTOP: 'Auto-stop not supported.',
+            _F.AUTODOWN: 'Auto-down not supported.',
+            _F.CUSTOM_MULTI_NETWORK:
+                'Customized multiple network interfaces not supported.',
+            _F.LOCAL_DISK: 'Local disk is not supported on Hyperbolic',
+        }
+
+    @classmethod
+    def regions_with_offering(cls, instance_type, accelerators, use_spot,
+                              region, zone, resources=None):
+        assert zone is None, 'Hyperbolic does not support zones.'
+        return super().regions_with_offering(instance_type, accelerators,
+                                             use_spot, region, zone, resources)
+
+
+@registry.CLOUD_REGISTRY.register
+class PrimeIntellect(cloud.Cloud):
+    """PrimeIntellect: single node; the default instance type is chosen
+    without looking at the requested region (primeintellect.py:196-232)."""
+    _REPR = 'PrimeIntellect'
+    _CATALOG = 'primeintellect'
+
+    @classmethod
+    def _unsupported_features_for_resources(cls, resources: Any,
+                                            region: Optional[str] = None):
+        del resources, region
+        return {
+            _F.AUTOSTOP: 'Stopping not supported.',
+            _F.AUTODOWN: 'Auto down not supported yet.',
+            _F.STOP: 'Stopping not supported.',
+            _F.MULTI_NODE: 'Multi-node not supported yet.',
+            _F.CUSTOM_DISK_TIER: 'Custom disk tier not supported yet.',
+            _F.CUSTOM_NETWORK_TIER: 'Custom network tier not supported yet.',
+            _F.CUSTOM_MULTI_NETWORK:
+                'Customized multiple network interfaces are not supported',
+            _F.IMAGE_ID: 'Custom image not supported yet.',
+            _F.DOCKER_IMAGE: 'Custom docker image not supported yet.',
+            _F.LOCAL_DISK: 'Local disk is not supported yet.',
+        }
 
 
 @registry.CLOUD_REGISTRY.register

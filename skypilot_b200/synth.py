@@ -567,6 +567,9 @@ _SIMPLE_CLOUDS = {
                     'blr1', 'sgp1', 'syd1'], None, False),
     'fluidstack': ('', ['us-east-1', 'us-west-2', 'eu-north-1', 'eu-west-2',
                         'ca-east-1', 'ap-south-1'], None, False),
+    'hyperbolic': ('', ['default'], None, False),
+    'primeintellect': ('', ['united_states', 'canada', 'germany', 'finland',
+                            'india', 'iceland'], (1, 2), True),
     'cudo': ('', ['gb-bournemouth', 'no-luster-1', 'se-smedjebacken-1',
                   'se-stockholm-1', 'us-newyork-1', 'us-santaclara-1',
                   'us-carlsbad-1'], None, False),
@@ -708,7 +711,8 @@ for _name in _SIMPLE_CLOUDS:
 # AWS 60 %, GCP 25 %, Azure 10 %, Lambda 5 %.
 DEFAULT_SHARES = {'aws': 0.60, 'gcp': 0.25, 'azure': 0.10, 'lambda': 0.05,
                   'runpod': 0.05, 'paperspace': 0.03, 'do': 0.04,
-                  'fluidstack': 0.04, 'cudo': 0.04, 'ibm': 0.08}
+                  'fluidstack': 0.04, 'cudo': 0.04, 'ibm': 0.08,
+                  'hyperbolic': 0.02, 'primeintellect': 0.05}
 
 
 def make_catalogs(seed: int,

@@ -34,6 +34,8 @@ CATALOGS = {
     # the small single-table GPU clouds next to AWS
     # IBM (default family, zones, egress tariff) next to AWS and Cudo
     'ibm5k': {'seed': 17, 'n_rows': 5000, 'clouds': ['aws', 'ibm', 'cudo']},
+    'hyperprime': {'seed': 19, 'n_rows': 4000,
+                   'clouds': ['aws', 'hyperbolic', 'primeintellect']},
     'gpuclouds': {'seed': 13, 'n_rows': 4000,
                   'clouds': ['aws', 'runpod', 'paperspace', 'do',
                              'fluidstack', 'cudo']},
@@ -349,6 +351,49 @@ def gpu_cloud_scenarios():
     return s
 
 
+def hyper_prime_scenarios():
+    s = []
+    for cloud in ('hyperbolic', 'primeintellect'):
+        s += [
+            _single(f'{cloud}_default', cloud=cloud),
+            _single(f'{cloud}_cpus8p', cloud=cloud, cpus='8+'),
+            _single(f'{cloud}_mem64p', cloud=cloud, memory='64+'),
+            _single(f'{cloud}_h100_mem', cloud=cloud, accelerators='H100',
+                    memory='200+'),
+            _single(f'{cloud}_t4_cpus', cloud=cloud, accelerators='T4:4',
+                    cpus='16+'),
+            _single(f'{cloud}_spot', cloud=cloud, accelerators='L4',
+                    use_spot=True),
+            _single(f'{cloud}_multinode', cloud=cloud, accelerators='V100',
+                    num_nodes=2),
+            _single(f'{cloud}_cap', cloud=cloud, accelerators='A100',
+                    max_hourly_cost=1.0),
+            _single(f'{cloud}_fuzzy', cloud=cloud, accelerators='A100:3'),
+            _single(f'{cloud}_instance', cloud=cloud,
+                    instance_type='8x_H100'),
+        ]
+    s += [
+        _single('prime_region_default', cloud='primeintellect',
+                region='finland'),
+        _single('prime_region_cpus', cloud='primeintellect', region='india',
+                cpus='16+'),
+        _single('prime_region_acc', cloud='primeintellect', region='canada',
+                accelerators='A100-80GB'),
+        _single('prime_zone_spot', cloud='primeintellect', region='germany',
+                accelerators='H100', use_spot=True),
+        _single('hyper_region', cloud='hyperbolic', region='default',
+                accelerators='RTX4090'),
+        _single('any_rtx4090', accelerators='RTX4090:2'),
+        _single('any_cpu32', cpus='32+'),
+        _chain('chain_three', [
+            dict(accelerators='H100:8', outputs_gb=50),
+            dict(cloud='hyperbolic', cpus='8+', outputs_gb=50),
+            dict(cloud='primeintellect', accelerators='T4', use_spot=True)
+        ]),
+    ]
+    return s
+
+
 def ibm_scenarios():
     s = [
         _single('ibm_default', cloud='ibm'),
@@ -410,6 +455,7 @@ SUITES = {
     'aws50k': aws_scenarios,
     'gpuclouds': gpu_cloud_scenarios,
     'ibm5k': ibm_scenarios,
+    'hyperprime': hyper_prime_scenarios,
 }
 
 
