@@ -225,8 +225,8 @@ class Optimizer:
 
         DAG *i* goes to GPU `devices[i % len(devices)]`; every GPU holds a
         replica of the catalog and solves its shard as ONE device problem
-        (one H2D, five launches, one D2H), the shards run concurrently from
-        one host thread per GPU. No collective is involved: the DAGs are
+        (one H2D; four launches: expand, scan, gather, solve; one D2H), the
+        shards run concurrently from one host thread per GPU. No collective is involved: the DAGs are
         independent (north_star: "no NCCL needed").
 
         Returns the DAGs (each task's `best_resources` set). A DAG without a
