@@ -311,10 +311,14 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *desc, int device,
 int skyopt_catalog_destroy(SkyoptCatalog *cat);
 int skyopt_catalog_bytes(const SkyoptCatalog *cat, int64_t *device_bytes,
                          int64_t *row_bytes);
-/* Scan kernel selection: 0 = auto (by catalog size), 1 = one tile per block
- * (rows straight to registers), 2 = streaming kernel (TMA double buffering
- * through shared memory). Results are identical; used by tests and tuning.
- * The environment variable SKYOPT_SCAN_MODE=tile|stream sets the default. */
+/* Scan kernel selection: 0 = auto (by the amount of work: the queue form for
+ * large scans, one tile per block for small ones), 1 = one tile per block
+ * (rows straight to registers), 2 / 3 = streaming kernel (TMA double buffering
+ * through shared memory; 3 forces three tiles per block), 4 = queue form
+ * (a block owns several tiles, its warps share the surviving (chunk, query)
+ * pairs), 5 = queue form with 32 tiles per block. Results are identical; used
+ * by tests and tuning. The environment variable
+ * SKYOPT_SCAN_MODE=tile|stream|stream3|queue|queue32 sets the default. */
 int skyopt_catalog_set_scan_mode(SkyoptCatalog *cat, int mode);
 
 /*

@@ -606,8 +606,10 @@ class CatalogStore:
         return handle
 
     def set_scan_mode(self, mode: str, device: int = 0) -> None:
-        """'auto' | 'tile' | 'stream' (skyopt_catalog_set_scan_mode)."""
-        code = {'auto': 0, 'tile': 1, 'stream': 2, 'stream3': 3}[mode]
+        """'auto' | 'tile' | 'stream' | 'stream3' | 'queue' | 'queue32'
+        (skyopt_catalog_set_scan_mode)."""
+        code = {'auto': 0, 'tile': 1, 'stream': 2, 'stream3': 3, 'queue': 4,
+                'queue32': 5}[mode]
         _native.check(_native.load().skyopt_catalog_set_scan_mode(
             self.handle(device), code))
 

@@ -163,7 +163,7 @@ int ensure(Ctx *x, size_t dbytes, size_t hbytes) {
 struct Plan {
   // sizes
   int nq = 0, nsets = 0, ns = 0, nt = 0, np = 0, ntar = 0, nb = 0, nd = 0;
-  int n_groups = 0, n_blocks = 0, rpt = 4, tpb = 1, nsq = 0; bool stream = false; bool want_finalize = true;
+  int n_groups = 0, n_blocks = 0, rpt = 4, tpb = 1, nsq = 0; bool stream = false; bool queue = false; bool want_finalize = true;
   int64_t n_partials = 0, list_entries = 0, fuzzy_entries = 0;
   int64_t cand_cap = 0;   // expand candidate buffers
   int64_t scan_rows = 0, pass_rows = 0;
@@ -318,7 +318,8 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   // n_tiles: tiles of the unit; n_blocks: blocks of each of its groups; tpb:
   // tiles per block (strided over the unit's tile list)
   struct Unit { int cloud, klass, n_tiles, n_blocks, tpb, list0, tile0; std::vector<int> cuts; };
-  auto make_units = [&](int rpt, int tpb, bool by_class, std::vector<Unit> &units) {
+  auto make_units = [&](int rpt, int tpb, bool by_class, std::vector<Unit> &units,
+                        float target_pairs = 0.f) {
     long long blocks = 0;
     units.clear();
     const int tile = kScanThreads * rpt;
@@ -338,9 +339,8 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
           u.n_tiles = (rows + tile - 1) / tile; u.list0 = -1; u.tile0 = 0;
           density = cat->flag_density[c].data();
         }
-        u.n_blocks = (u.n_tiles + tpb - 1) / tpb;
         u.cuts.push_back(0);
-        float dens = 0.f; int n = 0;
+        float dens = 0.f, dmax = 0.f; int n = 0;
         for (size_t i = 0; i < qs.size(); ++i) {
           const SkyoptQuery &q = pb->queries[qs[i]];
           float dq = density[(q.flags_require | SKYOPT_F_VALID) & 0xFFu];
@@ -349,8 +349,17 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
             u.cuts.push_back((int)i); dens = 0.f; n = 0;
           }
           dens += dq; ++n;
+          dmax = std::max(dmax, dens);
         }
         u.cuts.push_back((int)qs.size());
+        if (target_pairs > 0.f) {
+          // queue form: as many tiles per block (at most 32: one tested chunk
+          // per thread) as keep the expected number of surviving (chunk,
+          // query) pairs of the unit's densest group near the target
+          const float per_tile = (float)(tile / 128) * std::max(dmax, 1e-3f);
+          u.tpb = std::min(32, std::max(1, (int)(target_pairs / per_tile)));
+        }
+        u.n_blocks = (u.n_tiles + u.tpb - 1) / u.tpb;
         blocks += (long long)u.n_blocks * (long long)(u.cuts.size() - 1);
         units.push_back(std::move(u));
       }
@@ -367,7 +376,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   P.rpt = 4; P.tpb = 1; P.stream = false;
   std::vector<Unit> units;
   const long long wave = 2ll * cat->sm_count;
-  if (cat->scan_mode >= 2) {
+  if (cat->scan_mode == 2 || cat->scan_mode == 3) {
     P.stream = true;
     const long long tiles4 = make_units(4, 1, false, units);
     P.tpb = (int)std::max<long long>(1, (tiles4 + wave - 1) / wave);
@@ -375,13 +384,31 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     if (const char *t = getenv("SKYOPT_TPB")) P.tpb = std::max(1, atoi(t));
     make_units(4, P.tpb, false, units);
   } else {
+    static const float queue_target = [] { const char *e = getenv("SKYOPT_SCAN_Q"); return e ? (float)atof(e) : -1.f; }();
     if (const char *r = getenv("SKYOPT_RPT")) {
       const int v = atoi(r);
       if (v == 1 || v == 2 || v == 4) P.rpt = v;
       make_units(P.rpt, 1, true, units);
-    } else if (make_units(4, 1, true, units) < wave) {
-      P.rpt = 2;
-      if (make_units(2, 1, true, units) < wave) { P.rpt = 1; make_units(1, 1, true, units); }
+    } else if (cat->scan_mode < 4 &&
+               (cat->scan_mode == 1 || queue_target == 0.f || make_units(4, 1, true, units) < 3 * wave)) {
+      // few tiles: one per block, smaller ones when they do not cover the SMs
+      if (make_units(4, 1, true, units) < wave) {
+        P.rpt = 2;
+        if (make_units(2, 1, true, units) < wave) { P.rpt = 1; make_units(1, 1, true, units); }
+      }
+    } else {
+      // Queue form (scan_queue_kernel): blocks own several tiles and their
+      // warps share the surviving (chunk, query) pairs. The target number of
+      // pairs per block is the smallest that lets the whole grid be resident
+      // at once (kScanBlocksPerSM blocks per SM, a tenth left free): a second
+      // wave would start behind blocks that live 8-12 us
+      // (profiles/round1_scan_experiments.md).
+      P.queue = true;
+      const long long resident = (long long)(0.9 * kScanBlocksPerSM * cat->sm_count);
+      float target = queue_target > 0.f ? queue_target : 16.f;
+      if (cat->scan_mode == 5) target = 1e9f;  // tests: 32 tiles per block everywhere
+      while (make_units(4, 1, true, units, target) > resident && queue_target <= 0.f && target < 256.f)
+        target = target < 64.f ? target + 8.f : target * 1.5f;
     }
     // dense units first (their blocks live longest) when asked; with the
     // permuted launch order it makes no measurable difference
@@ -557,6 +584,8 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
       sa.n_blocks = P.n_blocks;
       sa.debug = 0;
       if (const char *dbg = getenv("SKYOPT_DEBUG")) sa.debug = (uint32_t)atoi(dbg);
+      sa.qsplit = 2;
+      if (const char *qs = getenv("SKYOPT_QSPLIT")) sa.qsplit = (uint32_t)std::max(1, atoi(qs));
       static unsigned long long *tl = nullptr; static int tl_blocks = 0;
       if (sa.debug & 2u) {
         if (tl_blocks < P.n_blocks) { if (tl) cudaFree(tl); CU(cudaMalloc(&tl, (size_t)P.n_blocks * 64 + 1024)); tl_blocks = P.n_blocks; }
@@ -575,6 +604,7 @@ int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
       CU(cudaEventRecord(x->ev[6], st));
       if (P.stream)
         scan_stream_kernel<<<P.n_blocks, kScanThreads, kStreamStages * sizeof(StreamStage), st>>>(sa);
+      else if (P.queue) scan_queue_kernel<<<P.n_blocks, kScanThreads, 0, st>>>(sa);
       else if (P.rpt == 4) scan_kernel<4><<<P.n_blocks, kScanThreads, 0, st>>>(sa);
       else if (P.rpt == 2) scan_kernel<2><<<P.n_blocks, kScanThreads, 0, st>>>(sa);
       else scan_kernel<1><<<P.n_blocks, kScanThreads, 0, st>>>(sa);
@@ -920,6 +950,8 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog 
     if (!strcmp(mode, "tile")) c->scan_mode = 1;
     else if (!strcmp(mode, "stream")) c->scan_mode = 2;
     else if (!strcmp(mode, "stream3")) c->scan_mode = 3;
+    else if (!strcmp(mode, "queue")) c->scan_mode = 4;
+    else if (!strcmp(mode, "queue32")) c->scan_mode = 5;
   }
   CU(cudaDeviceSynchronize());
   *out = c;
@@ -943,7 +975,9 @@ int skyopt_catalog_destroy(SkyoptCatalog *c) {
 }
 
 int skyopt_catalog_set_scan_mode(SkyoptCatalog *c, int mode) {
-  if (!c || mode < 0 || mode > 3) return fail(SKYOPT_EINVAL, "scan mode must be 0 (auto), 1 (tile), 2 (stream) or 3 (stream, 3 tiles per block)");
+  if (!c || mode < 0 || mode > 5)
+    return fail(SKYOPT_EINVAL, "scan mode must be 0 (auto), 1 (tile), 2 (stream), 3 (stream, 3 tiles per block), "
+                               "4 (queue) or 5 (queue, 32 tiles per block)");
   c->scan_mode = mode;
   return 0;
 }

@@ -224,6 +224,7 @@ struct ScanArgs {
   uint32_t perm_mul;           // odd, coprime with n_blocks
   uint32_t debug;              // bit 1: record the per-block timeline (profiling)
   uint32_t trace_vb, trace_warp;  // debug & 4: per-iteration trace of one warp
+  uint32_t qsplit;                // queue form: queries per work entry
   unsigned long long *timeline;  // debug & 2: per block {start, staged, scored, end} ns + smid
   int32_t inline_block0[kInlineGroups];    // first block of each group
   ScanGroup inline_groups[kInlineGroups];  // copy of groups[] when it fits
@@ -705,6 +706,148 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_kernel(Sc
 }
 
 // ---- TMA (cp.async.bulk) + mbarrier plumbing for the streaming kernel ------
+// K1, queue form: a block owns `tiles_per_block` tiles of its group (strided
+// over the group's tile list, so neighbouring -- similarly expensive -- tiles
+// land in different blocks). The zone-map entries of all its 128-row chunks
+// are fetched while the query records are being staged; each warp then tests
+// its share of the chunks (lane q <-> query q, one ballot per chunk) and pushes
+// the survivors as work entries -- a chunk and at most two of its surviving
+// queries -- into a shared-memory queue. All warps pop entries until the queue
+// is empty: scoring one (chunk, query) pair is a ~2000-cycle dependent chain,
+// so the block's throughput comes from every resident warp working on a
+// different pair, whichever chunk it came from.
+constexpr int kQueueChunks = kScanThreads;  // one fetched zone-map entry per thread
+constexpr int kQueueEntries = 1024;
+struct QueueShared {
+  uint4 z0[kQueueChunks], z1[kQueueChunks];  // zone-map entries
+  int32_t row[kQueueChunks];                 // first row of the chunk, -1 = none
+  uint32_t cmask[kQueueChunks];              // surviving queries per chunk
+  uint32_t emask[kQueueEntries];             // entry: queries to score ...
+  uint16_t echunk[kQueueEntries];            // ... on this chunk
+  int n_pairs, n_entries, next;
+};
+
+__global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_queue_kernel(ScanArgs a) {
+  constexpr int RPT = 4;
+  constexpr int kTileRows = kScanThreads * RPT;
+  constexpr int kChunksPerTile = kTileRows / kZoneRows;
+  __shared__ __align__(16) ScanShared S;
+  __shared__ __align__(16) QueueShared Q;
+  const int vb = permuted_block(a);
+  const ScanGroup G = find_group(a, vb);
+  const int slot = vb - G.block0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = G.q_count;
+  if (blockIdx.x == 0 && tid == 0 && a.zero_flag) *a.zero_flag = 0;
+  mark(a, 0);
+  if (tid == 0) { Q.n_pairs = 0; Q.n_entries = 0; Q.next = 0; }
+
+  // this thread fetches the entry of chunk c of tile (slot + k * blocks)
+  {
+    const int k = tid / kChunksPerTile, c = tid % kChunksPerTile;
+    const int tidx = slot + k * G.n_tiles;
+    int64_t crow = -1;
+    uint4 z0 = make_uint4(0, 0, 0, 0), z1 = make_uint4(0, 0, 0, 0);
+    if (k < G.tiles_per_block && tidx < G.total_tiles) {
+      const int tile = (G.list0 < 0) ? G.tile0 + tidx : __ldg(a.tile_list + G.list0 + tidx);
+      const int64_t r = (int64_t)G.row_begin + (int64_t)tile * kTileRows + c * kZoneRows;
+      if (r < G.row_end) {
+        crow = r;
+        const uint4 *zp = reinterpret_cast<const uint4 *>(a.cat.zone_map + r / kZoneRows);
+        z0 = __ldg(zp); z1 = __ldg(zp + 1);
+      }
+    }
+    Q.z0[tid] = z0; Q.z1[tid] = z1; Q.row[tid] = (int32_t)crow;
+  }
+  stage_queries(a, G, S);  // all records of the group; ends with a barrier
+  mark(a, 1);
+
+  // zone-map test: warp w takes chunks w, w + 8, ...
+  const int n_chunks = min(kQueueChunks, G.tiles_per_block * kChunksPerTile);
+  {
+    uint32_t req = 0, grp = 0, sg_lo = 0, sg_hi = 0, qf = 0, col = 0;
+    uint64_t gb = 0;
+    if (lane < nq) {
+      const QueryS &L = S.q[lane].s;
+      req = L.req_flags; grp = L.grp_bit; sg_lo = L.sig_lo; sg_hi = L.sig_hi;
+      qf = L.qflags; col = L.price_col ? 1u : 0u; gb = S.gb[lane];
+    }
+    const bool bounded = !(qf & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY));
+    int pairs = 0;
+    for (int ch = warp; ch < n_chunks; ch += kScanWarps) {
+      uint32_t m = 0;
+      if (Q.row[ch] >= 0) {
+        const uint4 z0 = Q.z0[ch], z1 = Q.z1[ch];
+        const uint64_t wmin = col ? (((uint64_t)z1.w << 32) | z1.z) : (((uint64_t)z1.y << 32) | z1.x);
+        const bool pass = lane < nq && ((z0.x & req) == req) && ((z0.w & grp) == grp) &&
+                          (!(qf & SKYOPT_Q_ACC) || (((sg_lo & z0.y) | (sg_hi & z0.z)) != 0u)) &&
+                          !(bounded && wmin > gb);
+        m = __ballot_sync(0xFFFFFFFFu, pass);
+      }
+      if (lane == 0) Q.cmask[ch] = m;
+      pairs += __popc(m);
+    }
+    if (lane == 0 && pairs) atomicAdd(&Q.n_pairs, pairs);
+  }
+  __syncthreads();
+  // entries: two queries each while they fit the queue, else whole chunks
+  {
+    const int split = (Q.n_pairs <= kQueueEntries) ? (int)a.qsplit : 32;
+    if (tid < n_chunks) {
+      uint32_t m = Q.cmask[tid];
+      while (m) {
+        uint32_t e = 0;
+        for (int n = 0; n < split && m; ++n) { const uint32_t low = m & (0u - m); e |= low; m ^= low; }
+        const int i = atomicAdd(&Q.n_entries, 1);
+        Q.emask[i] = e; Q.echunk[i] = (uint16_t)tid;
+      }
+    }
+  }
+  __syncthreads();
+  if ((a.debug & 2u) && tid == 0) {  // profiling: work of the block
+    a.timeline[(size_t)blockIdx.x * 8 + 4] =
+        (unsigned long long)Q.n_entries | ((unsigned long long)Q.n_pairs << 32);
+    a.timeline[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)G.block0 | ((unsigned long long)nq << 32);
+    a.timeline[(size_t)blockIdx.x * 8 + 6] = global_ns();
+  }
+  const int n_entries = Q.n_entries;
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.next, 1);
+    i = __shfl_sync(0xFFFFFFFFu, i, 0);
+    if (i >= n_entries) break;
+    const int ch = Q.echunk[i];
+    const int64_t base = (int64_t)Q.row[ch] + lane * RPT;
+    uint32_t active = Q.emask[i];
+    // the bound may have tightened since the chunk was tested
+    {
+      bool drop = false;
+      if (lane < nq && ((active >> lane) & 1u)) {
+        const QueryS &L = S.q[lane].s;
+        const uint4 z1 = Q.z1[ch];
+        const uint64_t wmin = L.price_col ? (((uint64_t)z1.w << 32) | z1.z) : (((uint64_t)z1.y << 32) | z1.x);
+        drop = !(L.qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY)) && wmin > S.gb[lane];
+      }
+      active &= ~__ballot_sync(0xFFFFFFFFu, drop);
+    }
+    if (!active) continue;
+    double od[RPT], sp[RPT], vc[RPT], mm[RPT];
+    uint32_t ak[RPT], rg[RPT], zn[RPT], fl[RPT];
+    if (G.need & 1u) load_f64<RPT>(a.cat.price, base, od);
+    if (G.need & 2u) load_f64<RPT>(a.cat.spot, base, sp);
+    load_f64<RPT>(a.cat.vcpus, base, vc);
+    load_f64<RPT>(a.cat.mem, base, mm);
+    load_u16<RPT>(a.cat.acc_key, base, ak);
+    load_u16<RPT>(a.cat.region_id, base, rg);
+    load_u16<RPT>(a.cat.zone_id, base, zn);
+    load_u16<RPT>(a.cat.flags, base, fl);
+    score_rows<RPT>(a, G, S, base, active, od, sp, vc, mm, ak, rg, zn, fl);
+  }
+  mark(a, 2);
+  finish_block(a, G, S, slot);
+  mark(a, 3);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }

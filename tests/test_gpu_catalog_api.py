@@ -71,6 +71,23 @@ def test_instance_type_for_accelerator_lists(frames, cloud, acc, count, kw):
     assert got[1] == want[1]
 
 
+@pytest.mark.parametrize('mode', ['queue', 'queue32'])
+def test_accelerator_lists_through_the_queue_scan(frames, mode):
+    """The sorted list / fuzzy tables come out of the scan kernel; the queue
+    form must fill them like the one-tile-per-block form."""
+    store = sky.catalog.get_store()
+    store.set_scan_mode(mode)
+    try:
+        for cloud, acc, count, kw in ACC_CASES:
+            want = co.instance_type_for_accelerator(frames[cloud], acc, count,
+                                                    **kw)
+            got = sky.catalog.get_instance_type_for_accelerator(
+                acc, count, clouds=cloud, **kw)
+            assert (got[0], got[1]) == (want[0], want[1]), (cloud, acc, kw)
+    finally:
+        store.set_scan_mode('auto')
+
+
 @pytest.mark.parametrize('cloud,instance_type,spot', [
     ('aws', 'p3.2xlarge', False), ('aws', 'g4dn.xlarge', True),
     ('gcp', 'n2-standard-8', False), ('gcp', 'n1-highmem-8', True),

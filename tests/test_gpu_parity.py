@@ -62,11 +62,13 @@ def test_scenario_matches_reference(catalog, scenario):
     assert not diffs, '\n'.join(diffs)
 
 
-@pytest.mark.parametrize('mode', ['tile', 'stream', 'stream3'])
+@pytest.mark.parametrize('mode',
+                         ['tile', 'stream', 'stream3', 'queue', 'queue32'])
 @pytest.mark.parametrize('catalog', ['multi50k', 'aws50k'])
 def test_scan_kernel_variants_agree_with_reference(catalog, mode):
-    """Both scan kernels (one tile per block / TMA streaming with one and
-    with three tiles per block) must give the reference's answers."""
+    """All scan kernels (one tile per block / TMA streaming with one and
+    with three tiles per block / the queue form with few and with 32 tiles
+    per block) must give the reference's answers."""
     spec, records = _golden(catalog)
     store = runner.activate_catalog(spec)
     store.set_scan_mode(mode)
