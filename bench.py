@@ -82,14 +82,22 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def measured_traffic(workload_name: str):
+def measured_traffic(workload_name: str, scan_form: int = 0):
     """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch, from
-    the committed ncu capture (profiles/round1_traffic.json); None if the
-    capture does not cover this workload."""
+    the committed ncu captures (profiles/round1_traffic.json); None if no
+    capture covers this workload with the scan kernel that ran."""
     path = os.path.join(_REPO, 'profiles', 'round1_traffic.json')
     try:
         with open(path, encoding='utf-8') as f:
-            return json.load(f)[workload_name]['traffic']
+            table = json.load(f)
+        entry = table[workload_name]
+        form = {'scan_queue_kernel': 2, 'scan_kernel': 0}.get(
+            entry.get('kernel', 'scan_kernel'))
+        if form != scan_form:
+            entry = table[f'{workload_name}_one_tile_per_block']
+            if scan_form != 0:
+                return None
+        return entry['traffic']
     except (OSError, KeyError, ValueError):
         return None
 
@@ -376,16 +384,18 @@ def main():
                 'solve': float(stats.solve_ms),
             },
             'roofline': {
-                'kernel': 'scan_kernel', 'bound': 'hbm', 'achieved': achieved,
+                'kernel': ('scan_kernel', 'scan_stream_kernel',
+                           'scan_queue_kernel')[int(stats.scan_form)],
+                'bound': 'hbm', 'achieved': achieved,
                 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                 'frac': achieved / peak if peak else None,
                 'algorithmic_bytes_per_launch': scan_bytes,
                 'bytes_per_row': row_bytes,
                 'rows_streamed_per_launch': int(stats.scan_passes_rows),
                 'queries_fused_per_pass': 32,
-                'traffic': measured_traffic(workload_name),
-                'traffic_source': ('ncu --set full, one launch, '
-                                   'profiles/round1_traffic.json'),
+                'traffic': measured_traffic(workload_name,
+                                             int(stats.scan_form)),
+                'traffic_source': 'ncu, per launch: profiles/round1_traffic.json',
             },
             'clocks': clocks.summary(),
             'wall_check_ms_per_step': 1e3 * wall_resident / args.steps,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SKYOPT_ABI_VERSION 1
+#define SKYOPT_ABI_VERSION 2
 
 /* error codes */
 #define SKYOPT_OK 0
@@ -295,6 +295,9 @@ typedef struct SkyoptStats {
   int64_t scan_passes_rows; /* rows streamed from HBM (queries fused per pass) */
   float scan_kernel_ms;     /* the scan kernel launch alone (events around it) */
   int32_t scan_blocks;      /* its grid size */
+  int32_t scan_form;        /* which scan kernel ran: 0 one tile per block,
+                               1 streaming (TMA), 2 queue form */
+  int32_t reserved_;
 } SkyoptStats;
 
 typedef struct SkyoptCatalog SkyoptCatalog; /* opaque */

@@ -11,7 +11,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ACC_SET_WORDS = 32
 MAX_CLOUDS = 32
 NONE16 = 0xFFFF
@@ -160,6 +160,7 @@ class Stats(ctypes.Structure):
         ('scan_launches', ctypes.c_int32), ('total_launches', ctypes.c_int32),
         ('scan_rows', ctypes.c_int64), ('scan_passes_rows', ctypes.c_int64),
         ('scan_kernel_ms', ctypes.c_float), ('scan_blocks', ctypes.c_int32),
+        ('scan_form', ctypes.c_int32), ('reserved_', ctypes.c_int32),
     ]
 
     def as_dict(self):

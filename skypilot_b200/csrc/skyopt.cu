@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -753,6 +754,7 @@ int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
   stats->scan_rows = P.scan_rows;
   stats->scan_passes_rows = P.pass_rows;
   stats->scan_blocks = P.n_blocks;
+  stats->scan_form = P.stream ? 1 : (P.queue ? 2 : 0); stats->reserved_ = 0;
   if (P.n_blocks) CU(cudaEventElapsedTime(&stats->scan_kernel_ms, x->ev[6], x->ev[7]));
   return 0;
 }
@@ -761,6 +763,7 @@ int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
 
 extern "C" {
 
+static_assert(sizeof(SkyoptStats) == 56 && offsetof(SkyoptStats, scan_form) == 48, "SkyoptStats ABI");
 int skyopt_abi_version(void) { return SKYOPT_ABI_VERSION; }
 
 uint64_t skyopt_price_key(double price) {
@@ -1231,6 +1234,7 @@ int skyopt_session_resolve(SkyoptSession *s, const SkyoptBlocked *blocked, int n
     // nothing was scanned or expanded this time
     stats->scan_launches = 0; stats->total_launches = 2;
     stats->scan_rows = 0; stats->scan_passes_rows = 0; stats->scan_blocks = 0;
+    stats->scan_form = 0; stats->reserved_ = 0;
     stats->scan_kernel_ms = 0.f;
   }
   return rc;

@@ -51,7 +51,8 @@ def test_struct_layouts_match_header():
     assert _native.SLOT_DTYPE.fields['hours'][1] == 48
     assert _native.CANDIDATE_DTYPE.fields['hourly'][1] == 16
     assert _native.DAG_RESULT_DTYPE.fields['objective'][1] == 8
-    assert ctypes.sizeof(_native.Stats) == 48
+    assert ctypes.sizeof(_native.Stats) == 56
+    assert _native.Stats.scan_form.offset == 48
 
 
 def test_no_device_fails_loudly():
