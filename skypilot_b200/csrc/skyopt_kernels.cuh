@@ -1458,8 +1458,6 @@ gather_kernel(CatDev cat, SolveIn in, SolveWork w, const int32_t *__restrict__ t
 __global__ void __launch_bounds__(kSolveThreads)
 solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   constexpr int kWarps = kSolveThreads / 32;
-  __shared__ int s_pos;
-  __shared__ int s_wcount[kWarps];
   __shared__ int s_fail;
   __shared__ double s_best_val[SKYOPT_MAX_CLOUDS];
   __shared__ int s_best_idx[SKYOPT_MAX_CLOUDS];
