@@ -350,6 +350,8 @@ def main():
         peak, peak_src = measured_peaks()
         achieved = scan_bytes / (scan_kernel_ms / 1e3) / 1e9 if scan_kernel_ms else 0
 
+        scan_form = min(2, max(0, int(getattr(stats, 'scan_form', 0))))
+
         line = {
             'metric': 'candidate (task,instance) placements scored/sec',
             'value': value, 'unit': 'candidates/s', 'n_gpus': world,
@@ -385,7 +387,7 @@ def main():
             },
             'roofline': {
                 'kernel': ('scan_kernel', 'scan_stream_kernel',
-                           'scan_queue_kernel')[int(stats.scan_form)],
+                           'scan_queue_kernel')[scan_form],
                 'bound': 'hbm', 'achieved': achieved,
                 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                 'frac': achieved / peak if peak else None,
@@ -393,8 +395,7 @@ def main():
                 'bytes_per_row': row_bytes,
                 'rows_streamed_per_launch': int(stats.scan_passes_rows),
                 'queries_fused_per_pass': 32,
-                'traffic': measured_traffic(workload_name,
-                                             int(stats.scan_form)),
+                'traffic': measured_traffic(workload_name, scan_form),
                 'traffic_source': 'ncu, per launch: profiles/round1_traffic.json',
             },
             'clocks': clocks.summary(),
