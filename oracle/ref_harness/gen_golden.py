@@ -30,7 +30,7 @@ def main():
     groups = '--job-groups' in argv
     argv = [a for a in argv if a not in ('--listings', '--job-groups')]
     suites = (scenarios.LISTING_SUITES if listings else
-              scenarios.JOB_GROUP_SUITES if groups else scenarios.SUITES)
+              scenarios.JOB_GROUP_SUITES if groups else scenarios.ALL_SUITES)
     prefix = 'accel_' if listings else 'jobgroup_' if groups else ''
     wanted = argv or list(suites.keys())
     out_dir = os.path.join(_REPO, 'tests', 'golden')

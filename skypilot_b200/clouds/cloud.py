@@ -393,11 +393,15 @@ class Cloud:
             return plan
 
         cloud_obj = self.__class__()
+        keeps_memory = rules.make_keeps_memory
 
         def make(instance_type: str, res):
             ok, _ = self.check_disk_tier(instance_type, res.disk_tier)
             if not ok:
                 return None
+            if keeps_memory:
+                return res.copy(cloud=cloud_obj, instance_type=instance_type,
+                                accelerators=None, cpus=None)
             return res.copy(cloud=cloud_obj, instance_type=instance_type,
                             accelerators=None, cpus=None, memory=None)
 

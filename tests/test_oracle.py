@@ -12,17 +12,18 @@ from tests import scenario_runner as runner
 from tests import scenarios
 
 # the 50k-row suites take ~15 s each on CPU; keep one, sample the other
-_FULL = ['multi6k', 'three4k', 'aws50k', 'gpuclouds', 'ibm5k', 'hyperprime']
+_FULL = ['multi6k', 'three4k', 'aws50k', 'gpuclouds', 'ibm5k', 'hyperprime',
+         'latecl']
 _SAMPLED = {'multi50k': 4}
 
 
 def _cases():
     out = []
-    for catalog in scenarios.SUITES:
+    for catalog in scenarios.ALL_SUITES:
         if not os.path.exists(
                 os.path.join(runner.GOLDEN_DIR, f'{catalog}.json')):
             continue
-        suite = scenarios.SUITES[catalog]()
+        suite = scenarios.ALL_SUITES[catalog]()
         if catalog in _SAMPLED:
             suite = suite[::_SAMPLED[catalog]]
         elif catalog not in _FULL:
