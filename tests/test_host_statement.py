@@ -20,7 +20,8 @@ from skypilot_b200 import optimizer as opt_lib
 from tests import scenario_runner as runner
 from tests import scenarios
 
-_SUITES = ['multi6k', 'gpuclouds', 'ibm5k', 'hyperprime', 'latecl', 'fuzz6k']
+_SUITES = ['multi6k', 'three4k', 'aws50k', 'multi50k', 'gpuclouds', 'ibm5k',
+           'hyperprime', 'latecl', 'fuzz6k']
 
 
 def _stage1(cols, sets, q, lo, hi):
