@@ -264,6 +264,21 @@ def default_instance_type(cloud: str, df, req: Dict) -> Optional[str]:
                                           req.get('zone') if in_region else None,
                                           req.get('use_spot', False),
                                           req.get('max_hourly_cost'))
+    if cloud == 'oci':
+        # oci_catalog.py:71-100: 8+ vCPUs whenever cpus is missing, memory
+        # 4x, families VM.Standard.E* / VM.Standard3*, every tier but ultra
+        if cpus is None:
+            cpus = '8+'
+        if memory is None:
+            memory = '4x'
+        if req.get('disk_tier') == 'ultra':
+            return None
+        df = df[df['InstanceType'].str.startswith(
+            ('VM.Standard.E', 'VM.Standard3'))]
+        return instance_type_for_cpus_mem(df, cpus, memory, req.get('region'),
+                                          req.get('zone'),
+                                          bool(req.get('use_spot')),
+                                          req.get('max_hourly_cost'))
     if cloud == 'ibm':
         # ibm_catalog.py:17-19, :98-122: family bx2, 8 vCPUs, 32 GB
         if cpus is None and memory is None:

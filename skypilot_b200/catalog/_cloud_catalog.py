@@ -96,7 +96,8 @@ class CloudCatalog:
                                   ) -> Optional[str]:
         """Cheapest instance of the default families (e.g.
         sky/catalog/aws_catalog.py:249-274)."""
-        if (cpus is None and memory is None and
+        if (cpus is None and
+                (memory is None or self.rules.default_cpus_always) and
                 self.rules.default_cpus is not None):
             cpus = f'{self.rules.default_cpus}+'
         if memory is None and self.rules.default_memory is not None:

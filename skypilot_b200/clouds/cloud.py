@@ -412,7 +412,8 @@ class Cloud:
         accelerators = resources.accelerators
         if accelerators is None:
             cpus, memory = resources.cpus, resources.memory
-            if (cpus is None and memory is None and
+            if (cpus is None and
+                    (memory is None or rules.default_cpus_always) and
                     rules.default_cpus is not None):
                 cpus = f'{rules.default_cpus}+'
             if memory is None and rules.default_memory is not None:
