@@ -265,6 +265,16 @@ def default_instance_type(cloud: str, df, req: Dict) -> Optional[str]:
                                           req.get('zone') if in_region else None,
                                           req.get('use_spot', False),
                                           req.get('max_hourly_cost'))
+    if cloud == 'scp':
+        # scp_catalog.py:56-76: exactly 8 vCPUs, memory 2x
+        if cpus is None and memory is None:
+            cpus = '8'
+        if memory is None:
+            memory = '2x'
+        return instance_type_for_cpus_mem(df, cpus, memory, req.get('region'),
+                                          req.get('zone'),
+                                          bool(req.get('use_spot')),
+                                          req.get('max_hourly_cost'))
     if cloud == 'oci':
         # oci_catalog.py:71-100: 8+ vCPUs whenever cpus is missing, memory
         # 4x, families VM.Standard.E* / VM.Standard3*, every tier but ultra

@@ -99,7 +99,8 @@ class CloudCatalog:
         if (cpus is None and
                 (memory is None or self.rules.default_cpus_always) and
                 self.rules.default_cpus is not None):
-            cpus = f'{self.rules.default_cpus}+'
+            cpus = (f'{self.rules.default_cpus}' if self.rules.default_cpus_exact
+                    else f'{self.rules.default_cpus}+')
         if memory is None and self.rules.default_memory is not None:
             memory = self.rules.default_memory
         elif memory is None and self.rules.default_mem_ratio is not None:

@@ -37,7 +37,9 @@ class CloudRules:
                  spot_without_regions: bool = False,
                  default_query_region: bool = True,
                  make_keeps_memory: bool = False,
-                 default_cpus_always: bool = False):
+                 default_cpus_always: bool = False,
+                 default_cpus_exact: bool = False,
+                 preferred_region: Optional[Callable[[str], bool]] = None):
         self.name = name
         self.default_family = default_family
         self.host_family = host_family
@@ -67,6 +69,13 @@ class CloudRules:
         # if a memory request is given? (OCI: oci_catalog.py:81-82; the other
         # clouds only when both are missing)
         self.default_cpus_always = default_cpus_always
+        # is the default vCPU count an exact request ('8', not '8+')? (SCP:
+        # scp_catalog.py:66-67)
+        self.default_cpus_exact = default_cpus_exact
+        # with `us_regions_first`: which regions go first (None: the ones
+        # named 'us-*', aws_catalog.py:327-336; SCP: names containing 'SCP',
+        # scp_catalog.py:118-126)
+        self.preferred_region = preferred_region
 
 
 # ---- OCI -----------------------------------------------------------------
@@ -254,6 +263,12 @@ RULES: Dict[str, CloudRules] = {
                          make_keeps_memory=True),
     'vast': CloudRules('vast', default_cpus=None, default_mem_ratio=None,
                        make_keeps_memory=True),
+    # SCP: exactly 8 vCPUs by default, memory 2x, no spot, regions whose name
+    # contains 'SCP' first (scp_catalog.py:14-15, :56-76, :108-126)
+    'scp': CloudRules('scp', default_cpus=8, default_mem_ratio=2,
+                      default_cpus_exact=True, supports_spot=False,
+                      us_regions_first=True,
+                      preferred_region=lambda name: 'SCP' in name),
     # OCI: default families VM.Standard.E* / VM.Standard3*, 8 vCPUs whenever
     # `cpus` is missing, memory 4x (oci_catalog.py:71-100,
     # oci_utils.py:32-44); zones and spot (preemptible) prices

@@ -228,8 +228,10 @@ class CatalogStore:
                                         len(table.region_names))
             cloud_n_zones.append(
                 max(len(table.zone_names), 1) if table.has_zone_column else 0)
+            preferred = rules.preferred_region or (
+                lambda name: name.startswith('us-'))
             region_is_us.extend(
-                1 if r.startswith('us-') else 0 for r in table.region_names)
+                1 if preferred(r) else 0 for r in table.region_names)
             # --- accelerators: (name, count) dictionary over all clouds
             ak = np.full(n, _native.NONE16, dtype=np.uint16)
             if 'AcceleratorName' in df.columns:

@@ -415,7 +415,8 @@ class Cloud:
             if (cpus is None and
                     (memory is None or rules.default_cpus_always) and
                     rules.default_cpus is not None):
-                cpus = f'{rules.default_cpus}+'
+                cpus = (f'{rules.default_cpus}' if rules.default_cpus_exact
+                    else f'{rules.default_cpus}+')
             if memory is None and rules.default_memory is not None:
                 memory = rules.default_memory
             elif memory is None and rules.default_mem_ratio is not None:

@@ -427,3 +427,19 @@ def test_statement_memos_are_transparent(store):
     # dropping the memos changes nothing either
     sky.catalog.clear_request_level_cache()
     assert _packed_bytes(dag) == full
+
+
+def test_preferred_regions_follow_the_clouds_rule():
+    """`us_first` on the device reads the per-region flag computed at ingest:
+    'us-*' names by default (aws_catalog.py:327-336), names containing 'SCP'
+    on SCP (scp_catalog.py:118-126)."""
+    store = runner.activate_catalog(scenarios.CATALOGS['scp4k'])
+    cols = store.columns
+    off = cols['cloud_region_offsets']
+    for i, table in enumerate(store.clouds):
+        flags = [int(f) for f in cols['region_is_us'][off[i]:off[i + 1]]]
+        if table.name == 'scp':
+            want = [int('SCP' in n) for n in table.region_names]
+        else:
+            want = [int(n.startswith('us-')) for n in table.region_names]
+        assert flags == want, table.name
