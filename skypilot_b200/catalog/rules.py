@@ -39,7 +39,8 @@ class CloudRules:
                  make_keeps_memory: bool = False,
                  default_cpus_always: bool = False,
                  default_cpus_exact: bool = False,
-                 preferred_region: Optional[Callable[[str], bool]] = None):
+                 preferred_region: Optional[Callable[[str], bool]] = None,
+                 zero_cost: bool = False):
         self.name = name
         self.default_family = default_family
         self.host_family = host_family
@@ -76,6 +77,10 @@ class CloudRules:
         # named 'us-*', aws_catalog.py:327-336; SCP: names containing 'SCP',
         # scp_catalog.py:118-126)
         self.preferred_region = preferred_region
+        # on-premise: every instance costs 0.0 per hour, whatever the catalog
+        # says (vsphere.py:128-135); the catalog prices still order instance
+        # types and regions
+        self.zero_cost = zero_cost
 
 
 # ---- OCI -----------------------------------------------------------------
@@ -269,6 +274,10 @@ RULES: Dict[str, CloudRules] = {
                       default_cpus_exact=True, supports_spot=False,
                       us_regions_first=True,
                       preferred_region=lambda name: 'SCP' in name),
+    # vSphere: 2 vCPUs and memory 4x by default, no spot, free
+    # (vsphere_catalog.py:13-14, :53-72; vsphere.py:128-135)
+    'vsphere': CloudRules('vsphere', default_cpus=2, default_mem_ratio=4,
+                          supports_spot=False, zero_cost=True),
     # OCI: default families VM.Standard.E* / VM.Standard3*, 8 vCPUs whenever
     # `cpus` is missing, memory 4x (oci_catalog.py:71-100,
     # oci_utils.py:32-44); zones and spot (preemptible) prices

@@ -410,6 +410,49 @@ class SCP(_GpuCloud):
 
 
 @registry.CLOUD_REGISTRY.register
+class Vsphere(_GpuCloud):
+    """vSphere: on-premise -- every instance costs 0.0 per hour
+    (vsphere.py:128-135) --, single node, no spot; a requested zone is
+    ignored when the regions are looked up (vsphere.py:37-105, :224-290)."""
+    _REPR = 'vSphere'
+    _CATALOG = 'vsphere'
+    _UNSUPPORTED = {
+        _F.MULTI_NODE:
+            'Multi-node is not supported by the vSphere implementation yet.',
+        _F.CLONE_DISK_FROM_CLUSTER:
+            'Migrating disk is currently not supported on vSphere.',
+        _F.IMAGE_ID:
+            'Specifying image id is currently not supported on vSphere.',
+        _F.DOCKER_IMAGE:
+            ('Docker image is currently not supported on vSphere. You can try '
+             'running docker command inside the `run` section in task.yaml.'),
+        _F.SPOT_INSTANCE: 'Spot instances are not supported in vSphere.',
+        _F.CUSTOM_DISK_TIER: 'Custom disk tiers are not supported in vSphere.',
+        _F.CUSTOM_NETWORK_TIER:
+            'Custom network tier is currently not supported in vSphere.',
+        _F.OPEN_PORTS: 'Opening ports is currently not supported on vSphere.',
+        _F.HIGH_AVAILABILITY_CONTROLLERS:
+            'High availability controllers are not supported on vSphere.',
+        _F.CUSTOM_MULTI_NETWORK:
+            ('Customized multiple network interfaces are not supported on '
+             'vSphere.'),
+        _F.LOCAL_DISK: 'Local disk is not supported on vSphere',
+    }
+
+    def instance_type_to_hourly_cost(self, instance_type: str, use_spot: bool,
+                                     region: Optional[str] = None,
+                                     zone: Optional[str] = None) -> float:
+        del instance_type, use_spot, region, zone
+        return 0.0
+
+    @classmethod
+    def regions_with_offering(cls, instance_type, accelerators, use_spot,
+                              region, zone, resources=None):
+        return super().regions_with_offering(instance_type, accelerators,
+                                             use_spot, region, None, resources)
+
+
+@registry.CLOUD_REGISTRY.register
 class Nebius(cloud.Cloud):
     """Nebius: spot prices, multi-node, no zones, every disk tier but `ultra`
     (nebius.py:53-133, :163-181, :358-420)."""

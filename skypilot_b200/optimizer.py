@@ -494,7 +494,7 @@ class Optimizer:
                     stated[3] is task.resources and stated[4] == ids and
                     stated[5] == (task.num_nodes > 1)):
                 (q_recs, slot_recs, qbase_rel, slot_res, infos,
-                 task_hints) = stated[6]
+                 task_hints, free_slots) = stated[6]
                 q0 = len(b.query_recs)
                 b.query_recs.extend(q_recs)
                 b.slot_recs.extend(slot_recs)
@@ -503,13 +503,21 @@ class Optimizer:
                 for res in res_list:
                     runtime = Optimizer._runtime(task, n_res, res)
                     costs.append((runtime / 3600, nodes, float(runtime)))
-                b.slot_cost.extend([costs[k] for k in slot_res])
+                if free_slots:
+                    # on-premise clouds: the hourly cost is 0.0
+                    b.slot_cost.extend([
+                        (0.0,) + costs[k][1:] if j in free_slots else costs[k]
+                        for j, k in enumerate(slot_res)
+                    ])
+                else:
+                    b.slot_cost.extend([costs[k] for k in slot_res])
                 slot_info.extend(infos)
                 for res, by_cloud in task_hints.items():
                     hints[res].update(by_cloud)
             else:
                 q_mark, info_mark = len(b.query_recs), len(slot_info)
                 slot_res: List[int] = []
+                free_slots = set()
                 task_hints: Dict[Any, Dict[Any, str]] = {}
                 for k, res in enumerate(res_list):
                     if res.__dict__.get('_validated_store') is not store:
@@ -539,7 +547,11 @@ class Optimizer:
                             task_hints.setdefault(res, {})[cloud] = plan.hint
                         if slot is None:
                             continue
-                        b.set_slot_cost(slot, hours, nodes, float(runtime))
+                        if table.rules.zero_cost:
+                            free_slots.add(len(slot_res))
+                            b.set_slot_cost(slot, 0.0, nodes, float(runtime))
+                        else:
+                            b.set_slot_cost(slot, hours, nodes, float(runtime))
                         slot_info.append(
                             _SlotInfo(task, res, cloud, plan, table))
                         slot_res.append(k)
@@ -548,7 +560,8 @@ class Optimizer:
                     task.num_nodes > 1,
                     (b.query_recs[q_mark:], b.slot_recs[slot_begin:],
                      [qb - q_mark for qb in b.slot_qbase[slot_begin:]],
-                     slot_res, slot_info[info_mark:], task_hints))
+                     slot_res, slot_info[info_mark:], task_hints,
+                     free_slots))
             slot_end = b.n_slots
             parents = [
                 p for p in dag_graph.predecessors(task) if not _is_dummy(p)

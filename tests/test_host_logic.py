@@ -443,3 +443,33 @@ def test_preferred_regions_follow_the_clouds_rule():
         else:
             want = [int(n.startswith('us-')) for n in table.region_names]
         assert flags == want, table.name
+
+
+def test_free_clouds_are_stated_with_zero_hours():
+    """vSphere instances cost 0.0 per hour whatever the catalog says
+    (vsphere.py:128-135): their slots carry `hours = 0`, also when the task
+    is replayed from the statement memo; the other clouds' slots do not."""
+    import networkx as nx
+    import numpy as np
+    from skypilot_b200 import optimizer as opt_lib
+    runner.activate_catalog(scenarios.CATALOGS['vsphere3k'])
+    dag = _chain([dict(accelerators='V100'), dict(cpus='8+')])
+    for t in dag.tasks:
+        t.set_time_estimator(lambda r: 7200)
+    graph = dag.get_graph()
+    topo = list(nx.topological_sort(graph))
+    packs = []
+    for _ in range(2):  # stated afresh, then replayed
+        problem = opt_lib.Optimizer._state_problem(  # pylint: disable=protected-access
+            graph, topo, True, [], True)
+        p = problem.builder.pack()
+        slots = p.slots[:p.n_slots]
+        names = [i.cloud.canonical_name() for i in problem.slot_info]
+        assert 'vsphere' in names and 'aws' in names
+        for s, name in zip(slots, names):
+            assert s['hours'] == (0.0 if name == 'vsphere' else 2.0), name
+            assert s['time_value'] == 7200.0
+        packs.append(slots.tobytes())
+    assert packs[0] == packs[1]
+    assert np.isclose(
+        sky.clouds.Vsphere().instance_type_to_hourly_cost('cpu_8', False), 0.0)
