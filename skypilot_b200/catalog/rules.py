@@ -14,7 +14,7 @@ Reference locations:
   Lambda defaults (30 vCPUs)                            lambda_catalog.py:24-25
 """
 import re
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 
 class CloudRules:
@@ -40,7 +40,10 @@ class CloudRules:
                  default_cpus_always: bool = False,
                  default_cpus_exact: bool = False,
                  preferred_region: Optional[Callable[[str], bool]] = None,
-                 zero_cost: bool = False):
+                 zero_cost: bool = False,
+                 acc_query_cpus: bool = True,
+                 acc_query_region: bool = True,
+                 frame_filter: Optional[Callable[[Any], Any]] = None):
         self.name = name
         self.default_family = default_family
         self.host_family = host_family
@@ -81,6 +84,23 @@ class CloudRules:
         # says (vsphere.py:128-135); the catalog prices still order instance
         # types and regions
         self.zero_cost = zero_cost
+        # does the accelerator look-up receive the request's cpus / region and
+        # zone? (Shadeform passes neither: shadeform.py:336-342)
+        self.acc_query_cpus = acc_query_cpus
+        self.acc_query_region = acc_query_region
+        # rows the cloud's catalog module drops when it loads the CSV
+        self.frame_filter = frame_filter
+
+
+# ---- Shadeform -------------------------------------------------------------
+def _shadeform_frame(df):
+    """shadeform_catalog.py:29-47: GPU instances only, names stripped."""
+    df = df[df['InstanceType'].notna()]
+    if 'AcceleratorName' in df.columns:
+        df = df[df['AcceleratorName'].notna()]
+        df = df.assign(
+            AcceleratorName=df['AcceleratorName'].astype(str).str.strip())
+    return df
 
 
 # ---- OCI -----------------------------------------------------------------
@@ -278,6 +298,19 @@ RULES: Dict[str, CloudRules] = {
     # (vsphere_catalog.py:13-14, :53-72; vsphere.py:128-135)
     'vsphere': CloudRules('vsphere', default_cpus=2, default_mem_ratio=4,
                           supports_spot=False, zero_cost=True),
+    # Seeweb: no defaults, no spot, region it-fr2 first
+    # (seeweb_catalog.py:72-86, :155-185)
+    'seeweb': CloudRules('seeweb', default_cpus=None, default_mem_ratio=None,
+                         supports_spot=False, us_regions_first=True,
+                         preferred_region=lambda name: name == 'it-fr2'),
+    # Shadeform: GPU rows only; no defaults; the accelerator look-up gets
+    # neither cpus, memory, region nor zone (shadeform_catalog.py:29-47,
+    # :92-108; shadeform.py:333-342); no spot
+    'shadeform': CloudRules('shadeform', default_cpus=None,
+                            default_mem_ratio=None, supports_spot=False,
+                            acc_query_memory=False, acc_query_cpus=False,
+                            acc_query_region=False,
+                            frame_filter=_shadeform_frame),
     # OCI: default families VM.Standard.E* / VM.Standard3*, 8 vCPUs whenever
     # `cpus` is missing, memory 4x (oci_catalog.py:71-100,
     # oci_utils.py:32-44); zones and spot (preemptible) prices

@@ -155,6 +155,9 @@ class CatalogStore:
         for ci, name in enumerate(names):
             df = frames[name].reset_index(drop=True)
             table = CloudTable(name, ci)
+            if table.rules.frame_filter is not None:
+                # the cloud's catalog module filters its CSV when loading it
+                df = table.rules.frame_filter(df).reset_index(drop=True)
             table.frame = df
             n = len(df)
             if 'GpuInfo' in df.columns:

@@ -439,10 +439,12 @@ class Cloud:
         assert len(accelerators) == 1, resources
         acc, acc_count = list(accelerators.items())[0]
         spec = builder.accelerator_query(
-            self._CATALOG, acc, acc_count, resources.cpus,
+            self._CATALOG, acc, acc_count,
+            resources.cpus if rules.acc_query_cpus else None,
             resources.memory if rules.acc_query_memory else None,
-            use_spot and not rules.spot_without_regions, resources.region,
-            resources.zone,
+            use_spot and not rules.spot_without_regions,
+            resources.region if rules.acc_query_region else None,
+            resources.zone if rules.acc_query_region else None,
             resources.max_hourly_cost, local_disk=local_disk,
             flags_require2=_native.F_PREMIUM_DISK if premium else 0,
             want_list=want_list, want_fuzzy=want_list)

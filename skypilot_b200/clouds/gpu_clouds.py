@@ -453,6 +453,72 @@ class Vsphere(_GpuCloud):
 
 
 @registry.CLOUD_REGISTRY.register
+class Seeweb(_GpuCloud):
+    """Seeweb: single node, no spot, no zones; region it-fr2 is tried first
+    (seeweb.py:40-131, :295-388 -- its feasibility function is written out by
+    hand there but computes what the template does: the cheapest instance type
+    for the request; seeweb_catalog.py:155-185)."""
+    _REPR = 'Seeweb'
+    _CATALOG = 'seeweb'
+    _ZONE_MESSAGE = 'Seeweb does not support zones.'
+    _UNSUPPORTED = {
+        _F.MULTI_NODE: ('Multi-node not supported. '
+                        'Seeweb does not support multi-node clusters.'),
+        _F.CUSTOM_DISK_TIER: ('Custom disk tiers not supported. '
+                              'Seeweb does not support custom disk tiers.'),
+        _F.STORAGE_MOUNTING: ('Storage mounting not supported. '
+                              'Seeweb does not support storage mounting.'),
+        _F.HIGH_AVAILABILITY_CONTROLLERS:
+            ('High availability controllers not supported. '
+             'Seeweb does not support high availability controllers.'),
+        _F.SPOT_INSTANCE: ('Spot instances not supported. '
+                           'Seeweb does not support spot instances.'),
+        _F.CLONE_DISK_FROM_CLUSTER: ('Disk cloning not supported. '
+                                     'Seeweb does not support disk cloning.'),
+        _F.IMAGE_ID: ('Custom image IDs not supported. '
+                      'Seeweb does not support custom image IDs.'),
+        _F.CUSTOM_NETWORK_TIER:
+            ('Custom network tiers not supported. '
+             'Seeweb does not support custom network tiers.'),
+        _F.HOST_CONTROLLERS: ('Host controllers not supported. '
+                              'Seeweb does not support host controllers.'),
+        _F.CUSTOM_MULTI_NETWORK:
+            ('Custom multi-network not supported. '
+             'Seeweb does not support custom multi-network.'),
+        _F.LOCAL_DISK: 'Local disk is not supported on Seeweb',
+    }
+
+
+@registry.CLOUD_REGISTRY.register
+class Shadeform(_GpuCloud):
+    """Shadeform: GPU instances only, single node, no spot, no zones; the
+    accelerator look-up sees only the accelerator and the price cap
+    (shadeform.py:40-115, :300-395; shadeform_catalog.py:29-47)."""
+    _REPR = 'Shadeform'
+    _CATALOG = 'shadeform'
+    _ZONE_MESSAGE = 'Shadeform does not support zones.'
+    _UNSUPPORTED = {
+        _F.STOP: 'Stopping instances not supported on Shadeform.',
+        _F.MULTI_NODE: 'Multi-node clusters not supported on Shadeform.',
+        _F.SPOT_INSTANCE: 'Spot instances not supported on Shadeform.',
+        _F.CUSTOM_DISK_TIER: 'Custom disk tiers not supported on Shadeform.',
+        _F.CUSTOM_NETWORK_TIER:
+            'Custom network tiers not supported on Shadeform.',
+        _F.STORAGE_MOUNTING:
+            'Object storage mounting not supported on Shadeform.',
+        _F.HOST_CONTROLLERS: 'Host controllers not supported on Shadeform.',
+        _F.HIGH_AVAILABILITY_CONTROLLERS:
+            'High availability controllers not supported.',
+        _F.CLONE_DISK_FROM_CLUSTER: 'Disk cloning not supported on Shadeform.',
+        _F.IMAGE_ID: 'Custom image IDs not supported on Shadeform.',
+        _F.DOCKER_IMAGE: 'Docker images not supported on Shadeform yet.',
+        _F.CUSTOM_MULTI_NETWORK:
+            'Custom multiple network interfaces not supported.',
+        _F.LOCAL_DISK: 'Local disk is not supported on Shadeform.',
+    }
+
+
+@registry.CLOUD_REGISTRY.register
 class Nebius(cloud.Cloud):
     """Nebius: spot prices, multi-node, no zones, every disk tier but `ultra`
     (nebius.py:53-133, :163-181, :358-420)."""
