@@ -43,6 +43,9 @@ CATALOGS = {
     'oci5k': {'seed': 31, 'n_rows': 5000, 'clouds': ['aws', 'oci', 'gcp']},
     # SCP next to AWS and Lambda
     'scp4k': {'seed': 41, 'n_rows': 4000, 'clouds': ['aws', 'scp', 'lambda']},
+    # random general DAGs (fuzz_dag_scenarios)
+    'fuzzdag': {'seed': 61, 'n_rows': 6000,
+                'clouds': ['aws', 'gcp', 'azure', 'lambda']},
     # ten clouds at once for the random requests of fuzz_many_scenarios
     'fuzzmany': {'seed': 47, 'n_rows': 9000,
                  'clouds': ['aws', 'gcp', 'lambda', 'runpod', 'cudo', 'ibm',
@@ -490,6 +493,45 @@ _FUZZ_REGIONS = {
 }
 
 
+def fuzz_dag_scenarios(seed=13, n=40):
+    """Seeded random general DAGs (3-6 tasks, every task after the first has
+    one or two parents), COST and TIME; the reference's objective is the
+    exhaustive optimum over its own candidate tables (PuLP / CBC are absent,
+    see oracle/ref_harness/run_reference.py)."""
+    import random
+    rng = random.Random(seed)
+    pool = [{'accelerators': 'V100'}, {'accelerators': 'T4'},
+            {'accelerators': 'L4'}, {'accelerators': 'A100:8'},
+            {'accelerators': 'H100:8'}, {'cpus': '8+'},
+            {'cpus': '32+', 'memory': '128+'}, {'accelerators': 'A10G'},
+            {'accelerators': 'T4:4', 'use_spot': True},
+            {'cpus': '4+', 'use_spot': True}, {'accelerators': 'K80'},
+            {'memory': '64+'}, {'accelerators': 'V100', 'cloud': 'gcp'},
+            {'cpus': '16+', 'cloud': 'azure'},
+            {'accelerators': 'A100', 'cloud': 'lambda'}]
+    out = []
+    for i in range(n):
+        n_tasks = rng.choice([3, 4, 4, 5, 6])
+        tasks, edges = [], []
+        for j in range(n_tasks):
+            t = {'name': f't{j}', 'resources': [dict(rng.choice(pool))]}
+            if rng.random() < 0.85:
+                t['outputs_gb'] = rng.choice([0.5, 20, 300, 2500, 12000])
+            if rng.random() < 0.3:
+                t['num_nodes'] = 2
+            if rng.random() < 0.5:
+                t['time_est'] = {'default': rng.choice([600, 1800, 3600,
+                                                        9000])}
+            tasks.append(t)
+            if j > 0:
+                k = 1 if j == 1 or rng.random() < 0.55 else 2
+                for p_ in rng.sample(range(j), k):
+                    edges.append([p_, j])
+        out.append({'name': f'dag{i}', 'tasks': tasks, 'edges': edges,
+                    'minimize': rng.choice(['cost', 'cost', 'time'])})
+    return out
+
+
 def fuzz_many_scenarios():
     """The same generator over ten clouds at once (enabled-cloud order, ties
     and egress between many clouds)."""
@@ -909,6 +951,7 @@ LATE_SUITES = {
     'vsphere3k': vsphere_scenarios,
     'seeweb3k': seeweb_scenarios,
     'shade3k': shadeform_scenarios,
+    'fuzzdag': fuzz_dag_scenarios,
 }
 ALL_SUITES = dict(SUITES, **LATE_SUITES)
 

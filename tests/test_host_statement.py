@@ -21,7 +21,7 @@ from tests import scenario_runner as runner
 from tests import scenarios
 
 _SUITES = ['multi6k', 'three4k', 'aws50k', 'multi50k', 'gpuclouds', 'ibm5k',
-           'hyperprime', 'latecl', 'fuzz6k', 'oci5k', 'nebvast', 'scp4k', 'fuzzmany', 'vsphere3k', 'seeweb3k', 'shade3k']
+           'hyperprime', 'latecl', 'fuzz6k', 'oci5k', 'nebvast', 'scp4k', 'fuzzmany', 'vsphere3k', 'seeweb3k', 'shade3k', 'fuzzdag']
 
 
 def _stage1(cols, sets, q, lo, hi):

@@ -13,7 +13,7 @@ from tests import scenarios
 
 # the 50k-row suites take ~15 s each on CPU; keep one, sample the other
 _FULL = ['multi6k', 'three4k', 'aws50k', 'gpuclouds', 'ibm5k', 'hyperprime',
-         'latecl', 'fuzz6k', 'oci5k', 'nebvast', 'scp4k', 'fuzzmany', 'vsphere3k', 'seeweb3k', 'shade3k']
+         'latecl', 'fuzz6k', 'oci5k', 'nebvast', 'scp4k', 'fuzzmany', 'vsphere3k', 'seeweb3k', 'shade3k', 'fuzzdag']
 _SAMPLED = {'multi50k': 4}
 
 
