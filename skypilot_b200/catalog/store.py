@@ -51,7 +51,8 @@ def price_keys(values: np.ndarray) -> np.ndarray:
     return np.where(neg, ~bits, bits | np.uint64(1 << 63))
 
 
-CACHE_VERSION = 1  # layout of the columnar cache written by CatalogStore.save
+CACHE_VERSION = 2  # layout + ingest rules of the columnar cache written by CatalogStore.save
+# (2: per-cloud frame filters and preferred regions are applied at ingest)
 
 
 def _zone_map(cols: Dict[str, np.ndarray]) -> np.ndarray:
