@@ -12,7 +12,7 @@ import networkx as nx
 import skypilot_b200 as sky
 from skypilot_b200 import optimizer as opt_lib
 from skypilot_b200 import synth
-from skypilot_b200.utils import registry
+from skypilot_b200 import workloads
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 _loaded: Dict[str, Any] = {}
@@ -40,73 +40,10 @@ def activate_catalog(spec: Dict[str, Any]):
     return store
 
 
-def make_time_estimator(spec):
-    by_acc = spec.get('by_acc', {})
-    default = spec.get('default', 3600)
-    by_cloud = spec.get('by_cloud', {})
-
-    def estimate(resources):
-        seconds = default
-        accs = resources.accelerators
-        if accs:
-            seconds = by_acc.get(list(accs.keys())[0], seconds)
-        if resources.cloud is not None:
-            seconds = by_cloud.get(str(resources.cloud).lower(), seconds)
-        return seconds
-
-    return estimate
-
-
-def _resources(spec):
-    kwargs = dict(spec)
-    cloud = kwargs.pop('cloud', None)
-    if cloud is not None:
-        kwargs['cloud'] = registry.CLOUD_REGISTRY.from_str(cloud)
-    return sky.Resources(**kwargs)
-
-
-def build_dag(scenario):
-    tasks = []
-    with sky.Dag() as dag:
-        for i, tspec in enumerate(scenario['tasks']):
-            task = sky.Task(name=tspec.get('name', f't{i}'),
-                            num_nodes=tspec.get('num_nodes', 1))
-            res = [_resources(r) for r in tspec['resources']]
-            kind = tspec.get('resources_kind', 'single')
-            if kind == 'single':
-                task.set_resources(res[0])
-            elif kind == 'list':
-                task.set_resources(res)
-            else:
-                task.set_resources(set(res))
-            if 'outputs_gb' in tspec:
-                task.set_outputs('CLOUD://out', tspec['outputs_gb'])
-            if 'inputs' in tspec:
-                task.set_inputs(tspec['inputs'][0], tspec['inputs'][1])
-            if 'time_est' in tspec:
-                task.set_time_estimator(make_time_estimator(tspec['time_est']))
-            tasks.append(task)
-        for u, v in scenario.get('edges', []):
-            dag.add_edge(tasks[u], tasks[v])
-    return dag, tasks
-
-
-def blocked_list(scenario) -> Optional[List[Any]]:
-    out = [_resources(spec) for spec in scenario.get('blocked', [])]
-    return out or None
-
-
-def res_record(r) -> Dict[str, Any]:
-    accs = r.accelerators
-    return {
-        'cloud': None if r.cloud is None else str(r.cloud).lower(),
-        'instance_type': r.instance_type,
-        'region': r.region,
-        'zone': r.zone,
-        'accelerators': None if accs is None else
-                        {k: float(v) for k, v in accs.items()},
-        'use_spot': bool(r.use_spot),
-    }
+make_time_estimator = workloads.make_time_estimator
+build_dag = workloads.build_dag
+blocked_list = workloads.blocked_list
+res_record = workloads.res_record
 
 
 def run_scenario(scenario, with_candidates: bool = True) -> Dict[str, Any]:
