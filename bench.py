@@ -57,20 +57,8 @@ WORKLOADS = {
 
 def chain_scenario(n_tasks: int):
     """The cfg2 constraint set, cycled with varying thresholds (cfg4)."""
-    from tests import scenarios  # pylint: disable=import-outside-toplevel
-    base = scenarios.CFG2_TASKS
-    specs = []
-    for i in range(n_tasks):
-        spec = dict(base[i % len(base)])
-        round_ = i // len(base)
-        if round_ and 'cpus' in spec:
-            spec['cpus'] = f'{int(spec["cpus"].rstrip("+")) * (round_ + 1)}+'
-        if round_ and 'memory' in spec and spec['memory'].endswith('+'):
-            spec['memory'] = f'{int(spec["memory"][:-1]) * (round_ + 1)}+'
-        if round_ and 'accelerators' in spec and round_ % 2 == 1:
-            spec['use_spot'] = True
-        specs.append(spec)
-    return scenarios._chain(f'chain{n_tasks}', specs)  # pylint: disable=protected-access
+    from skypilot_b200 import workloads  # pylint: disable=import-outside-toplevel
+    return workloads.chain_scenario(n_tasks)
 
 
 def measured_peaks():
@@ -223,7 +211,8 @@ def main():
     parser.add_argument('--no-latency', action='store_true',
                         help='skip the extra cfg2 (optimize() p50) run')
     parser.add_argument('--scan-mode', default='auto',
-                        choices=['auto', 'tile', 'stream', 'stream3'],
+                        choices=['auto', 'tile', 'stream', 'stream3', 'queue', 'fast',
+                                 'fast-noprune'],
                         help='scan kernel variant (tuning / tests)')
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -257,7 +246,7 @@ def main():
     import skypilot_b200 as sky  # pylint: disable=import-outside-toplevel
     from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
     from skypilot_b200 import optimizer as opt_lib  # pylint: disable=import-outside-toplevel
-    from tests import scenario_runner as runner  # pylint: disable=import-outside-toplevel
+    from skypilot_b200 import workloads as runner  # pylint: disable=import-outside-toplevel
     import networkx as nx  # pylint: disable=import-outside-toplevel
 
     def barrier():
@@ -350,7 +339,7 @@ def main():
         peak, peak_src = measured_peaks()
         achieved = scan_bytes / (scan_kernel_ms / 1e3) / 1e9 if scan_kernel_ms else 0
 
-        scan_form = min(2, max(0, int(getattr(stats, 'scan_form', 0))))
+        scan_form = min(3, max(0, int(getattr(stats, 'scan_form', 0))))
 
         line = {
             'metric': 'candidate (task,instance) placements scored/sec',
@@ -387,7 +376,7 @@ def main():
             },
             'roofline': {
                 'kernel': ('scan_kernel', 'scan_stream_kernel',
-                           'scan_queue_kernel')[scan_form],
+                           'scan_queue_kernel', 'scan2_kernel')[scan_form],
                 'bound': 'hbm', 'achieved': achieved,
                 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                 'frac': achieved / peak if peak else None,

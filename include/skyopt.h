@@ -296,8 +296,11 @@ typedef struct SkyoptStats {
   float scan_kernel_ms;     /* the scan kernel launch alone (events around it) */
   int32_t scan_blocks;      /* its grid size */
   int32_t scan_form;        /* which scan kernel ran: 0 one tile per block,
-                               1 streaming (TMA), 2 queue form */
-  int32_t reserved_;
+                               1 streaming (TMA), 2 queue form, 3 class-table
+                               scan (scan2_kernel), 4 the same inside the fused
+                               step_kernel */
+  int32_t reserved_;        /* scan_form >= 3: rows streamed by the launch in
+                               the 10-byte layout (one pass per query group) */
 } SkyoptStats;
 
 typedef struct SkyoptCatalog SkyoptCatalog; /* opaque */
@@ -314,14 +317,19 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *desc, int device,
 int skyopt_catalog_destroy(SkyoptCatalog *cat);
 int skyopt_catalog_bytes(const SkyoptCatalog *cat, int64_t *device_bytes,
                          int64_t *row_bytes);
-/* Scan kernel selection: 0 = auto (by the amount of work: the queue form for
- * large scans, one tile per block for small ones), 1 = one tile per block
- * (rows straight to registers), 2 / 3 = streaming kernel (TMA double buffering
- * through shared memory; 3 forces three tiles per block), 4 = queue form
- * (a block owns several tiles, its warps share the surviving (chunk, query)
- * pairs), 5 = queue form with 32 tiles per block. Results are identical; used
- * by tests and tuning. The environment variable
- * SKYOPT_SCAN_MODE=tile|stream|stream3|queue|queue32 sets the default. */
+/* Kernel selection: 0 = auto -- the class-table scan inside ONE cooperative
+ * launch per step (scan2 -> barrier -> place -> chain DP) when the catalog's
+ * class dictionaries fit shared memory and the problem has no list / fuzzy
+ * queries, else the round-1 kernels picked by the amount of work (queue form
+ * for large scans, one tile per block for small ones). Forced: 1 = one tile per
+ * block, 2 / 3 = TMA streaming kernel (3: three tiles per block), 4 = queue
+ * form, 5 = queue form with 32 tiles per block, 6 = class-table scan (fused),
+ * 7 = 6 with the zone map and the running bound ignored (HBM stress: every row
+ * is streamed and scored), 8 = 6 as separate launches (scan2, place, solve),
+ * 9 = 8 without pruning. Results are identical in every mode; used by tests,
+ * tuning and the roofline measurement. SKYOPT_SCAN_MODE=tile|stream|stream3|
+ * queue|queue32|fast|fast-noprune|fast-split|fast-split-noprune sets the
+ * default. */
 int skyopt_catalog_set_scan_mode(SkyoptCatalog *cat, int mode);
 
 /*

@@ -333,6 +333,13 @@ class CatalogStore:
                                                   np.int32)
         cols['cloud_n_zones'] = np.asarray(cloud_n_zones, np.int32)
         cols['region_is_us'] = np.asarray(region_is_us or [0], np.uint8)
+        store._finish_columns()
+        return store
+
+    def _finish_columns(self) -> None:
+        """Derived side tables of the per-row columns: the CSR of rows per
+        instance type / accelerator key and the zone map."""
+        store, cols = self, self.columns
         # --- CSR: rows grouped by instance type (ascending row order inside)
         iid = cols['inst_id']
         n_inst = len(store.inst_names)
@@ -364,7 +371,56 @@ class CatalogStore:
         store.max_group_rows = int(
             max([1] + list(counts) + list(acounts)))
         store.acc_names_lower = [k[0].lower() for k in store.acc_keys]
-        return store
+
+    _ROW_COLUMNS = (('price', np.nan), ('spot_price', np.nan),
+                    ('vcpus', np.nan), ('mem', np.nan), ('disk_total', 0.0),
+                    ('acc_key', _native.NONE16), ('region_id', 0),
+                    ('zone_id', _native.NONE16), ('flags', 0), ('inst_id', -1))
+
+    def replicated(self, k: int) -> 'CatalogStore':
+        """A catalog with every cloud's rows repeated `k` times (same names,
+        same dictionaries): a larger-than-L2 table for the HBM stress row of
+        bench.py. Equal prices resolve to the lowest row, so every answer is
+        the original catalog's answer -- which the bench checks."""
+        import copy  # pylint: disable=import-outside-toplevel
+        new = CatalogStore()
+        new.acc_keys = list(self.acc_keys)
+        new.acc_key_index = dict(self.acc_key_index)
+        new.inst_names = list(self.inst_names)
+        new.inst_cloud = list(self.inst_cloud)
+        new.cloud_index = dict(self.cloud_index)
+        parts: Dict[str, List[np.ndarray]] = {n: [] for n, _ in
+                                              self._ROW_COLUMNS}
+        offsets = [0]
+        for table in self.clouds:
+            t = copy.copy(table)
+            n = table.n_rows * k
+            pad = (-n) % _ROW_ALIGN
+            for name, fill in self._ROW_COLUMNS:
+                col = self.columns.get(name)
+                if col is None:
+                    continue
+                real = np.tile(col[table.row_begin:table.row_end], k)
+                if pad:
+                    real = np.concatenate(
+                        [real, np.full(pad, fill, dtype=real.dtype)])
+                parts[name].append(real)
+            t.row_begin = offsets[-1]
+            t.n_rows = n
+            t.row_end = t.row_begin + n
+            offsets.append(offsets[-1] + n + pad)
+            new.clouds.append(t)
+            new.n_real_rows += n
+        for name, _ in self._ROW_COLUMNS:
+            new.columns[name] = (np.ascontiguousarray(
+                np.concatenate(parts[name])) if parts[name] else None)
+        for name in ('cloud_inst_offsets', 'cloud_region_offsets',
+                     'cloud_n_zones', 'region_is_us'):
+            new.columns[name] = self.columns[name]
+        new.columns['cloud_row_offsets'] = np.asarray(offsets, np.int32)
+        new.n_rows = int(offsets[-1])
+        new._finish_columns()  # pylint: disable=protected-access
+        return new
 
     @classmethod
     def from_directory(cls,
@@ -612,10 +668,14 @@ class CatalogStore:
         return handle
 
     def set_scan_mode(self, mode: str, device: int = 0) -> None:
-        """'auto' | 'tile' | 'stream' | 'stream3' | 'queue' | 'queue32'
+        """'auto' | 'tile' | 'stream' | 'stream3' | 'queue' | 'queue32' (the
+        round-1 row-scoring kernels) | 'fast' (class-table scan, one fused
+        launch) | 'fast-noprune' (the same, zone map and bound ignored: HBM
+        stress) | 'fast-split' / 'fast-split-noprune' (separate launches)
         (skyopt_catalog_set_scan_mode)."""
         code = {'auto': 0, 'tile': 1, 'stream': 2, 'stream3': 3, 'queue': 4,
-                'queue32': 5}[mode]
+                'queue32': 5, 'fast': 6, 'fast-noprune': 7, 'fast-split': 8,
+                'fast-split-noprune': 9}[mode]
         _native.check(_native.load().skyopt_catalog_set_scan_mode(
             self.handle(device), code))
 

@@ -15,11 +15,15 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <array>
 #include <vector>
 
 #include "skyopt.h"
 #include "skyopt_kernels.cuh"
+#include "skyopt_fast.cuh"
+#include "skyopt_step.cuh"
 
 using namespace skyopt;
 
@@ -55,6 +59,8 @@ struct Ctx {
   char *dbuf = nullptr; size_t dcap = 0;   // device workspace
   char *hbuf = nullptr; size_t hcap = 0;   // pinned staging
   uint32_t *flush = nullptr; size_t flush_words = 0;
+  unsigned long long *trace = nullptr;  // SKYOPT_TRACE: device-side timeline
+  unsigned int *sync = nullptr;         // step_kernel's barrier counters (zero between launches)
 };
 
 // Bump allocator over one buffer; first pass (base == nullptr) only sizes.
@@ -100,6 +106,16 @@ struct SkyoptCatalog {
   int sort_n = 2, max_regions = 1, max_zones = 1;
   int sm_count = 148;
   int scan_mode = 0;  // 0 auto, 1 one tile per block, 2 streaming (TMA) kernel
+  // round-2 fast path (skyopt_fast.cuh): rank / class layouts and static
+  // launchable orders; fast_ok = the class dictionaries fit shared memory
+  FastCat fast{};
+  bool fast_ok = false;
+  bool noprune = false;   // stress mode: scan2 ignores the zone map and the bound
+  bool split = false;     // fast path as separate launches (scan2, place, solve) instead of step_kernel
+  bool coop = false;      // device supports cooperative launches
+  std::vector<int32_t> n_cm, n_fa, n_rz;   // class counts per cloud
+  std::vector<int32_t> cm_off, fa_off, rz_off;  // [n_clouds + 1] into the dictionaries
+  int64_t fast_bytes = 0;
   std::mutex mu;
   std::vector<Ctx *> free_ctx;
 };
@@ -120,6 +136,8 @@ int upload(SkyoptCatalog *c, const T *src, size_t n, size_t slack, const T **dst
   return 0;
 }
 
+#include "skyopt_fast_host.inc"
+
 int acquire(SkyoptCatalog *c, Ctx **out) {
   {
     std::lock_guard<std::mutex> g(c->mu);
@@ -133,6 +151,8 @@ int acquire(SkyoptCatalog *c, Ctx **out) {
   if (!x) return fail(SKYOPT_ENOMEM, "out of host memory");
   CU(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
   for (auto &e : x->ev) CU(cudaEventCreate(&e));
+  CU(cudaMalloc(&x->sync, 256));
+  CU(cudaMemset(x->sync, 0, 256));
   *out = x;
   return 0;
 }
@@ -168,6 +188,12 @@ struct Plan {
   int64_t n_partials = 0, list_entries = 0, fuzzy_entries = 0;
   int64_t cand_cap = 0;   // expand candidate buffers
   int64_t scan_rows = 0, pass_rows = 0;
+  // round-2 fast path (scan2_kernel + place_kernel)
+  bool fast = false; mutable bool fresh_inputs = true; int n_groups2 = 0, n_pieces = 0, scan2_grid = 0, smem_fa = 0, smem_cm = 0;
+  size_t scan2_smem = 0; int64_t layout_rows = 0;
+  Scan2Group *groups2; const Scan2Group *host_groups2 = nullptr; uint32_t *best_rank, *any_in;
+  PlaceTask *ptasks; SlotAux *saux; uint32_t cap_fa = 0, cap_cm = 0, cap_rz = 0;
+  int32_t *dag_done; unsigned long long *task_mv; bool chain_dags = false; int step_grid = 0; size_t step_smem = 0; mutable bool ran_fused = false;
   // input region (mirrored host/device)
   size_t in_bytes = 0;
   SkyoptQuery *queries; uint32_t *acc_sets; SkyoptSlot *slots; SkyoptTask *tasks;
@@ -206,6 +232,12 @@ void carve_inputs(Plan &P, Carver &c) {
   P.slot_off = c.take<int64_t>(P.ns);
   P.task_off = c.take<int64_t>(P.nt + 1);
   P.task_dag = c.take<int32_t>(P.nt);
+  P.groups2 = c.take<Scan2Group>(P.n_groups2);
+  P.ptasks = c.take<PlaceTask>(P.fast ? P.nt : 0);
+  P.saux = c.take<SlotAux>(P.fast ? P.ns : 0);
+  P.dag_done = c.take<int32_t>(P.fast ? P.nd : 0);
+  P.best_rank = c.take<uint32_t>(P.fast ? P.nq : 0);
+  P.any_in = c.take<uint32_t>(P.fast ? P.nq : 0);
 }
 
 void carve_rest(Plan &P, Carver &c) {
@@ -213,6 +245,7 @@ void carve_rest(Plan &P, Carver &c) {
   P.list_min = c.take<unsigned long long>(P.list_entries);
   P.fuzzy_min = c.take<unsigned long long>(P.fuzzy_entries);
   P.gbest = c.take<unsigned long long>(P.nsq);
+  P.task_mv = c.take<unsigned long long>(P.fast ? (size_t)P.nt * SKYOPT_MAX_CLOUDS : 0);
   P.cand_region = c.take<int32_t>(P.cand_cap);
   P.cand_zone = c.take<int32_t>(P.cand_cap);
   P.cand_pa = c.take<double>(P.cand_cap);
@@ -312,6 +345,25 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   // selective by key) reaches kDenseCut: the dense tiles of the catalog are
   // then spread over more blocks instead of forming the tail of the launch,
   // while the sparse tiles keep all queries fused.
+  // Round-2 fast path: plain argmin queries (no list / fuzzy tables), class
+  // dictionaries that fit shared memory, single-key accelerator slots.
+  P.fast = false;
+  if (cat->fast_ok && (cat->scan_mode == 0 || cat->scan_mode == 6)) {
+    bool ok = true;
+    for (int i = 0; i < P.nq && ok; ++i)
+      if (pb->queries[i].qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY)) ok = false;
+    for (int s = 0; s < P.ns && ok; ++s) {
+      const int set = pb->slots[s].acc_set;
+      if (set < 0) continue;
+      int bits = 0;
+      const uint32_t *w = pb->acc_sets + (size_t)set * SKYOPT_ACC_SET_WORDS;
+      for (int k = 0; k < SKYOPT_ACC_SET_WORDS; ++k) bits += __builtin_popcount(w[k]);
+      if (bits > 1) ok = false;  // several spellings of one accelerator: merge needs a sort
+    }
+    for (int t = 0; t < P.nt && ok; ++t)
+      if (pb->tasks[t].slot_end - pb->tasks[t].slot_begin > kFastMaxTaskSlots) ok = false;
+    P.fast = ok;
+  }
   static const float kDenseCut = [] {
     const char *e = getenv("SKYOPT_DENSE_CUT");
     return e ? (float)atof(e) : 3.0f;
@@ -377,6 +429,66 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   P.rpt = 4; P.tpb = 1; P.stream = false;
   std::vector<Unit> units;
   const long long wave = 2ll * cat->sm_count;
+  // fast path: groups of <= 32 queries per (cloud, price column), cut into
+  // pieces of consecutive 128-row chunks for a persistent grid
+  std::vector<Scan2Group> groups2;
+  std::vector<int> order2;  // scan order -> caller's query index
+  if (P.fast) {
+    long long visits = 0;
+    for (int c = 0; c < C; ++c)
+      for (int col = 0; col < 2; ++col) {
+        std::vector<int> qs;
+        for (int qi : by_cloud[c]) if ((pb->queries[qi].price_col ? 1 : 0) == col) qs.push_back(qi);
+        for (size_t b = 0; b < qs.size(); b += kQChunk) {
+          Scan2Group G{};
+          G.cloud = c; G.col = col; G.q_begin = (int)order2.size();
+          G.q_count = (int)std::min<size_t>(kQChunk, qs.size() - b);
+          G.n_cm = cat->n_cm[c]; G.n_fa = cat->n_fa[c]; G.n_rz = cat->n_rz[c];
+          G.cm_off = cat->cm_off[c]; G.fa_off = cat->fa_off[c]; G.rz_off = cat->rz_off[c];
+          G.chunk0 = cat->cloud_row_offsets[c] / kZoneRows;
+          G.n_chunks = cat->cloud_row_offsets[c + 1] / kZoneRows - G.chunk0;
+          for (int k = 0; k < G.q_count; ++k) order2.push_back(qs[b + k]);
+          if (G.n_chunks > 0) groups2.push_back(G);
+          visits += G.n_chunks;
+          P.cap_fa = std::max(P.cap_fa, (uint32_t)G.n_fa); P.cap_cm = std::max(P.cap_cm, (uint32_t)G.n_cm);
+          P.cap_rz = std::max(P.cap_rz, (uint32_t)G.n_rz);
+        }
+      }
+    P.cap_fa = (P.cap_fa + 3u) & ~3u; P.cap_cm = (P.cap_cm + 3u) & ~3u; P.cap_rz = (P.cap_rz + 3u) & ~3u;
+    P.scan2_smem = scan2_smem_bytes(P.cap_fa, P.cap_cm, P.cap_rz);
+    P.step_smem = std::max(P.scan2_smem, std::max(sizeof(PlaceSmem), sizeof(ChainSmem))) + 16;
+    int per_sm = kScanBlocksPerSM;
+    {
+      static std::mutex occ_mu;
+      std::lock_guard<std::mutex> g(occ_mu);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel, kScanThreads, P.step_smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    }
+    static const int grid_cap = [] { const char *e = getenv("SKYOPT_SCAN2_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (grid_cap > 0) per_sm = std::min(per_sm, grid_cap);
+    const long long resident = (long long)per_sm * cat->sm_count;
+    // Pieces of consecutive chunks: at most one per resident block (a second
+    // piece of another group would re-stage and rebuild the tables), at least
+    // `min_piece` chunks each.
+    static const int min_piece = [] { const char *e = getenv("SKYOPT_SCAN2_MIN_PIECE"); return e ? std::max(1, atoi(e)) : 8; }();
+    const long long spare = std::max<long long>(0, resident - (long long)groups2.size());
+    int piece0 = 0;
+    for (Scan2Group &G : groups2) {
+      long long k = 1 + (visits > 0 ? spare * G.n_chunks / visits : 0);
+      k = std::min<long long>(k, std::max<long long>(1, G.n_chunks / min_piece));
+      G.piece0 = piece0;
+      G.n_pieces = (int)std::max<long long>(1, std::min<long long>(k, G.n_chunks));
+      piece0 += G.n_pieces;
+      P.layout_rows += (long long)G.n_chunks * kZoneRows;
+    }
+    P.step_grid = (int)std::min<long long>(resident, std::max<long long>(piece0, P.nt));
+    P.n_groups2 = (int)groups2.size(); P.n_pieces = piece0;
+    P.scan2_grid = (int)std::min<long long>(resident, std::max(P.n_pieces, 1));
+    P.chain_dags = true;
+    for (int d = 0; d < P.nd; ++d)
+      if (!pb->dags[d].is_chain || pb->dags[d].task_end - pb->dags[d].task_begin > kFastTasks) P.chain_dags = false;
+    P.n_groups = 0; P.nsq = (int)order2.size();
+  } else
   if (cat->scan_mode == 2 || cat->scan_mode == 3) {
     P.stream = true;
     const long long tiles4 = make_units(4, 1, false, units);
@@ -418,7 +530,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
       std::stable_sort(units.begin(), units.end(), [](const Unit &a, const Unit &b) { return a.klass > b.klass; });
   }
   const int tile = kScanThreads * P.rpt;
-  P.n_groups = 0; P.nsq = 0;
+  if (!P.fast) { P.n_groups = 0; P.nsq = 0; }
   std::vector<int> cloud_tiles(C, 0);  // partial slots of one query of the cloud
   for (const Unit &u : units) {
     P.n_groups += (int)u.cuts.size() - 1;
@@ -491,6 +603,55 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   for (int t = 0; t < P.nt; ++t) P.task_dag[t] = 0;
   for (int d = 0; d < P.nd; ++d)
     for (int t = pb->dags[d].task_begin; t < pb->dags[d].task_end; ++t) P.task_dag[t] = d;
+  auto fill_record = [&](ScanQuery &R, int qi) {
+    const SkyoptQuery &q = pb->queries[qi];
+    memset(&R, 0, sizeof(R));
+    R.s = make_query_s(q);
+    R.qid = qi;
+    R.list_base = lbase[qi];
+    R.fuzzy_base = fbase[qi];
+    uint32_t lo32 = 0, hi32 = 0;
+    const int set_idx[2] = {(q.qflags & SKYOPT_Q_ACC) ? q.acc_set : -1,
+                            (q.qflags & SKYOPT_Q_FUZZY) ? q.fuzzy_set : -1};
+    for (int which = 0; which < 2; ++which) {
+      if (set_idx[which] < 0) continue;
+      const uint32_t *src = pb->acc_sets + (size_t)set_idx[which] * SKYOPT_ACC_SET_WORDS;
+      for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
+        R.set[which][w] = src[w];
+        if (w & 1) hi32 |= src[w]; else lo32 |= src[w];
+      }
+    }
+    // 64-bit signature (key id mod 64) of the keys the query can match
+    R.s.sig_lo = (q.qflags & SKYOPT_Q_ACC) ? lo32 : 0xFFFFFFFFu;
+    R.s.sig_hi = (q.qflags & SKYOPT_Q_ACC) ? hi32 : 0xFFFFFFFFu;
+  };
+  if (P.fast) {
+    for (int i = 0; i < P.nsq; ++i) fill_record(P.squeries[i], order2[i]);
+    memcpy(P.groups2, groups2.data(), sizeof(Scan2Group) * groups2.size());
+    memset(P.best_rank, 0xFF, sizeof(uint32_t) * P.nq);
+    memset(P.any_in, 0, sizeof(uint32_t) * P.nq);
+    if (P.nd) memset(P.dag_done, 0, sizeof(int32_t) * P.nd);
+    // what a task block / a slot needs, in one record each
+    for (int t = 0; t < P.nt; ++t) {
+      const SkyoptDag &D = pb->dags[P.task_dag[t]];
+      PlaceTask &T = P.ptasks[t];
+      T.slot_begin = pb->tasks[t].slot_begin; T.slot_end = pb->tasks[t].slot_end;
+      T.blocked_begin = D.blocked_begin; T.blocked_end = D.blocked_end;
+      T.minimize_cost = D.minimize_cost; T.pad_[0] = T.pad_[1] = T.pad_[2] = 0;
+    }
+    for (int sl = 0; sl < P.ns; ++sl) {
+      const SkyoptSlot &S = pb->slots[sl];
+      SlotAux &X = P.saux[sl];
+      memset(&X, 0, sizeof(X));
+      X.max_price = 1.0 / 0.0;
+      if (S.query >= 0) {
+        const SkyoptQuery &Q = pb->queries[S.query];
+        X.rec_base = cat->cloud_row_offsets[Q.cloud]; X.qcol = Q.price_col ? 1 : 0; X.max_price = Q.max_price;
+      }
+      X.cloud_r0 = cat->cloud_row_offsets[S.cloud]; X.cloud_r1 = cat->cloud_row_offsets[S.cloud + 1];
+      X.has_zones = cat->cloud_n_zones[S.cloud] > 0 ? 1 : 0;
+    }
+  }
   int g = 0, qpos = 0, block0 = 0;
   P.pass_rows = 0;
   std::vector<int> unit_pbase(C, 0);  // partial slots used by earlier units of the cloud
@@ -522,26 +683,8 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
         if (q.qflags & SKYOPT_Q_FUZZY) G.need |= 1u;
         // the staged record: constraint vector, offsets and key bitmasks
         ScanQuery &R = P.squeries[qpos + k];
-        memset(&R, 0, sizeof(R));
-        R.s = make_query_s(q);
-        R.qid = qi;
+        fill_record(R, qi);
         R.partial_base = pbase[qi] + unit_pbase[c];
-        R.list_base = lbase[qi];
-        R.fuzzy_base = fbase[qi];
-        uint32_t lo32 = 0, hi32 = 0;
-        const int set_idx[2] = {(q.qflags & SKYOPT_Q_ACC) ? q.acc_set : -1,
-                                (q.qflags & SKYOPT_Q_FUZZY) ? q.fuzzy_set : -1};
-        for (int which = 0; which < 2; ++which) {
-          if (set_idx[which] < 0) continue;
-          const uint32_t *src = pb->acc_sets + (size_t)set_idx[which] * SKYOPT_ACC_SET_WORDS;
-          for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
-            R.set[which][w] = src[w];
-            if (w & 1) hi32 |= src[w]; else lo32 |= src[w];
-          }
-        }
-        // 64-bit signature (key id mod 64) of the keys the query can match
-        R.s.sig_lo = (q.qflags & SKYOPT_Q_ACC) ? lo32 : 0xFFFFFFFFu;
-        R.s.sig_hi = (q.qflags & SKYOPT_Q_ACC) ? hi32 : 0xFFFFFFFFu;
         QueryTest &T = P.qtests[qpos + k];
         T.req_flags = R.s.req_flags; T.grp_bit = R.s.grp_bit;
         T.sig_lo = R.s.sig_lo; T.sig_hi = R.s.sig_hi;
@@ -556,6 +699,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   P.n_blocks = block0;
 
   const ScanGroup *host_groups = P.groups;
+  P.host_groups2 = P.groups2;
   // device views
   Carver d(x->dbuf);
   carve_inputs(P, d);
@@ -566,10 +710,106 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
 
 struct Timeline { float scan_ms = 0, expand_ms = 0, solve_ms = 0; };
 
+// Round-2 path: scan2 -> [finalize2] -> place -> solve. `first` = the result
+// arrays were just initialised by the H2D copy of the input region; later
+// iterations of the device-resident timing loop reset them with one memset.
+int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool want_scan_results) {
+  cudaStream_t st = x->stream;
+  CU(cudaEventRecord(x->ev[1], st));
+  if (P.nq && !P.fresh_inputs) {
+    // best_rank and any_in are adjacent in the input region
+    CU(cudaMemsetAsync(P.best_rank, 0xFF, sizeof(uint32_t) * P.nq, st));
+    CU(cudaMemsetAsync(P.any_in, 0, sizeof(uint32_t) * P.nq, st));
+  }
+  Scan2Args sa{};
+  sa.cat = cat->dev; sa.f = cat->fast; sa.squeries = P.squeries; sa.groups = P.groups2;
+  sa.n_groups = P.n_groups2; sa.n_pieces = P.n_pieces; sa.best_rank = P.best_rank; sa.any1 = P.any_in;
+  sa.zero_flag = P.err_out; sa.cap_fa = P.cap_fa; sa.cap_cm = P.cap_cm; sa.cap_rz = P.cap_rz;
+  sa.trace = x->trace;
+  for (int i = 0; i < std::min(P.n_groups2, kInlineGroups2); ++i) {
+    sa.inline_groups[i] = P.host_groups2[i]; sa.inline_piece0[i] = P.host_groups2[i].piece0;
+  }
+  static const bool noprune_env = [] { const char *e = getenv("SKYOPT_NOPRUNE"); return e && atoi(e) != 0; }();
+  sa.noprune = (noprune_env || cat->noprune) ? 1u : 0u;
+  ExpandOut ex0{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
+  SolveIn in0{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex0, 0};
+  SolveWork w0{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
+  static const bool split_env = [] { const char *e = getenv("SKYOPT_SPLIT"); return e && atoi(e) != 0; }();
+  P.ran_fused = false;
+  if (solve && !want_scan_results && P.nt && cat->coop && !cat->split && !split_env) {
+    // ---- the whole step in one cooperative launch
+    StepArgs sp{};
+    sp.scan = sa;
+    sp.place.cat = cat->dev; sp.place.f = cat->fast; sp.place.ptasks = P.ptasks; sp.place.saux = P.saux;
+    sp.place.best_rank = P.best_rank; sp.place.any1 = P.any_in; sp.place.acc_sets = P.acc_sets;
+    sp.place.in = in0; sp.place.w = w0; sp.place.task_n = P.task_n; sp.place.trace = x->trace;
+    sp.place.task_mv = P.task_mv;
+    sp.out = SolveOut{P.chosen, P.chosen_index, P.task_n, P.dagres, x->trace};
+    sp.task_dag = P.task_dag; sp.n_tasks = P.nt; sp.do_solve = P.chain_dags ? 1 : 0;
+    sp.dag_done = P.dag_done; sp.sync = x->sync;
+    void *args[] = {&sp};
+    CU(cudaEventRecord(x->ev[6], st));
+    cudaError_t le = cudaLaunchCooperativeKernel((const void *)step_kernel, dim3(P.step_grid), dim3(kScanThreads),
+                                                 args, P.step_smem, st);
+    if (le == cudaSuccess) {
+      CU(cudaEventRecord(x->ev[7], st));
+      CU(cudaEventRecord(x->ev[2], st));
+      CU(cudaEventRecord(x->ev[3], st));
+      if (!P.chain_dags && P.nd) {
+        SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres, x->trace};
+        solve_kernel<<<P.nd, kSolveThreads, 0, st>>>(cat->dev, in0, w0, out);
+        CU(cudaGetLastError());
+      }
+      CU(cudaEventRecord(x->ev[4], st));
+      P.ran_fused = true;
+      return 0;
+    }
+    (void)cudaGetLastError();  // not launched (too large for this device): separate launches below
+  }
+  if (P.nq) {
+    {
+    }
+    CU(cudaEventRecord(x->ev[6], st));
+    if (P.n_pieces) {
+      scan2_kernel<<<P.scan2_grid, kScanThreads, P.scan2_smem, st>>>(sa);
+      CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(x->ev[7], st));
+    if (want_scan_results || !solve) {
+      finalize2_kernel<<<(P.nq + 127) / 128, 128, 0, st>>>(cat->dev, cat->fast, P.nq, P.queries,
+                                                          P.best_rank, P.any_in, P.finals, P.any1);
+      CU(cudaGetLastError());
+    }
+  }
+  CU(cudaEventRecord(x->ev[2], st));
+  if (!solve) return 0;
+  if (!P.n_pieces) CU(cudaMemsetAsync(P.err_out, 0, sizeof(int32_t), st));
+  ExpandOut ex{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
+  SolveIn in{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex, 0};
+  SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
+  if (P.nt) {
+    PlaceArgs pa{};
+    pa.cat = cat->dev; pa.f = cat->fast; pa.ptasks = P.ptasks; pa.saux = P.saux; pa.best_rank = P.best_rank;
+    pa.any1 = P.any_in; pa.acc_sets = P.acc_sets; pa.in = in; pa.w = w;
+    pa.task_n = P.task_n; pa.trace = x->trace; pa.task_mv = nullptr;
+    place_kernel<<<P.nt, kScanThreads, sizeof(PlaceSmem), st>>>(pa);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(x->ev[3], st));
+  if (P.nd) {
+    SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres, x->trace};
+    solve_kernel<<<P.nd, kSolveThreads, 0, st>>>(cat->dev, in, w, out);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(x->ev[4], st));
+  return 0;
+}
+
 // Enqueue K1..K3 on the context's stream. Events ev[1..4] bracket the phases.
 int enqueue_kernels(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve,
                     bool want_scan_results = true) {
   cudaStream_t st = x->stream;
+  if (P.fast) return enqueue_fast(cat, x, P, solve, want_scan_results);
   CU(cudaEventRecord(x->ev[1], st));
   if (P.nq) {
     CU(cudaMemsetAsync(P.gbest, 0xFF, sizeof(unsigned long long) * P.nsq, st));
@@ -748,14 +988,17 @@ int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
     CU(cudaEventElapsedTime(&stats->solve_ms, x->ev[3], x->ev[4]));
   }
   CU(cudaEventElapsedTime(&stats->total_ms, x->ev[0], x->ev[5]));
-  stats->scan_launches = P.n_blocks ? 1 : 0;
-  stats->total_launches = (P.n_blocks ? 1 : 0) + ((P.nq && (P.want_finalize || !solve)) ? 1 : 0) +
-                          (solve ? ((P.ns ? 1 : 0) + (P.nd ? 2 : 0)) : 0);
+  stats->scan_launches = (P.fast ? P.n_pieces : P.n_blocks) ? 1 : 0;
+  stats->total_launches = stats->scan_launches + ((P.nq && (P.want_finalize || !solve)) ? 1 : 0) +
+                          (solve ? (P.fast ? ((P.nt ? 1 : 0) + (P.nd ? 1 : 0))
+                                           : ((P.ns ? 1 : 0) + (P.nd ? 2 : 0))) : 0);
+  if (P.ran_fused) { stats->scan_launches = 1; stats->total_launches = 1 + ((P.nd && !P.chain_dags) ? 1 : 0); }
   stats->scan_rows = P.scan_rows;
   stats->scan_passes_rows = P.pass_rows;
-  stats->scan_blocks = P.n_blocks;
-  stats->scan_form = P.stream ? 1 : (P.queue ? 2 : 0); stats->reserved_ = 0;
-  if (P.n_blocks) CU(cudaEventElapsedTime(&stats->scan_kernel_ms, x->ev[6], x->ev[7]));
+  stats->scan_blocks = P.fast ? (P.ran_fused ? P.step_grid : P.scan2_grid) : P.n_blocks;
+  stats->scan_form = P.fast ? (P.ran_fused ? 4 : 3) : (P.stream ? 1 : (P.queue ? 2 : 0));
+  stats->reserved_ = P.fast ? (int32_t)std::min<int64_t>(P.layout_rows, 0x7FFFFFFF) : 0;
+  if (P.fast ? P.n_pieces : P.n_blocks) CU(cudaEventElapsedTime(&stats->scan_kernel_ms, x->ev[6], x->ev[7]));
   return 0;
 }
 
@@ -955,6 +1198,22 @@ int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog 
     else if (!strcmp(mode, "stream3")) c->scan_mode = 3;
     else if (!strcmp(mode, "queue")) c->scan_mode = 4;
     else if (!strcmp(mode, "queue32")) c->scan_mode = 5;
+    else if (!strcmp(mode, "fast")) c->scan_mode = 6;
+    else if (!strcmp(mode, "fast-noprune")) { c->scan_mode = 6; c->noprune = true; }
+    else if (!strcmp(mode, "fast-split")) { c->scan_mode = 6; c->split = true; }
+    else if (!strcmp(mode, "fast-split-noprune")) { c->scan_mode = 6; c->split = true; c->noprune = true; }
+  }
+  rc = build_fast(c, d);
+  if (rc) { skyopt_catalog_destroy(c); return rc; }
+  if (c->fast_ok) {
+    int coop = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess) c->coop = coop != 0;
+    e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlaceSmem));
+    if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) { skyopt_catalog_destroy(c); return fail(SKYOPT_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   }
   CU(cudaDeviceSynchronize());
   *out = c;
@@ -970,6 +1229,8 @@ int skyopt_catalog_destroy(SkyoptCatalog *c) {
     if (x->dbuf) cudaFree(x->dbuf);
     if (x->hbuf) cudaFreeHost(x->hbuf);
     if (x->flush) cudaFree(x->flush);
+    if (x->trace) cudaFree(x->trace);
+    if (x->sync) cudaFree(x->sync);
     delete x;
   }
   for (void *p : c->allocs) cudaFree(p);
@@ -978,10 +1239,14 @@ int skyopt_catalog_destroy(SkyoptCatalog *c) {
 }
 
 int skyopt_catalog_set_scan_mode(SkyoptCatalog *c, int mode) {
-  if (!c || mode < 0 || mode > 5)
+  if (!c || mode < 0 || mode > 9)
     return fail(SKYOPT_EINVAL, "scan mode must be 0 (auto), 1 (tile), 2 (stream), 3 (stream, 3 tiles per block), "
-                               "4 (queue) or 5 (queue, 32 tiles per block)");
-  c->scan_mode = mode;
+                               "4 (queue), 5 (queue, 32 tiles per block), 6 (class-table scan, one fused launch), "
+                               "7 (6 without pruning), 8 (6 as separate launches) or 9 (8 without pruning)");
+  if (mode >= 6 && !c->fast_ok) return fail(SKYOPT_ELIMIT, "the class-table scan is not available for this catalog");
+  c->noprune = mode == 7 || mode == 9;
+  c->split = mode == 8 || mode == 9;
+  c->scan_mode = mode >= 6 ? 6 : mode;
   return 0;
 }
 
@@ -1346,10 +1611,15 @@ int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSol
       CU(cudaMemset(x->flush + flush_words, 0, flush_words * 4));
       x->flush_words = flush_words;
     }
+    const char *trace_path = getenv("SKYOPT_TRACE");
+    const size_t trace_words = (size_t)3 * kTraceBlocks * kTraceSlots;
+    if (trace_path && !x->trace) CU(cudaMalloc(&x->trace, trace_words * 8));
+    if (!trace_path && x->trace) { cudaFree(x->trace); x->trace = nullptr; }
     CU(cudaEventRecord(x->ev[0], st));
     CU(cudaMemcpyAsync(x->dbuf, x->hbuf, P.in_bytes, cudaMemcpyHostToDevice, st));
     P.want_finalize = sol->scan != nullptr;
     for (int it = 0; it < iters; ++it) {
+      if (x->trace) CU(cudaMemsetAsync(x->trace, 0, trace_words * 8, st));
       if (flush_l2) {
         flush_kernel<<<cat->sm_count * 8, 256, 0, st>>>(x->flush, (int64_t)x->flush_words, (uint32_t)it);
         CU(cudaGetLastError());
@@ -1359,10 +1629,17 @@ int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSol
           CU(cudaGetLastError());
         }
       }
+      P.fresh_inputs = false;  // the timed region resets the scan results itself
       if ((r = enqueue_kernels(cat, x, P, true, sol->scan != nullptr))) return r;
       CU(cudaStreamSynchronize(st));
       CU(cudaEventElapsedTime(&iter_ms[it], x->ev[1], x->ev[4]));
-      if (scan_ms && P.n_blocks) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[6], x->ev[7]));
+      if (scan_ms && (P.fast ? P.n_pieces : P.n_blocks)) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[6], x->ev[7]));
+    }
+    if (x->trace) {
+      // the last iteration's per-block timeline (tools/trace2.py reads it)
+      std::vector<unsigned long long> h(trace_words);
+      CU(cudaMemcpy(h.data(), x->trace, trace_words * 8, cudaMemcpyDeviceToHost));
+      if (FILE *f = fopen(trace_path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
     }
     CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(x->ev[5], st));

@@ -1,0 +1,714 @@
+// skyopt_fast.cuh -- the round-2 hot path: a bit-parallel streaming scan and
+// the fused expansion / blocked filter / cost kernel.
+//
+// K1' scan2_kernel  Same answers as scan_kernel (reference
+//                   sky/catalog/common.py:518-569, :641-694), different
+//                   algorithm. At ingest every row is reduced to three small
+//                   dictionary codes -- (vCPUs, MemoryGiB), (flags, accelerator
+//                   key, local disk) and (region, zone) -- and to its RANK in
+//                   the cloud's (price, row) order, one layout per price column,
+//                   10 bytes per row, each 128-row chunk stored in ascending
+//                   rank. A block evaluates the (at most 32) fused constraint
+//                   vectors of its group once per dictionary ENTRY into three
+//                   shared-memory tables of 32-bit masks (bit q = query q
+//                   accepts the entry). A row then costs three table look-ups
+//                   and two ANDs for all 32 queries at once; a 32x32 bit
+//                   transpose over the warp (five shuffles) hands lane q the
+//                   set of lanes whose rows query q accepts, and because lanes
+//                   hold ascending ranks the first set bit is the chunk's
+//                   argmin. No fp64 in the streaming loop, no per-(row, query)
+//                   work: the loop is bound by the HBM stream.
+// K2' place_kernel  expand_kernel + gather_kernel in one launch, block per
+//                   task. The (price, region, zone) ordering of an instance
+//                   type's rows (common.py:793-809; resources_utils.py:454-502)
+//                   does not depend on the request, so it is computed at ingest;
+//                   a slot is then a filtered copy of a static list.
+#pragma once
+
+#include "skyopt_kernels.cuh"
+
+namespace skyopt {
+
+constexpr uint32_t kRankNone = 0xFFFFFFFFu;
+constexpr int kFastWarps = kScanThreads / 32;
+constexpr int kFastMaxZones = 512;      // per-warp host-VM zone table (GCP)
+constexpr int kFastMaxTaskSlots = 64;
+constexpr int kInlineGroups2 = 24;      // scan groups that travel in the kernel parameters
+
+// Device-side timeline (SKYOPT_TRACE=<file>): 16 slots per block and kernel.
+constexpr int kTraceSlots = 16;
+constexpr int kTraceBlocks = 4096;
+__device__ __forceinline__ void trace_mark(unsigned long long *trace, int kernel, int slot) {
+  if (trace && threadIdx.x == 0 && blockIdx.x < kTraceBlocks)
+    trace[((size_t)kernel * kTraceBlocks + blockIdx.x) * kTraceSlots + slot] = global_ns();
+}
+__device__ __forceinline__ void trace_put(unsigned long long *trace, int kernel, int slot,
+                                          unsigned long long v) {
+  if (trace && blockIdx.x < kTraceBlocks)
+    trace[((size_t)kernel * kTraceBlocks + blockIdx.x) * kTraceSlots + slot] = v;
+}
+
+// rank -> what the expansion needs of the cheapest row
+struct RankRec {
+  double price;
+  int32_t row;
+  int32_t inst;
+};
+static_assert(sizeof(RankRec) == 16, "RankRec layout");
+
+// One entry of an instance type's (or accelerator key's) static launchable
+// order: rows with a price, sorted by (price, region, zone), regrouped by the
+// first appearance of their region (resources_utils.py:454-502).
+struct ExpEnt {
+  double price;
+  uint32_t row;      // bit 31: first (cheapest) row of its region
+  uint16_t rg, zn;
+};
+static_assert(sizeof(ExpEnt) == 16, "ExpEnt layout");
+constexpr uint32_t kRegionFirst = 0x80000000u;
+
+// Where a group's static list lives (instance type / accelerator key).
+struct ListRec {
+  int32_t off;       // into exp_ent / aexp_ent (both price columns)
+  int32_t cnt[2];    // entries kept per price column
+  int32_t acc_key;   // instance types: accelerators of the type (inst_acc_key)
+};
+static_assert(sizeof(ListRec) == 16, "ListRec layout");
+
+struct FastCat {
+  // scan layouts, one per price column: chunk-sorted ranks and class codes
+  const uint32_t *s_rank[2];
+  const uint16_t *s_cm[2], *s_fa[2], *s_rz[2];
+  const uint32_t *cmin[2];        // [n_rows / 128] smallest rank of the chunk
+  const RankRec *rank_rec[2];     // [cloud_row_offsets[c] + rank]
+  // class dictionaries, per cloud
+  const double2 *cm_val;          // (vCPUs, MemoryGiB)
+  const uint32_t *fa_key;         // flags | acc_key << 16
+  const double *fa_disk;
+  const uint32_t *rz_key;         // region | zone << 16
+  // static launchable orders
+  const ExpEnt *exp_ent[2];
+  const ListRec *inst_list;       // [n_inst]
+  const ExpEnt *aexp_ent[2];
+  const ListRec *acc_list;        // [n_acc_keys]
+};
+
+struct Scan2Group {
+  int32_t cloud, col;
+  int32_t q_begin, q_count;       // into the scan-order query records
+  int32_t n_cm, n_fa, n_rz;       // class counts of the cloud
+  int32_t cm_off, fa_off, rz_off; // into the class dictionaries
+  int32_t chunk0, n_chunks;       // the cloud's 128-row chunks
+  int32_t piece0, n_pieces;       // the group's share of the launch's pieces
+};
+
+struct Scan2Args {
+  CatDev cat;
+  FastCat f;
+  const ScanQuery *squeries;
+  const Scan2Group *groups;
+  int n_groups, n_pieces;
+  uint32_t *best_rank;            // [n_queries] by caller index; atomicMin
+  uint32_t *any1;                 // [n_queries] any_stage1
+  int32_t *zero_flag;
+  uint32_t noprune;               // 1: ignore the zone map and the bound
+  uint32_t cap_fa, cap_cm, cap_rz;  // shared-memory capacities (entries)
+  unsigned long long *trace;
+  int32_t inline_piece0[kInlineGroups2];
+  Scan2Group inline_groups[kInlineGroups2];
+};
+
+// out(lane q) bit l = in(lane l) bit q
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = (j == 16) ? 0x0000FFFFu : (j == 8) ? 0x00FF00FFu
+                     : (j == 4) ? 0x0F0F0F0Fu : (j == 2) ? 0x33333333u : 0x55555555u;
+    const uint32_t t = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((t & ~m) >> j)) : ((x & m) | ((t & m) << j));
+  }
+  return x;
+}
+
+struct Rows2 {
+  uint4 rk;       // ranks of positions 4*lane .. 4*lane+3 (ascending)
+  uint2 cm, fa, rz;
+};
+
+// Loads that stay where they are written (the prologue issues the first
+// chunk's rows before the tables are built).
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_nc_v2(const void *p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u32(const void *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ Rows2 load_rows2(const Scan2Args &a, int col, int64_t chunk, int lane) {
+  Rows2 r;
+  const int64_t base = chunk * kZoneRows;
+  r.rk = ldg_nc_v4(reinterpret_cast<const uint4 *>(a.f.s_rank[col] + base) + lane);
+  r.cm = ldg_nc_v2(reinterpret_cast<const uint2 *>(a.f.s_cm[col] + base) + lane);
+  r.fa = ldg_nc_v2(reinterpret_cast<const uint2 *>(a.f.s_fa[col] + base) + lane);
+  r.rz = ldg_nc_v2(reinterpret_cast<const uint2 *>(a.f.s_rz[col] + base) + lane);
+  return r;
+}
+
+__device__ __forceinline__ Scan2Group find_group2(const Scan2Args &a, int p) {
+  if (a.n_groups <= kInlineGroups2) {
+    int idx = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int probe = idx + step;
+      if (probe < a.n_groups && probe < kInlineGroups2 && a.inline_piece0[probe] <= p) idx = probe;
+    }
+    return a.inline_groups[idx];
+  }
+  int lo = 0, hi = a.n_groups - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&a.groups[mid].piece0) <= p) lo = mid; else hi = mid - 1;
+  }
+  return a.groups[lo];
+}
+
+// Shared memory of one scan2 block (dynamic): the staged constraint vectors,
+// the raw class dictionaries of the cloud and the three mask tables.
+struct Scan2Smem {
+  ScanQuery *sq;
+  uint32_t *sbest, *sany;
+  uint2 *Tfa; uint32_t *Tcm, *Trz;
+  double2 *d_cm; double *d_disk; uint32_t *d_fa, *d_rz;
+};
+__host__ __device__ inline size_t scan2_smem_bytes(size_t cap_fa, size_t cap_cm, size_t cap_rz) {
+  return kQChunk * sizeof(ScanQuery) + (kQChunk + 4) * sizeof(uint32_t) +
+         cap_fa * (8 + 8 + 4) + cap_cm * (4 + 16) + cap_rz * (4 + 4) + 64;
+}
+__device__ __forceinline__ Scan2Smem carve_scan2(unsigned char *base, const Scan2Args &a) {
+  Scan2Smem s;
+  s.sq = reinterpret_cast<ScanQuery *>(base); base += kQChunk * sizeof(ScanQuery);
+  s.d_cm = reinterpret_cast<double2 *>(base); base += (size_t)a.cap_cm * 16;
+  s.Tfa = reinterpret_cast<uint2 *>(base); base += (size_t)a.cap_fa * 8;
+  s.d_disk = reinterpret_cast<double *>(base); base += (size_t)a.cap_fa * 8;
+  s.sbest = reinterpret_cast<uint32_t *>(base); base += kQChunk * 4;
+  s.sany = reinterpret_cast<uint32_t *>(base); base += 16;
+  s.Tcm = reinterpret_cast<uint32_t *>(base); base += (size_t)a.cap_cm * 4;
+  s.Trz = reinterpret_cast<uint32_t *>(base); base += (size_t)a.cap_rz * 4;
+  s.d_fa = reinterpret_cast<uint32_t *>(base); base += (size_t)a.cap_fa * 4;
+  s.d_rz = reinterpret_cast<uint32_t *>(base);
+  return s;
+}
+
+__device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *smem2) {
+  const Scan2Smem S = carve_scan2(smem2, a);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x == 0 && tid == 0 && a.zero_flag) *a.zero_flag = 0;
+  trace_mark(a.trace, 0, 0);
+  if (a.trace && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    trace_put(a.trace, 0, 6, smid);
+  }
+  const bool prune = a.noprune == 0;
+  unsigned long long n_visit = 0, n_live = 0;
+
+  int cur_group = -1;
+  for (int p = blockIdx.x; p < a.n_pieces; p += gridDim.x) {
+    const Scan2Group G = find_group2(a, p);
+    const int gi = G.piece0;  // identifies the group
+    const int col = G.col, nq = G.q_count;
+    const int pi = p - G.piece0;
+    const int chunk_begin = G.chunk0 + (int)((int64_t)G.n_chunks * pi / G.n_pieces);
+    const int chunk_end = G.chunk0 + (int)((int64_t)G.n_chunks * (pi + 1) / G.n_pieces);
+
+    // ---- the first chunk's rows and the first two summaries leave before
+    // anything else: they do not depend on the tables
+    int ch = chunk_begin + warp;
+    Rows2 cur{}, nxt{};
+    uint4 z0c = make_uint4(0, 0, 0, 0), z0 = make_uint4(0, 0, 0, 0);
+    uint32_t cmc = 0, cm = 0;
+    if (ch < chunk_end) {
+      cur = load_rows2(a, col, ch, lane);
+      if (prune) {
+        z0c = ldg_nc_v4(a.cat.zone_map + ch);
+        cmc = ldg_nc_u32(a.f.cmin[col] + ch);
+        if (ch + kFastWarps < chunk_end) {
+          z0 = ldg_nc_v4(a.cat.zone_map + ch + kFastWarps);
+          cm = ldg_nc_u32(a.f.cmin[col] + ch + kFastWarps);
+        }
+      }
+    }
+
+    if (gi != cur_group) {
+      __syncthreads();  // previous group's tables are still being read
+      const bool first = cur_group < 0;
+      cur_group = gi;
+      // ---- one round trip: constraint vectors and the cloud's dictionaries
+      {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.squeries + G.q_begin);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.sq);
+        const int n16 = nq * (int)(sizeof(ScanQuery) / 16);
+        for (int i = tid; i < n16; i += kScanThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < G.n_cm; i += kScanThreads) S.d_cm[i] = __ldg(a.f.cm_val + G.cm_off + i);
+        for (int i = tid; i < G.n_fa; i += kScanThreads) {
+          S.d_fa[i] = __ldg(a.f.fa_key + G.fa_off + i);
+          S.d_disk[i] = __ldg(a.f.fa_disk + G.fa_off + i);
+        }
+        for (int i = tid; i < G.n_rz; i += kScanThreads) S.d_rz[i] = __ldg(a.f.rz_key + G.rz_off + i);
+      }
+      __syncthreads();
+      trace_mark(a.trace, 0, 1);
+      const long long c_tab = clock64();
+      if (tid < kQChunk) {
+        // a later piece starts from what the grid has found so far
+        uint32_t seed = kRankNone;
+        if (tid < nq && prune && !first)
+          seed = *reinterpret_cast<volatile uint32_t *>(a.best_rank + S.sq[tid].qid);
+        S.sbest[tid] = seed;
+      }
+      if (tid == 0) S.sany[0] = 0;
+      // ---- the three mask tables: lane q holds query q's constraint vector in
+      // registers, a warp takes one dictionary entry at a time and one ballot
+      // gives the entry's 32-bit mask. Every query is evaluated on the entry
+      // exactly like score_rows does on a row (same fp64 comparisons,
+      // common.py:431-480).
+      {
+        QueryS Q{};
+        const uint32_t *set0 = S.sq[0].set[0];
+        const bool lq = lane < nq;
+        if (lq) { Q = S.sq[lane].s; set0 = S.sq[lane].set[0]; }
+        const bool is_acc = (Q.qflags & SKYOPT_Q_ACC) != 0;
+        const bool ratio = Q.mem_op == SKYOPT_OP_RATIO;
+        for (int e = warp; e < G.n_fa; e += kFastWarps) {
+          const uint32_t key = S.d_fa[e];
+          const double disk = S.d_disk[e];
+          const uint32_t fl = key & 0xFFFFu, ak = key >> 16;
+          const uint32_t akey = (ak == SKYOPT_NONE16) ? (uint32_t)(32 * SKYOPT_ACC_SET_WORDS) : ak;
+          // flags / fixed-host group (the low 16 bits of the row key)
+          bool ok = lq && ((fl ^ Q.val_lo) & Q.mask_lo & 0xFFFFu) == 0u;
+          if (is_acc) ok = ok && ((set0[akey >> 5] >> (akey & 31u)) & 1u);
+          if (Q.disk_op != 0)
+            ok = ok && (Q.disk_op == SKYOPT_DISK_GE ? (disk >= Q.disk_size)
+                                                    : (fabs(disk - Q.disk_size) < 1.0));
+          const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, ok);
+          const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, ok && ((fl & Q.flags2) == Q.flags2));
+          if (lane == 0) S.Tfa[e] = make_uint2(m1, m2);
+        }
+        for (int e = warp; e < G.n_cm; e += kFastWarps) {
+          const double2 v = S.d_cm[e];
+          const double lo = ratio ? __dmul_rn(v.x, Q.mem_lo) : Q.mem_lo;
+          const bool okc = (Q.cpus_op == 0) | ((v.x >= Q.cpu_lo) & (v.x <= Q.cpu_hi));
+          const bool okr = (Q.mem_op == 0) | ((v.y >= lo) & (v.y <= Q.mem_hi));
+          const uint32_t m = __ballot_sync(0xFFFFFFFFu, lq & okc & okr);
+          if (lane == 0) S.Tcm[e] = m;
+        }
+        for (int e = warp; e < G.n_rz; e += kFastWarps) {
+          const uint32_t key = S.d_rz[e];  // region | zone << 16
+          // region: row-key bits 16..31, zone: bits 32..47
+          const bool ok = lq && (((key & 0xFFFFu) ^ (Q.val_lo >> 16)) & (Q.mask_lo >> 16)) == 0u &&
+                          (((key >> 16) ^ Q.val_hi) & Q.mask_hi & 0xFFFFu) == 0u;
+          const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+          if (lane == 0) S.Trz[e] = m;
+        }
+      }
+      __syncthreads();
+      trace_mark(a.trace, 0, 2);
+      if (tid == 0) trace_put(a.trace, 0, 7, (unsigned long long)(clock64() - c_tab));
+    }
+    // lane q <-> query q: what the zone-map test needs
+    uint32_t req = 0, grp = 0, sg_lo = 0, sg_hi = 0;
+    bool acc = false;
+    if (lane < nq) {
+      const QueryS &L = S.sq[lane].s;
+      req = L.req_flags; grp = L.grp_bit; sg_lo = L.sig_lo; sg_hi = L.sig_hi;
+      acc = (L.qflags & SKYOPT_Q_ACC) != 0;
+    }
+    uint32_t best = S.sbest[lane];
+    uint32_t anyw = 0;
+
+    auto test = [&](const uint4 &z, uint32_t cmn) -> uint32_t {
+      if (!prune) return 0xFFFFFFFFu;
+      const bool pass = lane < nq && ((z.x & req) == req) && ((z.w & grp) == grp) &&
+                        (!acc || (((sg_lo & z.y) | (sg_hi & z.z)) != 0u)) && cmn < best;
+      return __ballot_sync(0xFFFFFFFFu, pass);
+    };
+
+    // software pipeline: rows of chunk i + 1 and the summary of chunk i + 2
+    // are in flight while chunk i is scored
+    uint32_t live_cur = (ch < chunk_end) ? test(z0c, cmc) : 0u;
+    for (; ch < chunk_end; ch += kFastWarps) {
+      const int nch = ch + kFastWarps;
+      uint32_t live_next = 0;
+      if (nch < chunk_end) {
+        live_next = test(z0, cm);
+        if (live_next) nxt = load_rows2(a, col, nch, lane);
+        if (prune && nch + kFastWarps < chunk_end) {
+          z0 = ldg_nc_v4(a.cat.zone_map + nch + kFastWarps);
+          cm = ldg_nc_u32(a.f.cmin[col] + nch + kFastWarps);
+        }
+      }
+      ++n_visit;
+      if (live_cur) {
+        ++n_live;
+        const uint32_t c0 = cur.cm.x & 0xFFFFu, c1 = cur.cm.x >> 16, c2 = cur.cm.y & 0xFFFFu, c3 = cur.cm.y >> 16;
+        const uint32_t f0 = cur.fa.x & 0xFFFFu, f1 = cur.fa.x >> 16, f2 = cur.fa.y & 0xFFFFu, f3 = cur.fa.y >> 16;
+        const uint32_t r0 = cur.rz.x & 0xFFFFu, r1 = cur.rz.x >> 16, r2 = cur.rz.y & 0xFFFFu, r3 = cur.rz.y >> 16;
+        const uint2 a0 = S.Tfa[f0], a1 = S.Tfa[f1], a2 = S.Tfa[f2], a3 = S.Tfa[f3];
+        const uint32_t z_0 = S.Trz[r0], z_1 = S.Trz[r1], z_2 = S.Trz[r2], z_3 = S.Trz[r3];
+        const uint32_t m0 = a0.y & S.Tcm[c0] & z_0, m1 = a1.y & S.Tcm[c1] & z_1;
+        const uint32_t m2 = a2.y & S.Tcm[c2] & z_2, m3 = a3.y & S.Tcm[c3] & z_3;
+        anyw |= (a0.x & z_0) | (a1.x & z_1) | (a2.x & z_2) | (a3.x & z_3);
+        const uint32_t many = m0 | m1 | m2 | m3;
+        // lane q: which lanes hold a row query q accepts; lanes are in
+        // ascending rank order, so the first one holds the chunk's argmin
+        const uint32_t B = warp_transpose32(many, lane);
+        const int src = B ? (__ffs(B) - 1) : 0;
+        const uint32_t first = __shfl_sync(0xFFFFFFFFu, cur.rk.x, src);
+        const bool maybe = B != 0u && first < best;
+        if (__any_sync(0xFFFFFFFFu, maybe)) {
+          // which of that lane's four rows (ascending) is the first accepted
+          const uint32_t q0 = __shfl_sync(0xFFFFFFFFu, m0, src), q1 = __shfl_sync(0xFFFFFFFFu, m1, src);
+          const uint32_t q2 = __shfl_sync(0xFFFFFFFFu, m2, src);
+          const uint32_t k1 = __shfl_sync(0xFFFFFFFFu, cur.rk.y, src), k2 = __shfl_sync(0xFFFFFFFFu, cur.rk.z, src);
+          const uint32_t k3 = __shfl_sync(0xFFFFFFFFu, cur.rk.w, src);
+          if (maybe) {
+            const uint32_t cand = ((q0 >> lane) & 1u) ? first : ((q1 >> lane) & 1u) ? k1
+                                : ((q2 >> lane) & 1u) ? k2 : k3;
+            if (cand < best) best = cand;
+          }
+        }
+      }
+      cur = nxt; live_cur = live_next;
+      if (prune && lane < nq) {
+        // share the bound inside the block (any achieved rank is a valid bound)
+        const uint32_t sb = S.sbest[lane];
+        if (best < sb) atomicMin(&S.sbest[lane], best); else best = sb;
+      }
+    }
+    // ---- publish: block minimum per query, any-match bits
+    anyw = __reduce_or_sync(0xFFFFFFFFu, anyw);
+    if (lane < nq && best != kRankNone) atomicMin(&S.sbest[lane], best);
+    if (lane == 0 && anyw) atomicOr(&S.sany[0], anyw);
+    __syncthreads();
+    trace_mark(a.trace, 0, 3);
+    if (tid < nq) {
+      const int qid = S.sq[tid].qid;
+      const uint32_t v = S.sbest[tid];
+      if (v != kRankNone) atomicMin(a.best_rank + qid, v);
+      if ((S.sany[0] >> tid) & 1u) atomicOr(a.any1 + qid, 1u);
+    }
+  }
+  trace_mark(a.trace, 0, 4);
+  if (a.trace && lane == 0 && blockIdx.x < kTraceBlocks) {
+    atomicAdd(&a.trace[((size_t)blockIdx.x) * kTraceSlots + 5], n_visit | (n_live << 32));
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan2_kernel(Scan2Args a) {
+  extern __shared__ __align__(16) unsigned char smem2[];
+  scan2_body(a, smem2);
+}
+
+// Scan results in the caller's shape (skyopt_scan / SkyoptSolution.scan).
+__global__ void finalize2_kernel(CatDev cat, FastCat f, int n_queries,
+                                 const SkyoptQuery *__restrict__ queries,
+                                 const uint32_t *__restrict__ best_rank,
+                                 const uint32_t *__restrict__ any_in,
+                                 ScanFinal *__restrict__ finals, uint32_t *__restrict__ any1) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  const SkyoptQuery Q = queries[q];
+  ScanFinal out; out.key = kKeyNone; out.row = -1; out.inst = -1;
+  const uint32_t r = best_rank[q];
+  if (r != kRankNone) {
+    const RankRec rec = f.rank_rec[Q.price_col ? 1 : 0][(int64_t)cat.cloud_row_offsets[Q.cloud] + r];
+    if (rec.price <= Q.max_price) { out.key = price_key(rec.price); out.row = rec.row; out.inst = rec.inst; }
+  }
+  finals[q] = out;
+  any1[q] = any_in[q];
+}
+
+// ---------------------------------------------------------------------------
+// K2': block per task.
+
+// What a task block needs of its task and DAG, in one record (host-prepared).
+struct PlaceTask {
+  int32_t slot_begin, slot_end;
+  int32_t blocked_begin, blocked_end;
+  int32_t minimize_cost;
+  int32_t pad_[3];
+};
+static_assert(sizeof(PlaceTask) == 32, "PlaceTask layout");
+
+// What a slot needs of its query (host-prepared): where the query's ranks
+// decode and its price cap.
+struct SlotAux {
+  int64_t rec_base;     // cloud_row_offsets[query.cloud]
+  int32_t qcol;         // the query's price column
+  int32_t cloud_r0, cloud_r1;  // row range of the slot's cloud
+  int32_t has_zones;
+  double max_price;
+};
+static_assert(sizeof(SlotAux) == 32, "SlotAux layout");
+
+struct PlaceArgs {
+  CatDev cat;
+  FastCat f;
+  const PlaceTask *ptasks;
+  const SlotAux *saux;
+  const uint32_t *best_rank;
+  const uint32_t *any1;
+  const uint32_t *acc_sets;
+  SolveIn in;
+  SolveWork w;
+  int32_t *task_n;
+  unsigned long long *task_mv;   // [n_tasks][n_clouds] price_key(min value) per cloud, or null
+  unsigned long long *trace;
+};
+
+struct PlaceSlot {
+  int32_t inst;        // instance type expanded (-1: empty slot, -2: TPU-VM)
+  int32_t host_off, host_n;  // host VM's static list (GCP accelerator slots)
+  int32_t list_off, list_n;  // the list that is filtered into candidates
+  int32_t kind;        // 0 empty, 1 instance list, 2 accelerator list
+  int32_t cand_acc;
+  int32_t n_e[2], n_b[2];  // kept before / after the blocked filter, [us, other]
+  unsigned long long vmin; // price_key of the cheapest unblocked candidate's value
+};
+
+struct PlaceSmem {
+  double host[kFastWarps][kFastMaxZones];
+  SkyoptSlot slot[kFastMaxTaskSlots];
+  SlotAux aux[kFastMaxTaskSlots];
+  PlaceSlot ps[kFastMaxTaskSlots];
+  int base[kFastMaxTaskSlots + 1];
+};
+
+__device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned char *smem) {
+  PlaceSmem &M = *reinterpret_cast<PlaceSmem *>(smem);
+  PlaceSlot *ps = M.ps;
+  SkyoptSlot *s_slot = M.slot;
+  SlotAux *s_aux = M.aux;
+  int *s_base = M.base;
+  double (*s_host)[kFastMaxZones] = M.host;
+  const CatDev &cat = a.cat;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  trace_mark(a.trace, 1, 0);
+  const PlaceTask TK = a.ptasks[t];
+  const int ns = TK.slot_end - TK.slot_begin;
+  const double kNaN = __longlong_as_double(0x7FF8000000000000ll);
+
+  // ---- phase A: what each slot expands (thread per slot)
+  if (tid < ns) {
+    const int s = TK.slot_begin + tid;
+    const SkyoptSlot S = a.in.slots[s];
+    const SlotAux X = a.saux[s];
+    s_slot[tid] = S; s_aux[tid] = X;
+    PlaceSlot p{};
+    int inst = S.inst_id;
+    bool empty = false;
+    // independent loads first
+    const uint32_t gate = (S.gate_query >= 0) ? __ldcg(a.any1 + S.gate_query) : 1u;
+    const uint32_t r = (S.query >= 0) ? __ldcg(a.best_rank + S.query) : 0u;
+    if (gate == 0u) empty = true;
+    if (S.query >= 0) {
+      if (r == kRankNone) empty = true;
+      else {
+        const RankRec rec = a.f.rank_rec[X.qcol][X.rec_base + r];
+        if (!(rec.price <= X.max_price)) empty = true;  // price cap (common.py:563, :681)
+        inst = rec.inst;
+        if (inst < 0) empty = true;
+      }
+    }
+    const int col = S.price_col ? 1 : 0;
+    if (empty || (inst < 0 && inst != -2)) {
+      p.kind = 0; p.inst = -1;
+    } else {
+      p.inst = inst;
+      ListRec host{};
+      if (inst >= 0) host = a.f.inst_list[inst];
+      int acc = S.cand_acc_key;
+      if (acc < 0 && inst >= 0) acc = host.acc_key;
+      p.cand_acc = acc;
+      if (S.acc_set >= 0) {
+        // the set holds exactly one key (checked on the host)
+        const uint32_t *set = a.acc_sets + (int64_t)S.acc_set * SKYOPT_ACC_SET_WORDS;
+        int key = -1;
+        for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
+          const uint32_t v = set[w];
+          if (v && key < 0) key = 32 * w + __ffs(v) - 1;
+        }
+        p.kind = 2;
+        if (key >= 0) { const ListRec L = a.f.acc_list[key]; p.list_off = L.off; p.list_n = L.cnt[col]; }
+        if (inst >= 0) { p.host_off = host.off; p.host_n = host.cnt[col]; }
+      } else {
+        p.kind = 1;
+        p.list_off = host.off;
+        p.list_n = host.cnt[col];
+      }
+    }
+    ps[tid] = p;
+  }
+  __syncthreads();
+  trace_mark(a.trace, 1, 1);
+
+  // One pass over a slot's static list by one warp.
+  auto walk = [&](int ls, bool write, int base_e0, int base_e1, int base_b0, int base_b1) {
+    PlaceSlot &p = ps[ls];
+    const int s = TK.slot_begin + ls;
+    const SkyoptSlot &S = s_slot[ls];
+    const SlotAux &X = s_aux[ls];
+    const int col = S.price_col ? 1 : 0;
+    const bool has_zones = X.has_zones != 0;
+    const bool split = S.split_by_zone && has_zones;
+    const int reg0 = cat.cloud_region_offsets[S.cloud];
+    const bool gcp = p.kind == 2;
+    const ExpEnt *list = (gcp ? a.f.aexp_ent[col] : a.f.exp_ent[col]) + p.list_off;
+    double *host = s_host[warp];
+    if (gcp && p.inst >= 0) {
+      // host VM price per zone (gcp.py:296-322)
+      for (int i = lane; i < kFastMaxZones; i += 32) host[i] = kNaN;
+      __syncwarp();
+      const ExpEnt *hl = a.f.exp_ent[col] + p.host_off;
+      for (int i = lane; i < p.host_n; i += 32) {
+        const ExpEnt e = hl[i];
+        if (e.zn != SKYOPT_NONE16 && e.zn < kFastMaxZones) host[e.zn] = e.price;
+      }
+      __syncwarp();
+    }
+    int ne0 = 0, ne1 = 0, nb0 = 0, nb1 = 0;
+    unsigned long long vmin = kKeyNone;
+    const int64_t eoff = a.in.slot_off[s];
+    const int64_t toff = a.in.task_off[t];
+    for (int i0 = 0; i0 < p.list_n; i0 += 32) {
+      const int i = i0 + lane;
+      bool keep = i < p.list_n;
+      ExpEnt e{};
+      int rg = 0, zn = 0;
+      double pa = 0.0, pb = 0.0;
+      if (keep) {
+        e = list[i];
+        const int row = (int)(e.row & ~kRegionFirst);
+        rg = e.rg; zn = e.zn;
+        if (gcp && (row < X.cloud_r0 || row >= X.cloud_r1)) keep = false;
+        if (S.region_id >= 0 && rg != S.region_id) keep = false;
+        if (S.zone_id >= 0 && (!has_zones || zn != S.zone_id)) keep = false;
+        if (!split && S.zone_id < 0 && !(e.row & kRegionFirst)) keep = false;
+        pa = e.price;
+        if (gcp) {
+          pb = pa;
+          if (p.inst >= 0) {
+            const double hb = (zn < kFastMaxZones) ? host[zn] : kNaN;
+            if (hb != hb) keep = false;
+            pa = hb;
+          } else {
+            pa = 0.0;
+          }
+        }
+      }
+      const bool other = keep && S.us_first && !cat.region_is_us[reg0 + rg];
+      const int zout = (split || S.zone_id >= 0) ? (has_zones ? zn : -1) : -1;
+      bool blocked = false;
+      if (keep) {
+        for (int b = TK.blocked_begin; b < TK.blocked_end; ++b) {
+          const SkyoptBlocked Bk = a.in.blocked[b];
+          const bool m = (Bk.cloud == -1 || Bk.cloud == S.cloud) &&
+                         (Bk.inst_id == -1 || Bk.inst_id == p.inst) &&
+                         (Bk.region_id == -1 || Bk.region_id == rg) &&
+                         (Bk.zone_id == -1 || Bk.zone_id == zout) &&
+                         (Bk.acc_key == -1 || Bk.acc_key == p.cand_acc) &&
+                         (Bk.use_spot == -1 || Bk.use_spot == S.use_spot);
+          if (m) { blocked = true; break; }
+        }
+      }
+      const uint32_t ke0 = __ballot_sync(0xFFFFFFFFu, keep && !other);
+      const uint32_t ke1 = __ballot_sync(0xFFFFFFFFu, keep && other);
+      const uint32_t kb0 = __ballot_sync(0xFFFFFFFFu, keep && !other && !blocked);
+      const uint32_t kb1 = __ballot_sync(0xFFFFFFFFu, keep && other && !blocked);
+      if (write && keep) {
+        const uint32_t below = (1u << lane) - 1u;
+        const int pe = other ? base_e1 + ne1 + __popc(ke1 & below) : base_e0 + ne0 + __popc(ke0 & below);
+        const int64_t ref = eoff + pe;
+        a.in.ex.cand_region[ref] = rg;
+        a.in.ex.cand_zone[ref] = zout;
+        a.in.ex.cand_price_a[ref] = pa;
+        a.in.ex.cand_price_b[ref] = pb;
+        if (!blocked) {
+          const int pbk = other ? base_b1 + nb1 + __popc(kb1 & below) : base_b0 + nb0 + __popc(kb0 & below);
+          const int64_t o = toff + pbk;
+          // float(hourly_cost * hours) * max(num_nodes - reserved, 0)
+          const double hourly = __dadd_rn(pa, pb);
+          a.w.tc_ref[o] = (int32_t)ref;
+          a.w.tc_slot[o] = s;
+          a.w.tc_cloud[o] = S.cloud;
+          a.w.tc_hourly[o] = hourly;
+          const double value = TK.minimize_cost ? __dmul_rn(__dmul_rn(hourly, S.hours), S.node_mult)
+                                                : S.time_value;
+          a.w.tc_value[o] = value;
+          const unsigned long long vk = price_key(value);
+          if (vk < vmin) vmin = vk;
+        }
+      }
+      ne0 += __popc(ke0); ne1 += __popc(ke1); nb0 += __popc(kb0); nb1 += __popc(kb1);
+    }
+    if (!write && lane == 0) { p.n_e[0] = ne0; p.n_e[1] = ne1; p.n_b[0] = nb0; p.n_b[1] = nb1; }
+    if (write) {
+      // cheapest value of the slot (the chain DP starts from per-cloud minima)
+      const uint32_t hi = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)(vmin >> 32));
+      const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, ((uint32_t)(vmin >> 32) == hi) ? (uint32_t)vmin : 0xFFFFFFFFu);
+      if (lane == 0) p.vmin = ((unsigned long long)hi << 32) | lo;
+    }
+  };
+
+  // ---- phase B1: count
+  for (int ls = warp; ls < ns; ls += kFastWarps) {
+    if (ps[ls].kind != 0) walk(ls, false, 0, 0, 0, 0);
+    else if (lane == 0) { ps[ls].n_e[0] = ps[ls].n_e[1] = ps[ls].n_b[0] = ps[ls].n_b[1] = 0; }
+  }
+  __syncthreads();
+  trace_mark(a.trace, 1, 2);
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < ns; ++i) { s_base[i] = acc; acc += ps[i].n_b[0] + ps[i].n_b[1]; }
+    s_base[ns] = acc;
+    a.task_n[t] = acc;
+  }
+  if (tid < ns) {
+    const int s = TK.slot_begin + tid;
+    a.in.ex.slot_count[s] = ps[tid].n_e[0] + ps[tid].n_e[1];
+    a.in.ex.slot_inst[s] = ps[tid].inst;
+  }
+  __syncthreads();
+  // ---- phase B2: write (same walk, now with the partition bases)
+  for (int ls = warp; ls < ns; ls += kFastWarps) {
+    if (ps[ls].kind != 0) walk(ls, true, 0, ps[ls].n_e[0], s_base[ls], s_base[ls] + ps[ls].n_b[0]);
+    else if (lane == 0) ps[ls].vmin = kKeyNone;
+  }
+  if (a.task_mv) {
+    __syncthreads();
+    if (tid < cat.n_clouds) {
+      unsigned long long k = kKeyNone;
+      for (int i = 0; i < ns; ++i)
+        if (s_slot[i].cloud == tid && ps[i].vmin < k) k = ps[i].vmin;
+      a.task_mv[(int64_t)t * cat.n_clouds + tid] = k;
+    }
+  }
+  trace_mark(a.trace, 1, 3);
+}
+
+__global__ void __launch_bounds__(kScanThreads) place_kernel(PlaceArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_place[];
+  place_body(a, blockIdx.x, smem_place);
+}
+
+}  // namespace skyopt

@@ -1350,6 +1350,7 @@ struct SolveOut {
   int32_t *chosen_index;       // [n_tasks]
   int32_t *task_n;             // [n_tasks]
   SkyoptDagResult *dag;        // [n_dags]
+  unsigned long long *trace;   // SKYOPT_TRACE timeline (kernel 2), or null
 };
 
 __device__ __forceinline__ void lexmin(double &v, int &i, double ov, int oi) {
@@ -1455,6 +1456,11 @@ gather_kernel(CatDev cat, SolveIn in, SolveWork w, const int32_t *__restrict__ t
   if (tid == 0) task_n[t] = kept_total;
 }
 
+__device__ __forceinline__ void solve_mark(const SolveOut &out, int slot) {
+  if (out.trace && threadIdx.x == 0 && blockIdx.x < 4096)
+    out.trace[((size_t)2 * 4096 + blockIdx.x) * 16 + slot] = global_ns();
+}
+
 __global__ void __launch_bounds__(kSolveThreads)
 solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   constexpr int kWarps = kSolveThreads / 32;
@@ -1468,6 +1474,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   __shared__ double s_red_val[kWarps];
   __shared__ long long s_red_idx[kWarps];
 
+  solve_mark(out, 0);
   const SkyoptDag D = in.dags[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = cat.n_clouds;
@@ -1496,6 +1503,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   }
 
   const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+  solve_mark(out, 1);
 
   // ---- Phase B, fast path for chains of up to kFastTasks tasks. The
   // recurrence  dp[c] = value[c] + min_p (dp[p] + egress(p, c))  is the
@@ -1545,6 +1553,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
           atomicMin(&s_mv[lt][w.tc_cloud[toff + c]], (unsigned long long)price_key(w.tc_value[toff + c]));
       }
       __syncthreads();
+      solve_mark(out, 2);
       if (warp == 0) {
         // the C-vector recurrence: lane h owns cloud h
         for (int lt = 0; lt < T; ++lt) {
@@ -1568,6 +1577,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
         }
       }
       __syncthreads();
+      solve_mark(out, 3);
       // winners: pair (lt, h) = first minimum over task lt's candidates p of
       // fl(dp[p] + e_{lt+1}(cloud(p), h)); the pair (T-1, 0) is the dummy sink
       // (egress 0).
@@ -1601,6 +1611,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
         }
       }
       __syncthreads();
+      solve_mark(out, 4);
       if (tid == 0) {
         SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = s_obj;
         out.dag[blockIdx.x] = r;
@@ -1809,6 +1820,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
   }
 plan_records:
   __syncthreads();
+  solve_mark(out, 5);
   if (in.tables_only) return;
   // ---- the plan as candidate records
   for (int lt = tid; lt < T; lt += kSolveThreads) {
@@ -1825,6 +1837,7 @@ plan_records:
     c.value = w.tc_value[o];
     out.chosen[t] = c;
   }
+  solve_mark(out, 6);
 }
 
 // Optional full candidate tables (display / _fill_in_launchable_resources).

@@ -567,7 +567,13 @@ def solve(builder: ProblemBuilder,
     _native.check(
         lib.skyopt_optimize(handle, ctypes.byref(prob), ctypes.byref(csol),
                             ctypes.byref(sol.stats)))
+    global LAST_STATS  # pylint: disable=global-statement
+    LAST_STATS = sol.stats
     return sol
+
+
+# SkyoptStats of the most recent solve() in this process (tests / tracing).
+LAST_STATS = None
 
 
 class Session:

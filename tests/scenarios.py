@@ -972,7 +972,7 @@ BIG_SUITES = {
     'cfg5_50k': cfg5_scenarios,
 }
 
-ALL_SUITES = dict(SUITES, **LATE_SUITES, **BIG_SUITES)
+ALL_SUITES = dict(SUITES, **LATE_SUITES)
 
 
 # ---------------------------------------------------------------------------

@@ -19,9 +19,7 @@ pytestmark = pytest.mark.gpu
 def _cases():
     out = []
     for catalog in scenarios.SUITES:
-        path = os.path.join(runner.GOLDEN_DIR, f'{catalog}.json')
-        if not os.path.exists(path):
-            continue
+        # a missing fixture is a failure (load_golden raises), never a skip
         for sc in scenarios.SUITES[catalog]():
             out.append(pytest.param(catalog, sc, id=f'{catalog}:{sc["name"]}'))
     return out
@@ -62,13 +60,15 @@ def test_scenario_matches_reference(catalog, scenario):
     assert not diffs, '\n'.join(diffs)
 
 
-@pytest.mark.parametrize('mode',
-                         ['tile', 'stream', 'stream3', 'queue', 'queue32'])
+@pytest.mark.parametrize('mode', ['tile', 'stream', 'stream3', 'queue',
+                                  'queue32', 'fast', 'fast-noprune',
+                                  'fast-split', 'fast-split-noprune'])
 @pytest.mark.parametrize('catalog', ['multi50k', 'aws50k'])
 def test_scan_kernel_variants_agree_with_reference(catalog, mode):
     """All scan kernels (one tile per block / TMA streaming with one and
     with three tiles per block / the queue form with few and with 32 tiles
-    per block) must give the reference's answers."""
+    per block / the class-table scan with and without pruning) must give the
+    reference's answers."""
     spec, records = _golden(catalog)
     store = runner.activate_catalog(spec)
     store.set_scan_mode(mode)
@@ -84,3 +84,19 @@ def test_scan_kernel_variants_agree_with_reference(catalog, mode):
         assert not failures, failures
     finally:
         store.set_scan_mode('auto')
+
+
+def test_auto_mode_takes_the_class_table_scan():
+    """`auto` must run the fused step_kernel (SkyoptStats.scan_form 4: class-
+    table scan, placement and chain DP in one cooperative launch), not
+    silently fall back to the round-1 kernels."""
+    from skypilot_b200 import engine
+    spec, records = _golden('multi6k')
+    runner.activate_catalog(spec)
+    sc = next(s for s in scenarios.SUITES['multi6k']()
+              if s['name'] == 'chain3_mixed')
+    got = runner.run_scenario(sc, with_candidates=False)
+    assert not runner.compare(records[sc['name']], got)
+    assert engine.LAST_STATS is not None
+    assert int(engine.LAST_STATS.scan_form) == 4
+    assert int(engine.LAST_STATS.total_launches) == 1
