@@ -1,66 +1,57 @@
 """bench.py -- candidates scored / second of the placement-optimizer hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]
-                    [--workload cfg2|cfg4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU, N > 1)
 
 One *step* = one pass of the hot path over one DAG: every task's constraint
 vector is scored against every catalog row (filter + argmin), the winners are
 expanded to region/zone candidates and costed, and the chain DP picks the
-plan. Workloads (BASELINE.json `configs`):
+plan. Workloads (BASELINE.json `configs`, SURVEY.md section 8d;
+skypilot_b200/workloads.py):
 
-  cfg4  32-task chain DAG, synthetic 1M-row catalog -- the configuration the
-        throughput / HBM-roofline target is quoted on (BASELINE.md section 4,
-        item 4; BASELINE.json configs[3])                             [default]
-  cfg2  8-task chain DAG, synthetic multi-cloud catalog (~50k rows) -- the
-        optimize() p50 latency configuration (configs[1]); measured in the
-        same run and reported under "latency_cfg2"
+  cfg4   32-task chain DAG x synthetic 1M-row catalog -- the configuration the
+         throughput / HBM-roofline target is quoted on (configs[3]). The
+         headline of every line: each GPU optimises its own replica of the
+         DAG against its own replica of the catalog (weak scaling, no
+         collective -- the path only shards over independent DAGs).
+  cfg5   10 000 seeded single-task DAGs on the cfg2 catalog sharded over the
+         GPUs (configs[4]): DAG i -> rank i mod N, one device problem per
+         rank, plans gathered on rank 0 and compared with the reference's
+         records. Reported in every line under "scaling_cfg5" (strong scaling:
+         the total work is fixed as N grows).
+  cfg2   8-task chain x ~50k-row multi-cloud catalog, the optimize() latency
+         configuration (configs[1]) -- N = 1 only, under "latency_cfg2".
+  stress the cfg4 catalog with every row repeated 8 times (9.3M rows: larger
+         than the 126 MB L2) scanned WITHOUT pruning -- N = 1 only, under
+         "hbm_stress": what the scan kernel sustains when it must stream.
 
-`value`  = candidates / s with everything resident in HBM (CUDA events around
-           the kernels; L2 is flushed by writing 192 MB before every step);
-`e2e`    = the same metric through the public API, Optimizer.optimize(dag):
-           host Python, one H2D of the problem, one D2H of the plan per step;
-`roofline` is for the dominant kernel (scan_kernel): algorithmic bytes of one
-           launch / its event-timed duration vs MEASURED_PEAKS.json;
-`cpu_baseline` times the pandas oracle (oracle/, a port of the reference's
-           algorithm) on this box's host cores on a bounded sample.
-
-Multi-GPU (torchrun, one rank per GPU): independent DAGs per GPU, catalog
-replicated, no collective on the data path; weak scaling.
+Keys: `value` = candidates/s with the problem resident in HBM (CUDA events
+around the step, L2 flushed by a 192 MB write before every step); `e2e` = the
+same metric through the public API, `Optimizer.optimize(dag)`, with the
+host-side request memos dropped before every call (a fresh request), host
+buffers in and out; `roofline` = the scan kernel (scan2_kernel launched on its
+own, CUDA events) against MEASURED_PEAKS.json; `cpu_baseline` / `--impl
+reference` = the UNMODIFIED reference (baseline/_ref, else /root/reference)
+through oracle/ref_harness on this box's host cores, on a bounded sample.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
 _REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, _REPO)
 
-WORKLOADS = {
-    'cfg2': {
-        'catalog': {'seed': 1, 'n_rows': 50000,
-                    'clouds': ['aws', 'gcp', 'azure', 'lambda']},
-        'tasks': 8,
-        'desc': '8-task chain DAG, synthetic multi-cloud catalog (~50k rows)',
-    },
-    'cfg4': {
-        'catalog': {'seed': 3, 'n_rows': 1000000,
-                    'clouds': ['aws', 'gcp', 'azure', 'lambda']},
-        'tasks': 32,
-        'desc': '32-task chain DAG, synthetic 1M-row catalog',
-    },
-}
+METRIC = 'candidate (task,instance) placements scored/sec'
 
 
-def chain_scenario(n_tasks: int):
-    """The cfg2 constraint set, cycled with varying thresholds (cfg4)."""
-    from skypilot_b200 import workloads  # pylint: disable=import-outside-toplevel
-    return workloads.chain_scenario(n_tasks)
-
-
+# --------------------------------------------------------------------------
 def measured_peaks():
     path = os.path.join(_REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -70,53 +61,50 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def measured_traffic(workload_name: str, scan_form: int = 0):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch, from
-    the committed ncu captures (profiles/round1_traffic.json); None if no
-    capture covers this workload with the scan kernel that ran."""
-    path = os.path.join(_REPO, 'profiles', 'round1_traffic.json')
+def committed_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from
+    the committed ncu capture (profiles/round2_traffic.json), or None."""
     try:
-        with open(path, encoding='utf-8') as f:
-            table = json.load(f)
-        entry = table[workload_name]
-        form = {'scan_queue_kernel': 2, 'scan_kernel': 0}.get(
-            entry.get('kernel', 'scan_kernel'))
-        if form != scan_form:
-            entry = table[f'{workload_name}_one_tile_per_block']
-            if scan_form != 0:
-                return None
-        return entry['traffic']
-    except (OSError, KeyError, ValueError):
+        with open(os.path.join(_REPO, 'profiles', 'round2_traffic.json'),
+                  encoding='utf-8') as f:
+            return json.load(f)[key]['traffic']
+    except (OSError, KeyError, ValueError, TypeError):
         return None
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons while the GPU is being timed. One
+    low-rate thread (it forks a process per sample: it must not sit in the
+    latency-timed loops of eight ranks)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.1):
         self.index = index
+        self.period = period
         self.samples = []
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def sample(self):
         query = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
                  'clocks_event_reasons.hw_thermal_slowdown,'
                  'clocks_event_reasons.sw_thermal_slowdown,'
                  'clocks_event_reasons.sw_power_cap')
+        try:
+            out = subprocess.run([
+                'nvidia-smi', f'--query-gpu={query}',
+                '--format=csv,noheader,nounits', '-i',
+                str(self.index)
+            ], capture_output=True, text=True, timeout=5,
+                                 check=False).stdout.strip()
+            if out:
+                self.samples.append([v.strip() for v in out.split(',')])
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                out = subprocess.run([
-                    'nvidia-smi', f'--query-gpu={query}',
-                    '--format=csv,noheader,nounits', '-i',
-                    str(self.index)
-                ], capture_output=True, text=True, timeout=5,
-                                     check=False).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(',')])
-            except Exception:  # pylint: disable=broad-except
-                pass
-            self._stop.wait(0.01)
+            self.sample()
+            self._stop.wait(self.period)
 
     def __enter__(self):
         self._thread.start()
@@ -147,90 +135,167 @@ class ClockSampler:
         }
 
 
-def bench_reference(args, workload, scenario, n_candidates):
-    """`--impl reference`: the CPU arm. /root/reference is Python and does not
-    travel to the GPU box, so this times oracle/ -- the pandas port of the
-    reference's algorithm (kind "port"), single-threaded like the reference's
-    catalog path -- on a bounded sample of the same workload."""
-    from oracle import optimizer_oracle as oo  # pylint: disable=import-outside-toplevel
-    spec = workload['catalog']
-    sample = scenario
-    sample_tasks = len(scenario['tasks'])
-    if args.workload == 'cfg4':
-        # one task of the 32 per step keeps the run within minutes
-        sample = chain_scenario(32)
-        sample['tasks'] = sample['tasks'][:2]
-        sample['edges'] = [[0, 1]]
-        sample_tasks = 2
-    oo.catalog_for(spec)
-    for _ in range(max(1, min(args.warmup, 2))):
-        oo.run_scenario(spec, sample)
-    times = []
-    for _ in range(args.steps):
+# --------------------------------------------------------------------------
+# The CPU arm: the unmodified reference through oracle/ref_harness.
+
+
+def reference_root():
+    for path in (os.path.join(_REPO, 'baseline', '_ref'), '/root/reference'):
+        if os.path.isdir(os.path.join(path, 'sky')):
+            return path
+    return None
+
+
+class ReferenceArm:
+    """`sky.Optimizer.optimize` of the reference on one catalog spec (one per
+    process: the reference binds its catalog directory at import)."""
+
+    def __init__(self, spec):
+        from oracle.ref_harness import bootstrap  # pylint: disable=import-outside-toplevel
+        from oracle.ref_harness import run_reference  # pylint: disable=import-outside-toplevel
+        from skypilot_b200 import synth  # pylint: disable=import-outside-toplevel
+        root = reference_root()
+        if root is None:
+            raise RuntimeError('no reference tree (baseline/_ref, '
+                               '/root/reference)')
+        bootstrap.REFERENCE_ROOT = root
+        self.root = root
+        self._bootstrap = bootstrap
+        self._run = run_reference
+        spec = dict(spec)
+        enabled = spec.pop('enabled', None) or spec.get('clouds')
+        self._home = tempfile.TemporaryDirectory(prefix='skyref_home_')
+        frames = synth.make_catalogs(**spec)
+        self.n_rows = synth.total_rows(frames)
+        bootstrap.write_catalogs(self._home.name, frames)
+        self.sky = bootstrap.import_reference(self._home.name, enabled)
+
+    def optimize_seconds(self, scenario):
+        """One cold `Optimizer.optimize(dag, quiet=True)` (request cache
+        cleared, as tests/conftest.py:51-52 of the reference does)."""
+        from sky import optimizer as opt_lib  # pylint: disable=import-outside-toplevel
+        dag, tasks = self._run.build_dag(self.sky, scenario)
+        self._bootstrap.clear_request_cache()
         t0 = time.perf_counter()
-        rec = oo.run_scenario(spec, sample)
-        times.append(time.perf_counter() - t0)
-        assert 'error' not in rec, rec
+        opt_lib.Optimizer.optimize(dag, quiet=True)
+        dt = time.perf_counter() - t0
+        return dt, [self._run._res_record(t.best_resources) for t in tasks]  # pylint: disable=protected-access
+
+
+def port_seconds(spec, scenario):
+    """Fallback when no reference tree travelled: the pandas port."""
+    from oracle import optimizer_oracle as oo  # pylint: disable=import-outside-toplevel
+    oo.catalog_for(spec)
+    t0 = time.perf_counter()
+    rec = oo.run_scenario(spec, scenario)
+    return time.perf_counter() - t0, rec.get('plan')
+
+
+def sub_chain(scenario, n_tasks):
+    sample = dict(scenario)
+    sample['tasks'] = scenario['tasks'][:n_tasks]
+    sample['edges'] = [[i, i + 1] for i in range(n_tasks - 1)]
+    return sample
+
+
+def run_reference_arm(args, spec, scenario, workload_name, budget_s):
+    """Times the reference on a bounded sample: W warm-up and K timed steps,
+    each the first `m` tasks of the workload's chain, `m` sized so that the
+    whole run fits `budget_s`."""
+    n_tasks = len(scenario['tasks'])
+    kind = 'reference'
+    try:
+        arm = ReferenceArm(spec)
+        run = arm.optimize_seconds
+        n_rows = arm.n_rows
+    except Exception as e:  # pylint: disable=broad-except
+        kind = f'port (reference unavailable: {type(e).__name__}: {e})'[:200]
+        from skypilot_b200 import synth  # pylint: disable=import-outside-toplevel
+        n_rows = synth.total_rows(synth.make_catalogs(**spec))
+        run = lambda sc: port_seconds(spec, sc)  # noqa: E731
+    # one task (its time is not reported) sizes the sample
+    t1, _ = run(sub_chain(scenario, 1))
+    steps_total = max(1, args.steps + args.warmup)
+    m = int(max(1, min(n_tasks, (budget_s / steps_total) // max(t1, 1e-3))))
+    sample = sub_chain(scenario, m)
+    for _ in range(args.warmup):
+        run(sample)
+    times, plan = [], None
+    for _ in range(args.steps):
+        dt, plan = run(sample)
+        times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    cands = n_candidates * sample_tasks / len(scenario['tasks'])
-    value = cands / (ms / 1e3)
+    value = n_rows * m / (ms / 1e3)
     return {
-        'metric': 'candidate (task,instance) placements scored/sec',
-        'value': value, 'unit': 'candidates/s', 'impl': 'reference',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms, 'p50_ms': 1e3 * statistics.median(times),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {workload["desc"]}',
-                   'catalog': spec},
+        'value': value, 'ms_per_step': ms,
+        'p50_ms': 1e3 * statistics.median(times),
         'cpu_baseline': {
-            'value': value, 'unit': 'candidates/s',
-            'cores': 1, 'kind': 'port',
-            'threads': ('single-threaded pandas, like the reference except for '
-                        'its ThreadPool fan-out across clouds, which is slower '
-                        'under the GIL (measured 1.73 s vs 1.54 s per cfg2 step; '
-                        'SKYOPT_ORACLE_THREADS=1 enables it)'),
-            'sample': (f'{sample_tasks} of {len(scenario["tasks"])} tasks per '
-                       f'step, {args.steps} steps, full catalog')
+            'value': value, 'unit': 'candidates/s', 'cores': os.cpu_count(),
+            'kind': kind,
+            'threads': ('the reference\'s own: single-threaded pandas plus a '
+                        'ThreadPool of max(4, cores-1) across clouds '
+                        '(sky/optimizer.py:1712-1715)'),
+            'sample': (f'{m} of {n_tasks} tasks of the {workload_name} chain '
+                       f'per step, {args.steps} steps, full catalog '
+                       f'({n_rows} rows), request cache cleared every call'),
+            'ms_per_step': ms,
         },
-        'e2e': {'value': value, 'unit': 'candidates/s',
-                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
+        'plan': plan, 'sample_tasks': m,
     }
 
 
+# --------------------------------------------------------------------------
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=30)
+    parser.add_argument('--steps', type=int, default=20)
     parser.add_argument('--warmup', type=int, default=5)
-    parser.add_argument('--workload', default='cfg4', choices=list(WORKLOADS))
+    parser.add_argument('--workload', default='cfg4', choices=['cfg2', 'cfg4'])
     parser.add_argument('--impl', default='ours',
                         choices=['ours', 'reference'])
-    parser.add_argument('--cpu-baseline-steps', type=int, default=5)
-    parser.add_argument('--no-latency', action='store_true',
-                        help='skip the extra cfg2 (optimize() p50) run')
+    parser.add_argument('--cpu-baseline-budget', type=float, default=25.0,
+                        help='seconds of reference work in the cpu_baseline leg')
+    parser.add_argument('--reference-budget', type=float, default=200.0,
+                        help='seconds the --impl reference run may take')
+    parser.add_argument('--no-extras', action='store_true',
+                        help='skip cfg2 latency, the HBM stress row, cfg5 and '
+                        'the CPU baseline (tuning runs)')
+    parser.add_argument('--cfg5-dags', type=int, default=10000)
     parser.add_argument('--scan-mode', default='auto',
-                        choices=['auto', 'tile', 'stream', 'stream3', 'queue', 'fast',
-                                 'fast-noprune'],
-                        help='scan kernel variant (tuning / tests)')
+                        help='kernel selection for the headline loop (tests / '
+                        'tuning; see CatalogStore.set_scan_mode)')
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    workload = WORKLOADS[args.workload]
-    scenario = chain_scenario(workload['tasks'])
 
-    from skypilot_b200 import synth  # pylint: disable=import-outside-toplevel
+    from skypilot_b200 import workloads  # pylint: disable=import-outside-toplevel
+    spec = workloads.CATALOGS[args.workload]
+    n_tasks = 32 if args.workload == 'cfg4' else 8
+    scenario = workloads.chain_scenario(n_tasks)
+    desc = (f'{args.workload}: {n_tasks}-task chain DAG, synthetic '
+            f'{"1M" if args.workload == "cfg4" else "~50k"}-row catalog')
+
     if args.impl == 'reference':
         if rank != 0:
             return
-        frames = synth.make_catalogs(**workload['catalog'])
-        n_rows = synth.total_rows(frames)
-        line = bench_reference(args, workload, scenario,
-                               n_rows * workload['tasks'])
+        ref = run_reference_arm(args, spec, scenario, args.workload,
+                                args.reference_budget)
+        line = {
+            'metric': METRIC, 'value': ref['value'], 'unit': 'candidates/s',
+            'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ref['ms_per_step'],
+            'p50_ms': ref['p50_ms'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': desc, 'catalog': spec, 'tasks': n_tasks},
+            'cpu_baseline': ref['cpu_baseline'],
+            'e2e': {'value': ref['value'], 'unit': 'candidates/s',
+                    'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+        }
         print(json.dumps(line), flush=True)
         return
 
@@ -241,185 +306,361 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device(
             'cuda', local_rank))
+        # keep each rank's host threads on its own share of the cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            share = max(1, len(cores) // world)
+            os.sched_setaffinity(
+                0, cores[local_rank * share:(local_rank + 1) * share] or cores)
+        except (AttributeError, OSError):
+            pass
 
     import numpy as np  # pylint: disable=import-outside-toplevel
-    import skypilot_b200 as sky  # pylint: disable=import-outside-toplevel
-    from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
-    from skypilot_b200 import optimizer as opt_lib  # pylint: disable=import-outside-toplevel
-    from skypilot_b200 import workloads as runner  # pylint: disable=import-outside-toplevel
     import networkx as nx  # pylint: disable=import-outside-toplevel
+    import skypilot_b200 as sky  # pylint: disable=import-outside-toplevel
+    from skypilot_b200 import engine, sharding, synth  # pylint: disable=import-outside-toplevel
+    from skypilot_b200 import optimizer as opt_lib  # pylint: disable=import-outside-toplevel
+    from skypilot_b200.catalog.store import CatalogStore  # pylint: disable=import-outside-toplevel
+    Optimizer = opt_lib.Optimizer
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
     def max_over_ranks(x: float) -> float:
-        from skypilot_b200 import sharding  # pylint: disable=import-outside-toplevel
         return sharding.max_over_ranks(x, dist, device='cuda')
 
-    def measure(workload_name):
-        workload = WORKLOADS[workload_name]
-        scenario = chain_scenario(workload['tasks'])
-        frames = synth.make_catalogs(**workload['catalog'])
-        n_rows = synth.total_rows(frames)
-        store = sky.catalog.load_frames(frames, device=local_rank)
+    def load_store(catalog_spec):
+        """Rank 0 ingests the synthetic catalog and leaves it in the columnar
+        cache; the other ranks map the cache (CatalogStore.save / load)."""
+        key = hashlib.sha256(json.dumps(
+            catalog_spec, sort_keys=True).encode()).hexdigest()[:16]
+        cache = os.path.join(tempfile.gettempdir(), f'skyopt_bench_{key}')
+        store = None
+        if rank == 0:
+            frames = synth.make_catalogs(**catalog_spec)
+            store = CatalogStore.from_frames(frames)
+            if world > 1:
+                store.save(cache)
+        barrier()
+        if store is None:
+            store = CatalogStore.load(cache)
+        sky.catalog.set_store(store, local_rank)
+        sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
         store.handle(local_rank)
-        if args.scan_mode != 'auto':
-            store.set_scan_mode(args.scan_mode, local_rank)
-        n_tasks = workload['tasks']
-        n_candidates = n_rows * n_tasks
+        return store
 
-        dag, tasks = runner.build_dag(scenario)
-        Optimizer = opt_lib.Optimizer
+    def drop_memos(tasks):
+        """A fresh request: nothing stated before is replayed (SURVEY.md
+        section 8d item 2, "request cache cleared each call")."""
+        sky.catalog.clear_request_level_cache()
+        for t in tasks:
+            t.__dict__.pop('_stated', None)
+            for r in t.resources:
+                for k in ('_request_key', '_validated_store',
+                          '_plan_templates'):
+                    r.__dict__.pop(k, None)
 
-        # ---- device-resident arm: the problem is uploaded once, kernels re-run
+    def state(dag):
         Optimizer._add_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
         try:
             graph = dag.get_graph()
             topo = [t for t in nx.topological_sort(graph)
                     if not opt_lib._is_dummy(t)]  # pylint: disable=protected-access
-            problem = Optimizer._state_problem(graph, topo, True, [], True)  # pylint: disable=protected-access
+            return Optimizer._state_problem(graph, topo, True, [], True)  # pylint: disable=protected-access
         finally:
             Optimizer._remove_dummy_source_sink_nodes(dag)  # pylint: disable=protected-access
-        engine.solve_timed(problem.builder, args.warmup, True, local_rank)
+
+    def measure_chain(store, chain, n_rows):
+        """Device-resident loop, roofline loop, end-to-end loops of one chain
+        DAG on the active catalog."""
+        n_candidates = n_rows * len(chain['tasks'])
+        dag, tasks = workloads.build_dag(chain)
+        builder = state(dag).builder
+        if args.scan_mode != 'auto':
+            store.set_scan_mode(args.scan_mode, local_rank)
+        engine.solve_timed(builder, args.warmup, True, local_rank)
         barrier()
-        with ClockSampler(local_rank) as clocks:
-            t0 = time.perf_counter()
-            sol, iter_ms, scan_ms = engine.solve_timed(problem.builder, args.steps,
-                                                       True, local_rank)
-            wall_resident = time.perf_counter() - t0
-            device_ms = float(np.sum(iter_ms))
-            device_ms = max_over_ranks(device_ms)
-            barrier()
-
-            # ---- end to end through the public API, host buffers in and out
-            for _ in range(args.warmup):
-                Optimizer.optimize(dag, quiet=True)
-            barrier()
-            e2e_times = []
-            t_e2e0 = time.perf_counter()
-            for _ in range(args.steps):
-                t1 = time.perf_counter()
-                Optimizer.optimize(dag, quiet=True)
-                e2e_times.append(time.perf_counter() - t1)
-            e2e_total = time.perf_counter() - t_e2e0
-            e2e_total = max_over_ranks(e2e_total)
-            barrier()
-            # the latency percentiles are taken over at least 100 calls
-            # (SURVEY.md section 8d item 2); the e2e rate above is over
-            # exactly `steps`
-            while len(e2e_times) < 100:
-                t1 = time.perf_counter()
-                Optimizer.optimize(dag, quiet=True)
-                e2e_times.append(time.perf_counter() - t1)
-            # Same call with the host-side request memos dropped before every
-            # call ("request cache cleared each call").
-            cold_times = []
-            for _ in range(args.steps):
-                sky.catalog.clear_request_level_cache()
-                for t in tasks:
-                    for r in t.resources:
-                        r.__dict__.pop('_request_key', None)
-                        r.__dict__.pop('_validated_store', None)
-                        r.__dict__.pop('_plan_templates', None)
-                t1 = time.perf_counter()
-                Optimizer.optimize(dag, quiet=True)
-                cold_times.append(time.perf_counter() - t1)
-        assert sol.dag[0]['status'] == 0
-        plan = [runner.res_record(t.best_resources) for t in tasks]
-
-        ms_per_step = device_ms / args.steps
-        value = world * n_candidates / (ms_per_step / 1e3)
-        e2e_value = world * n_candidates * args.steps / e2e_total
-        packed = problem.builder.pack()
+        t0 = time.perf_counter()
+        sol, iter_ms, _ = engine.solve_timed(builder, args.steps, True,
+                                             local_rank)
+        wall = time.perf_counter() - t0
+        device_ms = max_over_ranks(float(np.sum(iter_ms)))
         stats = sol.stats
-        scan_kernel_ms = float(np.mean(scan_ms))
-        row_bytes = store.row_bytes()
-        scan_bytes = int(stats.scan_passes_rows) * row_bytes
-        peak, peak_src = measured_peaks()
-        achieved = scan_bytes / (scan_kernel_ms / 1e3) / 1e9 if scan_kernel_ms else 0
-
-        scan_form = min(3, max(0, int(getattr(stats, 'scan_form', 0))))
-
-        line = {
-            'metric': 'candidate (task,instance) placements scored/sec',
-            'value': value, 'unit': 'candidates/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
-            'config': {
-                'workload': f'{workload_name}: {workload["desc"]}',
-                'catalog': workload['catalog'], 'catalog_rows': n_rows,
-                'tasks': n_tasks, 'candidates_per_step': n_candidates,
-                'l2': 'flushed before every step (192 MB write)',
-                'parallelism': ('one DAG stream per GPU, catalog replicated, '
-                                'no collective'),
-            },
-            'optimize_calls': len(e2e_times),
-            'optimize_p50_ms': 1e3 * statistics.median(e2e_times),
-            'optimize_p90_ms': 1e3 * sorted(e2e_times)[int(0.9 *
-                                                           len(e2e_times))],
-            'optimize_cold_p50_ms': 1e3 * statistics.median(cold_times),
+        out = {
+            'ms_per_step': device_ms / args.steps,
+            'value': world * n_candidates / (device_ms / args.steps / 1e3),
+            'launches_per_step': int(stats.total_launches),
+            'scan_form': int(stats.scan_form),
+            'wall_check_ms_per_step': 1e3 * wall / args.steps,
+            'n_candidates': n_candidates,
+        }
+        assert sol.dag[0]['status'] == 0
+        # the scan kernel on its own (separate launches, events around it)
+        store.set_scan_mode('fast-split', local_rank)
+        engine.solve_timed(builder, args.warmup, True, local_rank)
+        s2, _, scan_ms = engine.solve_timed(builder, args.steps, True,
+                                            local_rank)
+        store.set_scan_mode('auto', local_rank)
+        st2 = s2.stats
+        out['split'] = {
+            'scan_kernel_ms': float(np.mean(scan_ms)),
+            'scan_kernel_ms_min': float(np.min(scan_ms)),
+            'phases_ms': {'scan': float(st2.scan_ms),
+                          'place': float(st2.expand_ms),
+                          'solve': float(st2.solve_ms)},
+            'scan_form': int(st2.scan_form),
+            'pass_rows': int(st2.scan_passes_rows),
+            'layout_rows': int(st2.reserved_),
+        }
+        barrier()
+        # ---- end to end through the public API, host buffers in and out,
+        # nothing replayed from an earlier call
+        for _ in range(args.warmup):
+            drop_memos(tasks)
+            Optimizer.optimize(dag, quiet=True)
+        barrier()
+        cold = []
+        t_e2e0 = time.perf_counter()
+        for _ in range(args.steps):
+            drop_memos(tasks)
+            t1 = time.perf_counter()
+            Optimizer.optimize(dag, quiet=True)
+            cold.append(time.perf_counter() - t1)
+        e2e_total = max_over_ranks(time.perf_counter() - t_e2e0)
+        barrier()
+        while len(cold) < 60:
+            drop_memos(tasks)
+            t1 = time.perf_counter()
+            Optimizer.optimize(dag, quiet=True)
+            cold.append(time.perf_counter() - t1)
+        warm = []
+        for _ in range(100):
+            t1 = time.perf_counter()
+            Optimizer.optimize(dag, quiet=True)
+            warm.append(time.perf_counter() - t1)
+        packed = builder.pack()
+        out.update({
             'e2e': {
-                'value': e2e_value, 'unit': 'candidates/s',
+                'value': world * n_candidates * args.steps / e2e_total,
+                'unit': 'candidates/s',
                 'h2d_bytes_per_step': packed.h2d_bytes(),
                 'd2h_bytes_per_step': sol.d2h_bytes(),
                 'ms_per_step': 1e3 * e2e_total / args.steps,
+                'what': ('Optimizer.optimize(dag), host-side request memos '
+                         'dropped before every call'),
             },
-            'gpu_launches': int(stats.total_launches) * args.steps,
-            'phases_ms': {
-                'scan_kernel': scan_kernel_ms,
-                'scan_total': float(stats.scan_ms),
-                'expand': float(stats.expand_ms),
-                'solve': float(stats.solve_ms),
-            },
-            'roofline': {
-                'kernel': ('scan_kernel', 'scan_stream_kernel',
-                           'scan_queue_kernel', 'scan2_kernel')[scan_form],
-                'bound': 'hbm', 'achieved': achieved,
-                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
-                'frac': achieved / peak if peak else None,
-                'algorithmic_bytes_per_launch': scan_bytes,
-                'bytes_per_row': row_bytes,
-                'rows_streamed_per_launch': int(stats.scan_passes_rows),
-                'queries_fused_per_pass': 32,
-                'traffic': measured_traffic(workload_name, scan_form),
-                'traffic_source': 'ncu, per launch: profiles/round1_traffic.json',
-            },
-            'clocks': clocks.summary(),
-            'wall_check_ms_per_step': 1e3 * wall_resident / args.steps,
-            'plan': [p['instance_type'] for p in plan],
+            'optimize_cold_p50_ms': 1e3 * statistics.median(cold),
+            'optimize_cold_p90_ms': 1e3 * sorted(cold)[int(0.9 * len(cold))],
+            'optimize_warm_p50_ms': 1e3 * statistics.median(warm),
+            'optimize_calls': len(cold) + len(warm),
+            'plan': [workloads.res_record(t.best_resources) for t in tasks],
+        })
+        return out
+
+    def roofline_of(split, traffic_key=None):
+        peak, peak_src = measured_peaks()
+        ms = split['scan_kernel_ms']
+        rows = split['pass_rows']
+        alg40 = rows * 40          # SURVEY.md section 8d: 40 B per (row, pass)
+        layout = split['layout_rows'] * 10
+        traffic = committed_traffic(traffic_key) if traffic_key else None
+        gbs = lambda b: b / (ms / 1e3) / 1e9 if ms else 0.0  # noqa: E731
+        return {
+            'kernel': 'scan2_kernel', 'bound': 'hbm', 'unit': 'GB/s',
+            'achieved': gbs(alg40), 'peak': peak, 'peak_source': peak_src,
+            'frac': gbs(alg40) / peak,
+            'algorithmic_bytes_per_launch': alg40,
+            'bytes_per_row': 40,
+            'bytes_per_row_note': (
+                'SURVEY.md section 8d figure (the reference columns a row '
+                'contributes to the predicate); rows x minimum passes '
+                '(ceil(queries / 32) per cloud)'),
+            'rows_streamed_per_launch': rows,
+            'layout_bytes_per_launch': layout,
+            'layout_note': ('what the kernel has to move: 10 B per row '
+                            '(u32 rank + 3 u16 class codes) x one pass per '
+                            'query group of <= 32 queries and price column'),
+            'layout_frac': gbs(layout) / peak,
+            'kernel_ms': ms,
+            'traffic': traffic,
+            'dram_frac': (gbs(traffic) / peak) if traffic else None,
+            'traffic_source': ('ncu dram__bytes_read.sum + '
+                               'dram__bytes_write.sum per launch, '
+                               'profiles/round2_traffic.json'),
         }
 
-        return line, scenario, n_candidates
+    # ------------------------------------------------------------ headline
+    store = load_store(spec)
+    n_rows = store.n_real_rows
+    with ClockSampler(local_rank) as clocks:
+        clocks.sample()
+        head = measure_chain(store, scenario, n_rows)
+        clocks.sample()
+    split = head.pop('split')
+    line = {
+        'metric': METRIC, 'value': head['value'], 'unit': 'candidates/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': head['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {
+            'workload': desc, 'catalog': spec, 'catalog_rows': n_rows,
+            'catalog_rows_note': ('the generator is asked for n_rows and '
+                                  'keeps whole instance types'),
+            'tasks': n_tasks, 'candidates_per_step': head['n_candidates'],
+            'l2': 'flushed before every step (192 MB write)',
+            'parallelism': ('one replica of the DAG and of the catalog per '
+                            'GPU, no collective; the DAG-sharded batch is '
+                            'under scaling_cfg5'),
+            'kernels': {3: 'scan2 + place + solve (separate launches)',
+                        4: 'step_kernel (one cooperative launch)'}.get(
+                            head['scan_form'], 'round-1 kernels'),
+        },
+        'e2e': head['e2e'],
+        'gpu_launches': head['launches_per_step'] * args.steps,
+        'launches_per_step': head['launches_per_step'],
+        'optimize_cold_p50_ms': head['optimize_cold_p50_ms'],
+        'optimize_cold_p90_ms': head['optimize_cold_p90_ms'],
+        'optimize_warm_p50_ms': head['optimize_warm_p50_ms'],
+        'optimize_calls': head['optimize_calls'],
+        'roofline': roofline_of(split, traffic_key=f'{args.workload}_scan2'),
+        'phases_ms_separate_launches': split['phases_ms'],
+        'clocks': clocks.summary(),
+        'wall_check_ms_per_step': head['wall_check_ms_per_step'],
+    }
+    line['roofline']['step_frac'] = (
+        line['roofline']['algorithmic_bytes_per_launch'] /
+        (head['ms_per_step'] / 1e3) / 1e9 / line['roofline']['peak'])
+    plan = head['plan']
+    line['plan'] = [p['instance_type'] for p in plan]
 
-    line, scenario, n_candidates = measure(args.workload)
-    workload = WORKLOADS[args.workload]
-    if args.workload != 'cfg2' and not args.no_latency:
-        # the latency configuration (BASELINE.json configs[1]) next to the
-        # throughput / roofline configuration
-        lat, _, _ = measure('cfg2')
-        line['latency_cfg2'] = {
-            k: lat[k] for k in ('value', 'unit', 'ms_per_step', 'e2e',
-                                'roofline', 'phases_ms', 'config',
-                                'optimize_p50_ms', 'optimize_p90_ms',
-                                'optimize_cold_p50_ms')
-        }
-    if rank == 0 and world == 1:
-        # ---- CPU baseline: the pandas oracle on a bounded sample
-        ref_args = argparse.Namespace(**vars(args))
-        ref_args.steps = args.cpu_baseline_steps
-        ref_args.warmup = 1
-        ref = bench_reference(ref_args, workload, scenario, n_candidates)
+    # parity of the timed workload against the reference's record
+    golden_path = os.path.join(_REPO, 'tests', 'golden', 'cfg4_1m.json')
+    if args.workload == 'cfg4' and os.path.exists(golden_path):
+        with open(golden_path, encoding='utf-8') as f:
+            rec = next(r for r in json.load(f)['records']
+                       if r['name'] == scenario['name'])
+        keys = ('cloud', 'instance_type', 'region', 'zone')
+        line['plan_matches_reference'] = (
+            [[p[k] for k in keys] for p in plan] ==
+            [[p[k] for k in keys] for p in rec['plan']])
+        line['reference_record'] = 'tests/golden/cfg4_1m.json:chain32'
+
+    extras = not args.no_extras
+    store5 = None
+    # ---------------------------------------------------------- cfg5 (all N)
+    if extras:
+        store5 = store if args.workload == 'cfg2' else load_store(
+            workloads.CATALOGS['cfg2'])
+        rows5 = store5.n_real_rows
+        scs = workloads.cfg5_scenarios(args.cfg5_dags)
+        dags = [workloads.build_dag(sc)[0] for sc in scs]
+        sharding.optimize_shard(dags[:200 * world], rank, world, local_rank,
+                                return_exceptions=True)
+        best, out = None, None
+        for _ in range(3):
+            for d in dags:
+                drop_memos(d.tasks)
+            barrier()
+            t0 = time.perf_counter()
+            out = sharding.optimize_shard(dags, rank, world, local_rank,
+                                          return_exceptions=True)
+            dt = max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        mine = sharding.shard(dags, rank, world)
+        records = []
+        for d, res in zip(mine, out):
+            if isinstance(res, Exception):
+                records.append(None)
+            else:
+                r = d.tasks[0].best_resources
+                records.append([str(r.cloud).lower(), r.instance_type,
+                                r.region, r.zone])
+        gathered = sharding.gather_on_root(records, len(dags), dist)
+        if rank == 0:
+            info = {
+                'workload': (f'cfg5: {len(dags)} single-task DAGs, cfg2 '
+                             f'catalog ({rows5} rows), DAG i -> rank i mod N'),
+                'scaling': 'strong', 'n_gpus': world, 'seconds': best,
+                'dags_per_s': len(dags) / best,
+                'value': len(dags) * rows5 / best, 'unit': 'candidates/s',
+                'what': ('Optimizer.optimize_batch per rank (fresh requests: '
+                         'memos dropped), best of 3, max over ranks; end to '
+                         'end, host buffers'),
+                'feasible': sum(r is not None for r in gathered),
+            }
+            g5 = os.path.join(_REPO, 'tests', 'golden', 'cfg5_50k.json')
+            if os.path.exists(g5) and len(dags) <= 10000:
+                with open(g5, encoding='utf-8') as f:
+                    recs = json.load(f)['records'][:len(dags)]
+                bad = sum(
+                    (got is None) != ('error' in rec) or
+                    (got is not None and got != rec['plan'])
+                    for got, rec in zip(gathered, recs))
+                info['plans_matching_reference'] = len(dags) - bad
+                info['reference_record'] = 'tests/golden/cfg5_50k.json'
+            line['scaling_cfg5'] = info
+
+    # ------------------------------------------------------- N = 1 extras
+    if extras and world == 1:
+        if args.workload == 'cfg4':
+            # cfg2: the optimize() latency configuration (store5 is active)
+            sc2 = workloads.chain_scenario(8)
+            lat = measure_chain(store5, sc2, store5.n_real_rows)
+            sp2 = lat.pop('split')
+            line['latency_cfg2'] = {
+                'workload': 'cfg2: 8-task chain DAG, ~50k-row catalog',
+                'ms_per_step': lat['ms_per_step'], 'value': lat['value'],
+                'unit': 'candidates/s', 'e2e': lat['e2e'],
+                'optimize_cold_p50_ms': lat['optimize_cold_p50_ms'],
+                'optimize_cold_p90_ms': lat['optimize_cold_p90_ms'],
+                'optimize_warm_p50_ms': lat['optimize_warm_p50_ms'],
+                'roofline': roofline_of(sp2, traffic_key='cfg2_scan2'),
+                'phases_ms_separate_launches': sp2['phases_ms'],
+            }
+            sky.catalog.set_store(store, local_rank)
+        # HBM stress: 8 copies of every row, nothing pruned
+        big = store.replicated(8)
+        sky.catalog.set_store(big, local_rank)
+        big.handle(local_rank)
+        dag, tasks = workloads.build_dag(scenario)
+        builder = state(dag).builder
+        big.set_scan_mode('fast-split-noprune', local_rank)
+        engine.solve_timed(builder, args.warmup, True, local_rank)
+        s3, _, scan_ms = engine.solve_timed(builder, args.steps, True,
+                                            local_rank)
+        st3 = s3.stats
+        sp3 = {'scan_kernel_ms': float(np.mean(scan_ms)),
+               'pass_rows': int(st3.scan_passes_rows),
+               'layout_rows': int(st3.reserved_)}
+        stress = roofline_of(sp3, traffic_key='stress_scan2')
+        drop_memos(tasks)
+        Optimizer.optimize(dag, quiet=True)
+        stress.update({
+            'workload': (f'{desc.split(":")[0]} chain on the catalog with '
+                         f'every row repeated 8 times ({big.n_real_rows} '
+                         'rows), scan2_kernel without zone map or bound: '
+                         'every row of every pass is streamed and scored'),
+            'catalog_rows': big.n_real_rows,
+            'candidates_per_s': big.n_real_rows * n_tasks /
+                                (sp3['scan_kernel_ms'] / 1e3),
+            'plan_equals_base_catalog': [
+                workloads.res_record(t.best_resources)['instance_type']
+                for t in tasks] == line['plan'],
+        })
+        line['hbm_stress'] = stress
+        big.close()
+        sky.catalog.set_store(store, local_rank)
+        # CPU baseline: the reference on a bounded sample of this workload
+        ref_args = argparse.Namespace(steps=1, warmup=0)
+        ref = run_reference_arm(ref_args, spec, scenario, args.workload,
+                                args.cpu_baseline_budget)
         line['cpu_baseline'] = ref['cpu_baseline']
-        line['cpu_baseline']['ms_per_step'] = ref['ms_per_step']
-        # the oracle's plan must be ours (cheap cross-check, cfg2 only)
-        if args.workload == 'cfg2':
-            from oracle import optimizer_oracle as oo  # pylint: disable=import-outside-toplevel
-            want = oo.run_scenario(workload['catalog'], scenario)
-            line['plan_matches_oracle'] = (
-                [p['instance_type'] for p in want['plan']] == line['plan'])
+        if ref['plan'] is not None:
+            m = ref['sample_tasks']
+            line['cpu_baseline']['sample_plan_equals_ours'] = (
+                [p['instance_type'] for p in ref['plan']] == line['plan'][:m])
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -247,7 +247,11 @@ typedef struct SkyoptCandidate {
 
 typedef struct SkyoptDagResult {
   int32_t status;     /* 0 ok; 1 = a task has no candidate (first such task
-                         in task_fail); 2 = search space too large */
+                         in task_fail); 2 = general DAG beyond the device
+                         enumeration (more than 16 tasks or 2^26 cloud
+                         assignments): the caller solves it from the candidate
+                         tables (skypilot_b200/dag_solver.py, exact bucket
+                         elimination for the COST objective) */
   int32_t task_fail;
   double objective;   /* best_total_objective */
 } SkyoptDagResult;

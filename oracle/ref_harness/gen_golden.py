@@ -30,9 +30,11 @@ def main():
     groups = '--job-groups' in argv
     argv = [a for a in argv if a not in ('--listings', '--job-groups')]
     suites = (scenarios.LISTING_SUITES if listings else
-              scenarios.JOB_GROUP_SUITES if groups else scenarios.ALL_SUITES)
+              scenarios.JOB_GROUP_SUITES if groups else
+              dict(scenarios.ALL_SUITES, **scenarios.EXTRA_GOLDEN_SUITES))
     prefix = 'accel_' if listings else 'jobgroup_' if groups else ''
-    wanted = argv or list(suites.keys())
+    wanted = argv or [k for k in suites
+                      if k not in scenarios.EXTRA_GOLDEN_SUITES or not argv]
     out_dir = os.path.join(_REPO, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
     for name in wanted:

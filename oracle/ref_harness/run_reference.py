@@ -302,8 +302,24 @@ def run_scenario(sky, scenario):
                     keys = [r for r in keys if best_of[str(r.cloud)] is r]
                 names.append(keys)
             record['exhaustive'] = 'full' if full else 'per-cloud'
+            n_combos = 1
+            for keys in names:
+                n_combos *= max(len(keys), 1)
             best, best_plan = None, None
-            for combo in itertools.product(*names):
+            if n_combos > 3_000_000 and minimize_cost:
+                # too many assignments to enumerate: the exact frontier DP of
+                # oracle/dag_oracle.py over the same tables and egress terms
+                from oracle import dag_oracle
+                record['exhaustive'] = 'frontier-dp'
+                children = {n: list(graph.successors(n)) for n in topo}
+                parents_of = {n: list(graph.predecessors(n)) for n in topo}
+                best, best_plan = dag_oracle.frontier_dp(
+                    topo, children, parents_of, dict(zip(topo, names)),
+                    lambda n, r: cost_map[n][r],
+                    lambda u, ru, v, rv: Optimizer._egress_cost_or_time(
+                        True, u, ru, v, rv))
+                names = None
+            for combo in (itertools.product(*names) if names is not None else []):
                 plan_try = dict(zip(topo, combo))
                 if minimize_cost:
                     total = 0.0

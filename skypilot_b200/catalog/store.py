@@ -24,6 +24,7 @@ import hashlib
 import json
 import os
 import threading
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -135,6 +136,7 @@ class CatalogStore:
         self._handles: Dict[int, ctypes.c_void_p] = {}
         self._lock = threading.Lock()
         self._keepalive: List[np.ndarray] = []
+        self._sessions = weakref.WeakSet()  # open engine.Session objects
 
     # ------------------------------------------------------------------ build
     @classmethod
@@ -459,8 +461,11 @@ class CatalogStore:
             if os.path.exists(os.path.join(cache_dir, 'meta.json')):
                 try:
                     return cls.load(cache_dir)
-                except (OSError, ValueError, KeyError):
-                    pass  # unreadable cache: parse the CSVs again
+                except Exception:  # pylint: disable=broad-except
+                    # unreadable / corrupt cache (zipfile.BadZipFile, a
+                    # truncated parquet, ...): parse the CSVs again
+                    import shutil  # pylint: disable=import-outside-toplevel
+                    shutil.rmtree(cache_dir, ignore_errors=True)
         frames = {name: pd.read_csv(csv) for name, csv in files}
         store = cls.from_frames(frames, order=list(frames.keys()))
         if cache_dir is not None:
@@ -477,11 +482,30 @@ class CatalogStore:
         `meta.json` (dictionaries: region / zone / instance-type names,
         accelerator keys) and `types_<cloud>.parquet` (one CSV row per
         instance type, for metadata look-ups)."""
-        os.makedirs(directory, exist_ok=True)
+        # Everything is written into a private scratch directory and committed
+        # with ONE rename: two processes ingesting the same catalog at once
+        # cannot interleave their files, and a reader never sees a half-written
+        # cache. Whoever renames first wins; the loser drops its copy.
+        import shutil  # pylint: disable=import-outside-toplevel
+        import uuid  # pylint: disable=import-outside-toplevel
+        final = directory.rstrip(os.sep)
+        os.makedirs(os.path.dirname(final) or '.', exist_ok=True)
+        directory = f'{final}.tmp.{os.getpid()}.{uuid.uuid4().hex[:8]}'
+        os.makedirs(directory)
+        try:
+            self._write_cache_files(directory)
+            try:
+                os.rename(directory, final)  # commit point
+            except OSError:
+                if not os.path.exists(os.path.join(final, 'meta.json')):
+                    raise
+        finally:
+            if os.path.isdir(directory):
+                shutil.rmtree(directory, ignore_errors=True)
+
+    def _write_cache_files(self, directory: str) -> None:
         arrays = {k: v for k, v in self.columns.items() if v is not None}
-        tmp = os.path.join(directory, 'columns.tmp.npz')
-        np.savez(tmp, **arrays)
-        os.replace(tmp, os.path.join(directory, 'columns.npz'))
+        np.savez(os.path.join(directory, 'columns.npz'), **arrays)
         meta = {
             'version': CACHE_VERSION, 'n_rows': self.n_rows,
             'n_real_rows': self.n_real_rows,
@@ -504,10 +528,9 @@ class CatalogStore:
                 'gpu_info_any_nan': t.gpu_info_any_nan,
                 'gpu_info_unique': t.gpu_info_unique,
             })
-        tmp = os.path.join(directory, 'meta.tmp.json')
-        with open(tmp, 'w', encoding='utf-8') as f:
+        with open(os.path.join(directory, 'meta.json'), 'w',
+                  encoding='utf-8') as f:
             json.dump(meta, f)
-        os.replace(tmp, os.path.join(directory, 'meta.json'))  # commit point
 
     @classmethod
     def load(cls, directory: str) -> 'CatalogStore':
@@ -679,7 +702,18 @@ class CatalogStore:
         _native.check(_native.load().skyopt_catalog_set_scan_mode(
             self.handle(device), code))
 
+    def register_session(self, session) -> None:
+        self._sessions.add(session)
+
+    def unregister_session(self, session) -> None:
+        self._sessions.discard(session)
+
     def close(self) -> None:
+        # sessions hold the raw catalog handle: close them first (a later
+        # resolve() on them raises 'session is closed' instead of touching
+        # freed device memory)
+        for session in list(self._sessions):
+            session.close()
         for handle in list(self._handles.values()):
             _native.load().skyopt_catalog_destroy(handle)
         self._handles.clear()

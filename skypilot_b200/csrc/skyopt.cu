@@ -193,7 +193,7 @@ struct Plan {
   size_t scan2_smem = 0; int64_t layout_rows = 0;
   Scan2Group *groups2; const Scan2Group *host_groups2 = nullptr; uint32_t *best_rank, *any_in;
   PlaceTask *ptasks; SlotAux *saux; uint32_t cap_fa = 0, cap_cm = 0, cap_rz = 0;
-  int32_t *dag_done; unsigned long long *task_mv; bool chain_dags = false; int step_grid = 0; size_t step_smem = 0; mutable bool ran_fused = false;
+  int32_t *dag_done; unsigned long long *task_mv; uint32_t *shared_tables; unsigned int *group_ready; bool chain_dags = false; int step_grid = 0; size_t step_smem = 0; mutable bool ran_fused = false;
   // input region (mirrored host/device)
   size_t in_bytes = 0;
   SkyoptQuery *queries; uint32_t *acc_sets; SkyoptSlot *slots; SkyoptTask *tasks;
@@ -236,6 +236,7 @@ void carve_inputs(Plan &P, Carver &c) {
   P.ptasks = c.take<PlaceTask>(P.fast ? P.nt : 0);
   P.saux = c.take<SlotAux>(P.fast ? P.ns : 0);
   P.dag_done = c.take<int32_t>(P.fast ? P.nd : 0);
+  P.group_ready = c.take<unsigned int>(P.n_groups2);
   P.best_rank = c.take<uint32_t>(P.fast ? P.nq : 0);
   P.any_in = c.take<uint32_t>(P.fast ? P.nq : 0);
 }
@@ -246,6 +247,7 @@ void carve_rest(Plan &P, Carver &c) {
   P.fuzzy_min = c.take<unsigned long long>(P.fuzzy_entries);
   P.gbest = c.take<unsigned long long>(P.nsq);
   P.task_mv = c.take<unsigned long long>(P.fast ? (size_t)P.nt * SKYOPT_MAX_CLOUDS : 0);
+  P.shared_tables = c.take<uint32_t>((size_t)P.n_groups2 * (2 * P.cap_fa + P.cap_cm + P.cap_rz));
   P.cand_region = c.take<int32_t>(P.cand_cap);
   P.cand_zone = c.take<int32_t>(P.cand_cap);
   P.cand_pa = c.take<double>(P.cand_cap);
@@ -476,7 +478,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     for (Scan2Group &G : groups2) {
       long long k = 1 + (visits > 0 ? spare * G.n_chunks / visits : 0);
       k = std::min<long long>(k, std::max<long long>(1, G.n_chunks / min_piece));
-      G.piece0 = piece0;
+      G.piece0 = piece0; G.index = (int)(&G - groups2.data());
       G.n_pieces = (int)std::max<long long>(1, std::min<long long>(k, G.n_chunks));
       piece0 += G.n_pieces;
       P.layout_rows += (long long)G.n_chunks * kZoneRows;
@@ -631,6 +633,7 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     memset(P.best_rank, 0xFF, sizeof(uint32_t) * P.nq);
     memset(P.any_in, 0, sizeof(uint32_t) * P.nq);
     if (P.nd) memset(P.dag_done, 0, sizeof(int32_t) * P.nd);
+    if (P.n_groups2) memset(P.group_ready, 0, sizeof(unsigned int) * P.n_groups2);
     // what a task block / a slot needs, in one record each
     for (int t = 0; t < P.nt; ++t) {
       const SkyoptDag &D = pb->dags[P.task_dag[t]];
@@ -650,6 +653,12 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
       }
       X.cloud_r0 = cat->cloud_row_offsets[S.cloud]; X.cloud_r1 = cat->cloud_row_offsets[S.cloud + 1];
       X.has_zones = cat->cloud_n_zones[S.cloud] > 0 ? 1 : 0;
+      X.acc_list_key = -1;
+      if (S.acc_set >= 0) {
+        const uint32_t *w = pb->acc_sets + (size_t)S.acc_set * SKYOPT_ACC_SET_WORDS;
+        for (int k = 0; k < SKYOPT_ACC_SET_WORDS && X.acc_list_key < 0; ++k)
+          if (w[k]) X.acc_list_key = (int16_t)(32 * k + __builtin_ctz(w[k]));
+      }
     }
   }
   int g = 0, qpos = 0, block0 = 0;
@@ -716,16 +725,11 @@ struct Timeline { float scan_ms = 0, expand_ms = 0, solve_ms = 0; };
 int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool want_scan_results) {
   cudaStream_t st = x->stream;
   CU(cudaEventRecord(x->ev[1], st));
-  if (P.nq && !P.fresh_inputs) {
-    // best_rank and any_in are adjacent in the input region
-    CU(cudaMemsetAsync(P.best_rank, 0xFF, sizeof(uint32_t) * P.nq, st));
-    CU(cudaMemsetAsync(P.any_in, 0, sizeof(uint32_t) * P.nq, st));
-  }
   Scan2Args sa{};
   sa.cat = cat->dev; sa.f = cat->fast; sa.squeries = P.squeries; sa.groups = P.groups2;
   sa.n_groups = P.n_groups2; sa.n_pieces = P.n_pieces; sa.best_rank = P.best_rank; sa.any1 = P.any_in;
   sa.zero_flag = P.err_out; sa.cap_fa = P.cap_fa; sa.cap_cm = P.cap_cm; sa.cap_rz = P.cap_rz;
-  sa.trace = x->trace;
+  sa.trace = x->trace; sa.shared_tables = nullptr; sa.group_ready = nullptr;
   for (int i = 0; i < std::min(P.n_groups2, kInlineGroups2); ++i) {
     sa.inline_groups[i] = P.host_groups2[i]; sa.inline_piece0[i] = P.host_groups2[i].piece0;
   }
@@ -740,6 +744,9 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     // ---- the whole step in one cooperative launch
     StepArgs sp{};
     sp.scan = sa;
+    static const int exp_flags = [] { const char *e = getenv("SKYOPT_EXP"); return e ? atoi(e) : 0; }();
+    if (!(exp_flags & 2)) { sp.scan.shared_tables = P.shared_tables; sp.scan.group_ready = P.group_ready; }
+    if (exp_flags & 4) sp.scan.noprune |= 4u;  // experiment: spin without nanosleep
     sp.place.cat = cat->dev; sp.place.f = cat->fast; sp.place.ptasks = P.ptasks; sp.place.saux = P.saux;
     sp.place.best_rank = P.best_rank; sp.place.any1 = P.any_in; sp.place.acc_sets = P.acc_sets;
     sp.place.in = in0; sp.place.w = w0; sp.place.task_n = P.task_n; sp.place.trace = x->trace;
@@ -747,14 +754,14 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     sp.out = SolveOut{P.chosen, P.chosen_index, P.task_n, P.dagres, x->trace};
     sp.task_dag = P.task_dag; sp.n_tasks = P.nt; sp.do_solve = P.chain_dags ? 1 : 0;
     sp.dag_done = P.dag_done; sp.sync = x->sync;
+    sp.n_queries = P.nq;
+    sp.in_base = x->dbuf; sp.in_lines = (int64_t)((P.in_bytes + 127) / 128);
     void *args[] = {&sp};
-    CU(cudaEventRecord(x->ev[6], st));
+    // step_kernel leaves best_rank / any_in reset for the next launch: no
+    // memset, no event between ev[1] and ev[4] (each costs microseconds here)
     cudaError_t le = cudaLaunchCooperativeKernel((const void *)step_kernel, dim3(P.step_grid), dim3(kScanThreads),
                                                  args, P.step_smem, st);
     if (le == cudaSuccess) {
-      CU(cudaEventRecord(x->ev[7], st));
-      CU(cudaEventRecord(x->ev[2], st));
-      CU(cudaEventRecord(x->ev[3], st));
       if (!P.chain_dags && P.nd) {
         SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres, x->trace};
         solve_kernel<<<P.nd, kSolveThreads, 0, st>>>(cat->dev, in0, w0, out);
@@ -767,7 +774,9 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     (void)cudaGetLastError();  // not launched (too large for this device): separate launches below
   }
   if (P.nq) {
-    {
+    if (!P.fresh_inputs) {
+      CU(cudaMemsetAsync(P.best_rank, 0xFF, sizeof(uint32_t) * P.nq, st));
+      CU(cudaMemsetAsync(P.any_in, 0, sizeof(uint32_t) * P.nq, st));
     }
     CU(cudaEventRecord(x->ev[6], st));
     if (P.n_pieces) {
@@ -982,10 +991,17 @@ int copy_solution(SkyoptCatalog *cat, Ctx *x, const Plan &P, const SkyoptProblem
 int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
   if (!stats) return 0;
   memset(stats, 0, sizeof(*stats));
+  if (P.ran_fused) {
+    // one launch: the step is not split into phases (SKYOPT_TRACE has the
+    // in-kernel timeline)
+    CU(cudaEventElapsedTime(&stats->scan_kernel_ms, x->ev[1], x->ev[4]));
+    stats->scan_ms = stats->scan_kernel_ms;
+  } else {
   CU(cudaEventElapsedTime(&stats->scan_ms, x->ev[1], x->ev[2]));
   if (solve) {
     CU(cudaEventElapsedTime(&stats->expand_ms, x->ev[2], x->ev[3]));
     CU(cudaEventElapsedTime(&stats->solve_ms, x->ev[3], x->ev[4]));
+  }
   }
   CU(cudaEventElapsedTime(&stats->total_ms, x->ev[0], x->ev[5]));
   stats->scan_launches = (P.fast ? P.n_pieces : P.n_blocks) ? 1 : 0;
@@ -998,7 +1014,7 @@ int fill_stats(Ctx *x, const Plan &P, SkyoptStats *stats, bool solve) {
   stats->scan_blocks = P.fast ? (P.ran_fused ? P.step_grid : P.scan2_grid) : P.n_blocks;
   stats->scan_form = P.fast ? (P.ran_fused ? 4 : 3) : (P.stream ? 1 : (P.queue ? 2 : 0));
   stats->reserved_ = P.fast ? (int32_t)std::min<int64_t>(P.layout_rows, 0x7FFFFFFF) : 0;
-  if (P.fast ? P.n_pieces : P.n_blocks) CU(cudaEventElapsedTime(&stats->scan_kernel_ms, x->ev[6], x->ev[7]));
+  if (!P.ran_fused && (P.fast ? P.n_pieces : P.n_blocks)) CU(cudaEventElapsedTime(&stats->scan_kernel_ms, x->ev[6], x->ev[7]));
   return 0;
 }
 
@@ -1633,13 +1649,19 @@ int skyopt_optimize_timed(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSol
       if ((r = enqueue_kernels(cat, x, P, true, sol->scan != nullptr))) return r;
       CU(cudaStreamSynchronize(st));
       CU(cudaEventElapsedTime(&iter_ms[it], x->ev[1], x->ev[4]));
-      if (scan_ms && (P.fast ? P.n_pieces : P.n_blocks)) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[6], x->ev[7]));
+      if (scan_ms && !P.ran_fused && (P.fast ? P.n_pieces : P.n_blocks)) CU(cudaEventElapsedTime(&scan_ms[it], x->ev[6], x->ev[7]));
+      if (scan_ms && P.ran_fused) scan_ms[it] = iter_ms[it];
     }
     if (x->trace) {
       // the last iteration's per-block timeline (tools/trace2.py reads it)
       std::vector<unsigned long long> h(trace_words);
       CU(cudaMemcpy(h.data(), x->trace, trace_words * 8, cudaMemcpyDeviceToHost));
-      if (FILE *f = fopen(trace_path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+      // one file per timing loop of the process: <path>, <path>.1, <path>.2, ...
+      static int trace_calls = 0;
+      std::string path = trace_path;
+      if (trace_calls) path += "." + std::to_string(trace_calls);
+      ++trace_calls;
+      if (FILE *f = fopen(path.c_str(), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
     }
     CU(cudaMemcpyAsync(x->hbuf, x->dbuf + P.out_off, P.out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(x->ev[5], st));

@@ -48,13 +48,17 @@ __device__ __forceinline__ void trace_put(unsigned long long *trace, int kernel,
     trace[((size_t)kernel * kTraceBlocks + blockIdx.x) * kTraceSlots + slot] = v;
 }
 
-// rank -> what the expansion needs of the cheapest row
+// rank -> what the expansion needs of the cheapest row: its price (the cap
+// test), its instance type and where that type's static list lives
 struct RankRec {
   double price;
   int32_t row;
   int32_t inst;
+  int32_t list_off;  // = inst_list[inst] (one dependent load less)
+  int32_t cnt[2];
+  int32_t acc_key;
 };
-static_assert(sizeof(RankRec) == 16, "RankRec layout");
+static_assert(sizeof(RankRec) == 32, "RankRec layout");
 
 // One entry of an instance type's (or accelerator key's) static launchable
 // order: rows with a price, sorted by (price, region, zone), regrouped by the
@@ -100,6 +104,7 @@ struct Scan2Group {
   int32_t cm_off, fa_off, rz_off; // into the class dictionaries
   int32_t chunk0, n_chunks;       // the cloud's 128-row chunks
   int32_t piece0, n_pieces;       // the group's share of the launch's pieces
+  int32_t index, pad_;            // position in the launch's group array
 };
 
 struct Scan2Args {
@@ -113,6 +118,10 @@ struct Scan2Args {
   int32_t *zero_flag;
   uint32_t noprune;               // 1: ignore the zone map and the bound
   uint32_t cap_fa, cap_cm, cap_rz;  // shared-memory capacities (entries)
+  // cooperative launch only: the blocks of a group build its tables together
+  // (one slice each) in `shared_tables` and wait on `group_ready`
+  uint32_t *shared_tables;        // [n_groups][2 * cap_fa + cap_cm + cap_rz] or null
+  unsigned int *group_ready;      // [n_groups] slices published (zero between launches)
   unsigned long long *trace;
   int32_t inline_piece0[kInlineGroups2];
   Scan2Group inline_groups[kInlineGroups2];
@@ -219,7 +228,7 @@ __device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *sm
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
     trace_put(a.trace, 0, 6, smid);
   }
-  const bool prune = a.noprune == 0;
+  const bool prune = (a.noprune & 1u) == 0;
   unsigned long long n_visit = 0, n_live = 0;
 
   int cur_group = -1;
@@ -258,12 +267,16 @@ __device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *sm
         const uint4 *src = reinterpret_cast<const uint4 *>(a.squeries + G.q_begin);
         uint4 *dst = reinterpret_cast<uint4 *>(S.sq);
         const int n16 = nq * (int)(sizeof(ScanQuery) / 16);
+#pragma unroll 1
         for (int i = tid; i < n16; i += kScanThreads) dst[i] = __ldg(src + i);
+#pragma unroll 1
         for (int i = tid; i < G.n_cm; i += kScanThreads) S.d_cm[i] = __ldg(a.f.cm_val + G.cm_off + i);
+#pragma unroll 1
         for (int i = tid; i < G.n_fa; i += kScanThreads) {
           S.d_fa[i] = __ldg(a.f.fa_key + G.fa_off + i);
           S.d_disk[i] = __ldg(a.f.fa_disk + G.fa_off + i);
         }
+#pragma unroll 1
         for (int i = tid; i < G.n_rz; i += kScanThreads) S.d_rz[i] = __ldg(a.f.rz_key + G.rz_off + i);
       }
       __syncthreads();
@@ -281,44 +294,84 @@ __device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *sm
       // registers, a warp takes one dictionary entry at a time and one ballot
       // gives the entry's 32-bit mask. Every query is evaluated on the entry
       // exactly like score_rows does on a row (same fp64 comparisons,
-      // common.py:431-480).
+      // common.py:431-480). Every block of the group needs the same tables:
+      // in the cooperative launch each builds one slice of the entries,
+      // publishes it and picks the rest up from L2 (building everything in
+      // every block kept all SMs issue-bound for 4 us,
+      // profiles/round2_timeline.md).
       {
+        // (one piece per block: nobody waits for a slice its owner has not reached)
+        const bool shared = a.shared_tables != nullptr && G.n_pieces > 1 && a.n_pieces <= (int)gridDim.x;
+        const int n_all = G.n_fa + G.n_cm + G.n_rz;
+        int e_lo = 0, e_hi = n_all;
+        if (shared) {
+          e_lo = (int)((int64_t)n_all * pi / G.n_pieces);
+          e_hi = (int)((int64_t)n_all * (pi + 1) / G.n_pieces);
+        }
+        uint32_t *gt = shared ? a.shared_tables + (size_t)G.index * (2 * a.cap_fa + a.cap_cm + a.cap_rz)
+                              : nullptr;
         QueryS Q{};
         const uint32_t *set0 = S.sq[0].set[0];
         const bool lq = lane < nq;
         if (lq) { Q = S.sq[lane].s; set0 = S.sq[lane].set[0]; }
         const bool is_acc = (Q.qflags & SKYOPT_Q_ACC) != 0;
         const bool ratio = Q.mem_op == SKYOPT_OP_RATIO;
-        for (int e = warp; e < G.n_fa; e += kFastWarps) {
-          const uint32_t key = S.d_fa[e];
-          const double disk = S.d_disk[e];
-          const uint32_t fl = key & 0xFFFFu, ak = key >> 16;
-          const uint32_t akey = (ak == SKYOPT_NONE16) ? (uint32_t)(32 * SKYOPT_ACC_SET_WORDS) : ak;
-          // flags / fixed-host group (the low 16 bits of the row key)
-          bool ok = lq && ((fl ^ Q.val_lo) & Q.mask_lo & 0xFFFFu) == 0u;
-          if (is_acc) ok = ok && ((set0[akey >> 5] >> (akey & 31u)) & 1u);
-          if (Q.disk_op != 0)
-            ok = ok && (Q.disk_op == SKYOPT_DISK_GE ? (disk >= Q.disk_size)
-                                                    : (fabs(disk - Q.disk_size) < 1.0));
-          const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, ok);
-          const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, ok && ((fl & Q.flags2) == Q.flags2));
-          if (lane == 0) S.Tfa[e] = make_uint2(m1, m2);
+#pragma unroll 1
+        for (int i = e_lo + warp; i < e_hi; i += kFastWarps) {
+          uint32_t m1, m2 = 0;
+          if (i < G.n_fa) {
+            const uint32_t key = S.d_fa[i];
+            const double disk = S.d_disk[i];
+            const uint32_t fl = key & 0xFFFFu, ak = key >> 16;
+            const uint32_t akey = (ak == SKYOPT_NONE16) ? (uint32_t)(32 * SKYOPT_ACC_SET_WORDS) : ak;
+            // flags / fixed-host group (the low 16 bits of the row key)
+            bool ok = lq && ((fl ^ Q.val_lo) & Q.mask_lo & 0xFFFFu) == 0u;
+            if (is_acc) ok = ok && ((set0[(akey >> 5) & 63u] >> (akey & 31u)) & 1u);
+            if (Q.disk_op != 0)
+              ok = ok && (Q.disk_op == SKYOPT_DISK_GE ? (disk >= Q.disk_size)
+                                                      : (fabs(disk - Q.disk_size) < 1.0));
+            m1 = __ballot_sync(0xFFFFFFFFu, ok);
+            m2 = __ballot_sync(0xFFFFFFFFu, ok && ((fl & Q.flags2) == Q.flags2));
+            if (lane == 0) {
+              S.Tfa[i] = make_uint2(m1, m2);
+              if (shared) { gt[2 * i] = m1; gt[2 * i + 1] = m2; }
+            }
+          } else if (i < G.n_fa + G.n_cm) {
+            const int e = i - G.n_fa;
+            const double2 v = S.d_cm[e];
+            const double lo = ratio ? __dmul_rn(v.x, Q.mem_lo) : Q.mem_lo;
+            const bool okc = (Q.cpus_op == 0) | ((v.x >= Q.cpu_lo) & (v.x <= Q.cpu_hi));
+            const bool okr = (Q.mem_op == 0) | ((v.y >= lo) & (v.y <= Q.mem_hi));
+            m1 = __ballot_sync(0xFFFFFFFFu, lq & okc & okr);
+            if (lane == 0) { S.Tcm[e] = m1; if (shared) gt[2 * a.cap_fa + e] = m1; }
+          } else {
+            const int e = i - G.n_fa - G.n_cm;
+            const uint32_t key = S.d_rz[e];  // region | zone << 16
+            // region: row-key bits 16..31, zone: bits 32..47
+            const bool ok = lq && (((key & 0xFFFFu) ^ (Q.val_lo >> 16)) & (Q.mask_lo >> 16)) == 0u &&
+                            (((key >> 16) ^ Q.val_hi) & Q.mask_hi & 0xFFFFu) == 0u;
+            m1 = __ballot_sync(0xFFFFFFFFu, ok);
+            if (lane == 0) { S.Trz[e] = m1; if (shared) gt[2 * a.cap_fa + a.cap_cm + e] = m1; }
+          }
         }
-        for (int e = warp; e < G.n_cm; e += kFastWarps) {
-          const double2 v = S.d_cm[e];
-          const double lo = ratio ? __dmul_rn(v.x, Q.mem_lo) : Q.mem_lo;
-          const bool okc = (Q.cpus_op == 0) | ((v.x >= Q.cpu_lo) & (v.x <= Q.cpu_hi));
-          const bool okr = (Q.mem_op == 0) | ((v.y >= lo) & (v.y <= Q.mem_hi));
-          const uint32_t m = __ballot_sync(0xFFFFFFFFu, lq & okc & okr);
-          if (lane == 0) S.Tcm[e] = m;
-        }
-        for (int e = warp; e < G.n_rz; e += kFastWarps) {
-          const uint32_t key = S.d_rz[e];  // region | zone << 16
-          // region: row-key bits 16..31, zone: bits 32..47
-          const bool ok = lq && (((key & 0xFFFFu) ^ (Q.val_lo >> 16)) & (Q.mask_lo >> 16)) == 0u &&
-                          (((key >> 16) ^ Q.val_hi) & Q.mask_hi & 0xFFFFu) == 0u;
-          const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-          if (lane == 0) S.Trz[e] = m;
+        if (shared) {
+          // publish the slice, wait for the others, fetch the rest
+          __syncthreads();
+          if (tid == 0) {
+            __threadfence();
+            atomicAdd(a.group_ready + G.index, 1u);
+            while (*reinterpret_cast<volatile unsigned int *>(a.group_ready + G.index) < (unsigned)G.n_pieces)
+              if (!(a.noprune & 4u)) __nanosleep(32);
+            __threadfence();
+          }
+          __syncthreads();
+#pragma unroll 1
+          for (int i = tid; i < n_all; i += kScanThreads) {
+            if (i >= e_lo && i < e_hi) continue;
+            if (i < G.n_fa) S.Tfa[i] = make_uint2(__ldcg(gt + 2 * i), __ldcg(gt + 2 * i + 1));
+            else if (i < G.n_fa + G.n_cm) S.Tcm[i - G.n_fa] = __ldcg(gt + 2 * a.cap_fa + (i - G.n_fa));
+            else S.Trz[i - G.n_fa - G.n_cm] = __ldcg(gt + 2 * a.cap_fa + a.cap_cm + (i - G.n_fa - G.n_cm));
+          }
         }
       }
       __syncthreads();
@@ -456,7 +509,8 @@ struct SlotAux {
   int64_t rec_base;     // cloud_row_offsets[query.cloud]
   int32_t qcol;         // the query's price column
   int32_t cloud_r0, cloud_r1;  // row range of the slot's cloud
-  int32_t has_zones;
+  int16_t has_zones;
+  int16_t acc_list_key;  // the one key of the slot's accelerator set, -1 = none
   double max_price;
 };
 static_assert(sizeof(SlotAux) == 32, "SlotAux layout");
@@ -517,9 +571,13 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
     PlaceSlot p{};
     int inst = S.inst_id;
     bool empty = false;
+    const int col = S.price_col ? 1 : 0;
     // independent loads first
     const uint32_t gate = (S.gate_query >= 0) ? __ldcg(a.any1 + S.gate_query) : 1u;
     const uint32_t r = (S.query >= 0) ? __ldcg(a.best_rank + S.query) : 0u;
+    ListRec acc_rec{};
+    if (S.acc_set >= 0 && X.acc_list_key >= 0) acc_rec = a.f.acc_list[X.acc_list_key];
+    ListRec host{};
     if (gate == 0u) empty = true;
     if (S.query >= 0) {
       if (r == kRankNone) empty = true;
@@ -527,29 +585,23 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
         const RankRec rec = a.f.rank_rec[X.qcol][X.rec_base + r];
         if (!(rec.price <= X.max_price)) empty = true;  // price cap (common.py:563, :681)
         inst = rec.inst;
+        host.off = rec.list_off; host.cnt[0] = rec.cnt[0]; host.cnt[1] = rec.cnt[1]; host.acc_key = rec.acc_key;
         if (inst < 0) empty = true;
       }
+    } else if (inst >= 0) {
+      host = a.f.inst_list[inst];
     }
-    const int col = S.price_col ? 1 : 0;
     if (empty || (inst < 0 && inst != -2)) {
       p.kind = 0; p.inst = -1;
     } else {
       p.inst = inst;
-      ListRec host{};
-      if (inst >= 0) host = a.f.inst_list[inst];
       int acc = S.cand_acc_key;
       if (acc < 0 && inst >= 0) acc = host.acc_key;
       p.cand_acc = acc;
       if (S.acc_set >= 0) {
         // the set holds exactly one key (checked on the host)
-        const uint32_t *set = a.acc_sets + (int64_t)S.acc_set * SKYOPT_ACC_SET_WORDS;
-        int key = -1;
-        for (int w = 0; w < SKYOPT_ACC_SET_WORDS; ++w) {
-          const uint32_t v = set[w];
-          if (v && key < 0) key = 32 * w + __ffs(v) - 1;
-        }
         p.kind = 2;
-        if (key >= 0) { const ListRec L = a.f.acc_list[key]; p.list_off = L.off; p.list_n = L.cnt[col]; }
+        p.list_off = acc_rec.off; p.list_n = acc_rec.cnt[col];
         if (inst >= 0) { p.host_off = host.off; p.host_n = host.cnt[col]; }
       } else {
         p.kind = 1;
@@ -577,9 +629,11 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
     double *host = s_host[warp];
     if (gcp && p.inst >= 0) {
       // host VM price per zone (gcp.py:296-322)
+#pragma unroll 1
       for (int i = lane; i < kFastMaxZones; i += 32) host[i] = kNaN;
       __syncwarp();
       const ExpEnt *hl = a.f.exp_ent[col] + p.host_off;
+#pragma unroll 1
       for (int i = lane; i < p.host_n; i += 32) {
         const ExpEnt e = hl[i];
         if (e.zn != SKYOPT_NONE16 && e.zn < kFastMaxZones) host[e.zn] = e.price;
@@ -590,6 +644,7 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
     unsigned long long vmin = kKeyNone;
     const int64_t eoff = a.in.slot_off[s];
     const int64_t toff = a.in.task_off[t];
+#pragma unroll 1
     for (int i0 = 0; i0 < p.list_n; i0 += 32) {
       const int i = i0 + lane;
       bool keep = i < p.list_n;
@@ -620,6 +675,7 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
       const int zout = (split || S.zone_id >= 0) ? (has_zones ? zn : -1) : -1;
       bool blocked = false;
       if (keep) {
+#pragma unroll 1
         for (int b = TK.blocked_begin; b < TK.blocked_end; ++b) {
           const SkyoptBlocked Bk = a.in.blocked[b];
           const bool m = (Bk.cloud == -1 || Bk.cloud == S.cloud) &&
@@ -670,34 +726,40 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
     }
   };
 
-  // ---- phase B1: count
-  for (int ls = warp; ls < ns; ls += kFastWarps) {
-    if (ps[ls].kind != 0) walk(ls, false, 0, 0, 0, 0);
-    else if (lane == 0) { ps[ls].n_e[0] = ps[ls].n_e[1] = ps[ls].n_b[0] = ps[ls].n_b[1] = 0; }
-  }
-  __syncthreads();
-  trace_mark(a.trace, 1, 2);
-  if (tid == 0) {
-    int acc = 0;
-    for (int i = 0; i < ns; ++i) { s_base[i] = acc; acc += ps[i].n_b[0] + ps[i].n_b[1]; }
-    s_base[ns] = acc;
-    a.task_n[t] = acc;
-  }
-  if (tid < ns) {
-    const int s = TK.slot_begin + tid;
-    a.in.ex.slot_count[s] = ps[tid].n_e[0] + ps[tid].n_e[1];
-    a.in.ex.slot_inst[s] = ps[tid].inst;
-  }
-  __syncthreads();
-  // ---- phase B2: write (same walk, now with the partition bases)
-  for (int ls = warp; ls < ns; ls += kFastWarps) {
-    if (ps[ls].kind != 0) walk(ls, true, 0, ps[ls].n_e[0], s_base[ls], s_base[ls] + ps[ls].n_b[0]);
-    else if (lane == 0) ps[ls].vmin = kKeyNone;
+  // ---- phase B: count, then write (one copy of the walk: this code runs
+  // once per launch, its size is its cost)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool write = pass == 1;
+#pragma unroll 1
+    for (int ls = warp; ls < ns; ls += kFastWarps) {
+      if (ps[ls].kind != 0)
+        walk(ls, write, 0, write ? ps[ls].n_e[0] : 0, write ? s_base[ls] : 0,
+             write ? s_base[ls] + ps[ls].n_b[0] : 0);
+      else if (lane == 0) { ps[ls].n_e[0] = ps[ls].n_e[1] = ps[ls].n_b[0] = ps[ls].n_b[1] = 0; ps[ls].vmin = kKeyNone; }
+    }
+    if (write) break;
+    __syncthreads();
+    trace_mark(a.trace, 1, 2);
+    if (tid == 0) {
+      int acc = 0;
+#pragma unroll 1
+      for (int i = 0; i < ns; ++i) { s_base[i] = acc; acc += ps[i].n_b[0] + ps[i].n_b[1]; }
+      s_base[ns] = acc;
+      a.task_n[t] = acc;
+    }
+    if (tid < ns) {
+      const int s = TK.slot_begin + tid;
+      a.in.ex.slot_count[s] = ps[tid].n_e[0] + ps[tid].n_e[1];
+      a.in.ex.slot_inst[s] = ps[tid].inst;
+    }
+    __syncthreads();
   }
   if (a.task_mv) {
     __syncthreads();
     if (tid < cat.n_clouds) {
       unsigned long long k = kKeyNone;
+#pragma unroll 1
       for (int i = 0; i < ns; ++i)
         if (s_slot[i].cloud == tid && ps[i].vmin < k) k = ps[i].vmin;
       a.task_mv[(int64_t)t * cat.n_clouds + tid] = k;

@@ -1744,7 +1744,7 @@ solve_kernel(CatDev cat, SolveIn in, SolveWork w, SolveOut out) {
     bool too_big = false;
     for (int lt = 0; lt < T; ++lt) {
       total *= s_nopt[lt];
-      if (total > (1ll << 36)) { too_big = true; break; }
+      if (total > (1ll << 26)) { too_big = true; break; }  // ~10 ms of one block; beyond: status 2
     }
     if (too_big) {
       if (tid == 0) {

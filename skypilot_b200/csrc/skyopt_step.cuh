@@ -10,7 +10,7 @@
 
 namespace skyopt {
 
-constexpr int kStepMaxCand = 2048;  // candidates of one DAG kept in shared memory
+constexpr int kStepMaxCand = 4096;  // candidates of one DAG kept in shared memory
 
 // Chain DP (reference sky/optimizer.py:429-487) of one DAG by one block of
 // kScanThreads threads: the algorithm of solve_kernel's fast path -- per-cloud
@@ -58,10 +58,12 @@ __device__ __forceinline__ void chain_body(const CatDev &cat, const SolveIn &in,
   if (tid < T && M.tn[tid] == 0) atomicMin(&M.first_empty, tid);
   if (tid == 0) {
     int acc = 0;
+#pragma unroll 1
     for (int i = 0; i < T; ++i) { M.cbase[i] = acc; acc += M.tn[i]; }
     M.cbase[T] = acc;
     M.staged = acc <= kStepMaxCand ? 1 : 0;
   }
+#pragma unroll 1
   for (int i = tid; i < T * C; i += kScanThreads) {
     const int lt = i / C, cc = i % C;
     // per-(task, cloud) minimum value: left by the task's place block
@@ -80,106 +82,134 @@ __device__ __forceinline__ void chain_body(const CatDev &cat, const SolveIn &in,
   step_mark(out.trace, 1);
   const long long c_start = clock64();
   const bool staged = M.staged != 0;
-  if (warp == 0) {
-    // B[t][h] = min_g fl(D[t-1][g] + e_t(g, h)),  D[t][g] = fl(mv[t][g] + B[t][g]):
-    // lane h owns cloud h and keeps D[t-1][h] in a register; the C sums of a
-    // step are independent of each other.
-    const int h = lane < C ? lane : 0;
-    double dprev = 0.0;
-    for (int lt = 0; lt < T; ++lt) {
-      double b;
-      if (M.np[lt] == 0) {
-        b = M.tar[lt][h];  // dummy source: 0 + egress from the inputs' cloud
-      } else {
-        b = kInf;
+  int Cp = 1;
+  while (Cp < C) Cp <<= 1;
+  const int parts = 32 / Cp;
+  // Two passes over ONE copy of the winners / back-tracking code. Pass 0: warp
+  // 0 walks the recurrence (serial, one warp) while the other warps bring the
+  // candidates to shared memory and then run the winners code on whatever B
+  // holds -- a rehearsal whose only purpose is to have that code in the
+  // instruction caches: this block is the only one that ever executes it, and
+  // after a cold start every new instruction line is a DRAM round trip
+  // (profiles/round2_timeline.md). Pass 1 is the real thing.
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 0) {
+      if (warp == 0) {
+        // B[t][h] = min_g fl(D[t-1][g] + e_t(g, h)),  D[t][h] = fl(mv[t][h] + B[t][h])
+        // with e_t(g, h) = tar_t[g] for g != h and 0 for g == h. So
+        //   B[t][h] = min(D[t-1][h], min_{g != h} A[g]),  A[g] = fl(D[t-1][g] + tar_t[g]):
+        // lane g forms its one sum, a butterfly over the Cp lanes gives every
+        // lane the smallest and second smallest A (with multiplicity), and
+        // lane h takes the second one when its own A is the smallest. Same
+        // sums, same minima as the reference's double loop
+        // (optimizer.py:456-470), a third of the dependent latency.
+        const int h = lane < C ? lane : 0;
+        double dprev = 0.0;
+#pragma unroll 1
+        for (int lt = 0; lt < T; ++lt) {
+          double b;
+          if (M.np[lt] == 0) {
+            b = M.tar[lt][h];  // dummy source: 0 + egress from the inputs' cloud
+          } else {
+            const double mine = lane < C ? __dadd_rn(dprev, M.tar[lt][h]) : kInf;
+            double m1 = mine, m2 = kInf;
+#pragma unroll 1
+            for (int o = 1; o < Cp; o <<= 1) {
+              const double p1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o);
+              const double p2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+              const double lo = p1 < m1 ? p1 : m1, hi = p1 < m1 ? m1 : p1;
+              const double s2 = p2 < m2 ? p2 : m2;
+              m1 = lo; m2 = s2 < hi ? s2 : hi;
+            }
+            const double others = (mine == m1) ? m2 : m1;
+            b = others < dprev ? others : dprev;
+          }
+          const unsigned long long mk = M.mv[lt][h];
+          if (lane < C) M.B[lt][lane] = b;
+          dprev = (mk == kKeyNone) ? kInf : __dadd_rn(key_price(mk), b);
+        }
+        if (out.trace && lane == 0 && blockIdx.x < kTraceBlocks)
+          out.trace[((size_t)2 * kTraceBlocks + blockIdx.x) * kTraceSlots + 8] = (unsigned long long)(clock64() - c_start);
+      } else if (staged) {
+#pragma unroll 1
+        for (int lt = warp - 1; lt < T; lt += kFastWarps - 1) {
+          const int n = M.tn[lt];
+          const long long toff = M.toff[lt];
+          const int cb = M.cbase[lt];
+#pragma unroll 1
+          for (int c = lane; c < n; c += 32) {
+            M.ccl[cb + c] = (unsigned char)__ldcg(w.tc_cloud + toff + c);
+            M.cval[cb + c] = __ldcg(w.tc_value + toff + c);
+          }
+        }
+      }
+    }
+    if (pass == 1 || warp != 0) {
+      // winners: for parent task lt and child cloud h, the first minimum over
+      // the parent's candidates p of fl(dp[p] + e_{lt+1}(cloud(p), h)) --
+      // exactly the sums the reference forms (optimizer.py:456-470). A warp
+      // takes a parent task; lane = (part, h): the candidates are dealt to
+      // 32 / Cp parts, each lane walks its part in candidate order (strict '<'
+      // keeps the first minimum), the parts are merged with (value, index)
+      // comparisons. The last task's only child is the dummy sink (egress 0).
+      const int h = lane % Cp, part = lane / Cp;
+#pragma unroll 1
+      for (int lt = warp; lt < T; lt += kFastWarps) {
+        const bool sink = lt == T - 1;
+        const int n = M.tn[lt];
+        const long long toff = M.toff[lt];
+        const int cb = M.cbase[lt];
+        double bv = kInf; int bi = 0x7FFFFFFF;
+        const bool wanted = h < C && (sink ? h == 0 : M.mv[lt + 1][h] != kKeyNone);
+        if (wanted) {
 #pragma unroll 4
-        for (int g = 0; g < C; ++g) {
-          const double dg = __shfl_sync(0xFFFFFFFFu, dprev, g);
-          const double e = (g != lane) ? M.tar[lt][g] : 0.0;
-          const double v = __dadd_rn(dg, e);
-          if (v < b) b = v;
+          for (int p = part; p < n; p += parts) {
+            const int cp = (staged ? (int)M.ccl[cb + p] : __ldcg(w.tc_cloud + toff + p)) & (SKYOPT_MAX_CLOUDS - 1);
+            const double val = staged ? M.cval[cb + p] : __ldcg(w.tc_value + toff + p);
+            const double dpp = __dadd_rn(val, M.B[lt][cp]);
+            const double e = (!sink && cp != h) ? M.tar[lt + 1][cp] : 0.0;
+            const double sum = sink ? dpp : __dadd_rn(dpp, e);
+            if (sum < bv) { bv = sum; bi = p; }
+          }
+        }
+#pragma unroll 1
+        for (int o = Cp; o < 32; o <<= 1) {
+          const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+          const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+          lexmin(bv, bi, ov, oi);
+        }
+        if (part == 0 && h < C && (!sink || h == 0)) {
+          const int slot_t = lt + 1;  // indexed by the child task; T = the sink
+          M.bk_idx[slot_t][h] = bi;
+          unsigned char cl = 0;
+          if (bi != 0x7FFFFFFF && bi < n)
+            cl = staged ? M.ccl[cb + bi] : (unsigned char)__ldcg(w.tc_cloud + toff + bi);
+          M.bk_cl[slot_t][h] = cl;
+          if (sink) M.obj = bv;
         }
       }
-      const unsigned long long mk = M.mv[lt][h];
-      if (lane < C) M.B[lt][lane] = b;
-      dprev = (mk == kKeyNone) ? kInf : __dadd_rn(key_price(mk), b);
-    }
-    if (out.trace && lane == 0 && blockIdx.x < kTraceBlocks)
-      out.trace[((size_t)2 * kTraceBlocks + blockIdx.x) * kTraceSlots + 8] = (unsigned long long)(clock64() - c_start);
-  } else if (staged) {
-    // meanwhile the other warps bring the candidates (cloud, value) to shared memory
-    for (int lt = warp - 1; lt < T; lt += kFastWarps - 1) {
-      const int n = M.tn[lt];
-      const long long toff = M.toff[lt];
-      const int cb = M.cbase[lt];
-      for (int c = lane; c < n; c += 32) {
-        M.ccl[cb + c] = (unsigned char)__ldcg(w.tc_cloud + toff + c);
-        M.cval[cb + c] = __ldcg(w.tc_value + toff + c);
-      }
-    }
-  }
-  __syncthreads();
-  step_mark(out.trace, 3);
-  // winners: for parent task lt and child cloud h, the first minimum over the
-  // parent's candidates p of fl(dp[p] + e_{lt+1}(cloud(p), h)) -- exactly the
-  // sums the reference forms (optimizer.py:456-470). A warp takes a parent
-  // task; lane = (part, h): the candidates are dealt to 32 / Cp parts, each
-  // lane walks its part in candidate order (strict '<' keeps the first
-  // minimum), the parts are merged with (value, index) comparisons. The last
-  // task's only child is the dummy sink (egress 0).
-  {
-    int Cp = 1;
-    while (Cp < C) Cp <<= 1;
-    const int parts = 32 / Cp;
-    const int h = lane % Cp, part = lane / Cp;
-    for (int lt = warp; lt < T; lt += kFastWarps) {
-      const bool sink = lt == T - 1;
-      const int n = M.tn[lt];
-      const long long toff = M.toff[lt];
-      const int cb = M.cbase[lt];
-      double bv = kInf; int bi = 0x7FFFFFFF;
-      const bool wanted = h < C && (sink ? h == 0 : M.mv[lt + 1][h] != kKeyNone);
-      if (wanted) {
-        for (int p = part; p < n; p += parts) {
-          const int cp = staged ? (int)M.ccl[cb + p] : __ldcg(w.tc_cloud + toff + p);
-          const double val = staged ? M.cval[cb + p] : __ldcg(w.tc_value + toff + p);
-          const double dpp = __dadd_rn(val, M.B[lt][cp]);
-          const double e = (!sink && cp != h) ? M.tar[lt + 1][cp] : 0.0;
-          const double sum = sink ? dpp : __dadd_rn(dpp, e);
-          if (sum < bv) { bv = sum; bi = p; }
+      // back-tracking (thread 0; rehearsed by thread 32)
+      if (pass == 1) { __syncthreads(); step_mark(out.trace, 4); }
+      if (tid == (pass == 1 ? 0 : 32)) {
+        int idx = M.bk_idx[T][0];
+        int cl = M.bk_cl[T][0] & (SKYOPT_MAX_CLOUDS - 1);
+#pragma unroll 1
+        for (int lt = T - 1; lt >= 0; --lt) {
+          if (pass == 1) M.choice[lt] = idx;
+          if (lt > 0) {
+            const int ni = M.bk_idx[lt][cl];
+            cl = M.bk_cl[lt][cl] & (SKYOPT_MAX_CLOUDS - 1);
+            idx = ni;
+          }
+        }
+        if (pass == 1) {
+          SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = M.obj;
+          out.dag[dag] = r;
         }
       }
-      for (int o = Cp; o < 32; o <<= 1) {
-        const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
-        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
-        lexmin(bv, bi, ov, oi);
-      }
-      if (part == 0 && h < C && (!sink || h == 0)) {
-        const int slot_t = lt + 1;  // indexed by the child task; T = the sink
-        M.bk_idx[slot_t][h] = bi;
-        unsigned char cl = 0;
-        if (bi != 0x7FFFFFFF)
-          cl = staged ? M.ccl[cb + bi] : (unsigned char)__ldcg(w.tc_cloud + toff + bi);
-        M.bk_cl[slot_t][h] = cl;
-        if (sink) M.obj = bv;
-      }
     }
-  }
-  __syncthreads();
-  step_mark(out.trace, 4);
-  if (tid == 0) {
-    SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = M.obj;
-    out.dag[dag] = r;
-    int idx = M.bk_idx[T][0];
-    int cl = M.bk_cl[T][0];
-    for (int lt = T - 1; lt >= 0; --lt) {
-      M.choice[lt] = idx;
-      if (lt > 0) {
-        const int ni = M.bk_idx[lt][cl];
-        cl = M.bk_cl[lt][cl];
-        idx = ni;
-      }
-    }
+    if (pass == 0) { __syncthreads(); step_mark(out.trace, 3); }
   }
   __syncthreads();
   step_mark(out.trace, 5);
@@ -209,7 +239,9 @@ struct StepArgs {
   PlaceArgs place;
   SolveOut out;
   const int32_t *task_dag;
-  int n_tasks;
+  int n_tasks, n_queries;
+  const char *in_base;    // the uploaded input region (descriptors), prefetched into L2
+  int64_t in_lines;
   int do_solve;           // every DAG is a chain of <= kFastTasks tasks
   int32_t *dag_done;      // [n_dags] tasks placed so far (zero between launches)
   unsigned int *sync;     // [2] arrivals at the barrier / at the exit (zero between launches)
@@ -226,6 +258,11 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) step_kernel(St
   __shared__ int s_last;
   const int tid = threadIdx.x;
   if (blockIdx.x == 0 && tid == 0 && a.scan.zero_flag) *a.scan.zero_flag = 0;
+  // the problem's descriptors (tens of KB) are wanted in L2 by the later
+  // phases: every block touches its share of the lines now
+  for (int64_t line = (int64_t)blockIdx.x * kScanThreads + tid; line < a.in_lines;
+       line += (int64_t)gridDim.x * kScanThreads)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_base + line * 128));
   if (a.scan.n_pieces) scan2_body(a.scan, smem_step);
   // ---- grid barrier: every scan result is published (cooperative launch:
   // all blocks are resident)
@@ -233,7 +270,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) step_kernel(St
   if (tid == 0) {
     __threadfence();
     atomicAdd(a.sync, 1u);
-    while (ld_acquire_u32(a.sync) < gridDim.x) __nanosleep(64);
+    while (ld_acquire_u32(a.sync) < gridDim.x) if (!(a.scan.noprune & 4u)) __nanosleep(64);
     __threadfence();
   }
   __syncthreads();
@@ -257,10 +294,20 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) step_kernel(St
     }
     __syncthreads();  // shared memory is reused by the next task
   }
-  // ---- the last block out re-arms the barrier
+  // ---- the last block out re-arms the barrier and the scan results (the
+  // next launch of this context starts from "nothing found")
   if (tid == 0) {
     __threadfence();
-    if (atomicAdd(a.sync + 1, 1u) == gridDim.x - 1) { a.sync[0] = 0; a.sync[1] = 0; }
+    s_last = (atomicAdd(a.sync + 1, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+#pragma unroll 1
+    for (int i = tid; i < a.n_queries; i += kScanThreads) { a.scan.best_rank[i] = kRankNone; a.scan.any1[i] = 0u; }
+    if (a.scan.group_ready)
+#pragma unroll 1
+      for (int i = tid; i < a.scan.n_groups; i += kScanThreads) a.scan.group_ready[i] = 0u;
+    if (tid == 0) { __threadfence(); a.sync[0] = 0; a.sync[1] = 0; }
   }
 }
 

@@ -598,6 +598,10 @@ class Session:
                                           ctypes.byref(csol),
                                           ctypes.byref(self.solution.stats),
                                           ctypes.byref(self._handle)))
+        # the native session holds the catalog handle: the store closes its
+        # open sessions before it destroys the handle (CatalogStore.close)
+        self._store = builder.store
+        builder.store.register_session(self)
 
     def resolve(self, blocked: List[Dict[str, int]]) -> Solution:
         """Re-masks and re-solves; `blocked` are `add_blocked`-style dicts."""
@@ -617,6 +621,7 @@ class Session:
         if self._handle:
             self._lib.skyopt_session_close(self._handle)
             self._handle = ctypes.c_void_p()
+            self._store.unregister_session(self)
 
     def __del__(self):
         try:

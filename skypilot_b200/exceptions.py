@@ -22,6 +22,13 @@ class NotSupportedError(Exception):
     """A cloud does not implement a requested feature (sky/exceptions.py)."""
 
 
+class OptimizerLimitError(NotSupportedError):
+    """The problem is valid but exceeds a documented capacity of this
+    optimizer (e.g. a densely connected general DAG under the TIME objective).
+    Deliberately NOT a ResourcesUnavailableError: failover loops must not read
+    it as "no capacity in this region"."""
+
+
 class ResourcesMismatchError(Exception):
     """The accelerators cannot be attached to the instance type."""
 

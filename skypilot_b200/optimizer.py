@@ -299,9 +299,12 @@ class Optimizer:
                         Optimizer._raise_unavailable(
                             problem.tasks[int(res['task_fail'])], blocked)
                     if res['status'] != 0:
-                        raise exceptions.ResourcesUnavailableError(
-                            'The DAG is too large for the exact general-DAG '
-                            'search.')
+                        # beyond the device enumeration: the single-DAG path
+                        # solves it by elimination on the host
+                        Optimizer.optimize(dags[i], minimize, blocked,
+                                           quiet=True)
+                        out[i] = dags[i]
+                        continue
                     for j, task in enumerate(problem.tasks):
                         task.best_resources = problem.launchable(
                             sol.chosen[first_task[i] + j])
@@ -651,9 +654,11 @@ class Optimizer:
             failed = topo_real[int(res['task_fail'])]
             Optimizer._raise_unavailable(failed, blocked)
         if res['status'] != 0:
-            raise exceptions.ResourcesUnavailableError(
-                'The DAG is too large for the exact general-DAG search '
-                '(more than 16 tasks or 2^36 cloud assignments).')
+            # beyond the device enumeration: exact elimination on the host
+            if sol.tables is None:
+                sol = Optimizer._solve(problem, want_tables=True)
+            _solve_large_dag(problem, sol, 0, 0, len(topo_real), minimize_cost)
+            res = sol.dag[0]
         best_plan: Dict[task_lib.Task, resources_lib.Resources] = {}
         for i, task in enumerate(topo_real):
             launchable = problem.launchable(sol.chosen[i])
@@ -770,10 +775,18 @@ class Optimizer:
         chosen, objective, status = engine.solve_tables(
             store, values, cl, parents, edge_rows, src_rows, is_chain,
             minimize_cost, device=catalog.get_device())
-        if status != 0:
+        if status == 2:
+            # beyond the device enumeration (dag_solver.py)
+            from skypilot_b200 import dag_solver  # pylint: disable=import-outside-toplevel
+            if not minimize_cost:
+                raise exceptions.OptimizerLimitError(
+                    'The DAG is too large for the exact general-DAG search '
+                    'under the TIME objective.')
+            chosen, objective = dag_solver.solve_cost_dag(
+                values, cl, parents, edge_rows, src_rows, n_clouds)
+        elif status != 0:
             raise exceptions.ResourcesUnavailableError(
-                'No launchable resource found, or the DAG is too large for '
-                'the exact general-DAG search (16 tasks / 2^36 assignments).')
+                'No launchable resource found for a task of the DAG.')
         best_plan = {}
         for task, idx, ks in zip(real, chosen, keys):
             task.best_resources = ks[idx]
@@ -986,6 +999,12 @@ class OptimizerSession:
             topo_order = list(nx.topological_sort(graph))
             topo_real = [t for t in topo_order if not _is_dummy(t)]
             store = catalog.get_store()
+            if self._session is not None and store is not self._problem.builder.store:
+                # region / zone / instance ids are ranks of ONE catalog: after
+                # a reload the device-resident candidates mean something else
+                raise RuntimeError(
+                    'the catalog changed while an OptimizerSession was open; '
+                    'close the session and open a new one')
             if self._session is None:
                 problem = Optimizer._state_problem(  # pylint: disable=protected-access
                     graph, topo_real, self.minimize_cost, blocked,
@@ -1020,6 +1039,50 @@ def _cloud_object(name: str) -> clouds.Cloud:
     return clouds.DummyCloud()
 
 
+def _solve_large_dag(problem, sol, dag_index: int, task_begin: int,
+                     n_tasks: int, minimize_cost: bool):
+    """A general DAG the device enumeration refused (status 2: more than 16
+    tasks or 2^26 cloud assignments): exact bucket elimination over the
+    per-cloud minima of the candidate tables (dag_solver.py). Fills
+    `sol.chosen` / `sol.dag` like the device does."""
+    from skypilot_b200 import dag_solver  # pylint: disable=import-outside-toplevel
+    if not minimize_cost:
+        raise exceptions.OptimizerLimitError(
+            'The DAG is too large for the exact general-DAG search under '
+            'the TIME objective (more than 16 tasks or 2^26 cloud '
+            'assignments); the COST objective has no such limit.')
+    packed = sol.packed
+    n_clouds = len(packed.store.clouds)
+    values, cls, parents, edge_rows, src_rows = [], [], [], [], []
+    for lt in range(n_tasks):
+        t = task_begin + lt
+        table = sol.task_table(t)
+        values.append([float(v) for v in table['value']])
+        cls.append([int(packed.slots['cloud'][int(sl)]) for sl in table['slot']])
+        tk = packed.tasks[t]
+        npar = int(tk['n_parents'])
+        pb = int(tk['parent_begin'])
+        parents.append([int(p) for p in packed.parents[pb:pb + npar]])
+        eb = int(tk['edge_tariff_begin'])
+        edge_rows.append([
+            [float(x) for x in packed.tariffs[eb + j * n_clouds:
+                                              eb + (j + 1) * n_clouds]]
+            for j in range(npar)
+        ])
+        sb = int(tk['src_tariff_begin'])
+        src_rows.append(None if (npar or sb < 0) else
+                        [float(x) for x in packed.tariffs[sb:sb + n_clouds]])
+    chosen, objective = dag_solver.solve_cost_dag(values, cls, parents,
+                                                  edge_rows, src_rows, n_clouds)
+    for lt, k in enumerate(chosen):
+        t = task_begin + lt
+        sol.chosen[t] = sol.task_table(t)[k]
+        sol.chosen_index[t] = k
+    sol.dag[dag_index]['status'] = 0
+    sol.dag[dag_index]['task_fail'] = -1
+    sol.dag[dag_index]['objective'] = objective
+
+
 def _add_blocked(b: engine.ProblemBuilder, store, blocked) -> None:
     """One `should_be_blocked_by` wildcard (sky/resources.py:1938-1961) as
     device entries; names are resolved against each cloud's dictionaries."""
@@ -1037,7 +1100,10 @@ def _add_blocked(b: engine.ProblemBuilder, store, blocked) -> None:
         if len(accs) != 1:
             return
         name, count = list(accs.items())[0]
-        acc_key = store.acc_key_index.get((name, float(count)), -2)
+        # -3: a name the catalog does not know matches no candidate -- not even
+        # a candidate whose own accelerator is unknown (-2, clouds/gcp.py): the
+        # reference compares the dicts themselves (sky/resources.py:1956-1958)
+        acc_key = store.acc_key_index.get((name, float(count)), -3)
     needs_cloud = (blocked.instance_type is not None or
                    blocked.region is not None or blocked.zone is not None)
     if not needs_cloud and blocked.cloud is None:

@@ -219,3 +219,10 @@ def res_record(r) -> Dict[str, Any]:
                         {k: float(v) for k, v in accs.items()},
         'use_spot': bool(r.use_spot),
     }
+
+
+# name -> catalog spec and chain length of the two chain workloads (tools/)
+WORKLOADS = {
+    'cfg2': {'catalog': CATALOGS['cfg2'], 'tasks': 8},
+    'cfg4': {'catalog': CATALOGS['cfg4'], 'tasks': 32},
+}

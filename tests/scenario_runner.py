@@ -36,7 +36,8 @@ def activate_catalog(spec: Dict[str, Any]):
         store.enabled = enabled
         _loaded[key] = store
     sky.catalog.set_store(store)
-    sky.check.set_enabled_clouds(getattr(store, 'enabled', None))
+    sky.check.set_enabled_clouds(
+        getattr(store, 'enabled', None) or sky.check.ALL_CATALOG_CLOUDS)
     return store
 
 

@@ -68,6 +68,9 @@ CATALOGS = {
     'cfg4_1m': dict(workloads.CATALOGS['cfg4']),
     # cfg5: 10 000 single-task DAGs on the cfg2 catalog
     'cfg5_50k': dict(workloads.CATALOGS['cfg2']),
+    # general DAGs of 18-26 tasks (big_dag_scenarios), the fuzzdag catalog
+    'bigdag': {'seed': 61, 'n_rows': 6000,
+               'clouds': ['aws', 'gcp', 'azure', 'lambda']},
     'gpuclouds': {'seed': 13, 'n_rows': 4000,
                   'clouds': ['aws', 'runpod', 'paperspace', 'do',
                              'fluidstack', 'cudo']},
@@ -501,6 +504,80 @@ def fuzz_dag_scenarios(seed=13, n=40):
                     edges.append([p_, j])
         out.append({'name': f'dag{i}', 'tasks': tasks, 'edges': edges,
                     'minimize': rng.choice(['cost', 'cost', 'time'])})
+    return out
+
+
+def big_dag_scenarios(seed=21):
+    """General DAGs beyond the device enumeration (more than 16 tasks): stage
+    pipelines with fan-out / fan-in, chains of diamonds and a sparse random
+    DAG -- 18 to 26 tasks, COST. The reference's ILP has no size limit
+    (sky/optimizer.py:490-637); its optimum here is the frontier dynamic
+    program of oracle/dag_oracle.py over the reference's own candidate tables
+    (run_reference.py), ours the bucket elimination of dag_solver.py."""
+    import random
+    rng = random.Random(seed)
+    pool = [{'accelerators': 'V100'}, {'accelerators': 'T4'},
+            {'accelerators': 'L4'}, {'accelerators': 'A100:8'},
+            {'cpus': '8+'}, {'cpus': '32+', 'memory': '128+'},
+            {'accelerators': 'A10G'}, {'memory': '64+'},
+            {'accelerators': 'T4:4', 'use_spot': True},
+            {'cpus': '4+', 'use_spot': True},
+            {'accelerators': 'V100', 'cloud': 'gcp'},
+            {'cpus': '16+', 'cloud': 'azure'}]
+
+    def task(j):
+        t = {'name': f't{j}', 'resources': [dict(rng.choice(pool))]}
+        if rng.random() < 0.9:
+            t['outputs_gb'] = rng.choice([0.5, 20, 300, 2500, 12000])
+        if rng.random() < 0.25:
+            t['num_nodes'] = 2
+        return t
+
+    out = []
+    # chain of six diamonds: a -> {b, c} -> d -> {e, f} -> g ...
+    tasks, edges = [task(0)], []
+    for _ in range(6):
+        a = len(tasks) - 1
+        tasks += [task(a + 1), task(a + 2), task(a + 3)]
+        edges += [[a, a + 1], [a, a + 2], [a + 1, a + 3], [a + 2, a + 3]]
+    out.append({'name': 'diamonds19', 'tasks': tasks, 'edges': edges})
+    # stage pipeline: 1 -> 4 -> 2 -> 5 -> 1 -> 4 -> 3 -> 1, full fan between
+    # neighbouring stages is too dense; every task takes 1-2 parents upstream
+    tasks, edges, prev = [], [], []
+    for width in [1, 4, 2, 5, 1, 4, 3, 1, 3, 2]:
+        cur = []
+        for _ in range(width):
+            j = len(tasks)
+            tasks.append(task(j))
+            cur.append(j)
+            for p_ in rng.sample(prev, min(len(prev), rng.choice([1, 1, 2]))):
+                edges.append([p_, j])
+        prev = cur
+    out.append({'name': 'stages26', 'tasks': tasks, 'edges': edges})
+    # sparse random DAG, 18 tasks
+    tasks, edges = [], []
+    for j in range(18):
+        tasks.append(task(j))
+        if j > 0:
+            lo = max(0, j - 4)
+            k = 1 if rng.random() < 0.6 else 2
+            for p_ in rng.sample(range(lo, j), min(k, j - lo)):
+                edges.append([p_, j])
+    out.append({'name': 'sparse18', 'tasks': tasks, 'edges': edges})
+    # two independent pipelines joined at the end, 22 tasks
+    tasks, edges = [], []
+    ends = []
+    for _ in range(2):
+        first = len(tasks)
+        for k in range(10):
+            tasks.append(task(len(tasks)))
+            if k:
+                edges.append([len(tasks) - 2, len(tasks) - 1])
+        edges.append([first + 2, first + 6])  # a skip connection
+        ends.append(len(tasks) - 1)
+    tasks += [task(len(tasks)), task(len(tasks) + 1)]
+    edges += [[ends[0], 20], [ends[1], 20], [20, 21]]
+    out.append({'name': 'join22', 'tasks': tasks, 'edges': edges})
     return out
 
 
@@ -971,6 +1048,9 @@ BIG_SUITES = {
     'cfg4_1m': cfg4_scenarios,
     'cfg5_50k': cfg5_scenarios,
 }
+
+# suites with their own tests (not part of the per-scenario sweeps)
+EXTRA_GOLDEN_SUITES = {'bigdag': big_dag_scenarios}
 
 ALL_SUITES = dict(SUITES, **LATE_SUITES)
 

@@ -291,6 +291,7 @@ def test_optimize_on_a_cache_loaded_catalog(tmp_path):
     for _ in range(2):  # first: parse + write the cache, second: cache hit
         store = CatalogStore.from_directory(str(tmp_path), clouds=names)
         sky.catalog.set_store(store)
+        sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
         dag, tasks = runner.build_dag(scenarios.basic_scenarios()[0])
         sky.Optimizer.optimize(dag, quiet=True)
         plans.append([runner.res_record(t.best_resources) for t in tasks])

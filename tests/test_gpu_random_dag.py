@@ -120,3 +120,26 @@ def test_standalone_dp_and_dag_search_match_the_fused_path(name):
         assert [key(plan[t]) for t in tasks] == [key(fused[t]) for t in tasks]
     finally:
         O._remove_dummy_source_sink_nodes(dag)
+
+
+@pytest.mark.parametrize('name', ['diamonds19', 'stages26', 'sparse18',
+                                  'join22'])
+def test_large_general_dag_matches_reference(name):
+    """General DAGs of 18-26 tasks: beyond the device enumeration, placed by
+    the exact elimination of dag_solver.py. The candidate tables and the
+    optimum are the reference's (tests/golden/bigdag.json: its tables, the
+    frontier DP of oracle/dag_oracle.py over them)."""
+    payload = runner.load_golden('bigdag')
+    assert payload['catalog'] == scenarios.CATALOGS['bigdag']
+    golden = next(r for r in payload['records'] if r['name'] == name)
+    sc = next(s for s in scenarios.big_dag_scenarios() if s['name'] == name)
+    runner.activate_catalog(payload['catalog'])
+    got = runner.run_scenario(sc)
+    assert 'error' not in got, got
+    # identical ordered candidate tables; the optimum within 1e-6 relative
+    # (plans among equal-cost optima are not compared)
+    plan_free = dict(golden)
+    plan_free['plan'] = got['plan']
+    diffs = runner.compare(plan_free, got)
+    assert not diffs, diffs
+    assert runner.close(got['objective'], golden['objective'])

@@ -421,7 +421,7 @@ def test_statement_memos_are_transparent(store):
         assert limited == _packed_bytes(_chain(specs2, num_nodes=3))
         assert set(limited[4]) <= {'aws', 'gcp'}
     finally:
-        sky.check.set_enabled_clouds(None)
+        sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
     full = _packed_bytes(dag)
     assert full == _packed_bytes(_chain(specs2, num_nodes=3))
     # dropping the memos changes nothing either

@@ -78,7 +78,7 @@ def _worker(rank, world, port, n_dags, out_path):
         sky.catalog.load_frames(
             synth.make_catalogs(seed=2, n_rows=3000,
                                 clouds=['aws', 'gcp', 'azure']))
-        sky.check.set_enabled_clouds(None)
+        sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
         dags = _make_dags(n_dags)
         mine = sharding.shard(dags, rank, world)
         local = [{'index': i, 'task': d.tasks[0].name}

@@ -5,7 +5,7 @@ import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import networkx as nx
-import bench
+from skypilot_b200 import workloads as bench
 from skypilot_b200 import synth, _native, engine
 from skypilot_b200.catalog.store import CatalogStore
 import skypilot_b200 as sky
@@ -19,6 +19,7 @@ scenario = bench.chain_scenario(w['tasks'])
 frames = synth.make_catalogs(**w['catalog'])
 store = CatalogStore.from_frames(frames)
 sky.catalog.set_store(store, 0)
+sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
 dag, tasks = runner.build_dag(scenario)
 Optimizer._add_dummy_source_sink_nodes(dag)
 graph = dag.get_graph()

@@ -57,6 +57,7 @@ def main_ranks(n: int, world: int) -> None:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     frames = synth.make_catalogs(1, 50000)
     store = sky.catalog.load_frames(frames, device=local)
+    sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
     store.handle(local)
     rows = synth.total_rows(frames)
     dags = make_dags(n)
@@ -93,6 +94,7 @@ def main():
     ngpu = int(sys.argv[2]) if len(sys.argv) > 2 else _native.device_count()
     frames = synth.make_catalogs(1, 50000)
     store = sky.catalog.load_frames(frames)
+    sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
     rows = synth.total_rows(frames)
     devices = list(range(ngpu))
     for d in devices:

@@ -7,7 +7,7 @@ import tempfile
 import time
 
 sys.path.insert(0, '.')
-import bench  # noqa: E402
+from skypilot_b200 import workloads as bench  # noqa: E402
 from skypilot_b200 import synth  # noqa: E402
 from skypilot_b200.catalog.store import CatalogStore  # noqa: E402
 

@@ -6,13 +6,14 @@ import sys
 import time
 
 sys.path.insert(0, '.')
-import bench  # noqa: E402
+from skypilot_b200 import workloads as bench  # noqa: E402
 import skypilot_b200 as sky  # noqa: E402
 from oracle import listing_oracle as lo  # noqa: E402
 from skypilot_b200 import synth  # noqa: E402
 
 frames = synth.make_catalogs(**bench.WORKLOADS['cfg2']['catalog'])
 store = sky.catalog.load_frames(frames)
+sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
 clouds = [t.name for t in store.clouds]
 CASES = [dict(), dict(all_regions=True, name_filter='A100'),
          dict(region_filter='us-', quantity_filter=8), dict(require_price=False)]

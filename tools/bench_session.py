@@ -7,7 +7,7 @@ import sys
 import time
 
 sys.path.insert(0, '.')
-import bench  # noqa: E402
+from skypilot_b200 import workloads as bench  # noqa: E402
 import skypilot_b200 as sky  # noqa: E402
 from skypilot_b200 import synth  # noqa: E402
 from skypilot_b200.utils import registry  # noqa: E402
@@ -16,6 +16,7 @@ from tests import scenario_runner as runner  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
 w = bench.WORKLOADS[name]
 sky.catalog.load_frames(synth.make_catalogs(**w['catalog']))
+sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
 scenario = bench.chain_scenario(w['tasks'])
 
 

@@ -4,7 +4,7 @@ import os
 import sys
 import numpy as np
 sys.path.insert(0, '.')
-import bench  # noqa: E402
+from skypilot_b200 import workloads as bench  # noqa: E402
 import networkx as nx  # noqa: E402
 import skypilot_b200 as sky  # noqa: E402
 from skypilot_b200 import engine, synth  # noqa: E402
@@ -14,6 +14,7 @@ from tests import scenario_runner as runner  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else 'cfg4'
 w = bench.WORKLOADS[name]
 store = sky.catalog.load_frames(synth.make_catalogs(**w['catalog']))
+sky.check.set_enabled_clouds(sky.check.ALL_CATALOG_CLOUDS)
 dag, tasks = runner.build_dag(bench.chain_scenario(w['tasks']))
 O = opt_lib.Optimizer
 O._add_dummy_source_sink_nodes(dag)
