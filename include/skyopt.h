@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SKYOPT_ABI_VERSION 2
+#define SKYOPT_ABI_VERSION 3
 
 /* error codes */
 #define SKYOPT_OK 0
@@ -197,6 +197,13 @@ typedef struct SkyoptSlot {
                            implied by the instance type (GCP); -1 = derive
                            from inst_acc_key; used by the blocked filter */
   int32_t use_spot;     /* for the blocked filter */
+  int32_t region_set;   /* allow-list of regions: index into acc_sets of a
+                           bitmask over the cloud's region ids (bit r = region
+                           r may be used), -1 = every region. Carries the
+                           filters of Resources.get_valid_regions_for_launchable
+                           (resources.py:1210-1246): the regions of a per-region
+                           image_id dict and of a per-region ssh_proxy_command */
+  int32_t pad_;
   double hours;         /* estimated_runtime / 3600 (optimizer.py:320-343) */
   double node_mult;     /* max(num_nodes - reserved, 0) (optimizer.py:353) */
   double time_value;    /* estimated_runtime, the TIME-mode value (:357) */

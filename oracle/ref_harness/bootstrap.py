@@ -83,10 +83,11 @@ def write_catalogs(home: str, catalogs: Dict[str, 'object'],
               'w',
               encoding='utf-8') as f:
         f.write('\n'.join(lines) + '\n')
-    with open(os.path.join(root, 'common', 'metadata.csv'),
-              'w',
-              encoding='utf-8') as f:
-        f.write('GPU,MemoryGB,Manufacturer\n')
+    # device memory table behind '32GB+' requests
+    # (sky/utils/accelerator_registry.py:39, :50-73)
+    from skypilot_b200 import synth  # pylint: disable=import-outside-toplevel
+    synth.accelerator_metadata().to_csv(
+        os.path.join(root, 'common', 'metadata.csv'), index=False)
 
 
 def import_reference(home: str, enabled_clouds: Sequence[str]):

@@ -70,12 +70,32 @@ def _resources_kwargs(sky, spec):
     return kwargs
 
 
+def _task_extras(task, tspec):
+    if 'outputs_gb' in tspec:
+        task.set_outputs(tspec.get('outputs', 'CLOUD://out'),
+                         estimated_size_gigabytes=tspec['outputs_gb'])
+    if 'inputs' in tspec:
+        task.set_inputs(tspec['inputs'][0],
+                        estimated_size_gigabytes=tspec['inputs'][1])
+    if 'time_est' in tspec:
+        task.set_time_estimator(_make_time_estimator(tspec['time_est']))
+
+
 def build_dag(sky, scenario):
     tasks = []
     with sky.Dag() as dag:
         for i, tspec in enumerate(scenario['tasks']):
             task = sky.Task(name=tspec.get('name', f't{i}'),
                             num_nodes=tspec.get('num_nodes', 1))
+            if 'resources_yaml' in tspec:
+                # request alternatives the way a task YAML states them
+                # (sky/resources.py:2264-2411)
+                import copy as _copy
+                task.set_resources(sky.Resources.from_yaml_config(
+                    _copy.deepcopy(tspec['resources_yaml'])))
+                tasks.append(task)
+                _task_extras(task, tspec)
+                continue
             res = [
                 sky.Resources(**_resources_kwargs(sky, r))
                 for r in tspec['resources']
@@ -91,15 +111,7 @@ def build_dag(sky, scenario):
                 # address order (reference sky/task.py:1292-1312); the harness
                 # records the realised order next to the candidates.
                 task.set_resources(set(res))
-            if 'outputs_gb' in tspec:
-                task.set_outputs(tspec.get('outputs', 'CLOUD://out'),
-                                 estimated_size_gigabytes=tspec['outputs_gb'])
-            if 'inputs' in tspec:
-                task.set_inputs(tspec['inputs'][0],
-                                estimated_size_gigabytes=tspec['inputs'][1])
-            if 'time_est' in tspec:
-                task.set_time_estimator(_make_time_estimator(
-                    tspec['time_est']))
+            _task_extras(task, tspec)
             tasks.append(task)
         for u, v in scenario.get('edges', []):
             dag.add_edge(tasks[u], tasks[v])
@@ -219,6 +231,15 @@ def run_job_group(sky, scenario):
 
 
 def run_scenario(sky, scenario):
+    if scenario.get('config') is not None and not scenario.get('_in_config'):
+        # a SkyPilot config for this scenario only (e.g. a per-region
+        # ssh_proxy_command: sky/resources.py:1210-1246)
+        from sky import skypilot_config
+        from sky.utils import config_utils
+        inner = dict(scenario, _in_config=True)
+        with skypilot_config.replace_skypilot_config(
+                config_utils.Config.from_dict(scenario['config'])):
+            return run_scenario(sky, inner)
     if scenario.get('kind') == 'list_accelerators':
         return run_listing(sky, scenario)
     if scenario.get('kind') == 'job_group':
@@ -239,7 +260,8 @@ def run_scenario(sky, scenario):
     record['is_chain'] = bool(is_chain)
 
     has_list = any(
-        t.get('resources_kind') == 'list' for t in scenario['tasks'])
+        t.get('resources_kind') == 'list' or isinstance(tk.resources, list)
+        for t, tk in zip(scenario['tasks'], tasks))
     if has_list:
         # Ordered resources are resolved by _optimize_dag's pre-pass
         # (sky/optimizer.py:1403-1448); only the end-to-end plan is recorded.

@@ -11,7 +11,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACC_SET_WORDS = 32
 MAX_CLOUDS = 32
 NONE16 = 0xFFFF
@@ -64,6 +64,7 @@ SLOT_DTYPE = np.dtype([
     ('gate_query', '<i4'), ('acc_set', '<i4'), ('price_col', '<i4'),
     ('region_id', '<i4'), ('zone_id', '<i4'), ('split_by_zone', '<i4'),
     ('us_first', '<i4'), ('cand_acc_key', '<i4'), ('use_spot', '<i4'),
+    ('region_set', '<i4'), ('pad_', '<i4'),
     ('hours', '<f8'), ('node_mult', '<f8'), ('time_value', '<f8'),
 ], align=True)
 
@@ -100,7 +101,7 @@ DAG_RESULT_DTYPE = np.dtype([
 ], align=True)
 
 _EXPECTED_SIZES = {
-    'query': 88, 'scan_result': 32, 'slot': 72, 'blocked': 24, 'task': 24,
+    'query': 88, 'scan_result': 32, 'slot': 80, 'blocked': 24, 'task': 24,
     'dag': 24, 'candidate': 32, 'dag_result': 16
 }
 assert QUERY_DTYPE.itemsize == _EXPECTED_SIZES['query'], QUERY_DTYPE.itemsize
@@ -181,6 +182,10 @@ _lib_lock = threading.Lock()
 
 
 def library_path() -> str:
+    # SKYOPT_LIBRARY: another build of the same sources (kernel tuning A/B)
+    override = os.environ.get('SKYOPT_LIBRARY')
+    if override:
+        return os.path.abspath(override)
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 

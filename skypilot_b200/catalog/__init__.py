@@ -72,12 +72,19 @@ def get_device() -> int:
 
 
 def view(cloud: str):
-    from skypilot_b200.catalog import common  # pylint: disable=import-outside-toplevel
     store = get_store()
-    if not store.has_cloud(cloud):
-        raise ValueError(f'cloud {cloud!r} is not in the loaded catalog '
-                         f'{[t.name for t in store.clouds]}')
-    return common.CatalogView(store, cloud.lower(), device=_device)
+    # one view object per (store, cloud, device): it only holds references
+    views = store.__dict__.setdefault('_views', {})
+    key = (cloud, _device)
+    v = views.get(key)
+    if v is None:
+        from skypilot_b200.catalog import common  # pylint: disable=import-outside-toplevel
+        if not store.has_cloud(cloud):
+            raise ValueError(f'cloud {cloud!r} is not in the loaded catalog '
+                             f'{[t.name for t in store.clouds]}')
+        v = common.CatalogView(store, cloud.lower(), device=_device)
+        views[key] = v
+    return v
 
 
 def module_for(cloud: str):
@@ -217,3 +224,23 @@ def get_region_zones_for_accelerators(acc_name, acc_count, use_spot,
                                       clouds=None):
     return _map_clouds_catalog(clouds, 'get_region_zones_for_accelerators',
                                acc_name, acc_count, use_spot)
+
+
+def check_accelerator_attachable_to_host(instance_type: str, accelerators,
+                                         zone: Optional[str] = None,
+                                         clouds=None) -> None:
+    """GCP only: can the accelerators be attached to the host VM
+    (sky/catalog/__init__.py:326-338)."""
+    _map_clouds_catalog(clouds, 'check_accelerator_attachable_to_host',
+                        instance_type, accelerators, zone)
+
+
+def get_image_id_from_tag(tag: str, region: Optional[str] = None,
+                          clouds=None):
+    """sky/catalog/__init__.py:372-376."""
+    return _map_clouds_catalog(clouds, 'get_image_id_from_tag', tag, region)
+
+
+def is_image_tag_valid(tag: str, region: Optional[str], clouds=None) -> bool:
+    """sky/catalog/__init__.py:379-383."""
+    return _map_clouds_catalog(clouds, 'is_image_tag_valid', tag, region)

@@ -148,3 +148,22 @@ class CloudCatalog:
                                        name_filter, region_filter,
                                        quantity_filter, case_sensitive,
                                        all_regions)
+
+    # -- images.csv ------------------------------------------------------
+    def _images(self):
+        import pandas as pd  # pylint: disable=import-outside-toplevel
+        from skypilot_b200 import catalog  # pylint: disable=import-outside-toplevel
+        df = catalog.get_store().images.get(self.cloud)
+        if df is None:
+            df = pd.DataFrame(columns=['Tag', 'Region', 'ImageId'])
+        return df
+
+    def get_image_id_from_tag(self, tag: str,
+                              region: Optional[str] = None) -> Optional[str]:
+        """sky/catalog/<cloud>_catalog.get_image_id_from_tag (the reference
+        re-downloads images.csv once when the tag is unknown; here the table
+        is whatever the catalog directory holds)."""
+        return common.get_image_id_from_tag_impl(self._images(), tag, region)
+
+    def is_image_tag_valid(self, tag: str, region: Optional[str]) -> bool:
+        return common.is_image_tag_valid_impl(self._images(), tag, region)

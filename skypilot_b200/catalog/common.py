@@ -374,3 +374,31 @@ def validate_region_zone_impl(
                              _candidates(zone, pool))
         valid_region = table.region_names[table.zone_region[zone_id]]
     return valid_region, valid_zone
+
+
+def get_image_id_from_tag_impl(df: pd.DataFrame, tag: str,
+                               region: Optional[str]) -> Optional[str]:
+    """The image id of `tag` in `region` (sky/catalog/common.py:813-831):
+    with region None the tag must name a single image; None when nothing
+    matches or the id is missing."""
+    df = df[df['Tag'] == tag]
+    if region is not None:
+        df = df[df['Region'].str.lower() == region.lower()]
+    assert len(df) <= 1, ('Multiple images found for tag '
+                          f'{tag} in region {region}')
+    if df.empty:
+        return None
+    image_id = df['ImageId'].iloc[0]
+    if pd.isna(image_id):
+        return None
+    return image_id
+
+
+def is_image_tag_valid_impl(df: pd.DataFrame, tag: str,
+                            region: Optional[str]) -> bool:
+    """sky/catalog/common.py:834-840."""
+    df = df[df['Tag'] == tag]
+    if region is not None:
+        df = df[df['Region'].str.lower() == region.lower()]
+    df = df.dropna(subset=['ImageId'])
+    return not df.empty

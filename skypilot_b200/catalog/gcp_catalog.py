@@ -160,3 +160,91 @@ def list_accelerators(gpus_only: bool, name_filter: Optional[str] = None,
                                region_filter, quantity_filter, case_sensitive,
                                all_regions, require_price)
 
+
+
+def check_accelerator_attachable_to_host(instance_type: str,
+                                         accelerators: Optional[Dict[str, int]],
+                                         zone: Optional[str] = None) -> None:
+    """Can the accelerators be attached to this host VM? The documented
+    limits of GCP (host families of A100 / L4 / H100 ..., valid counts,
+    maximum vCPUs and memory of the N1 host per accelerator count):
+    sky/catalog/gcp_catalog.py:584-683, same checks in the same order, same
+    messages. Raises exceptions.ResourcesMismatchError."""
+    from skypilot_b200 import exceptions  # pylint: disable=import-outside-toplevel
+    if accelerators is None:
+        if instance_type in rules.GCP_INSTANCE_TO_ACC:
+            accelerators = rules.GCP_INSTANCE_TO_ACC[instance_type]
+        else:
+            return
+    acc = list(accelerators.items())
+    assert len(acc) == 1, acc
+    acc_name, acc_count = acc[0]
+    if not list_accelerators(gpus_only=False, name_filter=acc_name):
+        raise exceptions.ResourcesMismatchError(
+            f'{acc_name} is not available in GCP. '
+            'See \'sky gpus list --cloud gcp\'')
+    if acc_name.startswith('tpu-'):
+        if instance_type != 'TPU-VM' and not instance_type.startswith('n1-'):
+            raise exceptions.ResourcesMismatchError(
+                'TPU Nodes can be only used with N1 machines. '
+                'Please refer to: '
+                'https://cloud.google.com/compute/docs/general-purpose-machines#n1_machines')  # pylint: disable=line-too-long
+        return
+    fixed = rules.GCP_FIXED_HOSTS
+    limits = rules.GCP_ACC_MAX_CPU_MEM
+    if acc_name in fixed:
+        matching_types = fixed[acc_name].get(acc_count)
+        if matching_types is None:
+            raise KeyError(acc_count)  # as the reference's dict look-up does
+        if instance_type not in matching_types:
+            raise exceptions.ResourcesMismatchError(
+                f'{acc_name} GPUs cannot be attached to {instance_type}. '
+                f'Use one of {matching_types} instead. Please refer to '
+                'https://cloud.google.com/compute/docs/gpus')
+    elif not instance_type.startswith('n1-'):
+        raise exceptions.ResourcesMismatchError(
+            f'{acc_name} GPUs cannot be attached to {instance_type}. '
+            'Use N1 instance types instead. Please refer to: '
+            'https://cloud.google.com/compute/docs/machine-types#gpus')
+    if acc_name in fixed:
+        valid_counts = list(fixed[acc_name].keys())
+    else:
+        assert acc_name in limits, acc_name
+        valid_counts = list(limits[acc_name].keys())
+    if acc_count not in valid_counts:
+        raise exceptions.ResourcesMismatchError(
+            f'{acc_name}:{acc_count} is not launchable on GCP. '
+            f'The valid {acc_name} counts are {valid_counts}.')
+    if acc_name in fixed:
+        max_cpus, max_memory = get_vcpus_mem_from_instance_type(instance_type)
+    else:
+        max_cpus, max_memory = limits[acc_name][acc_count]
+        if acc_name == 'K80' and acc_count == 8:
+            if zone in ['asia-east1-a', 'us-east1-d']:
+                max_memory = 416
+        elif acc_name == 'P100' and acc_count == 4:
+            if zone in ['us-east1-c', 'europe-west1-d', 'europe-west1-b']:
+                max_cpus = 64
+                max_memory = 208
+    num_cpus, memory = get_vcpus_mem_from_instance_type(instance_type)
+    if num_cpus > max_cpus:
+        raise exceptions.ResourcesMismatchError(
+            f'{acc_name}:{acc_count} cannot be attached to '
+            f'{instance_type}. The maximum number of vCPUs is {max_cpus}. '
+            'Please refer to: https://cloud.google.com/compute/docs/gpus')
+    if memory > max_memory:
+        raise exceptions.ResourcesMismatchError(
+            f'{acc_name}:{acc_count} cannot be attached to '
+            f'{instance_type}. The maximum CPU memory is {max_memory} GB. '
+            'Please refer to: https://cloud.google.com/compute/docs/gpus')
+
+
+def get_image_id_from_tag(tag: str, region: Optional[str] = None
+                         ) -> Optional[str]:
+    return _impl.get_image_id_from_tag(tag, region)
+
+
+def is_image_tag_valid(tag: str, region: Optional[str]) -> bool:
+    """GCP images are not region-specific (gcp_catalog.py:699-704)."""
+    del region
+    return get_image_id_from_tag(tag, None) is not None

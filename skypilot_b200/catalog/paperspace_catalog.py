@@ -15,3 +15,5 @@ get_local_disk_from_instance_type = _impl.get_local_disk_from_instance_type
 get_instance_type_for_accelerator = _impl.get_instance_type_for_accelerator
 get_region_zones_for_instance_type = _impl.get_region_zones_for_instance_type
 list_accelerators = _impl.list_accelerators
+get_image_id_from_tag = _impl.get_image_id_from_tag
+is_image_tag_valid = _impl.is_image_tag_valid

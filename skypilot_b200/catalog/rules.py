@@ -172,6 +172,15 @@ GCP_ACC_HOST_CPUS: Dict[str, Dict[int, int]] = {
     'DEFAULT': {1: 8, 2: 16, 4: 32, 8: 64, 16: 128},
 }
 GCP_GPU_MEMORY_CPU_RATIO = 4
+# accelerator -> count -> (max vCPUs, max memory GB) of the N1 host it can be
+# attached to (gcp_catalog.py:186-217; https://cloud.google.com/compute/docs/gpus)
+GCP_ACC_MAX_CPU_MEM: Dict[str, Dict[int, Tuple[int, int]]] = {
+    'K80': {1: (8, 52), 2: (16, 104), 4: (32, 208), 8: (64, 208)},
+    'V100': {1: (12, 78), 2: (24, 156), 4: (48, 312), 8: (96, 624)},
+    'T4': {1: (48, 312), 2: (48, 312), 4: (96, 624)},
+    'P4': {1: (24, 156), 2: (48, 312), 4: (96, 624)},
+    'P100': {1: (16, 104), 2: (32, 208), 4: (96, 624)},
+}
 
 
 def _gcp_default(instance_type: str) -> bool:

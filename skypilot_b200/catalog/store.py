@@ -137,6 +137,10 @@ class CatalogStore:
         self._lock = threading.Lock()
         self._keepalive: List[np.ndarray] = []
         self._sessions = weakref.WeakSet()  # open engine.Session objects
+        # <cloud>/images.csv (Tag, Region, ImageId, ...): a few rows, host only
+        self.images: Dict[str, pd.DataFrame] = {}
+        # common/metadata.csv (GPU, MemoryGB, Manufacturer): '32GB+' requests
+        self.metadata: Optional[pd.DataFrame] = None
 
     # ------------------------------------------------------------------ build
     @classmethod
@@ -460,7 +464,9 @@ class CatalogStore:
             cache_dir = os.path.join(path, '.skyopt_cache', key)
             if os.path.exists(os.path.join(cache_dir, 'meta.json')):
                 try:
-                    return cls.load(cache_dir)
+                    store = cls.load(cache_dir)
+                    store.load_images(path)
+                    return store
                 except Exception:  # pylint: disable=broad-except
                     # unreadable / corrupt cache (zipfile.BadZipFile, a
                     # truncated parquet, ...): parse the CSVs again
@@ -468,6 +474,7 @@ class CatalogStore:
                     shutil.rmtree(cache_dir, ignore_errors=True)
         frames = {name: pd.read_csv(csv) for name, csv in files}
         store = cls.from_frames(frames, order=list(frames.keys()))
+        store.load_images(path)
         if cache_dir is not None:
             try:
                 store.save(cache_dir)
@@ -701,6 +708,25 @@ class CatalogStore:
                 'fast-split-noprune': 9}[mode]
         _native.check(_native.load().skyopt_catalog_set_scan_mode(
             self.handle(device), code))
+
+    def load_images(self, path: str) -> None:
+        """`<path>/<cloud>/images.csv` of every loaded cloud (the reference
+        reads them with read_catalog('<cloud>/images.csv'),
+        sky/catalog/aws_catalog.py:355-372)."""
+        for t in self.clouds:
+            csv = os.path.join(path, t.name, 'images.csv')
+            if os.path.exists(csv):
+                self.images[t.name] = pd.read_csv(csv)
+        meta = os.path.join(path, 'common', 'metadata.csv')
+        if os.path.exists(meta):
+            self.metadata = pd.read_csv(meta)
+
+    def set_accelerator_metadata(self, frame: pd.DataFrame) -> None:
+        """GPU / MemoryGB / Manufacturer rows (common/metadata.csv)."""
+        self.metadata = frame.reset_index(drop=True)
+
+    def set_images(self, cloud: str, frame: pd.DataFrame) -> None:
+        self.images[cloud.lower()] = frame.reset_index(drop=True)
 
     def register_session(self, session) -> None:
         self._sessions.add(session)

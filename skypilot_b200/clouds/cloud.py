@@ -20,6 +20,21 @@ from skypilot_b200 import exceptions
 from skypilot_b200.utils import resources_utils
 
 
+_LATE: Dict[str, Any] = {}
+
+
+def _late(name: str):
+    """A sibling module that imports this one (resolved on first use; a
+    function-level `from ... import` costs a microsecond per call and these
+    sit in the per-request statement path)."""
+    mod = _LATE.get(name)
+    if mod is None:
+        import importlib  # pylint: disable=import-outside-toplevel
+        mod = importlib.import_module(f'skypilot_b200.{name}')
+        _LATE[name] = mod
+    return mod
+
+
 class CloudImplementationFeatures(enum.Enum):
     STOP = 'stop'
     MULTI_NODE = 'multi-node'
@@ -104,18 +119,15 @@ class Cloud:
     # ---- catalog plumbing ---------------------------------------------------
     @classmethod
     def _view(cls):
-        from skypilot_b200 import catalog  # pylint: disable=import-outside-toplevel
-        return catalog.view(cls._CATALOG)
+        return _late('catalog').view(cls._CATALOG)
 
     @classmethod
     def _rules(cls):
-        from skypilot_b200.catalog import rules  # pylint: disable=import-outside-toplevel
-        return rules.rules_for(cls._CATALOG)
+        return _late('catalog.rules').rules_for(cls._CATALOG)
 
     @classmethod
     def _catalog_module(cls):
-        from skypilot_b200 import catalog  # pylint: disable=import-outside-toplevel
-        return catalog.module_for(cls._CATALOG)
+        return _late('catalog').module_for(cls._CATALOG)
 
     # ---- regions / zones ----------------------------------------------------
     @classmethod
@@ -244,7 +256,7 @@ class Cloud:
         """Offerings of this cloud that satisfy `resources`
         (sky/clouds/cloud.py:459-501): feature gate, then the catalog filter
         -- here one `skyopt_scan` call instead of pandas passes."""
-        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        engine = _late('engine')
         hint = self._feature_hint(resources, num_nodes)
         if hint is not None:
             return resources_utils.FeasibleResources([], [], hint)
@@ -277,7 +289,7 @@ class Cloud:
 
     def _feasible_from_scan(self, view, plan: SlotPlan, out,
                             resources) -> resources_utils.FeasibleResources:
-        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        engine = _late('engine')
         fuzzy: List[str] = []
         gate = plan.gate_query if plan.gate_query is not None else (
             plan.fuzzy_query)
@@ -313,7 +325,8 @@ class Cloud:
                 r.local_disk, r.max_hourly_cost,
                 None if r.image_id is None else tuple(sorted(
                     (str(k), v) for k, v in r.image_id.items())),
-                None if r.ports is None else tuple(r.ports))
+                None if r.ports is None else tuple(r.ports),
+                _late('skypilot_config').generation())
 
     def plan_cached(self, builder, resources: Any,
                     num_nodes: int = 1) -> Tuple[SlotPlan, Optional[int]]:
@@ -335,7 +348,7 @@ class Cloud:
             resources.__dict__['_plan_templates'] = local
         tmpl = local[1].get((self.__class__, multi))
         if tmpl is None:
-            from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+            engine = _late('engine')
             cache = store.__dict__.setdefault('_plan_cache', {})
             rkey = resources.__dict__.get('_request_key')
             if rkey is None:
@@ -380,7 +393,8 @@ class Cloud:
             region_id=_exact_region(table, resources.region),
             zone_id=_exact_zone(table, resources.zone),
             split_by_zone=int(by_zone), us_first=int(rules.us_regions_first),
-            use_spot=int(use_spot))
+            use_spot=int(use_spot),
+            region_words=region_allow_words(table, resources, self))
 
         if resources.instance_type is not None:
             ok, _ = self.check_disk_tier(resources.instance_type,
@@ -468,12 +482,12 @@ class Cloud:
 
 
 def _exact_region(table, region: Optional[str]) -> int:
-    from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+    engine = _late('engine')
     return engine.region_exact_id(table, region)
 
 
 def _exact_zone(table, zone: Optional[str]) -> int:
-    from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+    engine = _late('engine')
     return engine.zone_exact_id(table, zone)
 
 
@@ -484,3 +498,28 @@ class DummyCloud(Cloud):
 
 def cloud_in_iterable(cloud: Cloud, cloud_list: Iterable[Cloud]) -> bool:
     return any(cloud.is_same_cloud(c) for c in cloud_list)
+
+
+def region_allow_words(table, resources: Any, cloud_obj: Any):
+    """Bitmask over the cloud's region ids of the regions a launchable of
+    `resources` on this cloud may use, or None (every region): the per-region
+    `image_id` dict and the per-region `ssh_proxy_command` of the SkyPilot
+    config (Resources.get_valid_regions_for_launchable,
+    sky/resources.py:1210-1246)."""
+    import numpy as np  # pylint: disable=import-outside-toplevel
+    names = None
+    image_id = resources.image_id
+    if image_id is not None and None not in image_id:
+        names = set(image_id.keys())
+    by_proxy = _late('skypilot_config').allowed_regions_by_ssh_proxy(
+        str(cloud_obj).lower())
+    if by_proxy is not None:
+        names = by_proxy if names is None else names & by_proxy
+    if names is None:
+        return None
+    words = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
+    for name in names:
+        rid = table.region_exact.get(name)
+        if rid is not None and rid < 32 * _native.ACC_SET_WORDS:
+            words[rid >> 5] |= np.uint32(1 << (rid & 31))
+    return words

@@ -101,7 +101,7 @@ class GCP(cloud.Cloud):
 
     def plan_feasible(self, builder, resources: Any,
                       want_list: bool = False) -> cloud.SlotPlan:
-        from skypilot_b200 import engine  # pylint: disable=import-outside-toplevel
+        engine = cloud._late('engine')  # pylint: disable=protected-access
         view = self._view()
         table = view.table
         store = view.store
@@ -111,7 +111,8 @@ class GCP(cloud.Cloud):
             cloud=table.index, price_col=1 if use_spot else 0,
             region_id=engine.region_exact_id(table, resources.region),
             zone_id=engine.zone_exact_id(table, resources.zone),
-            split_by_zone=1, us_first=0, use_spot=int(use_spot))
+            split_by_zone=1, us_first=0, use_spot=int(use_spot),
+            region_words=cloud.region_allow_words(table, resources, self))
 
         def acc_slot_fields(acc: str, count) -> Dict[str, Any]:
             _, _, strict = engine.accelerator_sets(store, acc, count)

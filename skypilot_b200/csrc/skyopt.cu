@@ -4,6 +4,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo
 //        -fmad=false -shared -Xcompiler -fPIC  (see __graft_entry__.build()).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -48,6 +49,13 @@ int fail(int code, const char *fmt, ...) {
       return fail(SKYOPT_ECUDA, "%s failed: %s (%s:%d)", #expr,             \
                   cudaGetErrorString(e_), __FILE__, __LINE__);              \
   } while (0)
+
+// NVTX range around a native entry point (shows up in Nsight timelines next
+// to the host events of skypilot_b200/utils/timeline.py).
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -294,6 +302,7 @@ int validate_problem(const SkyoptCatalog *cat, const SkyoptProblem *pb) {
     if (s.query < 0 && s.inst_id < -2) return fail(SKYOPT_EINVAL, "slot %d: no instance type", i);
     if (s.inst_id >= cat->dev.n_inst) return fail(SKYOPT_EINVAL, "slot %d: instance id out of range", i);
     if (s.acc_set >= pb->n_acc_sets) return fail(SKYOPT_EINVAL, "slot %d: accelerator set out of range", i);
+    if (s.region_set >= pb->n_acc_sets) return fail(SKYOPT_EINVAL, "slot %d: region set out of range", i);
     if (s.query < 0 && s.inst_id == -1) return fail(SKYOPT_EINVAL, "slot %d: neither query nor instance", i);
   }
   for (int i = 0; i < pb->n_tasks; ++i) {
@@ -435,6 +444,8 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   // pieces of consecutive 128-row chunks for a persistent grid
   std::vector<Scan2Group> groups2;
   std::vector<int> order2;  // scan order -> caller's query index
+  std::vector<char> gate_used(std::max(P.nq, 1), 0);
+  for (int sl = 0; sl < P.ns; ++sl) if (pb->slots[sl].gate_query >= 0) gate_used[pb->slots[sl].gate_query] = 1;
   if (P.fast) {
     long long visits = 0;
     for (int c = 0; c < C; ++c)
@@ -449,7 +460,8 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
           G.cm_off = cat->cm_off[c]; G.fa_off = cat->fa_off[c]; G.rz_off = cat->rz_off[c];
           G.chunk0 = cat->cloud_row_offsets[c] / kZoneRows;
           G.n_chunks = cat->cloud_row_offsets[c + 1] / kZoneRows - G.chunk0;
-          for (int k = 0; k < G.q_count; ++k) order2.push_back(qs[b + k]);
+          for (int k = 0; k < G.q_count; ++k) { order2.push_back(qs[b + k]); if (gate_used[qs[b + k]]) G.need_any = 1; }
+          if (P.ns == 0) G.need_any = 1;  // skyopt_scan: every result carries any_stage1
           if (G.n_chunks > 0) groups2.push_back(G);
           visits += G.n_chunks;
           P.cap_fa = std::max(P.cap_fa, (uint32_t)G.n_fa); P.cap_cm = std::max(P.cap_cm, (uint32_t)G.n_cm);
@@ -463,8 +475,12 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
     {
       static std::mutex occ_mu;
       std::lock_guard<std::mutex> g(occ_mu);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel, kScanThreads, P.step_smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
+      // the separate-launch scan (4 blocks of 61 registers per SM) has more
+      // resident blocks than the fused kernel (3)
+      const cudaError_t oe = cat->split
+          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan2_kernel, kScanThreads, P.scan2_smem)
+          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel, kScanThreads, P.step_smem);
+      if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
     }
     static const int grid_cap = [] { const char *e = getenv("SKYOPT_SCAN2_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     if (grid_cap > 0) per_sm = std::min(per_sm, grid_cap);
@@ -735,6 +751,7 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
   }
   static const bool noprune_env = [] { const char *e = getenv("SKYOPT_NOPRUNE"); return e && atoi(e) != 0; }();
   sa.noprune = (noprune_env || cat->noprune) ? 1u : 0u;
+  sa.force_any = (want_scan_results || !solve) ? 1u : 0u;
   ExpandOut ex0{P.slot_count, P.slot_inst, P.cand_region, P.cand_zone, P.cand_pa, P.cand_pb};
   SolveIn in0{P.slots, P.tasks, P.parents, P.tariffs, P.blocked, P.dags, P.slot_off, P.task_off, ex0, 0};
   SolveWork w0{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
@@ -1041,6 +1058,7 @@ int skyopt_device_count(int *count) {
 }
 
 int skyopt_catalog_create(const SkyoptCatalogDesc *d, int device, SkyoptCatalog **out) {
+  NvtxRange nvtx_("skyopt_catalog_create");
   if (!d || !out) return fail(SKYOPT_EINVAL, "NULL argument");
   *out = nullptr;
   if (d->n_rows <= 0 || d->n_rows % kZoneRows != 0) return fail(SKYOPT_EINVAL, "n_rows must be a positive multiple of 128");
@@ -1279,6 +1297,7 @@ int skyopt_list_offerings(SkyoptCatalog *cat, int cloud, int by_acc_key,
                           const int32_t *group_ids, int n_groups,
                           const uint32_t *region_mask, int per_region,
                           int32_t *out_rows) {
+  NvtxRange nvtx_("skyopt_list_offerings");
   if (!cat || !group_ids || !out_rows || n_groups <= 0) return fail(SKYOPT_EINVAL, "bad arguments");
   if (cloud < 0 || cloud >= cat->dev.n_clouds) return fail(SKYOPT_EINVAL, "cloud %d out of range", cloud);
   const int n_max = by_acc_key ? cat->dev.n_acc_keys : cat->dev.n_inst;
@@ -1324,6 +1343,7 @@ int skyopt_scan(SkyoptCatalog *cat, const SkyoptQuery *queries, int n_queries,
                 int32_t *list_ids, double *list_prices, int list_cap,
                 int32_t *fuzzy_keys, double *fuzzy_prices, int fuzzy_cap,
                 SkyoptStats *stats) {
+  NvtxRange nvtx_("skyopt_scan");
   if (!cat || !queries || !results || n_queries <= 0) return fail(SKYOPT_EINVAL, "bad arguments");
   if (list_cap > 2048 || fuzzy_cap > 2048) return fail(SKYOPT_ELIMIT, "list capacity is limited to 2048 entries");
   SkyoptProblem pb{};
@@ -1386,6 +1406,7 @@ int skyopt_scan(SkyoptCatalog *cat, const SkyoptQuery *queries, int n_queries,
 
 int skyopt_optimize(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution *sol,
                     SkyoptStats *stats) {
+  NvtxRange nvtx_("skyopt_optimize");
   if (!cat || !pb || !sol) return fail(SKYOPT_EINVAL, "NULL argument");
   if (pb->n_dags <= 0 || pb->n_tasks <= 0 || pb->n_slots <= 0)
     return fail(SKYOPT_EINVAL, "empty problem");
@@ -1427,6 +1448,7 @@ struct SkyoptSession {
 
 int skyopt_session_open(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolution *sol,
                         SkyoptStats *stats, SkyoptSession **out) {
+  NvtxRange nvtx_("skyopt_session_open");
   if (!cat || !pb || !sol || !out) return fail(SKYOPT_EINVAL, "NULL argument");
   *out = nullptr;
   if (pb->n_dags <= 0 || pb->n_tasks <= 0 || pb->n_slots <= 0)
@@ -1467,6 +1489,7 @@ int skyopt_session_open(SkyoptCatalog *cat, const SkyoptProblem *pb, SkyoptSolut
 
 int skyopt_session_resolve(SkyoptSession *s, const SkyoptBlocked *blocked, int n_blocked,
                            SkyoptSolution *sol, SkyoptStats *stats) {
+  NvtxRange nvtx_("skyopt_session_resolve");
   if (!s || !sol || n_blocked < 0 || (n_blocked > 0 && !blocked)) return fail(SKYOPT_EINVAL, "bad arguments");
   SkyoptCatalog *cat = s->cat;
   Ctx *x = s->x;
@@ -1536,6 +1559,7 @@ int skyopt_solve_tables(SkyoptCatalog *cat, const double *values, const int32_t 
                         const int32_t *parents, int n_parents, const double *tariffs,
                         int n_tariffs, const SkyoptDag *dags, int n_dags,
                         int32_t *chosen_index, SkyoptDagResult *results) {
+  NvtxRange nvtx_("skyopt_solve_tables");
   if (!cat || !values || !clouds || !task_offsets || !tasks || !dags || !chosen_index || !results ||
       n_tasks <= 0 || n_dags <= 0)
     return fail(SKYOPT_EINVAL, "bad arguments");

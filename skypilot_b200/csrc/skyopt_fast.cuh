@@ -104,7 +104,8 @@ struct Scan2Group {
   int32_t cm_off, fa_off, rz_off; // into the class dictionaries
   int32_t chunk0, n_chunks;       // the cloud's 128-row chunks
   int32_t piece0, n_pieces;       // the group's share of the launch's pieces
-  int32_t index, pad_;            // position in the launch's group array
+  int32_t index;                  // position in the launch's group array
+  int32_t need_any;               // some query of the group wants any_stage1
 };
 
 struct Scan2Args {
@@ -117,6 +118,7 @@ struct Scan2Args {
   uint32_t *any1;                 // [n_queries] any_stage1
   int32_t *zero_flag;
   uint32_t noprune;               // 1: ignore the zone map and the bound
+  uint32_t force_any;             // the caller reads any_stage1 of every query
   uint32_t cap_fa, cap_cm, cap_rz;  // shared-memory capacities (entries)
   // cooperative launch only: the blocks of a group build its tables together
   // (one slice each) in `shared_tables` and wait on `group_ready`
@@ -127,17 +129,59 @@ struct Scan2Args {
   Scan2Group inline_groups[kInlineGroups2];
 };
 
-// out(lane q) bit l = in(lane l) bit q
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+// 32x32 bit transpose over the warp: out(lane q) bit l = in(lane l) bit q.
+// Five block-swap steps; in step j a lane keeps the half of its bits that
+// already sits in the right block and takes the other half from lane ^ j,
+// shifted by j -- as a rotation, so that both directions are one funnel shift
+// and the merge one LOP3: three instructions per step. The per-lane masks and
+// rotation amounts are computed once per kernel.
+struct TransposeLane {
+  uint32_t keep[5];
+  uint32_t rot[5];
+};
+__device__ __forceinline__ TransposeLane transpose_lane(int lane) {
+  TransposeLane t;
 #pragma unroll
-  for (int j = 16; j >= 1; j >>= 1) {
+  for (int i = 0; i < 5; ++i) {
+    const int j = 16 >> i;
     const uint32_t m = (j == 16) ? 0x0000FFFFu : (j == 8) ? 0x00FF00FFu
                      : (j == 4) ? 0x0F0F0F0Fu : (j == 2) ? 0x33333333u : 0x55555555u;
-    const uint32_t t = __shfl_xor_sync(0xFFFFFFFFu, x, j);
-    x = (lane & j) ? ((x & ~m) | ((t & ~m) >> j)) : ((x & m) | ((t & m) << j));
+    // lanes with bit j clear keep the bits with bit j clear and take the
+    // partner's low-block bits shifted up; the others the mirror image
+    t.keep[i] = (lane & j) ? ~m : m;
+    t.rot[i] = (lane & j) ? (uint32_t)(32 - j) : (uint32_t)j;
+  }
+  return t;
+}
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const TransposeLane &t) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const uint32_t p = __shfl_xor_sync(0xFFFFFFFFu, x, 16 >> i);
+    const uint32_t r = __funnelshift_l(p, p, t.rot[i]);
+    x = (x & t.keep[i]) | (r & ~t.keep[i]);
   }
   return x;
 }
+
+#ifndef SKYOPT_RING_DEPTH
+#define SKYOPT_RING_DEPTH 3
+#endif
+constexpr int kRingDepth = SKYOPT_RING_DEPTH;   // chunk slots per warp (cp.async ring)
+struct RingSlot {
+  uint32_t rk[kZoneRows];
+  uint16_t cm[kZoneRows], fa[kZoneRows], rz[kZoneRows];
+};
+static_assert(sizeof(RingSlot) == 10 * kZoneRows, "ring slot = one chunk of the 10 B/row layout");
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct Rows2 {
   uint4 rk;       // ranks of positions 4*lane .. 4*lane+3 (ascending)
@@ -173,6 +217,16 @@ __device__ __forceinline__ Rows2 load_rows2(const Scan2Args &a, int col, int64_t
   return r;
 }
 
+// One chunk of the scan layout -> a ring slot (asynchronous, 40 B per lane).
+__device__ __forceinline__ void fetch_rows2(const Scan2Args &a, int col, int64_t chunk, int lane,
+                                            RingSlot &slot) {
+  const int64_t base = chunk * kZoneRows + 4 * lane;
+  cp_async16(slot.rk + 4 * lane, a.f.s_rank[col] + base);
+  cp_async8(slot.cm + 4 * lane, a.f.s_cm[col] + base);
+  cp_async8(slot.fa + 4 * lane, a.f.s_fa[col] + base);
+  cp_async8(slot.rz + 4 * lane, a.f.s_rz[col] + base);
+}
+
 __device__ __forceinline__ Scan2Group find_group2(const Scan2Args &a, int p) {
   if (a.n_groups <= kInlineGroups2) {
     int idx = 0;
@@ -198,14 +252,17 @@ struct Scan2Smem {
   uint32_t *sbest, *sany;
   uint2 *Tfa; uint32_t *Tcm, *Trz;
   double2 *d_cm; double *d_disk; uint32_t *d_fa, *d_rz;
+  RingSlot *ring;   // [kFastWarps][kRingDepth]
 };
 __host__ __device__ inline size_t scan2_smem_bytes(size_t cap_fa, size_t cap_cm, size_t cap_rz) {
   return kQChunk * sizeof(ScanQuery) + (kQChunk + 4) * sizeof(uint32_t) +
-         cap_fa * (8 + 8 + 4) + cap_cm * (4 + 16) + cap_rz * (4 + 4) + 64;
+         cap_fa * (8 + 8 + 4) + cap_cm * (4 + 16) + cap_rz * (4 + 4) + 64 +
+         (size_t)kFastWarps * kRingDepth * sizeof(RingSlot);
 }
 __device__ __forceinline__ Scan2Smem carve_scan2(unsigned char *base, const Scan2Args &a) {
   Scan2Smem s;
   s.sq = reinterpret_cast<ScanQuery *>(base); base += kQChunk * sizeof(ScanQuery);
+  s.ring = reinterpret_cast<RingSlot *>(base); base += (size_t)kFastWarps * kRingDepth * sizeof(RingSlot);
   s.d_cm = reinterpret_cast<double2 *>(base); base += (size_t)a.cap_cm * 16;
   s.Tfa = reinterpret_cast<uint2 *>(base); base += (size_t)a.cap_fa * 8;
   s.d_disk = reinterpret_cast<double *>(base); base += (size_t)a.cap_fa * 8;
@@ -229,7 +286,8 @@ __device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *sm
     trace_put(a.trace, 0, 6, smid);
   }
   const bool prune = (a.noprune & 1u) == 0;
-  unsigned long long n_visit = 0, n_live = 0;
+  const TransposeLane tl = transpose_lane(lane);
+  uint32_t n_visit = 0, n_live = 0;
 
   int cur_group = -1;
   for (int p = blockIdx.x; p < a.n_pieces; p += gridDim.x) {
@@ -240,23 +298,21 @@ __device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *sm
     const int chunk_begin = G.chunk0 + (int)((int64_t)G.n_chunks * pi / G.n_pieces);
     const int chunk_end = G.chunk0 + (int)((int64_t)G.n_chunks * (pi + 1) / G.n_pieces);
 
-    // ---- the first chunk's rows and the first two summaries leave before
-    // anything else: they do not depend on the tables
-    int ch = chunk_begin + warp;
-    Rows2 cur{}, nxt{};
-    uint4 z0c = make_uint4(0, 0, 0, 0), z0 = make_uint4(0, 0, 0, 0);
-    uint32_t cmc = 0, cm = 0;
-    if (ch < chunk_end) {
-      cur = load_rows2(a, col, ch, lane);
-      if (prune) {
-        z0c = ldg_nc_v4(a.cat.zone_map + ch);
-        cmc = ldg_nc_u32(a.f.cmin[col] + ch);
-        if (ch + kFastWarps < chunk_end) {
-          z0 = ldg_nc_v4(a.cat.zone_map + ch + kFastWarps);
-          cm = ldg_nc_u32(a.f.cmin[col] + ch + kFastWarps);
-        }
-      }
+    // ---- this warp's chunks: chunk_begin + warp + 8 j. The summaries of its
+    // first 32 chunks (one per lane) and the rows of the very first one leave
+    // before anything else: they do not depend on the tables.
+    const int n_mine = (chunk_end - chunk_begin - warp + kFastWarps - 1) / kFastWarps;
+    RingSlot *ring = S.ring + warp * kRingDepth;
+    uint4 zs = make_uint4(0, 0, 0, 0);
+    uint32_t cms = 0;
+    if (prune && lane < n_mine) {
+      const int cl = chunk_begin + warp + kFastWarps * lane;
+      zs = ldg_nc_v4(a.cat.zone_map + cl);
+      cms = ldg_nc_u32(a.f.cmin[col] + cl);
     }
+    __syncwarp();  // the ring's previous readers are done
+    if (n_mine > 0) fetch_rows2(a, col, chunk_begin + warp, lane, ring[0]);
+    cp_commit();
 
     if (gi != cur_group) {
       __syncthreads();  // previous group's tables are still being read
@@ -396,58 +452,96 @@ __device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *sm
       return __ballot_sync(0xFFFFFFFFu, pass);
     };
 
-    // software pipeline: rows of chunk i + 1 and the summary of chunk i + 2
-    // are in flight while chunk i is scored
-    uint32_t live_cur = (ch < chunk_end) ? test(z0c, cmc) : 0u;
-    for (; ch < chunk_end; ch += kFastWarps) {
-      const int nch = ch + kFastWarps;
-      uint32_t live_next = 0;
-      if (nch < chunk_end) {
-        live_next = test(z0, cm);
-        if (live_next) nxt = load_rows2(a, col, nch, lane);
-        if (prune && nch + kFastWarps < chunk_end) {
-          z0 = ldg_nc_v4(a.cat.zone_map + nch + kFastWarps);
-          cm = ldg_nc_u32(a.f.cmin[col] + nch + kFastWarps);
+    // Software pipeline through a per-warp ring of kRingDepth chunk slots in
+    // shared memory, filled with cp.async (no registers held by rows in
+    // flight): the rows of chunks k+1 .. k+kRingDepth-1 are on their way
+    // while chunk k is scored. The zone-map / bound test decides at issue
+    // time whether a chunk is fetched at all.
+    for (int j0 = 0; j0 < n_mine; j0 += 32) {
+      const int nr = min(32, n_mine - j0);
+      if (j0 > 0) {
+        // next round of 32 chunks: summaries and the first fetch
+        cp_wait<0>();
+        __syncwarp();
+        if (prune && lane < nr) {
+          const int cl = chunk_begin + warp + kFastWarps * (j0 + lane);
+          zs = ldg_nc_v4(a.cat.zone_map + cl);
+          cms = ldg_nc_u32(a.f.cmin[col] + cl);
         }
+        fetch_rows2(a, col, chunk_begin + warp + kFastWarps * j0, lane, ring[j0 % kRingDepth]);
+        cp_commit();
       }
-      ++n_visit;
-      if (live_cur) {
-        ++n_live;
-        const uint32_t c0 = cur.cm.x & 0xFFFFu, c1 = cur.cm.x >> 16, c2 = cur.cm.y & 0xFFFFu, c3 = cur.cm.y >> 16;
-        const uint32_t f0 = cur.fa.x & 0xFFFFu, f1 = cur.fa.x >> 16, f2 = cur.fa.y & 0xFFFFu, f3 = cur.fa.y >> 16;
-        const uint32_t r0 = cur.rz.x & 0xFFFFu, r1 = cur.rz.x >> 16, r2 = cur.rz.y & 0xFFFFu, r3 = cur.rz.y >> 16;
-        const uint2 a0 = S.Tfa[f0], a1 = S.Tfa[f1], a2 = S.Tfa[f2], a3 = S.Tfa[f3];
-        const uint32_t z_0 = S.Trz[r0], z_1 = S.Trz[r1], z_2 = S.Trz[r2], z_3 = S.Trz[r3];
-        const uint32_t m0 = a0.y & S.Tcm[c0] & z_0, m1 = a1.y & S.Tcm[c1] & z_1;
-        const uint32_t m2 = a2.y & S.Tcm[c2] & z_2, m3 = a3.y & S.Tcm[c3] & z_3;
-        anyw |= (a0.x & z_0) | (a1.x & z_1) | (a2.x & z_2) | (a3.x & z_3);
-        const uint32_t many = m0 | m1 | m2 | m3;
-        // lane q: which lanes hold a row query q accepts; lanes are in
-        // ascending rank order, so the first one holds the chunk's argmin
-        const uint32_t B = warp_transpose32(many, lane);
-        const int src = B ? (__ffs(B) - 1) : 0;
-        const uint32_t first = __shfl_sync(0xFFFFFFFFu, cur.rk.x, src);
-        const bool maybe = B != 0u && first < best;
-        if (__any_sync(0xFFFFFFFFu, maybe)) {
-          // which of that lane's four rows (ascending) is the first accepted
-          const uint32_t q0 = __shfl_sync(0xFFFFFFFFu, m0, src), q1 = __shfl_sync(0xFFFFFFFFu, m1, src);
-          const uint32_t q2 = __shfl_sync(0xFFFFFFFFu, m2, src);
-          const uint32_t k1 = __shfl_sync(0xFFFFFFFFu, cur.rk.y, src), k2 = __shfl_sync(0xFFFFFFFFu, cur.rk.z, src);
-          const uint32_t k3 = __shfl_sync(0xFFFFFFFFu, cur.rk.w, src);
-          if (maybe) {
-            const uint32_t cand = ((q0 >> lane) & 1u) ? first : ((q1 >> lane) & 1u) ? k1
-                                : ((q2 >> lane) & 1u) ? k2 : k3;
-            if (cand < best) best = cand;
+      // chunk j0 was fetched unconditionally; is it worth scoring?
+      uint32_t live_bits = 0;
+      auto live_of = [&](int k) -> bool {
+        if (!prune) return true;
+        uint4 z;
+        z.x = __shfl_sync(0xFFFFFFFFu, zs.x, k); z.y = __shfl_sync(0xFFFFFFFFu, zs.y, k);
+        z.z = __shfl_sync(0xFFFFFFFFu, zs.z, k); z.w = __shfl_sync(0xFFFFFFFFu, zs.w, k);
+        const uint32_t c = __shfl_sync(0xFFFFFFFFu, cms, k);
+        return test(z, c) != 0u;
+      };
+      if (live_of(0)) live_bits |= 1u;
+      auto issue = [&](int k) {
+        if (k < nr && live_of(k)) {
+          fetch_rows2(a, col, chunk_begin + warp + kFastWarps * (j0 + k), lane, ring[(j0 + k) % kRingDepth]);
+          live_bits |= 1u << k;
+        }
+        cp_commit();
+      };
+#pragma unroll
+      for (int k = 1; k < kRingDepth - 1; ++k) issue(k);
+#pragma unroll 1
+      for (int k = 0; k < nr; ++k) {
+        issue(k + kRingDepth - 1);
+        cp_wait<kRingDepth - 1>();
+        __syncwarp();
+        if (a.trace) ++n_visit;
+        if ((live_bits >> k) & 1u) {
+          if (a.trace) ++n_live;
+          const RingSlot &R = ring[(j0 + k) % kRingDepth];
+          const uint4 rk = *reinterpret_cast<const uint4 *>(R.rk + 4 * lane);
+          const uint2 cmv = *reinterpret_cast<const uint2 *>(R.cm + 4 * lane);
+          const uint2 fav = *reinterpret_cast<const uint2 *>(R.fa + 4 * lane);
+          const uint2 rzv = *reinterpret_cast<const uint2 *>(R.rz + 4 * lane);
+          const uint32_t c0 = cmv.x & 0xFFFFu, c1 = cmv.x >> 16, c2 = cmv.y & 0xFFFFu, c3 = cmv.y >> 16;
+          const uint32_t f0 = fav.x & 0xFFFFu, f1 = fav.x >> 16, f2 = fav.y & 0xFFFFu, f3 = fav.y >> 16;
+          const uint32_t r0 = rzv.x & 0xFFFFu, r1 = rzv.x >> 16, r2 = rzv.y & 0xFFFFu, r3 = rzv.y >> 16;
+          const uint2 a0 = S.Tfa[f0], a1 = S.Tfa[f1], a2 = S.Tfa[f2], a3 = S.Tfa[f3];
+          const uint32_t z_0 = S.Trz[r0], z_1 = S.Trz[r1], z_2 = S.Trz[r2], z_3 = S.Trz[r3];
+          const uint32_t m0 = a0.y & S.Tcm[c0] & z_0, m1 = a1.y & S.Tcm[c1] & z_1;
+          const uint32_t m2 = a2.y & S.Tcm[c2] & z_2, m3 = a3.y & S.Tcm[c3] & z_3;
+          // any_stage1 is only read for gate queries (GCP) and scan results
+          if (G.need_any | a.force_any) anyw |= (a0.x & z_0) | (a1.x & z_1) | (a2.x & z_2) | (a3.x & z_3);
+          const uint32_t many = m0 | m1 | m2 | m3;
+          // lane q: which lanes hold a row query q accepts; lanes are in
+          // ascending rank order, so the first one holds the chunk's argmin
+          const uint32_t B = warp_transpose32(many, tl);
+          const int src = B ? (__ffs(B) - 1) : 0;
+          const uint32_t first = __shfl_sync(0xFFFFFFFFu, rk.x, src);
+          const bool maybe = B != 0u && first < best;
+          if (__any_sync(0xFFFFFFFFu, maybe)) {
+            // which of that lane's four rows (ascending) is the first accepted
+            const uint32_t q0 = __shfl_sync(0xFFFFFFFFu, m0, src), q1 = __shfl_sync(0xFFFFFFFFu, m1, src);
+            const uint32_t q2 = __shfl_sync(0xFFFFFFFFu, m2, src);
+            const uint32_t k1 = __shfl_sync(0xFFFFFFFFu, rk.y, src), k2 = __shfl_sync(0xFFFFFFFFu, rk.z, src);
+            const uint32_t k3 = __shfl_sync(0xFFFFFFFFu, rk.w, src);
+            if (maybe) {
+              const uint32_t cand = ((q0 >> lane) & 1u) ? first : ((q1 >> lane) & 1u) ? k1
+                                  : ((q2 >> lane) & 1u) ? k2 : k3;
+              if (cand < best) best = cand;
+            }
           }
         }
-      }
-      cur = nxt; live_cur = live_next;
-      if (prune && lane < nq) {
-        // share the bound inside the block (any achieved rank is a valid bound)
-        const uint32_t sb = S.sbest[lane];
-        if (best < sb) atomicMin(&S.sbest[lane], best); else best = sb;
+        __syncwarp();  // the slot is free before it is refilled
+        if (prune && lane < nq) {
+          // share the bound inside the block (any achieved rank is a valid bound)
+          const uint32_t sb = S.sbest[lane];
+          if (best < sb) atomicMin(&S.sbest[lane], best); else best = sb;
+        }
       }
     }
+    cp_wait<0>();
     // ---- publish: block minimum per query, any-match bits
     anyw = __reduce_or_sync(0xFFFFFFFFu, anyw);
     if (lane < nq && best != kRankNone) atomicMin(&S.sbest[lane], best);
@@ -463,11 +557,12 @@ __device__ __forceinline__ void scan2_body(const Scan2Args &a, unsigned char *sm
   }
   trace_mark(a.trace, 0, 4);
   if (a.trace && lane == 0 && blockIdx.x < kTraceBlocks) {
-    atomicAdd(&a.trace[((size_t)blockIdx.x) * kTraceSlots + 5], n_visit | (n_live << 32));
+    atomicAdd(&a.trace[((size_t)blockIdx.x) * kTraceSlots + 5],
+              (unsigned long long)n_visit | ((unsigned long long)n_live << 32));
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan2_kernel(Scan2Args a) {
+__global__ void __launch_bounds__(kScanThreads, 4) scan2_kernel(Scan2Args a) {
   extern __shared__ __align__(16) unsigned char smem2[];
   scan2_body(a, smem2);
 }
@@ -657,6 +752,9 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
         rg = e.rg; zn = e.zn;
         if (gcp && (row < X.cloud_r0 || row >= X.cloud_r1)) keep = false;
         if (S.region_id >= 0 && rg != S.region_id) keep = false;
+        if (S.region_set >= 0 &&
+            !test_bit(a.acc_sets + (int64_t)S.region_set * SKYOPT_ACC_SET_WORDS, (uint32_t)rg & 1023u))
+          keep = false;  // image_id / ssh_proxy_command region allow-list
         if (S.zone_id >= 0 && (!has_zones || zn != S.zone_id)) keep = false;
         if (!split && S.zone_id < 0 && !(e.row & kRegionFirst)) keep = false;
         pa = e.price;

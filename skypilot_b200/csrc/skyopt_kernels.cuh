@@ -1261,6 +1261,9 @@ __global__ void expand_kernel(CatDev cat, const SkyoptSlot *__restrict__ slots,
       const int zn = (int)((v >> 32) & 0xFFFF);
       bool keep = true;
       if (S.region_id >= 0 && rg != S.region_id) keep = false;
+      if (S.region_set >= 0 &&
+          !test_bit(acc_sets + (int64_t)S.region_set * SKYOPT_ACC_SET_WORDS, (uint32_t)rg & 1023u))
+        keep = false;  // image_id / ssh_proxy_command region allow-list
       if (S.zone_id >= 0 && (!has_zones || zn != S.zone_id)) keep = false;
       const bool split = S.split_by_zone && has_zones;
       // Region-level candidates: the region's first sorted row carries its

@@ -14,6 +14,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from skypilot_b200.utils import timeline
 from skypilot_b200 import _native
 from skypilot_b200.catalog.store import CatalogStore
 from skypilot_b200.utils import resources_utils
@@ -81,6 +82,9 @@ def zone_exact_id(table, zone: Optional[str]) -> int:
     return table.zone_exact.get(zone, NO_MATCH_ID)
 
 
+_PLAIN_NAME = re.compile(r'[A-Za-z0-9_\- ]+')
+
+
 def accelerator_sets(store: CatalogStore, acc_name: str,
                      acc_count) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Dictionary-level accelerator predicates -> key bitmasks.
@@ -97,8 +101,37 @@ def accelerator_sets(store: CatalogStore, acc_name: str,
     hit = cache.get((acc_name, float(acc_count)))
     if hit is not None:
         return hit
-    pattern = re.compile(acc_name, flags=re.IGNORECASE)
     count = float(acc_count)
+    if _PLAIN_NAME.fullmatch(acc_name):
+        # A name without regex metacharacters: case-insensitive fullmatch is
+        # equality of the lower-cased names, `contains` a substring test --
+        # answered from the store's name index (a property of the catalog
+        # dictionary, not a request memo) instead of a regex per key.
+        index = store.__dict__.get('_acc_name_index')
+        if index is None:
+            index = {}
+            for k, (name, cnt) in enumerate(store.acc_keys):
+                index.setdefault(name.lower(), []).append((k, cnt))
+            store.__dict__['_acc_name_index'] = index
+        low = acc_name.lower()
+        exact = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
+        fuzzy = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
+        strict = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
+        for name, keys in index.items():
+            if low not in name:
+                continue
+            same = name == low
+            for k, cnt in keys:
+                bit = np.uint32(1 << (k & 31))
+                if cnt >= count:
+                    fuzzy[k >> 5] |= bit
+                if same and abs(cnt - count) <= 0.01:
+                    exact[k >> 5] |= bit
+                if same and cnt == count:
+                    strict[k >> 5] |= bit
+        cache[(acc_name, float(acc_count))] = (exact, fuzzy, strict)
+        return exact, fuzzy, strict
+    pattern = re.compile(acc_name, flags=re.IGNORECASE)
     exact = store.accelerator_set(lambda n, c: pattern.fullmatch(n) is not None
                                   and abs(c - count) <= 0.01)
     fuzzy = store.accelerator_set(
@@ -144,7 +177,7 @@ def set_table(store: CatalogStore) -> np.ndarray:
 
 
 _MINUS_ONE_DEFAULT = frozenset(('acc_set', 'fuzzy_set', 'region_id',
-                                'zone_id'))
+                                'zone_id', 'region_set'))
 _PACKERS: Dict[Any, Tuple[struct.Struct, Tuple[str, ...]]] = {}
 _FORMATS = {'i4': 'i', 'u4': 'I', 'f8': 'd', 'i8': 'q', 'u8': 'Q', 'u2': 'H',
             'i2': 'h'}
@@ -329,13 +362,16 @@ class ProblemBuilder:
             'query': -1, 'inst_id': -1, 'gate_query': -1, 'acc_set': -1,
             'price_col': 0, 'region_id': -1, 'zone_id': -1,
             'split_by_zone': 0, 'us_first': 0, 'cand_acc_key': -1,
-            'use_spot': 0, 'hours': 1.0, 'node_mult': 1.0,
-            'time_value': 3600.0
+            'use_spot': 0, 'region_set': -1, 'pad_': 0, 'hours': 1.0,
+            'node_mult': 1.0, 'time_value': 3600.0
         }
         words = fields.pop('acc_words', None)
+        region_words = fields.pop('region_words', None)
         slot.update(fields)
         if words is not None:
             slot['acc_set'] = self.add_set(words)
+        if region_words is not None:
+            slot['region_set'] = self.add_set(region_words)
         self.slot_recs.append(self._record(slot, _native.SLOT_DTYPE))
         self.slot_qbase.append(0)
         self.slot_cost.append(None)
@@ -569,6 +605,7 @@ def solve(builder: ProblemBuilder,
                             ctypes.byref(sol.stats)))
     global LAST_STATS  # pylint: disable=global-statement
     LAST_STATS = sol.stats
+    timeline.device_event('skyopt_optimize', sol.stats)
     return sol
 
 

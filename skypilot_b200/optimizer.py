@@ -29,6 +29,7 @@ from skypilot_b200 import exceptions
 from skypilot_b200 import resources as resources_lib
 from skypilot_b200 import task as task_lib
 from skypilot_b200.utils import resources_utils
+from skypilot_b200.utils import timeline
 
 logger = logging.getLogger(__name__)
 
@@ -159,6 +160,7 @@ class Optimizer:
 
     # -------------------------------------------------------------- public API
     @staticmethod
+    @timeline.event
     def optimize(dag: 'dag_lib.Dag',
                  minimize: OptimizeTarget = OptimizeTarget.COST,
                  blocked_resources: Optional[Iterable[
@@ -317,6 +319,7 @@ class Optimizer:
 
     # -------------------------------------------------------------- job groups
     @staticmethod
+    @timeline.event
     def optimize_job_group(dag: 'dag_lib.Dag',
                            minimize: OptimizeTarget = OptimizeTarget.COST,
                            blocked_resources: Optional[Iterable[
@@ -876,9 +879,10 @@ class Optimizer:
         indent = ' ' * len('Hint: ')
         hints_concat = '\n'.join(f'Resource: {r!r}\n' + '\n'.join(h)
                                  for r, h in resource_hints.items() if h)
+        # like the reference: ''.split('\n') is [''], so without any hint the
+        # text still ends in 'Hint: Check Per Resource Hint' and an indent
         hints_fmt = '\n'.join(
-            f'{indent}{line}' for line in hints_concat.split('\n')
-        ) if hints_concat else ''
+            f'{indent}{line}' for line in hints_concat.split('\n'))
         hints_str = (f'Hint: Check Per Resource Hint\n{hints_fmt}'
                      if hints_fmt else '')
         raise exceptions.ResourcesUnavailableError(

@@ -351,37 +351,56 @@ class Resources:
         return '[Spot]' if self.use_spot else ''
 
     def __repr__(self) -> str:
-        parts = []
-        if self._instance_type is not None:
-            parts.append(self._instance_type)
-        if self._accelerators is not None:
-            parts.append('{' + ', '.join(
-                f'{k}: {v}' for k, v in self._accelerators.items()) + '}')
+        """The reference's text (sky/resources.py:448-568): it is part of the
+        optimizer's error messages and tables. `<Cloud>(...)` without a cloud;
+        inside the parentheses instance type[Spot], cpus, mem, accelerators,
+        accelerator_args, image_id, disk_tier, network_tier, disk_size,
+        local_disk, max_cost, ports -- the fields that are set."""
+        fields = []
+        if self.accelerators is not None:
+            fields.append(f'{self.accelerators}')
+            if self.accelerator_args is not None:
+                fields.append(f'accelerator_args={self.accelerator_args}')
+        head = []
         if self._cpus is not None:
-            parts.append(f'cpus={self._cpus}')
-        if self._memory is not None:
-            parts.append(f'mem={self._memory}')
-        if self._use_spot:
-            parts.append('[Spot]')
+            head.append(f'cpus={self._cpus}')
+        if self.memory is not None:
+            head.append(f'mem={self.memory}')
+        tail = []
+        if self.image_id is not None:
+            tail.append(f'image_id={self.image_id[None]}' if None in
+                        self.image_id else f'image_id={self.image_id}')
+        if self.disk_tier is not None:
+            tail.append(f'disk_tier={self.disk_tier.value}')
+        if self.network_tier is not None:
+            tail.append(f'network_tier={self.network_tier.value}')
+        if self.disk_size != DEFAULT_DISK_SIZE_GB:
+            tail.append(f'disk_size={self.disk_size}')
         if self._local_disk is not None:
-            parts.append(f'local_disk={self._local_disk}')
+            tail.append(f'local_disk={self._local_disk}')
         if self._max_hourly_cost is not None:
-            parts.append(f'max_hourly_cost=${self._max_hourly_cost}')
-        body = ', '.join(parts)
-        cloud = f'{self._cloud}' if self._cloud is not None else ''
-        if cloud:
-            return f'{cloud}({body})'
-        return f'({body})' if body else '<Resources: empty>'
+            tail.append(f'max_cost=${self._max_hourly_cost}/hr')
+        if self.ports is not None:
+            tail.append(f'ports={self.ports}')
+        first = (self._instance_type or '') + ('[Spot]' if self.use_spot
+                                                else '')
+        parts = ([first] if first else []) + head + fields + tail
+        cloud = '<Cloud>' if self._cloud is None else f'{self._cloud}'
+        return f'{cloud}({", ".join(parts)})'
 
     @property
     def repr_with_region_zone(self) -> str:
+        """sky/resources.py:571-586."""
         where = ''
         if self._region is not None:
-            where += f', region={self._region}'
+            name = self._region
+            if name.startswith('ssh-'):
+                name = name[len('ssh-'):]
+            where += f', region={name}'
         if self._zone is not None:
             where += f', zone={self._zone}'
-        text = repr(self)
-        if where and text.endswith(')'):
+        text = str(self)
+        if text.endswith(')'):
             return text[:-1] + where + ')'
         return text + where
 
@@ -524,9 +543,25 @@ class Resources:
                                                     self._use_spot,
                                                     self._region, self._zone,
                                                     self)
-        if self._image_id is not None and None not in self._image_id:
-            regions = [r for r in regions if r.name in self._image_id]
+        allowed = self.allowed_region_names()
+        if allowed is not None:
+            regions = [r for r in regions if r.name in allowed]
         return regions
+
+    def allowed_region_names(self) -> Optional[Set[str]]:
+        """The region allow-list of sky/resources.py:1210-1246, or None: the
+        keys of a per-region `image_id` dict, intersected with the keys of a
+        per-region `ssh_proxy_command` in the SkyPilot config."""
+        from skypilot_b200 import skypilot_config  # pylint: disable=import-outside-toplevel
+        allowed: Optional[Set[str]] = None
+        if self._image_id is not None and None not in self._image_id:
+            allowed = set(self._image_id.keys())
+        if self._cloud is not None:
+            by_proxy = skypilot_config.allowed_regions_by_ssh_proxy(
+                str(self._cloud).lower())
+            if by_proxy is not None:
+                allowed = by_proxy if allowed is None else allowed & by_proxy
+        return allowed
 
     def get_cost(self, seconds: float) -> float:
         """USD for `seconds` of runtime (sky/resources.py:1685-1698)."""
@@ -668,6 +703,181 @@ class Resources:
         )
         assert not override, override
         return resources
+
+    # ------------------------------------------------------------------
+    # Request alternatives from a YAML-style config (sky/resources.py:
+    # 2209-2411): `any_of` / `ordered` lists, several accelerators, and
+    # accelerators given by memory size ('32GB+', 'nvidia:16GB:1').
+    @classmethod
+    def _parse_accelerators_from_str(cls, accelerators: str
+                                    ) -> List[Tuple[str, bool]]:
+        """-> [(accelerator string, named by the user?)]; a memory-size spec
+        expands to every device of that size in common/metadata.csv
+        (sky/resources.py:2209-2262)."""
+        import re  # pylint: disable=import-outside-toplevel
+        from skypilot_b200.utils import accelerator_registry  # pylint: disable=import-outside-toplevel
+        assert isinstance(accelerators, str), accelerators
+        size = re.compile(r'^[0-9]+[GgMmTt][Bb]\+?$')
+        manufacturer = None
+        memory = None
+        count = 1
+        split = accelerators.split(':')
+        if len(split) == 3:
+            manufacturer, memory, count_str = split
+            count = int(count_str)
+            assert size.match(memory), \
+                'If specifying a GPU manufacturer, you must also' \
+                'specify the memory size'
+        elif len(split) == 2 and size.match(split[0]):
+            memory = split[0]
+            count = int(split[1])
+        elif len(split) == 2 and size.match(split[1]):
+            manufacturer, memory = split
+        elif len(split) == 1 and size.match(split[0]):
+            memory = split[0]
+        else:
+            return [(accelerators, True)]
+        parsed = resources_utils.parse_memory_resource(memory, 'accelerators',
+                                                       allow_plus=True)
+        plus = parsed[-1] == '+'
+        if plus:
+            parsed = parsed[:-1]
+        memory_gb = int(parsed)
+        return [(f'{device}:{count}', False)
+                for device in accelerator_registry.get_devices_by_memory(
+                    memory_gb, plus, manufacturer=manufacturer)]
+
+    @classmethod
+    def from_yaml_config(cls, config: Optional[Dict[str, Any]]
+                        ) -> Union[Set['Resources'], List['Resources']]:
+        """A set of Resources for `any_of` (or several accelerators given as
+        a set / dict / string), a list for `ordered` (or a list of
+        accelerators), else a set with one Resources
+        (sky/resources.py:2264-2411)."""
+        import collections  # pylint: disable=import-outside-toplevel
+        if config is None:
+            return {Resources()}
+        config = dict(config)
+
+        def aliases(cfg):
+            if 'gpus' in cfg:
+                if 'accelerators' in cfg:
+                    raise ValueError(
+                        'Cannot specify both gpus and accelerators in config.')
+                cfg['accelerators'] = cfg.pop('gpus')
+
+        aliases(config)
+        for key in ('any_of', 'ordered'):
+            if isinstance(config.get(key), list):
+                config[key] = [dict(c) for c in config[key]]
+                for c in config[key]:
+                    aliases(c)
+                    if 'any_of' in c or 'ordered' in c:
+                        raise ValueError(
+                            'Invalid resources YAML: "any_of" / "ordered" '
+                            'cannot be nested.')
+
+        def override(base, overrides):
+            out = []
+            for ov in overrides:
+                ov = dict(ov)
+                new = dict(base)
+                ov_labels = ov.pop('labels', None)
+                new.update(ov)
+                labels = new.get('labels')
+                if labels is not None and ov_labels is not None:
+                    labels = dict(labels, **ov_labels)
+                elif ov_labels is not None:
+                    labels = ov_labels
+                new['labels'] = labels
+                out.extend(list(Resources.from_yaml_config(new)))
+            return out
+
+        any_of = config.pop('any_of', None)
+        ordered = config.pop('ordered', None)
+        if any_of is not None and ordered is not None:
+            raise ValueError(
+                'Cannot specify both "any_of" and "ordered" in resources.')
+        accelerators = config.get('accelerators')
+        if config and accelerators is not None:
+            if isinstance(accelerators, str):
+                parsed = cls._parse_accelerators_from_str(accelerators)
+            elif isinstance(accelerators, dict):
+                parsed = []
+                for k, v in accelerators.items():
+                    parsed.extend(cls._parse_accelerators_from_str(
+                        f'{k}:{v}' if v is not None else f'{k}'))
+            elif isinstance(accelerators, (list, set)):
+                parsed = []
+                for name in accelerators:
+                    parsed.extend(cls._parse_accelerators_from_str(name))
+            else:
+                raise AssertionError(
+                    f'Invalid accelerators type:{type(accelerators)}')
+            named: Dict[str, bool] = collections.OrderedDict()
+            for accel, user in parsed:
+                named[accel] = user or named.get(accel, False)
+            kind = list if isinstance(accelerators, list) else set
+            accelerators = kind([(a, u) for a, u in named.items()])
+            if len(accelerators) > 1 and ordered:
+                raise ValueError(
+                    'Cannot specify multiple "accelerators" with "ordered" '
+                    'in resources.')
+            if (len(accelerators) > 1 and any_of and
+                    not isinstance(accelerators, set)):
+                raise ValueError(
+                    'Cannot specify multiple "accelerators" with preferred '
+                    'order (i.e., list of accelerators) with "any_of" '
+                    'in resources.')
+        if any_of:
+            return set(override(config, any_of))
+        if ordered:
+            return override(config, ordered)
+        if accelerators:
+            out = []
+            for acc, user in accelerators:
+                one = dict(config)
+                one['accelerators'] = acc
+                if not user:
+                    one['_no_missing_accel_warnings'] = True
+                out.append(Resources._from_yaml_config_single(one))
+            return type(accelerators)(out)
+        return {Resources._from_yaml_config_single(config)}
+
+    _YAML_FIELDS = ('infra', 'region', 'zone', 'instance_type', 'cpus',
+                    'memory', 'accelerators', 'accelerator_args', 'use_spot',
+                    'job_recovery', 'disk_size', 'image_id', 'disk_tier',
+                    'network_tier', 'local_disk', 'max_hourly_cost', 'ports',
+                    'labels', '_no_missing_accel_warnings')
+    # fields of the reference's schema that do not reach the optimizer path
+    _YAML_IGNORED = ('ephemeral_storage', 'autostop', 'priority',
+                     'priority_class', 'volumes', '_docker_login_config',
+                     '_docker_username_for_runpod', '_is_image_managed',
+                     '_requires_fuse', '_cluster_config_overrides')
+
+    @classmethod
+    def _from_yaml_config_single(cls, config: Dict[str, Any]) -> 'Resources':
+        """sky/resources.py:2413-2489."""
+        config = dict(config)
+        fields: Dict[str, Any] = {
+            'cloud': registry.CLOUD_REGISTRY.from_str(config.pop('cloud',
+                                                                 None))
+        }
+        if config.get('spot_recovery') is not None:
+            config['job_recovery'] = config.pop('spot_recovery')
+        else:
+            config.pop('spot_recovery', None)
+        for name in cls._YAML_FIELDS:
+            fields[name] = config.pop(name, None)
+        for name in cls._YAML_IGNORED:
+            config.pop(name, None)
+        for name in ('cpus', 'memory', 'disk_size', 'local_disk'):
+            if fields[name] is not None:
+                fields[name] = str(fields[name])
+        if fields['accelerator_args'] is not None:
+            fields['accelerator_args'] = dict(fields['accelerator_args'])
+        assert not config, f'Invalid resource args: {config.keys()}'
+        return Resources(**fields)
 
 
 class LaunchableResources(Resources):

@@ -819,3 +819,23 @@ def make_catalogs(seed: int,
 
 def total_rows(catalogs: Dict[str, pd.DataFrame]) -> int:
     return int(sum(len(df) for df in catalogs.values()))
+
+
+# Device memory / manufacturer of the accelerator names the generators use:
+# the rows of `common/metadata.csv` (GPU, MemoryGB, Manufacturer) behind
+# memory-size requests like '32GB+' (sky/utils/accelerator_registry.py:50-73).
+ACCELERATOR_METADATA = [
+    ('T4', 16, 'NVIDIA'), ('V100', 16, 'NVIDIA'), ('V100-32GB', 32, 'NVIDIA'),
+    ('P100', 16, 'NVIDIA'), ('K80', 12, 'NVIDIA'), ('P4', 8, 'NVIDIA'),
+    ('A10G', 24, 'NVIDIA'), ('A10', 24, 'NVIDIA'), ('L4', 24, 'NVIDIA'),
+    ('L40S', 48, 'NVIDIA'), ('A100', 40, 'NVIDIA'),
+    ('A100-80GB', 80, 'NVIDIA'), ('H100', 80, 'NVIDIA'),
+    ('H200', 141, 'NVIDIA'), ('B200', 180, 'NVIDIA'), ('M60', 8, 'NVIDIA'),
+    ('RTX6000', 24, 'NVIDIA'), ('Gaudi', 32, 'Intel'),
+    ('MI300X', 192, 'AMD'),
+]
+
+
+def accelerator_metadata() -> pd.DataFrame:
+    return pd.DataFrame(ACCELERATOR_METADATA,
+                        columns=['GPU', 'MemoryGB', 'Manufacturer'])

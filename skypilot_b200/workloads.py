@@ -174,6 +174,15 @@ def make_resources(spec):
     return sky.Resources(**kwargs)
 
 
+def _task_extras(task, tspec) -> None:
+    if 'outputs_gb' in tspec:
+        task.set_outputs('CLOUD://out', tspec['outputs_gb'])
+    if 'inputs' in tspec:
+        task.set_inputs(tspec['inputs'][0], tspec['inputs'][1])
+    if 'time_est' in tspec:
+        task.set_time_estimator(make_time_estimator(tspec['time_est']))
+
+
 def build_dag(scenario):
     """-> (Dag, [Task ...]) of skypilot_b200 types."""
     import skypilot_b200 as sky  # pylint: disable=import-outside-toplevel
@@ -182,6 +191,13 @@ def build_dag(scenario):
         for i, tspec in enumerate(scenario['tasks']):
             task = sky.Task(name=tspec.get('name', f't{i}'),
                             num_nodes=tspec.get('num_nodes', 1))
+            if 'resources_yaml' in tspec:
+                import copy  # pylint: disable=import-outside-toplevel
+                task.set_resources(sky.Resources.from_yaml_config(
+                    copy.deepcopy(tspec['resources_yaml'])))
+                _task_extras(task, tspec)
+                tasks.append(task)
+                continue
             res = [make_resources(r) for r in tspec['resources']]
             kind = tspec.get('resources_kind', 'single')
             if kind == 'single':
@@ -190,12 +206,7 @@ def build_dag(scenario):
                 task.set_resources(res)
             else:
                 task.set_resources(set(res))
-            if 'outputs_gb' in tspec:
-                task.set_outputs('CLOUD://out', tspec['outputs_gb'])
-            if 'inputs' in tspec:
-                task.set_inputs(tspec['inputs'][0], tspec['inputs'][1])
-            if 'time_est' in tspec:
-                task.set_time_estimator(make_time_estimator(tspec['time_est']))
+            _task_extras(task, tspec)
             tasks.append(task)
         for u, v in scenario.get('edges', []):
             dag.add_edge(tasks[u], tasks[v])

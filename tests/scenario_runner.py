@@ -5,6 +5,7 @@ field."""
 import json
 import math
 import os
+import re
 from typing import Any, Dict, List, Optional
 
 import networkx as nx
@@ -16,6 +17,7 @@ from skypilot_b200 import workloads
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 _loaded: Dict[str, Any] = {}
+_ANSI = re.compile(r'\x1b\[[0-9;]*m')
 
 
 def load_golden(name: str) -> Dict[str, Any]:
@@ -34,6 +36,7 @@ def activate_catalog(spec: Dict[str, Any]):
         from skypilot_b200.catalog.store import CatalogStore
         store = CatalogStore.from_frames(frames)
         store.enabled = enabled
+        store.set_accelerator_metadata(synth.accelerator_metadata())
         _loaded[key] = store
     sky.catalog.set_store(store)
     sky.check.set_enabled_clouds(
@@ -50,6 +53,14 @@ res_record = workloads.res_record
 def run_scenario(scenario, with_candidates: bool = True) -> Dict[str, Any]:
     """Plan via Optimizer.optimize (fused device path) and, optionally, the
     ordered candidate tables via _estimate_nodes_cost_or_time."""
+    if scenario.get('config') is not None and not scenario.get('_in_config'):
+        from skypilot_b200 import skypilot_config  # pylint: disable=import-outside-toplevel
+        skypilot_config.set_config(scenario['config'])
+        try:
+            return run_scenario(dict(scenario, _in_config=True),
+                                with_candidates)
+        finally:
+            skypilot_config.set_config(None)
     minimize_cost = scenario.get('minimize', 'cost') == 'cost'
     target = (sky.OptimizeTarget.COST
               if minimize_cost else sky.OptimizeTarget.TIME)
@@ -60,7 +71,8 @@ def run_scenario(scenario, with_candidates: bool = True) -> Dict[str, Any]:
         record['is_chain'] = bool(dag.is_chain())
         Optimizer = opt_lib.Optimizer
         has_list = any(
-            t.get('resources_kind') == 'list' for t in scenario['tasks'])
+            t.get('resources_kind') == 'list' or isinstance(tk.resources, list)
+            for t, tk in zip(scenario['tasks'], tasks))
         if with_candidates and not has_list:
             Optimizer._add_dummy_source_sink_nodes(dag)
             try:
@@ -109,7 +121,8 @@ def close(a: float, b: float, rel: float = 1e-6) -> bool:
 
 
 def compare(golden: Dict[str, Any], got: Dict[str, Any],
-            unordered_candidates: bool = False) -> List[str]:
+            unordered_candidates: bool = False,
+            check_message: bool = True) -> List[str]:
     """Differences between a reference record and ours (empty = parity).
 
     Index fields (cloud, instance type, region, zone) must be identical,
@@ -121,13 +134,24 @@ def compare(golden: Dict[str, Any], got: Dict[str, Any],
         if g != o:
             diffs.append(f'error: reference {g}, ours {o}: '
                          f'{got.get("error", {}).get("message", "")[:300]}')
+            return diffs
+        # same exception class AND the same text: the
+        # hints and the fuzzy-candidate list are part of the interface
+        gm = _ANSI.sub('', golden['error'].get('message', ''))
+        om = _ANSI.sub('', got['error'].get('message', ''))
+        if check_message and gm != om:
+            diffs.append(f'error message:\n  reference {gm!r}\n  ours      {om!r}')
         return diffs
     if 'candidates' in golden and 'candidates' in got:
         for ti, (gc, oc) in enumerate(
                 zip(golden['candidates'], got['candidates'])):
             if unordered_candidates:
-                gc = sorted(gc, key=lambda c: [str(x) for x in c[:4]])
-                oc = sorted(oc, key=lambda c: [str(x) for x in c[:4]])
+                # identity, then value: two requests of a set may expand to the
+                # same (cloud, instance type, region, zone) at different
+                # prices (GCP: one host VM type under two accelerators)
+                key = lambda c: ([str(x) for x in c[:4]], float(c[4]))  # noqa: E731
+                gc = sorted(gc, key=key)
+                oc = sorted(oc, key=key)
             if len(gc) != len(oc):
                 diffs.append(f'task {ti}: {len(gc)} candidates in the '
                              f'reference, {len(oc)} ours')

@@ -71,6 +71,12 @@ CATALOGS = {
     # general DAGs of 18-26 tasks (big_dag_scenarios), the fuzzdag catalog
     'bigdag': {'seed': 61, 'n_rows': 6000,
                'clouds': ['aws', 'gcp', 'azure', 'lambda']},
+    # request alternatives from YAML configs (alternatives_scenarios)
+    'altres': {'seed': 67, 'n_rows': 6000,
+               'clouds': ['aws', 'gcp', 'azure', 'lambda']},
+    # region allow-lists (region_filter_scenarios)
+    'regfilter': {'seed': 71, 'n_rows': 6000,
+                  'clouds': ['aws', 'gcp', 'azure', 'lambda']},
     'gpuclouds': {'seed': 13, 'n_rows': 4000,
                   'clouds': ['aws', 'runpod', 'paperspace', 'do',
                              'fluidstack', 'cudo']},
@@ -581,6 +587,118 @@ def big_dag_scenarios(seed=21):
     return out
 
 
+def alternatives_scenarios():
+    """Where a task's alternatives R come from: the
+    `resources:` block of a task YAML through Resources.from_yaml_config
+    (sky/resources.py:2264-2411) -- `any_of` sets, `ordered` lists, several
+    accelerators, accelerators named by memory size and manufacturer
+    (sky/resources.py:2209-2262, common/metadata.csv)."""
+
+    def yaml_task(name, config, **extra):
+        task = {'name': 't0', 'resources_yaml': config}
+        task.update(extra)
+        return {'name': name, 'tasks': [task]}
+
+    def yaml_chain(name, configs, **kw):
+        tasks = [{'name': f't{i}', 'resources_yaml': c, 'outputs_gb': 50}
+                 for i, c in enumerate(configs)]
+        sc = {'name': name, 'tasks': tasks,
+              'edges': [[i, i + 1] for i in range(len(tasks) - 1)]}
+        sc.update(kw)
+        return sc
+
+    return [
+        yaml_task('mem_80gb_plus', {'accelerators': '80GB+'}),
+        yaml_task('mem_16gb_exact_x4', {'accelerators': '16GB:4'}),
+        yaml_task('mem_nvidia_24gb', {'accelerators': 'nvidia:24GB'}),
+        yaml_task('mem_nvidia_40gb_plus_x8',
+                  {'accelerators': 'NVIDIA:40GB+:8', 'use_spot': True}),
+        yaml_task('mem_amd_none', {'accelerators': 'amd:192GB'}),
+        yaml_task('acc_set', {'accelerators': {'V100': 1, 'T4': 1, 'L4': 1}}),
+        yaml_task('acc_list_ordered', {'accelerators': ['H100:8', 'A100:8',
+                                                        'V100:8']}),
+        yaml_task('acc_list_first_missing',
+                  {'accelerators': ['B200:4', 'A100:8'], 'cloud': 'aws'}),
+        yaml_task('any_of_clouds', {
+            'cpus': '8+',
+            'any_of': [{'cloud': 'aws'}, {'cloud': 'gcp'},
+                       {'cloud': 'azure', 'memory': '64+'}]
+        }),
+        yaml_task('any_of_acc_spot', {
+            'any_of': [{'accelerators': 'A100:8', 'use_spot': True},
+                       {'accelerators': 'V100:8'},
+                       {'accelerators': 'T4:4', 'cloud': 'gcp'}]
+        }),
+        yaml_task('ordered_regions', {
+            'accelerators': 'V100',
+            'ordered': [{'cloud': 'gcp', 'region': 'us-central1'},
+                        {'cloud': 'aws', 'region': 'us-east-1'}]
+        }),
+        yaml_task('ordered_fallback', {
+            'ordered': [{'accelerators': 'B200:4', 'cloud': 'lambda'},
+                        {'accelerators': 'A100:8'},
+                        {'cpus': '32+'}]
+        }),
+        yaml_task('gpus_alias', {'gpus': 'L4:2', 'memory': '32+'}),
+        yaml_task('any_of_mem_spec', {
+            'any_of': [{'accelerators': '80GB+', 'cloud': 'lambda'},
+                       {'accelerators': 'A100:8', 'cloud': 'gcp'}]
+        }),
+        yaml_chain('chain_alternatives', [
+            {'accelerators': '16GB'},
+            {'any_of': [{'cloud': 'aws', 'cpus': '16+'},
+                        {'cloud': 'gcp', 'cpus': '16+'}]},
+            {'accelerators': ['A100:8', 'V100:8']},
+        ]),
+        _with_times(yaml_chain('chain_alternatives_time', [
+            {'accelerators': {'V100': 1, 'T4': 1}},
+            {'cpus': '8+', 'any_of': [{'cloud': 'aws'}, {'cloud': 'gcp'}]},
+        ], minimize='time'), [
+            {'default': 3600, 'by_acc': {'V100': 1800, 'T4': 3000}},
+            {'default': 1200, 'by_cloud': {'aws': 1000, 'gcp': 900}},
+        ]),
+    ]
+
+
+def _with_times(scenario, estimators):
+    """Distinct run times per alternative: with equal times the reference's
+    pick among a *set* of requests is its address order."""
+    for task, est in zip(scenario['tasks'], estimators):
+        task['time_est'] = est
+    return scenario
+
+
+def region_filter_scenarios():
+    """The region allow-list of Resources.get_valid_regions_for_launchable
+    (sky/resources.py:1210-1246): a per-region ssh_proxy_command in the
+    SkyPilot config restricts the regions of that cloud's launchables."""
+    proxy = {'aws': {'ssh_proxy_command': {
+        'us-east-2': 'ssh -W %h:%p jump-a', 'eu-west-1': 'ssh -W %h:%p jump-b',
+        'ap-south-1': 'ssh -W %h:%p jump-c'}}}
+    proxy_str = {'aws': {'ssh_proxy_command': 'ssh -W %h:%p jump'}}
+    # (A per-region image_id dict takes the same device path -- the slot's
+    # region_set -- but the reference validates image ids against the cloud's
+    # API at Resources construction (aws.py get_image_size), which needs
+    # credentials: no offline fixture; tests/test_host_logic.py covers the
+    # host side of that filter.)
+    s = [
+        dict(_single('proxy_v100', accelerators='V100'), config=proxy),
+        dict(_single('proxy_cpu_aws', cloud='aws', cpus='8+'), config=proxy),
+        dict(_single('proxy_spot', cloud='aws', accelerators='T4',
+                     use_spot=True), config=proxy),
+        dict(_single('proxy_region_outside', cloud='aws', region='us-east-1',
+                     cpus='4+'), config=proxy),
+        dict(_single('proxy_string_no_filter', cloud='aws', cpus='8+'),
+             config=proxy_str),
+        dict(_chain('proxy_chain', [
+            {'accelerators': 'V100', 'outputs_gb': 100},
+            {'cpus': '8+', 'cloud': 'aws', 'outputs_gb': 10},
+            {'accelerators': 'A100:8'},
+        ]), config=proxy),
+    ]
+    return s
+
+
 def fuzz_many_scenarios():
     """The same generator over ten clouds at once (enabled-cloud order, ties
     and egress between many clouds)."""
@@ -1050,7 +1168,9 @@ BIG_SUITES = {
 }
 
 # suites with their own tests (not part of the per-scenario sweeps)
-EXTRA_GOLDEN_SUITES = {'bigdag': big_dag_scenarios}
+EXTRA_GOLDEN_SUITES = {'bigdag': big_dag_scenarios,
+                       'altres': alternatives_scenarios,
+                       'regfilter': region_filter_scenarios}
 
 ALL_SUITES = dict(SUITES, **LATE_SUITES)
 

@@ -47,8 +47,9 @@ def test_struct_layouts_match_header():
     assert _native.QUERY_DTYPE.itemsize == 88
     assert _native.QUERY_DTYPE.fields['cpus'][1] == 56
     assert _native.QUERY_DTYPE.fields['max_price'][1] == 80
-    assert _native.SLOT_DTYPE.itemsize == 72
-    assert _native.SLOT_DTYPE.fields['hours'][1] == 48
+    assert _native.SLOT_DTYPE.itemsize == 80
+    assert _native.SLOT_DTYPE.fields["region_set"][1] == 48
+    assert _native.SLOT_DTYPE.fields["hours"][1] == 56
     assert _native.CANDIDATE_DTYPE.fields['hourly'][1] == 16
     assert _native.DAG_RESULT_DTYPE.fields['objective'][1] == 8
     assert ctypes.sizeof(_native.Stats) == 56
@@ -473,3 +474,102 @@ def test_free_clouds_are_stated_with_zero_hours():
     assert packs[0] == packs[1]
     assert np.isclose(
         sky.clouds.Vsphere().instance_type_to_hourly_cost('cpu_8', False), 0.0)
+
+
+def test_no_cloud_is_enabled_until_someone_says_so(store):
+    """check.py: nothing configured -> NoCloudAccessError (never 'every cloud
+    of the catalog'); an explicit list, a provider callback, or the explicit
+    catalog-wide opt-in enable clouds."""
+    from skypilot_b200 import check
+    sky.catalog.set_store(store)
+    try:
+        check.set_enabled_clouds(None)
+        check.set_enabled_clouds_provider(None)
+        assert check.get_cached_enabled_clouds_or_refresh() == []
+        with pytest.raises(sky.exceptions.NoCloudAccessError):
+            check.get_cached_enabled_clouds_or_refresh(
+                raise_if_no_cloud_access=True)
+        check.set_enabled_clouds_provider(lambda **kw: ['AWS', 'gcp'])
+        assert [str(c) for c in check.get_cached_enabled_clouds_or_refresh()
+               ] == ['AWS', 'GCP']
+        check.set_enabled_clouds(['azure'])  # an explicit list wins
+        assert [str(c) for c in check.get_cached_enabled_clouds_or_refresh()
+               ] == ['Azure']
+        check.set_enabled_clouds(check.ALL_CATALOG_CLOUDS)
+        assert len(check.get_cached_enabled_clouds_or_refresh()) == len(
+            store.clouds)
+    finally:
+        check.set_enabled_clouds_provider(None)
+        check.set_enabled_clouds(check.ALL_CATALOG_CLOUDS)
+
+
+def test_image_tags(store):
+    import pandas as pd
+    sky.catalog.set_store(store)
+    store.set_images('aws', pd.DataFrame({
+        'Tag': ['skypilot:gpu-ubuntu-2004', 'skypilot:gpu-ubuntu-2004', 'x'],
+        'Region': ['us-east-1', 'us-west-2', 'us-east-1'],
+        'ImageId': ['ami-1', 'ami-2', None]
+    }))
+    cat = sky.catalog
+    assert cat.get_image_id_from_tag('skypilot:gpu-ubuntu-2004', 'US-EAST-1',
+                                     clouds='aws') == 'ami-1'
+    assert cat.get_image_id_from_tag('x', 'us-east-1', clouds='aws') is None
+    assert not cat.is_image_tag_valid('x', 'us-east-1', clouds='aws')
+    assert cat.is_image_tag_valid('skypilot:gpu-ubuntu-2004', None,
+                                  clouds='aws')
+    with pytest.raises(AssertionError, match='Multiple images'):
+        cat.get_image_id_from_tag('skypilot:gpu-ubuntu-2004', None,
+                                  clouds='aws')
+    assert cat.get_image_id_from_tag('nope', None, clouds='gcp') is None
+
+
+def test_timeline_hook(tmp_path, monkeypatch):
+    from skypilot_b200.utils import timeline
+    path = tmp_path / 'trace.json'
+    monkeypatch.setenv('SKYPILOT_TIMELINE_FILE_PATH', str(path))
+
+    @timeline.event
+    def work(x):
+        return x + 1
+
+    with timeline.Event('outer', 'msg'):
+        assert work(1) == 2
+    timeline.save()
+    import json
+    events = json.loads(path.read_text())['traceEvents']
+    names = [(e['name'], e['ph']) for e in events[-4:]]
+    assert names == [('outer', 'B'), (f'{__name__}.test_timeline_hook.<locals>.work', 'B'),
+                     (f'{__name__}.test_timeline_hook.<locals>.work', 'E'), ('outer', 'E')]
+    assert sky.Optimizer.optimize.__wrapped__ is not None
+
+
+# ---- region allow-lists (sky/resources.py:1210-1246) ------------------------
+def test_ssh_proxy_config_restricts_regions(tmp_path):
+    from skypilot_b200 import skypilot_config
+    gen = skypilot_config.generation()
+    try:
+        skypilot_config.set_config(
+            {'aws': {'ssh_proxy_command': {'us-east-1': 'ssh a',
+                                           'eu-west-1': 'ssh b'}},
+             'gcp': {'ssh_proxy_command': 'ssh -W %h:%p jump'}})
+        assert skypilot_config.generation() > gen
+        assert skypilot_config.allowed_regions_by_ssh_proxy('aws') == {
+            'us-east-1', 'eu-west-1'}
+        # one command for every region restricts nothing; unset neither
+        assert skypilot_config.allowed_regions_by_ssh_proxy('gcp') is None
+        assert skypilot_config.allowed_regions_by_ssh_proxy('azure') is None
+        r = sky.Resources(cloud=sky.clouds.AWS(),
+                          image_id={'us-east-1': 'ami-1', 'us-west-2': 'ami-2'})
+        assert r.allowed_region_names() == {'us-east-1'}
+        assert sky.Resources(cloud=sky.clouds.GCP()).allowed_region_names() \
+            is None
+        # a config file is read like the reference's ~/.sky/config.yaml
+        path = tmp_path / 'config.yaml'
+        path.write_text('aws:\n  ssh_proxy_command:\n    us-west-2: ssh c\n')
+        skypilot_config.load(str(path))
+        assert skypilot_config.allowed_regions_by_ssh_proxy('aws') == {
+            'us-west-2'}
+    finally:
+        skypilot_config.set_config(None)
+    assert skypilot_config.allowed_regions_by_ssh_proxy('aws') is None

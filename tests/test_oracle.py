@@ -50,7 +50,10 @@ def test_oracle_matches_reference_fixture(catalog, scenario):
     got = oo.run_scenario(spec, scenario)
     unordered = any(
         t.get('resources_kind') == 'set' for t in scenario['tasks'])
-    diffs = runner.compare(records[scenario['name']], got, unordered)
+    # the port restates the algorithm, not the error text: the class of the
+    # error is compared, the message only for the product (GPU tests)
+    diffs = runner.compare(records[scenario['name']], got, unordered,
+                           check_message=False)
     assert not diffs, '\n'.join(diffs)
 
 
