@@ -88,6 +88,10 @@ def write_catalogs(home: str, catalogs: Dict[str, 'object'],
     from skypilot_b200 import synth  # pylint: disable=import-outside-toplevel
     synth.accelerator_metadata().to_csv(
         os.path.join(root, 'common', 'metadata.csv'), index=False)
+    # <cloud>/images.csv behind `skypilot:` image tags
+    # (sky/catalog/aws_catalog.py:87, :355-372)
+    for cloud, frame in synth.images(catalogs).items():
+        frame.to_csv(os.path.join(root, cloud, 'images.csv'), index=False)
 
 
 def import_reference(home: str, enabled_clouds: Sequence[str]):

@@ -24,15 +24,20 @@ def main():
     """`gen_golden.py [catalog ...]` regenerates the optimizer fixtures,
     `gen_golden.py --listings [catalog ...]` the accelerator listings
     (tests/golden/accel_<catalog>.json), `--job-groups` the JobGroup plans
-    (tests/golden/jobgroup_<catalog>.json)."""
+    (tests/golden/jobgroup_<catalog>.json), `--calls` the catalog function
+    calls (tests/golden/calls_<catalog>.json)."""
     argv = sys.argv[1:]
     listings = '--listings' in argv
     groups = '--job-groups' in argv
-    argv = [a for a in argv if a not in ('--listings', '--job-groups')]
+    calls = '--calls' in argv
+    argv = [a for a in argv
+            if a not in ('--listings', '--job-groups', '--calls')]
     suites = (scenarios.LISTING_SUITES if listings else
               scenarios.JOB_GROUP_SUITES if groups else
+              scenarios.CALL_SUITES if calls else
               dict(scenarios.ALL_SUITES, **scenarios.EXTRA_GOLDEN_SUITES))
-    prefix = 'accel_' if listings else 'jobgroup_' if groups else ''
+    prefix = ('accel_' if listings else 'jobgroup_' if groups else
+              'calls_' if calls else '')
     wanted = argv or [k for k in suites
                       if k not in scenarios.EXTRA_GOLDEN_SUITES or not argv]
     out_dir = os.path.join(_REPO, 'tests', 'golden')

@@ -181,6 +181,36 @@ def run_listing(sky, scenario):
             'order': list(result.keys())}
 
 
+def _jsonable(x):
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, dict):
+        return {str(k): _jsonable(v) for k, v in x.items()}
+    if x is None or isinstance(x, (bool, str)):
+        return x
+    if isinstance(x, (int, float)) or hasattr(x, 'dtype'):
+        v = float(x)
+        if math.isnan(v):
+            return None
+        return int(v) if isinstance(x, int) else v
+    if hasattr(x, 'name'):  # Region / Zone
+        return x.name
+    return str(x)
+
+
+def run_call(sky, scenario):
+    """One call of the catalog function table (sky/catalog/__init__.py)."""
+    from sky import catalog
+    bootstrap.clear_request_cache()
+    fn = getattr(catalog, scenario['fn'])
+    try:
+        result = fn(*scenario.get('args', []), **scenario.get('kwargs', {}))
+    except Exception as e:  # pylint: disable=broad-except
+        return {'name': scenario['name'],
+                'error': {'type': type(e).__name__, 'message': str(e)}}
+    return {'name': scenario['name'], 'result': _jsonable(result)}
+
+
 def run_job_group(sky, scenario):
     """`Optimizer.optimize_job_group` (sky/optimizer.py:1039-1200) on a
     parallel-execution DAG. Besides the plan, records the common infras the
@@ -244,6 +274,8 @@ def run_scenario(sky, scenario):
         return run_listing(sky, scenario)
     if scenario.get('kind') == 'job_group':
         return run_job_group(sky, scenario)
+    if scenario.get('kind') == 'catalog_call':
+        return run_call(sky, scenario)
     from sky import exceptions
     from sky import optimizer as opt_lib
     from sky.utils import common as sky_common

@@ -233,6 +233,26 @@ class Cloud:
                 f'The following features are not supported by {cls._REPR}:'
                 f'\n\tFeature | Reason\n\t{rows}')
 
+    # ---- images --------------------------------------------------------------
+    # Size of a cloud's stock images in GB: what the reference answers for a
+    # `skypilot:` tag and when no credentials are present
+    # (sky/clouds/aws.py:59, :547-569; sky/clouds/gcp.py:96, :405-422).
+    _DEFAULT_IMAGE_GB = 0.0
+
+    @classmethod
+    def is_image_tag_valid(cls, image_tag: str, region: Optional[str]) -> bool:
+        """sky/clouds/cloud.py is_image_tag_valid: <cloud>/images.csv."""
+        return _late('catalog').is_image_tag_valid(image_tag, region,
+                                                   clouds=cls._CATALOG)
+
+    @classmethod
+    def get_image_size(cls, image_id: str, region: Optional[str]) -> float:
+        """GB of the image. The size of a custom image is a cloud API call in
+        the reference; offline it answers the stock size, as the reference
+        does without credentials."""
+        del image_id, region
+        return float(cls._DEFAULT_IMAGE_GB)
+
     def _check_instance_type_accelerators_combination(self,
                                                       resources: Any) -> None:
         del resources

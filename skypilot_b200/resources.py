@@ -12,6 +12,7 @@ from typing import Any, Dict, List, Optional, Set, Tuple, Union
 
 from skypilot_b200 import check as sky_check
 from skypilot_b200 import clouds
+from skypilot_b200 import exceptions
 from skypilot_b200.utils import registry
 from skypilot_b200.utils import resources_utils
 
@@ -155,6 +156,64 @@ class Resources:
         self._local_disk = (None if local_disk is None else
                             resources_utils.normalize_local_disk(local_disk))
         self._max_hourly_cost = max_hourly_cost
+        if self._image_id is not None:
+            self._try_validate_image_id()
+
+    def _try_validate_image_id(self) -> None:
+        """The checks of Resources._try_validate_image_id that need no cloud
+        API (sky/resources.py:1384-1500): docker images and custom images as
+        features of the cloud, the image of a pinned region, `skypilot:` tags
+        against <cloud>/images.csv, the stock image against disk_size."""
+        f = clouds.CloudImplementationFeatures
+        if self.extract_docker_image() is not None:
+            if self._cloud is not None:
+                self._cloud.check_features_are_supported(self,
+                                                         {f.DOCKER_IMAGE})
+            return
+        if self._cloud is None:
+            raise ValueError(
+                'Cloud must be specified when image_id is provided.')
+        try:
+            self._cloud.check_features_are_supported(self, {f.IMAGE_ID})
+        except exceptions.NotSupportedError as e:
+            if self._cloud.is_same_cloud(clouds.Lambda()):
+                raise ValueError(
+                    'Lambda cloud only supports Docker images. '
+                    'Please prefix your image with "docker:" '
+                    '(e.g., image_id: docker:your-image-name).') from e
+            raise ValueError(
+                'image_id is only supported for AWS/GCP/Azure/IBM/OCI/'
+                'Kubernetes/Nebius. For Lambda cloud, use "docker:" '
+                'prefix for Docker images.') from e
+        if self._region is not None:
+            if None in self._image_id:
+                self._image_id = {self._region: self._image_id[None]}
+            elif self._region not in self._image_id:
+                raise ValueError(
+                    f'image_id {self._image_id} should contain the image '
+                    f'for the specified region {self._region}.')
+            else:
+                self._image_id = {self._region: self._image_id[self._region]}
+        for region, image_id in self._image_id.items():
+            if (image_id.startswith('skypilot:') and
+                    not self._cloud.is_image_tag_valid(image_id, region)):
+                region_str = f' ({region})' if region else ''
+                raise ValueError(
+                    f'Image tag {image_id!r} is not valid, please make sure'
+                    f' the tag exists in {self._cloud}{region_str}.')
+            if (self._cloud.is_same_cloud(clouds.AWS()) and
+                    not image_id.startswith('skypilot:') and region is None):
+                raise ValueError(
+                    'image_id is only supported for AWS in a specific '
+                    'region, please explicitly specify the region.')
+        for region, image_id in self._image_id.items():
+            image_size = self._cloud.get_image_size(image_id, region)
+            if image_size > self.disk_size:
+                raise ValueError(
+                    f'Image {image_id!r} is {image_size}GB, which is '
+                    f'larger than the specified disk_size: {self.disk_size}'
+                    ' GB. Please specify a larger disk_size to use this '
+                    'image.')
 
     # ---- setters ------------------------------------------------------------
     def _set_cpus(self, cpus) -> None:

@@ -836,6 +836,39 @@ ACCELERATOR_METADATA = [
 ]
 
 
+def images(catalogs: Dict[str, pd.DataFrame]) -> Dict[str, pd.DataFrame]:
+    """<cloud>/images.csv (Tag, Region, OS, OSVersion, ImageId,
+    CreationDate) for the clouds that keep one: two stock tags in every AWS
+    region but sa-east-1 / me-south-1 ('skypilot:k80-ubuntu-2004' in us-east-1
+    only, one row without an image id), region-less tags on GCP."""
+    out: Dict[str, pd.DataFrame] = {}
+    cols = ['Tag', 'Region', 'OS', 'OSVersion', 'ImageId', 'CreationDate']
+    if 'aws' in catalogs:
+        regions = sorted(set(catalogs['aws']['Region']))
+        rows = []
+        first = 'us-east-1' if 'us-east-1' in regions else regions[0]
+        for i, r in enumerate(regions):
+            if r in ('sa-east-1', 'me-south-1'):
+                continue
+            rows.append(['skypilot:gpu-ubuntu-2004', r, 'ubuntu', '20.04',
+                         f'ami-{i:04d}a2004', '2024-01-01'])
+            rows.append(['skypilot:cpu-ubuntu-2204', r, 'ubuntu', '22.04',
+                         f'ami-{i:04d}c2204', '2024-01-01'])
+        rows.append(['skypilot:k80-ubuntu-2004', first, 'ubuntu',
+                     '20.04', 'ami-0000k2004', '2024-01-01'])
+        rows.append(['skypilot:broken', first, 'ubuntu', '20.04', None,
+                     '2024-01-01'])
+        out['aws'] = pd.DataFrame(rows, columns=cols)
+    if 'gcp' in catalogs:
+        out['gcp'] = pd.DataFrame(
+            [['skypilot:gpu-debian-11', None, 'debian', '11',
+              'projects/sky/global/images/gpu-debian-11', '2024-01-01'],
+             ['skypilot:cpu-debian-11', None, 'debian', '11',
+              'projects/sky/global/images/cpu-debian-11', '2024-01-01']],
+            columns=cols)
+    return out
+
+
 def accelerator_metadata() -> pd.DataFrame:
     return pd.DataFrame(ACCELERATOR_METADATA,
                         columns=['GPU', 'MemoryGB', 'Manufacturer'])

@@ -37,6 +37,8 @@ def activate_catalog(spec: Dict[str, Any]):
         store = CatalogStore.from_frames(frames)
         store.enabled = enabled
         store.set_accelerator_metadata(synth.accelerator_metadata())
+        for cloud, frame in synth.images(frames).items():
+            store.set_images(cloud, frame)
         _loaded[key] = store
     sky.catalog.set_store(store)
     sky.check.set_enabled_clouds(
@@ -111,6 +113,10 @@ def run_scenario(scenario, with_candidates: bool = True) -> Dict[str, Any]:
             'type': 'ResourcesUnavailableError',
             'message': str(e)
         }
+    except ValueError as e:
+        # an invalid request (e.g. an image tag the cloud does not have):
+        # the reference raises while the Resources is constructed
+        record['error'] = {'type': 'ValueError', 'message': str(e)}
     return record
 
 

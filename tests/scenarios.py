@@ -676,11 +676,12 @@ def region_filter_scenarios():
         'us-east-2': 'ssh -W %h:%p jump-a', 'eu-west-1': 'ssh -W %h:%p jump-b',
         'ap-south-1': 'ssh -W %h:%p jump-c'}}}
     proxy_str = {'aws': {'ssh_proxy_command': 'ssh -W %h:%p jump'}}
-    # (A per-region image_id dict takes the same device path -- the slot's
-    # region_set -- but the reference validates image ids against the cloud's
-    # API at Resources construction (aws.py get_image_size), which needs
-    # credentials: no offline fixture; tests/test_host_logic.py covers the
-    # host side of that filter.)
+    # `skypilot:` image tags resolve through <cloud>/images.csv
+    # (synth.images); a custom image id would need the cloud's API
+    # (aws.py get_image_size) and has no offline fixture.
+    gpu_tag, cpu_tag = 'skypilot:gpu-ubuntu-2004', 'skypilot:cpu-ubuntu-2204'
+    images = {'us-west-2': gpu_tag, 'eu-central-1': gpu_tag,
+              'eu-west-1': gpu_tag}
     s = [
         dict(_single('proxy_v100', accelerators='V100'), config=proxy),
         dict(_single('proxy_cpu_aws', cloud='aws', cpus='8+'), config=proxy),
@@ -695,6 +696,36 @@ def region_filter_scenarios():
             {'cpus': '8+', 'cloud': 'aws', 'outputs_gb': 10},
             {'accelerators': 'A100:8'},
         ]), config=proxy),
+        _single('image_dict_aws', cloud='aws', accelerators='V100',
+                image_id=images),
+        _single('image_dict_cpu_spot', cloud='aws', cpus='4+', use_spot=True,
+                image_id={'us-east-2': cpu_tag, 'ca-central-1': cpu_tag}),
+        _single('image_tag_every_region', cloud='aws', accelerators='T4',
+                image_id=gpu_tag),
+        _single('image_tag_region', cloud='aws', accelerators='T4',
+                region='us-west-2', image_id=gpu_tag),
+        _single('image_gcp_tag', cloud='gcp', accelerators='V100',
+                image_id='skypilot:gpu-debian-11'),
+        dict(_single('image_and_proxy', cloud='aws', accelerators='V100',
+                     image_id=images), config=proxy),
+        dict(_single('image_and_proxy_disjoint', cloud='aws', cpus='4+',
+                     image_id={'us-west-2': cpu_tag}), config=proxy),
+        _single('image_tag_invalid', cloud='aws', cpus='4+',
+                image_id='skypilot:no-such-tag'),
+        _single('image_tag_wrong_region', cloud='aws', cpus='4+',
+                image_id={'us-east-1': 'skypilot:k80-ubuntu-2004',
+                          'us-east-2': 'skypilot:k80-ubuntu-2004'}),
+        _single('image_region_missing', cloud='aws', cpus='4+',
+                region='us-east-1', image_id={'us-west-2': cpu_tag}),
+        _single('image_too_big', cloud='aws', cpus='4+', disk_size=30,
+                image_id=cpu_tag),
+        _single('image_lambda', cloud='lambda', accelerators='A100',
+                image_id='some-image'),
+        _chain('image_chain', [
+            {'accelerators': 'V100', 'cloud': 'aws', 'image_id': images,
+             'outputs_gb': 50},
+            {'cpus': '8+', 'outputs_gb': 10},
+        ]),
     ]
     return s
 
@@ -1228,6 +1259,142 @@ def listing_cases(clouds=('aws', 'gcp', 'azure', 'lambda')):
         s.append(_listing('two_clouds', clouds=clouds[:2],
                           name_filter='V100|T4'))
     return s
+
+
+def catalog_call_cases():
+    """Calls of the catalog function table (sky/catalog/__init__.py) whose
+    answers the reference gives offline: {'name', 'kind': 'catalog_call',
+    'fn', 'args', 'kwargs'}; the record holds the JSON-plain result or the
+    exception's class and text."""
+    out = []
+
+    def call(name, fn, *args, **kwargs):
+        out.append({'name': name, 'kind': 'catalog_call', 'fn': fn,
+                    'args': list(args), 'kwargs': kwargs})
+
+    att = 'check_accelerator_attachable_to_host'
+    # GCP host rules (sky/catalog/gcp_catalog.py:584-683), one per branch
+    for i, (inst, acc, zone) in enumerate([
+        ('n1-standard-8', {'V100': 1}, None),
+        ('n1-standard-8', None, None),
+        ('a2-highgpu-1g', None, None),
+        ('a2-highgpu-1g', {'A100': 1}, None),
+        ('a2-highgpu-2g', {'A100': 1}, None),
+        ('n1-standard-8', {'A100': 1}, None),
+        ('a2-highgpu-1g', {'V100': 1}, None),
+        ('n2-highmem-16', {'T4': 1}, None),
+        ('n1-standard-8', {'V100': 3}, None),
+        ('n1-highcpu-96', {'V100': 1}, None),
+        ('n1-highmem-16', {'V100': 1}, None),
+        ('n1-highmem-32', {'T4': 1}, None),
+        ('n1-standard-96', {'V100': 8}, None),
+        ('n1-highmem-96', {'K80': 8}, None),
+        ('n1-highmem-96', {'K80': 8}, 'us-east1-d'),
+        ('n1-highmem-64', {'K80': 8}, 'us-east1-d'),
+        ('n1-standard-96', {'P100': 4}, None),
+        ('n1-standard-96', {'P100': 4}, 'us-east1-c'),
+        ('n1-standard-64', {'P100': 4}, 'europe-west1-b'),
+        ('n1-highmem-64', {'P100': 4}, 'europe-west1-d'),
+        ('g2-standard-4', {'L4': 1}, None),
+        ('g2-standard-24', {'L4': 1}, None),
+        ('g2-standard-24', {'L4': 2}, None),
+        ('a3-highgpu-8g', {'H100': 8}, None),
+        ('a3-highgpu-8g', {'H100': 4}, None),
+        ('a3-megagpu-8g', {'H100-MEGA': 8}, None),
+        ('a2-ultragpu-4g', {'A100-80GB': 4}, None),
+        ('a2-ultragpu-4g', {'A100-80GB': 3}, None),
+        ('n1-standard-8', {'tpu-v3-8': 1}, None),
+        ('n2-highmem-16', {'tpu-v3-8': 1}, None),
+        ('TPU-VM', {'tpu-v3-8': 1}, None),
+        ('n1-standard-16', {'P4': 4}, None),
+        ('n1-standard-8', {'T4': 8}, None),
+    ]):
+        call(f'attach_{i:02d}', att, inst, acc, zone, clouds='gcp')
+    # accelerator counts of every cloud (sky/catalog/__init__.py:88-118)
+    clouds = ['aws', 'gcp', 'azure']
+    call('counts_default', 'list_accelerator_counts', clouds=clouds)
+    call('counts_all', 'list_accelerator_counts', gpus_only=False,
+         clouds=clouds)
+    call('counts_a100', 'list_accelerator_counts', name_filter='A100',
+         clouds=clouds)
+    call('counts_us', 'list_accelerator_counts', region_filter='us-',
+         clouds=clouds)
+    call('counts_q4', 'list_accelerator_counts', quantity_filter=4,
+         clouds=clouds)
+    for c in clouds:
+        call(f'counts_{c}', 'list_accelerator_counts', clouds=c)
+    # image tags (<cloud>/images.csv; sky/catalog/common.py:813-843)
+    gpu_tag = 'skypilot:gpu-ubuntu-2004'
+    for i, (tag, region, cloud) in enumerate([
+        (gpu_tag, 'us-east-1', 'aws'), (gpu_tag, 'eu-west-1', 'aws'),
+        (gpu_tag, 'sa-east-1', 'aws'), (gpu_tag, 'US-EAST-1', 'aws'),
+        ('skypilot:k80-ubuntu-2004', None, 'aws'),
+        ('skypilot:k80-ubuntu-2004', 'us-east-2', 'aws'),
+        ('skypilot:broken', 'us-east-1', 'aws'),
+        ('skypilot:nope', None, 'aws'), (gpu_tag, None, 'aws'),
+        ('skypilot:gpu-debian-11', None, 'gcp'),
+        ('skypilot:nope', None, 'gcp'),
+    ]):
+        call(f'image_id_{i:02d}', 'get_image_id_from_tag', tag, region,
+             clouds=cloud)
+        call(f'image_valid_{i:02d}', 'is_image_tag_valid', tag, region,
+             clouds=cloud)
+    # a few of the scalar look-ups beside them
+    for i, (inst, cloud) in enumerate([
+        ('p3.2xlarge', 'aws'), ('n1-standard-8', 'gcp'),
+        ('a2-highgpu-4g', 'gcp'), ('Standard_NC6s_v3', 'azure'),
+        ('no-such-type', 'aws')]):
+        call(f'exists_{i}', 'instance_type_exists', inst, clouds=cloud)
+        call(f'vcpus_mem_{i}', 'get_vcpus_mem_from_instance_type', inst,
+             clouds=cloud)
+        call(f'accs_{i}', 'get_accelerators_from_instance_type', inst,
+             clouds=cloud)
+    for i, (kw, cloud) in enumerate([
+        ({}, 'aws'), ({'cpus': '16+'}, 'aws'), ({'memory': '64+'}, 'gcp'),
+        ({'cpus': '4', 'memory': '4x'}, 'azure'),
+        ({'cpus': '1000+'}, 'aws'), ({'region': 'us-west-2'}, 'aws'),
+        ({'cpus': '8+', 'use_spot': True, 'max_hourly_cost': 0.1}, 'aws')]):
+        call(f'default_type_{i}', 'get_default_instance_type', clouds=cloud,
+             **kw)
+    for i, (name, count, kw, cloud) in enumerate([
+        ('V100', 1, {}, 'aws'), ('V100', 1, {}, 'gcp'),
+        ('A100', 8, {'use_spot': True}, 'aws'),
+        ('T4', 1, {'cpus': '8+'}, 'gcp'), ('A100', 3, {}, 'aws'),
+        ('a100', 8, {}, 'gcp'), ('V100', 2, {'memory': '200+'}, 'azure'),
+        ('tpu-v3-8', 1, {}, 'gcp'), ('H100', 8, {'region': 'us-east5'}, 'gcp'),
+        ('NoSuch', 1, {}, 'aws')]):
+        call(f'for_acc_{i}', 'get_instance_type_for_accelerator', name, count,
+             clouds=cloud, **kw)
+        call(f'acc_zones_{i}', 'get_region_zones_for_accelerators', name,
+             count, kw.get('use_spot', False), clouds=cloud)
+    for i, (inst, spot, region, zone, cloud) in enumerate([
+        ('p3.2xlarge', False, None, None, 'aws'),
+        ('p3.2xlarge', True, 'us-east-1', None, 'aws'),
+        ('n1-standard-8', False, 'us-central1', 'us-central1-a', 'gcp'),
+        ('a2-highgpu-1g', True, None, None, 'gcp'),
+        ('Standard_NC6s_v3', False, 'eastus', None, 'azure'),
+        ('p3.2xlarge', False, 'nowhere-1', None, 'aws')]):
+        call(f'hourly_{i}', 'get_hourly_cost', inst, spot, region, zone,
+             clouds=cloud)
+    for i, (name, count, spot, region, zone) in enumerate([
+        ('V100', 1, False, None, None), ('V100', 4, True, 'us-central1', 'us-central1-a'),
+        ('A100', 8, False, None, None), ('tpu-v3-8', 1, False, None, None),
+        ('T4', 1, False, 'us-west1', 'us-west1-a')]):
+        call(f'acc_hourly_{i}', 'get_accelerator_hourly_cost', name, count,
+             spot, region, zone, clouds='gcp')
+    for i, (region, zone, cloud) in enumerate([
+        ('us-east-1', None, 'aws'), ('us-east-1', 'us-east-1a', 'aws'),
+        (None, 'us-east-1a', 'aws'), ('us-east-9', None, 'aws'),
+        ('us-east-1', 'us-west-2a', 'aws'), ('us-central1', 'us-central1-a',
+                                             'gcp'),
+        (None, 'us-central1-z', 'gcp'), ('eastus', None, 'azure'),
+        ('eastus', '1', 'azure')]):
+        call(f'validate_{i}', 'validate_region_zone', region, zone,
+             clouds=cloud)
+    return out
+
+
+CALL_SUITES = {'three4k': catalog_call_cases}
 
 
 LISTING_SUITES = {
