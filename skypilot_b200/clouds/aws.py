@@ -12,7 +12,7 @@ class AWS(cloud.Cloud):
     on-demand candidates, zone-level spot candidates (aws.py:347-370)."""
     _REPR = 'AWS'
     _CATALOG = 'aws'
-    _DEFAULT_IMAGE_GB = 45.0  # DEFAULT_AMI_GB, sky/clouds/aws.py:59
+    _DEFAULT_IMAGE_GB = 45  # DEFAULT_AMI_GB, sky/clouds/aws.py:59
 
     @classmethod
     def _unsupported_features_for_resources(cls, resources: Any,

@@ -100,6 +100,9 @@ class Cloud:
     _REPR = '<Cloud>'
     _CATALOG = ''  # key of the cloud in the catalog store
     _CLOUD_UNSUPPORTED_FEATURES: Dict[CloudImplementationFeatures, str] = {}
+    # the name in the feature-gate message when it is not _REPR (the reference's
+    # Shadeform prints the base class's '<Cloud>' there)
+    _FEATURES_REPR: Optional[str] = None
 
     # ---- identity ---------------------------------------------------------
     def __repr__(self):
@@ -230,14 +233,15 @@ class Cloud:
         if hit:
             rows = '\n\t'.join(f'{f.value} | {unsupported[f]}' for f in hit)
             raise exceptions.NotSupportedError(
-                f'The following features are not supported by {cls._REPR}:'
+                f'The following features are not supported by '
+                f'{cls._FEATURES_REPR or cls._REPR}:'
                 f'\n\tFeature | Reason\n\t{rows}')
 
     # ---- images --------------------------------------------------------------
     # Size of a cloud's stock images in GB: what the reference answers for a
     # `skypilot:` tag and when no credentials are present
     # (sky/clouds/aws.py:59, :547-569; sky/clouds/gcp.py:96, :405-422).
-    _DEFAULT_IMAGE_GB = 0.0
+    _DEFAULT_IMAGE_GB = 0
 
     @classmethod
     def is_image_tag_valid(cls, image_tag: str, region: Optional[str]) -> bool:
@@ -251,7 +255,7 @@ class Cloud:
         the reference; offline it answers the stock size, as the reference
         does without credentials."""
         del image_id, region
-        return float(cls._DEFAULT_IMAGE_GB)
+        return cls._DEFAULT_IMAGE_GB
 
     def _check_instance_type_accelerators_combination(self,
                                                       resources: Any) -> None:
@@ -292,10 +296,10 @@ class Cloud:
                 if not out.results['any_stage1'][plan.fuzzy_query]:
                     fuzzy = engine.format_fuzzy(
                         view.store, out.fuzzy_list(plan.fuzzy_query))
-            return resources_utils.FeasibleResources([], fuzzy, plan.hint)
+            return self._nothing_feasible(resources, fuzzy, plan.hint)
         if plan.explicit_instance is not None:
             if plan.slot is None:
-                return resources_utils.FeasibleResources([], [], plan.hint)
+                return self._nothing_feasible(resources, [], plan.hint)
             return resources_utils.FeasibleResources(
                 [plan.make(plan.explicit_instance, resources)], [], None)
         n_inst = max(len(view.table.inst_names), 1)
@@ -315,7 +319,7 @@ class Cloud:
             plan.fuzzy_query)
         if gate is not None and not out.results['any_stage1'][gate]:
             fuzzy = engine.format_fuzzy(view.store, out.fuzzy_list(gate))
-            return resources_utils.FeasibleResources([], fuzzy, None)
+            return self._nothing_feasible(resources, fuzzy, None)
         q = plan.list_query
         res = out.results[q]
         names: List[str] = []
@@ -328,7 +332,17 @@ class Cloud:
                 names = [view.store.inst_names[int(res['best_inst'])]]
         made = [plan.make(n, resources) for n in names]
         made = [m for m in made if m is not None]
+        if not made:
+            return self._nothing_feasible(resources, fuzzy, None)
         return resources_utils.FeasibleResources(made, fuzzy, None)
+
+    def _nothing_feasible(self, resources: Any, fuzzy: List[str],
+                          hint: Optional[str]
+                         ) -> resources_utils.FeasibleResources:
+        """The answer when no offering satisfies `resources`; a few clouds
+        word their own hint here (seeweb.py:337-345, shadeform.py:365-369)."""
+        del resources
+        return resources_utils.FeasibleResources([], fuzzy, hint)
 
     @staticmethod
     def _request_key(resources: Any) -> tuple:

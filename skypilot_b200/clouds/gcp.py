@@ -35,7 +35,7 @@ def is_tpu_vm(resources: Optional[Any]) -> bool:
 class GCP(cloud.Cloud):
     _REPR = 'GCP'
     _CATALOG = 'gcp'
-    _DEFAULT_IMAGE_GB = 50.0  # DEFAULT_GCP_IMAGE_GB, sky/clouds/gcp.py:96
+    _DEFAULT_IMAGE_GB = 50  # DEFAULT_GCP_IMAGE_GB, sky/clouds/gcp.py:96
 
     @classmethod
     def _unsupported_features_for_resources(cls, resources: Any,

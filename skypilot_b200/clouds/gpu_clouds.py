@@ -488,6 +488,24 @@ class Seeweb(_GpuCloud):
         _F.LOCAL_DISK: 'Local disk is not supported on Seeweb',
     }
 
+    def _nothing_feasible(self, resources, fuzzy, hint):
+        # the texts of seeweb.py:337-345, :363-381 (spacing as there)
+        if hint is None:
+            accs = resources.accelerators
+            if resources.instance_type is not None:
+                if not self._catalog_module().instance_type_exists(
+                        resources.instance_type):
+                    hint = (f'Instance type {resources.instance_type}'
+                            ' not available on Seeweb')
+            elif accs:
+                acc_name, acc_count = list(accs.items())[0]
+                hint = ('No instance type found for accelerator'
+                        f'{acc_name}:{acc_count} on Seeweb')
+            else:
+                hint = ('No suitable instance type found for'
+                        f'cpus={resources.cpus}, memory={resources.memory}')
+        return resources_utils.FeasibleResources([], fuzzy, hint)
+
 
 @registry.CLOUD_REGISTRY.register
 class Shadeform(_GpuCloud):
@@ -495,6 +513,7 @@ class Shadeform(_GpuCloud):
     accelerator look-up sees only the accelerator and the price cap
     (shadeform.py:40-115, :300-395; shadeform_catalog.py:29-47)."""
     _REPR = 'Shadeform'
+    _FEATURES_REPR = '<Cloud>'  # the reference's class sets no _REPR
     _CATALOG = 'shadeform'
     _ZONE_MESSAGE = 'Shadeform does not support zones.'
     _UNSUPPORTED = {
@@ -516,6 +535,18 @@ class Shadeform(_GpuCloud):
             'Custom multiple network interfaces not supported.',
         _F.LOCAL_DISK: 'Local disk is not supported on Shadeform.',
     }
+
+    def _nothing_feasible(self, resources, fuzzy, hint):
+        # shadeform.py:365-369: the near misses go into the hint, not into
+        # the optimizer's "Try one of these" list
+        accs = resources.accelerators
+        if hint is None and accs and resources.instance_type is None:
+            hint = ('No instances available for accelerator '
+                    f'{list(accs.keys())[0]}')
+            if fuzzy:
+                hint += f': {"; ".join(fuzzy)}'
+            fuzzy = []
+        return resources_utils.FeasibleResources([], fuzzy, hint)
 
 
 @registry.CLOUD_REGISTRY.register

@@ -22,7 +22,7 @@ class Lambda(cloud.Cloud):
             features.CLONE_DISK_FROM_CLUSTER:
                 'Migrating disk is currently not supported on Lambda.',
             features.SPOT_INSTANCE:
-                'Spot instances are not supported in Lambda Cloud.',
+                'Spot instances are not supported in Lambda.',
             features.IMAGE_ID:
                 'Specifying image ID is not supported in Lambda Cloud.',
             features.CUSTOM_DISK_TIER:

@@ -201,7 +201,7 @@ struct Plan {
   size_t scan2_smem = 0; int64_t layout_rows = 0;
   Scan2Group *groups2; const Scan2Group *host_groups2 = nullptr; uint32_t *best_rank, *any_in;
   PlaceTask *ptasks; SlotAux *saux; uint32_t cap_fa = 0, cap_cm = 0, cap_rz = 0;
-  int32_t *dag_done; unsigned long long *task_mv; uint32_t *shared_tables; unsigned int *group_ready; bool chain_dags = false; int step_grid = 0; size_t step_smem = 0; mutable bool ran_fused = false;
+  int32_t *dag_done; TaskMin *task_mv; uint32_t *shared_tables; unsigned int *group_ready; bool chain_dags = false; int step_grid = 0; size_t step_smem = 0; mutable bool ran_fused = false;
   // input region (mirrored host/device)
   size_t in_bytes = 0;
   SkyoptQuery *queries; uint32_t *acc_sets; SkyoptSlot *slots; SkyoptTask *tasks;
@@ -254,7 +254,7 @@ void carve_rest(Plan &P, Carver &c) {
   P.list_min = c.take<unsigned long long>(P.list_entries);
   P.fuzzy_min = c.take<unsigned long long>(P.fuzzy_entries);
   P.gbest = c.take<unsigned long long>(P.nsq);
-  P.task_mv = c.take<unsigned long long>(P.fast ? (size_t)P.nt * SKYOPT_MAX_CLOUDS : 0);
+  P.task_mv = c.take<TaskMin>(P.fast ? (size_t)P.nt * SKYOPT_MAX_CLOUDS : 0);
   P.shared_tables = c.take<uint32_t>((size_t)P.n_groups2 * (2 * P.cap_fa + P.cap_cm + P.cap_rz));
   P.cand_region = c.take<int32_t>(P.cand_cap);
   P.cand_zone = c.take<int32_t>(P.cand_cap);
@@ -764,6 +764,7 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     static const int exp_flags = [] { const char *e = getenv("SKYOPT_EXP"); return e ? atoi(e) : 0; }();
     if (!(exp_flags & 2)) { sp.scan.shared_tables = P.shared_tables; sp.scan.group_ready = P.group_ready; }
     if (exp_flags & 4) sp.scan.noprune |= 4u;  // experiment: spin without nanosleep
+    sp.force_full = (exp_flags & 8) ? 1 : 0;   // test knob: evaluate every candidate in the chain DP
     sp.place.cat = cat->dev; sp.place.f = cat->fast; sp.place.ptasks = P.ptasks; sp.place.saux = P.saux;
     sp.place.best_rank = P.best_rank; sp.place.any1 = P.any_in; sp.place.acc_sets = P.acc_sets;
     sp.place.in = in0; sp.place.w = w0; sp.place.task_n = P.task_n; sp.place.trace = x->trace;

@@ -610,6 +610,19 @@ struct SlotAux {
 };
 static_assert(sizeof(SlotAux) == 32, "SlotAux layout");
 
+// The cheapest candidate of one (task, cloud): what the chain DP needs of a
+// task's candidate table. `idx` is the FIRST candidate (task order) with the
+// smallest value; `v2` the smallest value among the cloud's candidates in front
+// of it (all larger than vmin) -- the only ones that could take a first-minimum
+// tie from it after rounding (skyopt_step.cuh, "hazard").
+struct TaskMin {
+  unsigned long long vmin;  // price_key(value), kKeyNone = the cloud has no candidate
+  unsigned long long v2;    // price_key, kKeyNone = nothing in front
+  int32_t idx;
+  int32_t pad_[3];
+};
+static_assert(sizeof(TaskMin) == 32, "TaskMin layout");
+
 struct PlaceArgs {
   CatDev cat;
   FastCat f;
@@ -621,7 +634,7 @@ struct PlaceArgs {
   SolveIn in;
   SolveWork w;
   int32_t *task_n;
-  unsigned long long *task_mv;   // [n_tasks][n_clouds] price_key(min value) per cloud, or null
+  TaskMin *task_mv;   // [n_tasks][n_clouds] cheapest candidate of every cloud, or null
   unsigned long long *trace;
 };
 
@@ -633,6 +646,9 @@ struct PlaceSlot {
   int32_t cand_acc;
   int32_t n_e[2], n_b[2];  // kept before / after the blocked filter, [us, other]
   unsigned long long vmin; // price_key of the cheapest unblocked candidate's value
+  unsigned long long v2;   // ... of the cheapest one in front of it (kKeyNone: none)
+  int32_t vidx;            // first candidate (index in the task) with that value
+  int32_t pad_;
 };
 
 struct PlaceSmem {
@@ -737,6 +753,7 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
     }
     int ne0 = 0, ne1 = 0, nb0 = 0, nb1 = 0;
     unsigned long long vmin = kKeyNone;
+    int vidx = 0x7FFFFFFF;
     const int64_t eoff = a.in.slot_off[s];
     const int64_t toff = a.in.task_off[t];
 #pragma unroll 1
@@ -810,7 +827,7 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
                                                 : S.time_value;
           a.w.tc_value[o] = value;
           const unsigned long long vk = price_key(value);
-          if (vk < vmin) vmin = vk;
+          if (vk < vmin || (vk == vmin && pbk < vidx)) { vmin = vk; vidx = pbk; }
         }
       }
       ne0 += __popc(ke0); ne1 += __popc(ke1); nb0 += __popc(kb0); nb1 += __popc(kb1);
@@ -820,7 +837,23 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
       // cheapest value of the slot (the chain DP starts from per-cloud minima)
       const uint32_t hi = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)(vmin >> 32));
       const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, ((uint32_t)(vmin >> 32) == hi) ? (uint32_t)vmin : 0xFFFFFFFFu);
-      if (lane == 0) p.vmin = ((unsigned long long)hi << 32) | lo;
+      const unsigned long long vm = ((unsigned long long)hi << 32) | lo;
+      const int first = (int)__reduce_min_sync(0xFFFFFFFFu, (vmin == vm) ? (uint32_t)vidx : 0x7FFFFFFFu);
+      // candidates of the slot in front of the first minimum (none when the
+      // list is in price order, the usual case)
+      unsigned long long v2 = kKeyNone;
+      if (vm != kKeyNone && first > base_b0) {
+        __syncwarp();
+#pragma unroll 1
+        for (int j = base_b0 + lane; j < first; j += 32) {
+          const unsigned long long k = price_key(__ldcg(a.w.tc_value + toff + j));
+          if (k < v2) v2 = k;
+        }
+        const uint32_t h2 = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)(v2 >> 32));
+        const uint32_t l2 = __reduce_min_sync(0xFFFFFFFFu, ((uint32_t)(v2 >> 32) == h2) ? (uint32_t)v2 : 0xFFFFFFFFu);
+        v2 = ((unsigned long long)h2 << 32) | l2;
+      }
+      if (lane == 0) { p.vmin = vm; p.vidx = first; p.v2 = v2; }
     }
   };
 
@@ -856,11 +889,18 @@ __device__ __forceinline__ void place_body(const PlaceArgs &a, int t, unsigned c
   if (a.task_mv) {
     __syncthreads();
     if (tid < cat.n_clouds) {
-      unsigned long long k = kKeyNone;
+      // slots are in candidate order: a later slot only wins with a strictly
+      // smaller value, and then everything seen so far is in front of it
+      TaskMin m; m.vmin = kKeyNone; m.v2 = kKeyNone; m.idx = 0x7FFFFFFF; m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
 #pragma unroll 1
-      for (int i = 0; i < ns; ++i)
-        if (s_slot[i].cloud == tid && ps[i].vmin < k) k = ps[i].vmin;
-      a.task_mv[(int64_t)t * cat.n_clouds + tid] = k;
+      for (int i = 0; i < ns; ++i) {
+        if (s_slot[i].cloud != tid || ps[i].kind == 0 || ps[i].vmin == kKeyNone) continue;
+        if (ps[i].vmin < m.vmin) {
+          m.v2 = m.vmin < ps[i].v2 ? m.vmin : ps[i].v2;
+          m.vmin = ps[i].vmin; m.idx = ps[i].vidx;
+        }
+      }
+      a.task_mv[(int64_t)t * cat.n_clouds + tid] = m;
     }
   }
   trace_mark(a.trace, 1, 3);

@@ -10,24 +10,36 @@
 
 namespace skyopt {
 
-constexpr int kStepMaxCand = 4096;  // candidates of one DAG kept in shared memory
-
-// Chain DP (reference sky/optimizer.py:429-487) of one DAG by one block of
-// kScanThreads threads: the algorithm of solve_kernel's fast path -- per-cloud
-// minima, a C-vector recurrence, then the first-minimum winners from exactly
-// the sums the reference forms -- with the recurrence kept in registers.
+// Chain DP (reference sky/optimizer.py:429-487) of one DAG by one block.
+//
+// The reference walks the chain with, per child candidate c and parent
+// candidate p, the sum fl(dp[p] + egress(cloud(p), cloud(c))) and keeps the
+// FIRST minimum over p. Egress only depends on the two clouds, so with
+//   vmin[t][g] = smallest candidate value of task t in cloud g, idx[t][g] the
+//                first candidate holding it (left by the task's place block),
+//   D[t][g]    = fl(vmin[t][g] + B[t][g])     (dp of that candidate),
+//   B[t][h]    = min_g fl(D[t-1][g] + e_t(g, h)),  e_t(g, h) = tar_t[g] (g != h), 0 (g == h)
+// the recurrence is C wide, and the argmin over g -- ties to the smaller
+// candidate index, i.e. the first minimum in candidate order -- IS the
+// reference's best parent of every child candidate in cloud h: fl() is
+// monotone, so within a cloud no candidate beats the one with the smallest
+// value. Same sums, same minima as optimizer.py:456-470, and no candidate is
+// ever read. One case needs the full tables: a candidate in FRONT of idx[t][g]
+// with a larger value whose sum rounds to the same double would be the
+// reference's first minimum. v2[t][g] (the smallest value in front) makes
+// that checkable: if fl(fl(v2 + B) + e) == fl(fl(vmin + B) + e) for any cloud
+// the block falls back to chain_full() below, which evaluates every candidate.
 struct ChainSmem {
   double tar[kFastTasks][SKYOPT_MAX_CLOUDS];
-  unsigned long long mv[kFastTasks][SKYOPT_MAX_CLOUDS];  // price_key(min value)
+  unsigned long long mv[kFastTasks][SKYOPT_MAX_CLOUDS];  // price_key(vmin)
+  unsigned long long v2[kFastTasks][SKYOPT_MAX_CLOUDS];  // price_key(v2)
+  int mi[kFastTasks][SKYOPT_MAX_CLOUDS];                 // (idx << 5) | cloud
   double B[kFastTasks][SKYOPT_MAX_CLOUDS];
-  double cval[kStepMaxCand];
   long long toff[kFastTasks];
-  int bk_idx[kFastTasks + 1][SKYOPT_MAX_CLOUDS];
-  int tn[kFastTasks], np[kFastTasks], src[kFastTasks], cbase[kFastTasks + 1], choice[kFastTasks];
-  unsigned char bk_cl[kFastTasks + 1][SKYOPT_MAX_CLOUDS];
-  unsigned char ccl[kStepMaxCand];
+  int bk[kFastTasks + 1][SKYOPT_MAX_CLOUDS];  // best parent (idx << 5 | cloud) by child task, child cloud
+  int tn[kFastTasks], np[kFastTasks], src[kFastTasks], choice[kFastTasks];
   double obj;
-  int first_empty, staged;
+  int first_empty, hazard;
 };
 
 __device__ __forceinline__ void step_mark(unsigned long long *trace, int slot) {
@@ -35,9 +47,54 @@ __device__ __forceinline__ void step_mark(unsigned long long *trace, int slot) {
     trace[((size_t)2 * kTraceBlocks + blockIdx.x) * kTraceSlots + slot] = global_ns();
 }
 
+// (value, id) pairs in lexicographic order
+__device__ __forceinline__ bool lex_less(double av, int ai, double bv, int bi) {
+  return av < bv || (av == bv && ai < bi);
+}
+
+// The full evaluation: winners from every candidate's own sum, candidates read
+// from the task tables in global memory. Only runs after a hazard (see above),
+// so it is written for size, not speed.
+__device__ __noinline__ void chain_full(ChainSmem &M, const SolveWork &w, int T, int C, int Cp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+  const int parts = 32 / Cp;
+  const int h = lane % Cp, part = lane / Cp;
+#pragma unroll 1
+  for (int lt = warp; lt < T; lt += kFastWarps) {
+    const bool sink = lt == T - 1;
+    const int n = M.tn[lt];
+    const long long toff = M.toff[lt];
+    double bv = kInf; int bi = 0x7FFFFFFF;
+    const bool wanted = h < C && (sink ? h == 0 : M.mv[lt + 1][h] != kKeyNone);
+    if (wanted) {
+#pragma unroll 1
+      for (int p = part; p < n; p += parts) {
+        const int cp = __ldcg(w.tc_cloud + toff + p) & (SKYOPT_MAX_CLOUDS - 1);
+        const double dpp = __dadd_rn(__ldcg(w.tc_value + toff + p), M.B[lt][cp]);
+        const double e = (!sink && cp != h) ? M.tar[lt + 1][cp] : 0.0;
+        const double sum = sink ? dpp : __dadd_rn(dpp, e);
+        if (sum < bv) { bv = sum; bi = p; }
+      }
+    }
+#pragma unroll 1
+    for (int o = Cp; o < 32; o <<= 1) {
+      const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+      const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+      lexmin(bv, bi, ov, oi);
+    }
+    if (part == 0 && h < C && (!sink || h == 0)) {
+      int cl = 0;
+      if (bi != 0x7FFFFFFF && bi < n) cl = __ldcg(w.tc_cloud + toff + bi) & (SKYOPT_MAX_CLOUDS - 1);
+      M.bk[lt + 1][h] = (int)(((unsigned)bi << 5) | (unsigned)cl);
+      if (sink) M.obj = bv;
+    }
+  }
+}
+
 __device__ __forceinline__ void chain_body(const CatDev &cat, const SolveIn &in, const SolveWork &w,
-                                           const SolveOut &out, const unsigned long long *task_mv,
-                                           int dag, unsigned char *smem) {
+                                           const SolveOut &out, const TaskMin *task_mv,
+                                           int dag, int force_full, unsigned char *smem) {
   ChainSmem &M = *reinterpret_cast<ChainSmem *>(smem);
   const SkyoptDag D = in.dags[dag];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -45,7 +102,7 @@ __device__ __forceinline__ void chain_body(const CatDev &cat, const SolveIn &in,
   const int T = D.task_end - D.task_begin;
   const double kInf = __longlong_as_double(0x7FF0000000000000ll);
   step_mark(out.trace, 0);
-  if (tid == 0) M.first_empty = 0x7FFFFFFF;
+  if (tid == 0) { M.first_empty = 0x7FFFFFFF; M.hazard = force_full; }
   if (tid < T) {
     const int t = D.task_begin + tid;
     const SkyoptTask TK = in.tasks[t];
@@ -54,20 +111,21 @@ __device__ __forceinline__ void chain_body(const CatDev &cat, const SolveIn &in,
     M.np[tid] = TK.n_parents;
     M.src[tid] = TK.n_parents ? TK.edge_tariff_begin : TK.src_tariff_begin;
   }
-  __syncthreads();
-  if (tid < T && M.tn[tid] == 0) atomicMin(&M.first_empty, tid);
-  if (tid == 0) {
-    int acc = 0;
-#pragma unroll 1
-    for (int i = 0; i < T; ++i) { M.cbase[i] = acc; acc += M.tn[i]; }
-    M.cbase[T] = acc;
-    M.staged = acc <= kStepMaxCand ? 1 : 0;
-  }
 #pragma unroll 1
   for (int i = tid; i < T * C; i += kScanThreads) {
     const int lt = i / C, cc = i % C;
-    // per-(task, cloud) minimum value: left by the task's place block
-    M.mv[lt][cc] = __ldcg(task_mv + (int64_t)(D.task_begin + lt) * C + cc);
+    // the cheapest candidate of (task, cloud): left by the task's place block
+    const ulonglong2 *pm = reinterpret_cast<const ulonglong2 *>(task_mv + (int64_t)(D.task_begin + lt) * C + cc);
+    const ulonglong2 m0 = __ldcg(pm), m1 = __ldcg(pm + 1);
+    M.mv[lt][cc] = m0.x;
+    M.v2[lt][cc] = m0.y;
+    M.mi[lt][cc] = (int)(((unsigned)m1.x << 5) | (unsigned)cc);
+  }
+  __syncthreads();
+  if (tid < T && M.tn[tid] == 0) atomicMin(&M.first_empty, tid);
+#pragma unroll 1
+  for (int i = tid; i < T * C; i += kScanThreads) {
+    const int lt = i / C, cc = i % C;
     M.tar[lt][cc] = M.src[lt] >= 0 ? in.tariffs[M.src[lt] + cc] : 0.0;
   }
   __syncthreads();
@@ -81,135 +139,99 @@ __device__ __forceinline__ void chain_body(const CatDev &cat, const SolveIn &in,
   }
   step_mark(out.trace, 1);
   const long long c_start = clock64();
-  const bool staged = M.staged != 0;
   int Cp = 1;
   while (Cp < C) Cp <<= 1;
-  const int parts = 32 / Cp;
-  // Two passes over ONE copy of the winners / back-tracking code. Pass 0: warp
-  // 0 walks the recurrence (serial, one warp) while the other warps bring the
-  // candidates to shared memory and then run the winners code on whatever B
-  // holds -- a rehearsal whose only purpose is to have that code in the
-  // instruction caches: this block is the only one that ever executes it, and
-  // after a cold start every new instruction line is a DRAM round trip
-  // (profiles/round2_timeline.md). Pass 1 is the real thing.
+  if (warp == 0) {
+    const int h = lane < C ? lane : 0;
+    const bool live = lane < C;
+    double dprev = 0.0, hprev = 0.0;   // D[t-1][lane], fl(v2[t-1][lane] + B[t-1][lane])
+    int myid = 0x7FFFFFFF;
+    bool has2 = false, hz = false;
+    // the next task's operands are fetched one step ahead of the dependent chain
+    double tar_n = M.tar[0][h];
+    unsigned long long mk_n = M.mv[0][h], v2_n = M.v2[0][h];
+    int mi_n = M.mi[0][h], np_n = M.np[0];
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 0) {
-      if (warp == 0) {
-        // B[t][h] = min_g fl(D[t-1][g] + e_t(g, h)),  D[t][h] = fl(mv[t][h] + B[t][h])
-        // with e_t(g, h) = tar_t[g] for g != h and 0 for g == h. So
-        //   B[t][h] = min(D[t-1][h], min_{g != h} A[g]),  A[g] = fl(D[t-1][g] + tar_t[g]):
-        // lane g forms its one sum, a butterfly over the Cp lanes gives every
-        // lane the smallest and second smallest A (with multiplicity), and
-        // lane h takes the second one when its own A is the smallest. Same
-        // sums, same minima as the reference's double loop
-        // (optimizer.py:456-470), a third of the dependent latency.
-        const int h = lane < C ? lane : 0;
-        double dprev = 0.0;
-#pragma unroll 1
-        for (int lt = 0; lt < T; ++lt) {
-          double b;
-          if (M.np[lt] == 0) {
-            b = M.tar[lt][h];  // dummy source: 0 + egress from the inputs' cloud
-          } else {
-            const double mine = lane < C ? __dadd_rn(dprev, M.tar[lt][h]) : kInf;
-            double m1 = mine, m2 = kInf;
-#pragma unroll 1
-            for (int o = 1; o < Cp; o <<= 1) {
-              const double p1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o);
-              const double p2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
-              const double lo = p1 < m1 ? p1 : m1, hi = p1 < m1 ? m1 : p1;
-              const double s2 = p2 < m2 ? p2 : m2;
-              m1 = lo; m2 = s2 < hi ? s2 : hi;
-            }
-            const double others = (mine == m1) ? m2 : m1;
-            b = others < dprev ? others : dprev;
-          }
-          const unsigned long long mk = M.mv[lt][h];
-          if (lane < C) M.B[lt][lane] = b;
-          dprev = (mk == kKeyNone) ? kInf : __dadd_rn(key_price(mk), b);
-        }
-        if (out.trace && lane == 0 && blockIdx.x < kTraceBlocks)
-          out.trace[((size_t)2 * kTraceBlocks + blockIdx.x) * kTraceSlots + 8] = (unsigned long long)(clock64() - c_start);
-      } else if (staged) {
-#pragma unroll 1
-        for (int lt = warp - 1; lt < T; lt += kFastWarps - 1) {
-          const int n = M.tn[lt];
-          const long long toff = M.toff[lt];
-          const int cb = M.cbase[lt];
-#pragma unroll 1
-          for (int c = lane; c < n; c += 32) {
-            M.ccl[cb + c] = (unsigned char)__ldcg(w.tc_cloud + toff + c);
-            M.cval[cb + c] = __ldcg(w.tc_value + toff + c);
-          }
-        }
+    for (int lt = 0; lt < T; ++lt) {
+      const double tar = tar_n;
+      const unsigned long long mk = mk_n, v2k = v2_n;
+      const int mi = mi_n, np = np_n;
+      if (lt + 1 < T) {
+        tar_n = M.tar[lt + 1][h]; mk_n = M.mv[lt + 1][h]; v2_n = M.v2[lt + 1][h];
+        mi_n = M.mi[lt + 1][h]; np_n = M.np[lt + 1];
       }
+      double b;
+      if (np == 0) {
+        b = tar;  // dummy source: 0 + egress from the inputs' cloud
+      } else {
+        const double mine = live ? __dadd_rn(dprev, tar) : kInf;
+        // a candidate in front of the cheapest one whose sum rounds the same
+        if (live && has2 && dprev < kInf && (hprev == dprev || __dadd_rn(hprev, tar) == mine)) hz = true;
+        double m1 = mine, m2 = kInf;
+        int i1 = live ? myid : 0x7FFFFFFF, i2 = 0x7FFFFFFF;
+#pragma unroll 1
+        for (int o = 1; o < Cp; o <<= 1) {
+          const double p1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o);
+          const int q1 = __shfl_xor_sync(0xFFFFFFFFu, i1, o);
+          const double p2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+          const int q2 = __shfl_xor_sync(0xFFFFFFFFu, i2, o);
+          const bool pl = lex_less(p1, q1, m1, i1);
+          const double lo = pl ? p1 : m1, hi = pl ? m1 : p1;
+          const int loi = pl ? q1 : i1, hii = pl ? i1 : q1;
+          const bool sl = lex_less(p2, q2, m2, i2);
+          const double s2 = sl ? p2 : m2;
+          const int s2i = sl ? q2 : i2;
+          const bool tl = lex_less(s2, s2i, hi, hii);
+          m1 = lo; i1 = loi;
+          m2 = tl ? s2 : hi; i2 = tl ? s2i : hii;
+        }
+        const bool own = i1 == myid;   // ids are distinct: (candidate index, cloud)
+        const double ov = own ? m2 : m1;
+        const int oi = own ? i2 : i1;
+        const bool ol = lex_less(ov, oi, dprev, myid);
+        b = ol ? ov : dprev;
+        if (live) M.bk[lt][lane] = ol ? oi : myid;
+      }
+      if (live) M.B[lt][lane] = b;
+      dprev = (mk == kKeyNone || !live) ? kInf : __dadd_rn(key_price(mk), b);
+      has2 = v2k != kKeyNone;
+      hprev = has2 ? __dadd_rn(key_price(v2k), b) : 0.0;
+      myid = mi;
     }
-    if (pass == 1 || warp != 0) {
-      // winners: for parent task lt and child cloud h, the first minimum over
-      // the parent's candidates p of fl(dp[p] + e_{lt+1}(cloud(p), h)) --
-      // exactly the sums the reference forms (optimizer.py:456-470). A warp
-      // takes a parent task; lane = (part, h): the candidates are dealt to
-      // 32 / Cp parts, each lane walks its part in candidate order (strict '<'
-      // keeps the first minimum), the parts are merged with (value, index)
-      // comparisons. The last task's only child is the dummy sink (egress 0).
-      const int h = lane % Cp, part = lane / Cp;
+    // the sink: egress 0 from every cloud, first minimum of D[T-1][.]
+    if (live && has2 && dprev < kInf && hprev == dprev) hz = true;
+    double bv = live ? dprev : kInf;
+    int bi = live ? myid : 0x7FFFFFFF;
 #pragma unroll 1
-      for (int lt = warp; lt < T; lt += kFastWarps) {
-        const bool sink = lt == T - 1;
-        const int n = M.tn[lt];
-        const long long toff = M.toff[lt];
-        const int cb = M.cbase[lt];
-        double bv = kInf; int bi = 0x7FFFFFFF;
-        const bool wanted = h < C && (sink ? h == 0 : M.mv[lt + 1][h] != kKeyNone);
-        if (wanted) {
-#pragma unroll 4
-          for (int p = part; p < n; p += parts) {
-            const int cp = (staged ? (int)M.ccl[cb + p] : __ldcg(w.tc_cloud + toff + p)) & (SKYOPT_MAX_CLOUDS - 1);
-            const double val = staged ? M.cval[cb + p] : __ldcg(w.tc_value + toff + p);
-            const double dpp = __dadd_rn(val, M.B[lt][cp]);
-            const double e = (!sink && cp != h) ? M.tar[lt + 1][cp] : 0.0;
-            const double sum = sink ? dpp : __dadd_rn(dpp, e);
-            if (sum < bv) { bv = sum; bi = p; }
-          }
-        }
-#pragma unroll 1
-        for (int o = Cp; o < 32; o <<= 1) {
-          const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
-          const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
-          lexmin(bv, bi, ov, oi);
-        }
-        if (part == 0 && h < C && (!sink || h == 0)) {
-          const int slot_t = lt + 1;  // indexed by the child task; T = the sink
-          M.bk_idx[slot_t][h] = bi;
-          unsigned char cl = 0;
-          if (bi != 0x7FFFFFFF && bi < n)
-            cl = staged ? M.ccl[cb + bi] : (unsigned char)__ldcg(w.tc_cloud + toff + bi);
-          M.bk_cl[slot_t][h] = cl;
-          if (sink) M.obj = bv;
-        }
-      }
-      // back-tracking (thread 0; rehearsed by thread 32)
-      if (pass == 1) { __syncthreads(); step_mark(out.trace, 4); }
-      if (tid == (pass == 1 ? 0 : 32)) {
-        int idx = M.bk_idx[T][0];
-        int cl = M.bk_cl[T][0] & (SKYOPT_MAX_CLOUDS - 1);
-#pragma unroll 1
-        for (int lt = T - 1; lt >= 0; --lt) {
-          if (pass == 1) M.choice[lt] = idx;
-          if (lt > 0) {
-            const int ni = M.bk_idx[lt][cl];
-            cl = M.bk_cl[lt][cl] & (SKYOPT_MAX_CLOUDS - 1);
-            idx = ni;
-          }
-        }
-        if (pass == 1) {
-          SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = M.obj;
-          out.dag[dag] = r;
-        }
-      }
+    for (int o = 1; o < Cp; o <<= 1) {
+      const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+      const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+      lexmin(bv, bi, ov, oi);
     }
-    if (pass == 0) { __syncthreads(); step_mark(out.trace, 3); }
+    const bool any_hz = __any_sync(0xFFFFFFFFu, hz);
+    if (lane == 0) {
+      M.bk[T][0] = bi; M.obj = bv;
+      if (any_hz) M.hazard = 1;
+      if (out.trace && blockIdx.x < kTraceBlocks)
+        out.trace[((size_t)2 * kTraceBlocks + blockIdx.x) * kTraceSlots + 8] = (unsigned long long)(clock64() - c_start);
+    }
+  }
+  __syncthreads();
+  step_mark(out.trace, 3);
+  if (M.hazard) {
+    chain_full(M, w, T, C, Cp);
+    __syncthreads();
+  }
+  step_mark(out.trace, 4);
+  if (tid == 0) {
+    int id = M.bk[T][0];
+#pragma unroll 1
+    for (int lt = T - 1; lt >= 0; --lt) {
+      M.choice[lt] = (int)((unsigned)id >> 5);
+      if (lt > 0) id = M.bk[lt][id & (SKYOPT_MAX_CLOUDS - 1)];
+    }
+    SkyoptDagResult r; r.status = 0; r.task_fail = -1; r.objective = M.obj;
+    out.dag[dag] = r;
   }
   __syncthreads();
   step_mark(out.trace, 5);
@@ -243,6 +265,7 @@ struct StepArgs {
   const char *in_base;    // the uploaded input region (descriptors), prefetched into L2
   int64_t in_lines;
   int do_solve;           // every DAG is a chain of <= kFastTasks tasks
+  int force_full;         // test knob: chain_full() on every DAG (SKYOPT_EXP bit 3)
   int32_t *dag_done;      // [n_dags] tasks placed so far (zero between launches)
   unsigned int *sync;     // [2] arrivals at the barrier / at the exit (zero between launches)
 };
@@ -289,7 +312,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) step_kernel(St
       __syncthreads();
       if (s_last) {
         __threadfence();
-        chain_body(a.scan.cat, a.place.in, a.place.w, a.out, a.place.task_mv, dag, smem_step);
+        chain_body(a.scan.cat, a.place.in, a.place.w, a.out, a.place.task_mv, dag, a.force_full, smem_step);
       }
     }
     __syncthreads();  // shared memory is reused by the next task

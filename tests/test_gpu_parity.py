@@ -10,6 +10,7 @@ import os
 
 import pytest
 
+import skypilot_b200 as sky
 from tests import scenario_runner as runner
 from tests import scenarios
 
@@ -100,3 +101,74 @@ def test_auto_mode_takes_the_class_table_scan():
     assert engine.LAST_STATS is not None
     assert int(engine.LAST_STATS.scan_form) == 4
     assert int(engine.LAST_STATS.total_launches) == 1
+
+
+def test_chain_dp_full_evaluation_agrees():
+    """The fused step's chain DP works on per-cloud minima and only reads the
+    candidate tables after a rounding hazard (skyopt_step.cuh). SKYOPT_EXP=8
+    forces that full evaluation on every DAG: same plans, same objectives.
+    (The knob is read once per process, hence the subprocess.)"""
+    import os
+    import subprocess
+    import sys
+    code = (
+        'import sys; sys.path.insert(0, ".")\n'
+        'from tests import scenario_runner as runner, scenarios\n'
+        'from skypilot_b200 import engine\n'
+        'bad = []\n'
+        'for cat in ("multi6k", "fuzz6k"):\n'
+        '    payload = runner.load_golden(cat)\n'
+        '    records = {r["name"]: r for r in payload["records"]}\n'
+        '    runner.activate_catalog(payload["catalog"])\n'
+        '    for sc in scenarios.ALL_SUITES[cat]():\n'
+        '        if len(sc["tasks"]) < 2:\n'
+        '            continue\n'
+        '        got = runner.run_scenario(sc, with_candidates=False)\n'
+        '        d = runner.compare(records[sc["name"]], got)\n'
+        '        if d:\n'
+        '            bad.append((sc["name"], d[:2]))\n'
+        '        assert int(engine.LAST_STATS.scan_form) in (0, 1, 2, 3, 4)\n'
+        'assert not bad, bad\n'
+        'print("chains ok")\n')
+    env = dict(os.environ, SKYOPT_EXP='8')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, '-c', code], cwd=root, env=env,
+                          capture_output=True, text=True, timeout=600,
+                          check=False)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert 'chains ok' in proc.stdout
+
+
+def test_fresh_request_with_equal_content_hits_the_statement_memo():
+    """A new DAG (new Task / Resources objects) whose requests have the same
+    content as an earlier one replays the stated plans kept on the catalog
+    store -- the memo is keyed by request content, not by object identity --
+    and still gives the reference's record."""
+    spec, records = _golden('multi6k')
+    store = runner.activate_catalog(spec)
+    sky.catalog.clear_request_level_cache()
+    sc = next(s for s in scenarios.SUITES['multi6k']()
+              if s['name'] == 'chain3_mixed')
+    first = runner.run_scenario(sc, with_candidates=False)
+    assert not runner.compare(records[sc['name']], first)
+    cache = store.__dict__['_plan_cache']
+    stated = len(cache)
+    assert stated > 0
+    # what the rule code costs is what the memo saves: it must not run again
+    from skypilot_b200.clouds import cloud as cloud_lib
+    calls = []
+    original = cloud_lib.Cloud._feature_hint  # pylint: disable=protected-access
+
+    def counting(self, resources, num_nodes):
+        calls.append(type(self).__name__)
+        return original(self, resources, num_nodes)
+
+    cloud_lib.Cloud._feature_hint = counting  # pylint: disable=protected-access
+    try:
+        again = runner.run_scenario(sc, with_candidates=False)  # fresh objects
+    finally:
+        cloud_lib.Cloud._feature_hint = original  # pylint: disable=protected-access
+    assert not calls, calls
+    assert len(store.__dict__['_plan_cache']) == stated
+    assert not runner.compare(records[sc['name']], again)
+    assert again['plan'] == first['plan']

@@ -12,7 +12,7 @@ KB, KS = 4096, 16
 NAMES = {
     0: ['start', 'staged', 'tables', 'streamed', 'end'],
     1: ['start', 'resolved', 'counted', 'end'],
-    2: ['start', 'loaded', '-', 'recurrence', 'winners', 'backtrack', 'end'],
+    2: ['start', 'loaded', '-', 'recurrence', 'full-eval', 'backtrack', 'end'],
 }
 
 
