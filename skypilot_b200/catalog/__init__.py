@@ -62,6 +62,7 @@ def clear_request_level_cache() -> None:
     if _store is not None:
         _store.__dict__.pop('_plan_cache', None)
         _store.__dict__.pop('_acc_set_cache', None)
+        _store.__dict__.pop('_set_id_by_obj', None)
         # invalidates what tasks remember of earlier statements
         _store.__dict__['_memo_generation'] = _store.__dict__.get(
             '_memo_generation', 0) + 1

@@ -267,6 +267,8 @@ class Cloud:
         required = resources.get_required_cloud_features()
         if num_nodes > 1:
             required.add(CloudImplementationFeatures.MULTI_NODE)
+        if not required:
+            return None  # nothing asked for, nothing to refuse
         try:
             self.check_features_are_supported(resources, required)
         except exceptions.NotSupportedError as e:
@@ -411,21 +413,29 @@ class Cloud:
         """States `resources` against this cloud for the device: the template
         shared by AWS, Azure, Lambda and the other single-table clouds
         (aws.py:881-953, azure.py:485-557, lambda_cloud.py:217-280)."""
-        rules = self._rules()
-        view = self._view()
-        table = view.table
+        store = builder.store
+        ctxs = store.__dict__.setdefault('_plan_ctx', {})
+        ctx = ctxs.get(self.__class__)
+        if ctx is None:
+            # what the statement needs of this cloud's table and rules: a
+            # property of (catalog, cloud), looked up once
+            rules = self._rules()
+            table = self._view().table
+            ctx = (rules, table, bool(table.has_zone_column),
+                   bool(self.optimize_by_zone()), _late('engine'))
+            ctxs[self.__class__] = ctx
+        rules, table, has_zone_column, by_zone_always, engine = ctx
         plan = SlotPlan()
         use_spot = bool(resources.use_spot)
         if use_spot and not rules.supports_spot:
             return plan
         # IBM: the queries are stated, but a spot request gets no slot
         no_slot = use_spot and rules.spot_without_regions
-        by_zone = bool(table.has_zone_column and
-                       (use_spot or self.optimize_by_zone()))
+        by_zone = has_zone_column and (use_spot or by_zone_always)
         slot_common = dict(
             cloud=table.index, price_col=1 if use_spot else 0,
-            region_id=_exact_region(table, resources.region),
-            zone_id=_exact_zone(table, resources.zone),
+            region_id=engine.region_exact_id(table, resources.region),
+            zone_id=engine.zone_exact_id(table, resources.zone),
             split_by_zone=int(by_zone), us_first=int(rules.us_regions_first),
             use_spot=int(use_spot),
             region_words=region_allow_words(table, resources, self))
@@ -475,7 +485,7 @@ class Cloud:
             q_region = resources.region if rules.default_query_region else None
             q_zone = resources.zone if rules.default_query_region else None
             spec = builder.cpus_mem_query(
-                self._CATALOG, cpus, memory, q_region, q_zone,
+                table, cpus, memory, q_region, q_zone,
                 use_spot, resources.max_hourly_cost, flags_require=flags,
                 local_disk=local_disk)
             q = builder.add_query(spec)
@@ -487,7 +497,7 @@ class Cloud:
         assert len(accelerators) == 1, resources
         acc, acc_count = list(accelerators.items())[0]
         spec = builder.accelerator_query(
-            self._CATALOG, acc, acc_count,
+            table, acc, acc_count,
             resources.cpus if rules.acc_query_cpus else None,
             resources.memory if rules.acc_query_memory else None,
             use_spot and not rules.spot_without_regions,
@@ -540,13 +550,15 @@ def region_allow_words(table, resources: Any, cloud_obj: Any):
     `image_id` dict and the per-region `ssh_proxy_command` of the SkyPilot
     config (Resources.get_valid_regions_for_launchable,
     sky/resources.py:1210-1246)."""
+    image_id = resources.image_id
+    config = _late('skypilot_config')
+    if image_id is None and not config.has_config():
+        return None
     import numpy as np  # pylint: disable=import-outside-toplevel
     names = None
-    image_id = resources.image_id
     if image_id is not None and None not in image_id:
         names = set(image_id.keys())
-    by_proxy = _late('skypilot_config').allowed_regions_by_ssh_proxy(
-        str(cloud_obj).lower())
+    by_proxy = config.allowed_regions_by_ssh_proxy(str(cloud_obj).lower())
     if by_proxy is not None:
         names = by_proxy if names is None else names & by_proxy
     if names is None:

@@ -47,9 +47,10 @@ __device__ __forceinline__ void step_mark(unsigned long long *trace, int slot) {
     trace[((size_t)2 * kTraceBlocks + blockIdx.x) * kTraceSlots + slot] = global_ns();
 }
 
-// (value, id) pairs in lexicographic order
-__device__ __forceinline__ bool lex_less(double av, int ai, double bv, int bi) {
-  return av < bv || (av == bv && ai < bi);
+// (price key, id) pairs in lexicographic order, branch-free
+constexpr unsigned long long kKeyInf = 0xFFF0000000000000ull;  // price_key(+inf)
+__device__ __forceinline__ bool key_less(unsigned long long ak, int ai, unsigned long long bk, int bi) {
+  return (ak < bk) | ((ak == bk) & (ai < bi));
 }
 
 // The full evaluation: winners from every candidate's own sum, candidates read
@@ -167,29 +168,34 @@ __device__ __forceinline__ void chain_body(const CatDev &cat, const SolveIn &in,
         const double mine = live ? __dadd_rn(dprev, tar) : kInf;
         // a candidate in front of the cheapest one whose sum rounds the same
         if (live && has2 && dprev < kInf && (hprev == dprev || __dadd_rn(hprev, tar) == mine)) hz = true;
-        double m1 = mine, m2 = kInf;
+        // The minima are taken on price keys: a total order on doubles as
+        // 64-bit integers (equal doubles <=> equal keys for the non-negative
+        // sums here). An fp64 compare-and-select costs four times the latency
+        // of the integer one, and this loop is nothing but dependent compares.
+        const unsigned long long kd = price_key(dprev);
+        unsigned long long k1 = price_key(mine), k2 = kKeyInf;
         int i1 = live ? myid : 0x7FFFFFFF, i2 = 0x7FFFFFFF;
 #pragma unroll 1
         for (int o = 1; o < Cp; o <<= 1) {
-          const double p1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o);
+          const unsigned long long p1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
           const int q1 = __shfl_xor_sync(0xFFFFFFFFu, i1, o);
-          const double p2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+          const unsigned long long p2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
           const int q2 = __shfl_xor_sync(0xFFFFFFFFu, i2, o);
-          const bool pl = lex_less(p1, q1, m1, i1);
-          const double lo = pl ? p1 : m1, hi = pl ? m1 : p1;
+          const bool pl = key_less(p1, q1, k1, i1);
+          const unsigned long long lo = pl ? p1 : k1, hi = pl ? k1 : p1;
           const int loi = pl ? q1 : i1, hii = pl ? i1 : q1;
-          const bool sl = lex_less(p2, q2, m2, i2);
-          const double s2 = sl ? p2 : m2;
+          const bool sl = key_less(p2, q2, k2, i2);
+          const unsigned long long s2 = sl ? p2 : k2;
           const int s2i = sl ? q2 : i2;
-          const bool tl = lex_less(s2, s2i, hi, hii);
-          m1 = lo; i1 = loi;
-          m2 = tl ? s2 : hi; i2 = tl ? s2i : hii;
+          const bool tl = key_less(s2, s2i, hi, hii);
+          k1 = lo; i1 = loi;
+          k2 = tl ? s2 : hi; i2 = tl ? s2i : hii;
         }
         const bool own = i1 == myid;   // ids are distinct: (candidate index, cloud)
-        const double ov = own ? m2 : m1;
+        const unsigned long long ok = own ? k2 : k1;
         const int oi = own ? i2 : i1;
-        const bool ol = lex_less(ov, oi, dprev, myid);
-        b = ol ? ov : dprev;
+        const bool ol = key_less(ok, oi, kd, myid);
+        b = key_price(ol ? ok : kd);
         if (live) M.bk[lt][lane] = ol ? oi : myid;
       }
       if (live) M.B[lt][lane] = b;

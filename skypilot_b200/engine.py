@@ -9,6 +9,8 @@ on the GPU. There is no CPU implementation behind these calls.
 import ctypes
 import math
 import struct
+import functools
+import operator
 import re
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -23,6 +25,7 @@ NO_MATCH_ID = 65534  # a region / zone id no row carries
 _INF = float('inf')
 
 
+@functools.lru_cache(maxsize=4096)
 def parse_cpus(cpus: Optional[str]) -> Tuple[int, float]:
     """'8' -> (EQ, 8.0), '8+' -> (GE, 8.0) (sky/catalog/common.py:431-452)."""
     if cpus is None:
@@ -37,6 +40,7 @@ def parse_cpus(cpus: Optional[str]) -> Tuple[int, float]:
     return (_native.OP_GE if text.endswith('+') else _native.OP_EQ), value
 
 
+@functools.lru_cache(maxsize=4096)
 def parse_memory(memory: Optional[str]) -> Tuple[int, float]:
     """'16' EQ, '16+' GE, '4x' RATIO (sky/catalog/common.py:455-478)."""
     if memory is None:
@@ -114,21 +118,25 @@ def accelerator_sets(store: CatalogStore, acc_name: str,
                 index.setdefault(name.lower(), []).append((k, cnt))
             store.__dict__['_acc_name_index'] = index
         low = acc_name.lower()
-        exact = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
-        fuzzy = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
-        strict = np.zeros(_native.ACC_SET_WORDS, dtype=np.uint32)
+        # bitmasks as Python ints (one shift-or per key), turned into the
+        # uint32 words of the C ABI once
+        e_bits = f_bits = s_bits = 0
         for name, keys in index.items():
             if low not in name:
                 continue
             same = name == low
             for k, cnt in keys:
-                bit = np.uint32(1 << (k & 31))
                 if cnt >= count:
-                    fuzzy[k >> 5] |= bit
-                if same and abs(cnt - count) <= 0.01:
-                    exact[k >> 5] |= bit
-                if same and cnt == count:
-                    strict[k >> 5] |= bit
+                    f_bits |= 1 << k
+                if same:
+                    if abs(cnt - count) <= 0.01:
+                        e_bits |= 1 << k
+                    if cnt == count:
+                        s_bits |= 1 << k
+        nbytes = 4 * _native.ACC_SET_WORDS
+        exact, fuzzy, strict = (np.frombuffer(
+            bits.to_bytes(nbytes, 'little'), dtype=np.uint32)
+                                for bits in (e_bits, f_bits, s_bits))
         cache[(acc_name, float(acc_count))] = (exact, fuzzy, strict)
         return exact, fuzzy, strict
     pattern = re.compile(acc_name, flags=re.IGNORECASE)
@@ -209,6 +217,25 @@ def _packer(dtype: np.dtype) -> Tuple[struct.Struct, Tuple[str, ...]]:
     return _PACKERS[key]
 
 
+def _defaults(dtype: np.dtype, overrides: Dict[str, Any]) -> Dict[str, Any]:
+    base = {n: (-1 if n in _MINUS_ONE_DEFAULT else 0) for n in dtype.names
+            if n != 'pad_'}
+    base.update(overrides)
+    return base
+
+
+# every field of a record with its default; itemgetter pulls them out in
+# struct order at C speed
+_QUERY_DEFAULTS = _defaults(_native.QUERY_DTYPE, {})
+_SLOT_DEFAULTS = _defaults(_native.SLOT_DTYPE, {
+    'query': -1, 'inst_id': -1, 'gate_query': -1, 'cand_acc_key': -1,
+    'hours': 1.0, 'node_mult': 1.0, 'time_value': 3600.0})
+_QUERY_PACK = _packer(_native.QUERY_DTYPE)[0].pack
+_QUERY_FIELDS = operator.itemgetter(*_packer(_native.QUERY_DTYPE)[1])
+_SLOT_PACK = _packer(_native.SLOT_DTYPE)[0].pack
+_SLOT_FIELDS = operator.itemgetter(*_packer(_native.SLOT_DTYPE)[1])
+
+
 class ProblemBuilder:
     """Accumulates one batch for the device.
 
@@ -243,8 +270,17 @@ class ProblemBuilder:
     def add_set(self, words: Optional[np.ndarray]) -> int:
         if words is None:
             return -1
-        return set_id(self.store,
-                      np.ascontiguousarray(words, dtype=np.uint32).tobytes())
+        # the bitmask arrays of accelerator_sets() live as long as the store's
+        # memo: their ids are remembered by object
+        by_obj = self.store.__dict__.setdefault('_set_id_by_obj', {})
+        hit = by_obj.get(id(words))
+        if hit is not None and hit[0] is words:
+            return hit[1]
+        idx = set_id(self.store,
+                     np.ascontiguousarray(words, dtype=np.uint32).tobytes())
+        if len(by_obj) < 4096:
+            by_obj[id(words)] = (words, idx)
+        return idx
 
     @staticmethod
     def _record(fields: Dict[str, Any], dtype: np.dtype) -> bytes:
@@ -275,10 +311,11 @@ class ProblemBuilder:
         self.slot_cost[slot] = (hours, node_mult, time_value)
 
     def add_query(self, spec: Dict[str, Any]) -> int:
-        q = dict(spec)
+        q = dict(_QUERY_DEFAULTS)
+        q.update(spec)
         q['acc_set'] = self.add_set(q.pop('acc_words', None))
         q['fuzzy_set'] = self.add_set(q.pop('fuzzy_words', None))
-        self.query_recs.append(self._record(q, _native.QUERY_DTYPE))
+        self.query_recs.append(_QUERY_PACK(*_QUERY_FIELDS(q)))
         return len(self.query_recs) - 1
 
     def cpus_mem_query(self,
@@ -295,7 +332,7 @@ class ProblemBuilder:
                        local_disk: Optional[str] = None) -> Dict[str, Any]:
         """Constraint vector of get_instance_type_for_cpus_mem_impl
         (sky/catalog/common.py:518-569)."""
-        table = self.store.cloud(cloud)
+        table = self.store.cloud(cloud) if isinstance(cloud, str) else cloud
         cop, cval = parse_cpus(cpus)
         mop, mval = parse_memory(memory)
         # Spot prices only order the rows when a price cap is set
@@ -331,7 +368,7 @@ class ProblemBuilder:
                           want_fuzzy: bool = True) -> Dict[str, Any]:
         """Constraint vector of get_instance_type_for_accelerator_impl
         (sky/catalog/common.py:641-694)."""
-        table = self.store.cloud(cloud)
+        table = self.store.cloud(cloud) if isinstance(cloud, str) else cloud
         exact, fuzzy, _ = accelerator_sets(self.store, acc_name, acc_count)
         cop, cval = parse_cpus(cpus)
         mop, mval = parse_memory(memory)
@@ -358,13 +395,7 @@ class ProblemBuilder:
 
     # -- slots / tasks / dags ----------------------------------------------
     def add_slot(self, **fields) -> int:
-        slot = {
-            'query': -1, 'inst_id': -1, 'gate_query': -1, 'acc_set': -1,
-            'price_col': 0, 'region_id': -1, 'zone_id': -1,
-            'split_by_zone': 0, 'us_first': 0, 'cand_acc_key': -1,
-            'use_spot': 0, 'region_set': -1, 'pad_': 0, 'hours': 1.0,
-            'node_mult': 1.0, 'time_value': 3600.0
-        }
+        slot = dict(_SLOT_DEFAULTS)
         words = fields.pop('acc_words', None)
         region_words = fields.pop('region_words', None)
         slot.update(fields)
@@ -372,7 +403,7 @@ class ProblemBuilder:
             slot['acc_set'] = self.add_set(words)
         if region_words is not None:
             slot['region_set'] = self.add_set(region_words)
-        self.slot_recs.append(self._record(slot, _native.SLOT_DTYPE))
+        self.slot_recs.append(_SLOT_PACK(*_SLOT_FIELDS(slot)))
         self.slot_qbase.append(0)
         self.slot_cost.append(None)
         return len(self.slot_recs) - 1

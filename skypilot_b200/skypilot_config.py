@@ -33,6 +33,10 @@ def _changed() -> None:
     _generation += 1
 
 
+def has_config() -> bool:
+    return bool(_config)
+
+
 def set_config(config: Optional[Dict[str, Any]]) -> None:
     global _config
     _config = copy.deepcopy(config) if config else {}

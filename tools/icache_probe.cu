@@ -21,9 +21,17 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define S256 S64 S64 S64 S64
 #define S1024 S256 S256 S256 S256
 
+__device__ __noinline__ float body(float v) {
+  S1024 S1024 S1024 S1024
+  return v;
+}
+
+typedef float (*body_fn)(float);
+__device__ body_fn g_body = body;
+
 __global__ void __launch_bounds__(32) big(float *x, int prefetch_bytes, unsigned long long code, unsigned long long *t, unsigned long long *peek) {
   if (peek && threadIdx.x == 0) {
-    peek[0] = (unsigned long long)(void *)big;
+    peek[0] = (unsigned long long)(void *)g_body;
   }
   if (prefetch_bytes) {
     const char *base = (const char *)code;
@@ -34,7 +42,7 @@ __global__ void __launch_bounds__(32) big(float *x, int prefetch_bytes, unsigned
   }
   const unsigned long long t0 = gtime();
   float v = x[threadIdx.x];
-  S1024 S1024 S1024 S1024
+  v = body(v);
   const unsigned long long t1 = gtime();
   x[threadIdx.x] = v;
   if (threadIdx.x == 0) { t[0] = t1 - t0; }
