@@ -375,32 +375,36 @@ class Cloud:
         Returns the (shared, read-only) plan template and the index of the
         slot it added to `builder` (None: nothing to ask the device)."""
         store = builder.store
-        multi = num_nodes > 1
-        # templates are also pinned on the Resources object, which skips
-        # hashing the long request key when the same object is stated again
-        local = resources.__dict__.get('_plan_templates')
-        if local is None or local[0] is not store:
-            local = (store, {})
-            resources.__dict__['_plan_templates'] = local
-        tmpl = local[1].get((self.__class__, multi))
-        if tmpl is None:
-            engine = _late('engine')
-            cache = store.__dict__.setdefault('_plan_cache', {})
-            rkey = resources.__dict__.get('_request_key')
-            if rkey is None:
+        d = resources.__dict__
+        # {request key: {(cloud class, multi-node): template}} on the store;
+        # the inner dict is pinned on the Resources object, so that the long
+        # request key is built and hashed once per object
+        local = d.get('_plan_templates')
+        generation = _late('skypilot_config')._generation  # pylint: disable=protected-access
+        if (local is None or local[0] is not store or
+                local[2] != generation):
+            rkey = d.get('_request_key')
+            if rkey is None or rkey[-1] != generation:
                 rkey = self._request_key(resources)
-                resources.__dict__['_request_key'] = rkey
-            key = (self.__class__, multi, rkey)
-            tmpl = cache.get(key)
-            if tmpl is None:
-                plan = SlotPlan()
-                recorder = engine.ProblemBuilder(store)
-                plan.hint = self._feature_hint(resources, num_nodes)
-                if plan.hint is None:
-                    plan = self.plan_feasible(recorder, resources)
-                tmpl = (plan, recorder)
-                cache[key] = tmpl
-            local[1][(self.__class__, multi)] = tmpl
+                d['_request_key'] = rkey
+            cache = store.__dict__.get('_plan_cache')
+            if cache is None:
+                cache = store.__dict__['_plan_cache'] = {}
+            by_cloud = cache.get(rkey)
+            if by_cloud is None:
+                by_cloud = cache[rkey] = {}
+            local = (store, by_cloud, generation)
+            d['_plan_templates'] = local
+        key = (self.__class__, num_nodes > 1)
+        tmpl = local[1].get(key)
+        if tmpl is None:
+            plan = SlotPlan()
+            recorder = _late('engine').ProblemBuilder(store)
+            plan.hint = self._feature_hint(resources, num_nodes)
+            if plan.hint is None:
+                plan = self.plan_feasible(recorder, resources)
+            tmpl = (plan, recorder)
+            local[1][key] = tmpl
         plan, recorder = tmpl
         if plan.slot is None:
             return plan, None

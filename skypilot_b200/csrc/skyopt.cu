@@ -764,7 +764,7 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     static const int exp_flags = [] { const char *e = getenv("SKYOPT_EXP"); return e ? atoi(e) : 0; }();
     if (!(exp_flags & 2)) { sp.scan.shared_tables = P.shared_tables; sp.scan.group_ready = P.group_ready; }
     if (exp_flags & 4) sp.scan.noprune |= 4u;  // experiment: spin without nanosleep
-    sp.force_full = (exp_flags & 8) ? 1 : 0;   // test knob: evaluate every candidate in the chain DP
+    sp.force_full = ((exp_flags & 8) ? 1 : 0) | ((exp_flags & 16) ? 2 : 0);   // test knob: evaluate every candidate in the chain DP
     sp.place.cat = cat->dev; sp.place.f = cat->fast; sp.place.ptasks = P.ptasks; sp.place.saux = P.saux;
     sp.place.best_rank = P.best_rank; sp.place.any1 = P.any_in; sp.place.acc_sets = P.acc_sets;
     sp.place.in = in0; sp.place.w = w0; sp.place.task_n = P.task_n; sp.place.trace = x->trace;

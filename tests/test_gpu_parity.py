@@ -103,11 +103,14 @@ def test_auto_mode_takes_the_class_table_scan():
     assert int(engine.LAST_STATS.total_launches) == 1
 
 
-def test_chain_dp_full_evaluation_agrees():
+@pytest.mark.parametrize('knob', ['8', '16', '24'])
+def test_chain_dp_code_paths_agree(knob):
     """The fused step's chain DP works on per-cloud minima and only reads the
-    candidate tables after a rounding hazard (skyopt_step.cuh). SKYOPT_EXP=8
-    forces that full evaluation on every DAG: same plans, same objectives.
-    (The knob is read once per process, hence the subprocess.)"""
+    candidate tables after a rounding hazard; with at most four clouds and
+    non-negative values it runs a shorter recurrence (skyopt_step.cuh).
+    SKYOPT_EXP=8 forces the full evaluation on every DAG, =16 the general
+    recurrence, =24 both: same plans, same objectives. (The knob is read once
+    per process, hence the subprocess.)"""
     import os
     import subprocess
     import sys
@@ -130,7 +133,7 @@ def test_chain_dp_full_evaluation_agrees():
         '        assert int(engine.LAST_STATS.scan_form) in (0, 1, 2, 3, 4)\n'
         'assert not bad, bad\n'
         'print("chains ok")\n')
-    env = dict(os.environ, SKYOPT_EXP='8')
+    env = dict(os.environ, SKYOPT_EXP=knob)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     proc = subprocess.run([sys.executable, '-c', code], cwd=root, env=env,
                           capture_output=True, text=True, timeout=600,

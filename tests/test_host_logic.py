@@ -573,3 +573,23 @@ def test_ssh_proxy_config_restricts_regions(tmp_path):
     finally:
         skypilot_config.set_config(None)
     assert skypilot_config.allowed_regions_by_ssh_proxy('aws') is None
+
+
+def test_config_change_invalidates_pinned_plans(store):
+    """Plans pinned on a Resources object are not replayed after the
+    SkyPilot config changed (the region allow-list is part of the plan)."""
+    from skypilot_b200 import engine, skypilot_config
+    sky.catalog.set_store(store)
+    r = sky.Resources(cloud=sky.clouds.AWS(), cpus='4+')
+    aws = sky.clouds.AWS()
+    try:
+        plan_a, _ = aws.plan_cached(engine.ProblemBuilder(store), r)
+        rec_a = r.__dict__['_plan_templates'][1][(sky.clouds.AWS, False)][1]
+        skypilot_config.set_config(
+            {'aws': {'ssh_proxy_command': {'us-east-1': 'ssh a'}}})
+        plan_b, _ = aws.plan_cached(engine.ProblemBuilder(store), r)
+        rec_b = r.__dict__['_plan_templates'][1][(sky.clouds.AWS, False)][1]
+        assert plan_a is not plan_b
+        assert rec_a.slot_recs != rec_b.slot_recs  # region_set differs
+    finally:
+        skypilot_config.set_config(None)

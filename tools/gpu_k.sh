@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/ncu_target.py cfg4 auto 8 | tail -1
+python tools/ncu_target.py cfg2 auto 8 | tail -1
+SKYOPT_EXP=16 python tools/ncu_target.py cfg4 auto 8 | tail -1
+SKYOPT_TRACE=gpurun_out/trace_cfg4.txt python tools/ncu_target.py cfg4 auto 6 | tail -1
+python tools/trace2.py gpurun_out/trace_cfg4.txt | tail -9
+SKYOPT_TRACE=gpurun_out/trace_cfg2.txt python tools/ncu_target.py cfg2 auto 6 | tail -1
+python tools/trace2.py gpurun_out/trace_cfg2.txt | tail -22
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zz_late_clouds.py tests/test_gpu_big_configs.py tests/test_gpu_region_filter.py tests/test_gpu_random_dag.py -m gpu -q --timeout 600 -x 2>&1 | tail -3
+timeout 300 /usr/local/cuda/bin/compute-sanitizer --tool racecheck --print-limit 10 python tools/sanitize_target.py auto 2>&1 | grep -E "RACECHECK SUMMARY|mismatches"

@@ -54,6 +54,10 @@ def main(path):
             if ok.any():
                 print(f'  recurrence: {cyc[ok][0]:.0f} cycles in {dur[ok][0]:.0f} ns -> '
                       f'{cyc[ok][0] / dur[ok][0]:.2f} GHz')
+            if blk.shape[1] > 12 and blk[0, 9:13].any():
+                print('  one recurrence step (cycles): operands '
+                      f'{int(blk[0, 9])}, sums + hazard {int(blk[0, 10])}, '
+                      f'minimum {int(blk[0, 11])}, stores + next {int(blk[0, 12])}')
 
 
 if __name__ == '__main__':
