@@ -35,6 +35,7 @@ reference` = the UNMODIFIED reference (baseline/_ref, else /root/reference)
 through oracle/ref_harness on this box's host cores, on a bounded sample.
 """
 import argparse
+import contextlib
 import hashlib
 import json
 import os
@@ -146,6 +147,21 @@ def reference_root():
     return None
 
 
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """The reference writes progress payloads to stdout; this program's
+    stdout carries exactly one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 class ReferenceArm:
     """`sky.Optimizer.optimize` of the reference on one catalog spec (one per
     process: the reference binds its catalog directory at import)."""
@@ -168,7 +184,8 @@ class ReferenceArm:
         frames = synth.make_catalogs(**spec)
         self.n_rows = synth.total_rows(frames)
         bootstrap.write_catalogs(self._home.name, frames)
-        self.sky = bootstrap.import_reference(self._home.name, enabled)
+        with stdout_to_stderr():
+            self.sky = bootstrap.import_reference(self._home.name, enabled)
 
     def optimize_seconds(self, scenario):
         """One cold `Optimizer.optimize(dag, quiet=True)` (request cache
@@ -176,9 +193,10 @@ class ReferenceArm:
         from sky import optimizer as opt_lib  # pylint: disable=import-outside-toplevel
         dag, tasks = self._run.build_dag(self.sky, scenario)
         self._bootstrap.clear_request_cache()
-        t0 = time.perf_counter()
-        opt_lib.Optimizer.optimize(dag, quiet=True)
-        dt = time.perf_counter() - t0
+        with stdout_to_stderr():
+            t0 = time.perf_counter()
+            opt_lib.Optimizer.optimize(dag, quiet=True)
+            dt = time.perf_counter() - t0
         return dt, [self._run._res_record(t.best_resources) for t in tasks]  # pylint: disable=protected-access
 
 
