@@ -85,6 +85,10 @@ class Azure(cloud.Cloud):
                            'S-series instance.')
         return True, ''
 
+    # the override below only looks at disk_tier, which the fast statement
+    # path never sees (cloud.Cloud.plan_fast)
+    _FAST_TEMPLATE_OK = True
+
     def plan_feasible(self, builder, resources: Any,
                       want_list: bool = False) -> cloud.SlotPlan:
         if resources.disk_tier == resources_utils.DiskTier.ULTRA:

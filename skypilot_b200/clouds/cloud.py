@@ -94,6 +94,28 @@ class SlotPlan:
         self.make: Optional[Callable[[str, Any], Any]] = None
 
 
+_INF = float('inf')
+
+
+class _Recorded:
+    """The records of one stated (request, cloud) pair: what plan_cached
+    replays into a ProblemBuilder."""
+    __slots__ = ('query_recs', 'slot_recs')
+
+    def __init__(self):
+        self.query_recs: List[bytes] = []
+        self.slot_recs: List[bytes] = []
+
+    @staticmethod
+    def add_set(store, words) -> int:
+        engine = _late('engine')
+        by_obj = store.__dict__.setdefault('_set_id_by_obj', {})
+        hit = by_obj.get(id(words))
+        if hit is not None and hit[0] is words:
+            return hit[1]
+        return engine.ProblemBuilder(store).add_set(words)
+
+
 class Cloud:
     """A cloud whose offerings live in the GPU-resident catalog."""
 
@@ -398,12 +420,14 @@ class Cloud:
         key = (self.__class__, num_nodes > 1)
         tmpl = local[1].get(key)
         if tmpl is None:
-            plan = SlotPlan()
-            recorder = _late('engine').ProblemBuilder(store)
-            plan.hint = self._feature_hint(resources, num_nodes)
-            if plan.hint is None:
-                plan = self.plan_feasible(recorder, resources)
-            tmpl = (plan, recorder)
+            tmpl = self.plan_fast(store, resources, num_nodes)
+            if tmpl is None:
+                plan = SlotPlan()
+                recorder = _late('engine').ProblemBuilder(store)
+                plan.hint = self._feature_hint(resources, num_nodes)
+                if plan.hint is None:
+                    plan = self.plan_feasible(recorder, resources)
+                tmpl = (plan, recorder)
             local[1][key] = tmpl
         plan, recorder = tmpl
         if plan.slot is None:
@@ -411,6 +435,144 @@ class Cloud:
         qbase = len(builder.query_recs)
         builder.query_recs.extend(recorder.query_recs)
         return plan, builder.replay_slot(recorder, plan.slot, qbase)
+
+    # ---- the common request shapes, stated without the generic machinery ----
+    # `plan_fast` writes the same bytes as `_feature_hint` + `plan_feasible`
+    # for a request that only names accelerators or vCPUs / memory (plus spot,
+    # region, zone, price cap) -- the shape of nearly every task -- with
+    # positional struct packs instead of per-field dicts. Anything else
+    # (instance type, image, disks, ports, TPUs, a feature the cloud lacks, a
+    # SkyPilot config) returns None and takes the generic path. Equality of
+    # the two paths is a CPU test over every fixture scenario
+    # (tests/test_host_statement.py::test_fast_statement_is_byte_identical).
+    _FAST_PLAN = True
+
+    def _fast_ctx(self, store):
+        ctxs = store.__dict__.setdefault('_fast_ctx', {})
+        ctx = ctxs.get(self.__class__)
+        if ctx is None:
+            engine = _late('engine')
+            rules = self._rules()
+            table = self._view().table
+            cloud_obj = self.__class__()
+            keeps_memory = rules.make_keeps_memory
+            check = self.check_disk_tier
+
+            def make(instance_type: str, res):
+                ok, _ = check(instance_type, res.disk_tier)
+                if not ok:
+                    return None
+                if keeps_memory:
+                    return res.copy(cloud=cloud_obj,
+                                    instance_type=instance_type,
+                                    accelerators=None, cpus=None)
+                return res.copy(cloud=cloud_obj, instance_type=instance_type,
+                                accelerators=None, cpus=None, memory=None)
+
+            default_cpus = None
+            if rules.default_cpus is not None:
+                default_cpus = (f'{rules.default_cpus}'
+                                if rules.default_cpus_exact else
+                                f'{rules.default_cpus}+')
+            ctx = {
+                'rules': rules, 'table': table, 'engine': engine,
+                'index': table.index,
+                'has_zone': bool(table.has_zone_column),
+                'by_zone_always': bool(self.optimize_by_zone()),
+                'us_first': int(rules.us_regions_first),
+                'premium': bool(self._needs_premium_disk(None)),
+                'make': make, 'default_cpus': default_cpus,
+                'qpack': engine._QUERY_PACK, 'spack': engine._SLOT_PACK,  # pylint: disable=protected-access
+                'generic': (self.__class__.plan_feasible is Cloud.plan_feasible
+                            or getattr(self.__class__, '_FAST_TEMPLATE_OK',
+                                       False)),
+            }
+            ctxs[self.__class__] = ctx
+        return ctx
+
+    def plan_fast(self, store, resources: Any, num_nodes: int):
+        r = resources
+        if (not self._FAST_PLAN or r._instance_type is not None or  # pylint: disable=protected-access
+                r._image_id is not None or r._local_disk is not None or  # pylint: disable=protected-access
+                r._disk_tier is not None or r._network_tier is not None or  # pylint: disable=protected-access
+                r._ports is not None or r._accelerator_args is not None or  # pylint: disable=protected-access
+                _late('skypilot_config').has_config()):
+            return None
+        ctx = self._fast_ctx(store)
+        if not ctx['generic']:
+            return None
+        use_spot = bool(r._use_spot)  # pylint: disable=protected-access
+        if use_spot or num_nodes > 1:
+            # the feature gate (only these two can be asked for here)
+            unsupported = self._unsupported_features_for_resources(r, None)
+            if ((use_spot and
+                 CloudImplementationFeatures.SPOT_INSTANCE in unsupported) or
+                (num_nodes > 1 and
+                 CloudImplementationFeatures.MULTI_NODE in unsupported)):
+                return None
+        rules, table, engine = ctx['rules'], ctx['table'], ctx['engine']
+        plan = SlotPlan()
+        rec = _Recorded()
+        if use_spot and not rules.supports_spot:
+            return plan, rec
+        no_slot = use_spot and rules.spot_without_regions
+        plan.make = ctx['make']
+        accelerators = r._accelerators  # pylint: disable=protected-access
+        max_cost = r._max_hourly_cost  # pylint: disable=protected-access
+        max_price = _INF if max_cost is None else float(max_cost)
+        region, zone = r._region, r._zone  # pylint: disable=protected-access
+        premium = ctx['premium']
+        index = ctx['index']
+        if accelerators is None:
+            cpus, memory = r._cpus, r._memory  # pylint: disable=protected-access
+            if (cpus is None and
+                    (memory is None or rules.default_cpus_always) and
+                    ctx['default_cpus'] is not None):
+                cpus = ctx['default_cpus']
+            if memory is None and rules.default_memory is not None:
+                memory = rules.default_memory
+            elif memory is None and rules.default_mem_ratio is not None:
+                memory = f'{rules.default_mem_ratio}x'
+            flags = (_native.F_DEFAULT_FAMILY | _native.F_HAS_INSTANCE |
+                     (_native.F_PREMIUM_DISK if premium else 0))
+            in_region = rules.default_query_region
+            cop, cval = engine.parse_cpus(cpus)
+            mop, mval = engine.parse_memory(memory)
+            rec.query_recs.append(ctx['qpack'](
+                index, 0, flags, 0, -1, -1,
+                1 if (use_spot and max_cost is not None) else 0, cop, mop, 0,
+                engine.region_filter_id(table, region if in_region else None),
+                engine.zone_filter_id(table, zone if in_region else None),
+                0, cval, mval, 0, max_price))
+            plan.list_query = 0
+        else:
+            assert len(accelerators) == 1, resources
+            acc, acc_count = next(iter(accelerators.items()))
+            exact, _, _ = engine.accelerator_sets(store, acc, acc_count)
+            in_region = rules.acc_query_region
+            cop, cval = engine.parse_cpus(
+                r._cpus if rules.acc_query_cpus else None)  # pylint: disable=protected-access
+            mop, mval = engine.parse_memory(
+                r._memory if rules.acc_query_memory else None)  # pylint: disable=protected-access
+            rec.query_recs.append(ctx['qpack'](
+                index, _native.Q_ACC, 0, 0, rec.add_set(store, exact), -1,
+                1 if (use_spot and not rules.spot_without_regions) else 0,
+                cop, mop, 0,
+                engine.region_filter_id(table, region if in_region else None),
+                engine.zone_filter_id(table, zone if in_region else None),
+                _native.F_PREMIUM_DISK if premium else 0, cval, mval, 0,
+                max_price))
+            plan.list_query = 0
+            plan.fuzzy_query = 0
+        if not no_slot:
+            by_zone = ctx['has_zone'] and (use_spot or ctx['by_zone_always'])
+            rec.slot_recs.append(ctx['spack'](
+                index, 0, -1, -1, -1, 1 if use_spot else 0,
+                engine.region_exact_id(table, region),
+                engine.zone_exact_id(table, zone), int(by_zone),
+                ctx['us_first'], -1, int(use_spot), -1, 1.0, 1.0, 3600.0))
+            plan.slot = 0
+        return plan, rec
 
     def plan_feasible(self, builder, resources: Any,
                       want_list: bool = False) -> SlotPlan:

@@ -100,6 +100,123 @@ class GCP(cloud.Cloud):
             regions = [r for r in regions if r.zones]
         return regions
 
+    def plan_fast(self, store, resources: Any, num_nodes: int):
+        """The two common shapes of plan_feasible below (vCPUs / memory; one
+        non-TPU accelerator), same bytes, positional packs
+        (cloud.Cloud.plan_fast)."""
+        r = resources
+        if (r._instance_type is not None or r._image_id is not None or  # pylint: disable=protected-access
+                r._local_disk is not None or r._disk_tier is not None or  # pylint: disable=protected-access
+                r._network_tier is not None or r._ports is not None or  # pylint: disable=protected-access
+                r._accelerator_args is not None or  # pylint: disable=protected-access
+                cloud._late('skypilot_config').has_config()):  # pylint: disable=protected-access
+            return None
+        if num_nodes > 1 or r._use_spot:  # pylint: disable=protected-access
+            unsupported = self._unsupported_features_for_resources(r, None)
+            feats = cloud.CloudImplementationFeatures
+            if ((r._use_spot and feats.SPOT_INSTANCE in unsupported) or  # pylint: disable=protected-access
+                    (num_nodes > 1 and feats.MULTI_NODE in unsupported)):
+                return None
+        engine = cloud._late('engine')  # pylint: disable=protected-access
+        ctxs = store.__dict__.setdefault('_fast_ctx', {})
+        ctx = ctxs.get(GCP)
+        if ctx is None:
+            gcp = GCP()
+            ctx = {
+                'table': self._view().table, 'rules': self._rules(),
+                'make_cpu': lambda name, res: res.copy(
+                    cloud=gcp, instance_type=name, accelerators=None,
+                    cpus=None, memory=None),
+                'gcp': gcp,
+            }
+            ctxs[GCP] = ctx
+        table = ctx['table']
+        index = table.index
+        use_spot = bool(r._use_spot)  # pylint: disable=protected-access
+        region, zone = r._region, r._zone  # pylint: disable=protected-access
+        max_cost = r._max_hourly_cost  # pylint: disable=protected-access
+        max_price = cloud._INF if max_cost is None else float(max_cost)  # pylint: disable=protected-access
+        plan = cloud.SlotPlan()
+        rec = cloud._Recorded()  # pylint: disable=protected-access
+        qpack, spack = engine._QUERY_PACK, engine._SLOT_PACK  # pylint: disable=protected-access
+        has_inst = _native.F_HAS_INSTANCE
+        accelerators = r._accelerators  # pylint: disable=protected-access
+        cpus, memory = r._cpus, r._memory  # pylint: disable=protected-access
+        region_x = engine.region_exact_id(table, region)
+        zone_x = engine.zone_exact_id(table, zone)
+        if accelerators is None:
+            if cpus is None and memory is None:
+                cpus = f'{ctx["rules"].default_cpus}+'
+            if memory is None:
+                memory = f'{ctx["rules"].default_mem_ratio}x'
+            cop, cval = engine.parse_cpus(cpus)
+            mop, mval = engine.parse_memory(memory)
+            rec.query_recs.append(qpack(
+                index, 0, _native.F_DEFAULT_FAMILY | has_inst, 0, -1, -1,
+                1 if (use_spot and max_cost is not None) else 0, cop, mop, 0,
+                engine.region_filter_id(table, region),
+                engine.zone_filter_id(table, zone), 0, cval, mval, 0,
+                max_price))
+            plan.list_query = 0
+            plan.make = ctx['make_cpu']
+            rec.slot_recs.append(spack(
+                index, 0, -1, -1, -1, 1 if use_spot else 0, region_x, zone_x,
+                1, 0, -1, int(use_spot), -1, 1.0, 1.0, 3600.0))
+            plan.slot = 0
+            return plan, rec
+        assert len(accelerators) == 1, resources
+        acc, acc_count = next(iter(accelerators.items()))
+        if acc.startswith('tpu-'):
+            return None
+        exact, _, strict = engine.accelerator_sets(store, acc, acc_count)
+        cop, cval = engine.parse_cpus(cpus)
+        mop, mval = engine.parse_memory(memory)
+        # 1) the gate: do accelerator rows exist at all
+        rec.query_recs.append(qpack(
+            index, _native.Q_ACC, 0, 0, rec.add_set(store, exact), -1,
+            1 if use_spot else 0, cop, mop, 0,
+            engine.region_filter_id(table, region),
+            engine.zone_filter_id(table, zone), 0, cval, mval, 0, max_price))
+        plan.gate_query = 0
+        plan.fuzzy_query = 0
+        gcp = ctx['gcp']
+        acc_dict = {acc: acc_count}
+        plan.make = lambda name, res: res.copy(
+            cloud=gcp, instance_type=name, accelerators=acc_dict, cpus=None,
+            memory=None)
+        # 2) the host VM
+        if acc in rules.GCP_FIXED_HOSTS:
+            group = rules.GCP_GROUP_IDS.get((acc, acc_count))
+            if group is None:
+                return plan, rec
+            rec.query_recs.append(qpack(
+                index, 0, has_inst, group, -1, -1, 0, cop, mop, 0, -1, -1, 0,
+                cval, mval, 0, cloud._INF))  # pylint: disable=protected-access
+        else:
+            table_cpus = rules.GCP_ACC_HOST_CPUS.get(
+                acc, rules.GCP_ACC_HOST_CPUS['DEFAULT'])
+            default_cpus = table_cpus.get(acc_count)
+            if cpus is None and memory is None:
+                if default_cpus is None:
+                    return plan, rec
+                cpus = f'{default_cpus}+'
+            if memory is None:
+                cpu_val = int(cpus.strip('+').strip('x'))
+                memory = f'{cpu_val * rules.GCP_GPU_MEMORY_CPU_RATIO}+'
+            hop, hval = engine.parse_cpus(cpus)
+            hmop, hmval = engine.parse_memory(memory)
+            rec.query_recs.append(qpack(
+                index, 0, _native.F_HOST_FAMILY | has_inst, 0, -1, -1, 0, hop,
+                hmop, 0, -1, -1, 0, hval, hmval, 0, cloud._INF))  # pylint: disable=protected-access
+        plan.list_query = 1
+        key = store.acc_key_index.get((acc, float(acc_count)), -2)
+        rec.slot_recs.append(spack(
+            index, 1, -1, 0, rec.add_set(store, strict),
+            1 if use_spot else 0, region_x, zone_x, 1, 0, key, int(use_spot),
+            -1, 1.0, 1.0, 3600.0))
+        plan.slot = 0
+        return plan, rec
+
     def plan_feasible(self, builder, resources: Any,
                       want_list: bool = False) -> cloud.SlotPlan:
         engine = cloud._late('engine')  # pylint: disable=protected-access

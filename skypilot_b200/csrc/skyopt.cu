@@ -176,6 +176,9 @@ int ensure(Ctx *x, size_t dbytes, size_t hbytes) {
     x->dbuf = nullptr; x->dcap = 0;
     const size_t cap = align_up(dbytes + dbytes / 4, 1 << 20);
     CU(cudaMalloc(&x->dbuf, cap));
+    // result fields a kernel does not write for a given problem (e.g. the
+    // chosen candidate of a DAG without a plan) are copied back as zeros
+    CU(cudaMemset(x->dbuf, 0, cap));
     x->dcap = cap;
   }
   if (hbytes > x->hcap) {

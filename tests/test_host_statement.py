@@ -163,3 +163,72 @@ def test_stated_queries_pick_the_oracles_instance(catalog, scenario):
                 # spot: ibm.py:88-92) -- no candidates either way
                 continue
             assert have == want, (ti, cloud, have, want)
+
+
+# ---------------------------------------------------------------------------
+# The fast statement path (Cloud.plan_fast) writes the bytes of the generic
+# one (_feature_hint + plan_feasible).
+def _both_statements(store, cloud, res, num_nodes):
+    from skypilot_b200 import engine
+    from skypilot_b200.clouds import cloud as cloud_lib
+    fast = cloud.plan_fast(store, res, num_nodes)
+    plan = cloud_lib.SlotPlan()
+    recorder = engine.ProblemBuilder(store)
+    plan.hint = cloud._feature_hint(res, num_nodes)  # pylint: disable=protected-access
+    if plan.hint is None:
+        plan = cloud.plan_feasible(recorder, res)
+    return fast, (plan, recorder)
+
+
+@pytest.mark.parametrize('suite', _SUITES + ['altres', 'regfilter'])
+def test_fast_statement_is_byte_identical(suite):
+    import skypilot_b200 as sky
+    from skypilot_b200 import workloads
+    all_suites = dict(scenarios.ALL_SUITES, **scenarios.EXTRA_GOLDEN_SUITES)
+    store = runner.activate_catalog(scenarios.CATALOGS[suite])
+    enabled = sky.check.get_cached_enabled_clouds_or_refresh()
+    n_fast = n_all = 0
+    for sc in all_suites[suite]():
+        if sc.get('config') is not None:
+            continue  # a SkyPilot config always takes the generic path
+        try:
+            _, tasks = workloads.build_dag(sc)
+        except ValueError:
+            continue  # an invalid request (e.g. a bad image tag)
+        for task in tasks:
+            for res in task.resources:
+                clouds_list = [res.cloud] if res.cloud is not None else enabled
+                for cloud in clouds_list:
+                    if not store.has_cloud(cloud.canonical_name()):
+                        continue
+                    fast, (plan, rec) = _both_statements(
+                        store, cloud, res, task.num_nodes)
+                    n_all += 1
+                    if fast is None:
+                        continue
+                    n_fast += 1
+                    fplan, frec = fast
+                    where = (sc['name'], repr(res), repr(cloud))
+                    assert fplan.hint is None and plan.hint is None, where
+                    for attr in ('slot', 'list_query', 'fuzzy_query',
+                                 'gate_query', 'explicit_instance',
+                                 'no_fuzzy_when_matched'):
+                        assert getattr(fplan, attr) == getattr(plan, attr), (
+                            where, attr)
+                    assert frec.query_recs == rec.query_recs, where
+                    assert frec.slot_recs == rec.slot_recs, where
+                    assert (fplan.make is None) == (plan.make is None), where
+                    if plan.make is not None and plan.list_query is not None:
+                        # same launchable for some instance type of the cloud
+                        name = store.cloud(
+                            cloud.canonical_name()).inst_names[0]
+                        a, b = fplan.make(name, res), plan.make(name, res)
+                        assert repr(a) == repr(b) and (
+                            a is None or
+                            (a.cpus, a.memory, a.accelerators, a.use_spot,
+                             a.region, a.zone) ==
+                            (b.cpus, b.memory, b.accelerators, b.use_spot,
+                             b.region, b.zone)), where
+    assert n_all > 0
+    if suite in ('multi6k', 'multi50k', 'fuzz6k', 'fuzzmany'):
+        assert n_fast > n_all // 2, (n_fast, n_all)  # the path is really taken
