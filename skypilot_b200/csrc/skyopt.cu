@@ -68,7 +68,8 @@ struct Ctx {
   char *hbuf = nullptr; size_t hcap = 0;   // pinned staging
   uint32_t *flush = nullptr; size_t flush_words = 0;
   unsigned long long *trace = nullptr;  // SKYOPT_TRACE: device-side timeline
-  unsigned int *sync = nullptr;         // step_kernel's barrier counters (zero between launches)
+  unsigned int *sync = nullptr;         // step_kernel's barrier counter: monotone, never reset in a launch
+  unsigned int sync_total = 0;          // arrivals expected so far (the next launch's barrier target)
 };
 
 // Bump allocator over one buffer; first pass (base == nullptr) only sizes.
@@ -200,7 +201,7 @@ struct Plan {
   int64_t cand_cap = 0;   // expand candidate buffers
   int64_t scan_rows = 0, pass_rows = 0;
   // round-2 fast path (scan2_kernel + place_kernel)
-  bool fast = false; mutable bool fresh_inputs = true; int n_groups2 = 0, n_pieces = 0, scan2_grid = 0, smem_fa = 0, smem_cm = 0;
+  bool fast = false; mutable bool fresh_inputs = true; mutable int parity = 0; int n_groups2 = 0, n_pieces = 0, scan2_grid = 0, smem_fa = 0, smem_cm = 0;
   size_t scan2_smem = 0; int64_t layout_rows = 0;
   Scan2Group *groups2; const Scan2Group *host_groups2 = nullptr; uint32_t *best_rank, *any_in;
   PlaceTask *ptasks; SlotAux *saux; uint32_t cap_fa = 0, cap_cm = 0, cap_rz = 0;
@@ -247,9 +248,11 @@ void carve_inputs(Plan &P, Carver &c) {
   P.ptasks = c.take<PlaceTask>(P.fast ? P.nt : 0);
   P.saux = c.take<SlotAux>(P.fast ? P.ns : 0);
   P.dag_done = c.take<int32_t>(P.fast ? P.nd : 0);
-  P.group_ready = c.take<unsigned int>(P.n_groups2);
-  P.best_rank = c.take<uint32_t>(P.fast ? P.nq : 0);
-  P.any_in = c.take<uint32_t>(P.fast ? P.nq : 0);
+  // two copies: a launch works on one and re-arms the other for the next
+  // launch of a device-resident loop (skyopt_optimize_timed), off its own path
+  P.group_ready = c.take<unsigned int>(2 * (size_t)P.n_groups2);
+  P.best_rank = c.take<uint32_t>(P.fast ? 2 * (size_t)P.nq : 0);
+  P.any_in = c.take<uint32_t>(P.fast ? 2 * (size_t)P.nq : 0);
 }
 
 void carve_rest(Plan &P, Carver &c) {
@@ -649,10 +652,10 @@ int build_plan(SkyoptCatalog *cat, const SkyoptProblem *pb, Ctx *x, Plan &P) {
   if (P.fast) {
     for (int i = 0; i < P.nsq; ++i) fill_record(P.squeries[i], order2[i]);
     memcpy(P.groups2, groups2.data(), sizeof(Scan2Group) * groups2.size());
-    memset(P.best_rank, 0xFF, sizeof(uint32_t) * P.nq);
-    memset(P.any_in, 0, sizeof(uint32_t) * P.nq);
+    memset(P.best_rank, 0xFF, sizeof(uint32_t) * 2 * P.nq);
+    memset(P.any_in, 0, sizeof(uint32_t) * 2 * P.nq);
     if (P.nd) memset(P.dag_done, 0, sizeof(int32_t) * P.nd);
-    if (P.n_groups2) memset(P.group_ready, 0, sizeof(unsigned int) * P.n_groups2);
+    if (P.n_groups2) memset(P.group_ready, 0, sizeof(unsigned int) * 2 * P.n_groups2);
     // what a task block / a slot needs, in one record each
     for (int t = 0; t < P.nt; ++t) {
       const SkyoptDag &D = pb->dags[P.task_dag[t]];
@@ -746,7 +749,11 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
   CU(cudaEventRecord(x->ev[1], st));
   Scan2Args sa{};
   sa.cat = cat->dev; sa.f = cat->fast; sa.squeries = P.squeries; sa.groups = P.groups2;
-  sa.n_groups = P.n_groups2; sa.n_pieces = P.n_pieces; sa.best_rank = P.best_rank; sa.any1 = P.any_in;
+  sa.n_groups = P.n_groups2; sa.n_pieces = P.n_pieces;
+  // fused launches alternate between the two copies of the scan results
+  const size_t par = (size_t)(P.parity & 1), oth = par ^ 1;
+  uint32_t *best_rank = P.best_rank + par * P.nq, *any_in = P.any_in + par * P.nq;
+  sa.best_rank = best_rank; sa.any1 = any_in;
   sa.zero_flag = P.err_out; sa.cap_fa = P.cap_fa; sa.cap_cm = P.cap_cm; sa.cap_rz = P.cap_rz;
   sa.trace = x->trace; sa.shared_tables = nullptr; sa.group_ready = nullptr;
   for (int i = 0; i < std::min(P.n_groups2, kInlineGroups2); ++i) {
@@ -765,16 +772,23 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     StepArgs sp{};
     sp.scan = sa;
     static const int exp_flags = [] { const char *e = getenv("SKYOPT_EXP"); return e ? atoi(e) : 0; }();
-    if (!(exp_flags & 2)) { sp.scan.shared_tables = P.shared_tables; sp.scan.group_ready = P.group_ready; }
+    if (!(exp_flags & 2)) { sp.scan.shared_tables = P.shared_tables; sp.scan.group_ready = P.group_ready + par * P.n_groups2; }
+    sp.next_best_rank = P.best_rank + oth * P.nq; sp.next_any1 = P.any_in + oth * P.nq;
+    sp.next_group_ready = P.group_ready + oth * P.n_groups2;
     if (exp_flags & 4) sp.scan.noprune |= 4u;  // experiment: spin without nanosleep
     sp.force_full = ((exp_flags & 8) ? 1 : 0) | ((exp_flags & 16) ? 2 : 0);   // test knob: evaluate every candidate in the chain DP
     sp.place.cat = cat->dev; sp.place.f = cat->fast; sp.place.ptasks = P.ptasks; sp.place.saux = P.saux;
-    sp.place.best_rank = P.best_rank; sp.place.any1 = P.any_in; sp.place.acc_sets = P.acc_sets;
+    sp.place.best_rank = best_rank; sp.place.any1 = any_in; sp.place.acc_sets = P.acc_sets;
     sp.place.in = in0; sp.place.w = w0; sp.place.task_n = P.task_n; sp.place.trace = x->trace;
     sp.place.task_mv = P.task_mv;
     sp.out = SolveOut{P.chosen, P.chosen_index, P.task_n, P.dagres, x->trace};
     sp.task_dag = P.task_dag; sp.n_tasks = P.nt; sp.do_solve = P.chain_dags ? 1 : 0;
     sp.dag_done = P.dag_done; sp.sync = x->sync;
+    if (x->sync_total > 0x70000000u - (unsigned)P.step_grid) {
+      CU(cudaMemsetAsync(x->sync, 0, sizeof(unsigned int), st));
+      x->sync_total = 0;
+    }
+    sp.sync_target = x->sync_total + (unsigned)P.step_grid;
     sp.n_queries = P.nq;
     sp.in_base = x->dbuf; sp.in_lines = (int64_t)((P.in_bytes + 127) / 128);
     void *args[] = {&sp};
@@ -783,6 +797,8 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     cudaError_t le = cudaLaunchCooperativeKernel((const void *)step_kernel, dim3(P.step_grid), dim3(kScanThreads),
                                                  args, P.step_smem, st);
     if (le == cudaSuccess) {
+      x->sync_total += (unsigned)P.step_grid;
+      P.parity ^= 1;
       if (!P.chain_dags && P.nd) {
         SolveOut out{P.chosen, P.chosen_index, P.task_n, P.dagres, x->trace};
         solve_kernel<<<P.nd, kSolveThreads, 0, st>>>(cat->dev, in0, w0, out);
@@ -796,8 +812,8 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
   }
   if (P.nq) {
     if (!P.fresh_inputs) {
-      CU(cudaMemsetAsync(P.best_rank, 0xFF, sizeof(uint32_t) * P.nq, st));
-      CU(cudaMemsetAsync(P.any_in, 0, sizeof(uint32_t) * P.nq, st));
+      CU(cudaMemsetAsync(best_rank, 0xFF, sizeof(uint32_t) * P.nq, st));
+      CU(cudaMemsetAsync(any_in, 0, sizeof(uint32_t) * P.nq, st));
     }
     CU(cudaEventRecord(x->ev[6], st));
     if (P.n_pieces) {
@@ -807,7 +823,7 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
     CU(cudaEventRecord(x->ev[7], st));
     if (want_scan_results || !solve) {
       finalize2_kernel<<<(P.nq + 127) / 128, 128, 0, st>>>(cat->dev, cat->fast, P.nq, P.queries,
-                                                          P.best_rank, P.any_in, P.finals, P.any1);
+                                                          best_rank, any_in, P.finals, P.any1);
       CU(cudaGetLastError());
     }
   }
@@ -819,8 +835,8 @@ int enqueue_fast(SkyoptCatalog *cat, Ctx *x, const Plan &P, bool solve, bool wan
   SolveWork w{P.tc_ref, P.tc_slot, P.tc_cloud, P.tc_hourly, P.tc_value, P.dp, P.back};
   if (P.nt) {
     PlaceArgs pa{};
-    pa.cat = cat->dev; pa.f = cat->fast; pa.ptasks = P.ptasks; pa.saux = P.saux; pa.best_rank = P.best_rank;
-    pa.any1 = P.any_in; pa.acc_sets = P.acc_sets; pa.in = in; pa.w = w;
+    pa.cat = cat->dev; pa.f = cat->fast; pa.ptasks = P.ptasks; pa.saux = P.saux; pa.best_rank = best_rank;
+    pa.any1 = any_in; pa.acc_sets = P.acc_sets; pa.in = in; pa.w = w;
     pa.task_n = P.task_n; pa.trace = x->trace; pa.task_mv = nullptr;
     place_kernel<<<P.nt, kScanThreads, sizeof(PlaceSmem), st>>>(pa);
     CU(cudaGetLastError());

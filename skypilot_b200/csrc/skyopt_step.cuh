@@ -421,7 +421,12 @@ struct StepArgs {
   int do_solve;           // every DAG is a chain of <= kFastTasks tasks
   int force_full;         // test knobs: bit 0 chain_full() on every DAG (SKYOPT_EXP=8), bit 1 the general recurrence (SKYOPT_EXP=16)
   int32_t *dag_done;      // [n_dags] tasks placed so far (zero between launches)
-  unsigned int *sync;     // [2] arrivals at the barrier / at the exit (zero between launches)
+  unsigned int *sync;     // arrivals at the grid barrier, counted across launches
+  unsigned int sync_target;  // ... and the count that completes this launch's barrier
+  // the other copy of the scan results: re-armed here for the next launch of a
+  // device-resident loop, by blocks that have passed the barrier
+  uint32_t *next_best_rank, *next_any1;
+  unsigned int *next_group_ready;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
@@ -447,20 +452,38 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) step_kernel(St
   if (tid == 0) {
     __threadfence();
     atomicAdd(a.sync, 1u);
-    while (ld_acquire_u32(a.sync) < gridDim.x) if (!(a.scan.noprune & 4u)) __nanosleep(64);
+    // (the counter only grows: the host passes the total that ends this
+    // launch's barrier, so nothing has to be reset on the way out)
+    while ((int)(ld_acquire_u32(a.sync) - a.sync_target) < 0) if (!(a.scan.noprune & 4u)) __nanosleep(64);
     __threadfence();
   }
   __syncthreads();
+  // ---- re-arm the other copy of the scan results (nobody reads it in this
+  // launch): a few stores per block, off the critical path
+#pragma unroll 1
+  for (int i = blockIdx.x * kScanThreads + tid; i < a.n_queries; i += gridDim.x * kScanThreads) {
+    a.next_best_rank[i] = kRankNone; a.next_any1[i] = 0u;
+  }
+  if (a.scan.group_ready)
+#pragma unroll 1
+    for (int i = blockIdx.x * kScanThreads + tid; i < a.scan.n_groups; i += gridDim.x * kScanThreads)
+      a.next_group_ready[i] = 0u;
   for (int t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+    // which DAG, and how many tasks it has: asked for before the placement,
+    // needed right after it
+    int dag = 0, dag_tasks = 0;
+    if (a.do_solve) {
+      dag = a.task_dag[t];
+      const SkyoptDag D = a.place.in.dags[dag];
+      dag_tasks = D.task_end - D.task_begin;
+    }
     place_body(a.place, t, smem_step);
     if (a.do_solve) {
-      const int dag = a.task_dag[t];
       __syncthreads();  // the task's tables are written
       if (tid == 0) {
-        const SkyoptDag D = a.place.in.dags[dag];
         __threadfence();
         const int done = atomicAdd(a.dag_done + dag, 1);
-        s_last = (done == D.task_end - D.task_begin - 1) ? 1 : 0;
+        s_last = (done == dag_tasks - 1) ? 1 : 0;
         if (s_last) a.dag_done[dag] = 0;  // ready for the next launch
       }
       __syncthreads();
@@ -470,21 +493,6 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) step_kernel(St
       }
     }
     __syncthreads();  // shared memory is reused by the next task
-  }
-  // ---- the last block out re-arms the barrier and the scan results (the
-  // next launch of this context starts from "nothing found")
-  if (tid == 0) {
-    __threadfence();
-    s_last = (atomicAdd(a.sync + 1, 1u) == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-#pragma unroll 1
-    for (int i = tid; i < a.n_queries; i += kScanThreads) { a.scan.best_rank[i] = kRankNone; a.scan.any1[i] = 0u; }
-    if (a.scan.group_ready)
-#pragma unroll 1
-      for (int i = tid; i < a.scan.n_groups; i += kScanThreads) a.scan.group_ready[i] = 0u;
-    if (tid == 0) { __threadfence(); a.sync[0] = 0; a.sync[1] = 0; }
   }
 }
 
