@@ -386,8 +386,9 @@ class Cloud:
                 None if r.ports is None else tuple(r.ports),
                 _late('skypilot_config').generation())
 
-    def plan_cached(self, builder, resources: Any,
-                    num_nodes: int = 1) -> Tuple[SlotPlan, Optional[int]]:
+    def plan_cached(self, builder, resources: Any, num_nodes: int = 1,
+                    cost: Tuple[float, float, float] = (1.0, 1.0, 3600.0)
+                   ) -> Tuple[SlotPlan, Optional[int]]:
         """`_feature_hint` + `plan_feasible`, memoised per (cloud, request
         fields) on the catalog store and replayed into `builder`: the fused
         optimizer states the same request shapes over and over (failover
@@ -432,9 +433,14 @@ class Cloud:
         plan, recorder = tmpl
         if plan.slot is None:
             return plan, None
-        qbase = len(builder.query_recs)
+        # replay: the recorded bytes, the query base of this copy and the
+        # slot's (hours, node_mult, time_value)
+        builder.slot_qbase.append(len(builder.query_recs))
         builder.query_recs.extend(recorder.query_recs)
-        return plan, builder.replay_slot(recorder, plan.slot, qbase)
+        slots = builder.slot_recs
+        slots.append(recorder.slot_recs[plan.slot])
+        builder.slot_cost.extend(cost)
+        return plan, len(slots) - 1
 
     # ---- the common request shapes, stated without the generic machinery ----
     # `plan_fast` writes the same bytes as `_feature_hint` + `plan_feasible`

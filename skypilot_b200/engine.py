@@ -230,10 +230,13 @@ _QUERY_DEFAULTS = _defaults(_native.QUERY_DTYPE, {})
 _SLOT_DEFAULTS = _defaults(_native.SLOT_DTYPE, {
     'query': -1, 'inst_id': -1, 'gate_query': -1, 'cand_acc_key': -1,
     'hours': 1.0, 'node_mult': 1.0, 'time_value': 3600.0})
+_DEFAULT_COST = (1.0, 1.0, 3600.0)
 _QUERY_PACK = _packer(_native.QUERY_DTYPE)[0].pack
 _QUERY_FIELDS = operator.itemgetter(*_packer(_native.QUERY_DTYPE)[1])
 _SLOT_PACK = _packer(_native.SLOT_DTYPE)[0].pack
 _SLOT_FIELDS = operator.itemgetter(*_packer(_native.SLOT_DTYPE)[1])
+_TASK_PACK = _packer(_native.TASK_DTYPE)[0].pack
+_TASK_FIELDS = operator.itemgetter(*_packer(_native.TASK_DTYPE)[1])
 
 
 class ProblemBuilder:
@@ -251,7 +254,10 @@ class ProblemBuilder:
         self.query_recs: List[bytes] = []
         self.slot_recs: List[bytes] = []
         self.slot_qbase: List[int] = []
-        self.slot_cost: List[Optional[Tuple[float, float, float]]] = []
+        # (hours, node_mult, time_value) of every slot, flat: three floats
+        # per slot, patched into the records by one numpy pass in pack()
+        self.slot_cost: List[float] = []
+        self.task_recs: List[bytes] = []
         self.tasks: List[Dict[str, Any]] = []
         self.parents: List[int] = []
         self.tariffs: List[float] = []
@@ -303,12 +309,12 @@ class ProblemBuilder:
         starting at index `qbase`."""
         self.slot_recs.append(recorder.slot_recs[i])
         self.slot_qbase.append(qbase)
-        self.slot_cost.append(None)
+        self.slot_cost.extend(_DEFAULT_COST)
         return len(self.slot_recs) - 1
 
     def set_slot_cost(self, slot: int, hours: float, node_mult: float,
                       time_value: float) -> None:
-        self.slot_cost[slot] = (hours, node_mult, time_value)
+        self.slot_cost[3 * slot:3 * slot + 3] = (hours, node_mult, time_value)
 
     def add_query(self, spec: Dict[str, Any]) -> int:
         q = dict(_QUERY_DEFAULTS)
@@ -405,7 +411,8 @@ class ProblemBuilder:
             slot['region_set'] = self.add_set(region_words)
         self.slot_recs.append(_SLOT_PACK(*_SLOT_FIELDS(slot)))
         self.slot_qbase.append(0)
-        self.slot_cost.append(None)
+        self.slot_cost.extend((slot['hours'], slot['node_mult'],
+                               slot['time_value']))
         return len(self.slot_recs) - 1
 
     def add_task(self,
@@ -430,7 +437,12 @@ class ProblemBuilder:
             task['src_tariff_begin'] = len(self.tariffs)
             self.tariffs.extend(float(v) for v in src_tariff)
         self.tasks.append(task)
+        self.task_recs.append(_TASK_PACK(*_TASK_FIELDS(task)))
         return len(self.tasks) - 1
+
+    def set_task_field(self, i: int, name: str, value: int) -> None:
+        self.tasks[i][name] = value
+        self.task_recs[i] = _TASK_PACK(*_TASK_FIELDS(self.tasks[i]))
 
     def add_blocked(self, **fields) -> int:
         entry = {
@@ -501,21 +513,19 @@ class PackedProblem:
             slots = np.frombuffer(b''.join(b.slot_recs),
                                   dtype=_native.SLOT_DTYPE).copy()
             qbase = np.asarray(b.slot_qbase, dtype=np.int32)
-            if qbase.any():
-                for name in ('query', 'gate_query'):
-                    col = slots[name]
-                    slots[name] = np.where(col >= 0, col + qbase, col)
-            costed = [i for i, c in enumerate(b.slot_cost) if c is not None]
-            if costed:
-                cost = np.asarray([b.slot_cost[i] for i in costed],
-                                  dtype=np.float64)
-                slots['hours'][costed] = cost[:, 0]
-                slots['node_mult'][costed] = cost[:, 1]
-                slots['time_value'][costed] = cost[:, 2]
+            for name in ('query', 'gate_query'):
+                col = slots[name]
+                col += qbase * (col >= 0)
+            cost = np.asarray(b.slot_cost, dtype=np.float64).reshape(-1, 3)
+            slots['hours'] = cost[:, 0]
+            slots['node_mult'] = cost[:, 1]
+            slots['time_value'] = cost[:, 2]
             self.slots = slots
         else:
             self.slots = np.zeros(1, dtype=_native.SLOT_DTYPE)
-        self.tasks = ProblemBuilder._pack(b.tasks, _native.TASK_DTYPE)
+        self.tasks = (np.frombuffer(b''.join(b.task_recs),
+                                    dtype=_native.TASK_DTYPE)
+                      if b.task_recs else np.zeros(1, _native.TASK_DTYPE))
         self.n_tasks = len(b.tasks)
         self.parents = np.asarray(b.parents or [0], dtype=np.int32)
         self.n_parents = len(b.parents)

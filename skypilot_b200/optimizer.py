@@ -174,6 +174,17 @@ class Optimizer:
             exceptions.NoCloudAccessError: no cloud is enabled.
         """
         _check_specified_clouds(dag)
+        if quiet:
+            # The dummy source / sink only matter to the reference's Python DP
+            # and to the totals of the printed plan: the device problem is
+            # stated on the real tasks (a DAG is a chain with or without them,
+            # Dag.is_chain), so a quiet call leaves the graph alone.
+            Optimizer._optimize_dag(
+                dag=dag,
+                minimize_cost=minimize == OptimizeTarget.COST,
+                blocked_resources=blocked_resources,
+                quiet=True)
+            return dag
         Optimizer._add_dummy_source_sink_nodes(dag)
         try:
             Optimizer._optimize_dag(
@@ -489,6 +500,7 @@ class Optimizer:
             res_list = list(task.resources)
             n_res = len(res_list)
             nodes = float(max(task.num_nodes, 0))
+            num_nodes = task.num_nodes
             # A task stated before (same catalog, clouds, request objects,
             # node count) is replayed from its recorded slice of the problem:
             # its query / slot records are bytes that do not depend on the DAG
@@ -509,14 +521,15 @@ class Optimizer:
                 for res in res_list:
                     runtime = Optimizer._runtime(task, n_res, res)
                     costs.append((runtime / 3600, nodes, float(runtime)))
+                flat = b.slot_cost
                 if free_slots:
                     # on-premise clouds: the hourly cost is 0.0
-                    b.slot_cost.extend([
-                        (0.0,) + costs[k][1:] if j in free_slots else costs[k]
-                        for j, k in enumerate(slot_res)
-                    ])
+                    for j, k in enumerate(slot_res):
+                        flat.extend((0.0,) + costs[k][1:]
+                                    if j in free_slots else costs[k])
                 else:
-                    b.slot_cost.extend([costs[k] for k in slot_res])
+                    for k in slot_res:
+                        flat.extend(costs[k])
                 slot_info.extend(infos)
                 for res, by_cloud in task_hints.items():
                     hints[res].update(by_cloud)
@@ -531,13 +544,15 @@ class Optimizer:
                         # catalog
                         res.validate()
                         res.__dict__['_validated_store'] = store
-                    if res.cloud is not None and not clouds.cloud_in_iterable(
-                            res.cloud, enabled):
-                        continue
-                    clouds_list = ([res.cloud]
-                                   if res.cloud is not None else enabled)
-                    runtime = Optimizer._runtime(task, n_res, res)
-                    hours = runtime / 3600
+                    if res.cloud is not None:
+                        if not clouds.cloud_in_iterable(res.cloud, enabled):
+                            continue
+                        clouds_list = [res.cloud]
+                    else:
+                        clouds_list = enabled
+                    runtime = float(Optimizer._runtime(task, n_res, res))
+                    cost = (runtime / 3600, nodes, runtime)
+                    free = (0.0, nodes, runtime)
                     for cloud in clouds_list:
                         table = tables.get(cloud.__class__, 0)
                         if table == 0:
@@ -547,17 +562,16 @@ class Optimizer:
                             tables[cloud.__class__] = table
                         if table is None:
                             continue
-                        plan, slot = cloud.plan_cached(b, res, task.num_nodes)
+                        zero = table.rules.zero_cost
+                        plan, slot = cloud.plan_cached(
+                            b, res, num_nodes, free if zero else cost)
                         if plan.hint is not None:
                             hints[res][cloud] = plan.hint
                             task_hints.setdefault(res, {})[cloud] = plan.hint
                         if slot is None:
                             continue
-                        if table.rules.zero_cost:
+                        if zero:
                             free_slots.add(len(slot_res))
-                            b.set_slot_cost(slot, 0.0, nodes, float(runtime))
-                        else:
-                            b.set_slot_cost(slot, hours, nodes, float(runtime))
                         slot_info.append(
                             _SlotInfo(task, res, cloud, plan, table))
                         slot_res.append(k)
@@ -843,7 +857,7 @@ class Optimizer:
         b.dags = []
         n_blocked = len(b.blocked)
         for i in range(len(real)):
-            b.tasks[i]['n_parents'] = 0
+            b.set_task_field(i, 'n_parents', 0)
             b.add_dag(i, i + 1, True, minimize_cost, 0, n_blocked)
         sol = Optimizer._solve(problem, want_tables=True)
         for i, task in enumerate(real):
