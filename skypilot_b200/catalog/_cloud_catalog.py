@@ -11,6 +11,7 @@ from typing import Dict, List, Optional, Tuple, Union
 
 from skypilot_b200 import _native
 from skypilot_b200.catalog import common
+from skypilot_b200.utils import resources_utils
 from skypilot_b200.catalog import rules as rules_lib
 
 
@@ -76,6 +77,12 @@ class CloudCatalog:
         if self.rules.supports_local_disk:
             view = common.filter_with_local_disk(view, local_disk)
         if self.rules.premium_disk is not None and disk_tier is not None:
+            if not isinstance(disk_tier, resources_utils.DiskTier):
+                # a caller outside this package (the reference's own clouds
+                # when only the catalog function table is swapped,
+                # INTEGRATION.md level 2) passes its own enum
+                disk_tier = resources_utils.DiskTier(
+                    getattr(disk_tier, 'value', disk_tier))
             # e.g. Azure: premium SSD tiers need an S-series VM
             # (sky/catalog/azure_catalog.py:108-112)
             from skypilot_b200.utils import registry  # pylint: disable=import-outside-toplevel

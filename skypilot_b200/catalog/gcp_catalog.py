@@ -78,20 +78,25 @@ def get_instance_type_for_accelerator(
         table = rules.GCP_ACC_HOST_CPUS.get(acc_name,
                                             rules.GCP_ACC_HOST_CPUS['DEFAULT'])
         default_cpus = table.get(acc_count)
-        if cpus is None and memory is None:
-            assert default_cpus is not None, (acc_name, acc_count)
-            cpus = f'{default_cpus}+'
-        if memory is None:
-            assert cpus is not None, (acc_name, acc_count)
-            cpu_val = int(cpus.strip('+').strip('x'))
-            memory = f'{cpu_val * rules.GCP_GPU_MEMORY_CPU_RATIO}+'
-        host = b.add_query(
-            b.cpus_mem_query('gcp', cpus, memory,
-                             flags_require=_native.F_HOST_FAMILY))
+        no_rule = cpus is None and memory is None and default_cpus is None
+        if not no_rule:
+            if cpus is None and memory is None:
+                cpus = f'{default_cpus}+'
+            if memory is None:
+                assert cpus is not None, (acc_name, acc_count)
+                cpu_val = int(cpus.strip('+').strip('x'))
+                memory = f'{cpu_val * rules.GCP_GPU_MEMORY_CPU_RATIO}+'
+            host = b.add_query(
+                b.cpus_mem_query('gcp', cpus, memory,
+                                 flags_require=_native.F_HOST_FAMILY))
     out = engine.scan(b, fuzzy_cap=min(max(len(view.store.acc_keys), 1),
                                        2048), device=view.device)
     if not out.results['any_stage1'][gate]:
         return None, engine.format_fuzzy(view.store, out.fuzzy_list(gate))
+    if acc_name not in rules.GCP_FIXED_HOSTS:
+        # the reference only looks the host rule up once accelerator rows
+        # exist, and asserts there (gcp_catalog.py:376-378)
+        assert host is not None, (acc_name, acc_count)
     if host is None or out.results['best_inst'][host] < 0:
         return None, []
     return [view.store.inst_names[int(out.results['best_inst'][host])]], []

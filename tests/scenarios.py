@@ -1362,7 +1362,8 @@ def catalog_call_cases():
         ('T4', 1, {'cpus': '8+'}, 'gcp'), ('A100', 3, {}, 'aws'),
         ('a100', 8, {}, 'gcp'), ('V100', 2, {'memory': '200+'}, 'azure'),
         ('tpu-v3-8', 1, {}, 'gcp'), ('H100', 8, {'region': 'us-east5'}, 'gcp'),
-        ('NoSuch', 1, {}, 'aws')]):
+        ('NoSuch', 1, {}, 'aws'), ('A10', 0.5, {}, 'gcp'),
+        ('V100', 3, {}, 'gcp')]):
         call(f'for_acc_{i}', 'get_instance_type_for_accelerator', name, count,
              clouds=cloud, **kw)
         call(f'acc_zones_{i}', 'get_region_zones_for_accelerators', name,
