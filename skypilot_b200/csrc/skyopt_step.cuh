@@ -98,100 +98,100 @@ __device__ __noinline__ void chain_full(ChainSmem &M, const SolveWork &w, int T,
 __device__ __noinline__ void recurrence_general(ChainSmem &M, int T, int C, int Cp, bool &hz, double &bv, int &bi) {
   const int lane = threadIdx.x & 31;
   const double kInf = __longlong_as_double(0x7FF0000000000000ll);
-    const int h = lane < C ? lane : 0;
-    const bool live = lane < C;
-    double dprev = 0.0, hprev = 0.0;   // D[t-1][lane], fl(v2[t-1][lane] + B[t-1][lane])
-    int myid = 0x7FFFFFFF;
-    bool has2 = false;
-    // the next task's operands are fetched one step ahead of the dependent chain
-    double tar_n = M.tar[0][h];
-    unsigned long long mk_n = M.mv[0][h], v2_n = M.v2[0][h];
-    int mi_n = M.mi[0][h], np_n = M.np[0];
+  const int h = lane < C ? lane : 0;
+  const bool live = lane < C;
+  double dprev = 0.0, hprev = 0.0;   // D[t-1][lane], fl(v2[t-1][lane] + B[t-1][lane])
+  int myid = 0x7FFFFFFF;
+  bool has2 = false;
+  // the next task's operands are fetched one step ahead of the dependent chain
+  double tar_n = M.tar[0][h];
+  unsigned long long mk_n = M.mv[0][h], v2_n = M.v2[0][h];
+  int mi_n = M.mi[0][h], np_n = M.np[0];
 #pragma unroll 1
-    for (int lt = 0; lt < T; ++lt) {
-      const double tar = tar_n;
-      const unsigned long long mk = mk_n, v2k = v2_n;
-      const int mi = mi_n, np = np_n;
-      if (lt + 1 < T) {
-        tar_n = M.tar[lt + 1][h]; mk_n = M.mv[lt + 1][h]; v2_n = M.v2[lt + 1][h];
-        mi_n = M.mi[lt + 1][h]; np_n = M.np[lt + 1];
-      }
-      double b;
-      if (np == 0) {
-        b = tar;  // dummy source: 0 + egress from the inputs' cloud
-      } else {
-        const double mine = live ? __dadd_rn(dprev, tar) : kInf;
-        // a candidate in front of the cheapest one whose sum rounds the same
-        if (live && has2 && dprev < kInf && (hprev == dprev || __dadd_rn(hprev, tar) == mine)) hz = true;
-        // The minima are taken on price keys: a total order on doubles as
-        // 64-bit integers (equal doubles <=> equal keys for the non-negative
-        // sums here). An fp64 compare-and-select costs four times the latency
-        // of the integer one, and this loop is nothing but dependent compares.
-        const unsigned long long kd = price_key(dprev);
-        const unsigned long long km = price_key(mine);
-        const int idm = live ? myid : 0x7FFFFFFF;
-        unsigned long long bkey = kd;   // own cloud: egress 0
-        int bid = myid;
-        if (Cp <= 8) {
-          // few clouds: every lane reads every cloud's sum (independent
-          // shuffles) and keeps a running first minimum -- a third of the
-          // instructions of the butterfly below, and one warp's time here is
-          // its dependent-instruction count
+  for (int lt = 0; lt < T; ++lt) {
+    const double tar = tar_n;
+    const unsigned long long mk = mk_n, v2k = v2_n;
+    const int mi = mi_n, np = np_n;
+    if (lt + 1 < T) {
+      tar_n = M.tar[lt + 1][h]; mk_n = M.mv[lt + 1][h]; v2_n = M.v2[lt + 1][h];
+      mi_n = M.mi[lt + 1][h]; np_n = M.np[lt + 1];
+    }
+    double b;
+    if (np == 0) {
+      b = tar;  // dummy source: 0 + egress from the inputs' cloud
+    } else {
+      const double mine = live ? __dadd_rn(dprev, tar) : kInf;
+      // a candidate in front of the cheapest one whose sum rounds the same
+      if (live && has2 && dprev < kInf && (hprev == dprev || __dadd_rn(hprev, tar) == mine)) hz = true;
+      // The minima are taken on price keys: a total order on doubles as
+      // 64-bit integers (equal doubles <=> equal keys for the non-negative
+      // sums here). An fp64 compare-and-select costs four times the latency
+      // of the integer one, and this loop is nothing but dependent compares.
+      const unsigned long long kd = price_key(dprev);
+      const unsigned long long km = price_key(mine);
+      const int idm = live ? myid : 0x7FFFFFFF;
+      unsigned long long bkey = kd;   // own cloud: egress 0
+      int bid = myid;
+      if (Cp <= 8) {
+        // few clouds: every lane reads every cloud's sum (independent
+        // shuffles) and keeps a running first minimum -- a third of the
+        // instructions of the butterfly below, and one warp's time here is
+        // its dependent-instruction count
 #pragma unroll 4
-          for (int g = 0; g < C; ++g) {
-            const unsigned long long kg = __shfl_sync(0xFFFFFFFFu, km, g);
-            const int ig = __shfl_sync(0xFFFFFFFFu, idm, g);
-            const bool take = (g != lane) & key_less(kg, ig, bkey, bid);
-            bkey = take ? kg : bkey;
-            bid = take ? ig : bid;
-          }
-        } else {
-          // smallest and second smallest sum (with their ids) by a butterfly;
-          // a lane whose own sum is the smallest takes the second
-          unsigned long long k1 = km, k2 = kKeyInf;
-          int i1 = idm, i2 = 0x7FFFFFFF;
-#pragma unroll 1
-          for (int o = 1; o < Cp; o <<= 1) {
-            const unsigned long long p1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
-            const int q1 = __shfl_xor_sync(0xFFFFFFFFu, i1, o);
-            const unsigned long long p2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
-            const int q2 = __shfl_xor_sync(0xFFFFFFFFu, i2, o);
-            const bool pl = key_less(p1, q1, k1, i1);
-            const unsigned long long lo = pl ? p1 : k1, hi = pl ? k1 : p1;
-            const int loi = pl ? q1 : i1, hii = pl ? i1 : q1;
-            const bool sl = key_less(p2, q2, k2, i2);
-            const unsigned long long s2 = sl ? p2 : k2;
-            const int s2i = sl ? q2 : i2;
-            const bool tl = key_less(s2, s2i, hi, hii);
-            k1 = lo; i1 = loi;
-            k2 = tl ? s2 : hi; i2 = tl ? s2i : hii;
-          }
-          const bool own = i1 == myid;   // ids are distinct: (candidate index, cloud)
-          const unsigned long long ok = own ? k2 : k1;
-          const int oi = own ? i2 : i1;
-          const bool ol = key_less(ok, oi, kd, myid);
-          bkey = ol ? ok : kd;
-          bid = ol ? oi : myid;
+        for (int g = 0; g < C; ++g) {
+          const unsigned long long kg = __shfl_sync(0xFFFFFFFFu, km, g);
+          const int ig = __shfl_sync(0xFFFFFFFFu, idm, g);
+          const bool take = (g != lane) & key_less(kg, ig, bkey, bid);
+          bkey = take ? kg : bkey;
+          bid = take ? ig : bid;
         }
-        b = key_price(bkey);
-        if (live) M.bk[lt][lane] = bid;
-      }
-      if (live) M.B[lt][lane] = b;
-      dprev = (mk == kKeyNone || !live) ? kInf : __dadd_rn(key_price(mk), b);
-      has2 = v2k != kKeyNone;
-      hprev = has2 ? __dadd_rn(key_price(v2k), b) : 0.0;
-      myid = mi;
-    }
-    // the sink: egress 0 from every cloud, first minimum of D[T-1][.]
-    if (live && has2 && dprev < kInf && hprev == dprev) hz = true;
-    bv = live ? dprev : kInf;
-    bi = live ? myid : 0x7FFFFFFF;
+      } else {
+        // smallest and second smallest sum (with their ids) by a butterfly;
+        // a lane whose own sum is the smallest takes the second
+        unsigned long long k1 = km, k2 = kKeyInf;
+        int i1 = idm, i2 = 0x7FFFFFFF;
 #pragma unroll 1
-    for (int o = 1; o < Cp; o <<= 1) {
-      const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
-      const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
-      lexmin(bv, bi, ov, oi);
+        for (int o = 1; o < Cp; o <<= 1) {
+          const unsigned long long p1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o);
+          const int q1 = __shfl_xor_sync(0xFFFFFFFFu, i1, o);
+          const unsigned long long p2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
+          const int q2 = __shfl_xor_sync(0xFFFFFFFFu, i2, o);
+          const bool pl = key_less(p1, q1, k1, i1);
+          const unsigned long long lo = pl ? p1 : k1, hi = pl ? k1 : p1;
+          const int loi = pl ? q1 : i1, hii = pl ? i1 : q1;
+          const bool sl = key_less(p2, q2, k2, i2);
+          const unsigned long long s2 = sl ? p2 : k2;
+          const int s2i = sl ? q2 : i2;
+          const bool tl = key_less(s2, s2i, hi, hii);
+          k1 = lo; i1 = loi;
+          k2 = tl ? s2 : hi; i2 = tl ? s2i : hii;
+        }
+        const bool own = i1 == myid;   // ids are distinct: (candidate index, cloud)
+        const unsigned long long ok = own ? k2 : k1;
+        const int oi = own ? i2 : i1;
+        const bool ol = key_less(ok, oi, kd, myid);
+        bkey = ol ? ok : kd;
+        bid = ol ? oi : myid;
+      }
+      b = key_price(bkey);
+      if (live) M.bk[lt][lane] = bid;
     }
+    if (live) M.B[lt][lane] = b;
+    dprev = (mk == kKeyNone || !live) ? kInf : __dadd_rn(key_price(mk), b);
+    has2 = v2k != kKeyNone;
+    hprev = has2 ? __dadd_rn(key_price(v2k), b) : 0.0;
+    myid = mi;
+  }
+  // the sink: egress 0 from every cloud, first minimum of D[T-1][.]
+  if (live && has2 && dprev < kInf && hprev == dprev) hz = true;
+  bv = live ? dprev : kInf;
+  bi = live ? myid : 0x7FFFFFFF;
+#pragma unroll 1
+  for (int o = 1; o < Cp; o <<= 1) {
+    const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+    const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+    lexmin(bv, bi, ov, oi);
+  }
 }
 
 // shared memory by 32-bit address: the loop below must not re-derive the

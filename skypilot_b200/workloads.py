@@ -22,8 +22,6 @@ CATALOGS: Dict[str, Dict[str, Any]] = {
     'cfg2': {'seed': 1, 'n_rows': 50000, 'clouds': list(CLOUDS4)},
     # cfg4: synthetic 1M-row catalog (seed 3)
     'cfg4': {'seed': 3, 'n_rows': 1000000, 'clouds': list(CLOUDS4)},
-    # no-prune HBM stress: >= 8M rows, larger than the 126 MB L2
-    'stress8m': {'seed': 5, 'n_rows': 8000000, 'clouds': list(CLOUDS4)},
 }
 
 # The cfg2 constraint set.
@@ -84,23 +82,6 @@ def chain_scenario(n_tasks: int) -> Dict[str, Any]:
             spec['use_spot'] = True
         specs.append(spec)
     return chain(f'chain{n_tasks}', specs)
-
-
-def dense_scenario(n_tasks: int = 32) -> Dict[str, Any]:
-    """HBM stress: `n_tasks` CPU-only requests over the default families --
-    the common request, and the one no accelerator summary can prune."""
-    specs = []
-    cpus = [2, 4, 8, 16, 32, 48, 64, 96]
-    mems = [None, '8+', '16+', '32+', '64+', '128+', '256+', '2x', '4x', '8x']
-    for i in range(n_tasks):
-        spec = {'cpus': f'{cpus[i % len(cpus)]}+', 'outputs_gb': 1}
-        mem = mems[(i // len(cpus) + i) % len(mems)]
-        if mem:
-            spec['memory'] = mem
-        if i % 5 == 4:
-            spec['use_spot'] = True
-        specs.append(spec)
-    return chain(f'dense{n_tasks}', specs)
 
 
 # cfg5 (BASELINE.json configs[4]; SURVEY.md section 8d): independent

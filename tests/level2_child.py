@@ -11,6 +11,7 @@ import json
 import os
 import sys
 import tempfile
+import time
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, _REPO)
@@ -42,6 +43,7 @@ def main():
     # the one-line change of INTEGRATION.md, as a monkeypatch
     import sky.catalog as ref_catalog
     calls = {'n': 0}
+    by_method = {}
     original = ref_catalog._map_clouds_catalog  # pylint: disable=protected-access
 
     def dispatch(clouds, method_name, *args, **kwargs):
@@ -53,8 +55,14 @@ def main():
             # own module answers, as it would in a partial swap
             return original(clouds, method_name, *args, **kwargs)
         calls['n'] += 1
-        return skyb.catalog._map_clouds_catalog(  # pylint: disable=protected-access
-            clouds, method_name, *args, **kwargs)
+        t0 = time.perf_counter()
+        try:
+            return skyb.catalog._map_clouds_catalog(  # pylint: disable=protected-access
+                clouds, method_name, *args, **kwargs)
+        finally:
+            spent = by_method.setdefault(method_name, [0, 0.0])
+            spent[0] += 1
+            spent[1] += time.perf_counter() - t0
 
     ref_catalog._map_clouds_catalog = dispatch  # pylint: disable=protected-access
 
@@ -76,7 +84,8 @@ def main():
             ] for c in cands] for cands in rec['candidates']]
         out.append(rec)
     with open(out_path, 'w', encoding='utf-8') as f:
-        json.dump({'records': out, 'catalog_calls': calls['n']}, f)
+        json.dump({'records': out, 'catalog_calls': calls['n'],
+                   'by_method': by_method}, f)
 
 
 if __name__ == '__main__':
