@@ -56,3 +56,11 @@ class AWS(cloud.Cloud):
             return resources_utils.FeasibleResources(
                 [resources.copy(accelerators=None)], [], None)
         return super().get_feasible_launchable_resources(resources, num_nodes)
+
+    def feasible_begin(self, b, resources: Any, num_nodes: int = 1):
+        if resources.instance_type is not None:
+            # the explicit-instance rule above is its own device call
+            answer = self.get_feasible_launchable_resources(resources,
+                                                            num_nodes)
+            return lambda out: answer
+        return super().feasible_begin(b, resources, num_nodes)

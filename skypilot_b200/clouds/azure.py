@@ -90,7 +90,8 @@ class Azure(cloud.Cloud):
     _FAST_TEMPLATE_OK = True
 
     def plan_feasible(self, builder, resources: Any,
-                      want_list: bool = False) -> cloud.SlotPlan:
+                      want_list: bool = False,
+                      want_fuzzy=None) -> cloud.SlotPlan:
         if resources.disk_tier == resources_utils.DiskTier.ULTRA:
             return cloud.SlotPlan()
-        return super().plan_feasible(builder, resources, want_list)
+        return super().plan_feasible(builder, resources, want_list, want_fuzzy)

@@ -331,6 +331,40 @@ class Cloud:
                           fuzzy_cap=self._fuzzy_cap(view), device=view.device)
         return self._feasible_from_scan(view, plan, out, resources)
 
+    def feasible_begin(self, b, resources: Any, num_nodes: int = 1):
+        """get_feasible_launchable_resources in two halves, for many requests
+        in ONE scan: states the request into the shared builder `b` (fuzzy
+        candidates wanted, instance-type lists not) and returns a function of
+        the scan output that gives the FeasibleResources -- cheapest instance
+        type only. Used where only hints, fuzzy candidates and "anything at
+        all?" matter: the error texts of a batch (Optimizer.optimize_batch)."""
+        hint = self._feature_hint(resources, num_nodes)
+        if hint is not None:
+            gated = resources_utils.FeasibleResources([], [], hint)
+            return lambda out: gated
+        view = self._view()
+        plan = self.plan_feasible(b, resources, want_list=False,
+                                  want_fuzzy=True)
+        engine = _late('engine')
+
+        def end(out):
+            if plan.slot is None and plan.list_query is None and (
+                    plan.explicit_instance is None):
+                fuzzy: List[str] = []
+                if (plan.fuzzy_query is not None and
+                        not out.results['any_stage1'][plan.fuzzy_query]):
+                    fuzzy = engine.format_fuzzy(
+                        view.store, out.fuzzy_list(plan.fuzzy_query))
+                return self._nothing_feasible(resources, fuzzy, plan.hint)
+            if plan.explicit_instance is not None:
+                if plan.slot is None:
+                    return self._nothing_feasible(resources, [], plan.hint)
+                return resources_utils.FeasibleResources(
+                    [plan.make(plan.explicit_instance, resources)], [], None)
+            return self._feasible_from_scan(view, plan, out, resources)
+
+        return end
+
     @staticmethod
     def _fuzzy_cap(view) -> int:
         return min(max(len(view.store.acc_keys), 1), 2048)
@@ -581,7 +615,8 @@ class Cloud:
         return plan, rec
 
     def plan_feasible(self, builder, resources: Any,
-                      want_list: bool = False) -> SlotPlan:
+                      want_list: bool = False,
+                      want_fuzzy: Optional[bool] = None) -> SlotPlan:
         """States `resources` against this cloud for the device: the template
         shared by AWS, Azure, Lambda and the other single-table clouds
         (aws.py:881-953, azure.py:485-557, lambda_cloud.py:217-280)."""
@@ -677,7 +712,8 @@ class Cloud:
             resources.zone if rules.acc_query_region else None,
             resources.max_hourly_cost, local_disk=local_disk,
             flags_require2=_native.F_PREMIUM_DISK if premium else 0,
-            want_list=want_list, want_fuzzy=want_list)
+            want_list=want_list,
+            want_fuzzy=want_list if want_fuzzy is None else want_fuzzy)
         q = builder.add_query(spec)
         plan.list_query = q
         plan.fuzzy_query = q
@@ -713,7 +749,11 @@ class DummyCloud(Cloud):
 
 
 def cloud_in_iterable(cloud: Cloud, cloud_list: Iterable[Cloud]) -> bool:
-    return any(cloud.is_same_cloud(c) for c in cloud_list)
+    cls = cloud.__class__
+    for c in cloud_list:
+        if c.__class__ is cls or cloud.is_same_cloud(c):
+            return True
+    return False
 
 
 def region_allow_words(table, resources: Any, cloud_obj: Any):

@@ -218,7 +218,10 @@ class GCP(cloud.Cloud):
         return plan, rec
 
     def plan_feasible(self, builder, resources: Any,
-                      want_list: bool = False) -> cloud.SlotPlan:
+                      want_list: bool = False,
+                      want_fuzzy=None) -> cloud.SlotPlan:
+        if want_fuzzy is None:
+            want_fuzzy = want_list
         engine = cloud._late('engine')  # pylint: disable=protected-access
         view = self._view()
         table = view.table
@@ -283,7 +286,7 @@ class GCP(cloud.Cloud):
                 'gcp', acc, acc_count, None if tpu_vm else resources.cpus,
                 None if tpu_vm else resources.memory, use_spot,
                 resources.region, resources.zone, resources.max_hourly_cost,
-                want_list=False, want_fuzzy=want_list))
+                want_list=False, want_fuzzy=want_fuzzy))
         plan.gate_query = gate
         plan.fuzzy_query = gate
         acc_dict = {acc: acc_count}

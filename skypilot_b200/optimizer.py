@@ -302,6 +302,7 @@ class Optimizer:
             if e is not None:
                 raise e
         out: List[Any] = [None] * len(dags)
+        failed: List[Tuple[int, task_lib.Task]] = []
         for k, shard in enumerate(shards):
             sol = solutions[k]
             for d, i in enumerate(shard):
@@ -309,8 +310,11 @@ class Optimizer:
                 res = sol.dag[d]
                 try:
                     if res['status'] == 1:
-                        Optimizer._raise_unavailable(
-                            problem.tasks[int(res['task_fail'])], blocked)
+                        task = problem.tasks[int(res['task_fail'])]
+                        if return_exceptions:
+                            failed.append((i, task))  # worded below, together
+                            continue
+                        Optimizer._raise_unavailable(task, blocked)
                     if res['status'] != 0:
                         # beyond the device enumeration: the single-DAG path
                         # solves it by elimination on the host
@@ -326,6 +330,10 @@ class Optimizer:
                     if not return_exceptions:
                         raise
                     out[i] = e
+        if failed:
+            errors = Optimizer._unavailable_errors([t for _, t in failed])
+            for (i, _), e in zip(failed, errors):
+                out[i] = e
         return out
 
     # -------------------------------------------------------------- job groups
@@ -885,6 +893,11 @@ class Optimizer:
         """Builds the reference's error text (sky/optimizer.py:368-425)."""
         _, _, fuzzy, resource_hints = _fill_in_launchable_resources(
             task, blocked, quiet=True)
+        raise Optimizer._unavailable_error(task, fuzzy, resource_hints)
+
+    @staticmethod
+    def _unavailable_error(task, fuzzy, resource_hints
+                          ) -> exceptions.ResourcesUnavailableError:
         fuzzy_str = ''
         if fuzzy:
             fuzzy_str = f'\nTry one of these offered accelerators: {fuzzy}'
@@ -899,12 +912,60 @@ class Optimizer:
             f'{indent}{line}' for line in hints_concat.split('\n'))
         hints_str = (f'Hint: Check Per Resource Hint\n{hints_fmt}'
                      if hints_fmt else '')
-        raise exceptions.ResourcesUnavailableError(
+        return exceptions.ResourcesUnavailableError(
             'Catalog does not contain any instances satisfying the request: '
             f'{reprs}.\nTo fix: relax or change the resource requirements.'
             f'{fuzzy_str}\n\nHint: sky gpus list to list available '
             f'accelerators.\n{indent}sky check to check the enabled clouds.\n'
             f'{hints_str}')
+
+    @staticmethod
+    def _unavailable_errors(tasks: List[task_lib.Task]
+                           ) -> List[exceptions.ResourcesUnavailableError]:
+        """The errors of many infeasible tasks from ONE device scan: every
+        (request, cloud) of every task is stated into one batch with fuzzy
+        candidates wanted (Cloud.feasible_begin); hints and fuzzy lists are
+        collected exactly like `_fill_in_launchable_resources` does for one
+        task. A batch with thousands of infeasible DAGs used to pay one
+        scan per (task, cloud) just to word its errors."""
+        enabled = sky_check.get_cached_enabled_clouds_or_refresh(
+            raise_if_no_cloud_access=True)
+        store = catalog.get_store()
+        b = engine.ProblemBuilder(store)
+        pending = []
+        for task in tasks:
+            per_task = []
+            for resources in task.resources:
+                resources.validate()
+                if (resources.cloud is not None and
+                        not clouds.cloud_in_iterable(resources.cloud,
+                                                     enabled)):
+                    continue
+                clouds_list = ([resources.cloud]
+                               if resources.cloud is not None else enabled)
+                for cloud in clouds_list:
+                    per_task.append(
+                        (resources,
+                         cloud.feasible_begin(b, resources, task.num_nodes)))
+            pending.append(per_task)
+        out = None
+        if b.n_queries:
+            out = engine.scan(b, fuzzy_cap=min(max(len(store.acc_keys), 1),
+                                               2048),
+                              device=catalog.get_device())
+        errors = []
+        for task, per_task in zip(tasks, pending):
+            all_fuzzy = set()
+            hints: Dict[Any, List[str]] = collections.defaultdict(list)
+            for resources, end in per_task:
+                feasible = end(out)
+                if feasible.hint is not None:
+                    hints[resources].append(feasible.hint)
+                if not feasible.resources_list:
+                    all_fuzzy.update(feasible.fuzzy_candidate_list)
+            errors.append(
+                Optimizer._unavailable_error(task, sorted(all_fuzzy), hints))
+        return errors
 
     @staticmethod
     def _compute_total_time(graph, topo_order, plan) -> float:

@@ -258,20 +258,23 @@ def test_optimize_batch_matches_one_by_one():
             sky.optimize(dag, quiet=True)
             r = t.best_resources
             want.append((str(r.cloud), r.instance_type, r.region, r.zone))
-        except sky.exceptions.ResourcesUnavailableError:
-            want.append(None)
+        except sky.exceptions.ResourcesUnavailableError as e:
+            want.append(('unavailable', str(e)))
         t.best_resources = None
     devices = list(range(_native.device_count()))
     out = sky.optimize_batch(dags, devices=devices, return_exceptions=True)
     got = []
     for o, t in zip(out, tasks):
         if isinstance(o, Exception):
-            got.append(None)
+            # worded from one scan for the whole batch: same text as the
+            # one-DAG path (hints, fuzzy candidates)
+            got.append(('unavailable', str(o)))
         else:
             r = t.best_resources
             got.append((str(r.cloud), r.instance_type, r.region, r.zone))
     assert got == want
-    assert any(w is None for w in want) and any(w is not None for w in want)
+    assert any(w[0] == 'unavailable' for w in want)
+    assert any(w[0] != 'unavailable' for w in want)
     with pytest.raises(sky.exceptions.ResourcesUnavailableError):
         sky.optimize_batch(dags, devices=devices)
 
