@@ -201,7 +201,9 @@ struct ScanShared {
   ScanQuery q[kQChunk];
   uint64_t wkey[kQChunk][kScanWarps];
   uint32_t wrow[kQChunk][kScanWarps];
-  uint64_t gb[kQChunk];   // best price key any block has found so far
+  // best price key found so far, one copy per warp: a warp reads and tightens
+  // its own (any achieved key is a valid bound; no cross-warp hand-off)
+  uint64_t gb[kQChunk][kScanWarps];
   uint32_t sany[kQChunk];
   uint32_t wact[kScanWarps];  // per-warp masks of surviving queries
 };
@@ -304,7 +306,9 @@ __device__ __forceinline__ void stage_queries(const ScanArgs &a, const ScanGroup
   if (tid < nq) {
     S.sany[tid] = 0;
     // Running best of the whole grid (pruning bound); stale values are fine.
-    S.gb[tid] = *reinterpret_cast<volatile unsigned long long *>(a.gbest + G.q_begin + tid);
+    const uint64_t g0 = *reinterpret_cast<volatile unsigned long long *>(a.gbest + G.q_begin + tid);
+#pragma unroll
+    for (int w = 0; w < kScanWarps; ++w) S.gb[tid][w] = g0;
   }
   __syncthreads();
 }
@@ -336,7 +340,7 @@ __device__ __forceinline__ uint32_t active_queries(const ScanShared &S, int nq,
            (!(L.qflags & SKYOPT_Q_ACC) ||
             (((L.sig_lo & z.sg_lo) | (L.sig_hi & z.sg_hi)) != 0u));
     const bool prunable = !(L.qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY));
-    if (prunable && z.wmin[L.price_col ? 1 : 0] > S.gb[lane]) pass = false;
+    if (prunable && z.wmin[L.price_col ? 1 : 0] > S.gb[lane][threadIdx.x >> 5]) pass = false;
   }
   return __ballot_sync(0xFFFFFFFFu, pass);
 }
@@ -495,7 +499,7 @@ __device__ __forceinline__ void score_rows(
         }
       }
       // cannot beat (or tie) what the grid already has: no reduction needed
-      if (bkey > S.gb[q]) brow = kRowNone;
+      if (bkey > S.gb[q][threadIdx.x >> 5]) brow = kRowNone;
     }
     if (mf) {
       // Fuzzy table: min 'Price' per accelerator key (common.py:661-667).
@@ -529,6 +533,7 @@ __device__ __forceinline__ void score_rows(
         const uint32_t kr = (khi32 == mhi32 && klo32 == mlo32) ? brow : kRowNone;
         mr = __reduce_min_sync(0xFFFFFFFFu, kr);
       }
+      __syncwarp();  // every lane has read the warp's bound for this query
       if (lane == 0) {
         const uint64_t k = ((uint64_t)mhi32 << 32) | mlo32;
         const uint64_t ok_ = S.wkey[q][warp];
@@ -536,13 +541,14 @@ __device__ __forceinline__ void score_rows(
           S.wkey[q][warp] = k;
           S.wrow[q][warp] = mr;
         }
-        if (k < S.gb[q]) {
-          // publish the bound (any achieved key is a valid bound, so the
-          // unsynchronised shared copy is harmless)
-          S.gb[q] = k;
+        if (k < S.gb[q][warp]) {
+          // tighten this warp's bound and the grid's (any achieved key is
+          // a valid bound)
+          S.gb[q][warp] = k;
           atomicMin(a.gbest + G.q_begin + q, (unsigned long long)k);
         }
       }
+      __syncwarp();  // ... and sees the tightened one from here on
     }
   }
 }
@@ -655,7 +661,11 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_kernel(Sc
       S.wkey[i / kScanWarps][i % kScanWarps] = kKeyNone;
       S.wrow[i / kScanWarps][i % kScanWarps] = kRowNone;
     }
-    if (tid < nq) { S.sany[tid] = 0; S.gb[tid] = gb; }
+    if (tid < nq) {
+      S.sany[tid] = 0;
+#pragma unroll
+      for (int w = 0; w < kScanWarps; ++w) S.gb[tid][w] = gb;
+    }
   }
   __syncthreads();
   mark(a, 1);
@@ -770,7 +780,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_queue_ker
     if (lane < nq) {
       const QueryS &L = S.q[lane].s;
       req = L.req_flags; grp = L.grp_bit; sg_lo = L.sig_lo; sg_hi = L.sig_hi;
-      qf = L.qflags; col = L.price_col ? 1u : 0u; gb = S.gb[lane];
+      qf = L.qflags; col = L.price_col ? 1u : 0u; gb = S.gb[lane][threadIdx.x >> 5];
     }
     const bool bounded = !(qf & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY));
     int pairs = 0;
@@ -826,7 +836,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_queue_ker
         const QueryS &L = S.q[lane].s;
         const uint4 z1 = Q.z1[ch];
         const uint64_t wmin = L.price_col ? (((uint64_t)z1.w << 32) | z1.z) : (((uint64_t)z1.y << 32) | z1.x);
-        drop = !(L.qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY)) && wmin > S.gb[lane];
+        drop = !(L.qflags & (SKYOPT_Q_LIST | SKYOPT_Q_FUZZY)) && wmin > S.gb[lane][threadIdx.x >> 5];
       }
       active &= ~__ballot_sync(0xFFFFFFFFu, drop);
     }
