@@ -186,6 +186,34 @@ class ReferenceArm:
         bootstrap.write_catalogs(self._home.name, frames)
         with stdout_to_stderr():
             self.sky = bootstrap.import_reference(self._home.name, enabled)
+        self.phase_s = {}
+        self._wrap_phases()
+
+    def _wrap_phases(self):
+        """Per-phase split of the reference's optimize:
+        seconds inside `_fill_in_launchable_resources`, `Resources.get_cost`
+        and `_optimize_by_dp`, accumulated by thin wrappers (a perf_counter
+        pair per call; the functions are millisecond-scale)."""
+        from sky import optimizer as opt_lib  # pylint: disable=import-outside-toplevel
+        from sky import resources as res_lib  # pylint: disable=import-outside-toplevel
+        acc = self.phase_s
+
+        def timed(fn, label):
+            def inner(*a, **k):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    acc[label] = acc.get(label, 0.0) + time.perf_counter() - t
+            return inner
+
+        opt_lib._fill_in_launchable_resources = timed(  # pylint: disable=protected-access
+            opt_lib._fill_in_launchable_resources,  # pylint: disable=protected-access
+            'fill_in_launchable_resources')
+        res_lib.Resources.get_cost = timed(res_lib.Resources.get_cost,
+                                           'get_cost')
+        opt_lib.Optimizer._optimize_by_dp = staticmethod(timed(  # pylint: disable=protected-access
+            opt_lib.Optimizer._optimize_by_dp, 'optimize_by_dp'))  # pylint: disable=protected-access
 
     def optimize_seconds(self, scenario):
         """One cold `Optimizer.optimize(dag, quiet=True)` (request cache
@@ -239,6 +267,9 @@ def run_reference_arm(args, spec, scenario, workload_name, budget_s):
     for _ in range(args.warmup):
         run(sample)
     times, plan = [], None
+    phases = getattr(arm, 'phase_s', None) if kind == 'reference' else None
+    if phases is not None:
+        phases.clear()
     for _ in range(args.steps):
         dt, plan = run(sample)
         times.append(dt)
@@ -257,6 +288,9 @@ def run_reference_arm(args, spec, scenario, workload_name, budget_s):
                        f'per step, {args.steps} steps, full catalog '
                        f'({n_rows} rows), request cache cleared every call'),
             'ms_per_step': ms,
+            'phases_ms_per_step': ({k: 1e3 * v / len(times)
+                                    for k, v in phases.items()}
+                                   if phases else None),
         },
         'plan': plan, 'sample_tasks': m,
     }
