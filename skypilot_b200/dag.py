@@ -62,13 +62,18 @@ class Dag:
     def is_chain(self) -> bool:
         """True iff the tasks form one linear chain: every node has at most
         one parent / child and exactly one node has none."""
-        nodes = list(self.graph.nodes)
-        if not nodes:
+        succ, pred = self.graph._succ, self.graph._pred  # pylint: disable=protected-access
+        if not succ:
             return True
-        indeg = [self.graph.in_degree(n) for n in nodes]
-        outdeg = [self.graph.out_degree(n) for n in nodes]
-        return (max(outdeg) <= 1 and outdeg.count(0) == 1 and
-                max(indeg) <= 1 and indeg.count(0) == 1)
+        # (the adjacency dicts directly: a degree view per node is most of
+        # what this costs on a small DAG)
+        roots = leaves = 0
+        for n, out in succ.items():
+            if len(out) > 1 or len(pred[n]) > 1:
+                return False
+            leaves += not out
+            roots += not pred[n]
+        return roots == 1 and leaves == 1
 
 
 class _DagContext(threading.local):

@@ -25,6 +25,12 @@ NO_MATCH_ID = 65534  # a region / zone id no row carries
 _INF = float('inf')
 
 
+def _addr(arr: np.ndarray) -> int:
+    """Address of a numpy buffer. (`__array_interface__` is no shortcut: for
+    a structured dtype it rebuilds the field description on every access.)"""
+    return arr.ctypes.data
+
+
 @functools.lru_cache(maxsize=4096)
 def parse_cpus(cpus: Optional[str]) -> Tuple[int, float]:
     """'8' -> (EQ, 8.0), '8+' -> (GE, 8.0) (sky/catalog/common.py:431-452)."""
@@ -538,21 +544,21 @@ class PackedProblem:
 
     def c_problem(self) -> _native.Problem:
         p = _native.Problem()
-        p.queries = self.queries.ctypes.data
+        p.queries = _addr(self.queries)
         p.n_queries = self.n_queries
-        p.acc_sets = self.acc_sets.ctypes.data
+        p.acc_sets = _addr(self.acc_sets)
         p.n_acc_sets = self.n_sets
-        p.slots = self.slots.ctypes.data
+        p.slots = _addr(self.slots)
         p.n_slots = self.n_slots
-        p.tasks = self.tasks.ctypes.data
+        p.tasks = _addr(self.tasks)
         p.n_tasks = self.n_tasks
-        p.parents = self.parents.ctypes.data
+        p.parents = _addr(self.parents)
         p.n_parents = self.n_parents
-        p.tariffs = self.tariffs.ctypes.data
+        p.tariffs = _addr(self.tariffs)
         p.n_tariffs = self.n_tariffs
-        p.blocked = self.blocked.ctypes.data
+        p.blocked = _addr(self.blocked)
         p.n_blocked = self.n_blocked
-        p.dags = self.dags.ctypes.data
+        p.dags = _addr(self.dags)
         p.n_dags = self.n_dags
         return p
 
@@ -594,17 +600,17 @@ class Solution:
 
     def c_solution(self) -> _native.Solution:
         s = _native.Solution()
-        s.scan = None if self.scan is None else self.scan.ctypes.data
-        s.slot_count = self.slot_count.ctypes.data
-        s.slot_inst = self.slot_inst.ctypes.data
-        s.chosen = self.chosen.ctypes.data
-        s.chosen_index = self.chosen_index.ctypes.data
-        s.task_n_candidates = self.task_n.ctypes.data
-        s.dag = self.dag.ctypes.data
+        s.scan = None if self.scan is None else _addr(self.scan)
+        s.slot_count = _addr(self.slot_count)
+        s.slot_inst = _addr(self.slot_inst)
+        s.chosen = _addr(self.chosen)
+        s.chosen_index = _addr(self.chosen_index)
+        s.task_n_candidates = _addr(self.task_n)
+        s.dag = _addr(self.dag)
         if self.tables is not None:
-            s.candidates = self.tables.ctypes.data
+            s.candidates = _addr(self.tables)
             s.cand_cap = len(self.tables)
-            s.task_cand_offset = self.table_offsets.ctypes.data
+            s.task_cand_offset = _addr(self.table_offsets)
         else:
             s.candidates = None
             s.cand_cap = 0
@@ -690,7 +696,7 @@ class Session:
         csol = sol.c_solution()
         _native.check(
             self._lib.skyopt_session_resolve(
-                self._handle, rows.ctypes.data if len(blocked) else None,
+                self._handle, _addr(rows) if len(blocked) else None,
                 len(blocked), ctypes.byref(csol), ctypes.byref(sol.stats)))
         self.solution = sol
         return sol
@@ -722,7 +728,7 @@ def solve_timed(builder: ProblemBuilder, iters: int, flush_l2: bool = True,
     _native.check(
         lib.skyopt_optimize_timed(handle, ctypes.byref(prob),
                                   ctypes.byref(csol), iters, int(flush_l2),
-                                  iter_ms.ctypes.data, scan_ms.ctypes.data,
+                                  _addr(iter_ms), _addr(scan_ms),
                                   ctypes.byref(sol.stats)))
     return sol, iter_ms, scan_ms
 
@@ -767,9 +773,9 @@ def scan(builder: ProblemBuilder,
         fuzzy_prices = np.full((n, fuzzy_cap), math.nan, dtype=np.float64)
     stats = _native.Stats()
     _native.check(
-        lib.skyopt_scan(handle, packed.queries.ctypes.data, n,
-                        packed.acc_sets.ctypes.data, packed.n_sets,
-                        results.ctypes.data, _native.ptr(list_ids),
+        lib.skyopt_scan(handle, _addr(packed.queries), n,
+                        _addr(packed.acc_sets), packed.n_sets,
+                        _addr(results), _native.ptr(list_ids),
                         _native.ptr(list_prices), list_cap,
                         _native.ptr(fuzzy_keys), _native.ptr(fuzzy_prices),
                         fuzzy_cap, ctypes.byref(stats)))
@@ -823,12 +829,12 @@ def solve_tables(store: CatalogStore, values: Sequence[Sequence[float]],
     results = np.zeros(1, dtype=_native.DAG_RESULT_DTYPE)
     lib = _native.load()
     _native.check(
-        lib.skyopt_solve_tables(store.handle(device), flat_v.ctypes.data,
-                                flat_c.ctypes.data, offsets.ctypes.data,
-                                tasks.ctypes.data, n_tasks,
-                                par_a.ctypes.data, len(par),
-                                tar_a.ctypes.data, len(tar),
-                                dags.ctypes.data, 1, chosen.ctypes.data,
-                                results.ctypes.data))
+        lib.skyopt_solve_tables(store.handle(device), _addr(flat_v),
+                                _addr(flat_c), _addr(offsets),
+                                _addr(tasks), n_tasks,
+                                _addr(par_a), len(par),
+                                _addr(tar_a), len(tar),
+                                _addr(dags), 1, _addr(chosen),
+                                _addr(results)))
     return ([int(i) for i in chosen], float(results['objective'][0]),
             int(results['status'][0]))
