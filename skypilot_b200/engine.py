@@ -428,22 +428,29 @@ class ProblemBuilder:
                  edge_tariffs: Sequence[Sequence[float]] = (),
                  src_tariff: Optional[Sequence[float]] = None) -> int:
         n_clouds = len(self.store.clouds)
-        task = {
-            'slot_begin': slot_begin, 'slot_end': slot_end,
-            'n_parents': len(parents), 'parent_begin': len(self.parents),
-            'edge_tariff_begin': len(self.tariffs), 'src_tariff_begin': -1
-        }
-        self.parents.extend(int(p) for p in parents)
-        assert len(edge_tariffs) == len(parents)
+        n_parents = len(parents)
+        parent_begin = len(self.parents)
+        edge_begin = len(self.tariffs)
+        src_begin = -1
+        # (parents are ints and tariff rows lists of floats already: the
+        # callers build them; no per-element conversion here)
+        self.parents.extend(parents)
+        assert len(edge_tariffs) == n_parents
+        tariffs = self.tariffs
         for row in edge_tariffs:
             assert len(row) == n_clouds
-            self.tariffs.extend(float(v) for v in row)
+            tariffs.extend(row)
         if src_tariff is not None:
             assert len(src_tariff) == n_clouds
-            task['src_tariff_begin'] = len(self.tariffs)
-            self.tariffs.extend(float(v) for v in src_tariff)
-        self.tasks.append(task)
-        self.task_recs.append(_TASK_PACK(*_TASK_FIELDS(task)))
+            src_begin = len(tariffs)
+            tariffs.extend(src_tariff)
+        self.tasks.append({
+            'slot_begin': slot_begin, 'slot_end': slot_end,
+            'n_parents': n_parents, 'parent_begin': parent_begin,
+            'edge_tariff_begin': edge_begin, 'src_tariff_begin': src_begin
+        })
+        self.task_recs.append(_TASK_PACK(slot_begin, slot_end, n_parents,
+                                         parent_begin, edge_begin, src_begin))
         return len(self.tasks) - 1
 
     def set_task_field(self, i: int, name: str, value: int) -> None:
